@@ -1,0 +1,205 @@
+/*
+ * sgc_b200.h -- C-ABI of libsgc_b200.so: the B200 (sm_100a) implementation of
+ * spacegraphcats' k-mer -> cDBG-unitig indexing hot path.
+ *
+ * This is the drop-in boundary.  The reference has no native code of its own on
+ * this path; it binds two third-party natives (khmer, bbhash_table) from Python at
+ * spacegraphcats/cdbg/hashing.py:7-8.  Each entry point below names the reference
+ * interface it replaces.  Paths are relative to the reference checkout.
+ *
+ * Conventions
+ *   - plain C types only; every pointer named d_* is DEVICE memory on the context's
+ *     GPU, every h_* is HOST memory; sizes are explicit; buffers are caller-owned.
+ *   - every function returns 0 on success or a negative sgc_status; it never throws
+ *     and there is no CPU fallback: without a usable CUDA device sgc_ctx_create
+ *     fails with SGC_ERR_CUDA.  sgc_last_error() gives the message (thread-local).
+ *   - work is enqueued on the context's CUDA stream.  Functions with host out
+ *     parameters (h_*) synchronise that stream before returning; the others are
+ *     asynchronous.
+ *   - sequences are passed as one concatenated ASCII buffer d_seq[seq_bytes] plus
+ *     int64 offsets d_off[nseq+1] (sequence s = d_seq[d_off[s] .. d_off[s+1])).
+ *     A sequence shorter than k contributes no k-mers (callers of the reference
+ *     guard this case: cdbg/index_reads.py:143, search/query_by_sequence.py:174).
+ *   - unitig ids are uint32; SGC_MISS (0xFFFFFFFF, the reference's UNSET_VALUE,
+ *     cdbg/index_cdbg_by_kmer.py:24) means "hash not in the table" (Python None).
+ */
+#ifndef SGC_B200_H
+#define SGC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGC_MISS 0xFFFFFFFFu
+#define SGC_MAX_ID 0xFFFFFFFDu /* 0xFFFFFFFE marks a dropped (multicount) hash internally */
+#define SGC_MAX_K 255          /* khmer WordLength is a byte */
+
+typedef enum {
+    SGC_OK = 0,
+    SGC_ERR_CUDA = -1,      /* CUDA runtime error (message in sgc_last_error) */
+    SGC_ERR_ARG = -2,       /* bad argument */
+    SGC_ERR_CAPACITY = -3,  /* an output buffer or the table is too small */
+    SGC_ERR_NOMEM = -4
+} sgc_status;
+
+typedef struct sgc_ctx sgc_ctx;     /* one GPU + one stream + scratch memory */
+typedef struct sgc_table sgc_table; /* GPU-resident exact map u64 hash -> u32 unitig id */
+
+const char* sgc_last_error(void);
+int sgc_abi_version(void);
+
+/* device = CUDA ordinal; stream = an existing cudaStream_t to adopt, or NULL to create one. */
+int sgc_ctx_create(int device, void* stream, sgc_ctx** out);
+void sgc_ctx_destroy(sgc_ctx* ctx);
+int sgc_ctx_sync(sgc_ctx* ctx);
+void* sgc_ctx_stream(sgc_ctx* ctx);
+/* number of kernels of this library launched through ctx so far (bench.py gpu_launches) */
+int64_t sgc_ctx_launches(const sgc_ctx* ctx);
+
+/*
+ * K1 -- replaces khmer.Nodetable(k,1,1).get_kmer_hashes(seq) as called by
+ * hash_sequence(), cdbg/hashing.py:14-20, batched over nseq sequences.
+ * Writes d_kmer_off[nseq+1] (exclusive scan of max(0, L-k+1)) and the hashes of
+ * sequence s at d_hash_out[d_kmer_off[s] ..], in k-mer position order.
+ * d_status (nullable, nseq int32): bit 0 set when the sequence contains a byte other
+ * than A/C/G/T (khmer raises on those; the caller decides).  hash_cap = capacity of
+ * d_hash_out in k-mers (SGC_ERR_CAPACITY when short; nothing is written then).
+ * h_total_kmers (nullable): total k-mers; passing it synchronises.
+ */
+int sgc_hash_batch(sgc_ctx* ctx, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off,
+                   int64_t nseq, int k, uint64_t* d_hash_out, int64_t hash_cap,
+                   int64_t* d_kmer_off, int32_t* d_status, int64_t* h_total_kmers);
+
+/*
+ * K2 -- replaces BBHashTable() + .initialize(list(all_kmers)) + table[kmer] = cdbg_id,
+ * i.e. build_mphf(), cdbg/index_cdbg_by_kmer.py:27-115.
+ * sgc_table_create sizes an empty table for up to max_entries distinct hashes.
+ * Insertion semantics are build_mphf's: a hash inserted with two DIFFERENT ids is
+ * dropped from the map for good (multicount, :40-57); the same (hash, id) again is a no-op.
+ */
+int sgc_table_create(sgc_ctx* ctx, int64_t max_entries, sgc_table** out);
+void sgc_table_free(sgc_table* t);
+/* insert n (hash, id) pairs; also how a reference-written contigs.indices
+ * (mphf_to_hash, mphf_to_value; BBHashTable.load, cdbg/hashing.py:126) is loaded. */
+int sgc_table_insert_pairs(sgc_table* t, const uint64_t* d_hash, const uint32_t* d_id, int64_t n);
+/* fused K1+K2: hash every k-mer of every sequence and insert it with the sequence's id
+ * (d_ids[s], or id_base + s when d_ids is NULL).  Both passes of build_mphf in one. */
+int sgc_table_insert_sequences(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes,
+                               const int64_t* d_off, int64_t nseq, int k, const uint32_t* d_ids,
+                               uint32_t id_base, int32_t* d_status);
+/* live = hashes in the map (len(table), cdbg/hashing.py:33-34); multi = dropped hashes;
+ * max_id = max stored id (index_cdbg_by_kmer.py:106).  Synchronises. */
+int sgc_table_stats(sgc_table* t, int64_t* h_live, int64_t* h_multi, uint32_t* h_max_id);
+/* all live (hash, id) pairs, sorted by hash -- what BBHashTable.save writes to
+ * contigs.indices (cdbg/hashing.py:115), up to order.  cap in pairs.  Synchronises. */
+int sgc_table_export(sgc_table* t, uint64_t* d_hash_out, uint32_t* d_id_out, int64_t cap,
+                     int64_t* h_n_out);
+int64_t sgc_table_bytes(const sgc_table* t);
+/* hash-range partitioned tables: the top `shift` bits of every hash stored here are the owner
+ * rank and therefore constant; skip them when choosing the home bucket.  Call before inserting. */
+int sgc_table_set_home_shift(sgc_table* t, int shift);
+
+/*
+ * K3 -- replaces BBHashTable.__getitem__ (kmer_idx.get_cdbg_id, cdbg/hashing.py:36-37)
+ * over an array: d_id_out[i] = id or SGC_MISS.
+ */
+int sgc_lookup(sgc_table* t, const uint64_t* d_hash, int64_t n, uint32_t* d_id_out);
+
+/*
+ * K5 -- replaces BBHashTable.get_unique_values(hashes) = MPHF_KmerIndex.count_cdbg_matches,
+ * cdbg/hashing.py:67-69: d_count_by_id[id] += 1 for every input hash present (duplicates
+ * counted, exactly like iterating a list).  distinct != 0 first de-duplicates the hashes
+ * (the set() that Query builds at search/query_by_sequence.py:170-176).
+ * d_count_by_id must hold n_ids uint32 and is zeroed here.  h_n_miss nullable.
+ */
+int sgc_count_matches(sgc_table* t, const uint64_t* d_hash, int64_t n, int distinct,
+                      uint32_t* d_count_by_id, int64_t n_ids, int64_t* h_n_miss,
+                      int64_t* h_n_distinct);
+
+/*
+ * Fused K1+K3+K5 -- per-k-mer get_cdbg_id with no de-duplication, the loop of
+ * search/count_dominator_abundance.py:80-85.  d_kmer_ids (nullable) receives the
+ * unitig id or SGC_MISS of every k-mer (laid out by d_kmer_off like sgc_hash_batch);
+ * d_count_by_id (nullable, n_ids, zeroed here) the per-unitig totals.
+ */
+int sgc_lookup_sequences(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes,
+                         const int64_t* d_off, int64_t nseq, int k, uint32_t* d_kmer_ids,
+                         int64_t ids_cap, int64_t* d_kmer_off, uint32_t* d_count_by_id,
+                         int64_t n_ids, int32_t* d_status, int64_t* h_n_kmers, int64_t* h_n_hits);
+
+/*
+ * Fused K1+K3+K4 -- the per-read step of index_reads, cdbg/index_reads.py:143-152:
+ * for every sequence the DISTINCT unitig ids its k-mers hit, ascending, as CSR:
+ * d_ids_off[nseq+1], d_ids_out[ids_cap].  Returns SGC_ERR_CAPACITY (with
+ * *h_n_labels = needed size) when ids_cap is short.  Synchronises.
+ */
+int sgc_label_reads(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off,
+                    int64_t nseq, int k, int64_t* d_ids_off, uint32_t* d_ids_out, int64_t ids_cap,
+                    int32_t* d_status, int64_t* h_n_kmers, int64_t* h_n_hits, int64_t* h_n_labels);
+/* asynchronous two-step form of the same (for pipelined callers): _launch enqueues the
+ * work, _finish synchronises and reports; the outputs are valid after _finish. */
+int sgc_label_reads_launch(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes,
+                           const int64_t* d_off, int64_t nseq, int k, int64_t* d_ids_off,
+                           uint32_t* d_ids_out, int64_t ids_cap, int32_t* d_status);
+int sgc_label_reads_finish(sgc_table* t, int64_t* h_n_kmers, int64_t* h_n_hits,
+                           int64_t* h_n_labels);
+
+/*
+ * K6 -- replaces MPHF_KmerIndex.count_catlas_matches / build_catlas_node_sizes,
+ * cdbg/hashing.py:71-107 and :42-65: sums over the catlas.  The catlas is given as CSR
+ * in child-before-parent level order (search/catlas.py:142-154):
+ *   level-1 node v : d_node_count[v] = sum of d_count_by_id[c] for c in d_member[d_member_off[v] ..)
+ *                    (members are unitig ids: catlas.layer1_to_cdbg)
+ *   level>1 node v : sum of d_node_count[c] over its children (members are node ids)
+ * Nodes are processed level by level: d_level_nodes[d_level_off[l] .. d_level_off[l+1]) are the
+ * node ids of level l+1 (h_level_off is a HOST array of n_levels+1 offsets).
+ */
+int sgc_count_doms(sgc_ctx* ctx, const uint32_t* d_count_by_id, const int64_t* d_member_off,
+                   const uint32_t* d_member, const uint32_t* d_level_nodes,
+                   const int64_t* h_level_off, int n_levels, uint32_t* d_node_count,
+                   int64_t n_nodes);
+
+/*
+ * K7 -- hash-range partitioned table across R GPUs (owner(hash) = (hash * R) >> 64).
+ * sgc_hash_partition hashes every k-mer and writes it into the bucket of its owner rank:
+ * d_bucketed[d_bucket_off[r] ..) holds rank r's hashes; d_perm[j] = original k-mer index of
+ * bucketed element j (to un-permute the replies).  d_bucket_off has R+1 int64 (device);
+ * h_bucket_off (nullable, host, R+1) receives a copy and synchronises.  The exchange itself
+ * is an NCCL all-to-all issued by the host layer on the same stream.
+ */
+int sgc_hash_partition(sgc_ctx* ctx, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off,
+                       int64_t nseq, int k, int n_ranks, uint64_t* d_bucketed, int64_t* d_perm,
+                       int64_t cap, int64_t* d_bucket_off, int64_t* d_kmer_off, int32_t* d_status,
+                       int64_t* h_bucket_off);
+/* bucket precomputed (hash[, id]) pairs by owner rank (partitioned table build) */
+int sgc_partition_pairs(sgc_ctx* ctx, const uint64_t* d_hash, const uint32_t* d_id, int64_t n,
+                        int n_ranks, uint64_t* d_hash_out, uint32_t* d_id_out, int64_t* d_perm,
+                        int64_t* d_bucket_off, int64_t* h_bucket_off);
+/* K4 on gathered per-k-mer ids: d_kmer_ids[n_kmers] laid out by d_kmer_off[nseq+1] ->
+ * CSR of distinct ids per sequence (same outputs as sgc_label_reads).  Synchronises. */
+int sgc_labels_from_ids(sgc_ctx* ctx, const uint32_t* d_kmer_ids, const int64_t* d_kmer_off,
+                        int64_t nseq, int64_t n_kmers, int64_t* d_ids_off, uint32_t* d_ids_out,
+                        int64_t ids_cap, int64_t* h_n_hits, int64_t* h_n_labels);
+/* d_out[d_perm[j]] = d_in[j] */
+int sgc_unpermute_u32(sgc_ctx* ctx, const uint32_t* d_in, const int64_t* d_perm, int64_t n,
+                      uint32_t* d_out);
+
+/*
+ * Bench / test utilities (no reference counterpart): CUDA-event timing of the tile kernel on the
+ * context's stream, and on-device generators for the synthetic workloads of SURVEY.md 8(d).
+ */
+int sgc_ctx_set_timing(sgc_ctx* ctx, int on);
+/* synchronises; total milliseconds and number of tile-kernel launches since the last call */
+int sgc_ctx_tile_ms(sgc_ctx* ctx, double* h_ms_total, int64_t* h_n);
+int sgc_synth_genome(sgc_ctx* ctx, uint8_t* d_out, int64_t n, uint64_t seed);
+int sgc_synth_reads(sgc_ctx* ctx, const uint8_t* d_genome, int64_t glen, int64_t nreads, int read_len,
+                    uint64_t seed, uint32_t err_ppm, int rc_half, uint8_t* d_out, int64_t* d_off);
+int sgc_synth_unitigs(sgc_ctx* ctx, const uint8_t* d_genome, const int64_t* d_cuts, int64_t n, int k,
+                      int64_t out_bytes, uint8_t* d_out, int64_t* d_out_off);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGC_B200_H */

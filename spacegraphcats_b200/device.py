@@ -1,0 +1,335 @@
+"""Host-side handles over the C-ABI: one :class:`Context` per GPU, :class:`DeviceTable`
+for the GPU-resident hash -> unitig-id map.  PyTorch is used only to own device / pinned
+memory and the CUDA stream; every computation is a kernel of ``libsgc_b200.so``.
+
+Inputs may be numpy arrays (copied host->device through pinned memory on the context's
+stream) or CUDA tensors already resident on the context's device (used as they are).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import SGC_MISS, SgcCapacityError, check
+
+_contexts = {}
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def pack_sequences(seqs):
+    """list of str/bytes -> (uint8 concatenation, int64 offsets[n+1])."""
+    bs = [s.encode("ascii") if isinstance(s, str) else bytes(s) for s in seqs]
+    off = np.zeros(len(bs) + 1, np.int64)
+    if bs:
+        np.cumsum([len(b) for b in bs], out=off[1:])
+    buf = np.frombuffer(b"".join(bs), dtype=np.uint8) if off[-1] else np.zeros(0, np.uint8)
+    return buf, off
+
+
+def kmer_counts(off, ksize):
+    """per-sequence k-mer counts max(0, L-k+1) from offsets (host)."""
+    return np.maximum(np.diff(np.asarray(off, np.int64)) - int(ksize) + 1, 0)
+
+
+class Context:
+    """One GPU, one CUDA stream, scratch memory (``sgc_ctx``)."""
+
+    def __init__(self, device=0):
+        torch = _torch()
+        L = _lib.lib()
+        if not torch.cuda.is_available():
+            raise RuntimeError("spacegraphcats_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.stream = torch.cuda.Stream(device=self.device)
+        h = ctypes.c_void_p()
+        check(L.sgc_ctx_create(self.device_index, ctypes.c_void_p(self.stream.cuda_stream), ctypes.byref(h)))
+        self._h = h
+        self._L = L
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sgc_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- memory helpers -------------------------------------------------
+    def empty(self, n, dtype):
+        torch = _torch()
+        with torch.cuda.stream(self.stream):  # block belongs to the context stream's pool
+            return torch.empty(max(int(n), 0), dtype=dtype, device=self.device)
+
+    def to_device(self, a, dtype=None):
+        """numpy array / CUDA tensor -> CUDA tensor on this context's device (stream-ordered)."""
+        torch = _torch()
+        if isinstance(a, torch.Tensor):
+            if a.device != self.device:
+                raise ValueError("tensor lives on %s, context on %s" % (a.device, self.device))
+            return a.contiguous()
+        a = np.ascontiguousarray(a, dtype=dtype)
+        if a.dtype == np.uint64:
+            a = a.view(np.int64)
+        elif a.dtype == np.uint32:
+            a = a.view(np.int32)
+        with torch.cuda.stream(self.stream):
+            if a.size == 0:
+                return torch.empty(0, dtype=torch.from_numpy(a).dtype, device=self.device)
+            t = torch.from_numpy(a)
+            return t.to(self.device, non_blocking=False)
+
+    def to_host(self, t, dtype=None):
+        torch = _torch()
+        with torch.cuda.stream(self.stream):
+            a = t.cpu().numpy()
+        return a.view(dtype) if dtype is not None else a
+
+    @staticmethod
+    def ptr(t):
+        return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+    def sync(self):
+        check(self._L.sgc_ctx_sync(self._h))
+
+    @property
+    def launches(self):
+        return int(self._L.sgc_ctx_launches(self._h))
+
+    # ---- K1 --------------------------------------------------------------
+    def hash_batch(self, seq, off, ksize, want_status=True, to_host=True):
+        """Hash every k-mer of every sequence.  Returns (hashes u64, kmer_off i64, status i32)."""
+        torch = _torch()
+        d_seq = self.to_device(seq, np.uint8)
+        d_off = self.to_device(off, np.int64)
+        nseq = d_off.numel() - 1
+        nbytes = d_seq.numel()
+        cap = max(nbytes, 1)  # total k-mers <= total bases
+        d_hash = self.empty(cap, torch.int64)
+        d_koff = self.empty(nseq + 1, torch.int64)
+        d_stat = self.empty(nseq, torch.int32) if want_status else None
+        total = ctypes.c_int64(0)
+        check(
+            self._L.sgc_hash_batch(
+                self._h, self.ptr(d_seq), nbytes, self.ptr(d_off), nseq, int(ksize), self.ptr(d_hash), cap,
+                self.ptr(d_koff), self.ptr(d_stat) if d_stat is not None else None, ctypes.byref(total),
+            )
+        )
+        d_hash = d_hash[: total.value]
+        if not to_host:
+            self.sync()
+            return d_hash, d_koff, d_stat
+        return (
+            self.to_host(d_hash, np.uint64),
+            self.to_host(d_koff),
+            self.to_host(d_stat) if d_stat is not None else None,
+        )
+
+    # ---- K6 --------------------------------------------------------------
+    def count_doms(self, d_count_by_id, member_off, member, level_nodes, level_off, n_nodes):
+        torch = _torch()
+        d_moff = self.to_device(member_off, np.int64)
+        d_mem = self.to_device(member, np.uint32)
+        d_lvl = self.to_device(level_nodes, np.uint32)
+        h_loff = np.ascontiguousarray(level_off, np.int64)
+        d_out = self.empty(n_nodes, torch.int32)
+        check(
+            self._L.sgc_count_doms(
+                self._h, self.ptr(d_count_by_id), self.ptr(d_moff), self.ptr(d_mem), self.ptr(d_lvl),
+                h_loff.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), len(h_loff) - 1, self.ptr(d_out), int(n_nodes),
+            )
+        )
+        return d_out
+
+
+def get_context(device=None):
+    """Process-wide context for a device (default: LOCAL_RANK or 0)."""
+    import os
+
+    if device is None:
+        device = int(os.environ.get("SGC_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    ctx = _contexts.get(device)
+    if ctx is None:
+        ctx = _contexts[device] = Context(device)
+    return ctx
+
+
+class DeviceTable:
+    """GPU-resident exact map u64 k-mer hash -> u32 unitig id (``sgc_table``)."""
+
+    def __init__(self, ctx, max_entries, home_shift=0):
+        self.ctx = ctx
+        self._L = ctx._L
+        h = ctypes.c_void_p()
+        check(self._L.sgc_table_create(ctx._h, int(max_entries), ctypes.byref(h)))
+        self._h = h
+        self.max_entries = int(max_entries)
+        if home_shift:
+            check(self._L.sgc_table_set_home_shift(self._h, int(home_shift)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sgc_table_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def nbytes(self):
+        return int(self._L.sgc_table_bytes(self._h))
+
+    # ---- K2 --------------------------------------------------------------
+    def insert_pairs(self, hashes, ids):
+        c = self.ctx
+        d_h = c.to_device(hashes, np.uint64)
+        d_v = c.to_device(ids, np.uint32)
+        if d_h.numel() != d_v.numel():
+            raise ValueError("hashes and ids differ in length")
+        check(self._L.sgc_table_insert_pairs(self._h, c.ptr(d_h), c.ptr(d_v), d_h.numel()))
+
+    def insert_sequences(self, seq, off, ksize, ids=None, id_base=0):
+        """Fused hash + insert of every k-mer of every sequence under the sequence's id.
+        Returns the per-sequence status array (bit 0: non-ACGT byte seen)."""
+        torch = _torch()
+        c = self.ctx
+        d_seq = c.to_device(seq, np.uint8)
+        d_off = c.to_device(off, np.int64)
+        nseq = d_off.numel() - 1
+        d_ids = c.to_device(ids, np.uint32) if ids is not None else None
+        d_stat = c.empty(nseq, torch.int32)
+        check(
+            self._L.sgc_table_insert_sequences(
+                self._h, c.ptr(d_seq), d_seq.numel(), c.ptr(d_off), nseq, int(ksize),
+                c.ptr(d_ids) if d_ids is not None else None, int(id_base), c.ptr(d_stat),
+            )
+        )
+        return d_stat
+
+    def stats(self):
+        live, multi, mx = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_uint32(0)
+        check(self._L.sgc_table_stats(self._h, ctypes.byref(live), ctypes.byref(multi), ctypes.byref(mx)))
+        return live.value, multi.value, mx.value
+
+    def export(self):
+        """All live (hash, id) pairs sorted by hash -> (uint64[n], uint32[n]) on the host."""
+        torch = _torch()
+        c = self.ctx
+        live, _, _ = self.stats()
+        d_h = c.empty(max(live, 1), torch.int64)
+        d_v = c.empty(max(live, 1), torch.int32)
+        n = ctypes.c_int64(0)
+        check(self._L.sgc_table_export(self._h, c.ptr(d_h), c.ptr(d_v), live, ctypes.byref(n)))
+        return c.to_host(d_h[: n.value], np.uint64), c.to_host(d_v[: n.value], np.uint32)
+
+    # ---- K3 --------------------------------------------------------------
+    def lookup(self, hashes, to_host=True):
+        torch = _torch()
+        c = self.ctx
+        d_h = c.to_device(hashes, np.uint64)
+        d_o = c.empty(d_h.numel(), torch.int32)
+        check(self._L.sgc_lookup(self._h, c.ptr(d_h), d_h.numel(), c.ptr(d_o)))
+        if not to_host:
+            return d_o
+        return c.to_host(d_o, np.uint32)
+
+    # ---- K5 --------------------------------------------------------------
+    def count_matches(self, hashes, n_ids, distinct=False, to_host=True):
+        """-> (count_by_id u32[n_ids], n_miss, n_distinct)"""
+        torch = _torch()
+        c = self.ctx
+        d_h = c.to_device(hashes, np.uint64)
+        d_cnt = c.empty(n_ids, torch.int32)
+        miss, nd = ctypes.c_int64(0), ctypes.c_int64(0)
+        check(
+            self._L.sgc_count_matches(
+                self._h, c.ptr(d_h), d_h.numel(), 1 if distinct else 0, c.ptr(d_cnt), int(n_ids),
+                ctypes.byref(miss), ctypes.byref(nd),
+            )
+        )
+        cnt = c.to_host(d_cnt, np.uint32) if to_host else d_cnt
+        return cnt, miss.value, nd.value
+
+    def lookup_sequences(self, seq, off, ksize, n_ids=0, want_ids=True, to_host=True):
+        """Fused hash + lookup of every k-mer.  -> dict(kmer_ids, kmer_off, count_by_id, status, n_kmers, n_hits)"""
+        torch = _torch()
+        c = self.ctx
+        d_seq = c.to_device(seq, np.uint8)
+        d_off = c.to_device(off, np.int64)
+        nseq = d_off.numel() - 1
+        nbytes = d_seq.numel()
+        cap = max(nbytes, 1)
+        d_ids = c.empty(cap, torch.int32) if want_ids else None
+        d_koff = c.empty(nseq + 1, torch.int64)
+        d_cnt = c.empty(n_ids, torch.int32) if n_ids else None
+        d_stat = c.empty(nseq, torch.int32)
+        nk, nh = ctypes.c_int64(0), ctypes.c_int64(0)
+        check(
+            self._L.sgc_lookup_sequences(
+                self._h, c.ptr(d_seq), nbytes, c.ptr(d_off), nseq, int(ksize),
+                c.ptr(d_ids) if d_ids is not None else None, cap, c.ptr(d_koff),
+                c.ptr(d_cnt) if d_cnt is not None else None, int(n_ids), c.ptr(d_stat),
+                ctypes.byref(nk), ctypes.byref(nh),
+            )
+        )
+        out = {"n_kmers": nk.value, "n_hits": nh.value}
+        if d_ids is not None:
+            d_ids = d_ids[: nk.value]
+        if to_host:
+            out["kmer_ids"] = c.to_host(d_ids, np.uint32) if d_ids is not None else None
+            out["kmer_off"] = c.to_host(d_koff)
+            out["count_by_id"] = c.to_host(d_cnt, np.uint32) if d_cnt is not None else None
+            out["status"] = c.to_host(d_stat)
+        else:
+            out.update(kmer_ids=d_ids, kmer_off=d_koff, count_by_id=d_cnt, status=d_stat)
+        return out
+
+    # ---- K4 --------------------------------------------------------------
+    def label_reads(self, seq, off, ksize, ids_cap=None, to_host=True):
+        """index_reads' per-read step: distinct unitig ids per sequence as CSR.
+        -> dict(ids_off i64[nseq+1], ids u32[n_labels], status, n_kmers, n_hits)"""
+        torch = _torch()
+        c = self.ctx
+        d_seq = c.to_device(seq, np.uint8)
+        d_off = c.to_device(off, np.int64)
+        nseq = d_off.numel() - 1
+        nbytes = d_seq.numel()
+        cap = int(ids_cap) if ids_cap is not None else max(4 * nseq, 1024)
+        d_stat = c.empty(nseq, torch.int32)
+        d_ioff = c.empty(nseq + 1, torch.int64)
+        for _ in range(8):
+            d_ids = c.empty(cap, torch.int32)
+            nk, nh, nl = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+            try:
+                check(
+                    self._L.sgc_label_reads(
+                        self._h, c.ptr(d_seq), nbytes, c.ptr(d_off), nseq, int(ksize), c.ptr(d_ioff), c.ptr(d_ids),
+                        cap, c.ptr(d_stat), ctypes.byref(nk), ctypes.byref(nh), ctypes.byref(nl),
+                    )
+                )
+                break
+            except SgcCapacityError:
+                cap = max(2 * cap, int(nl.value) + 1024)
+        else:
+            raise RuntimeError("label_reads: could not size the label buffer")
+        d_ids = d_ids[: nl.value]
+        out = {"n_kmers": nk.value, "n_hits": nh.value, "n_labels": nl.value}
+        if to_host:
+            out.update(ids_off=c.to_host(d_ioff), ids=c.to_host(d_ids, np.uint32), status=c.to_host(d_stat))
+        else:
+            out.update(ids_off=d_ioff, ids=d_ids, status=d_stat)
+        return out
+
+
+__all__ = ["Context", "DeviceTable", "get_context", "pack_sequences", "kmer_counts", "SGC_MISS"]

@@ -1,0 +1,122 @@
+"""Query a catlas with sequences: the hot-path half of the reference's
+``spacegraphcats/search/query_by_sequence.py`` -- ``Query.__init__`` :153-185 (hash every record's
+k-mers into ONE set) and ``Query.execute`` :187-227 (per-unitig match counts -> per-dominator
+counts -> dominators -> neighbourhood).  Signature / CSV / contig retrieval output (``QueryOutput``
+:27-150, sourmash + sqlite) stays on the CPU reference and is out of scope here.
+
+All records of a query are hashed in one batch; the set() is a device sort + adjacent-unique
+fused into the lookup/count kernel (``sgc_count_matches(distinct=1)``).
+"""
+import numpy as np
+
+from ..cdbg.hashing import get_context, pack_sequences
+from ..utils.seqio import read_records
+
+
+class QueryResult:
+    """What ``Query.execute`` hands to the reference's ``QueryOutput``: the matched dominators
+    and, derived from them, the neighbourhood ("shadow") of cDBG nodes."""
+
+    def __init__(self, query, catlas, kmer_idx, doms, catlas_name):
+        self.query = query
+        self.catlas = catlas
+        self.kmer_idx = kmer_idx
+        self.doms = doms
+        self.catlas_name = catlas_name
+        self.total_bp = 0
+        self.total_seq = 0
+        self.query_sig = getattr(query, "sig", None)
+        # here is where we go from the dominators to the actual cDBG nodes (:34)
+        self.shadow = catlas.shadow(doms)
+
+    # the two id lists QueryOutput.write saves (:126-132)
+    def cdbg_ids_lines(self):
+        return [str(x) for x in sorted(self.shadow)]
+
+    def frontier_lines(self):
+        return [str(x) for x in sorted(self.doms)]
+
+
+class Query:
+    def __init__(self, query_file, ksize, scaled=None, catlas_name=None, debug=True, records=None):
+        self.filename = query_file
+        self.ksize = int(ksize)
+        self.name = None
+        self.catlas_name = catlas_name
+        self.debug = debug
+        self.sig = None  # sourmash signature: out of scope (CPU reference)
+
+        seqs = []
+        for record in (records if records is not None else read_records(query_file)):
+            if self.name is None:
+                self.name = record.name
+            if len(record.sequence) >= self.ksize:  # :174
+                seqs.append(record.sequence)
+        ctx = get_context()
+        buf, off = pack_sequences(seqs)
+        # hashes stay on the device; the distinct set is only materialised on demand
+        d_hashes, _, d_status = ctx.hash_batch(buf, off, self.ksize, to_host=False)
+        if d_status is not None and d_status.numel() and bool(d_status.any().item()):
+            raise ValueError("Invalid base in read (query %s)" % query_file)
+        self._d_hashes = d_hashes
+        self._ctx = ctx
+        self._kmers = None
+        self._n_distinct = None
+        self.cdbg_match_counts = None
+        self.catlas_match_counts = None
+
+    # the reference exposes a Python set of ints; build it lazily
+    @property
+    def kmers(self):
+        if self._kmers is None:
+            h = self._ctx.to_host(self._d_hashes, np.uint64)
+            self._kmers = set(np.unique(h).tolist())
+            self._n_distinct = len(self._kmers)
+        return self._kmers
+
+    def __len__(self):
+        return self.n_kmers
+
+    @property
+    def n_kmers(self):
+        if self._n_distinct is None:
+            len(self.kmers)
+        return self._n_distinct
+
+    def execute(self, catlas, kmer_idx):
+        table = kmer_idx.table
+        counts, n_miss, n_distinct = table.count_matches_array(self._d_hashes, distinct=True)
+        self._n_distinct = n_distinct
+        nz = np.flatnonzero(counts)
+        self.cdbg_match_counts = dict(zip(nz.tolist(), counts[nz].tolist()))  # :189
+        for k, v in self.cdbg_match_counts.items():  # :191-192
+            assert v <= kmer_idx.get_cdbg_size(k), k
+
+        self.catlas_match_counts = kmer_idx.count_catlas_matches(self.cdbg_match_counts, catlas)  # :195
+
+        if self.debug and self.catlas_match_counts:  # :199-211
+            assert sum(self.cdbg_match_counts.values()) == self.catlas_match_counts[catlas.root]
+            index_sizes = getattr(catlas, "index_sizes", None)
+            if index_sizes is not None:
+                for v, match_amount in self.catlas_match_counts.items():
+                    assert match_amount <= index_sizes[v], v
+                self.con_sim_upper_bounds(catlas, kmer_idx)
+
+        doms = {catlas.cdbg_to_layer1[c] for c in self.cdbg_match_counts}  # :214-220
+        return QueryResult(self, catlas, kmer_idx, doms, self.catlas_name)
+
+    def con_sim_upper_bounds(self, catlas, kmer_idx):
+        """Best possible containment / overheads (:229-270) -- host-side ratios."""
+        root = catlas.root
+        total_match = sum(self.cdbg_match_counts.values())
+        best_containment = total_match / self.n_kmers if self.n_kmers else 0.0
+        in_nodes = sum(kmer_idx.get_cdbg_size(c) for c in self.cdbg_match_counts)
+        cdbg_min_overhead = (in_nodes - total_match) / in_nodes if in_nodes else 0
+        catlas_min_overhead = 0
+        cm = self.catlas_match_counts
+        if cm and cm.get(root):
+            in_doms = sum(
+                catlas.index_sizes[v] for v, lvl in catlas.levels.items() if lvl == 1 and cm.get(v)
+            )
+            catlas_min_overhead = (in_doms - cm[root]) / in_doms
+        return best_containment, cdbg_min_overhead, catlas_min_overhead

@@ -1,0 +1,496 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle and the
+reference's own golden fixtures.  Integer work: everything is compared bit-exact."""
+import hashlib
+import json
+import os
+import sqlite3
+
+import numpy as np
+import pytest
+
+from conftest import golden_path
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import __graft_entry__ as g
+
+    g.build()
+    from spacegraphcats_b200.device import get_context
+
+    return get_context(0)
+
+
+@pytest.fixture(scope="module")
+def dory(O):
+    recs = O.read_unitigs_tsv(golden_path("dory_k21_unitigs.tsv.gz"))
+    z = np.load(golden_path("dory_k21_contigs.indices.npz"))
+    with open(golden_path("dory_k21_contigs.sizes.json")) as fp:
+        sz = json.load(fp)
+    sizes = {int(a): b for a, b in sz["sizes"].items()}
+    return recs, z["mphf_to_hash"], z["mphf_to_value"], sizes
+
+
+@pytest.fixture(scope="module")
+def dory_index(ctx, dory):
+    from spacegraphcats_b200.cdbg.index_cdbg_by_kmer import build_mphf
+    from spacegraphcats_b200.cdbg.hashing import MPHF_KmerIndex
+
+    recs = dory[0]
+    table, sizes = build_mphf(21, lambda: iter(recs), ctx=ctx, verbose=False)
+    return MPHF_KmerIndex(21, table, sizes)
+
+
+def rand_seq(rng, n):
+    return "".join("ACGT"[i] for i in rng.integers(0, 4, n))
+
+
+# ---------------------------------------------------------------- K1: hashing
+KATS = {
+    "GACCAAAGGCTTACGGTGAGC": 10218271035842461694,  # reference tests/test_dory_workflow.py:196
+    "TCTCCGTTTGCAGAAATCGTA": 8436068710919520258,
+    "AGCAGGTACAATGGACTGGAT": 13994045974119358468,
+    "TTCGGCAAGAAAATTTTAATA": 11971930231572094512,
+    "AGACCAACCTTTAGCCTATTCAAGACGAGTG": 505484382184005004,
+    "GACCAACCTTTAGCCTATTCAAGACGAGTGT": 17407874517182356438,
+    "A" * 31: 8676834403036734983,
+    "ACGT" * 8: 0,  # even-k palindrome
+}
+
+
+def test_hash_kats(ctx):
+    from spacegraphcats_b200.cdbg.hashing import hash_sequence
+
+    for kmer, want in KATS.items():
+        got = hash_sequence(kmer, len(kmer))
+        assert got == [want] and isinstance(got[0], int)
+
+
+@pytest.mark.parametrize("k", [21, 31, 1, 2, 7, 8, 9, 15, 16, 17, 24, 32, 33, 47, 48, 49, 63, 64, 65, 127, 255])
+def test_hash_sequence_vs_oracle_many_k(ctx, O, k):
+    from spacegraphcats_b200.cdbg.hashing import hash_sequence
+
+    rng = np.random.default_rng(k)
+    for n in (k, k + 1, k + 3, k + 4, 150, 511, 1000):
+        if n < k:
+            continue
+        seq = rand_seq(rng, n)
+        assert hash_sequence(seq, k) == O.hash_sequence(seq, k).tolist(), (k, n)
+
+
+def test_hash_sequence_short_raises(ctx):
+    from spacegraphcats_b200.cdbg.hashing import hash_sequence
+
+    with pytest.raises(ValueError):
+        hash_sequence("ACGT", 5)
+
+
+def test_hash_invalid_base_policy(ctx, O):
+    """Non-ACGT bytes: the kernel flags the sequence (host raises, like khmer's 'Invalid base in
+    read'); the hash values themselves follow the oracle's documented pass-through rule."""
+    from spacegraphcats_b200.cdbg.hashing import hash_sequence
+    from spacegraphcats_b200.device import pack_sequences
+
+    seq = "ACGTNNacgtRYACGTACGTTTGACCAGGTTACGATCGGACTAGCATCAGGACGT"
+    with pytest.raises(ValueError):
+        hash_sequence(seq, 9)
+    buf, off = pack_sequences([seq, "ACGTACGTAGCTAGCTAGCATCGAT"])
+    h, koff, status = ctx.hash_batch(buf, off, 9)
+    assert status.tolist() == [1, 0]
+    want, woff = O.hash_batch(buf, off, 9)
+    assert np.array_equal(h, want) and np.array_equal(koff, woff)
+
+
+@pytest.mark.parametrize("k", [21, 31, 12])
+def test_hash_batch_ragged_empty_and_long(ctx, O, k):
+    """ragged batch: empty sequences, shorter than k, exactly k, multi-segment (> 256 k-mers),
+    a 300 kbp sequence, and an empty batch."""
+    from spacegraphcats_b200.device import pack_sequences
+
+    rng = np.random.default_rng(100 + k)
+    lens = [0, 1, k - 1, k, k + 1, 150, 0, 255 + k, 256 + k - 1, 256 + k, 257 + k, 5000, 300_000, k, 3]
+    lens += rng.integers(0, 700, 400).tolist()
+    seqs = [rand_seq(rng, n) for n in lens]
+    buf, off = pack_sequences(seqs)
+    h, koff, status = ctx.hash_batch(buf, off, k)
+    want, woff = O.hash_batch(buf, off, k)
+    assert np.array_equal(koff, woff)
+    assert np.array_equal(h, want)
+    assert not status.any()
+    h, koff, status = ctx.hash_batch(np.zeros(0, np.uint8), np.zeros(1, np.int64), k)
+    assert len(h) == 0 and koff.tolist() == [0]
+    # unaligned device views of the same buffer give the same hashes
+    import torch
+
+    d = ctx.to_device(np.concatenate([np.zeros(3, np.uint8), buf]))
+    h2, _, _ = ctx.hash_batch(d[3:], off, k)
+    assert np.array_equal(h2, want)
+
+
+def test_dory_unitig_hashes_match_reference_table(ctx, dory):
+    """Every dory unitig k-mer hash, under its unitig id, is a pair of the reference's own
+    contigs.indices (212,475 pairs)."""
+    from spacegraphcats_b200.device import pack_sequences
+
+    recs, ref_h, ref_v, sizes = dory
+    buf, off = pack_sequences([r.sequence for r in recs])
+    h, koff, _ = ctx.hash_batch(buf, off, 21)
+    ids = np.repeat(np.array([int(r.name) for r in recs], np.uint32), np.diff(koff))
+    got = np.unique(np.stack([h, ids.astype(np.uint64)], 1), axis=0)
+    want = np.unique(np.stack([ref_h, ref_v.astype(np.uint64)], 1), axis=0)
+    assert np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------- K2/K3: table
+def test_dory_build_mphf_whole_table(dory, dory_index):
+    recs, ref_h, ref_v, ref_sizes = dory
+    t = dory_index.table
+    assert len(dory_index) == 212475 == len(t)
+    assert dory_index.sizes == ref_sizes
+    live, multi, max_id = t.stats()
+    assert (live, multi, max_id) == (212475, 0, 735)
+    order = np.argsort(ref_h)
+    assert np.array_equal(t.mphf_to_hash, ref_h[order])
+    assert np.array_equal(t.mphf_to_value, ref_v[order])
+    # reference tests/test_dory_workflow.py:195-199
+    assert t[10218271035842461694] == 118
+    assert t[8436068710919520258] == 118
+    assert t[13994045974119358468] == 118
+    assert t[11971930231572094512] == 187
+    assert dory_index.get_cdbg_id(12345) is None
+    assert max(t.mphf_to_value) == 735
+
+
+def test_table_from_reference_arrays_and_lookup(ctx, O, dory):
+    from spacegraphcats_b200.cdbg.hashing import GpuKmerTable
+
+    _, ref_h, ref_v, _ = dory
+    t = GpuKmerTable.from_pairs(ref_h, ref_v, ctx=ctx)
+    assert len(t) == len(ref_h)
+    rng = np.random.default_rng(1)
+    q = np.concatenate([ref_h[rng.integers(0, len(ref_h), 50000)], rng.integers(0, 2**63, 50000).astype(np.uint64),
+                        np.array([0, 2**64 - 1], np.uint64)])
+    got = t.lookup_many(q)
+    want = O.COracleTable(ref_h, ref_v).lookup(q)
+    assert np.array_equal(got, want)
+    assert (got[:50000] != 0xFFFFFFFF).all()
+
+
+def test_save_and_from_directory_roundtrip(tmp_path, dory, dory_index):
+    from spacegraphcats_b200.cdbg.hashing import MPHF_KmerIndex
+
+    _, ref_h, ref_v, ref_sizes = dory
+    dory_index.save(str(tmp_path))
+    for fn in ("contigs.mphf", "contigs.indices", "contigs.sizes"):
+        assert os.path.exists(tmp_path / fn)
+    z = np.load(str(tmp_path / "contigs.indices"))
+    assert set(z.files) == {"mphf_to_hash", "mphf_to_value"}
+    assert z["mphf_to_hash"].dtype == np.uint64 and z["mphf_to_value"].dtype == np.uint32
+    idx = MPHF_KmerIndex.from_directory(str(tmp_path))
+    assert idx.ksize == 21 and idx.sizes == ref_sizes and len(idx) == 212475
+    assert idx.get_cdbg_id(11971930231572094512) == 187
+
+
+def test_build_mphf_multicounts_vs_oracle(ctx, O):
+    """Hashes shared by two DIFFERENT unitigs are dropped; repeats inside one unitig are kept
+    (index_cdbg_by_kmer.py:40-57).  Includes reverse-complement duplicates and k-mers repeated
+    within a record."""
+    from spacegraphcats_b200.cdbg.index_cdbg_by_kmer import build_mphf
+
+    rng = np.random.default_rng(9)
+    k = 31
+    base = [rand_seq(rng, int(n)) for n in rng.integers(31, 900, 300)]
+    seqs = list(base)
+    seqs[10] = seqs[3][5:200] + rand_seq(rng, 40)  # shares k-mers with unitig 3
+    seqs[20] = O.revcomp(seqs[7].encode()).decode()  # the RC of unitig 7: every hash collides
+    seqs[30] = seqs[30] + seqs[30][:60]  # internal repeat: stays
+    seqs[299] = rand_seq(rng, 500)  # the max id must keep >= 1 k-mer
+    order = rng.permutation(len(seqs))
+    recs = [O.Record(str(i), seqs[i]) for i in order]  # ids are not in file order
+    table, sizes = build_mphf(k, lambda: iter(recs), ctx=ctx, verbose=False)
+    otable, osizes, n_multi = O.build_mphf(k, lambda: iter(recs))
+    assert n_multi > 0
+    assert sizes == osizes
+    live, multi, max_id = table.stats()
+    assert (live, multi) == (len(otable), n_multi)
+    oh, ov = otable.mphf_to_hash, otable.mphf_to_value
+    o = np.argsort(oh)
+    assert np.array_equal(table.mphf_to_hash, oh[o]) and np.array_equal(table.mphf_to_value, ov[o])
+    # dropped hashes are misses
+    dropped = O.hash_sequence(seqs[7], k)
+    assert (table.lookup_many(dropped) == 0xFFFFFFFF).all()
+
+
+def test_table_full_is_an_error(ctx):
+    from spacegraphcats_b200.device import DeviceTable
+    from spacegraphcats_b200._lib import SgcCapacityError
+
+    t = DeviceTable(ctx, 64)
+    rng = np.random.default_rng(2)
+    with pytest.raises(SgcCapacityError):
+        t.insert_pairs(rng.integers(0, 2**63, 1000).astype(np.uint64), np.zeros(1000, np.uint32))
+
+
+# ---------------------------------------------------------------- K4: read labelling
+@pytest.fixture(scope="module")
+def dory_reads(O):
+    return O.read_records(golden_path("data", "dory-subset.fq.gz"))
+
+
+def test_label_reads_dory_vs_oracle(ctx, O, dory, dory_index, dory_reads):
+    from spacegraphcats_b200.device import pack_sequences
+
+    _, ref_h, ref_v, _ = dory
+    buf, off = pack_sequences([r.sequence for r in dory_reads])
+    res = dory_index.table.label_reads(buf, off, 21)
+    o_off, o_ids, o_nk, o_nh = O.COracleTable(ref_h, ref_v).label_reads(buf, off, 21)
+    assert np.array_equal(res["ids_off"], o_off)
+    assert np.array_equal(res["ids"], o_ids)
+    assert (res["n_kmers"], res["n_hits"]) == (o_nk, o_nh) == (240920, 240920)
+    # SURVEY 8c derived pin: 537 reads -> 907 (read, id) pairs
+    assert len(dory_reads) == 537 and len(res["ids"]) == 907
+    lines = sorted("%d,%d\n" % (i, c) for i in range(537) for c in res["ids"][res["ids_off"][i] : res["ids_off"][i + 1]])
+    assert hashlib.sha256("".join(lines).encode()).hexdigest() == \
+        "933dbab55d9262d91ce6f3fe4c883957480e4f22e6d9ff503a44ee24d3ea7c90"
+    assert set(res["ids"].tolist()) == set(range(736))  # test_dory_index_reads: rc == 0
+
+
+def test_label_reads_synthetic_with_errors_vs_oracle(ctx, O):
+    """Reads cut from a random genome with substitution errors and reverse complements against a
+    pseudo-unitig table: hits, misses, several ids per read, reads shorter than k, empty reads."""
+    from spacegraphcats_b200.cdbg.hashing import GpuKmerTable
+    from spacegraphcats_b200.device import pack_sequences
+
+    rng = np.random.default_rng(21)
+    k = 31
+    genome = rng.integers(0, 4, 400_000).astype(np.uint8)
+    lut = np.frombuffer(b"ACGT", np.uint8)
+    g = lut[genome]
+    # unitigs: consecutive pieces overlapping by k-1 so every k-mer lies in exactly one
+    cuts = np.concatenate([[0], np.cumsum(rng.integers(1, 200, 6000))])
+    cuts = cuts[cuts < len(g) - k]
+    useqs = [g[a : b + k - 1].tobytes() for a, b in zip(cuts[:-1], cuts[1:])]
+    ubuf, uoff = pack_sequences(useqs)
+    table = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx)
+    oh, ooff = O.hash_batch(ubuf, uoff, k)
+    oid = np.repeat(np.arange(len(useqs), dtype=np.uint32), np.diff(ooff))
+    otab, _, _ = O.build_mphf(k, lambda: iter(O.Record(str(i), s.decode()) for i, s in enumerate(useqs)))
+    ot = O.COracleTable(otab.mphf_to_hash, otab.mphf_to_value)
+    assert len(table) == len(ot)
+
+    reads = []
+    for i in range(20000):
+        ln = int(rng.integers(0, 400)) if i % 50 == 0 else 150
+        p = int(rng.integers(0, len(g) - 400))
+        r = g[p : p + ln].copy()
+        err = rng.random(ln) < 0.01
+        r[err] = lut[rng.integers(0, 4, int(err.sum()))]
+        r = r.tobytes()
+        reads.append(O.revcomp(r) if i & 1 else r)
+    buf, off = pack_sequences(reads)
+    res = table.label_reads(buf, off, k)
+    o_off, o_ids, o_nk, o_nh = ot.label_reads(buf, off, k)
+    assert (res["n_kmers"], res["n_hits"]) == (o_nk, o_nh)
+    assert 0 < o_nh < o_nk
+    assert np.array_equal(res["ids_off"], o_off) and np.array_equal(res["ids"], o_ids)
+    # the same through per-k-mer ids (count_dominator_abundance shape) and the K4 tail alone
+    lk = table.lookup_sequences(buf, off, k, n_ids=len(useqs))
+    oh2, ooff2 = O.hash_batch(buf, off, k)
+    want_ids = ot.lookup(oh2)
+    assert np.array_equal(lk["kmer_off"], ooff2) and np.array_equal(lk["kmer_ids"], want_ids)
+    cnt, miss = ot.count_matches(oh2, len(useqs))
+    assert np.array_equal(lk["count_by_id"], cnt) and lk["n_kmers"] - lk["n_hits"] == miss
+
+
+def test_label_reads_many_ids_per_read_overflows_staging(ctx, O):
+    """Worst case for the candidate staging buffer: every k-mer of a read maps to a different
+    unitig (unitigs of exactly one k-mer), far more candidates than the per-round buffer."""
+    from spacegraphcats_b200.cdbg.hashing import GpuKmerTable
+    from spacegraphcats_b200.device import pack_sequences
+
+    rng = np.random.default_rng(33)
+    k = 21
+    g = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 60_000)]
+    useqs = [g[i : i + k].tobytes() for i in range(len(g) - k + 1)]
+    ubuf, uoff = pack_sequences(useqs)
+    table = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx)
+    otab, _, _ = O.build_mphf(k, lambda: iter(O.Record(str(i), s.decode()) for i, s in enumerate(useqs)))
+    ot = O.COracleTable(otab.mphf_to_hash, otab.mphf_to_value)
+    reads = [g[i * 1000 : i * 1000 + 5000].tobytes() for i in range(50)] + [g.tobytes()]
+    buf, off = pack_sequences(reads)
+    res = table.label_reads(buf, off, k)
+    o_off, o_ids, _, _ = ot.label_reads(buf, off, k)
+    assert np.array_equal(res["ids_off"], o_off) and np.array_equal(res["ids"], o_ids)
+    assert res["n_labels"] > 100_000
+
+
+# ---------------------------------------------------------------- K5/K6: queries
+@pytest.fixture(scope="module")
+def dory_catlas():
+    from spacegraphcats_b200.search.catlas import CAtlas
+
+    return CAtlas(golden_path(), golden_path("dory_k21_r1"))
+
+
+def test_count_cdbg_matches_semantics(O, dory, dory_index):
+    """A list counts duplicates, a set does not (BBHashTable.get_unique_values)."""
+    _, ref_h, ref_v, _ = dory
+    ot = O.OracleTable.from_arrays(ref_h, ref_v)
+    recs = O.read_records(golden_path("data", "dory-head.fa"))
+    hs = []
+    for r in recs:
+        hs.extend(O.hash_sequence(r.sequence, 21).tolist())
+    hs = hs + hs[:100] + [5, 6, 7]
+    assert dory_index.count_cdbg_matches(hs) == O.count_cdbg_matches(ot, hs)
+    assert dory_index.count_cdbg_matches(set(hs)) == O.count_cdbg_matches(ot, set(hs)) == {118: 834, 187: 797}
+    with pytest.raises(ValueError):
+        dory_index.count_cdbg_matches(hs, require_exist=True)
+    assert dory_index.count_cdbg_matches([]) == {}
+
+
+def test_query_dory_head_matches_reference_outputs(O, dory, dory_index, dory_catlas):
+    import gzip
+
+    from spacegraphcats_b200.search.query_by_sequence import Query
+
+    _, ref_h, ref_v, ref_sizes = dory
+    dory_catlas.decorate_with_index_sizes(dory_index)
+    q = Query(golden_path("data", "dory-head.fa"), 21, 1000, "dory_k21_r1")
+    out = q.execute(dory_catlas, dory_index)
+    assert q.cdbg_match_counts == {118: 834, 187: 797}
+    assert q.n_kmers == 1631 == len(q.kmers)
+    # oracle of Query.execute
+    ocat = O.OracleCAtlas(golden_path("dory_k21_r1", "catlas.csv"), golden_path("dory_k21_r1", "first_doms.txt"))
+    okm = O.query_kmers(O.read_records(golden_path("data", "dory-head.fa")), 21)
+    ocdbg, ocat_counts, odoms, oshadow = O.query_execute(okm, O.OracleTable.from_arrays(ref_h, ref_v), ref_sizes, ocat)
+    assert q.kmers == okm
+    assert q.catlas_match_counts == ocat_counts
+    assert out.doms == odoms == {97, 150}
+    assert out.shadow == oshadow == {118, 187}
+    # the reference's own result files
+    with gzip.open(golden_path("dory_k21_r1_search", "dory-head.fa.cdbg_ids.txt.gz"), "rt") as fp:
+        assert [ln.strip() for ln in fp] == out.cdbg_ids_lines() == ["118", "187"]
+    with gzip.open(golden_path("dory_k21_r1_search", "dory-head.fa.frontier.txt.gz"), "rt") as fp:
+        assert sorted(ln.strip() for ln in fp) == sorted(out.frontier_lines())
+    assert dory_catlas.index_sizes == O.build_catlas_node_sizes(ref_sizes, ocat)
+    assert q.con_sim_upper_bounds(dory_catlas, dory_index)[0] == 1.0
+
+
+def test_query_nomatch(dory_index, dory_catlas):
+    """reference test_dory_search_nomatch: zero matching k-mers must not crash."""
+    from spacegraphcats_b200.search.query_by_sequence import Query
+
+    q = Query(golden_path("data", "random-query-nomatch.fa"), 21, 1000, "dory_k21_r1")
+    out = q.execute(dory_catlas, dory_index)
+    assert q.n_kmers == 8 and q.cdbg_match_counts == {} and q.catlas_match_counts == {}
+    assert out.doms == set() and out.shadow == set()
+
+
+def test_dominator_abundance_totals(O, dory, dory_index, dory_catlas):
+    """count_dominator_abundance.py:80-97 on dory-subset: reference totals 240920 / 212475
+    (tests/test_dory_workflow.py:859-870)."""
+    from spacegraphcats_b200.device import pack_sequences
+
+    recs = O.read_records(golden_path("data", "dory-subset.fa.gz"))
+    buf, off = pack_sequences([r.sequence for r in recs])
+    res = dory_index.table.lookup_sequences(buf, off, 21, n_ids=736, want_ids=False)
+    assert res["n_kmers"] == 240920 == res["n_hits"]
+    cdbg_counts = dict(enumerate(res["count_by_id"].tolist()))
+    ocat = O.OracleCAtlas(golden_path("dory_k21_r1", "catlas.csv"), golden_path("dory_k21_r1", "first_doms.txt"))
+    _, ref_h, ref_v, ref_sizes = dory
+    want_cdbg, want_dom = O.dominator_abundance(recs, O.OracleTable.from_arrays(ref_h, ref_v), 21, ocat)
+    assert {k: v for k, v in cdbg_counts.items() if v} == want_cdbg
+    got_dom = dory_index.count_catlas_matches({k: v for k, v in cdbg_counts.items() if v}, dory_catlas)
+    assert {d: got_dom.get(d, 0) for d in want_dom} == want_dom
+    assert sum(want_dom.values()) == 240920 and sum(ref_sizes.values()) == 212475
+
+
+# ---------------------------------------------------------------- index_reads main
+def _write_index(tmp_path, dory_index):
+    d = tmp_path / "dory_k21"
+    d.mkdir()
+    dory_index.save(str(d))
+    return str(d)
+
+
+def test_index_reads_main_dory(tmp_path, O, dory, dory_index, dory_reads):
+    """reference test_dory_index_reads (rc 0 <=> all 736 ids hit) + the rows against the oracle's
+    restatement of the index_reads loop."""
+    from spacegraphcats_b200.cdbg import index_reads
+    from spacegraphcats_b200.utils import bgzf
+
+    cdbg = _write_index(tmp_path, dory_index)
+    fq = "".join("@%s\n%s\n+\n%s\n" % (r.name, r.sequence, r.quality) for r in dory_reads).encode()
+    reads = str(tmp_path / "reads.bgz")
+    bgzf.write_bgzf(reads, fq)
+    db = str(tmp_path / "reads.index")
+    assert index_reads.main([cdbg, reads, db, "-k", "21"]) == 0
+    rows = sorted(sqlite3.connect(db).execute("SELECT offset, cdbg_id FROM sequences").fetchall())
+    src = bgzf.open_reads(reads)
+    _, _, _, pos = bgzf.parse_records(src.data)
+    offs = src.virtual_offsets(pos).tolist()
+    _, ref_h, ref_v, _ = dory
+    want, n_paired, total = O.label_reads(zip(dory_reads, offs), O.OracleTable.from_arrays(ref_h, ref_v), 21)
+    assert rows == sorted(want) and len(total) == 736
+    assert index_reads.main([cdbg, reads, db, "-k", "21", "-P"]) == -1  # no pairs in dory-subset
+    assert index_reads.main([cdbg, reads, db, "-P", "-N"]) == -1
+
+
+@pytest.mark.parametrize("ignore_paired", [False, True])
+def test_index_reads_pairing_semantics(tmp_path, ctx, O, ignore_paired):
+    """Pairing rules of index_reads.py:124-141 (/1,/2 names, equal names, short mates) on the
+    reference's own pairing fixture plus synthetic corner cases, against the oracle loop."""
+    from spacegraphcats_b200.cdbg import index_reads
+    from spacegraphcats_b200.cdbg.hashing import MPHF_KmerIndex
+    from spacegraphcats_b200.cdbg.index_cdbg_by_kmer import build_mphf
+    from spacegraphcats_b200.utils import bgzf
+
+    k = 31
+    ref = O.read_records(golden_path("data", "twofoo-short-paired-test.fa.gz"))
+    rng = np.random.default_rng(4)
+    genome = rand_seq(rng, 6000)
+    extra = [
+        O.Record("p1/1", genome[0:150]), O.Record("p1/2", genome[300:450]),
+        O.Record("p2/1", genome[600:750]), O.Record("p3/2", genome[900:1050]),  # names differ: unpaired
+        O.Record("same", genome[1200:1350]), O.Record("same", genome[1500:1650]),  # SRR style
+        O.Record("q/1", genome[2000:2150]), O.Record("short", "ACGT"), O.Record("q/2", genome[2300:2450]),
+        O.Record("r/1", genome[2600:2750]), O.Record("r/2", "ACGTACGT"),  # short mate
+        O.Record("/1", genome[3000:3150]), O.Record("/2", genome[3300:3450]),  # len(name) == 2
+        O.Record("nohit", rand_seq(rng, 150)),
+    ]
+    reads = list(ref) + extra
+    # pseudo-unitigs: 100-k-mer pieces of everything
+    pieces = []
+    for r in list(ref) + [O.Record("g", genome)]:
+        s = r.sequence
+        for a in range(0, max(len(s) - k + 1, 0), 100):
+            pieces.append(s[a : a + 100 + k - 1])
+    urecs = [O.Record(str(i), s) for i, s in enumerate(pieces)]
+    table, sizes = build_mphf(k, lambda: iter(urecs), ctx=ctx, verbose=False)
+    d = tmp_path / "cdbg"
+    d.mkdir()
+    MPHF_KmerIndex(k, table, sizes).save(str(d))
+    fa = "".join(">%s\n%s\n" % (r.name, r.sequence) for r in reads).encode()
+    rp = str(tmp_path / "reads.bgz")
+    bgzf.write_bgzf(rp, fa, block_size=700)
+    db = str(tmp_path / "out.index")
+    rc = index_reads.main([str(d), rp, db, "-k", str(k)] + (["-N"] if ignore_paired else []))
+    rows = sorted(sqlite3.connect(db).execute("SELECT offset, cdbg_id FROM sequences").fetchall())
+    src = bgzf.open_reads(rp)
+    names, _, _, pos = bgzf.parse_records(src.data)
+    assert names == [r.name for r in reads]
+    offs = src.virtual_offsets(pos).tolist()
+    otab, _, _ = O.build_mphf(k, lambda: iter(urecs))
+    want, n_paired, total = O.label_reads(zip(reads, offs), otab, k, ignore_paired=ignore_paired)
+    assert rows == sorted(want)
+    assert (n_paired > 0) != ignore_paired
+    assert rc == (0 if max(total) + 1 == len(total) else -1)
