@@ -262,6 +262,19 @@ class MPHF_KmerIndex:
             a[k] = v
         return a
 
+    def sum_by_catlas_node(self, counts_by_cdbg, catlas):
+        """Raw K6: per-catlas-node sums of a per-unitig count vector (dict or dense array), with
+        no assertions -- the per-dominator abundance sums of count_dominator_abundance.py:90-97."""
+        if isinstance(counts_by_cdbg, dict):
+            n = (max(counts_by_cdbg) + 1) if counts_by_cdbg else 0
+            dense = np.zeros(n, np.uint32)
+            for k, v in counts_by_cdbg.items():
+                dense[k] = v
+        else:
+            dense = np.ascontiguousarray(counts_by_cdbg, np.uint32)
+        out, _ = self._sum_over_catlas(dense, catlas)
+        return {v: int(out[v]) for v in catlas}
+
     def build_catlas_node_sizes(self, catlas):
         """Number of k-mers in the shadow of each catlas node (hashing.py:42-65)."""
         out, nodes = self._sum_over_catlas(self._dense_sizes(), catlas)

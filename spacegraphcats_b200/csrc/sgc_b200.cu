@@ -123,6 +123,7 @@ struct TileArgs {
     // MODE_LABEL
     unsigned long long* pairs;
     unsigned long long pairs_cap;
+    unsigned long long zero;  // always 0 (scheduling dependency, see the pipelined probe loop)
 };
 
 // ----------------------------------------------------------------------------------
@@ -353,97 +354,101 @@ __global__ void __launch_bounds__(NT) tile_kernel(const TileArgs a) {
 
         // ---- hash + sink ----
         const int G = sm.gpre[SPC];
-        for (int g0 = 0; g0 < G; g0 += NT) {
-            const int g = g0 + tid;
-            const bool active = g < G;
-            int sg = 0, i = 0, nv = 0;
-            uint64_t h[4] = {0, 0, 0, 0};
-            if (active) {
-                // segment of this group: largest sg with gpre[sg] <= g
-                int lo = 0;
+
+        // locate group g (segment sg, first k-mer i, nv valid k-mers) and hash its 4 k-mers
+        auto locate_and_hash = [&](int g, int& sg, int& i, int& nv, uint64_t (&h)[4]) {
+            // segment of this group: largest sg with gpre[sg] <= g
+            int lo = 0;
 #pragma unroll
-                for (int step = SPC / 2; step > 0; step >>= 1)
-                    if (sm.gpre[lo + step] <= g) lo += step;
-                sg = lo;
-                i = (g - sm.gpre[sg]) << 2;
-                const int nk = sm.nk[sg];
-                nv = nk - i < 4 ? nk - i : 4;
-                const uint32_t* Fs = sm.F + sg * WPS;
-                const uint32_t* Rs = sm.R + sg * WPS;
-                if constexpr (K != 0) {
-                    constexpr int NWIN = sgc::KW<K ? K : 1>::NWIN;
-                    uint32_t fw[NWIN], rw[NWIN];
-                    const uint32_t* fp = Fs + (i >> 2);
-                    const uint32_t* rp = Rs + sgc::rc_group_word(nk, i);
+            for (int step = SPC / 2; step > 0; step >>= 1)
+                if (sm.gpre[lo + step] <= g) lo += step;
+            sg = lo;
+            i = (g - sm.gpre[sg]) << 2;
+            const int nk = sm.nk[sg];
+            nv = nk - i < 4 ? nk - i : 4;
+            const uint32_t* Fs = sm.F + sg * WPS;
+            const uint32_t* Rs = sm.R + sg * WPS;
+            if constexpr (K != 0) {
+                constexpr int NWIN = sgc::KW<K ? K : 1>::NWIN;
+                uint32_t fw[NWIN], rw[NWIN];
+                const uint32_t* fp = Fs + (i >> 2);
+                const uint32_t* rp = Rs + sgc::rc_group_word(nk, i);
 #pragma unroll
-                    for (int j = 0; j < NWIN; j++) {
-                        fw[j] = fp[j];
-                        rw[j] = rp[j];
-                    }
+                for (int j = 0; j < NWIN; j++) {
+                    fw[j] = fp[j];
+                    rw[j] = rp[j];
+                }
 #pragma unroll
-                    for (int t = 0; t < 4; t++) h[t] = sgc::hash_group_kmer<K ? K : 1>(fw, rw, t);
-                } else {
-                    for (int t = 0; t < nv; t++) {
-                        int q = i + t;
-                        h[t] = sgc::murmur3_h1_stream(Fs, q, k) ^
-                               sgc::murmur3_h1_stream(Rs, sgc::rc_byte_of(nk, nk - 1 - q), k);
-                    }
+                for (int t = 0; t < 4; t++) h[t] = sgc::hash_group_kmer<K ? K : 1>(fw, rw, t);
+            } else {
+                for (int t = 0; t < nv; t++) {
+                    int q = i + t;
+                    h[t] = sgc::murmur3_h1_stream(Fs, q, k) ^
+                           sgc::murmur3_h1_stream(Rs, sgc::rc_byte_of(nk, nk - 1 - q), k);
                 }
             }
+        };
 
-            if constexpr (MODE == MODE_HASH) {
-                if (active) {
+        if constexpr (MODE == MODE_HASH || MODE == MODE_INSERT) {
+            for (int g0 = 0; g0 < G; g0 += NT) {
+                const int g = g0 + tid;
+                if (g >= G) continue;
+                int sg, i, nv;
+                uint64_t h[4] = {0, 0, 0, 0};
+                locate_and_hash(g, sg, i, nv, h);
+                if constexpr (MODE == MODE_HASH) {
                     uint64_t* o = a.hash_out + sm.kout[sg] + i;
 #pragma unroll
                     for (int t = 0; t < 4; t++)
                         if (t < nv) o[t] = h[t];
-                }
-            } else if constexpr (MODE == MODE_INSERT) {
-                if (active) {
+                } else {
                     long long sq = sm.seq[sg];
                     uint32_t id = a.seq_ids ? a.seq_ids[sq] : a.id_base + (uint32_t)sq;
                     if (id > SGC_MAX_ID) atomicOr(&a.scal->err, 2);
                     else
                         for (int t = 0; t < nv; t++) table_insert(a.tbl, a.nbuckets, a.home_shift, h[t], id, a.scal);
                 }
-            } else {
-                // MODE_LOOKUP / MODE_LABEL: 4 independent probes in flight per thread
+            }
+        } else {
+            // MODE_LOOKUP / MODE_LABEL, software-pipelined: the 4 table probes of a group are issued
+            // and then left in flight while the NEXT group's 8 Murmur3 evaluations run; they are
+            // resolved one iteration later.  Integer pipe and HBM latency overlap inside a thread.
+            bool p_active = false;
+            int p_sg = 0, p_i = 0, p_nv = 0;
+            uint64_t p_h[4] = {0, 0, 0, 0};
+            uint32_t p_b[4] = {0, 0, 0, 0};
+            Entry p_e0[4], p_e1[4];
+
+            auto resolve = [&]() {
                 uint32_t ids[4] = {SGC_MISS, SGC_MISS, SGC_MISS, SGC_MISS};
-                if (active) {
-                    uint32_t b[4];
-                    Entry e0[4], e1[4];
+                if (p_active) {
 #pragma unroll
                     for (int t = 0; t < 4; t++) {
-                        b[t] = home_bucket(h[t], a.nbuckets, a.home_shift);
-                        if (t < nv) load_bucket_nc(a.tbl + b[t], e0[t], e1[t]);
-                    }
-#pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        if (t < nv) {
-                            ids[t] = lookup_resolve(a.tbl, a.nbuckets, b[t], h[t], e0[t], e1[t]);
+                        if (t < p_nv) {
+                            ids[t] = lookup_resolve(a.tbl, a.nbuckets, p_b[t], p_h[t], p_e0[t], p_e1[t]);
                             if (ids[t] != SGC_MISS) my_hits++; else my_miss++;
                         }
                     }
                 }
                 if constexpr (MODE == MODE_LOOKUP) {
-                    if (active) {
+                    if (p_active) {
                         if (a.kmer_ids) {
-                            uint32_t* o = a.kmer_ids + sm.kout[sg] + i;
+                            uint32_t* o = a.kmer_ids + sm.kout[p_sg] + p_i;
 #pragma unroll
                             for (int t = 0; t < 4; t++)
-                                if (t < nv) o[t] = ids[t];
+                                if (t < p_nv) o[t] = ids[t];
                         }
                         if (a.count_by_id) {
                             // run-length aggregate within the group before touching L2
 #pragma unroll
                             for (int t = 0; t < 4; t++) {
-                                if (t < nv && ids[t] != SGC_MISS) {
+                                if (t < p_nv && ids[t] != SGC_MISS) {
                                     unsigned run = 1;
                                     bool counted = false;
 #pragma unroll
                                     for (int u = 0; u < 4; u++) {
                                         if (u < t && ids[u] == ids[t]) counted = true;
-                                        if (u > t && u < nv && ids[u] == ids[t]) run++;
+                                        if (u > t && u < p_nv && ids[u] == ids[t]) run++;
                                     }
                                     if (!counted) atomicAdd(&a.count_by_id[ids[t]], run);
                                 }
@@ -452,15 +457,21 @@ __global__ void __launch_bounds__(NT) tile_kernel(const TileArgs a) {
                     }
                 } else {
                     // MODE_LABEL: candidate = hit whose predecessor k-mer (same segment) has another id
-                    uint32_t prev_lane = __shfl_up_sync(0xffffffffu, ids[3], 1);
-                    unsigned long long keys[4];
+                    const uint32_t prev_lane = __shfl_up_sync(0xffffffffu, ids[3], 1);
+                    unsigned long long keys[4] = {0, 0, 0, 0};
                     unsigned nc = 0;
-                    if (active) {
-                        const unsigned long long sq = (unsigned long long)sm.seq[sg] << 32;
-                        uint32_t prev = (i > 0 && lane > 0) ? prev_lane : SGC_MISS;
+                    if (p_active) {
+                        const unsigned long long sq = (unsigned long long)sm.seq[p_sg] << 32;
+                        uint32_t prev = (p_i > 0 && lane > 0) ? prev_lane : SGC_MISS;
 #pragma unroll
                         for (int t = 0; t < 4; t++) {
-                            if (t < nv && ids[t] != SGC_MISS && ids[t] != prev) keys[nc++] = sq | ids[t];
+                            if (t < p_nv && ids[t] != SGC_MISS && ids[t] != prev) {
+                                // nc is at most t: constant-indexed writes keep keys[] in registers
+#pragma unroll
+                                for (int u = 0; u < 4; u++)
+                                    if (u == (int)nc) keys[u] = sq | ids[t];
+                                nc++;
+                            }
                             prev = ids[t];
                         }
                     }
@@ -484,16 +495,45 @@ __global__ void __launch_bounds__(NT) tile_kernel(const TileArgs a) {
                         gover = __shfl_sync(0xffffffffu, gover, 31);
                         const unsigned first_over = base > PAIR_BUF ? base : PAIR_BUF;
                         unsigned pos = base + incl - nc;
-                        for (unsigned j = 0; j < nc; j++, pos++) {
-                            if (pos < PAIR_BUF) s_pairs[pos] = keys[j];
-                            else {
-                                unsigned long long gp = gover + (pos - first_over);
-                                if (gp < a.pairs_cap) a.pairs[gp] = keys[j];
+#pragma unroll
+                        for (unsigned j = 0; j < 4; j++) {
+                            if (j < nc) {
+                                if (pos < PAIR_BUF) s_pairs[pos] = keys[j];
+                                else {
+                                    unsigned long long gp = gover + (pos - first_over);
+                                    if (gp < a.pairs_cap) a.pairs[gp] = keys[j];
+                                }
+                                pos++;
                             }
                         }
                     }
                 }
+            };
+
+            for (int g0 = 0; g0 < G; g0 += NT) {
+                const int g = g0 + tid;
+                const bool active = g < G;
+                int sg = 0, i = 0, nv = 0;
+                uint64_t h[4] = {0, 0, 0, 0};
+                if (active) locate_and_hash(g, sg, i, nv, h);   // previous group's probes are in flight here
+                // Order the resolve AFTER the hash computation in the instruction stream: a.zero is
+                // always 0 but only known at run time, so the compare below truly depends on the new
+                // hashes and neither nvcc nor ptxas can sink the Murmur3 code under the resolve.
+                {
+                    const uint64_t dep = (h[0] ^ h[1] ^ h[2] ^ h[3]) & a.zero;
+#pragma unroll
+                    for (int t = 0; t < 4; t++) p_h[t] ^= dep;
+                }
+                if (g0 > 0) resolve();
+                p_active = active; p_sg = sg; p_i = i; p_nv = nv;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    p_h[t] = h[t];
+                    p_b[t] = home_bucket(h[t], a.nbuckets, a.home_shift);
+                    if (active && t < nv) load_bucket_nc(a.tbl + p_b[t], p_e0[t], p_e1[t]);
+                }
             }
+            if (G > 0) resolve();
         }
 
         if constexpr (MODE == MODE_LABEL) {

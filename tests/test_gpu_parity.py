@@ -258,7 +258,8 @@ def test_label_reads_dory_vs_oracle(ctx, O, dory, dory_index, dory_reads):
     assert (res["n_kmers"], res["n_hits"]) == (o_nk, o_nh) == (240920, 240920)
     # SURVEY 8c derived pin: 537 reads -> 907 (read, id) pairs
     assert len(dory_reads) == 537 and len(res["ids"]) == 907
-    lines = sorted("%d,%d\n" % (i, c) for i in range(537) for c in res["ids"][res["ids_off"][i] : res["ids_off"][i + 1]])
+    pairs = sorted((i, int(c)) for i in range(537) for c in res["ids"][res["ids_off"][i] : res["ids_off"][i + 1]])
+    lines = ["%d,%d\n" % p for p in pairs]
     assert hashlib.sha256("".join(lines).encode()).hexdigest() == \
         "933dbab55d9262d91ce6f3fe4c883957480e4f22e6d9ff503a44ee24d3ea7c90"
     assert set(res["ids"].tolist()) == set(range(736))  # test_dory_index_reads: rc == 0
@@ -409,8 +410,9 @@ def test_dominator_abundance_totals(O, dory, dory_index, dory_catlas):
     _, ref_h, ref_v, ref_sizes = dory
     want_cdbg, want_dom = O.dominator_abundance(recs, O.OracleTable.from_arrays(ref_h, ref_v), 21, ocat)
     assert {k: v for k, v in cdbg_counts.items() if v} == want_cdbg
-    got_dom = dory_index.count_catlas_matches({k: v for k, v in cdbg_counts.items() if v}, dory_catlas)
-    assert {d: got_dom.get(d, 0) for d in want_dom} == want_dom
+    got_dom = dory_index.sum_by_catlas_node(res["count_by_id"], dory_catlas)
+    assert {d: got_dom[d] for d in want_dom} == want_dom
+    assert got_dom[dory_catlas.root] == 240920
     assert sum(want_dom.values()) == 240920 and sum(ref_sizes.values()) == 212475
 
 
