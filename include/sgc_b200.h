@@ -75,11 +75,12 @@ int sgc_hash_batch(sgc_ctx* ctx, const uint8_t* d_seq, int64_t seq_bytes, const 
 /*
  * K2 -- replaces BBHashTable() + .initialize(list(all_kmers)) + table[kmer] = cdbg_id,
  * i.e. build_mphf(), cdbg/index_cdbg_by_kmer.py:27-115.
- * sgc_table_create sizes an empty table for up to max_entries distinct hashes.
+ * sgc_table_create sizes an empty table for up to max_entries distinct hashes; load = expected
+ * hashes per 32-byte bucket (0 = default 0.75; memory = 32 B * max_entries / load).
  * Insertion semantics are build_mphf's: a hash inserted with two DIFFERENT ids is
  * dropped from the map for good (multicount, :40-57); the same (hash, id) again is a no-op.
  */
-int sgc_table_create(sgc_ctx* ctx, int64_t max_entries, sgc_table** out);
+int sgc_table_create(sgc_ctx* ctx, int64_t max_entries, float load, sgc_table** out);
 void sgc_table_free(sgc_table* t);
 /* insert n (hash, id) pairs; also how a reference-written contigs.indices
  * (mphf_to_hash, mphf_to_value; BBHashTable.load, cdbg/hashing.py:126) is loaded. */

@@ -58,9 +58,10 @@ int fail(int code, const char* fmt, ...) {
 // tile geometry
 // ----------------------------------------------------------------------------------
 constexpr int NT = 256;         // threads per CTA
-constexpr int SPC = 32;         // segments staged per round (one warp builds the descriptors)
+constexpr int WPB = NT / 32;    // warps per CTA; every warp runs its own rounds (no block barriers)
+constexpr int SPW = 8;          // segments staged per warp round (4 lanes stage one segment)
 constexpr int SEG_K = 256;      // k-mers per segment
-constexpr int PAIR_BUF = 2048;  // label pairs staged in shared memory per round
+constexpr int PAIR_BUF = 128;   // label keys staged per warp before one global reservation
 constexpr unsigned long long SEQ_MASK = (1ULL << 40) - 1ULL;
 
 constexpr uint32_t VAL_EMPTY = 0xFFFFFFFFu;
@@ -76,10 +77,15 @@ struct Geo {
     static constexpr int WPS = STRIDE / 4;
 };
 
+// The table: 32-byte buckets of two 16-byte slots; four buckets share a 128-byte line (the unit
+// HBM actually moves per random access on B200: measured).  A key lives at probe
+// step s >= 0 from its home bucket hb: steps 1..3 are the other buckets of the home line, steps
+// 4.. walk the following lines.  flg of slot 0 of the HOME bucket holds the largest step any key
+// homed there was placed at, so a lookup knows exactly how far to look (0 = home only).
 struct __align__(16) Entry {
     unsigned long long key;
     unsigned int val;  // VAL_EMPTY = free slot, VAL_MULTI = dropped hash, else unitig id
-    unsigned int flg;  // entry 0 of a bucket: bit 0 = some key overflowed past this bucket
+    unsigned int flg;  // slot 0 of a bucket: max probe step of the keys homed in this bucket
 };
 struct __align__(32) Bucket {
     Entry e[2];
@@ -114,6 +120,7 @@ struct TileArgs {
     // table (MODE_INSERT / MODE_LOOKUP / MODE_LABEL)
     Bucket* tbl;
     uint32_t nbuckets;
+    uint32_t nlines;
     int home_shift;
     const uint32_t* seq_ids;
     uint32_t id_base;
@@ -131,6 +138,12 @@ struct TileArgs {
 // ----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t home_bucket(uint64_t h, uint32_t nb, int home_shift) {
     return __umulhi((uint32_t)((h << home_shift) >> 32), nb);
+}
+
+__device__ __forceinline__ uint32_t probe_bucket(uint32_t hb, uint32_t step, uint32_t nlines) {
+    uint32_t line = (hb >> 2) + (step >> 2);
+    if (line >= nlines) line -= nlines;
+    return (line << 2) | ((hb + step) & 3u);
 }
 
 // one 32-byte sector, read-only path, no L1 allocation (random access, no reuse)
@@ -166,62 +179,75 @@ __device__ __forceinline__ bool cas_entry(Entry* p, const Entry& expect, const E
 
 __device__ __forceinline__ uint32_t resolve_val(uint32_t v) { return v >= VAL_MULTI ? SGC_MISS : v; }
 
-// Slow path of a lookup: continue from bucket b (already examined, overflow flag set).
-__device__ __noinline__ uint32_t lookup_overflow(const Bucket* tbl, uint32_t nb, uint32_t b, uint64_t h) {
-    for (uint32_t probes = 1; probes < nb; probes++) {
-        b = (b + 1 == nb) ? 0u : b + 1;
+__device__ __forceinline__ bool bucket_match(const Entry& e0, const Entry& e1, uint64_t h, uint32_t& out) {
+    if (e0.key == h && e0.val != VAL_EMPTY) { out = resolve_val(e0.val); return true; }
+    if (e1.key == h && e1.val != VAL_EMPTY) { out = resolve_val(e1.val); return true; }
+    return false;
+}
+
+// Slow path of a lookup (the home bucket did not hold the key and its max-step is > 0): the other
+// three buckets of the home line are read together (the line is already in L2: HBM moved all
+// 128 bytes), then, rarely, the following lines.
+__device__ __noinline__ uint32_t lookup_slow(const Bucket* tbl, uint32_t nlines, uint32_t hb, uint32_t maxstep,
+                                             uint64_t h) {
+    Entry a0[3], a1[3];
+#pragma unroll
+    for (uint32_t s = 1; s <= 3; s++)
+        if (s <= maxstep) load_bucket_nc(tbl + probe_bucket(hb, s, nlines), a0[s - 1], a1[s - 1]);
+    uint32_t out;
+#pragma unroll
+    for (uint32_t s = 1; s <= 3; s++)
+        if (s <= maxstep && bucket_match(a0[s - 1], a1[s - 1], h, out)) return out;
+    for (uint32_t s = 4; s <= maxstep; s++) {
         Entry e0, e1;
-        load_bucket_nc(tbl + b, e0, e1);
-        if (e0.key == h && e0.val != VAL_EMPTY) return resolve_val(e0.val);
-        if (e1.key == h && e1.val != VAL_EMPTY) return resolve_val(e1.val);
-        if (!(e0.flg & 1u)) return SGC_MISS;
+        load_bucket_nc(tbl + probe_bucket(hb, s, nlines), e0, e1);
+        if (bucket_match(e0, e1, h, out)) return out;
     }
     return SGC_MISS;
 }
 
-__device__ __forceinline__ uint32_t lookup_resolve(const Bucket* tbl, uint32_t nb, uint32_t b, uint64_t h,
-                                                   const Entry& e0, const Entry& e1) {
-    if (e0.key == h && e0.val != VAL_EMPTY) return resolve_val(e0.val);
-    if (e1.key == h && e1.val != VAL_EMPTY) return resolve_val(e1.val);
-    if (!(e0.flg & 1u)) return SGC_MISS;
-    return lookup_overflow(tbl, nb, b, h);
-}
-
-__device__ __forceinline__ uint32_t table_lookup(const Bucket* tbl, uint32_t nb, int hs, uint64_t h) {
-    uint32_t b = home_bucket(h, nb, hs);
+__device__ __forceinline__ uint32_t table_lookup(const Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, uint64_t h) {
+    uint32_t hb = home_bucket(h, nb, hs);
     Entry e0, e1;
-    load_bucket_nc(tbl + b, e0, e1);
-    return lookup_resolve(tbl, nb, b, h, e0, e1);
+    load_bucket_nc(tbl + hb, e0, e1);
+    uint32_t out;
+    if (bucket_match(e0, e1, h, out)) return out;
+    if (e0.flg == 0) return SGC_MISS;
+    return lookup_slow(tbl, nlines, hb, e0.flg, h);
 }
 
 // build_mphf insertion semantics (cdbg/index_cdbg_by_kmer.py:40-57, 88-89):
 //   new hash -> stored with id;  same hash, same id -> no-op;
 //   same hash, different id -> the hash is dropped for good (VAL_MULTI).
-// The outcome is independent of the order in which threads arrive.
-__device__ void table_insert(Bucket* tbl, uint32_t nb, int hs, uint64_t h, uint32_t id, Scalars* scal) {
-    uint32_t b = home_bucket(h, nb, hs);
+// The outcome is independent of the order in which threads arrive: slots only ever go from
+// empty to occupied, every thread walks the same probe sequence, and a lost CAS re-examines
+// what the winner wrote.
+__device__ void table_insert(Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, uint64_t h, uint32_t id,
+                             Scalars* scal) {
+    const uint32_t hb = home_bucket(h, nb, hs);
     const Entry empty{0ULL, VAL_EMPTY, 0u};
     const Entry mine{h, id, 0u};
-    for (uint32_t probes = 0; probes < nb; probes++) {
-        Bucket* bp = tbl + b;
-        unsigned flg0 = 0;
+    const uint32_t max_steps = nlines > (1u << 20) ? (4u << 20) : nlines * 4u;
+    for (uint32_t step = 0; step < max_steps; step++) {
+        Bucket* bp = tbl + probe_bucket(hb, step, nlines);
 #pragma unroll
         for (int s = 0; s < 2; s++) {
             Entry e;
             load_entry_volatile(&bp->e[s], e);
+            bool placed = false;
             if (e.val == VAL_EMPTY) {
                 Entry old;
-                if (cas_entry(&bp->e[s], empty, mine, old)) return;
-                e = old;  // somebody else claimed the slot first: examine what they wrote
+                if (cas_entry(&bp->e[s], empty, mine, old)) placed = true;
+                else e = old;  // somebody else claimed the slot first: examine what they wrote
             }
-            if (e.key == h) {
-                if (e.val != id && e.val != VAL_MULTI) atomicExch(&bp->e[s].val, VAL_MULTI);
+            if (placed || e.key == h) {
+                if (!placed && e.val != id && e.val != VAL_MULTI) atomicExch(&bp->e[s].val, VAL_MULTI);
+                // publish how far this key sits from home (its home bucket is full by now, so its
+                // slot 0 is occupied and never CAS-ed again)
+                if (step) atomicMax(&tbl[hb].e[0].flg, step);
                 return;
             }
-            if (s == 0) flg0 = e.flg;
         }
-        if (!(flg0 & 1u)) atomicOr(&bp->e[0].flg, 1u);
-        b = (b + 1 == nb) ? 0u : b + 1;
     }
     atomicOr(&scal->err, 1);
 }
@@ -251,123 +277,172 @@ __global__ void plan_expand_kernel(const int64_t* __restrict__ seg_first, int64_
 }
 
 // ----------------------------------------------------------------------------------
-// the tile kernel: stage SPC segments (forward + reverse complement), then every thread
-// hashes groups of 4 consecutive k-mers and feeds them to the mode's sink.
+// staging helpers
+// ----------------------------------------------------------------------------------
+// bytes F[f .. f+4) of a segment whose Ls bases start at global byte address `base`; bytes outside
+// [0, Ls) read as 0 and no aligned word that lies wholly outside the segment is touched.
+__device__ __forceinline__ uint32_t load_window4(uintptr_t base, int f, int Ls, uint32_t& mask) {
+    const int lo_clip = f < 0 ? -f : 0;
+    const int hi_clip = f + 4 > Ls ? f + 4 - Ls : 0;
+    if (lo_clip >= 4 || hi_clip >= 4) { mask = 0; return 0; }
+    mask = (0xFFFFFFFFu << (8 * lo_clip)) & (0xFFFFFFFFu >> (8 * hi_clip));
+    const uintptr_t addr = base + (intptr_t)f;
+    const int s = (int)(addr & 3);
+    const uintptr_t a0 = addr - s;
+    const uintptr_t first = base, last = base + (uintptr_t)Ls;  // valid byte range [first, last)
+    uint32_t lo = 0, hi = 0;
+    if (a0 + 4 > first && a0 < last) lo = __ldg((const uint32_t*)a0);
+    if (s && a0 + 8 > first && a0 + 4 < last) hi = __ldg((const uint32_t*)(a0 + 4));
+    return sgc::funnel_bytes(lo, hi, s) & mask;
+}
+
+// reverse complement of 4 packed bases (byte-reversed, A<->T, C<->G); ok = every byte selected by
+// mask is one of A, C, G, T.  Bytes that are not pass through unchanged (oracle rule).
+__device__ __forceinline__ uint32_t revcomp_word(uint32_t u, uint32_t mask, bool& ok) {
+    // 2-bit code per base from ASCII bits 1..2: A=0 C=1 T=2 G=3
+    const uint32_t code = (u >> 1) & 0x03030303u;
+    const uint32_t t = code | (code >> 4);
+    const uint32_t sel = (t & 0xFFu) | ((t >> 8) & 0xFF00u);
+    const uint32_t expect = __byte_perm(0x47544341u, 0u, sel);   // "ACTG"[code]
+    uint32_t comp = __byte_perm(0x43414754u, 0u, sel);           // "TGAC"[code]
+    ok = ((expect ^ u) & mask) == 0;
+    if (!ok) {
+        comp = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) comp |= (uint32_t)sgc::comp_base((uint8_t)(u >> (8 * b))) << (8 * b);
+    }
+    return __byte_perm(comp & mask, 0u, 0x0123u);
+}
+
+// ----------------------------------------------------------------------------------
+// the tile kernel.  Every WARP runs its own rounds: fetch SPW segments, stage their forward and
+// reverse-complement bytes in its slice of shared memory (4 lanes per segment), then each lane
+// hashes groups of 4 consecutive k-mers and feeds them to the mode's sink.  No block barriers:
+// warps drift apart, so one warp's exposed latencies (round fetch, staging loads, table probes)
+// are covered by the other warps of the SM.
 // ----------------------------------------------------------------------------------
 template <int K>
-struct TileSmem {
-    uint32_t F[SPC * Geo<K>::WPS];
-    uint32_t R[SPC * Geo<K>::WPS];
-    long long start[SPC];
-    long long seq[SPC];
-    long long kout[SPC];
-    int nk[SPC];
-    int gpre[SPC + 1];
-    int round;
-    unsigned pair_n;
-    unsigned long long pair_base;
+struct WarpTile {
+    uint32_t F[SPW * Geo<K>::WPS];
+    uint32_t R[SPW * Geo<K>::WPS];
+    unsigned long long pairs[PAIR_BUF];
+    long long start[SPW];
+    long long seq[SPW];
+    long long kout[SPW];
+    int nk[SPW];
+    int gpre[SPW + 1];
+    int pad[3];
 };
 
 template <int K, int MODE>
 __global__ void __launch_bounds__(NT) tile_kernel(const TileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileSmem<K>& sm = *reinterpret_cast<TileSmem<K>*>(smem_raw);
-    unsigned long long* s_pairs = reinterpret_cast<unsigned long long*>(smem_raw + sizeof(TileSmem<K>));
     constexpr int WPS = Geo<K>::WPS;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
+    const int lane = threadIdx.x & 31;
+    WarpTile<K>& wt = reinterpret_cast<WarpTile<K>*>(smem_raw)[threadIdx.x >> 5];
     const int k = K ? K : a.k;
     const int64_t nsegs = *a.nsegs_p;
+    const int64_t nrounds = (nsegs + SPW - 1) / SPW;
     unsigned long long my_hits = 0, my_miss = 0;
+    unsigned pair_fill = 0;  // warp-uniform: keys waiting in wt.pairs
+
+    auto flush_pairs = [&]() {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&a.scal->pair_count, (unsigned long long)pair_fill);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (unsigned j = lane; j < pair_fill; j += 32)
+            if (base + j < a.pairs_cap) a.pairs[base + j] = wt.pairs[j];
+        __syncwarp();
+        pair_fill = 0;
+    };
+
+    // dynamic round scheduling; the NEXT round index is always requested one round ahead
+    unsigned next_round = 0;
+    if (lane == 0) next_round = atomicAdd(&a.scal->round_ctr, 1u);
 
     for (;;) {
-        if (tid == 0) {
-            sm.round = (int)atomicAdd(&a.scal->round_ctr, 1u);
-            sm.pair_n = 0;
-        }
-        __syncthreads();
-        const int64_t seg0 = (int64_t)sm.round * SPC;
-        if (seg0 >= nsegs) break;
+        const unsigned round = __shfl_sync(0xffffffffu, next_round, 0);
+        if ((int64_t)round >= nrounds) break;
+        if (lane == 0) next_round = atomicAdd(&a.scal->round_ctr, 1u);
+        const int64_t seg0 = (int64_t)round * SPW;
 
-        // ---- descriptors (warp 0) ----
-        if (tid < SPC) {
-            int64_t g = seg0 + tid;
+        // ---- descriptors (lanes 0..SPW-1) ----
+        {
             int nk = 0;
             long long start = 0, sq = 0, kout = 0;
-            if (g < nsegs) {
-                unsigned long long e = (unsigned long long)a.seg_map[g];
+            const int64_t g = seg0 + lane;
+            if (lane < SPW && g < nsegs) {
+                const unsigned long long e = (unsigned long long)a.seg_map[g];
                 sq = (long long)(e & SEQ_MASK);
-                long long sn = (long long)(e >> 40);
-                long long o0 = a.off[sq], o1 = a.off[sq + 1];
-                long long nkseq = o1 - o0 - k + 1;
-                long long q0 = sn * SEG_K;
-                long long rem = nkseq - q0;
+                const long long sn = (long long)(e >> 40);
+                const long long o0 = a.off[sq], o1 = a.off[sq + 1];
+                const long long q0 = sn * SEG_K;
+                const long long rem = o1 - o0 - k + 1 - q0;
                 nk = (int)(rem < SEG_K ? rem : SEG_K);
                 start = o0 + q0;
                 if (a.kmer_off) kout = a.kmer_off[sq] + q0;
             }
-            sm.start[tid] = start;
-            sm.seq[tid] = sq;
-            sm.kout[tid] = kout;
-            sm.nk[tid] = nk;
-            int groups = (nk + 3) >> 2;
-            int incl = groups;
+            int incl = (nk + 3) >> 2;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
+            for (int d = 1; d < SPW; d <<= 1) {
                 int v = __shfl_up_sync(0xffffffffu, incl, d);
                 if (lane >= d) incl += v;
             }
-            sm.gpre[tid + 1] = incl;
-            if (tid == 0) sm.gpre[0] = 0;
+            if (lane < SPW) {
+                wt.start[lane] = start;
+                wt.seq[lane] = sq;
+                wt.kout[lane] = kout;
+                wt.nk[lane] = nk;
+                wt.gpre[lane + 1] = incl;
+            }
+            if (lane == 0) wt.gpre[0] = 0;
         }
-        __syncthreads();
+        __syncwarp();
 
-        // ---- stage forward bytes: word w of segment sg = bases [4w, 4w+4) ----
-        for (int idx = tid; idx < SPC * WPS; idx += NT) {
-            int sg = idx / WPS, w = idx - sg * WPS;
-            int nk = sm.nk[sg];
-            int Ls = nk ? nk + k - 1 : 0;
-            if (4 * w < Ls) {
-                uintptr_t addr = (uintptr_t)a.seq + (uintptr_t)sm.start[sg] + 4u * (unsigned)w;
-                int s = (int)(addr & 3);
-                const uint32_t* ap = (const uint32_t*)(addr - s);
-                uint32_t lo = __ldg(ap);
-                uint32_t hi = 0;
-                if (s && (4 * w + 4 - s) < Ls) hi = __ldg(ap + 1);
-                sm.F[idx] = sgc::funnel_bytes(lo, hi, s);
+        // ---- stage forward + reverse-complement words straight from global memory ----
+        {
+            const int sg = lane >> 2, sub = lane & 3;
+            const int nk = wt.nk[sg];
+            if (nk) {
+                const int Ls = nk + k - 1;
+                const uintptr_t base = (uintptr_t)a.seq + (uintptr_t)wt.start[sg];
+                uint32_t* Fs = wt.F + sg * WPS;
+                uint32_t* Rs = wt.R + sg * WPS;
+                const int p = sgc::rc_pad(nk);
+                bool all_ok = true;
+                for (int w = sub; 4 * w < Ls; w += 4) {
+                    uint32_t mask;
+                    Fs[w] = load_window4(base, 4 * w, Ls, mask);
+                }
+                // R word m holds R[4m-4-p .. +4) = revcomp of F[Ls-4m+p .. +4)
+                const int nrw = (Ls + 4 + p + 3) >> 2;
+                for (int m = sub; m < nrw; m += 4) {
+                    uint32_t mask;
+                    const uint32_t u = load_window4(base, Ls - 4 * m + p, Ls, mask);
+                    bool ok;
+                    Rs[m] = revcomp_word(u, mask, ok);
+                    all_ok &= ok;
+                }
+                if (!all_ok && a.status) atomicOr(&a.status[wt.seq[sg]], 1);
             }
         }
-        __syncthreads();
-
-        // ---- stage the reverse complement (and flag non-ACGT bytes) ----
-        for (int idx = tid; idx < SPC * WPS; idx += NT) {
-            int sg = idx / WPS, m = idx - sg * WPS;
-            int nk = sm.nk[sg];
-            int Ls = nk ? nk + k - 1 : 0;
-            if (nk && 4 * m < Ls + 8) {
-                bool invalid = false;
-                sm.R[idx] = sgc::rc_word((const uint8_t*)(sm.F + sg * WPS), Ls, nk, m, &invalid);
-                if (invalid && a.status) atomicOr(&a.status[sm.seq[sg]], 1);
-            }
-        }
-        __syncthreads();
+        __syncwarp();
 
         // ---- hash + sink ----
-        const int G = sm.gpre[SPC];
+        const int G = wt.gpre[SPW];
 
         // locate group g (segment sg, first k-mer i, nv valid k-mers) and hash its 4 k-mers
         auto locate_and_hash = [&](int g, int& sg, int& i, int& nv, uint64_t (&h)[4]) {
-            // segment of this group: largest sg with gpre[sg] <= g
-            int lo = 0;
+            int lo = 0;  // largest sg with gpre[sg] <= g
 #pragma unroll
-            for (int step = SPC / 2; step > 0; step >>= 1)
-                if (sm.gpre[lo + step] <= g) lo += step;
+            for (int step = SPW / 2; step > 0; step >>= 1)
+                if (wt.gpre[lo + step] <= g) lo += step;
             sg = lo;
-            i = (g - sm.gpre[sg]) << 2;
-            const int nk = sm.nk[sg];
+            i = (g - wt.gpre[sg]) << 2;
+            const int nk = wt.nk[sg];
             nv = nk - i < 4 ? nk - i : 4;
-            const uint32_t* Fs = sm.F + sg * WPS;
-            const uint32_t* Rs = sm.R + sg * WPS;
+            const uint32_t* Fs = wt.F + sg * WPS;
+            const uint32_t* Rs = wt.R + sg * WPS;
             if constexpr (K != 0) {
                 constexpr int NWIN = sgc::KW<K ? K : 1>::NWIN;
                 uint32_t fw[NWIN], rw[NWIN];
@@ -390,29 +465,30 @@ __global__ void __launch_bounds__(NT) tile_kernel(const TileArgs a) {
         };
 
         if constexpr (MODE == MODE_HASH || MODE == MODE_INSERT) {
-            for (int g0 = 0; g0 < G; g0 += NT) {
-                const int g = g0 + tid;
+            for (int g0 = 0; g0 < G; g0 += 32) {
+                const int g = g0 + lane;
                 if (g >= G) continue;
                 int sg, i, nv;
                 uint64_t h[4] = {0, 0, 0, 0};
                 locate_and_hash(g, sg, i, nv, h);
                 if constexpr (MODE == MODE_HASH) {
-                    uint64_t* o = a.hash_out + sm.kout[sg] + i;
+                    uint64_t* o = a.hash_out + wt.kout[sg] + i;
 #pragma unroll
                     for (int t = 0; t < 4; t++)
                         if (t < nv) o[t] = h[t];
                 } else {
-                    long long sq = sm.seq[sg];
+                    long long sq = wt.seq[sg];
                     uint32_t id = a.seq_ids ? a.seq_ids[sq] : a.id_base + (uint32_t)sq;
                     if (id > SGC_MAX_ID) atomicOr(&a.scal->err, 2);
                     else
-                        for (int t = 0; t < nv; t++) table_insert(a.tbl, a.nbuckets, a.home_shift, h[t], id, a.scal);
+                        for (int t = 0; t < nv; t++)
+                            table_insert(a.tbl, a.nbuckets, a.nlines, a.home_shift, h[t], id, a.scal);
                 }
             }
         } else {
             // MODE_LOOKUP / MODE_LABEL, software-pipelined: the 4 table probes of a group are issued
-            // and then left in flight while the NEXT group's 8 Murmur3 evaluations run; they are
-            // resolved one iteration later.  Integer pipe and HBM latency overlap inside a thread.
+            // and left in flight while the NEXT group's 8 Murmur3 evaluations run; they are resolved
+            // one iteration later.  Integer pipe and HBM latency overlap inside a thread.
             bool p_active = false;
             int p_sg = 0, p_i = 0, p_nv = 0;
             uint64_t p_h[4] = {0, 0, 0, 0};
@@ -421,19 +497,28 @@ __global__ void __launch_bounds__(NT) tile_kernel(const TileArgs a) {
 
             auto resolve = [&]() {
                 uint32_t ids[4] = {SGC_MISS, SGC_MISS, SGC_MISS, SGC_MISS};
-                if (p_active) {
+                unsigned slow = 0;
 #pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        if (t < p_nv) {
-                            ids[t] = lookup_resolve(a.tbl, a.nbuckets, p_b[t], p_h[t], p_e0[t], p_e1[t]);
-                            if (ids[t] != SGC_MISS) my_hits++; else my_miss++;
-                        }
+                for (int t = 0; t < 4; t++) {
+                    if (p_active && t < p_nv) {
+                        uint32_t v;
+                        if (bucket_match(p_e0[t], p_e1[t], p_h[t], v)) ids[t] = v;
+                        else if (p_e0[t].flg) slow |= 1u << t;
                     }
                 }
+                if (slow) {  // rare per lane: keys that overflowed their home bucket
+#pragma unroll
+                    for (int t = 0; t < 4; t++)
+                        if (slow & (1u << t)) ids[t] = lookup_slow(a.tbl, a.nlines, p_b[t], p_e0[t].flg, p_h[t]);
+                }
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+                    if (p_active && t < p_nv) { if (ids[t] != SGC_MISS) my_hits++; else my_miss++; }
+
                 if constexpr (MODE == MODE_LOOKUP) {
                     if (p_active) {
                         if (a.kmer_ids) {
-                            uint32_t* o = a.kmer_ids + sm.kout[p_sg] + p_i;
+                            uint32_t* o = a.kmer_ids + wt.kout[p_sg] + p_i;
 #pragma unroll
                             for (int t = 0; t < 4; t++)
                                 if (t < p_nv) o[t] = ids[t];
@@ -461,14 +546,13 @@ __global__ void __launch_bounds__(NT) tile_kernel(const TileArgs a) {
                     unsigned long long keys[4] = {0, 0, 0, 0};
                     unsigned nc = 0;
                     if (p_active) {
-                        const unsigned long long sq = (unsigned long long)sm.seq[p_sg] << 32;
+                        const unsigned long long sq = (unsigned long long)wt.seq[p_sg] << 32;
                         uint32_t prev = (p_i > 0 && lane > 0) ? prev_lane : SGC_MISS;
 #pragma unroll
                         for (int t = 0; t < 4; t++) {
                             if (t < p_nv && ids[t] != SGC_MISS && ids[t] != prev) {
-                                // nc is at most t: constant-indexed writes keep keys[] in registers
 #pragma unroll
-                                for (int u = 0; u < 4; u++)
+                                for (int u = 0; u < 4; u++)  // constant indices keep keys[] in registers
                                     if (u == (int)nc) keys[u] = sq | ids[t];
                                 nc++;
                             }
@@ -483,41 +567,24 @@ __global__ void __launch_bounds__(NT) tile_kernel(const TileArgs a) {
                     }
                     const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
                     if (total) {
-                        unsigned base = 0;
-                        unsigned long long gover = 0;
-                        if (lane == 31) {
-                            base = atomicAdd(&sm.pair_n, total);
-                            unsigned first_over = base > PAIR_BUF ? base : PAIR_BUF;
-                            if (base + total > first_over)
-                                gover = atomicAdd(&a.scal->pair_count, (unsigned long long)(base + total - first_over));
-                        }
-                        base = __shfl_sync(0xffffffffu, base, 31);
-                        gover = __shfl_sync(0xffffffffu, gover, 31);
-                        const unsigned first_over = base > PAIR_BUF ? base : PAIR_BUF;
-                        unsigned pos = base + incl - nc;
+                        if (pair_fill + total > PAIR_BUF) flush_pairs();
+                        unsigned pos = pair_fill + incl - nc;
 #pragma unroll
-                        for (unsigned j = 0; j < 4; j++) {
-                            if (j < nc) {
-                                if (pos < PAIR_BUF) s_pairs[pos] = keys[j];
-                                else {
-                                    unsigned long long gp = gover + (pos - first_over);
-                                    if (gp < a.pairs_cap) a.pairs[gp] = keys[j];
-                                }
-                                pos++;
-                            }
-                        }
+                        for (unsigned j = 0; j < 4; j++)
+                            if (j < nc) wt.pairs[pos++] = keys[j];
+                        pair_fill += total;
                     }
                 }
             };
 
-            for (int g0 = 0; g0 < G; g0 += NT) {
-                const int g = g0 + tid;
+            for (int g0 = 0; g0 < G; g0 += 32) {
+                const int g = g0 + lane;
                 const bool active = g < G;
                 int sg = 0, i = 0, nv = 0;
                 uint64_t h[4] = {0, 0, 0, 0};
                 if (active) locate_and_hash(g, sg, i, nv, h);   // previous group's probes are in flight here
                 // Order the resolve AFTER the hash computation in the instruction stream: a.zero is
-                // always 0 but only known at run time, so the compare below truly depends on the new
+                // always 0 but only known at run time, so the compares below truly depend on the new
                 // hashes and neither nvcc nor ptxas can sink the Murmur3 code under the resolve.
                 {
                     const uint64_t dep = (h[0] ^ h[1] ^ h[2] ^ h[3]) & a.zero;
@@ -529,25 +596,20 @@ __global__ void __launch_bounds__(NT) tile_kernel(const TileArgs a) {
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
                     p_h[t] = h[t];
-                    p_b[t] = home_bucket(h[t], a.nbuckets, a.home_shift);
-                    if (active && t < nv) load_bucket_nc(a.tbl + p_b[t], p_e0[t], p_e1[t]);
+                    // lanes / k-mers with nothing to look up probe bucket 0 (an L2 hit) so that the
+                    // loads are unconditional and land directly in the pipeline registers
+                    p_b[t] = (active && t < nv) ? home_bucket(h[t], a.nbuckets, a.home_shift) : 0u;
+                    load_bucket_nc(a.tbl + p_b[t], p_e0[t], p_e1[t]);
                 }
             }
             if (G > 0) resolve();
+            __syncwarp();
         }
-
-        if constexpr (MODE == MODE_LABEL) {
-            __syncthreads();
-            const unsigned n = sm.pair_n < PAIR_BUF ? sm.pair_n : PAIR_BUF;
-            if (tid == 0 && n) sm.pair_base = atomicAdd(&a.scal->pair_count, (unsigned long long)n);
-            __syncthreads();
-            const unsigned long long gb = sm.pair_base;
-            for (unsigned j = tid; j < n; j += NT)
-                if (gb + j < a.pairs_cap) a.pairs[gb + j] = s_pairs[j];
-        }
-        __syncthreads();
     }
 
+    if constexpr (MODE == MODE_LABEL) {
+        if (pair_fill) flush_pairs();
+    }
     if constexpr (MODE == MODE_LOOKUP || MODE == MODE_LABEL) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
@@ -571,41 +633,48 @@ __global__ void table_clear_kernel(Bucket* tbl, uint32_t nb) {
         reinterpret_cast<Entry*>(tbl)[i] = empty;
 }
 
-__global__ void insert_pairs_kernel(Bucket* tbl, uint32_t nb, int hs, const uint64_t* __restrict__ hash,
-                                    const uint32_t* __restrict__ id, int64_t n, Scalars* scal) {
+__global__ void insert_pairs_kernel(Bucket* tbl, uint32_t nb, uint32_t nlines, int hs,
+                                    const uint64_t* __restrict__ hash, const uint32_t* __restrict__ id, int64_t n,
+                                    Scalars* scal) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         uint32_t v = id[i];
         if (v > SGC_MAX_ID) atomicOr(&scal->err, 2);
-        else table_insert(tbl, nb, hs, hash[i], v, scal);
+        else table_insert(tbl, nb, nlines, hs, hash[i], v, scal);
     }
 }
 
-__global__ void lookup_kernel(const Bucket* tbl, uint32_t nb, int hs, const uint64_t* __restrict__ hash,
-                              int64_t n, uint32_t* __restrict__ out) {
+__global__ void lookup_kernel(const Bucket* tbl, uint32_t nb, uint32_t nlines, int hs,
+                              const uint64_t* __restrict__ hash, int64_t n, uint32_t* __restrict__ out) {
     // two probes in flight per thread
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
         const int64_t j = i + stride;
-        uint64_t h0 = hash[i], h1 = j < n ? hash[j] : 0;
-        uint32_t b0 = home_bucket(h0, nb, hs), b1 = home_bucket(h1, nb, hs);
+        const uint64_t h0 = hash[i], h1 = j < n ? hash[j] : 0;
+        const uint32_t b0 = home_bucket(h0, nb, hs), b1 = j < n ? home_bucket(h1, nb, hs) : 0u;
         Entry a0, a1, c0, c1;
         load_bucket_nc(tbl + b0, a0, a1);
-        if (j < n) load_bucket_nc(tbl + b1, c0, c1);
-        out[i] = lookup_resolve(tbl, nb, b0, h0, a0, a1);
-        if (j < n) out[j] = lookup_resolve(tbl, nb, b1, h1, c0, c1);
+        load_bucket_nc(tbl + b1, c0, c1);
+        uint32_t v;
+        if (!bucket_match(a0, a1, h0, v)) v = a0.flg ? lookup_slow(tbl, nlines, b0, a0.flg, h0) : SGC_MISS;
+        out[i] = v;
+        if (j < n) {
+            if (!bucket_match(c0, c1, h1, v)) v = c0.flg ? lookup_slow(tbl, nlines, b1, c0.flg, h1) : SGC_MISS;
+            out[j] = v;
+        }
     }
 }
 
 // get_unique_values: count_by_id[id]++ per present hash.  With distinct != 0 the input is
 // sorted and a hash equal to its predecessor is skipped.
-__global__ void count_kernel(const Bucket* tbl, uint32_t nb, int hs, const uint64_t* __restrict__ hash,
-                             int64_t n, int distinct, uint32_t* count_by_id, Scalars* scal) {
+__global__ void count_kernel(const Bucket* tbl, uint32_t nb, uint32_t nlines, int hs,
+                             const uint64_t* __restrict__ hash, int64_t n, int distinct, uint32_t* count_by_id,
+                             Scalars* scal) {
     unsigned long long miss = 0, nd = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         uint64_t h = hash[i];
         if (distinct && i > 0 && hash[i - 1] == h) continue;
         nd++;
-        uint32_t v = table_lookup(tbl, nb, hs, h);
+        uint32_t v = table_lookup(tbl, nb, nlines, hs, h);
         if (v == SGC_MISS) miss++;
         else atomicAdd(&count_by_id[v], 1u);
     }
@@ -845,6 +914,7 @@ struct sgc_table {
     sgc_ctx* ctx = nullptr;
     Bucket* buckets = nullptr;
     uint32_t nbuckets = 0;
+    uint32_t nlines = 0;
     int home_shift = 0;
     int64_t max_entries = 0;
     // pending label call
@@ -944,7 +1014,7 @@ int make_plan(sgc_ctx* c, const int64_t* d_off, int64_t nseq, int64_t seq_bytes,
 
 template <int K, int MODE>
 int launch_tile_k(sgc_ctx* c, const TileArgs& a) {
-    size_t smem = sizeof(TileSmem<K>) + (MODE == MODE_LABEL ? PAIR_BUF * sizeof(unsigned long long) : 0);
+    size_t smem = sizeof(WarpTile<K>) * WPB;
     static thread_local int blocks_per_sm = 0;
     if (!blocks_per_sm) {
         CU(cudaFuncSetAttribute(tile_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1002,6 +1072,7 @@ TileArgs base_args(sgc_ctx* c, const uint8_t* d_seq, const int64_t* d_off, int k
 void table_args(TileArgs& a, sgc_table* t) {
     a.tbl = t->buckets;
     a.nbuckets = t->nbuckets;
+    a.nlines = t->nlines;
     a.home_shift = t->home_shift;
 }
 
@@ -1145,18 +1216,23 @@ int sgc_hash_batch(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, const in
 }
 
 // ---------------------------------------------------------------------------- K2
-int sgc_table_create(sgc_ctx* c, int64_t max_entries, sgc_table** out) {
+int sgc_table_create(sgc_ctx* c, int64_t max_entries, float load, sgc_table** out) {
     if (!c || !out) return fail(SGC_ERR_ARG, "NULL argument");
     *out = nullptr;
     if (max_entries < 0) return fail(SGC_ERR_ARG, "max_entries < 0");
     TRY(set_device(c));
-    // one 32-byte bucket (two 16-byte slots) per expected hash: slot load factor <= 0.5
-    int64_t nb = std::max<int64_t>(max_entries, 64);
+    // 32-byte buckets of two 16-byte slots, four per 128-byte line; `load` = expected hashes per
+    // bucket (default 0.75: ~4 % of lookups leave their home bucket, still inside the home line)
+    if (!(load > 0.0f)) load = 0.75f;
+    if (load > 1.6f) return fail(SGC_ERR_ARG, "table load %.2f too high (max 1.6 hashes per 2-slot bucket)", load);
+    int64_t nb = (int64_t)((double)std::max<int64_t>(max_entries, 64) / load) + 4;
+    nb = (nb + 3) & ~(int64_t)3;
     if (nb >= ((int64_t)1 << 32)) return fail(SGC_ERR_CAPACITY, "table of %lld buckets exceeds 2^32-1", (long long)nb);
     sgc_table* t = new (std::nothrow) sgc_table();
     if (!t) return fail(SGC_ERR_NOMEM, "out of host memory");
     t->ctx = c;
     t->nbuckets = (uint32_t)nb;
+    t->nlines = (uint32_t)(nb / 4);
     t->max_entries = max_entries;
     cudaError_t e = cudaMalloc(&t->buckets, (size_t)nb * sizeof(Bucket));
     if (e != cudaSuccess) {
@@ -1194,8 +1270,8 @@ int sgc_table_insert_pairs(sgc_table* t, const uint64_t* d_hash, const uint32_t*
     sgc_ctx* c = t->ctx;
     TRY(set_device(c));
     TRY(zero_scalars(c));
-    insert_pairs_kernel<<<grid_for(n, 256, c->num_sms * 8), 256, 0, c->stream>>>(t->buckets, t->nbuckets, t->home_shift,
-                                                                               d_hash, d_id, n, c->d_scal);
+    insert_pairs_kernel<<<grid_for(n, 256, c->num_sms * 8), 256, 0, c->stream>>>(t->buckets, t->nbuckets, t->nlines,
+                                                                               t->home_shift, d_hash, d_id, n, c->d_scal);
     c->launches++;
     CU(cudaGetLastError());
     TRY(fetch_scalars(c));
@@ -1271,8 +1347,8 @@ int sgc_lookup(sgc_table* t, const uint64_t* d_hash, int64_t n, uint32_t* d_id_o
     if (n == 0) return SGC_OK;
     sgc_ctx* c = t->ctx;
     TRY(set_device(c));
-    lookup_kernel<<<grid_for((n + 1) / 2, 256, c->num_sms * 8), 256, 0, c->stream>>>(t->buckets, t->nbuckets,
-                                                                                    t->home_shift, d_hash, n, d_id_out);
+    lookup_kernel<<<grid_for((n + 1) / 2, 256, c->num_sms * 8), 256, 0, c->stream>>>(
+        t->buckets, t->nbuckets, t->nlines, t->home_shift, d_hash, n, d_id_out);
     c->launches++;
     CU(cudaGetLastError());
     return SGC_OK;
@@ -1297,8 +1373,8 @@ int sgc_count_matches(sgc_table* t, const uint64_t* d_hash, int64_t n, int disti
             CU(cub::DeviceRadixSort::SortKeys(c->cub_tmp.p, tb, d_hash, (uint64_t*)c->tmp_hash.p, n, 0, 64, c->stream));
             src = (const uint64_t*)c->tmp_hash.p;
         }
-        count_kernel<<<grid_for(n, 256, c->num_sms * 8), 256, 0, c->stream>>>(t->buckets, t->nbuckets, t->home_shift, src,
-                                                                            n, distinct, d_count_by_id, c->d_scal);
+        count_kernel<<<grid_for(n, 256, c->num_sms * 8), 256, 0, c->stream>>>(
+            t->buckets, t->nbuckets, t->nlines, t->home_shift, src, n, distinct, d_count_by_id, c->d_scal);
         c->launches++;
         CU(cudaGetLastError());
     }

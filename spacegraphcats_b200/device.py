@@ -165,11 +165,11 @@ def get_context(device=None):
 class DeviceTable:
     """GPU-resident exact map u64 k-mer hash -> u32 unitig id (``sgc_table``)."""
 
-    def __init__(self, ctx, max_entries, home_shift=0):
+    def __init__(self, ctx, max_entries, home_shift=0, load=0.0):
         self.ctx = ctx
         self._L = ctx._L
         h = ctypes.c_void_p()
-        check(self._L.sgc_table_create(ctx._h, int(max_entries), ctypes.byref(h)))
+        check(self._L.sgc_table_create(ctx._h, int(max_entries), float(load), ctypes.byref(h)))
         self._h = h
         self.max_entries = int(max_entries)
         if home_shift:
