@@ -1,0 +1,64 @@
+"""Hash-range partitioned table over N GPUs (BASELINE.json configs[4] shape, scaled by flags):
+torchrun --nproc-per-node N scripts/partitioned_run.py [--table-kmers 1e9] [--reads 4e6]
+Every rank builds 1/N of the unitigs, the table is partitioned by hash range with an NCCL
+all-to-all, each rank labels its own reads through request/reply all-to-alls.  Rank 0 checks its
+labels against a replicated table built on the same GPU (when --check) and prints k-mers/s."""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--table-kmers", type=float, default=4e8)
+ap.add_argument("--reads", type=float, default=4e6)
+ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--check", action="store_true")
+args = ap.parse_args()
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29511")
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+import __graft_entry__ as g
+if rank == 0: g.build()
+dist.barrier()
+from spacegraphcats_b200.device import Context
+from spacegraphcats_b200.synth import SyntheticCdbg
+from spacegraphcats_b200.parallel import DeviceEngine, PartitionedIndex, shard_range
+
+ctx = Context(local)
+K = 31
+n_kmers, n_reads = int(args.table_kmers), int(args.reads)
+cd = SyntheticCdbg(ctx, n_kmers, K, seed=1)          # same genome/unitigs on every rank (same seeds)
+ulo, uhi = shard_range(cd.n_unitigs, rank, world)
+uoff_all = cd.uoff
+with torch.cuda.stream(ctx.stream):
+    b0, b1 = int(uoff_all[ulo].item()), int(uoff_all[uhi].item())
+    useq = cd.useq[b0:b1]
+    uoff = (uoff_all[ulo:uhi + 1] - b0).contiguous()
+    ids = torch.arange(ulo, uhi, dtype=torch.int32, device=ctx.device)
+eng = DeviceEngine(ctx)
+t0 = time.time()
+idx = PartitionedIndex(eng).build(useq, uoff, K, ids)
+ctx.sync(); dist.barrier()
+if rank == 0:
+    print("partitioned build: %.2fs, rank0 holds %d hashes (%.2f GB)" % (time.time() - t0, idx.n_local, idx.table.nbytes / 1e9), flush=True)
+seq, off = cd.reads(n_reads, 150, seed=100 + rank)
+ctx.sync()
+res = None
+for it in range(args.steps + 1):
+    if it == 1:
+        dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+    res = idx.label_reads(seq, off, K)
+ctx.sync(); dist.barrier(); torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+t = torch.tensor([dt], dtype=torch.float64, device=ctx.device); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+rate = world * n_reads * 120 * args.steps / float(t.item())
+if args.check:
+    table = cd.build_table()
+    ref = table.label_reads(seq, off, K, to_host=False)
+    ok = torch.equal(ref["ids_off"], res[0]) and torch.equal(ref["ids"], res[1])
+    okt = torch.tensor([1 if ok else 0], device=ctx.device); dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    if rank == 0: print("labels identical to the replicated table on every rank:", bool(okt.item()), flush=True)
+if rank == 0:
+    print(json.dumps({"mode": "partitioned", "n_gpus": world, "table_kmers": n_kmers, "reads_per_rank_step": n_reads,
+                      "value": rate, "unit": "k-mers/s", "ms_per_step": float(t.item()) / args.steps * 1e3}), flush=True)
+dist.destroy_process_group()

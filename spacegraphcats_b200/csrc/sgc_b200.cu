@@ -188,20 +188,19 @@ __device__ __forceinline__ bool bucket_match(const Entry& e0, const Entry& e1, u
 // Slow path of a lookup (the home bucket did not hold the key and its max-step is > 0): the other
 // three buckets of the home line are read together (the line is already in L2: HBM moved all
 // 128 bytes), then, rarely, the following lines.
-__device__ __noinline__ uint32_t lookup_slow(const Bucket* tbl, uint32_t nlines, uint32_t hb, uint32_t maxstep,
-                                             uint64_t h) {
-    Entry a0[3], a1[3];
-#pragma unroll
-    for (uint32_t s = 1; s <= 3; s++)
-        if (s <= maxstep) load_bucket_nc(tbl + probe_bucket(hb, s, nlines), a0[s - 1], a1[s - 1]);
+__device__ __forceinline__ uint32_t lookup_slow(const Bucket* tbl, uint32_t nlines, uint32_t hb, uint32_t maxstep,
+                                                uint64_t h) {
+    Entry a0, a1, b0, b1, c0, c1;
+    load_bucket_nc(tbl + probe_bucket(hb, 1, nlines), a0, a1);
+    load_bucket_nc(tbl + probe_bucket(hb, 2, nlines), b0, b1);
+    load_bucket_nc(tbl + probe_bucket(hb, 3, nlines), c0, c1);
     uint32_t out;
-#pragma unroll
-    for (uint32_t s = 1; s <= 3; s++)
-        if (s <= maxstep && bucket_match(a0[s - 1], a1[s - 1], h, out)) return out;
+    if (bucket_match(a0, a1, h, out)) return out;
+    if (maxstep >= 2 && bucket_match(b0, b1, h, out)) return out;
+    if (maxstep >= 3 && bucket_match(c0, c1, h, out)) return out;
     for (uint32_t s = 4; s <= maxstep; s++) {
-        Entry e0, e1;
-        load_bucket_nc(tbl + probe_bucket(hb, s, nlines), e0, e1);
-        if (bucket_match(e0, e1, h, out)) return out;
+        load_bucket_nc(tbl + probe_bucket(hb, s, nlines), a0, a1);
+        if (bucket_match(a0, a1, h, out)) return out;
     }
     return SGC_MISS;
 }
@@ -506,10 +505,16 @@ __global__ void __launch_bounds__(NT) tile_kernel(const TileArgs a) {
                         else if (p_e0[t].flg) slow |= 1u << t;
                     }
                 }
-                if (slow) {  // rare per lane: keys that overflowed their home bucket
+                while (slow) {  // ~6 % of lookups: the key is not in its home bucket; one trip per key
+                    const int t = __ffs(slow) - 1;
+                    slow &= slow - 1;
+                    const uint64_t hk = t == 0 ? p_h[0] : t == 1 ? p_h[1] : t == 2 ? p_h[2] : p_h[3];
+                    const uint32_t hb = t == 0 ? p_b[0] : t == 1 ? p_b[1] : t == 2 ? p_b[2] : p_b[3];
+                    const uint32_t ms = t == 0 ? p_e0[0].flg : t == 1 ? p_e0[1].flg : t == 2 ? p_e0[2].flg : p_e0[3].flg;
+                    const uint32_t v = lookup_slow(a.tbl, a.nlines, hb, ms, hk);
 #pragma unroll
-                    for (int t = 0; t < 4; t++)
-                        if (slow & (1u << t)) ids[t] = lookup_slow(a.tbl, a.nlines, p_b[t], p_e0[t].flg, p_h[t]);
+                    for (int u = 0; u < 4; u++)
+                        if (u == t) ids[u] = v;
                 }
 #pragma unroll
                 for (int t = 0; t < 4; t++)

@@ -1,0 +1,215 @@
+"""Multi-GPU host layer: one process per GPU over ``torch.distributed``.
+
+* **Replicated table** needs nothing from here: every rank builds / loads the full table and labels
+  its own contiguous range of reads (:func:`shard_range`); results are concatenated by the caller.
+* **Hash-range partitioned table** (:class:`PartitionedIndex`): owner(hash) = top log2(R) bits.
+  Build: every rank hashes its shard of the unitigs, buckets the (hash, id) pairs by owner, one
+  all-to-all, local insert -- all copies of a hash meet on one rank, so build_mphf's multicount rule
+  stays exact.  Lookup: hash local reads, bucket hashes by owner (remembering the permutation),
+  all-to-all (8 B per k-mer), owner-side probe, all-to-all back (4 B per k-mer), un-permute,
+  per-read distinct ids.
+
+The compute steps go through an *engine* object; :class:`DeviceEngine` is the product engine (CUDA
+kernels through the C-ABI, NCCL for the exchange).  The exchange protocol itself is backend
+agnostic, which is what the world_size-2 gloo tests exercise with a host engine of their own.
+"""
+import ctypes
+
+import numpy as np
+
+from ._lib import check
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def shard_range(n, rank, world):
+    """Contiguous [lo, hi) of n records for this rank (keeps mates together when n is even-split
+    by the caller on pair boundaries)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def log2_ranks(world):
+    b = world.bit_length() - 1
+    if world < 1 or (1 << b) != world:
+        raise ValueError("hash-range partitioning needs a power-of-two number of ranks (got %d)" % world)
+    return b
+
+
+def exchange(send, send_counts, group=None):
+    """Variable all-to-all of a 1-D tensor: ``send`` holds the rows for rank 0, 1, ... back to
+    back (``send_counts[r]`` rows for rank r).  -> (recv tensor, recv_counts list)."""
+    torch = _torch()
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    sc = torch.tensor(list(send_counts), dtype=torch.int64, device=send.device)
+    rc = torch.empty(world, dtype=torch.int64, device=send.device)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = rc.tolist()
+    recv = torch.empty(int(sum(recv_counts)), dtype=send.dtype, device=send.device)
+    dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=list(send_counts), group=group)
+    return recv, recv_counts
+
+
+class DeviceEngine:
+    """CUDA engine: every step is a kernel of libsgc_b200.so on the context's stream."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self._L = ctx._L
+
+    # -- build side -------------------------------------------------------
+    def hash_pairs(self, seq, off, ksize, ids):
+        """(hash per k-mer, id per k-mer) for a shard of unitigs, on the device."""
+        torch = _torch()
+        c = self.ctx
+        d_off = c.to_device(off, np.int64)
+        d_hash, d_koff, d_stat = c.hash_batch(seq, d_off, ksize, to_host=False)
+        if d_stat is not None and d_stat.numel() and bool(d_stat.any().item()):
+            raise ValueError("Invalid base in read")
+        d_ids = c.to_device(ids, np.uint32)
+        with torch.cuda.stream(c.stream):
+            per_kmer = torch.repeat_interleave(d_ids, (d_koff[1:] - d_koff[:-1]))
+        return d_hash, per_kmer
+
+    def partition_pairs(self, d_hash, d_ids, world):
+        torch = _torch()
+        c = self.ctx
+        n = d_hash.numel()
+        oh = c.empty(n, torch.int64)
+        oi = c.empty(n, torch.int32)
+        d_boff = c.empty(world + 1, torch.int64)
+        h_boff = (ctypes.c_int64 * (world + 1))()
+        check(self._L.sgc_partition_pairs(c._h, c.ptr(d_hash), c.ptr(d_ids), n, world, c.ptr(oh), c.ptr(oi), None,
+                                          c.ptr(d_boff), h_boff))
+        return oh, oi, list(h_boff)
+
+    def new_table(self, n, home_shift):
+        from .device import DeviceTable
+
+        return DeviceTable(self.ctx, max(n, 1), home_shift=home_shift)
+
+    def insert_pairs(self, table, d_hash, d_ids):
+        table.insert_pairs(d_hash, d_ids)
+
+    # -- lookup side ------------------------------------------------------
+    def hash_partition(self, seq, off, ksize, world):
+        """-> (bucketed hashes, perm, bucket_off list, kmer_off tensor, n_kmers)"""
+        torch = _torch()
+        c = self.ctx
+        d_seq = c.to_device(seq, np.uint8)
+        d_off = c.to_device(off, np.int64)
+        nseq = d_off.numel() - 1
+        cap = max(d_seq.numel(), 1)
+        d_b = c.empty(cap, torch.int64)
+        d_perm = c.empty(cap, torch.int64)
+        d_boff = c.empty(world + 1, torch.int64)
+        d_koff = c.empty(nseq + 1, torch.int64)
+        d_stat = c.empty(nseq, torch.int32)
+        h_boff = (ctypes.c_int64 * (world + 1))()
+        check(self._L.sgc_hash_partition(c._h, c.ptr(d_seq), d_seq.numel(), c.ptr(d_off), nseq, int(ksize), world,
+                                         c.ptr(d_b), c.ptr(d_perm), cap, c.ptr(d_boff), c.ptr(d_koff), c.ptr(d_stat),
+                                         h_boff))
+        boff = list(h_boff)
+        if nseq and bool(d_stat.any().item()):
+            raise ValueError("Invalid base in read")
+        n = boff[-1]
+        return d_b[:n], d_perm[:n], boff, d_koff, n
+
+    def lookup(self, table, d_hash):
+        return table.lookup(d_hash, to_host=False)
+
+    def unpermute(self, d_ids, d_perm):
+        torch = _torch()
+        c = self.ctx
+        out = c.empty(d_ids.numel(), torch.int32)
+        check(self._L.sgc_unpermute_u32(c._h, c.ptr(d_ids), c.ptr(d_perm), d_ids.numel(), c.ptr(out)))
+        return out
+
+    def labels_from_ids(self, d_kmer_ids, d_koff, nseq):
+        torch = _torch()
+        c = self.ctx
+        cap = max(4 * nseq, 1024)
+        d_ioff = c.empty(nseq + 1, torch.int64)
+        for _ in range(8):
+            d_out = c.empty(cap, torch.int32)
+            nh, nl = ctypes.c_int64(0), ctypes.c_int64(0)
+            from ._lib import SgcCapacityError
+
+            try:
+                check(self._L.sgc_labels_from_ids(c._h, c.ptr(d_kmer_ids), c.ptr(d_koff), nseq, d_kmer_ids.numel(),
+                                                  c.ptr(d_ioff), c.ptr(d_out), cap, ctypes.byref(nh), ctypes.byref(nl)))
+                break
+            except SgcCapacityError:
+                cap = max(2 * cap, int(nl.value) + 1024)
+        return d_ioff, d_out[: nl.value], nh.value
+
+    def sync(self):
+        self.ctx.sync()
+
+    def stream(self):
+        """Context in which collectives must be issued so that they are ordered with the kernels."""
+        return _torch().cuda.stream(self.ctx.stream)
+
+    def to_host(self, t, dtype=None):
+        return self.ctx.to_host(t, dtype)
+
+
+class PartitionedIndex:
+    """k-mer -> unitig table hash-range partitioned over the ranks of a process group."""
+
+    def __init__(self, engine, group=None):
+        import torch.distributed as dist
+
+        self.engine = engine
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.bits = log2_ranks(self.world)
+        self.table = None
+        self.n_local = 0
+
+    def build(self, seq, off, ksize, ids):
+        """Every rank passes ITS shard of the unitigs (ids are global cDBG ids)."""
+        e = self.engine
+        d_hash, d_ids = e.hash_pairs(seq, off, ksize, ids)
+        bh, bi, boff = e.partition_pairs(d_hash, d_ids, self.world)
+        counts = [boff[r + 1] - boff[r] for r in range(self.world)]
+        e.sync()
+        with e.stream():
+            rh, rcounts = exchange(bh, counts, self.group)
+            ri, _ = exchange(bi, counts, self.group)
+        self.n_local = int(sum(rcounts))
+        self.table = e.new_table(self.n_local, self.bits)
+        if self.n_local:
+            e.insert_pairs(self.table, rh, ri)
+        return self
+
+    def lookup_sequences(self, seq, off, ksize):
+        """Per-k-mer unitig ids (MISS = 0xFFFFFFFF) of this rank's sequences, original order.
+        -> (kmer_ids tensor, kmer_off tensor)"""
+        e = self.engine
+        bh, perm, boff, koff, n = e.hash_partition(seq, off, ksize, self.world)
+        counts = [boff[r + 1] - boff[r] for r in range(self.world)]
+        e.sync()
+        with e.stream():
+            rh, rcounts = exchange(bh, counts, self.group)  # requests: 8 B per k-mer
+        rid = e.lookup(self.table, rh)
+        e.sync()
+        with e.stream():
+            back, bcounts = exchange(rid, rcounts, self.group)  # replies: 4 B per k-mer
+        assert bcounts == counts
+        return e.unpermute(back, perm), koff
+
+    def label_reads(self, seq, off, ksize):
+        """index_reads' per-read step against the partitioned table.
+        -> (ids_off, ids, n_hits) as engine tensors"""
+        kmer_ids, koff = self.lookup_sequences(seq, off, ksize)
+        nseq = koff.numel() - 1 if hasattr(koff, "numel") else len(koff) - 1
+        return self.engine.labels_from_ids(kmer_ids, koff, nseq)

@@ -496,3 +496,59 @@ def test_index_reads_pairing_semantics(tmp_path, ctx, O, ignore_paired):
     assert rows == sorted(want)
     assert (n_paired > 0) != ignore_paired
     assert rc == (0 if max(total) + 1 == len(total) else -1)
+
+
+# ---------------------------------------------------------------- K7: partitioned pipeline
+def test_partition_kernels_single_gpu(ctx, O):
+    """sgc_hash_partition / sgc_partition_pairs / sgc_unpermute_u32 / sgc_labels_from_ids on one
+    GPU, emulating R=4 owner ranks (the exchange itself is covered by the gloo test on CPU and
+    by the multi-GPU run): per-owner buckets hold exactly the hashes whose top 2 bits name the
+    owner, the permutation restores k-mer order, and the K4 tail reproduces label_reads."""
+    from spacegraphcats_b200.cdbg.hashing import GpuKmerTable
+    from spacegraphcats_b200.device import DeviceTable, pack_sequences
+    from spacegraphcats_b200.parallel import DeviceEngine
+
+    rng = np.random.default_rng(77)
+    k, R = 31, 4
+    lut = np.frombuffer(b"ACGT", np.uint8)
+    g = lut[rng.integers(0, 4, 80_000)]
+    cuts = np.concatenate([[0], np.cumsum(rng.integers(1, 150, 2000))])
+    cuts = cuts[cuts < len(g) - k]
+    useqs = [g[a : b + k - 1].tobytes() for a, b in zip(cuts[:-1], cuts[1:])]
+    reads = [g[p : p + 150].tobytes() for p in rng.integers(0, len(g) - 150, 3000)] + [b"ACGT", b""]
+    ubuf, uoff = pack_sequences(useqs)
+    rbuf, roff = pack_sequences(reads)
+    eng = DeviceEngine(ctx)
+
+    # build side: bucket (hash, id) pairs by owner, insert each bucket into that owner's table
+    d_hash, d_ids = eng.hash_pairs(ubuf, uoff, k, np.arange(len(useqs), dtype=np.uint32))
+    bh, bi, boff = eng.partition_pairs(d_hash, d_ids, R)
+    hh = ctx.to_host(bh, np.uint64)
+    assert boff[0] == 0 and boff[-1] == len(hh)
+    for r in range(R):
+        assert ((hh[boff[r] : boff[r + 1]] >> np.uint64(62)) == r).all()
+    tables = []
+    for r in range(R):
+        t = DeviceTable(ctx, max(boff[r + 1] - boff[r], 1), home_shift=2)
+        if boff[r + 1] > boff[r]:
+            t.insert_pairs(bh[boff[r] : boff[r + 1]], bi[boff[r] : boff[r + 1]])
+        tables.append(t)
+
+    # lookup side
+    qh, perm, qoff, koff, n = eng.hash_partition(rbuf, roff, k, R)
+    want_h, want_koff = O.hash_batch(rbuf, roff, k)
+    assert n == len(want_h) and np.array_equal(ctx.to_host(koff), want_koff)
+    got_h = np.empty(n, np.uint64)
+    got_h[ctx.to_host(perm)] = ctx.to_host(qh, np.uint64)
+    assert np.array_equal(got_h, want_h)
+    import torch
+
+    replies = torch.cat([tables[r].lookup(qh[qoff[r] : qoff[r + 1]], to_host=False) for r in range(R)])
+    kmer_ids = eng.unpermute(replies, perm)
+    whole = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx)
+    ref = whole.lookup_sequences(rbuf, roff, k)
+    assert np.array_equal(ctx.to_host(kmer_ids, np.uint32), ref["kmer_ids"])
+    ioff, ids, nh = eng.labels_from_ids(kmer_ids, koff, len(reads))
+    lab = whole.label_reads(rbuf, roff, k)
+    assert np.array_equal(ctx.to_host(ioff), lab["ids_off"]) and np.array_equal(ctx.to_host(ids, np.uint32), lab["ids"])
+    assert nh == lab["n_hits"]
