@@ -191,7 +191,7 @@ def workload_config(args, cpu=False):
                     "1 B200 replicated table (BASELINE.json configs[3])" % (args.table_kmers, KSIZE),
         "ksize": KSIZE, "read_len": READ_LEN, "reads_per_step": args.batch_reads,
         "kmers_per_step": args.batch_reads * (READ_LEN - KSIZE + 1), "error_rate": ERR_PPM / 1e6,
-        "table": "replicated", "l2": "inputs (2.5 GB reads/step, 16 GB table) far larger than the 126 MB L2",
+        "table": "replicated", "l2": "inputs (2.5 GB reads/step, 21 GB table) far larger than the 126 MB L2; no flush needed",
         **({"cpu_sample": {"table_kmers": args.cpu_kmers, "reads_per_step": args.cpu_reads}} if cpu else {}),
     }
 
@@ -305,12 +305,16 @@ def main():
         for b in range(nh_b):
             h_seq[b].copy_(batches[b % nb][0])
             h_off[b].copy_(batches[b % nb][1])
-        h_ids_off = torch.empty(n_reads + 1, dtype=torch.int64).pin_memory()
-        h_ids = torch.empty(ids_cap, dtype=torch.int32).pin_memory()
+        h_ids_off = [torch.empty(n_reads + 1, dtype=torch.int64).pin_memory() for _ in range(2)]
+        h_ids = [torch.empty(ids_cap, dtype=torch.int32).pin_memory() for _ in range(2)]
         d_seq = [ctx.empty(n_reads * READ_LEN, torch.uint8) for _ in range(2)]
         d_off = [ctx.empty(n_reads + 1, torch.int64) for _ in range(2)]
+        o_ids_off = [ctx.empty(n_reads + 1, torch.int64) for _ in range(2)]
+        o_ids = [ctx.empty(ids_cap, torch.int32) for _ in range(2)]
         copy_stream = torch.cuda.Stream(device=ctx.device)
+        back_stream = torch.cuda.Stream(device=ctx.device)
         copied = [torch.cuda.Event() for _ in range(2)]
+        returned = [torch.cuda.Event() for _ in range(2)]
         torch.cuda.synchronize()
 
         def h2d(i):
@@ -320,20 +324,30 @@ def main():
                 d_off[s].copy_(h_off[i % nh_b], non_blocking=True)
                 copied[s].record(copy_stream)
 
+        def label_into(s):
+            nk, nh, nl = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+            check(L.sgc_label_reads(table._h, ctx.ptr(d_seq[s]), d_seq[s].numel(), ctx.ptr(d_off[s]), n_reads, KSIZE,
+                                    ctx.ptr(o_ids_off[s]), ctx.ptr(o_ids[s]), ids_cap, ctx.ptr(d_stat), ctypes.byref(nk),
+                                    ctypes.byref(nh), ctypes.byref(nl)))
+            return nl.value
+
         def e2e_steps(n):
+            """H2D of step i+1 and D2H of step i-1 overlap the kernels of step i."""
             h2d(0)
             tot_labels = 0
             for i in range(n):
                 s = i % 2
                 ctx.stream.wait_event(copied[s])
+                ctx.stream.wait_event(returned[s])  # outputs of step i-2 have left this buffer
                 if i + 1 < n:
-                    h2d(i + 1)  # overlaps the kernels of step i (other buffer; step i-1 is finished)
-                nk, nh, nl = label(d_seq[s], d_off[s])
-                with torch.cuda.stream(ctx.stream):
-                    h_ids_off.copy_(d_ids_off, non_blocking=True)
-                    h_ids[:nl].copy_(d_ids[:nl], non_blocking=True)
-                ctx.sync()
+                    h2d(i + 1)
+                nl = label_into(s)  # returns when the kernels of step i are done (host sync inside)
+                with torch.cuda.stream(back_stream):
+                    h_ids_off[s].copy_(o_ids_off[s], non_blocking=True)
+                    h_ids[s][:nl].copy_(o_ids[s][:nl], non_blocking=True)
+                    returned[s].record(back_stream)
                 tot_labels += nl
+            back_stream.synchronize()
             return tot_labels
 
         e2e_steps(min(2, args.warmup))
@@ -369,13 +383,22 @@ def main():
     bytes_per_kmer = READ_LEN / (READ_LEN - KSIZE + 1) + SECTOR + 4.0 * labels_per_read / (READ_LEN - KSIZE + 1)
     tile_s = tile_ms.value / 1e3 / max(tile_n.value, 1)
     achieved = bytes_per_kmer * step_kmers / tile_s / 1e9
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes per k-mer of this kernel from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = float(tj["dram_bytes_per_kmer"]) * step_kmers / 1e9
+        traffic_src = tj.get("source")
+    except Exception:
+        pass
     roofline = {
         "bound": "hbm", "kernel": "tile_kernel<31, MODE_LABEL>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": traffic, "traffic_unit": "GB per launch", "traffic_source": traffic_src,
+        "peak_source": peak_src,
         "bytes_per_kmer": bytes_per_kmer, "kernel_ms": tile_s * 1e3, "kernel_launches": int(tile_n.value),
         "kernel_share_of_step": tile_ms.value / ms,
         "note": "algorithmic bytes = read bases + ONE 32-byte table sector per k-mer + label output; the "
-                "random-sector ceiling measured on this part is ~36.5 G sectors/s (scripts/sector_probe*.cu)",
+                "measured random-access ceiling of HBM on this part is 36-46 G accesses/s and every access moves a "
+                "128-byte line (scripts/sector_probe*.cu, profiles/)",
     }
 
     # ---- CPU baseline on the host cores ---------------------------------------------------

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <utility>
@@ -860,13 +861,17 @@ __global__ void synth_reads_kernel(const uint8_t* __restrict__ genome, int64_t g
         int j = (int)(i - r * read_len);
         uint64_t d = splitmix64(seed ^ splitmix64((uint64_t)r));
         int64_t p = (int64_t)((d >> 1) % (uint64_t)(glen - read_len + 1));
-        bool rc = rc_half && (d & 1);
-        uint8_t b = rc ? sgc::comp_base(genome[p + read_len - 1 - j]) : genome[p + j];
-        uint64_t e = splitmix64(seed * 31 + 7 + (uint64_t)i);
+        const bool rc = rc_half && (d & 1);
+        // errors are drawn in GENOME orientation, so the rc_half=0 and rc_half=1 versions of a batch
+        // are exact reverse complements of each other read by read
+        const int gj = rc ? read_len - 1 - j : j;
+        uint8_t b = genome[p + gj];
+        const uint64_t e = splitmix64(seed * 31 + 7 + (uint64_t)(r * read_len + gj));
         if ((uint32_t)(e % 1000000ULL) < err_ppm) {
             int cur = b == 'A' ? 0 : b == 'C' ? 1 : b == 'G' ? 2 : 3;
             b = "ACGT"[(cur + 1 + (int)((e >> 40) % 3)) & 3];
         }
+        if (rc) b = sgc::comp_base(b);
         out[i] = b;
         if (j == 0) off[r] = r * (int64_t)read_len;
         if (i == total - 1) off[nreads] = total;
@@ -1147,6 +1152,9 @@ int sgc_ctx_create(int device, void* stream, sgc_ctx** out) {
     if (prop.major < 10)
         return fail(SGC_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
                     prop.minor);
+    if (const char* gran = getenv("SGC_L2_FETCH_GRANULARITY")) {  // experiment knob: 32 / 64 / 128
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(gran));
+    }
     sgc_ctx* c = new (std::nothrow) sgc_ctx();
     if (!c) return fail(SGC_ERR_NOMEM, "out of host memory");
     c->device = device;

@@ -81,6 +81,8 @@ class Context:
             a = a.view(np.int64)
         elif a.dtype == np.uint32:
             a = a.view(np.int32)
+        if not a.flags.writeable:
+            a = a.copy()
         with torch.cuda.stream(self.stream):
             if a.size == 0:
                 return torch.empty(0, dtype=torch.from_numpy(a).dtype, device=self.device)

@@ -552,3 +552,63 @@ def test_partition_kernels_single_gpu(ctx, O):
     lab = whole.label_reads(rbuf, roff, k)
     assert np.array_equal(ctx.to_host(ioff), lab["ids_off"]) and np.array_equal(ctx.to_host(ids, np.uint32), lab["ids"])
     assert nh == lab["n_hits"]
+
+
+# ---------------------------------------------------------------- full-size properties
+def test_full_size_properties(ctx, O):
+    """BASELINE.json configs[3] at FULL size (500 M unitig k-mers, 2^24 x 150 bp reads = 2.0e9
+    k-mers per batch): too big for the oracle, so size-independent properties are checked --
+    strand symmetry of the labels, batch-split invariance, sortedness, count identities -- plus an
+    oracle cross-check of a sample of reads through an independent path (CPU hashes -> stand-alone
+    lookup kernel)."""
+    import torch
+
+    from spacegraphcats_b200.synth import SyntheticCdbg
+
+    n_kmers = int(os.environ.get("SGC_TEST_TABLE_KMERS", 500_000_000))
+    n_reads = int(os.environ.get("SGC_TEST_READS", 1 << 24))
+    k = 31
+    cd = SyntheticCdbg(ctx, n_kmers, k, seed=1)
+    table = cd.build_table()
+    live, multi, max_id = table.stats()
+    assert live + multi == n_kmers  # every genome k-mer is distinct at this size w.h.p.; duplicated unitigs drop
+    assert multi == cd.dup_kmers and max_id < cd.n_unitigs - cd.n_dup  # duplicated unitigs (highest ids) vanish
+
+    seq_f, off = cd.reads(n_reads, 150, seed=5, err_ppm=5000, rc_half=False)
+    seq_r, _ = cd.reads(n_reads, 150, seed=5, err_ppm=5000, rc_half=True)
+    a = table.label_reads(seq_f, off, k, to_host=False)
+    b = table.label_reads(seq_r, off, k, to_host=False)
+    assert a["n_kmers"] == n_reads * 120 == b["n_kmers"]
+    assert a["n_hits"] == b["n_hits"] and 0.80 < a["n_hits"] / a["n_kmers"] < 0.90  # (1-0.005)^31 = 0.856
+    # strand symmetry: a read and its reverse complement get the same label set
+    assert torch.equal(a["ids_off"], b["ids_off"]) and torch.equal(a["ids"], b["ids"])
+    assert not torch.equal(seq_f, seq_r)
+    # ids ascending inside every read, offsets monotone, no MISS stored
+    ioff, ids = a["ids_off"], a["ids"].to(torch.int64) & 0xFFFFFFFF
+    assert bool((ioff[1:] >= ioff[:-1]).all()) and int(ioff[-1]) == ids.numel() == a["n_labels"]
+    inc = ids[1:] > ids[:-1]
+    starts = torch.zeros(ids.numel(), dtype=torch.bool, device=ids.device)
+    starts[ioff[:-1][ioff[:-1] < ids.numel()]] = True
+    assert bool((inc | starts[1:]).all())
+    assert int(ids.max()) <= max_id
+    # batch-split invariance: two halves labelled separately == the whole batch
+    h = n_reads // 2
+    a1 = table.label_reads(seq_f[: h * 150], off[: h + 1], k, to_host=False)
+    a2 = table.label_reads(seq_f[h * 150 :], (off[h:] - off[h]).contiguous(), k, to_host=False)
+    assert torch.equal(torch.cat([a1["ids"], a2["ids"]]), a["ids"])
+    assert torch.equal(torch.cat([a1["ids_off"], a2["ids_off"][1:] + a1["ids_off"][-1]]), a["ids_off"])
+    # per-k-mer path: histogram total == hits == the label path's hits
+    lk = table.lookup_sequences(seq_f, off, k, n_ids=max_id + 1, want_ids=False, to_host=False)
+    assert lk["n_hits"] == a["n_hits"] and int(lk["count_by_id"].to(torch.int64).sum()) == a["n_hits"]
+    # oracle cross-check on a sample of reads through an independent path
+    rng = np.random.default_rng(0)
+    pick = np.sort(rng.choice(n_reads, 3000, replace=False))
+    hs = ctx.to_host(seq_f.view(n_reads, 150)[torch.from_numpy(pick).to(seq_f.device)])
+    sbuf = np.ascontiguousarray(hs).reshape(-1)
+    soff = np.arange(len(pick) + 1, dtype=np.int64) * 150
+    want_h, koff = O.hash_batch(sbuf, soff, k)  # CPU oracle hashes
+    got_ids = table.lookup(want_h)  # stand-alone lookup kernel
+    ioff_h, ids_h = ctx.to_host(a["ids_off"]), ctx.to_host(a["ids"], np.uint32)
+    for j, r in enumerate(pick.tolist()):
+        v = got_ids[koff[j] : koff[j + 1]]
+        assert np.array_equal(np.unique(v[v != 0xFFFFFFFF]), ids_h[ioff_h[r] : ioff_h[r + 1]]), r
