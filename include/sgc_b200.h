@@ -183,6 +183,19 @@ int sgc_partition_pairs(sgc_ctx* ctx, const uint64_t* d_hash, const uint32_t* d_
 int sgc_labels_from_ids(sgc_ctx* ctx, const uint32_t* d_kmer_ids, const int64_t* d_kmer_off,
                         int64_t nseq, int64_t n_kmers, int64_t* d_ids_off, uint32_t* d_ids_out,
                         int64_t ids_cap, int64_t* h_n_hits, int64_t* h_n_labels);
+/* Fused K7 (no sort, no permutation array).  Request side: hash every k-mer and append it to the
+ * send region of its owner rank: d_send = n_ranks regions of send_cap hashes; d_ridx[k-mer] =
+ * owner << (32 - log2 R) | position in that region; h_counts[n_ranks] (host) = hashes per owner.
+ * Synchronises.  Reply side: d_replies has the layout of d_send (one uint32 id per request, as
+ * returned by the owners); outputs like sgc_label_reads (+ optional per-k-mer ids). */
+int sgc_partition_hashes(sgc_ctx* ctx, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off,
+                         int64_t nseq, int k, int n_ranks, uint64_t* d_send, int64_t send_cap,
+                         uint32_t* d_ridx, int64_t ridx_cap, int32_t* d_status, int64_t* h_counts);
+int sgc_labels_from_replies(sgc_ctx* ctx, const int64_t* d_off, int64_t nseq, int64_t seq_bytes, int k,
+                            int n_ranks, const uint32_t* d_ridx, const uint32_t* d_replies,
+                            int64_t send_cap, int64_t* d_ids_off, uint32_t* d_ids_out, int64_t ids_cap,
+                            uint32_t* d_kmer_ids, int64_t* h_n_kmers, int64_t* h_n_hits,
+                            int64_t* h_n_labels);
 /* d_out[d_perm[j]] = d_in[j] */
 int sgc_unpermute_u32(sgc_ctx* ctx, const uint32_t* d_in, const int64_t* d_perm, int64_t n,
                       uint32_t* d_out);

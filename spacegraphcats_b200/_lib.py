@@ -63,6 +63,8 @@ PROTOTYPES = {
     "sgc_partition_pairs": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _pi64]),
     "sgc_labels_from_ids": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _pi64, _pi64]),
     "sgc_unpermute_u32": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "sgc_partition_hashes": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _pi64]),
+    "sgc_labels_from_replies": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _pi64, _pi64, _pi64]),
     "sgc_ctx_set_timing": (_i32, [_vp, _i32]),
     "sgc_ctx_tile_ms": (_i32, [_vp, ctypes.POINTER(ctypes.c_double), _pi64]),
     "sgc_synth_genome": (_i32, [_vp, _vp, _i64, ctypes.c_uint64]),

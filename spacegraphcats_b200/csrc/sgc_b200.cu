@@ -68,7 +68,7 @@ constexpr unsigned long long SEQ_MASK = (1ULL << 40) - 1ULL;
 constexpr uint32_t VAL_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t VAL_MULTI = 0xFFFFFFFEu;
 
-enum Mode { MODE_HASH = 0, MODE_INSERT = 1, MODE_LOOKUP = 2, MODE_LABEL = 3 };
+enum Mode { MODE_HASH = 0, MODE_INSERT = 1, MODE_LOOKUP = 2, MODE_LABEL = 3, MODE_PARTITION = 4, MODE_GATHER = 5 };
 
 template <int K>
 struct Geo {
@@ -132,6 +132,14 @@ struct TileArgs {
     unsigned long long* pairs;
     unsigned long long pairs_cap;
     unsigned long long zero;  // always 0 (scheduling dependency, see the pipelined probe loop)
+    // MODE_PARTITION (hash -> owner rank's send region) / MODE_GATHER (replies -> labels)
+    uint64_t* send;                 // n_ranks regions of send_cap hashes
+    unsigned long long send_cap;
+    unsigned long long* cursor;     // n_ranks fill counters
+    uint32_t* ridx;                 // per k-mer: owner << (32 - owner_bits) | position in the owner's region
+    const uint32_t* replies;        // same layout as send, 4 bytes per request
+    int owner_bits;
+    int n_ranks;
 };
 
 // ----------------------------------------------------------------------------------
@@ -332,6 +340,8 @@ struct WarpTile {
     int nk[SPW];
     int gpre[SPW + 1];
     int pad[3];
+    unsigned wcnt[32];              // MODE_PARTITION: per-owner counts of one warp iteration
+    unsigned long long wbase[32];   // ... and the reserved base positions
 };
 
 template <int K, int MODE>
@@ -354,6 +364,44 @@ __global__ void __launch_bounds__(NT) tile_kernel(const TileArgs a) {
             if (base + j < a.pairs_cap) a.pairs[base + j] = wt.pairs[j];
         __syncwarp();
         pair_fill = 0;
+    };
+
+    // K4 candidate rule shared by MODE_LABEL and MODE_GATHER: a hit is a candidate (sequence, id) key
+    // unless the previous k-mer of the same segment has the same id (known through a warp shuffle;
+    // the first k-mer of a lane-0 group is conservatively a candidate).  All 32 lanes must call this.
+    auto emit_candidates = [&](const uint32_t (&ids)[4], bool active, int sg, int i, int nv) {
+        const uint32_t prev_lane = __shfl_up_sync(0xffffffffu, ids[3], 1);
+        unsigned long long keys[4] = {0, 0, 0, 0};
+        unsigned nc = 0;
+        if (active) {
+            const unsigned long long sq = (unsigned long long)wt.seq[sg] << 32;
+            uint32_t prev = (i > 0 && lane > 0) ? prev_lane : SGC_MISS;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                if (t < nv && ids[t] != SGC_MISS && ids[t] != prev) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++)  // constant indices keep keys[] in registers
+                        if (u == (int)nc) keys[u] = sq | ids[t];
+                    nc++;
+                }
+                prev = ids[t];
+            }
+        }
+        unsigned incl = nc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {
+            if (pair_fill + total > PAIR_BUF) flush_pairs();
+            unsigned pos = pair_fill + incl - nc;
+#pragma unroll
+            for (unsigned j = 0; j < 4; j++)
+                if (j < nc) wt.pairs[pos++] = keys[j];
+            pair_fill += total;
+        }
     };
 
     // dynamic round scheduling; the NEXT round index is always requested one round ahead
@@ -400,7 +448,7 @@ __global__ void __launch_bounds__(NT) tile_kernel(const TileArgs a) {
         __syncwarp();
 
         // ---- stage forward + reverse-complement words straight from global memory ----
-        {
+        if constexpr (MODE != MODE_GATHER) {
             const int sg = lane >> 2, sub = lane & 3;
             const int nk = wt.nk[sg];
             if (nk) {
@@ -485,6 +533,82 @@ __global__ void __launch_bounds__(NT) tile_kernel(const TileArgs a) {
                             table_insert(a.tbl, a.nbuckets, a.nlines, a.home_shift, h[t], id, a.scal);
                 }
             }
+        } else if constexpr (MODE == MODE_PARTITION) {
+            // K7 request side: every hash goes to the send region of its owner rank (top owner_bits
+            // bits).  Positions are reserved per warp iteration (<=128 k-mers): lanes count owners in
+            // shared memory, one lane per owner reserves a run in that owner's region, so each owner
+            // receives runs of consecutive hashes.  ridx remembers where every k-mer's reply will be.
+            const int sh = 32 - a.owner_bits;
+            for (int g0 = 0; g0 < G; g0 += 32) {
+                const int g = g0 + lane;
+                const bool active = g < G;
+                int sg = 0, i = 0, nv = 0;
+                uint64_t h[4] = {0, 0, 0, 0};
+                if (active) locate_and_hash(g, sg, i, nv, h);
+                if (lane < a.n_ranks) wt.wcnt[lane] = 0;
+                __syncwarp();
+                uint32_t own[4], rank[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    own[t] = a.owner_bits ? (uint32_t)(h[t] >> (64 - a.owner_bits)) : 0u;
+                    rank[t] = (active && t < nv) ? atomicAdd(&wt.wcnt[own[t]], 1u) : 0u;
+                }
+                __syncwarp();
+                if (lane < a.n_ranks) {
+                    const unsigned c = wt.wcnt[lane];
+                    wt.wbase[lane] = c ? atomicAdd(&a.cursor[lane], (unsigned long long)c) : 0ULL;
+                }
+                __syncwarp();
+                if (active) {
+                    const long long ko = wt.kout[sg] + i;
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        if (t < nv) {
+                            const unsigned long long pos = wt.wbase[own[t]] + rank[t];
+                            if (pos < a.send_cap) a.send[(unsigned long long)own[t] * a.send_cap + pos] = h[t];
+                            a.ridx[ko + t] = (a.owner_bits ? (own[t] << sh) : 0u) | (uint32_t)pos;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        } else if constexpr (MODE == MODE_GATHER) {
+            // K7 reply side: ids come from the owners' replies instead of local probes; same K4 rule
+            const int sh = 32 - a.owner_bits;
+            const uint32_t pmask = a.owner_bits ? ((1u << sh) - 1u) : 0xFFFFFFFFu;
+            for (int g0 = 0; g0 < G; g0 += 32) {
+                const int g = g0 + lane;
+                const bool active = g < G;
+                int sg = 0, i = 0, nv = 0;
+                uint32_t ids[4] = {SGC_MISS, SGC_MISS, SGC_MISS, SGC_MISS};
+                if (active) {
+                    int lo = 0;
+#pragma unroll
+                    for (int step = SPW / 2; step > 0; step >>= 1)
+                        if (wt.gpre[lo + step] <= g) lo += step;
+                    sg = lo;
+                    i = (g - wt.gpre[sg]) << 2;
+                    const int nk = wt.nk[sg];
+                    nv = nk - i < 4 ? nk - i : 4;
+                    const long long ko = wt.kout[sg] + i;
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        if (t < nv) {
+                            const uint32_t r = a.ridx[ko + t];
+                            const unsigned long long own = a.owner_bits ? (r >> sh) : 0u;
+                            ids[t] = a.replies[own * a.send_cap + (r & pmask)];
+                            if (ids[t] != SGC_MISS) my_hits++; else my_miss++;
+                        }
+                    }
+                }
+                if (a.kmer_ids && active) {
+                    uint32_t* o = a.kmer_ids + wt.kout[sg] + i;
+#pragma unroll
+                    for (int t = 0; t < 4; t++)
+                        if (t < nv) o[t] = ids[t];
+                }
+                emit_candidates(ids, active, sg, i, nv);
+            }
         } else {
             // MODE_LOOKUP / MODE_LABEL, software-pipelined: the 4 table probes of a group are issued
             // and left in flight while the NEXT group's 8 Murmur3 evaluations run; they are resolved
@@ -547,39 +671,7 @@ __global__ void __launch_bounds__(NT) tile_kernel(const TileArgs a) {
                         }
                     }
                 } else {
-                    // MODE_LABEL: candidate = hit whose predecessor k-mer (same segment) has another id
-                    const uint32_t prev_lane = __shfl_up_sync(0xffffffffu, ids[3], 1);
-                    unsigned long long keys[4] = {0, 0, 0, 0};
-                    unsigned nc = 0;
-                    if (p_active) {
-                        const unsigned long long sq = (unsigned long long)wt.seq[p_sg] << 32;
-                        uint32_t prev = (p_i > 0 && lane > 0) ? prev_lane : SGC_MISS;
-#pragma unroll
-                        for (int t = 0; t < 4; t++) {
-                            if (t < p_nv && ids[t] != SGC_MISS && ids[t] != prev) {
-#pragma unroll
-                                for (int u = 0; u < 4; u++)  // constant indices keep keys[] in registers
-                                    if (u == (int)nc) keys[u] = sq | ids[t];
-                                nc++;
-                            }
-                            prev = ids[t];
-                        }
-                    }
-                    unsigned incl = nc;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
-                        if (lane >= d) incl += v;
-                    }
-                    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-                    if (total) {
-                        if (pair_fill + total > PAIR_BUF) flush_pairs();
-                        unsigned pos = pair_fill + incl - nc;
-#pragma unroll
-                        for (unsigned j = 0; j < 4; j++)
-                            if (j < nc) wt.pairs[pos++] = keys[j];
-                        pair_fill += total;
-                    }
+                    emit_candidates(ids, p_active, p_sg, p_i, p_nv);
                 }
             };
 
@@ -613,10 +705,10 @@ __global__ void __launch_bounds__(NT) tile_kernel(const TileArgs a) {
         }
     }
 
-    if constexpr (MODE == MODE_LABEL) {
+    if constexpr (MODE == MODE_LABEL || MODE == MODE_GATHER) {
         if (pair_fill) flush_pairs();
     }
-    if constexpr (MODE == MODE_LOOKUP || MODE == MODE_LABEL) {
+    if constexpr (MODE == MODE_LOOKUP || MODE == MODE_LABEL || MODE == MODE_GATHER) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             my_hits += __shfl_xor_sync(0xffffffffu, my_hits, d);
@@ -914,7 +1006,7 @@ struct sgc_ctx {
     int64_t launches = 0;
     Scalars* d_scal = nullptr;
     Scalars* h_scal = nullptr;  // pinned
-    DevBuf nk, nseg, seg_first, kmer_off, seg_map, cub_tmp, pairs_a, pairs_b, tmp_hash, tmp_id, tmp_idx;
+    DevBuf nk, nseg, seg_first, kmer_off, seg_map, cub_tmp, pairs_a, pairs_b, tmp_hash, tmp_id, tmp_idx, cursor;
     // optional CUDA-event timing of the tile kernel (bench.py roofline leg)
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
@@ -1181,7 +1273,7 @@ void sgc_ctx_destroy(sgc_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->nk, &c->nseg, &c->seg_first, &c->kmer_off, &c->seg_map, &c->cub_tmp,
-                      &c->pairs_a, &c->pairs_b, &c->tmp_hash, &c->tmp_id, &c->tmp_idx};
+                      &c->pairs_a, &c->pairs_b, &c->tmp_hash, &c->tmp_id, &c->tmp_idx, &c->cursor};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->d_scal) cudaFree(c->d_scal);
@@ -1610,6 +1702,87 @@ int sgc_hash_partition(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, cons
     TRY(sgc_hash_batch(c, d_seq, seq_bytes, d_off, nseq, k, (uint64_t*)c->tmp_hash.p, cap, d_kmer_off, d_status, &total));
     return sgc_partition_pairs(c, (const uint64_t*)c->tmp_hash.p, nullptr, total, n_ranks, d_bucketed, nullptr, d_perm,
                                d_bucket_off, h_bucket_off);
+}
+
+// fused K7: hash + owner bucketing in ONE pass (no sort, no permutation array)
+int sgc_partition_hashes(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off, int64_t nseq, int k,
+                         int n_ranks, uint64_t* d_send, int64_t send_cap, uint32_t* d_ridx, int64_t ridx_cap,
+                         int32_t* d_status, int64_t* h_counts) {
+    if (!c) return fail(SGC_ERR_ARG, "ctx is NULL");
+    const int bits = log2_ranks(n_ranks);
+    if (bits < 0 || n_ranks > 32) return fail(SGC_ERR_ARG, "n_ranks must be a power of two <= 32 (got %d)", n_ranks);
+    TRY(check_seq_args(d_seq, seq_bytes, d_off, nseq, k));
+    if (send_cap < 0 || ridx_cap < 0 || !h_counts) return fail(SGC_ERR_ARG, "bad argument");
+    if (send_cap >= ((int64_t)1 << (32 - bits))) return fail(SGC_ERR_ARG, "send_cap too large for 32-bit reply indices");
+    TRY(set_device(c));
+    if (d_status) CU(cudaMemsetAsync(d_status, 0, (size_t)nseq * 4, c->stream));
+    Plan p;
+    TRY(make_plan(c, d_off, nseq, seq_bytes, k, nullptr, &p));
+    CU(cudaMemcpyAsync(&c->h_scal->n_unique, p.kmer_off + nseq, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const int64_t total = c->h_scal->n_unique;
+    if (total > ridx_cap) return fail(SGC_ERR_CAPACITY, "ridx_cap %lld < %lld k-mers", (long long)ridx_cap, (long long)total);
+    TRY(ensure(c, c->cursor, 32 * 8));
+    CU(cudaMemsetAsync(c->cursor.p, 0, 32 * 8, c->stream));
+    TRY(zero_scalars(c));
+    if (nseq > 0 && total > 0) {
+        TileArgs a = base_args(c, d_seq, d_off, k, p, d_status);
+        a.send = d_send;
+        a.send_cap = (unsigned long long)send_cap;
+        a.cursor = (unsigned long long*)c->cursor.p;
+        a.ridx = d_ridx;
+        a.owner_bits = bits;
+        a.n_ranks = n_ranks;
+        TRY(launch_tile<MODE_PARTITION>(c, a));
+    }
+    unsigned long long counts[32];
+    CU(cudaMemcpyAsync(counts, c->cursor.p, 32 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < n_ranks; r++) {
+        h_counts[r] = (int64_t)counts[r];
+        if ((int64_t)counts[r] > send_cap)
+            return fail(SGC_ERR_CAPACITY, "send_cap %lld < %llu hashes for owner %d", (long long)send_cap, counts[r], r);
+    }
+    return SGC_OK;
+}
+
+int sgc_labels_from_replies(sgc_ctx* c, const int64_t* d_off, int64_t nseq, int64_t seq_bytes, int k, int n_ranks,
+                            const uint32_t* d_ridx, const uint32_t* d_replies, int64_t send_cap, int64_t* d_ids_off,
+                            uint32_t* d_ids_out, int64_t ids_cap, uint32_t* d_kmer_ids, int64_t* h_n_kmers,
+                            int64_t* h_n_hits, int64_t* h_n_labels) {
+    if (!c) return fail(SGC_ERR_ARG, "ctx is NULL");
+    const int bits = log2_ranks(n_ranks);
+    if (bits < 0 || n_ranks > 32) return fail(SGC_ERR_ARG, "n_ranks must be a power of two <= 32 (got %d)", n_ranks);
+    TRY(check_seq_args((const void*)1, seq_bytes, d_off, nseq, k));
+    if (!d_ids_off || ids_cap < 0) return fail(SGC_ERR_ARG, "bad label buffers");
+    TRY(set_device(c));
+    Plan p;
+    TRY(make_plan(c, d_off, nseq, seq_bytes, k, nullptr, &p));
+    unsigned long long pairs_cap = (unsigned long long)std::max<int64_t>(std::max<int64_t>(ids_cap * 2, nseq * 4), 4096);
+    TRY(ensure(c, c->pairs_a, (size_t)pairs_cap * 8));
+    pairs_cap = c->pairs_a.cap / 8;
+    TRY(zero_scalars(c));
+    if (nseq > 0) {
+        TileArgs a = base_args(c, nullptr, d_off, k, p, nullptr);
+        a.pairs = (unsigned long long*)c->pairs_a.p;
+        a.pairs_cap = pairs_cap;
+        a.ridx = const_cast<uint32_t*>(d_ridx);
+        a.replies = d_replies;
+        a.send_cap = (unsigned long long)send_cap;
+        a.owner_bits = bits;
+        a.n_ranks = n_ranks;
+        a.kmer_ids = d_kmer_ids;
+        TRY(launch_tile<MODE_GATHER>(c, a));
+    }
+    TRY(fetch_scalars(c));
+    const unsigned long long n_pairs = c->h_scal->pair_count;
+    if (h_n_hits) *h_n_hits = (int64_t)c->h_scal->n_hits;
+    if (h_n_kmers) *h_n_kmers = (int64_t)(c->h_scal->n_hits + c->h_scal->n_miss);
+    if (n_pairs > pairs_cap) {
+        if (h_n_labels) *h_n_labels = (int64_t)n_pairs;
+        return fail(SGC_ERR_CAPACITY, "candidate buffer %llu < %llu", pairs_cap, n_pairs);
+    }
+    return pairs_to_csr(c, (int64_t)n_pairs, nseq, d_ids_off, d_ids_out, ids_cap, h_n_labels);
 }
 
 int sgc_unpermute_u32(sgc_ctx* c, const uint32_t* d_in, const int64_t* d_perm, int64_t n, uint32_t* d_out) {

@@ -150,6 +150,61 @@ class DeviceEngine:
                 cap = max(2 * cap, int(nl.value) + 1024)
         return d_ioff, d_out[: nl.value], nh.value
 
+    # -- fused lookup side (no sort, no permutation array) ---------------------------
+    def partition_hashes(self, seq, off, ksize, world, slack=1.08):
+        """hash + owner bucketing in one kernel.  -> (send regions [world*cap] int64, cap, ridx int32,
+        counts list, d_off, n_bytes)"""
+        torch = _torch()
+        c = self.ctx
+        d_seq = c.to_device(seq, np.uint8)
+        d_off = c.to_device(off, np.int64)
+        nseq = d_off.numel() - 1
+        n_max = max(d_seq.numel(), 1)  # k-mers <= bases
+        cap = int(n_max / world * slack) + 4096
+        from ._lib import SgcCapacityError
+
+        for _ in range(4):
+            d_send = c.empty(world * cap, torch.int64)
+            d_ridx = c.empty(n_max, torch.int32)
+            d_stat = c.empty(nseq, torch.int32)
+            h_counts = (ctypes.c_int64 * world)()
+            try:
+                check(self._L.sgc_partition_hashes(c._h, c.ptr(d_seq), d_seq.numel(), c.ptr(d_off), nseq, int(ksize),
+                                                   world, c.ptr(d_send), cap, c.ptr(d_ridx), n_max, c.ptr(d_stat),
+                                                   h_counts))
+                break
+            except SgcCapacityError:
+                cap = max(list(h_counts)) + 4096  # skewed owners: size for the real maximum and redo
+        else:
+            raise RuntimeError("partition_hashes: could not size the send regions")
+        if nseq and bool(d_stat.any().item()):
+            raise ValueError("Invalid base in read")
+        return d_send, cap, d_ridx, list(h_counts), d_off, d_seq.numel()
+
+    def labels_from_replies(self, d_off, n_bytes, ksize, world, d_ridx, d_replies, cap, want_kmer_ids=False):
+        torch = _torch()
+        c = self.ctx
+        nseq = d_off.numel() - 1
+        ids_cap = max(4 * nseq, 1024)
+        d_ioff = c.empty(nseq + 1, torch.int64)
+        d_kids = c.empty(max(n_bytes, 1), torch.int32) if want_kmer_ids else None
+        from ._lib import SgcCapacityError
+
+        for _ in range(8):
+            d_out = c.empty(ids_cap, torch.int32)
+            nk, nh, nl = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+            try:
+                check(self._L.sgc_labels_from_replies(c._h, c.ptr(d_off), nseq, n_bytes, int(ksize), world,
+                                                      c.ptr(d_ridx), c.ptr(d_replies), cap, c.ptr(d_ioff), c.ptr(d_out),
+                                                      ids_cap, c.ptr(d_kids) if d_kids is not None else None,
+                                                      ctypes.byref(nk), ctypes.byref(nh), ctypes.byref(nl)))
+                break
+            except SgcCapacityError:
+                ids_cap = max(2 * ids_cap, int(nl.value) + 1024)
+        if d_kids is not None:
+            d_kids = d_kids[: nk.value]
+        return d_ioff, d_out[: nl.value], nh.value, d_kids
+
     def sync(self):
         self.ctx.sync()
 
@@ -207,9 +262,57 @@ class PartitionedIndex:
         assert bcounts == counts
         return e.unpermute(back, perm), koff
 
+    def _label_reads_fused(self, seq, off, ksize):
+        """Fused request/reply path of the CUDA engine: one kernel hashes and appends each hash to
+        its owner's send region; the owners probe; one kernel turns the replies into labels."""
+        import torch.distributed as dist
+
+        import os
+        import time
+
+        torch = _torch()
+        e, R = self.engine, self.world
+        trace = os.environ.get("SGC_TRACE") and self.rank == 0
+        marks = []
+
+        def mark(name):
+            if trace:
+                e.sync()
+                torch.cuda.synchronize()
+                marks.append((name, time.perf_counter()))
+
+        mark("start")
+        d_send, cap, ridx, counts, d_off, n_bytes = e.partition_hashes(seq, off, ksize, R)
+        mark("hash+partition")
+        with e.stream():
+            sc = torch.tensor(counts, dtype=torch.int64, device=d_send.device)
+            rc = torch.empty(R, dtype=torch.int64, device=d_send.device)
+            dist.all_to_all_single(rc, sc, group=self.group)
+            rcounts = rc.tolist()
+            recv = torch.empty(int(sum(rcounts)), dtype=torch.int64, device=d_send.device)
+            dist.all_to_all(list(recv.split(rcounts)), [d_send[r * cap : r * cap + counts[r]] for r in range(R)],
+                            group=self.group)  # requests: 8 B per k-mer
+        mark("all-to-all requests")
+        rid = e.lookup(self.table, recv)
+        e.sync()
+        mark("owner probe")
+        with e.stream():
+            back = torch.empty(R * cap, dtype=torch.int32, device=d_send.device)
+            dist.all_to_all([back[r * cap : r * cap + counts[r]] for r in range(R)], list(rid.split(rcounts)),
+                            group=self.group)  # replies: 4 B per k-mer, same positions as the requests
+        mark("all-to-all replies")
+        ioff, ids, nh, _ = e.labels_from_replies(d_off, n_bytes, ksize, R, ridx, back, cap)
+        mark("gather+labels")
+        if trace:
+            print("[K7 trace] " + ", ".join("%s %.2f ms" % (b[0], (b[1] - a[1]) * 1e3) for a, b in zip(marks, marks[1:])),
+                  flush=True)
+        return ioff, ids, nh
+
     def label_reads(self, seq, off, ksize):
         """index_reads' per-read step against the partitioned table.
         -> (ids_off, ids, n_hits) as engine tensors"""
+        if hasattr(self.engine, "partition_hashes"):
+            return self._label_reads_fused(seq, off, ksize)
         kmer_ids, koff = self.lookup_sequences(seq, off, ksize)
         nseq = koff.numel() - 1 if hasattr(koff, "numel") else len(koff) - 1
         return self.engine.labels_from_ids(kmer_ids, koff, nseq)

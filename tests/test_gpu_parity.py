@@ -612,3 +612,46 @@ def test_full_size_properties(ctx, O):
     for j, r in enumerate(pick.tolist()):
         v = got_ids[koff[j] : koff[j + 1]]
         assert np.array_equal(np.unique(v[v != 0xFFFFFFFF]), ids_h[ioff_h[r] : ioff_h[r + 1]]), r
+
+
+def test_fused_partition_and_gather_single_gpu(ctx, O):
+    """sgc_partition_hashes + sgc_labels_from_replies (the fused K7 path) with R=4 owners emulated on
+    one GPU: every owner region holds exactly its hashes, ridx points at each k-mer's own hash, and
+    labels built from the owners' replies equal label_reads on the whole table."""
+    import torch
+
+    from spacegraphcats_b200.cdbg.hashing import GpuKmerTable
+    from spacegraphcats_b200.device import DeviceTable, pack_sequences
+    from spacegraphcats_b200.parallel import DeviceEngine
+
+    rng = np.random.default_rng(78)
+    k, R = 31, 4
+    lut = np.frombuffer(b"ACGT", np.uint8)
+    g = lut[rng.integers(0, 4, 90_000)]
+    cuts = np.concatenate([[0], np.cumsum(rng.integers(1, 150, 2000))])
+    cuts = cuts[cuts < len(g) - k]
+    useqs = [g[a : b + k - 1].tobytes() for a, b in zip(cuts[:-1], cuts[1:])]
+    reads = [g[p : p + int(n)].tobytes() for p, n in zip(rng.integers(0, len(g) - 700, 4000), rng.integers(0, 700, 4000))]
+    ubuf, uoff = pack_sequences(useqs)
+    rbuf, roff = pack_sequences(reads)
+    eng = DeviceEngine(ctx)
+    whole = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx)
+
+    d_send, cap, ridx, counts, d_off, n_bytes = eng.partition_hashes(rbuf, roff, k, R)
+    want_h, want_koff = O.hash_batch(rbuf, roff, k)
+    assert sum(counts) == len(want_h)
+    send = ctx.to_host(d_send, np.uint64).reshape(R, cap)
+    for r in range(R):
+        assert ((send[r, : counts[r]] >> np.uint64(62)) == r).all()
+        assert counts[r] == int(((want_h >> np.uint64(62)) == r).sum())
+    ri = ctx.to_host(ridx, np.uint32)[: len(want_h)]
+    assert np.array_equal(send[ri >> 30, ri & ((1 << 30) - 1)], want_h)  # every k-mer finds its own hash
+    # owners answer (here: the whole table answers every region)
+    back = ctx.empty(R * cap, torch.int32)
+    for r in range(R):
+        back[r * cap : r * cap + counts[r]] = whole._dev.lookup(d_send[r * cap : r * cap + counts[r]], to_host=False)
+    ioff, ids, nh, kids = eng.labels_from_replies(d_off, n_bytes, k, R, ridx, back, cap, want_kmer_ids=True)
+    lab = whole.label_reads(rbuf, roff, k)
+    assert np.array_equal(ctx.to_host(ioff), lab["ids_off"]) and np.array_equal(ctx.to_host(ids, np.uint32), lab["ids"])
+    assert nh == lab["n_hits"]
+    assert np.array_equal(ctx.to_host(kids, np.uint32), whole.lookup_sequences(rbuf, roff, k)["kmer_ids"])
