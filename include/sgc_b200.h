@@ -196,6 +196,25 @@ int sgc_labels_from_replies(sgc_ctx* ctx, const int64_t* d_off, int64_t nseq, in
                             int64_t send_cap, int64_t* d_ids_off, uint32_t* d_ids_out, int64_t ids_cap,
                             uint32_t* d_kmer_ids, int64_t* h_n_kmers, int64_t* h_n_hits,
                             int64_t* h_n_labels);
+/*
+ * Fused compute + exchange over NVLink peer memory (one process per GPU, buffers shared with CUDA
+ * IPC): sgc_partition_hashes_p2p stores every hash straight into its OWNER GPU's inbox
+ * (h_peer_inboxes[r] = base of GPU r's inbox, mapped in this process; this rank writes region
+ * my_rank of region_cap hashes); sgc_lookup_regions_p2p probes all source regions of the local
+ * inbox and stores every reply straight into the SOURCE GPU's reply buffer (region my_rank, same
+ * position), which is exactly the d_replies layout sgc_labels_from_replies consumes.  Between the
+ * two calls the ranks only exchange the per-region counts and a barrier.
+ */
+int sgc_partition_hashes_p2p(sgc_ctx* ctx, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off,
+                             int64_t nseq, int k, int n_ranks, int my_rank,
+                             uint64_t* const* h_peer_inboxes, int64_t region_cap, uint32_t* d_ridx,
+                             int64_t ridx_cap, int32_t* d_status, int64_t* h_counts);
+int sgc_lookup_regions_p2p(sgc_table* t, const uint64_t* d_inbox, const int64_t* h_counts_from,
+                           int64_t region_cap, int n_ranks, int my_rank, uint32_t* const* h_peer_replies);
+int sgc_peer_alloc(sgc_ctx* ctx, int64_t bytes, void** d_ptr, uint8_t* h_handle64);
+int sgc_peer_open(sgc_ctx* ctx, const uint8_t* h_handle64, void** d_ptr);
+int sgc_peer_close(sgc_ctx* ctx, void* d_ptr);
+int sgc_peer_free(sgc_ctx* ctx, void* d_ptr);
 /* d_out[d_perm[j]] = d_in[j] */
 int sgc_unpermute_u32(sgc_ctx* ctx, const uint32_t* d_in, const int64_t* d_perm, int64_t n,
                       uint32_t* d_out);

@@ -12,6 +12,7 @@ ap.add_argument("--table-kmers", type=float, default=4e8)
 ap.add_argument("--reads", type=float, default=4e6)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--p2p", action="store_true", help="fuse the exchange into the kernels (NVLink peer stores)")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29511")
@@ -37,7 +38,7 @@ with torch.cuda.stream(ctx.stream):
     ids = torch.arange(ulo, uhi, dtype=torch.int32, device=ctx.device)
 eng = DeviceEngine(ctx)
 t0 = time.time()
-idx = PartitionedIndex(eng).build(useq, uoff, K, ids)
+idx = PartitionedIndex(eng, p2p=args.p2p).build(useq, uoff, K, ids)
 ctx.sync(); dist.barrier()
 if rank == 0:
     print("partitioned build: %.2fs, rank0 holds %d hashes (%.2f GB)" % (time.time() - t0, idx.n_local, idx.table.nbytes / 1e9), flush=True)
@@ -59,6 +60,6 @@ if args.check:
     okt = torch.tensor([1 if ok else 0], device=ctx.device); dist.all_reduce(okt, op=dist.ReduceOp.MIN)
     if rank == 0: print("labels identical to the replicated table on every rank:", bool(okt.item()), flush=True)
 if rank == 0:
-    print(json.dumps({"mode": "partitioned", "n_gpus": world, "table_kmers": n_kmers, "reads_per_rank_step": n_reads,
+    print(json.dumps({"mode": "partitioned-p2p" if args.p2p else "partitioned-nccl", "n_gpus": world, "table_kmers": n_kmers, "reads_per_rank_step": n_reads,
                       "value": rate, "unit": "k-mers/s", "ms_per_step": float(t.item()) / args.steps * 1e3}), flush=True)
 dist.destroy_process_group()

@@ -64,6 +64,12 @@ PROTOTYPES = {
     "sgc_labels_from_ids": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _pi64, _pi64]),
     "sgc_unpermute_u32": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "sgc_partition_hashes": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _pi64]),
+    "sgc_partition_hashes_p2p": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _pi64]),
+    "sgc_lookup_regions_p2p": (_i32, [_vp, _vp, _pi64, _i64, _i32, _i32, _vp]),
+    "sgc_peer_alloc": (_i32, [_vp, _i64, ctypes.POINTER(_vp), _vp]),
+    "sgc_peer_open": (_i32, [_vp, _vp, ctypes.POINTER(_vp)]),
+    "sgc_peer_close": (_i32, [_vp, _vp]),
+    "sgc_peer_free": (_i32, [_vp, _vp]),
     "sgc_labels_from_replies": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _pi64, _pi64, _pi64]),
     "sgc_ctx_set_timing": (_i32, [_vp, _i32]),
     "sgc_ctx_tile_ms": (_i32, [_vp, ctypes.POINTER(ctypes.c_double), _pi64]),

@@ -134,6 +134,9 @@ struct TileArgs {
     unsigned long long zero;  // always 0 (scheduling dependency, see the pipelined probe loop)
     // MODE_PARTITION (hash -> owner rank's send region) / MODE_GATHER (replies -> labels)
     uint64_t* send;                 // n_ranks regions of send_cap hashes
+    uint64_t* peer_send[32];        // where owner r's requests go: send + r*send_cap locally, or the
+                                    // peer-mapped inbox of GPU r (P2P stores over NVLink)
+    unsigned long long send_region_off;  // my region inside a peer inbox (my_rank * send_cap), else 0
     unsigned long long send_cap;
     unsigned long long* cursor;     // n_ranks fill counters
     uint32_t* ridx;                 // per k-mer: owner << (32 - owner_bits) | position in the owner's region
@@ -565,7 +568,7 @@ __global__ void __launch_bounds__(NT) tile_kernel(const TileArgs a) {
                     for (int t = 0; t < 4; t++) {
                         if (t < nv) {
                             const unsigned long long pos = wt.wbase[own[t]] + rank[t];
-                            if (pos < a.send_cap) a.send[(unsigned long long)own[t] * a.send_cap + pos] = h[t];
+                            if (pos < a.send_cap) a.peer_send[own[t]][a.send_region_off + pos] = h[t];
                             a.ridx[ko + t] = (a.owner_bits ? (own[t] << sh) : 0u) | (uint32_t)pos;
                         }
                     }
@@ -1705,9 +1708,10 @@ int sgc_hash_partition(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, cons
 }
 
 // fused K7: hash + owner bucketing in ONE pass (no sort, no permutation array)
-int sgc_partition_hashes(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off, int64_t nseq, int k,
-                         int n_ranks, uint64_t* d_send, int64_t send_cap, uint32_t* d_ridx, int64_t ridx_cap,
-                         int32_t* d_status, int64_t* h_counts) {
+static int partition_hashes_impl(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off,
+                                 int64_t nseq, int k, int n_ranks, uint64_t* d_send, int64_t send_cap,
+                                 uint32_t* d_ridx, int64_t ridx_cap, int32_t* d_status, int64_t* h_counts,
+                                 uint64_t* const* h_peer_inboxes, int my_rank) {
     if (!c) return fail(SGC_ERR_ARG, "ctx is NULL");
     const int bits = log2_ranks(n_ranks);
     if (bits < 0 || n_ranks > 32) return fail(SGC_ERR_ARG, "n_ranks must be a power of two <= 32 (got %d)", n_ranks);
@@ -1729,6 +1733,9 @@ int sgc_partition_hashes(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, co
         TileArgs a = base_args(c, d_seq, d_off, k, p, d_status);
         a.send = d_send;
         a.send_cap = (unsigned long long)send_cap;
+        for (int r = 0; r < n_ranks; r++)
+            a.peer_send[r] = h_peer_inboxes ? h_peer_inboxes[r] : d_send + (size_t)r * (size_t)send_cap;
+        a.send_region_off = h_peer_inboxes ? (unsigned long long)my_rank * (unsigned long long)send_cap : 0ULL;
         a.cursor = (unsigned long long*)c->cursor.p;
         a.ridx = d_ridx;
         a.owner_bits = bits;
@@ -1742,6 +1749,83 @@ int sgc_partition_hashes(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, co
         h_counts[r] = (int64_t)counts[r];
         if ((int64_t)counts[r] > send_cap)
             return fail(SGC_ERR_CAPACITY, "send_cap %lld < %llu hashes for owner %d", (long long)send_cap, counts[r], r);
+    }
+    return SGC_OK;
+}
+
+int sgc_partition_hashes(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off, int64_t nseq, int k,
+                         int n_ranks, uint64_t* d_send, int64_t send_cap, uint32_t* d_ridx, int64_t ridx_cap,
+                         int32_t* d_status, int64_t* h_counts) {
+    if (!d_send) return fail(SGC_ERR_ARG, "d_send is NULL");
+    return partition_hashes_impl(c, d_seq, seq_bytes, d_off, nseq, k, n_ranks, d_send, send_cap, d_ridx, ridx_cap,
+                                 d_status, h_counts, nullptr, 0);
+}
+
+// the same with the exchange fused in: every hash is stored straight into its owner GPU's inbox
+int sgc_partition_hashes_p2p(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off, int64_t nseq,
+                             int k, int n_ranks, int my_rank, uint64_t* const* h_peer_inboxes, int64_t region_cap,
+                             uint32_t* d_ridx, int64_t ridx_cap, int32_t* d_status, int64_t* h_counts) {
+    if (!h_peer_inboxes || my_rank < 0 || my_rank >= n_ranks) return fail(SGC_ERR_ARG, "bad peer arguments");
+    return partition_hashes_impl(c, d_seq, seq_bytes, d_off, nseq, k, n_ranks, nullptr, region_cap, d_ridx, ridx_cap,
+                                 d_status, h_counts, h_peer_inboxes, my_rank);
+}
+
+// owner side of the fused exchange: probe the requests of every source region of my inbox and store
+// each reply straight into the source GPU's reply buffer (region my_rank, same position)
+int sgc_lookup_regions_p2p(sgc_table* t, const uint64_t* d_inbox, const int64_t* h_counts_from, int64_t region_cap,
+                           int n_ranks, int my_rank, uint32_t* const* h_peer_replies) {
+    if (!t || !d_inbox || !h_counts_from || !h_peer_replies) return fail(SGC_ERR_ARG, "NULL argument");
+    if (n_ranks < 1 || n_ranks > 32 || my_rank < 0 || my_rank >= n_ranks) return fail(SGC_ERR_ARG, "bad ranks");
+    sgc_ctx* c = t->ctx;
+    TRY(set_device(c));
+    for (int s = 0; s < n_ranks; s++) {
+        const int64_t n = h_counts_from[s];
+        if (n < 0 || n > region_cap) return fail(SGC_ERR_ARG, "bad region count");
+        if (n == 0) continue;
+        lookup_kernel<<<grid_for((n + 1) / 2, 256, c->num_sms * 8), 256, 0, c->stream>>>(
+            t->buckets, t->nbuckets, t->nlines, t->home_shift, d_inbox + (size_t)s * (size_t)region_cap, n,
+            h_peer_replies[s] + (size_t)my_rank * (size_t)region_cap);
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    return SGC_OK;
+}
+
+// peer-visible device memory (CUDA IPC): allocate here, open in the other ranks' processes
+int sgc_peer_alloc(sgc_ctx* c, int64_t bytes, void** d_ptr, uint8_t* h_handle64) {
+    if (!c || !d_ptr || !h_handle64 || bytes <= 0) return fail(SGC_ERR_ARG, "bad argument");
+    TRY(set_device(c));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaError_t e = cudaMalloc(d_ptr, (size_t)bytes);
+    if (e != cudaSuccess) return fail(SGC_ERR_NOMEM, "cudaMalloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e));
+    cudaIpcMemHandle_t hnd;
+    CU(cudaIpcGetMemHandle(&hnd, *d_ptr));
+    memcpy(h_handle64, &hnd, 64);
+    return SGC_OK;
+}
+
+int sgc_peer_open(sgc_ctx* c, const uint8_t* h_handle64, void** d_ptr) {
+    if (!c || !d_ptr || !h_handle64) return fail(SGC_ERR_ARG, "bad argument");
+    TRY(set_device(c));
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, h_handle64, 64);
+    CU(cudaIpcOpenMemHandle(d_ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+    return SGC_OK;
+}
+
+int sgc_peer_close(sgc_ctx* c, void* d_ptr) {
+    if (!c) return fail(SGC_ERR_ARG, "ctx is NULL");
+    TRY(set_device(c));
+    if (d_ptr) CU(cudaIpcCloseMemHandle(d_ptr));
+    return SGC_OK;
+}
+
+int sgc_peer_free(sgc_ctx* c, void* d_ptr) {
+    if (!c) return fail(SGC_ERR_ARG, "ctx is NULL");
+    TRY(set_device(c));
+    if (d_ptr) {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaFree(d_ptr));
     }
     return SGC_OK;
 }

@@ -57,6 +57,16 @@ def exchange(send, send_counts, group=None):
     return recv, recv_counts
 
 
+class _RawPtr:
+    """Minimal stand-in for a tensor where only ``data_ptr()`` is needed (library-owned memory)."""
+
+    def __init__(self, ptr):
+        self._p = int(ptr)
+
+    def data_ptr(self):
+        return self._p
+
+
 class DeviceEngine:
     """CUDA engine: every step is a kernel of libsgc_b200.so on the context's stream."""
 
@@ -216,14 +226,68 @@ class DeviceEngine:
         return self.ctx.to_host(t, dtype)
 
 
+class PeerBuffers:
+    """This rank's inbox (R regions of region_cap hashes) and reply buffer (R regions of region_cap
+    ids), allocated by the library and mapped into every other rank's process with CUDA IPC, so
+    kernels store requests / replies straight into the destination GPU over NVLink."""
+
+    def __init__(self, ctx, group, region_cap):
+        import torch.distributed as dist
+
+        self.ctx, self.group = ctx, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.region_cap = int(region_cap)
+        L = ctx._L
+        self._own = []
+        handles = []
+        for nbytes in (self.world * self.region_cap * 8, self.world * self.region_cap * 4):
+            ptr = ctypes.c_void_p()
+            hnd = (ctypes.c_uint8 * 64)()
+            check(L.sgc_peer_alloc(ctx._h, nbytes, ctypes.byref(ptr), hnd))
+            self._own.append(ptr)
+            handles.append(bytes(hnd))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, handles, group=group)
+        self._opened = []
+        self.inbox_ptrs = (ctypes.c_void_p * self.world)()
+        self.reply_ptrs = (ctypes.c_void_p * self.world)()
+        for r in range(self.world):
+            for which, arr in ((0, self.inbox_ptrs), (1, self.reply_ptrs)):
+                if r == self.rank:
+                    arr[r] = self._own[which].value
+                else:
+                    ptr = ctypes.c_void_p()
+                    hnd = (ctypes.c_uint8 * 64).from_buffer_copy(everyone[r][which])
+                    check(L.sgc_peer_open(ctx._h, hnd, ctypes.byref(ptr)))
+                    self._opened.append(ptr)
+                    arr[r] = ptr.value
+        self.inbox = self._own[0]
+        self.replies = self._own[1]
+
+    def close(self):
+        import torch.distributed as dist
+
+        L = self.ctx._L
+        self.ctx.sync()
+        for ptr in self._opened:
+            L.sgc_peer_close(self.ctx._h, ptr)
+        self._opened = []
+        dist.barrier(group=self.group)  # nobody still maps our memory
+        for ptr in self._own:
+            L.sgc_peer_free(self.ctx._h, ptr)
+        self._own = []
+
+
 class PartitionedIndex:
     """k-mer -> unitig table hash-range partitioned over the ranks of a process group."""
 
-    def __init__(self, engine, group=None):
+    def __init__(self, engine, group=None, p2p=False):
         import torch.distributed as dist
 
         self.engine = engine
         self.group = group
+        self.p2p = bool(p2p)  # fuse the exchange into the kernels over NVLink peer memory
+        self._peers = None
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.bits = log2_ranks(self.world)
@@ -308,9 +372,75 @@ class PartitionedIndex:
                   flush=True)
         return ioff, ids, nh
 
+    def _label_reads_p2p(self, seq, off, ksize):
+        """Exchange fused into the kernels: the hash kernel stores each hash straight into its owner
+        GPU's inbox, the owner's probe kernel stores each id straight into the requester's reply
+        buffer (peer memory over NVLink).  Per step the ranks exchange only the region counts (which
+        also orders the stores) and one barrier."""
+        import os
+        import time
+
+        import torch.distributed as dist
+
+        torch = _torch()
+        e, R, c = self.engine, self.world, self.engine.ctx
+        L = c._L
+        trace = os.environ.get("SGC_TRACE") and self.rank == 0
+        marks = [("start", time.perf_counter())] if trace else []
+
+        def mark(name):
+            if trace:
+                c.sync()
+                torch.cuda.synchronize()
+                marks.append((name, time.perf_counter()))
+
+        d_seq = c.to_device(seq, np.uint8)
+        d_off = c.to_device(off, np.int64)
+        nseq, n_bytes = d_off.numel() - 1, d_seq.numel()
+        need = int(max(n_bytes, 1) / R * 1.08) + 4096
+        with e.stream():
+            t = torch.tensor([need], dtype=torch.int64, device=c.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        need = int(t.item())
+        if self._peers is None or self._peers.region_cap < need:
+            if self._peers is not None:
+                self._peers.close()
+            self._peers = PeerBuffers(c, self.group, need)
+        pb = self._peers
+        cap = pb.region_cap
+        d_ridx = c.empty(max(n_bytes, 1), torch.int32)
+        d_stat = c.empty(nseq, torch.int32)
+        h_counts = (ctypes.c_int64 * R)()
+        mark("setup")
+        check(L.sgc_partition_hashes_p2p(c._h, c.ptr(d_seq), n_bytes, c.ptr(d_off), nseq, int(ksize), R, self.rank,
+                                         pb.inbox_ptrs, cap, c.ptr(d_ridx), max(n_bytes, 1), c.ptr(d_stat), h_counts))
+        if nseq and bool(d_stat.any().item()):
+            raise ValueError("Invalid base in read")
+        mark("hash + P2P stores into the owners' inboxes")
+        with e.stream():
+            sc = torch.tensor(list(h_counts), dtype=torch.int64, device=c.device)
+            rc = torch.empty(R, dtype=torch.int64, device=c.device)
+            dist.all_to_all_single(rc, sc, group=self.group)  # also orders every rank's stores before the probes
+        counts_from = (ctypes.c_int64 * R)(*rc.tolist())
+        mark("counts")
+        check(L.sgc_lookup_regions_p2p(self.table._h, pb.inbox, counts_from, cap, R, self.rank, pb.reply_ptrs))
+        c.sync()
+        mark("owner probe + P2P stores of the replies")
+        with e.stream():
+            dist.barrier(group=self.group)  # all replies have landed; all inboxes may be reused
+        mark("barrier")
+        ioff, ids, nh, _ = e.labels_from_replies(d_off, n_bytes, ksize, R, d_ridx, _RawPtr(pb.replies.value), cap)
+        mark("gather+labels")
+        if trace:
+            print("[K7 p2p trace] " + ", ".join("%s %.2f ms" % (b[0], (b[1] - a[1]) * 1e3) for a, b in zip(marks, marks[1:])),
+                  flush=True)
+        return ioff, ids, nh
+
     def label_reads(self, seq, off, ksize):
         """index_reads' per-read step against the partitioned table.
         -> (ids_off, ids, n_hits) as engine tensors"""
+        if self.p2p and hasattr(self.engine, "partition_hashes"):
+            return self._label_reads_p2p(seq, off, ksize)
         if hasattr(self.engine, "partition_hashes"):
             return self._label_reads_fused(seq, off, ksize)
         kmer_ids, koff = self.lookup_sequences(seq, off, ksize)

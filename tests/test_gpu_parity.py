@@ -655,3 +655,25 @@ def test_fused_partition_and_gather_single_gpu(ctx, O):
     assert np.array_equal(ctx.to_host(ioff), lab["ids_off"]) and np.array_equal(ctx.to_host(ids, np.uint32), lab["ids"])
     assert nh == lab["n_hits"]
     assert np.array_equal(ctx.to_host(kids, np.uint32), whole.lookup_sequences(rbuf, roff, k)["kmer_ids"])
+
+
+def test_partitioned_two_gpus_p2p_and_nccl_match_replicated():
+    """2 ranks on 2 GPUs (skipped on a 1-GPU box): hash-range partitioned table, exchange fused into
+    the kernels over NVLink peer memory (--p2p) and through NCCL all-to-all; both must give the
+    labels of the replicated table on every rank."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from conftest import ROOT
+
+    for extra in (["--p2p"], []):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+               "127.0.0.1", "--master-port", "29547", os.path.join(ROOT, "scripts", "partitioned_run.py"),
+               "--table-kmers", "2e7", "--reads", "3e5", "--steps", "2", "--check"] + extra
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert "labels identical to the replicated table on every rank: True" in out.stdout
