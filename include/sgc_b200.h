@@ -73,6 +73,19 @@ int sgc_hash_batch(sgc_ctx* ctx, const uint8_t* d_seq, int64_t seq_bytes, const 
                    int64_t* d_kmer_off, int32_t* d_status, int64_t* h_total_kmers);
 
 /*
+ * sourmash-style DNA k-mer hash, next rows f3/f4 of the scope table: for every k-mer
+ * MurmurHash3_x64_128(min(kmer, revcomp(kmer)), k, seed).lo64 (lexicographic minimum of the ASCII
+ * strings; sourmash uses seed 42).  Replaces MinHash.add_sequence as used for the per-unitig
+ * n=1 MinHash of cdbg/sort_bcalm_unitigs.py:56-128 (d_seq_min[s] = minimum hash of sequence s,
+ * UINT64_MAX when it has no k-mer) and for scaled signatures (search/query_by_sequence.py:52-89,176:
+ * d_hash_out holds every hash, the caller keeps those below 2^64/scaled).  Either output may be NULL.
+ */
+int sgc_minhash_batch(sgc_ctx* ctx, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off,
+                      int64_t nseq, int k, uint64_t seed, uint64_t* d_hash_out, int64_t hash_cap,
+                      int64_t* d_kmer_off, uint64_t* d_seq_min, int32_t* d_status,
+                      int64_t* h_total_kmers);
+
+/*
  * K2 -- replaces BBHashTable() + .initialize(list(all_kmers)) + table[kmer] = cdbg_id,
  * i.e. build_mphf(), cdbg/index_cdbg_by_kmer.py:27-115.
  * sgc_table_create sizes an empty table for up to max_entries distinct hashes; load = expected

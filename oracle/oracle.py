@@ -125,6 +125,21 @@ def hash_sequence_py(seq, ksize):
     return [hash_kmer_py(seq[i : i + ksize]) for i in range(len(seq) - ksize + 1)]
 
 
+def minhash_kmer_py(kmer, seed=42):
+    """sourmash DNA k-mer hash: Murmur3_x64_128(min(kmer, revcomp(kmer)), seed).h1 -- the hash behind
+    MinHash.add_sequence (sourmash is third-party and absent; pinned by the reference's own
+    ``min_hashval`` column, cdbg/sort_bcalm_unitigs.py:56-128, tests/golden/dory_k21_min_hashval.json)."""
+    if isinstance(kmer, str):
+        kmer = kmer.encode()
+    return murmur3_x64_128(min(kmer, revcomp(kmer)), seed)[0]
+
+
+def minhash_sequence_py(seq, ksize, seed=42):
+    if isinstance(seq, str):
+        seq = seq.encode()
+    return [minhash_kmer_py(seq[i : i + ksize], seed) for i in range(len(seq) - ksize + 1)]
+
+
 # --------------------------------------------------------------------------
 # C oracle (sgc_oracle.c) through ctypes
 # --------------------------------------------------------------------------

@@ -44,6 +44,7 @@ PROTOTYPES = {
     "sgc_ctx_stream": (_vp, [_vp]),
     "sgc_ctx_launches": (_i64, [_vp]),
     "sgc_hash_batch": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _pi64]),
+    "sgc_minhash_batch": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, ctypes.c_uint64, _vp, _i64, _vp, _vp, _vp, _pi64]),
     "sgc_table_create": (_i32, [_vp, _i64, ctypes.c_float, ctypes.POINTER(_vp)]),
     "sgc_table_free": (None, [_vp]),
     "sgc_table_insert_pairs": (_i32, [_vp, _vp, _vp, _i64]),

@@ -58,6 +58,9 @@ int fail(int code, const char* fmt, ...) {
 // ----------------------------------------------------------------------------------
 // tile geometry
 // ----------------------------------------------------------------------------------
+#ifndef SGC_PROBE_MIN_CTAS
+#define SGC_PROBE_MIN_CTAS 2
+#endif
 constexpr int NT = 256;         // threads per CTA
 constexpr int WPB = NT / 32;    // warps per CTA; every warp runs its own rounds (no block barriers)
 constexpr int SPW = 8;          // segments staged per warp round (4 lanes stage one segment)
@@ -68,7 +71,7 @@ constexpr unsigned long long SEQ_MASK = (1ULL << 40) - 1ULL;
 constexpr uint32_t VAL_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t VAL_MULTI = 0xFFFFFFFEu;
 
-enum Mode { MODE_HASH = 0, MODE_INSERT = 1, MODE_LOOKUP = 2, MODE_LABEL = 3, MODE_PARTITION = 4, MODE_GATHER = 5 };
+enum Mode { MODE_HASH = 0, MODE_INSERT = 1, MODE_LOOKUP = 2, MODE_LABEL = 3, MODE_PARTITION = 4, MODE_GATHER = 5, MODE_MINHASH = 6 };
 
 template <int K>
 struct Geo {
@@ -116,8 +119,10 @@ struct TileArgs {
     int32_t* status;
     Scalars* scal;
     int k;
-    // MODE_HASH
+    // MODE_HASH / MODE_MINHASH
     uint64_t* hash_out;
+    unsigned long long* seq_min;    // MODE_MINHASH: per-sequence minimum (atomicMin), nullable
+    unsigned long long seed;        // MODE_MINHASH: Murmur3 seed (sourmash: 42)
     // table (MODE_INSERT / MODE_LOOKUP / MODE_LABEL)
     Bucket* tbl;
     uint32_t nbuckets;
@@ -348,7 +353,7 @@ struct WarpTile {
 };
 
 template <int K, int MODE>
-__global__ void __launch_bounds__(NT) tile_kernel(const TileArgs a) {
+__global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP) ? SGC_PROBE_MIN_CTAS : 1) tile_kernel(const TileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int WPS = Geo<K>::WPS;
     const int lane = threadIdx.x & 31;
@@ -515,7 +520,56 @@ __global__ void __launch_bounds__(NT) tile_kernel(const TileArgs a) {
             }
         };
 
-        if constexpr (MODE == MODE_HASH || MODE == MODE_INSERT) {
+        if constexpr (MODE == MODE_MINHASH) {
+            // sourmash-style hash: Murmur3(min(kmer, revcomp), seed); all hashes and/or the per-sequence
+            // minimum (MinHash n=1 of cdbg/sort_bcalm_unitigs.py:56-128)
+            for (int g0 = 0; g0 < G; g0 += 32) {
+                const int g = g0 + lane;
+                if (g >= G) continue;
+                int lo = 0;
+#pragma unroll
+                for (int step = SPW / 2; step > 0; step >>= 1)
+                    if (wt.gpre[lo + step] <= g) lo += step;
+                const int sg = lo, i = (g - wt.gpre[sg]) << 2;
+                const int nk = wt.nk[sg];
+                const int nv = nk - i < 4 ? nk - i : 4;
+                const uint32_t* Fs = wt.F + sg * WPS;
+                const uint32_t* Rs = wt.R + sg * WPS;
+                uint64_t h[4] = {~0ULL, ~0ULL, ~0ULL, ~0ULL};
+                if constexpr (K != 0) {
+                    constexpr int NWIN = sgc::KW<K ? K : 1>::NWIN;
+                    uint32_t fw[NWIN], rw[NWIN];
+                    const uint32_t* fp = Fs + (i >> 2);
+                    const uint32_t* rp = Rs + sgc::rc_group_word(nk, i);
+#pragma unroll
+                    for (int j = 0; j < NWIN; j++) {
+                        fw[j] = fp[j];
+                        rw[j] = rp[j];
+                    }
+#pragma unroll
+                    for (int t = 0; t < 4; t++)
+                        if (t < nv) h[t] = sgc::minhash_group_kmer<K ? K : 1>(fw, rw, t, a.seed);
+                } else {
+                    for (int t = 0; t < nv; t++) {
+                        const int q = i + t, rq = sgc::rc_byte_of(nk, nk - 1 - q);
+                        h[t] = sgc::stream_less(Rs, rq, Fs, q, k) ? sgc::murmur3_h1_stream(Rs, rq, k, a.seed)
+                                                                  : sgc::murmur3_h1_stream(Fs, q, k, a.seed);
+                    }
+                }
+                if (a.hash_out) {
+                    uint64_t* o = a.hash_out + wt.kout[sg] + i;
+#pragma unroll
+                    for (int t = 0; t < 4; t++)
+                        if (t < nv) o[t] = h[t];
+                }
+                if (a.seq_min) {
+                    uint64_t m = h[0];
+#pragma unroll
+                    for (int t = 1; t < 4; t++) m = h[t] < m ? h[t] : m;
+                    atomicMin(&a.seq_min[wt.seq[sg]], (unsigned long long)m);
+                }
+            }
+        } else if constexpr (MODE == MODE_HASH || MODE == MODE_INSERT) {
             for (int g0 = 0; g0 < G; g0 += 32) {
                 const int g = g0 + lane;
                 if (g >= G) continue;
@@ -1321,6 +1375,35 @@ int sgc_hash_batch(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, const in
     TileArgs a = base_args(c, d_seq, d_off, k, p, d_status);
     a.hash_out = d_hash_out;
     return launch_tile<MODE_HASH>(c, a);
+}
+
+// sourmash-style MinHash primitives (rows f3 / f4 of SURVEY.md 8f)
+int sgc_minhash_batch(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off, int64_t nseq, int k,
+                      uint64_t seed, uint64_t* d_hash_out, int64_t hash_cap, int64_t* d_kmer_off, uint64_t* d_seq_min,
+                      int32_t* d_status, int64_t* h_total_kmers) {
+    if (!c) return fail(SGC_ERR_ARG, "ctx is NULL");
+    TRY(check_seq_args(d_seq, seq_bytes, d_off, nseq, k));
+    TRY(set_device(c));
+    Plan p;
+    TRY(make_plan(c, d_off, nseq, seq_bytes, k, d_kmer_off, &p));
+    int64_t total = -1;
+    if ((d_hash_out && hash_cap < seq_bytes) || h_total_kmers) {
+        CU(cudaMemcpyAsync(&c->h_scal->n_unique, p.kmer_off + nseq, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        total = c->h_scal->n_unique;
+        if (h_total_kmers) *h_total_kmers = total;
+        if (d_hash_out && total > hash_cap)
+            return fail(SGC_ERR_CAPACITY, "hash_cap %lld < %lld k-mers", (long long)hash_cap, (long long)total);
+    }
+    if (d_status) CU(cudaMemsetAsync(d_status, 0, (size_t)nseq * 4, c->stream));
+    if (d_seq_min && nseq) CU(cudaMemsetAsync(d_seq_min, 0xFF, (size_t)nseq * 8, c->stream));
+    if (nseq == 0 || total == 0) return SGC_OK;
+    TRY(zero_scalars(c));
+    TileArgs a = base_args(c, d_seq, d_off, k, p, d_status);
+    a.hash_out = d_hash_out;
+    a.seq_min = (unsigned long long*)d_seq_min;
+    a.seed = seed;
+    return launch_tile<MODE_MINHASH>(c, a);
 }
 
 // ---------------------------------------------------------------------------- K2

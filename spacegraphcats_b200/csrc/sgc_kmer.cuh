@@ -90,10 +90,10 @@ SGC_HD uint64_t u64_of(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) |
 // constant so that the block loop and the tail are fully unrolled.
 // ---------------------------------------------------------------------------
 template <int K>
-SGC_HD uint64_t murmur3_h1_words(const uint32_t* w) {
+SGC_HD uint64_t murmur3_h1_words(const uint32_t* w, uint64_t seed = 0) {
     constexpr int NB = K / 16;
     constexpr int TAIL = K % 16;
-    uint64_t h1 = 0, h2 = 0;
+    uint64_t h1 = seed, h2 = seed;
 #pragma unroll
     for (int b = 0; b < NB; b++) {
         uint64_t k1 = u64_of(w[4 * b], w[4 * b + 1]);
@@ -142,6 +142,41 @@ SGC_HD uint64_t murmur3_h1_window(const uint32_t* win, int shift) {
     return murmur3_h1_words<K>(w);
 }
 
+SGC_HD uint32_t bswap32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(x, 0u, 0x0123u);
+#else
+    return (x >> 24) | ((x >> 8) & 0xFF00u) | ((x << 8) & 0xFF0000u) | (x << 24);
+#endif
+}
+
+// sourmash-style DNA k-mer hash: MurmurHash3_x64_128(min(kmer, revcomp(kmer)), K, seed).h1 with the
+// minimum taken lexicographically on the ASCII strings (sourmash add_sequence / MinHash; used by
+// cdbg/sort_bcalm_unitigs.py:56-128 with seed 42, n=1).  Same window convention as hash_group_kmer.
+template <int K>
+SGC_HD uint64_t minhash_group_kmer(const uint32_t* fwin, const uint32_t* rwin, int t, uint64_t seed) {
+    constexpr int NWK = KW<K>::NWK;
+    constexpr int NWIN = KW<K>::NWIN;
+    uint32_t f[NWK], r[NWK];
+#pragma unroll
+    for (int j = 0; j < NWK; j++) {
+        f[j] = funnel_bytes(fwin[j], (j + 1 < NWIN) ? fwin[j + 1] : 0u, t);
+        r[j] = funnel_bytes(rwin[j], (j + 1 < NWIN) ? rwin[j + 1] : 0u, 3 - t);
+    }
+    f[NWK - 1] &= KW<K>::LASTMASK;
+    r[NWK - 1] &= KW<K>::LASTMASK;
+    bool r_less = false;  // scan from the last word to the first: the earliest difference decides
+#pragma unroll
+    for (int j = NWK - 1; j >= 0; j--) {
+        const uint32_t a = bswap32(f[j]), b = bswap32(r[j]);
+        r_less = (b < a) || (b == a && r_less);
+    }
+    uint32_t w[NWK];
+#pragma unroll
+    for (int j = 0; j < NWK; j++) w[j] = r_less ? r[j] : f[j];
+    return murmur3_h1_words<K>(w, seed);
+}
+
 // Hash of k-mer t (0..3) of a group: fwin = forward words at the group's aligned
 // start, rwin = RC words at the group's aligned RC start (see header comment).
 template <int K>
@@ -163,9 +198,9 @@ SGC_HD uint64_t keep_low_bytes(uint64_t v, int n /*1..8*/) {
     return n >= 8 ? v : (v & ((1ULL << (8 * n)) - 1ULL));
 }
 
-SGC_HD uint64_t murmur3_h1_stream(const uint32_t* base, int byteoff, int k) {
+SGC_HD uint64_t murmur3_h1_stream(const uint32_t* base, int byteoff, int k, uint64_t seed = 0) {
     const int nb = k >> 4, tail = k & 15;
-    uint64_t h1 = 0, h2 = 0;
+    uint64_t h1 = seed, h2 = seed;
     for (int b = 0; b < nb; b++) {
         uint64_t k1 = load_le64_at(base, byteoff + 16 * b);
         uint64_t k2 = load_le64_at(base, byteoff + 16 * b + 8);
@@ -181,6 +216,23 @@ SGC_HD uint64_t murmur3_h1_stream(const uint32_t* base, int byteoff, int k) {
     h1 = fmix64(h1); h2 = fmix64(h2);
     h1 += h2;
     return h1;
+}
+
+// true when the k bytes at (rbase, roff) are lexicographically smaller than those at (fbase, foff)
+SGC_HD bool stream_less(const uint32_t* rbase, int roff, const uint32_t* fbase, int foff, int k) {
+    for (int j = 0; j < k; j += 8) {
+        const int n = k - j < 8 ? k - j : 8;
+        const uint64_t a = keep_low_bytes(load_le64_at(rbase, roff + j), n);
+        const uint64_t b = keep_low_bytes(load_le64_at(fbase, foff + j), n);
+        if (a != b) {
+            const uint64_t d = a ^ b;  // lowest differing byte = earliest string position
+            const uint64_t low = d & (~d + 1);
+            int sh = 0;
+            while (!((low >> sh) & 0xFFULL)) sh += 8;
+            return ((a >> sh) & 0xFFULL) < ((b >> sh) & 0xFFULL);
+        }
+    }
+    return false;
 }
 
 // khmer _revcomp base map; every byte other than A,C,G,T maps to itself (that is how

@@ -11,6 +11,8 @@ against it:
 
   dory_k21_unitigs.tsv.gz      <- tests/test-data/catlas.dory_k21/bcalm.unitigs.db
                                   (sqlite ``sequences(id, sequence)``; "id<TAB>sequence")
+  dory_k21_min_hashval.json    <- same DB, column ``min_hashval`` (sourmash MinHash n=1, seed 42, written by
+                                  cdbg/sort_bcalm_unitigs.py:56-128)
   dory_k21_contigs.indices.npz <- .../catlas.dory_k21/contigs.indices  (verbatim; written
                                   by the reference's BBHashTable.save: mphf_to_hash u64[n],
                                   mphf_to_value u32[n] -- 212,475 (hash -> unitig id) pairs)
@@ -56,6 +58,9 @@ def main():
         with gzip.GzipFile(filename="", mode="wb", fileobj=raw, mtime=0) as fo:
             for i, s in rows:
                 fo.write(("%d\t%s\n" % (i, s)).encode())
+    mins = db.execute("SELECT id, min_hashval FROM sequences ORDER BY id").fetchall()
+    with open(out("dory_k21_min_hashval.json"), "w") as fp:  # sourmash n=1 MinHash (seed 42) per unitig
+        json.dump({str(i): int(v) for i, v in mins}, fp)
     shutil.copyfile(ref("tests/test-data/catlas.dory_k21/contigs.indices"), out("dory_k21_contigs.indices.npz"))
     with open(ref("tests/test-data/catlas.dory_k21/contigs.sizes"), "rb") as fp:
         k, sizes = pickle.load(fp)

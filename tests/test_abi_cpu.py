@@ -91,6 +91,27 @@ def test_host_emulation_of_tile_geometry_matches_oracle():
                 assert inv.value == (1 if ln == 300 else 0)
 
 
+def test_host_emulation_of_minhash_geometry_matches_oracle():
+    """sourmash-style hash (lexicographic min of k-mer / reverse complement, seeded Murmur3) through
+    the tile kernel's staged windows, on the host."""
+    from oracle import oracle as O
+
+    L = ctypes.CDLL(os.path.join(ROOT, "tests", "host", "libemul_tile.so"))
+    rng = np.random.default_rng(5)
+    for k in (21, 31, 5, 8, 9, 16, 33, 64, 255):
+        for ln in (k, k + 1, k + 5, 150, 600):
+            if ln < k:
+                continue
+            seq = rng.choice(list(b"ACGT"), ln).astype(np.uint8)
+            if ln == 150:
+                seq[:] = np.frombuffer((b"ACGT" * 40)[:ln], np.uint8)  # many k-mer == revcomp ties
+            out = np.zeros(ln - k + 1, np.uint64)
+            rc = L.emul_minhash_sequence(seq.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(ln), k, 7,
+                                         ctypes.c_uint64(42), out.ctypes.data_as(ctypes.c_void_p))
+            assert rc == 0
+            assert out.tolist() == O.minhash_sequence_py(seq.tobytes(), k), (k, ln)
+
+
 def test_bgzf_roundtrip_and_record_offsets(tmp_path):
     from spacegraphcats_b200.utils import bgzf
 

@@ -677,3 +677,35 @@ def test_partitioned_two_gpus_p2p_and_nccl_match_replicated():
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, out.stderr[-2000:]
         assert "labels identical to the replicated table on every rank: True" in out.stdout
+
+
+# ---------------------------------------------------------------- next rows f3 / f4: sourmash-style hashing
+def test_unitig_min_hashvals_match_reference_sqlite_column(ctx, dory):
+    """All 736 ``min_hashval`` values the reference stored for the dory unitigs
+    (cdbg/sort_bcalm_unitigs.py:56-128) from the GPU MinHash mode."""
+    from spacegraphcats_b200.cdbg.minhash import unitig_min_hashvals
+
+    with open(golden_path("dory_k21_min_hashval.json")) as fp:
+        want = {int(a): b for a, b in json.load(fp).items()}
+    recs = dory[0]
+    got = unitig_min_hashvals([r.sequence for r in recs], 21)
+    assert got.tolist() == [want[int(r.name)] for r in recs]
+
+
+@pytest.mark.parametrize("k", [21, 31, 12, 33])
+def test_sourmash_hashes_vs_oracle(ctx, O, k):
+    from spacegraphcats_b200.cdbg.minhash import scaled_minhash, sourmash_hashes, unitig_min_hashvals
+
+    rng = np.random.default_rng(k)
+    seqs = [rand_seq(rng, int(n)) for n in [k, k + 1, 0, 5, 150, 700, 3000] + rng.integers(0, 400, 60).tolist()]
+    seqs.append("ACGT" * 50)  # k-mer == reverse complement ties for even k
+    h, koff = sourmash_hashes(seqs, k)
+    want = [O.minhash_sequence_py(s, k) if len(s) >= k else [] for s in seqs]
+    assert koff.tolist() == np.concatenate([[0], np.cumsum([len(w) for w in want])]).tolist()
+    assert h.tolist() == [x for w in want for x in w]
+    mins = unitig_min_hashvals(seqs, k)
+    assert mins.tolist() == [min(w) if w else 2**64 - 1 for w in want]
+    sk = scaled_minhash(seqs, k, 10)
+    assert sk.tolist() == sorted({x for w in want for x in w if x <= (2**64 - 1) // 10})
+    with pytest.raises(ValueError):
+        sourmash_hashes(["ACGTNACGTACGTACGTACGTAGCTAGCTAGCTAGCTAGCATCGATCGATCGATG"], k)

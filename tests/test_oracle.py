@@ -261,3 +261,15 @@ def test_dominator_abundance_totals(dory_index):
     # tests/test_dory_workflow.py:859-860, 869-870
     assert sum(cdbg_counts.values()) == 240920 and None not in cdbg_counts
     assert sum(dom_counts.values()) == 240920
+
+
+def test_sourmash_min_hashval_all_unitigs():
+    """Every unitig's ``min_hashval`` written by the reference (cdbg/sort_bcalm_unitigs.py:56-128,
+    sourmash MinHash n=1 seed 42) equals the minimum of the restated sourmash k-mer hash: pins
+    oracle.minhash_kmer_py (the checker of the GPU MinHash mode) on 736 reference values."""
+    with open(golden_path("dory_k21_min_hashval.json")) as fp:
+        want = {int(a): b for a, b in json.load(fp).items()}
+    recs = O.read_unitigs_tsv(golden_path("dory_k21_unitigs.tsv.gz"))
+    assert len(want) == 736
+    for r in recs[::7] + recs[-3:]:
+        assert min(O.minhash_sequence_py(r.sequence, 21)) == want[int(r.name)], r.name
