@@ -37,6 +37,58 @@ class QueryResult:
         return [str(x) for x in sorted(self.doms)]
 
 
+def pseudo_unitigs(sequences, ksize, piece_kmers=100):
+    """Chop sequences into consecutive pieces that overlap by k-1 bases, so that every k-mer
+    position lies in exactly one piece (stand-in for a BCALM cDBG when bcalm is not
+    available; k-mers repeated across pieces become multicounts, which build_mphf drops)."""
+    out = []
+    for s in sequences:
+        for a in range(0, max(len(s) - ksize + 1, 0), piece_kmers):
+            out.append(s[a : a + piece_kmers + ksize - 1])
+    return out
+
+
+def query_batch(query_files, ksize, catlas, kmer_idx, scaled=None, catlas_name=None, debug=False):
+    """Batched ``Query(...)`` + ``execute`` over many query files (BASELINE.json configs[2]: batched
+    count_cdbg_matches over many query sequences).  All records of all queries are hashed in ONE
+    kernel launch; each query's distinct-hash set and per-unitig counts come from its slice of the
+    device-resident hash array.  -> list of (Query, QueryResult or None when catlas is None)."""
+    from ..cdbg.hashing import get_context, pack_sequences
+
+    ctx = get_context()
+    queries, seqs, spans = [], [], []
+    for qf in query_files:
+        q = Query.__new__(Query)
+        q.filename, q.ksize, q.name, q.catlas_name, q.debug, q.sig = qf, int(ksize), None, catlas_name, debug, None
+        lo = len(seqs)
+        for record in read_records(qf):
+            if q.name is None:
+                q.name = record.name
+            if len(record.sequence) >= q.ksize:
+                seqs.append(record.sequence)
+        spans.append((lo, len(seqs)))
+        queries.append(q)
+    buf, off = pack_sequences(seqs)
+    d_hashes, d_koff, d_status = ctx.hash_batch(buf, off, ksize, to_host=False)
+    if d_status is not None and d_status.numel() and bool(d_status.any().item()):
+        raise ValueError("Invalid base in read (query batch)")
+    koff = ctx.to_host(d_koff)
+    out = []
+    for q, (lo, hi) in zip(queries, spans):
+        q._ctx, q._kmers, q._n_distinct = ctx, None, None
+        q._d_hashes = d_hashes[int(koff[lo]) : int(koff[hi])]
+        q.cdbg_match_counts = q.catlas_match_counts = None
+        if catlas is not None:
+            out.append((q, q.execute(catlas, kmer_idx)))
+        else:
+            counts, _, nd = kmer_idx.table.count_matches_array(q._d_hashes, distinct=True)
+            q._n_distinct = nd
+            nz = np.flatnonzero(counts)
+            q.cdbg_match_counts = dict(zip(nz.tolist(), counts[nz].tolist()))
+            out.append((q, None))
+    return out
+
+
 class Query:
     def __init__(self, query_file, ksize, scaled=None, catlas_name=None, debug=True, records=None):
         self.filename = query_file

@@ -709,3 +709,49 @@ def test_sourmash_hashes_vs_oracle(ctx, O, k):
     assert sk.tolist() == sorted({x for w in want for x in w if x <= (2**64 - 1) // 10})
     with pytest.raises(ValueError):
         sourmash_hashes(["ACGTNACGTACGTACGTACGTAGCTAGCTAGCTAGCTAGCATCGATCGATCGATG"], k)
+
+
+# ---------------------------------------------------------------- configs[1]/[2]: twofoo-short and shew/acido proxies
+def test_batched_queries_k31_pseudo_unitigs_vs_oracle(ctx, O):
+    """BASELINE.json configs[1] and [2] with the offline proxies of SURVEY.md 8d: a k=31 table from
+    pseudo-unitigs of the twofoo-short genomes + acido chunk 1, queried in one batch by
+    shew-os223-200k, acido-chunk1/2, {2,47,63}.short and twofoo-genes; per-query {unitig: distinct
+    matching k-mers} against the oracle's Query restatement; reads of twofoo-short labelled too."""
+    from spacegraphcats_b200.cdbg.hashing import MPHF_KmerIndex
+    from spacegraphcats_b200.cdbg.index_cdbg_by_kmer import build_mphf
+    from spacegraphcats_b200.device import pack_sequences
+    from spacegraphcats_b200.search.query_by_sequence import pseudo_unitigs, query_batch
+
+    k = 31
+    data = lambda f: golden_path("data", f)  # noqa: E731
+    genome_files = ["63.short.fa.gz", "47.short.fa.gz", "acido-chunk1.fa.gz"]
+    gseqs = [r.sequence for f in genome_files for r in O.read_records(data(f))]
+    pieces = pseudo_unitigs(gseqs, k)
+    urecs = [O.Record(str(i), s) for i, s in enumerate(pieces)]
+    table, sizes = build_mphf(k, lambda: iter(urecs), ctx=ctx, verbose=False)
+    idx = MPHF_KmerIndex(k, table, sizes)
+    otab, osizes, n_multi = O.build_mphf(k, lambda: iter(urecs))
+    assert sizes == osizes and len(table) == len(otab)
+    assert table.stats()[1] == n_multi
+
+    qfiles = [data(f) for f in ("shew-os223-200k.fa.gz", "acido-chunk1.fa.gz", "acido-chunk2.fa.gz", "2.short.fa.gz",
+                                "47.short.fa.gz", "63.short.fa.gz", "twofoo-genes.fa.gz")]
+    res = query_batch(qfiles, k, None, idx)
+    containment = {}
+    for (q, _), qf in zip(res, qfiles):
+        okm = O.query_kmers(O.read_records(qf), k)
+        want = O.count_cdbg_matches(otab, okm)
+        assert q.cdbg_match_counts == want, qf
+        assert q.n_kmers == len(okm)
+        containment[os.path.basename(qf)] = sum(want.values()) / len(okm)
+    # sanity of the proxy: an indexed genome is (almost) fully contained, an unrelated one is not; the
+    # closely related 47/63 genomes share k-mers, which build_mphf drops as multicounts (~half of 63)
+    assert containment["acido-chunk1.fa.gz"] > 0.95 and containment["shew-os223-200k.fa.gz"] < 0.05
+    assert n_multi > 1000 and 0.2 < containment["63.short.fa.gz"] < 0.8
+
+    reads = O.read_records(data("twofoo-short-reads.fa.gz"))
+    rbuf, roff = pack_sequences([r.sequence for r in reads])
+    lab = table.label_reads(rbuf, roff, k)
+    o_off, o_ids, o_nk, o_nh = O.COracleTable(otab.mphf_to_hash, otab.mphf_to_value).label_reads(rbuf, roff, k)
+    assert np.array_equal(lab["ids_off"], o_off) and np.array_equal(lab["ids"], o_ids)
+    assert (lab["n_kmers"], lab["n_hits"]) == (o_nk, o_nh)
