@@ -349,7 +349,9 @@ struct WarpTile {
     int gpre[SPW + 1];
     int pad[3];
     unsigned wcnt[32];              // MODE_PARTITION: per-owner counts of one warp iteration
-    unsigned long long wbase[32];   // ... and the reserved base positions
+    unsigned wpre[32];              // ... their exclusive prefix (slot of the owner's run in the staging area)
+    uint64_t* dst[PAIR_BUF];        // ... destination address of every staged hash
+    unsigned long long wbase[32];   // ... and the reserved base positions in the owners' regions
 };
 
 template <int K, int MODE>
@@ -611,20 +613,64 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                     rank[t] = (active && t < nv) ? atomicAdd(&wt.wcnt[own[t]], 1u) : 0u;
                 }
                 __syncwarp();
-                if (lane < a.n_ranks) {
-                    const unsigned c = wt.wcnt[lane];
-                    wt.wbase[lane] = c ? atomicAdd(&a.cursor[lane], (unsigned long long)c) : 0ULL;
+                {   // one lane per owner: reserve the run in the owner's region, prefix for the staging slots
+                    const unsigned c = lane < a.n_ranks ? wt.wcnt[lane] : 0u;
+                    unsigned incl = c;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += v;
+                    }
+                    if (lane < a.n_ranks) {
+                        wt.wpre[lane] = incl - c;
+                        wt.wbase[lane] = c ? atomicAdd(&a.cursor[lane], (unsigned long long)c) : 0ULL;
+                    }
                 }
                 __syncwarp();
+                // Stage the <=128 hashes of this iteration grouped by owner (reusing the idle label
+                // staging area: 128 hashes + 128 destination addresses), then copy them out with
+                // consecutive lanes on consecutive addresses: each owner gets its run as full-width
+                // coalesced stores -- what NVLink wants when the destination is a peer GPU's inbox.
+                unsigned long long* stage_h = wt.pairs;                       // PAIR_BUF = 128 entries
                 if (active) {
                     const long long ko = wt.kout[sg] + i;
 #pragma unroll
                     for (int t = 0; t < 4; t++) {
                         if (t < nv) {
                             const unsigned long long pos = wt.wbase[own[t]] + rank[t];
-                            if (pos < a.send_cap) a.peer_send[own[t]][a.send_region_off + pos] = h[t];
                             a.ridx[ko + t] = (a.owner_bits ? (own[t] << sh) : 0u) | (uint32_t)pos;
                         }
+                    }
+                }
+                __syncwarp();
+                if (a.n_ranks <= 2) {
+                    // few owners: runs are long enough for direct stores (measured faster at R = 2)
+                    if (active) {
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            if (t < nv) {
+                                const unsigned long long pos = wt.wbase[own[t]] + rank[t];
+                                if (pos < a.send_cap) a.peer_send[own[t]][a.send_region_off + pos] = h[t];
+                            }
+                        }
+                    }
+                } else {
+                    if (active) {
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            if (t < nv) {
+                                const unsigned slot = wt.wpre[own[t]] + rank[t];
+                                const unsigned long long pos = wt.wbase[own[t]] + rank[t];
+                                stage_h[slot] = h[t];
+                                wt.dst[slot] = pos < a.send_cap ? a.peer_send[own[t]] + a.send_region_off + pos : nullptr;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    const unsigned total = wt.wpre[a.n_ranks - 1] + wt.wcnt[a.n_ranks - 1];
+                    for (unsigned j = lane; j < total; j += 32) {
+                        uint64_t* d = wt.dst[j];
+                        if (d) *d = stage_h[j];
                     }
                 }
                 __syncwarp();
