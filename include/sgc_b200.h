@@ -216,14 +216,17 @@ int sgc_labels_from_replies(sgc_ctx* ctx, const int64_t* d_off, int64_t nseq, in
  * my_rank of region_cap hashes); sgc_lookup_regions_p2p probes all source regions of the local
  * inbox and stores every reply straight into the SOURCE GPU's reply buffer (region my_rank, same
  * position), which is exactly the d_replies layout sgc_labels_from_replies consumes.  Between the
- * two calls the ranks only exchange the per-region counts and a barrier.
+ * two calls the ranks only exchange the per-region counts and a barrier.  sgc_lookup_regions_p2p
+ * is asynchronous (it only enqueues), so the next sub-batch's sgc_partition_hashes_p2p, issued
+ * through a second context, overlaps it: integer-bound hashing under HBM-bound probing.
  */
 int sgc_partition_hashes_p2p(sgc_ctx* ctx, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off,
                              int64_t nseq, int k, int n_ranks, int my_rank,
                              uint64_t* const* h_peer_inboxes, int64_t region_cap, uint32_t* d_ridx,
                              int64_t ridx_cap, int32_t* d_status, int64_t* h_counts);
 int sgc_lookup_regions_p2p(sgc_table* t, const uint64_t* d_inbox, const int64_t* h_counts_from,
-                           int64_t region_cap, int n_ranks, int my_rank, uint32_t* const* h_peer_replies);
+                           int64_t region_cap, int n_ranks, int my_rank, uint32_t* const* h_peer_replies,
+                           int ctas_per_sm /* 0 = fill the GPU; 1..7 = leave room for a concurrent kernel */);
 int sgc_peer_alloc(sgc_ctx* ctx, int64_t bytes, void** d_ptr, uint8_t* h_handle64);
 int sgc_peer_open(sgc_ctx* ctx, const uint8_t* h_handle64, void** d_ptr);
 int sgc_peer_close(sgc_ctx* ctx, void* d_ptr);

@@ -13,6 +13,7 @@ ap.add_argument("--reads", type=float, default=4e6)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--p2p", action="store_true", help="fuse the exchange into the kernels (NVLink peer stores)")
+ap.add_argument("--pipeline", type=int, default=0, help="with --p2p: split each step into this many sub-batches and overlap their phases")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29511")
@@ -45,10 +46,28 @@ if rank == 0:
 seq, off = cd.reads(n_reads, 150, seed=100 + rank)
 ctx.sync()
 res = None
+subs = None
+if args.pipeline > 1:
+    assert args.p2p
+    per = n_reads // args.pipeline
+    with torch.cuda.stream(ctx.stream):
+        subs = [(seq[j * per * 150:(j + 1) * per * 150], (off[j * per:(j + 1) * per + 1] - off[j * per]).contiguous())
+                for j in range(args.pipeline)]
+    ctx.sync()
 for it in range(args.steps + 1):
     if it == 1:
         dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+    if subs is not None:
+        parts = idx.label_reads_pipelined(subs, K)
+        continue
     res = idx.label_reads(seq, off, K)
+if subs is not None:
+    torch.cuda.synchronize()
+    ids_all = torch.cat([p[1] for p in parts])
+    offs, base = [parts[0][0]], int(parts[0][0][-1])
+    for p in parts[1:]:
+        offs.append(p[0][1:] + base); base += int(p[0][-1])
+    res = (torch.cat(offs), ids_all, sum(p[2] for p in parts))
 ctx.sync(); dist.barrier(); torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 t = torch.tensor([dt], dtype=torch.float64, device=ctx.device); dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -60,6 +79,6 @@ if args.check:
     okt = torch.tensor([1 if ok else 0], device=ctx.device); dist.all_reduce(okt, op=dist.ReduceOp.MIN)
     if rank == 0: print("labels identical to the replicated table on every rank:", bool(okt.item()), flush=True)
 if rank == 0:
-    print(json.dumps({"mode": "partitioned-p2p" if args.p2p else "partitioned-nccl", "n_gpus": world, "table_kmers": n_kmers, "reads_per_rank_step": n_reads,
+    print(json.dumps({"mode": ("partitioned-p2p-pipelined%d" % args.pipeline if args.pipeline > 1 else "partitioned-p2p") if args.p2p else "partitioned-nccl", "n_gpus": world, "table_kmers": n_kmers, "reads_per_rank_step": n_reads,
                       "value": rate, "unit": "k-mers/s", "ms_per_step": float(t.item()) / args.steps * 1e3}), flush=True)
 dist.destroy_process_group()

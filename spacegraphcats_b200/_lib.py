@@ -66,7 +66,7 @@ PROTOTYPES = {
     "sgc_unpermute_u32": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "sgc_partition_hashes": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _pi64]),
     "sgc_partition_hashes_p2p": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _pi64]),
-    "sgc_lookup_regions_p2p": (_i32, [_vp, _vp, _pi64, _i64, _i32, _i32, _vp]),
+    "sgc_lookup_regions_p2p": (_i32, [_vp, _vp, _pi64, _i64, _i32, _i32, _vp, _i32]),
     "sgc_peer_alloc": (_i32, [_vp, _i64, ctypes.POINTER(_vp), _vp]),
     "sgc_peer_open": (_i32, [_vp, _vp, ctypes.POINTER(_vp)]),
     "sgc_peer_close": (_i32, [_vp, _vp]),

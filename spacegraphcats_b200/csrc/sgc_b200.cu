@@ -1902,7 +1902,7 @@ int sgc_partition_hashes_p2p(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes
 // owner side of the fused exchange: probe the requests of every source region of my inbox and store
 // each reply straight into the source GPU's reply buffer (region my_rank, same position)
 int sgc_lookup_regions_p2p(sgc_table* t, const uint64_t* d_inbox, const int64_t* h_counts_from, int64_t region_cap,
-                           int n_ranks, int my_rank, uint32_t* const* h_peer_replies) {
+                           int n_ranks, int my_rank, uint32_t* const* h_peer_replies, int ctas_per_sm) {
     if (!t || !d_inbox || !h_counts_from || !h_peer_replies) return fail(SGC_ERR_ARG, "NULL argument");
     if (n_ranks < 1 || n_ranks > 32 || my_rank < 0 || my_rank >= n_ranks) return fail(SGC_ERR_ARG, "bad ranks");
     sgc_ctx* c = t->ctx;
@@ -1911,7 +1911,10 @@ int sgc_lookup_regions_p2p(sgc_table* t, const uint64_t* d_inbox, const int64_t*
         const int64_t n = h_counts_from[s];
         if (n < 0 || n > region_cap) return fail(SGC_ERR_ARG, "bad region count");
         if (n == 0) continue;
-        lookup_kernel<<<grid_for((n + 1) / 2, 256, c->num_sms * 8), 256, 0, c->stream>>>(
+        // ctas_per_sm < 8 leaves SM room for a concurrently running hash kernel (the probe is bound by
+        // HBM accesses and saturates with few resident threads)
+        const int per_sm = ctas_per_sm > 0 && ctas_per_sm < 8 ? ctas_per_sm : 8;
+        lookup_kernel<<<grid_for((n + 1) / 2, 256, c->num_sms * per_sm), 256, 0, c->stream>>>(
             t->buckets, t->nbuckets, t->nlines, t->home_shift, d_inbox + (size_t)s * (size_t)region_cap, n,
             h_peer_replies[s] + (size_t)my_rank * (size_t)region_cap);
         c->launches++;

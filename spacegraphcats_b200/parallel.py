@@ -288,6 +288,8 @@ class PartitionedIndex:
         self.group = group
         self.p2p = bool(p2p)  # fuse the exchange into the kernels over NVLink peer memory
         self._peers = None
+        self._peers2 = None  # double-buffered peer buffers of the pipelined path
+        self._aux = None  # (partition context, gather context) of the pipelined path
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.bits = log2_ranks(self.world)
@@ -401,7 +403,7 @@ class PartitionedIndex:
         with e.stream():
             t = torch.tensor([need], dtype=torch.int64, device=c.device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-        need = int(t.item())
+            need = int(t.item())  # read on the stream the collective was issued on
         if self._peers is None or self._peers.region_cap < need:
             if self._peers is not None:
                 self._peers.close()
@@ -421,9 +423,9 @@ class PartitionedIndex:
             sc = torch.tensor(list(h_counts), dtype=torch.int64, device=c.device)
             rc = torch.empty(R, dtype=torch.int64, device=c.device)
             dist.all_to_all_single(rc, sc, group=self.group)  # also orders every rank's stores before the probes
-        counts_from = (ctypes.c_int64 * R)(*rc.tolist())
+            counts_from = (ctypes.c_int64 * R)(*rc.tolist())
         mark("counts")
-        check(L.sgc_lookup_regions_p2p(self.table._h, pb.inbox, counts_from, cap, R, self.rank, pb.reply_ptrs))
+        check(L.sgc_lookup_regions_p2p(self.table._h, pb.inbox, counts_from, cap, R, self.rank, pb.reply_ptrs, 0))
         c.sync()
         mark("owner probe + P2P stores of the replies")
         with e.stream():
@@ -435,6 +437,100 @@ class PartitionedIndex:
             print("[K7 p2p trace] " + ", ".join("%s %.2f ms" % (b[0], (b[1] - a[1]) * 1e3) for a, b in zip(marks, marks[1:])),
                   flush=True)
         return ioff, ids, nh
+
+    def label_reads_pipelined(self, batches, ksize):
+        """Label a list of sub-batches [(seq, off), ...] with the phases of consecutive sub-batches
+        overlapped on three streams: while the owners probe sub-batch j (HBM-bound, table context),
+        this rank turns the replies of sub-batch j-1 into labels (gather context) and hashes +
+        stores sub-batch j+1 into the owners' other inbox (partition context, integer-bound).
+        Inboxes and reply buffers are double-buffered.  -> list of (ids_off, ids, n_hits)."""
+        import torch.distributed as dist
+
+        from .device import Context
+
+        torch = _torch()
+        e, R, cT = self.engine, self.world, self.engine.ctx
+        L = cT._L
+        if self._aux is None:
+            self._aux = (Context(cT.device_index), Context(cT.device_index))
+        cP, cG = self._aux
+        eG = DeviceEngine(cG)
+        S = len(batches)
+        if S == 0:
+            return []
+        d_in = [(cP.to_device(s, np.uint8), cP.to_device(o, np.int64)) for s, o in batches]
+        need = max(int(max(s.numel(), 1) / R * 1.08) + 4096 for s, _ in d_in)
+        with torch.cuda.stream(cP.stream):
+            t = torch.tensor([need], dtype=torch.int64, device=cP.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            need = int(t.item())
+        if self._peers2 is None or self._peers2[0].region_cap < need:
+            if self._peers2 is not None:
+                for pb in self._peers2:
+                    pb.close()
+            self._peers2 = (PeerBuffers(cT, self.group, need), PeerBuffers(cT, self.group, need))
+        cap = self._peers2[0].region_cap
+        ridx = [None, None]
+
+        def part(j):
+            d_seq, d_off = d_in[j]
+            nseq, n_bytes = d_off.numel() - 1, d_seq.numel()
+            pb = self._peers2[j % 2]
+            ridx[j % 2] = cP.empty(max(n_bytes, 1), torch.int32)
+            d_stat = cP.empty(nseq, torch.int32)
+            h_counts = (ctypes.c_int64 * R)()
+            check(L.sgc_partition_hashes_p2p(cP._h, cP.ptr(d_seq), n_bytes, cP.ptr(d_off), nseq, int(ksize), R, self.rank,
+                                             pb.inbox_ptrs, cap, cP.ptr(ridx[j % 2]), max(n_bytes, 1), cP.ptr(d_stat),
+                                             h_counts))
+            if nseq and bool(d_stat.any().item()):
+                raise ValueError("Invalid base in read")
+            with torch.cuda.stream(cP.stream):
+                sc = torch.tensor(list(h_counts), dtype=torch.int64, device=cP.device)
+                rc = torch.empty(R, dtype=torch.int64, device=cP.device)
+                dist.all_to_all_single(rc, sc, group=self.group)
+                return (ctypes.c_int64 * R)(*rc.tolist())
+
+        def gather(j):
+            d_seq, d_off = d_in[j]
+            pb = self._peers2[j % 2]
+            ioff, ids, nh, _ = eG.labels_from_replies(d_off, d_seq.numel(), ksize, R, ridx[j % 2], _RawPtr(pb.replies.value), cap)
+            return ioff, ids, nh
+
+        import os
+        import time
+
+        trace = os.environ.get("SGC_TRACE") and self.rank == 0
+        marks = [("start", time.perf_counter())]
+
+        def mark(name):
+            if trace:
+                marks.append((name, time.perf_counter()))
+
+        out = [None] * S
+        cf = part(0)
+        mark("part0")
+        for j in range(S):
+            pb = self._peers2[j % 2]
+            check(L.sgc_lookup_regions_p2p(self.table._h, pb.inbox, cf, cap, R, self.rank, pb.reply_ptrs, 2))  # async
+            mark("launch probe%d" % j)
+            if j >= 1:
+                out[j - 1] = gather(j - 1)
+                mark("gather%d" % (j - 1))
+            if j + 1 < S:
+                cf = part(j + 1)
+                mark("part%d" % (j + 1))
+            cT.sync()
+            mark("probe%d done" % j)
+            with torch.cuda.stream(cT.stream):
+                dist.barrier(group=self.group)
+            cT.sync()  # host-blocking: the other two streams are not ordered after the barrier by themselves
+            mark("barrier%d" % j)
+        out[S - 1] = gather(S - 1)
+        mark("gather%d" % (S - 1))
+        if trace:
+            print("[K7 pipeline trace] " + ", ".join("%s %.2f" % (b[0], (b[1] - a[1]) * 1e3) for a, b in zip(marks, marks[1:])),
+                  flush=True)
+        return out
 
     def label_reads(self, seq, off, ksize):
         """index_reads' per-read step against the partitioned table.
