@@ -111,6 +111,12 @@ int sgc_table_stats(sgc_table* t, int64_t* h_live, int64_t* h_multi, uint32_t* h
 int sgc_table_export(sgc_table* t, uint64_t* d_hash_out, uint32_t* d_id_out, int64_t cap,
                      int64_t* h_n_out);
 int64_t sgc_table_bytes(const sgc_table* t);
+/* Optional unitig-ordered side array ({hash, id} per inserted k-mer, 16 B each, up to max_entries
+ * records): call before sgc_table_insert_sequences.  With it sgc_label_reads probes the hash table
+ * only for the first k-mer of every group of four and matches the others by full 64-bit hash
+ * equality against the neighbouring unitig positions (fewer HBM lines per k-mer, identical result). */
+int sgc_table_enable_side(sgc_table* t);
+int64_t sgc_table_side_bytes(const sgc_table* t);
 /* hash-range partitioned tables: the top `shift` bits of every hash stored here are the owner
  * rank and therefore constant; skip them when choosing the home bucket.  Call before inserting. */
 int sgc_table_set_home_shift(sgc_table* t, int shift);

@@ -53,6 +53,8 @@ PROTOTYPES = {
     "sgc_table_export": (_i32, [_vp, _vp, _vp, _i64, _pi64]),
     "sgc_table_bytes": (_i64, [_vp]),
     "sgc_table_set_home_shift": (_i32, [_vp, _i32]),
+    "sgc_table_enable_side": (_i32, [_vp]),
+    "sgc_table_side_bytes": (_i64, [_vp]),
     "sgc_lookup": (_i32, [_vp, _vp, _i64, _vp]),
     "sgc_count_matches": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _pi64, _pi64]),
     "sgc_lookup_sequences": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _i64, _vp, _pi64, _pi64]),

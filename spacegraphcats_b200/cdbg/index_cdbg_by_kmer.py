@@ -8,6 +8,7 @@ the reference's ``multicounts`` rule), and the observable result -- the exact ma
 consistency asserts -- is the same.
 """
 import argparse
+import os
 import sqlite3
 import sys
 
@@ -56,6 +57,8 @@ def build_mphf(ksize, records_iter_fn, ctx=None, verbose=True):
     from ..device import DeviceTable
 
     table._dev = DeviceTable(ctx, max(total_kmers, 1))
+    if os.environ.get("SGC_SIDE") == "1":  # experimental unitig-ordered side array
+        table._dev.enable_side()
     lo = 0
     while lo < n_contigs:
         hi, nb = lo, 0

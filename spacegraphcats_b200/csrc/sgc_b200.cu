@@ -71,7 +71,7 @@ constexpr unsigned long long SEQ_MASK = (1ULL << 40) - 1ULL;
 constexpr uint32_t VAL_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t VAL_MULTI = 0xFFFFFFFEu;
 
-enum Mode { MODE_HASH = 0, MODE_INSERT = 1, MODE_LOOKUP = 2, MODE_LABEL = 3, MODE_PARTITION = 4, MODE_GATHER = 5, MODE_MINHASH = 6 };
+enum Mode { MODE_HASH = 0, MODE_INSERT = 1, MODE_LOOKUP = 2, MODE_LABEL = 3, MODE_PARTITION = 4, MODE_GATHER = 5, MODE_MINHASH = 6, MODE_LABEL_SIDE = 7 };
 
 template <int K>
 struct Geo {
@@ -84,13 +84,15 @@ struct Geo {
 // The table: 32-byte buckets of two 16-byte slots; four buckets share a 128-byte line (the unit
 // HBM actually moves per random access on B200: measured).  A key lives at probe
 // step s >= 0 from its home bucket hb: steps 1..3 are the other buckets of the home line, steps
-// 4.. walk the following lines.  flg of slot 0 of the HOME bucket holds the largest step any key
-// homed there was placed at, so a lookup knows exactly how far to look (0 = home only).
+// 4.. walk the following lines.  It sits in the FIRST bucket of that sequence that had a free slot
+// when it arrived and slots are never freed, so a lookup stops at the first bucket that is not
+// full.  aux = index of the k-mer in the table's unitig-ordered side array (AUX_NONE if none).
 struct __align__(16) Entry {
     unsigned long long key;
     unsigned int val;  // VAL_EMPTY = free slot, VAL_MULTI = dropped hash, else unitig id
-    unsigned int flg;  // slot 0 of a bucket: max probe step of the keys homed in this bucket
+    unsigned int aux;  // position g of this k-mer in the side array, or AUX_NONE
 };
+constexpr uint32_t AUX_NONE = 0xFFFFFFFFu;
 struct __align__(32) Bucket {
     Entry e[2];
 };
@@ -130,6 +132,11 @@ struct TileArgs {
     int home_shift;
     const uint32_t* seq_ids;
     uint32_t id_base;
+    // side array (unitig-ordered {hash, id} records): written by MODE_INSERT, read by MODE_LABEL_SIDE
+    uint4* side;
+    unsigned long long side_base;   // MODE_INSERT: first record of this batch
+    unsigned long long side_n;      // MODE_LABEL_SIDE: number of records
+    int debug;                      // experiment switches (results become wrong): 1 = no pending probes, 2 = no anchor slow path
     // MODE_LOOKUP
     uint32_t* kmer_ids;
     uint32_t* count_by_id;
@@ -169,20 +176,20 @@ __device__ __forceinline__ void load_bucket_nc(const Bucket* p, Entry& e0, Entry
     asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
                  : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
                  : "l"(p));
-    e0.key = a; e0.val = (uint32_t)b; e0.flg = (uint32_t)(b >> 32);
-    e1.key = c; e1.val = (uint32_t)d; e1.flg = (uint32_t)(d >> 32);
+    e0.key = a; e0.val = (uint32_t)b; e0.aux = (uint32_t)(b >> 32);
+    e1.key = c; e1.val = (uint32_t)d; e1.aux = (uint32_t)(d >> 32);
 }
 
 // coherent variant for the build kernels (the table is being written concurrently)
 __device__ __forceinline__ void load_entry_volatile(const Entry* p, Entry& e) {
     unsigned long long a, b;
     asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
-    e.key = a; e.val = (uint32_t)b; e.flg = (uint32_t)(b >> 32);
+    e.key = a; e.val = (uint32_t)b; e.aux = (uint32_t)(b >> 32);
 }
 
 __device__ __forceinline__ bool cas_entry(Entry* p, const Entry& expect, const Entry& desired, Entry& old) {
-    unsigned long long e0 = expect.key, e1 = ((unsigned long long)expect.flg << 32) | expect.val;
-    unsigned long long d0 = desired.key, d1 = ((unsigned long long)desired.flg << 32) | desired.val;
+    unsigned long long e0 = expect.key, e1 = ((unsigned long long)expect.aux << 32) | expect.val;
+    unsigned long long d0 = desired.key, d1 = ((unsigned long long)desired.aux << 32) | desired.val;
     unsigned long long o0, o1;
     asm volatile(
         "{\n .reg .b128 e, d, o;\n mov.b128 e, {%2, %3};\n mov.b128 d, {%4, %5};\n"
@@ -190,46 +197,65 @@ __device__ __forceinline__ bool cas_entry(Entry* p, const Entry& expect, const E
         : "=l"(o0), "=l"(o1)
         : "l"(e0), "l"(e1), "l"(d0), "l"(d1), "l"(p)
         : "memory");
-    old.key = o0; old.val = (uint32_t)o1; old.flg = (uint32_t)(o1 >> 32);
+    old.key = o0; old.val = (uint32_t)o1; old.aux = (uint32_t)(o1 >> 32);
     return o0 == e0 && o1 == e1;
 }
 
 __device__ __forceinline__ uint32_t resolve_val(uint32_t v) { return v >= VAL_MULTI ? SGC_MISS : v; }
 
-__device__ __forceinline__ bool bucket_match(const Entry& e0, const Entry& e1, uint64_t h, uint32_t& out) {
-    if (e0.key == h && e0.val != VAL_EMPTY) { out = resolve_val(e0.val); return true; }
-    if (e1.key == h && e1.val != VAL_EMPTY) { out = resolve_val(e1.val); return true; }
+__device__ __forceinline__ bool bucket_match(const Entry& e0, const Entry& e1, uint64_t h, uint32_t& out, uint32_t& aux) {
+    if (e0.key == h && e0.val != VAL_EMPTY) { out = resolve_val(e0.val); aux = e0.aux; return true; }
+    if (e1.key == h && e1.val != VAL_EMPTY) { out = resolve_val(e1.val); aux = e1.aux; return true; }
     return false;
 }
+__device__ __forceinline__ bool bucket_match(const Entry& e0, const Entry& e1, uint64_t h, uint32_t& out) {
+    uint32_t aux;
+    return bucket_match(e0, e1, h, out, aux);
+}
+__device__ __forceinline__ bool bucket_full(const Entry& e0, const Entry& e1) {
+    return e0.val != VAL_EMPTY && e1.val != VAL_EMPTY;
+}
 
-// Slow path of a lookup (the home bucket did not hold the key and its max-step is > 0): the other
-// three buckets of the home line are read together (the line is already in L2: HBM moved all
-// 128 bytes), then, rarely, the following lines.
-__device__ __forceinline__ uint32_t lookup_slow(const Bucket* tbl, uint32_t nlines, uint32_t hb, uint32_t maxstep,
-                                                uint64_t h) {
+// Slow path of a lookup: the home bucket is full and does not hold the key.  The other three
+// buckets of the home line are read together (the line is already in L2: HBM moved all 128 bytes),
+// then, rarely, the following lines; the walk ends at the first bucket that is not full.
+__device__ __forceinline__ uint32_t lookup_slow(const Bucket* tbl, uint32_t nlines, uint32_t hb, uint64_t h,
+                                                uint32_t& aux) {
     Entry a0, a1, b0, b1, c0, c1;
     load_bucket_nc(tbl + probe_bucket(hb, 1, nlines), a0, a1);
     load_bucket_nc(tbl + probe_bucket(hb, 2, nlines), b0, b1);
     load_bucket_nc(tbl + probe_bucket(hb, 3, nlines), c0, c1);
     uint32_t out;
-    if (bucket_match(a0, a1, h, out)) return out;
-    if (maxstep >= 2 && bucket_match(b0, b1, h, out)) return out;
-    if (maxstep >= 3 && bucket_match(c0, c1, h, out)) return out;
-    for (uint32_t s = 4; s <= maxstep; s++) {
+    aux = AUX_NONE;
+    if (bucket_match(a0, a1, h, out, aux)) return out;
+    if (!bucket_full(a0, a1)) return SGC_MISS;
+    if (bucket_match(b0, b1, h, out, aux)) return out;
+    if (!bucket_full(b0, b1)) return SGC_MISS;
+    if (bucket_match(c0, c1, h, out, aux)) return out;
+    if (!bucket_full(c0, c1)) return SGC_MISS;
+    const uint32_t max_steps = nlines > (1u << 20) ? (4u << 20) : nlines * 4u;
+    for (uint32_t s = 4; s < max_steps; s++) {
         load_bucket_nc(tbl + probe_bucket(hb, s, nlines), a0, a1);
-        if (bucket_match(a0, a1, h, out)) return out;
+        if (bucket_match(a0, a1, h, out, aux)) return out;
+        if (!bucket_full(a0, a1)) return SGC_MISS;
     }
     return SGC_MISS;
 }
 
-__device__ __forceinline__ uint32_t table_lookup(const Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, uint64_t h) {
+__device__ __forceinline__ uint32_t table_lookup(const Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, uint64_t h,
+                                                 uint32_t& aux) {
     uint32_t hb = home_bucket(h, nb, hs);
     Entry e0, e1;
     load_bucket_nc(tbl + hb, e0, e1);
     uint32_t out;
-    if (bucket_match(e0, e1, h, out)) return out;
-    if (e0.flg == 0) return SGC_MISS;
-    return lookup_slow(tbl, nlines, hb, e0.flg, h);
+    if (bucket_match(e0, e1, h, out, aux)) return out;
+    aux = AUX_NONE;
+    if (!bucket_full(e0, e1)) return SGC_MISS;
+    return lookup_slow(tbl, nlines, hb, h, aux);
+}
+__device__ __forceinline__ uint32_t table_lookup(const Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, uint64_t h) {
+    uint32_t aux;
+    return table_lookup(tbl, nb, nlines, hs, h, aux);
 }
 
 // build_mphf insertion semantics (cdbg/index_cdbg_by_kmer.py:40-57, 88-89):
@@ -238,11 +264,11 @@ __device__ __forceinline__ uint32_t table_lookup(const Bucket* tbl, uint32_t nb,
 // The outcome is independent of the order in which threads arrive: slots only ever go from
 // empty to occupied, every thread walks the same probe sequence, and a lost CAS re-examines
 // what the winner wrote.
-__device__ void table_insert(Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, uint64_t h, uint32_t id,
+__device__ void table_insert(Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, uint64_t h, uint32_t id, uint32_t aux,
                              Scalars* scal) {
     const uint32_t hb = home_bucket(h, nb, hs);
     const Entry empty{0ULL, VAL_EMPTY, 0u};
-    const Entry mine{h, id, 0u};
+    const Entry mine{h, id, aux};
     const uint32_t max_steps = nlines > (1u << 20) ? (4u << 20) : nlines * 4u;
     for (uint32_t step = 0; step < max_steps; step++) {
         Bucket* bp = tbl + probe_bucket(hb, step, nlines);
@@ -250,17 +276,13 @@ __device__ void table_insert(Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, 
         for (int s = 0; s < 2; s++) {
             Entry e;
             load_entry_volatile(&bp->e[s], e);
-            bool placed = false;
             if (e.val == VAL_EMPTY) {
                 Entry old;
-                if (cas_entry(&bp->e[s], empty, mine, old)) placed = true;
-                else e = old;  // somebody else claimed the slot first: examine what they wrote
+                if (cas_entry(&bp->e[s], empty, mine, old)) return;
+                e = old;  // somebody else claimed the slot first: examine what they wrote
             }
-            if (placed || e.key == h) {
-                if (!placed && e.val != id && e.val != VAL_MULTI) atomicExch(&bp->e[s].val, VAL_MULTI);
-                // publish how far this key sits from home (its home bucket is full by now, so its
-                // slot 0 is occupied and never CAS-ed again)
-                if (step) atomicMax(&tbl[hb].e[0].flg, step);
+            if (e.key == h) {
+                if (e.val != id && e.val != VAL_MULTI) atomicExch(&bp->e[s].val, VAL_MULTI);
                 return;
             }
         }
@@ -355,7 +377,7 @@ struct WarpTile {
 };
 
 template <int K, int MODE>
-__global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP) ? SGC_PROBE_MIN_CTAS : 1) tile_kernel(const TileArgs a) {
+__global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP || MODE == MODE_LABEL_SIDE) ? SGC_PROBE_MIN_CTAS : 1) tile_kernel(const TileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int WPS = Geo<K>::WPS;
     const int lane = threadIdx.x & 31;
@@ -587,9 +609,17 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                     long long sq = wt.seq[sg];
                     uint32_t id = a.seq_ids ? a.seq_ids[sq] : a.id_base + (uint32_t)sq;
                     if (id > SGC_MAX_ID) atomicOr(&a.scal->err, 2);
-                    else
-                        for (int t = 0; t < nv; t++)
-                            table_insert(a.tbl, a.nbuckets, a.nlines, a.home_shift, h[t], id, a.scal);
+                    else {
+                        const unsigned long long g0 = a.side_base + (unsigned long long)(wt.kout[sg] + i);
+                        for (int t = 0; t < nv; t++) {
+                            uint32_t aux = AUX_NONE;
+                            if (a.side) {  // unitig-ordered record; its id is fixed up after the build
+                                aux = (uint32_t)(g0 + t);
+                                a.side[g0 + t] = make_uint4((uint32_t)h[t], (uint32_t)(h[t] >> 32), id, 0u);
+                            }
+                            table_insert(a.tbl, a.nbuckets, a.nlines, a.home_shift, h[t], id, aux, a.scal);
+                        }
+                    }
                 }
             }
         } else if constexpr (MODE == MODE_PARTITION) {
@@ -712,6 +742,100 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                 }
                 emit_candidates(ids, active, sg, i, nv);
             }
+        } else if constexpr (MODE == MODE_LABEL_SIDE) {
+            // K4 with fewer HBM lines per k-mer.  Only the FIRST k-mer of a group (the anchor) probes the
+            // hash table (software-pipelined like MODE_LABEL).  Its slot carries g, the k-mer's position in
+            // the table's unitig-ordered side array of {hash, id} records (id = what a table lookup of that
+            // hash returns, fixed up after the build).  Consecutive k-mers of a read are consecutive
+            // k-mers of the unitig, on one strand or the other, so k-mer t is looked for at side[g+t] and
+            // side[g-t]: a full 64-bit hash match there IS the table's answer for that hash.  Anything
+            // not matched (sequencing errors, unitig ends, anchor missing) does its own table probe, so
+            // the result is exactly what per-k-mer probing gives.  Neighbouring threads share side lines.
+            bool p_active = false;
+            int p_sg = 0, p_i = 0, p_nv = 0;
+            uint64_t p_h[4] = {0, 0, 0, 0};
+            uint32_t p_b0 = 0;
+            Entry p_e0, p_e1;
+
+            auto resolve = [&]() {
+                uint32_t ids[4] = {SGC_MISS, SGC_MISS, SGC_MISS, SGC_MISS};
+                unsigned pending = 0;
+                if (p_active) {
+                    uint32_t v = SGC_MISS, g = AUX_NONE;
+                    if (!bucket_match(p_e0, p_e1, p_h[0], v, g)) {
+                        v = SGC_MISS;
+                        g = AUX_NONE;
+                        if (bucket_full(p_e0, p_e1) && !(a.debug & 2)) v = lookup_slow(a.tbl, a.nlines, p_b0, p_h[0], g);
+                    }
+                    ids[0] = v;
+                    pending = ((1u << p_nv) - 1u) & ~1u;  // k-mers 1..nv-1 until proven otherwise
+                    if (g != AUX_NONE) {
+                        uint4 up[3], um[3];
+#pragma unroll
+                        for (int d = 1; d < 4; d++) {
+                            const bool hi_ok = d < p_nv && (unsigned long long)g + d < a.side_n;
+                            const bool lo_ok = d < p_nv && g >= (uint32_t)d;
+                            up[d - 1] = hi_ok ? __ldg(a.side + g + d) : make_uint4(0, 0, SGC_MISS, 1);
+                            um[d - 1] = lo_ok ? __ldg(a.side + g - d) : make_uint4(0, 0, SGC_MISS, 1);
+                        }
+#pragma unroll
+                        for (int d = 1; d < 4; d++) {
+                            if (d < p_nv) {
+                                const uint32_t lo = (uint32_t)p_h[d], hi = (uint32_t)(p_h[d] >> 32);
+                                if (up[d - 1].x == lo && up[d - 1].y == hi && up[d - 1].w == 0) {
+                                    ids[d] = up[d - 1].z;
+                                    pending &= ~(1u << d);
+                                } else if (um[d - 1].x == lo && um[d - 1].y == hi && um[d - 1].w == 0) {
+                                    ids[d] = um[d - 1].z;
+                                    pending &= ~(1u << d);
+                                }
+                            }
+                        }
+                    }
+                }
+                if (pending && !(a.debug & 1)) {  // own probes, all issued before any is consumed
+                    Entry q0[3], q1[3];
+                    uint32_t qb[3];
+#pragma unroll
+                    for (int d = 1; d < 4; d++) {
+                        qb[d - 1] = (pending >> d) & 1u ? home_bucket(p_h[d], a.nbuckets, a.home_shift) : 0u;
+                        if ((pending >> d) & 1u) load_bucket_nc(a.tbl + qb[d - 1], q0[d - 1], q1[d - 1]);
+                    }
+#pragma unroll
+                    for (int d = 1; d < 4; d++) {
+                        if ((pending >> d) & 1u) {
+                            uint32_t v, aux;
+                            if (bucket_match(q0[d - 1], q1[d - 1], p_h[d], v)) ids[d] = v;
+                            else if (bucket_full(q0[d - 1], q1[d - 1])) ids[d] = lookup_slow(a.tbl, a.nlines, qb[d - 1], p_h[d], aux);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+                    if (p_active && t < p_nv) { if (ids[t] != SGC_MISS) my_hits++; else my_miss++; }
+                emit_candidates(ids, p_active, p_sg, p_i, p_nv);
+            };
+
+            for (int g0 = 0; g0 < G; g0 += 32) {
+                const int g = g0 + lane;
+                const bool active = g < G;
+                int sg = 0, i = 0, nv = 0;
+                uint64_t h[4] = {0, 0, 0, 0};
+                if (active) locate_and_hash(g, sg, i, nv, h);   // the previous group's anchor probe is in flight here
+                {
+                    const uint64_t dep = (h[0] ^ h[1] ^ h[2] ^ h[3]) & a.zero;  // see MODE_LABEL
+#pragma unroll
+                    for (int t = 0; t < 4; t++) p_h[t] ^= dep;
+                }
+                if (g0 > 0) resolve();
+                p_active = active; p_sg = sg; p_i = i; p_nv = nv;
+#pragma unroll
+                for (int t = 0; t < 4; t++) p_h[t] = h[t];
+                p_b0 = active ? home_bucket(h[0], a.nbuckets, a.home_shift) : 0u;
+                load_bucket_nc(a.tbl + p_b0, p_e0, p_e1);
+            }
+            if (G > 0) resolve();
+            __syncwarp();
         } else {
             // MODE_LOOKUP / MODE_LABEL, software-pipelined: the 4 table probes of a group are issued
             // and left in flight while the NEXT group's 8 Murmur3 evaluations run; they are resolved
@@ -730,7 +854,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                     if (p_active && t < p_nv) {
                         uint32_t v;
                         if (bucket_match(p_e0[t], p_e1[t], p_h[t], v)) ids[t] = v;
-                        else if (p_e0[t].flg) slow |= 1u << t;
+                        else if (bucket_full(p_e0[t], p_e1[t])) slow |= 1u << t;
                     }
                 }
                 while (slow) {  // ~6 % of lookups: the key is not in its home bucket; one trip per key
@@ -738,8 +862,8 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                     slow &= slow - 1;
                     const uint64_t hk = t == 0 ? p_h[0] : t == 1 ? p_h[1] : t == 2 ? p_h[2] : p_h[3];
                     const uint32_t hb = t == 0 ? p_b[0] : t == 1 ? p_b[1] : t == 2 ? p_b[2] : p_b[3];
-                    const uint32_t ms = t == 0 ? p_e0[0].flg : t == 1 ? p_e0[1].flg : t == 2 ? p_e0[2].flg : p_e0[3].flg;
-                    const uint32_t v = lookup_slow(a.tbl, a.nlines, hb, ms, hk);
+                    uint32_t aux_unused;
+                    const uint32_t v = lookup_slow(a.tbl, a.nlines, hb, hk, aux_unused);
 #pragma unroll
                     for (int u = 0; u < 4; u++)
                         if (u == t) ids[u] = v;
@@ -808,10 +932,10 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
         }
     }
 
-    if constexpr (MODE == MODE_LABEL || MODE == MODE_GATHER) {
+    if constexpr (MODE == MODE_LABEL || MODE == MODE_GATHER || MODE == MODE_LABEL_SIDE) {
         if (pair_fill) flush_pairs();
     }
-    if constexpr (MODE == MODE_LOOKUP || MODE == MODE_LABEL || MODE == MODE_GATHER) {
+    if constexpr (MODE == MODE_LOOKUP || MODE == MODE_LABEL || MODE == MODE_GATHER || MODE == MODE_LABEL_SIDE) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             my_hits += __shfl_xor_sync(0xffffffffu, my_hits, d);
@@ -840,7 +964,7 @@ __global__ void insert_pairs_kernel(Bucket* tbl, uint32_t nb, uint32_t nlines, i
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         uint32_t v = id[i];
         if (v > SGC_MAX_ID) atomicOr(&scal->err, 2);
-        else table_insert(tbl, nb, nlines, hs, hash[i], v, scal);
+        else table_insert(tbl, nb, nlines, hs, hash[i], v, AUX_NONE, scal);
     }
 }
 
@@ -856,10 +980,11 @@ __global__ void lookup_kernel(const Bucket* tbl, uint32_t nb, uint32_t nlines, i
         load_bucket_nc(tbl + b0, a0, a1);
         load_bucket_nc(tbl + b1, c0, c1);
         uint32_t v;
-        if (!bucket_match(a0, a1, h0, v)) v = a0.flg ? lookup_slow(tbl, nlines, b0, a0.flg, h0) : SGC_MISS;
+        uint32_t aux;
+        if (!bucket_match(a0, a1, h0, v)) v = bucket_full(a0, a1) ? lookup_slow(tbl, nlines, b0, h0, aux) : SGC_MISS;
         out[i] = v;
         if (j < n) {
-            if (!bucket_match(c0, c1, h1, v)) v = c0.flg ? lookup_slow(tbl, nlines, b1, c0.flg, h1) : SGC_MISS;
+            if (!bucket_match(c0, c1, h1, v)) v = bucket_full(c0, c1) ? lookup_slow(tbl, nlines, b1, h1, aux) : SGC_MISS;
             out[j] = v;
         }
     }
@@ -914,6 +1039,18 @@ __global__ void table_stats_kernel(const Bucket* tbl, uint32_t nb, Scalars* scal
         if (live) atomicAdd(&scal->n_live, live);
         if (multi) atomicAdd(&scal->n_multi, multi);
         if (mx) atomicMax(&scal->max_id, mx);
+    }
+}
+
+// side[g].id := what a table lookup of side[g].hash returns (MISS for dropped hashes), so that a
+// hash match against a side record is by construction the table's own answer
+__global__ void side_fixup_kernel(const Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, uint4* side, uint64_t n) {
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 r = side[g];
+        const uint64_t h = ((uint64_t)r.y << 32) | r.x;
+        r.z = table_lookup(tbl, nb, nlines, hs, h);
+        r.w = 0;
+        side[g] = r;
     }
 }
 
@@ -1122,6 +1259,10 @@ struct sgc_table {
     uint32_t nlines = 0;
     int home_shift = 0;
     int64_t max_entries = 0;
+    // unitig-ordered side array of {hash, id} records (tables built from sequences)
+    uint4* side = nullptr;
+    int64_t side_cap = 0, side_fill = 0;
+    bool side_dirty = false;
     // pending label call
     bool label_pending = false;
     int64_t label_nseq = 0;
@@ -1489,10 +1630,31 @@ void sgc_table_free(sgc_table* t) {
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
     if (t->buckets) cudaFree(t->buckets);
+    if (t->side) cudaFree(t->side);
     delete t;
 }
 
 int64_t sgc_table_bytes(const sgc_table* t) { return t ? (int64_t)t->nbuckets * (int64_t)sizeof(Bucket) : 0; }
+
+int sgc_table_enable_side(sgc_table* t) {
+    if (!t) return fail(SGC_ERR_ARG, "table is NULL");
+    if (t->side) return SGC_OK;
+    sgc_ctx* c = t->ctx;
+    TRY(set_device(c));
+    const int64_t cap = std::max<int64_t>(t->max_entries, 64);
+    if (cap >= (int64_t)AUX_NONE) return fail(SGC_ERR_CAPACITY, "side array limited to 2^32-2 records");
+    cudaError_t e = cudaMalloc(&t->side, (size_t)cap * sizeof(uint4));
+    if (e != cudaSuccess) {
+        t->side = nullptr;
+        return fail(SGC_ERR_NOMEM, "cudaMalloc(%zu) for the side array failed: %s", (size_t)cap * sizeof(uint4),
+                    cudaGetErrorString(e));
+    }
+    t->side_cap = cap;
+    t->side_fill = 0;
+    return SGC_OK;
+}
+
+int64_t sgc_table_side_bytes(const sgc_table* t) { return t && t->side ? t->side_cap * (int64_t)sizeof(uint4) : 0; }
 
 int sgc_table_set_home_shift(sgc_table* t, int shift) {
     if (!t || shift < 0 || shift > 16) return fail(SGC_ERR_ARG, "bad home shift");
@@ -1525,13 +1687,28 @@ int sgc_table_insert_sequences(sgc_table* t, const uint8_t* d_seq, int64_t seq_b
     if (nseq == 0) return SGC_OK;
     Plan p;
     TRY(make_plan(c, d_off, nseq, seq_bytes, k, nullptr, &p));
+    int64_t total = 0;
+    if (t->side) {
+        CU(cudaMemcpyAsync(&c->h_scal->n_unique, p.kmer_off + nseq, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        total = c->h_scal->n_unique;
+        if (t->side_fill + total > t->side_cap || t->side_fill + total >= (int64_t)AUX_NONE)
+            return fail(SGC_ERR_CAPACITY, "side array of %lld records cannot take %lld more", (long long)t->side_cap,
+                        (long long)total);
+    }
     TRY(zero_scalars(c));
     TileArgs a = base_args(c, d_seq, d_off, k, p, d_status);
     table_args(a, t);
     a.seq_ids = d_ids;
     a.id_base = id_base;
+    a.side = t->side;
+    a.side_base = (unsigned long long)t->side_fill;
     TRY(launch_tile<MODE_INSERT>(c, a));
     TRY(fetch_scalars(c));
+    if (t->side) {
+        t->side_fill += total;
+        t->side_dirty = true;
+    }
     return device_err_check(c);
 }
 
@@ -1678,7 +1855,20 @@ int sgc_label_reads_launch(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes
         table_args(a, t);
         a.pairs = (unsigned long long*)c->pairs_a.p;
         a.pairs_cap = pairs_cap;
-        TRY(launch_tile<MODE_LABEL>(c, a));
+        if (t->side && t->side_fill > 0 && !getenv("SGC_NO_SIDE")) {
+            if (t->side_dirty) {
+                side_fixup_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(t->buckets, t->nbuckets, t->nlines, t->home_shift,
+                                                                        t->side, (uint64_t)t->side_fill);
+                c->launches++;
+                t->side_dirty = false;
+            }
+            a.side = t->side;
+            a.side_n = (unsigned long long)t->side_fill;
+            if (const char* dbg = getenv("SGC_SIDE_DEBUG")) a.debug = atoi(dbg);
+            TRY(launch_tile<MODE_LABEL_SIDE>(c, a));
+        } else {
+            TRY(launch_tile<MODE_LABEL>(c, a));
+        }
     }
     CU(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(Scalars), cudaMemcpyDeviceToHost, c->stream));
     t->label_pending = true;

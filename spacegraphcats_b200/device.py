@@ -201,6 +201,14 @@ class DeviceTable:
             raise ValueError("hashes and ids differ in length")
         check(self._L.sgc_table_insert_pairs(self._h, c.ptr(d_h), c.ptr(d_v), d_h.numel()))
 
+    def enable_side(self):
+        """Allocate the unitig-ordered side array (16 B per k-mer); must precede insert_sequences."""
+        check(self._L.sgc_table_enable_side(self._h))
+
+    @property
+    def side_nbytes(self):
+        return int(self._L.sgc_table_side_bytes(self._h))
+
     def insert_sequences(self, seq, off, ksize, ids=None, id_base=0):
         """Fused hash + insert of every k-mer of every sequence under the sequence's id.
         Returns the per-sequence status array (bit 0: non-ACGT byte seen)."""

@@ -77,10 +77,12 @@ class SyntheticCdbg:
         ctx.sync()
         self.total_unitig_kmers = self.n_kmers + self.dup_kmers
 
-    def build_table(self):
+    def build_table(self, side=False):
         from .device import DeviceTable
 
         t = DeviceTable(self.ctx, self.total_unitig_kmers)
+        if side:
+            t.enable_side()
         t.insert_sequences(self.useq, self.uoff, self.ksize)
         return t
 

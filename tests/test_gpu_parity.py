@@ -263,6 +263,23 @@ def test_label_reads_dory_vs_oracle(ctx, O, dory, dory_index, dory_reads):
     assert hashlib.sha256("".join(lines).encode()).hexdigest() == \
         "933dbab55d9262d91ce6f3fe4c883957480e4f22e6d9ff503a44ee24d3ea7c90"
     assert set(res["ids"].tolist()) == set(range(736))  # test_dory_index_reads: rc == 0
+    # the same from a table loaded from the reference's arrays (no unitig-ordered side array: every
+    # k-mer probes the table) -- both label kernels must agree
+    from spacegraphcats_b200.cdbg.hashing import GpuKmerTable
+
+    plain = GpuKmerTable.from_pairs(ref_h, ref_v, ctx=ctx)
+    assert plain._dev.side_nbytes == 0
+    res2 = plain.label_reads(buf, off, 21)
+    assert np.array_equal(res2["ids_off"], o_off) and np.array_equal(res2["ids"], o_ids)
+    # ... and from a table with the experimental unitig-ordered side array (anchor probe + 64-bit
+    # hash matching against neighbouring unitig positions): identical labels
+    recs = dory[0]
+    ubuf, uoff = pack_sequences([r.sequence for r in recs])
+    sided = GpuKmerTable.from_sequences(ubuf, uoff, 21, ids=np.array([int(r.name) for r in recs], np.uint32), ctx=ctx, side=True)
+    assert sided._dev.side_nbytes > 0
+    res3 = sided.label_reads(buf, off, 21)
+    assert np.array_equal(res3["ids_off"], o_off) and np.array_equal(res3["ids"], o_ids)
+    assert (res3["n_kmers"], res3["n_hits"]) == (o_nk, o_nh)
 
 
 def test_label_reads_synthetic_with_errors_vs_oracle(ctx, O):
@@ -281,9 +298,8 @@ def test_label_reads_synthetic_with_errors_vs_oracle(ctx, O):
     cuts = cuts[cuts < len(g) - k]
     useqs = [g[a : b + k - 1].tobytes() for a, b in zip(cuts[:-1], cuts[1:])]
     ubuf, uoff = pack_sequences(useqs)
-    table = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx)
-    oh, ooff = O.hash_batch(ubuf, uoff, k)
-    oid = np.repeat(np.arange(len(useqs), dtype=np.uint32), np.diff(ooff))
+    table = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx, side=True)  # experimental side-array label kernel
+    table_plain = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx)  # default: every k-mer probes the table
     otab, _, _ = O.build_mphf(k, lambda: iter(O.Record(str(i), s.decode()) for i, s in enumerate(useqs)))
     ot = O.COracleTable(otab.mphf_to_hash, otab.mphf_to_value)
     assert len(table) == len(ot)
@@ -303,6 +319,9 @@ def test_label_reads_synthetic_with_errors_vs_oracle(ctx, O):
     assert (res["n_kmers"], res["n_hits"]) == (o_nk, o_nh)
     assert 0 < o_nh < o_nk
     assert np.array_equal(res["ids_off"], o_off) and np.array_equal(res["ids"], o_ids)
+    res_p = table_plain.label_reads(buf, off, k)  # per-k-mer probing kernel (no side array)
+    assert np.array_equal(res_p["ids_off"], o_off) and np.array_equal(res_p["ids"], o_ids)
+    assert (res_p["n_kmers"], res_p["n_hits"]) == (o_nk, o_nh)
     # the same through per-k-mer ids (count_dominator_abundance shape) and the K4 tail alone
     lk = table.lookup_sequences(buf, off, k, n_ids=len(useqs))
     oh2, ooff2 = O.hash_batch(buf, off, k)
@@ -323,15 +342,16 @@ def test_label_reads_many_ids_per_read_overflows_staging(ctx, O):
     g = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 60_000)]
     useqs = [g[i : i + k].tobytes() for i in range(len(g) - k + 1)]
     ubuf, uoff = pack_sequences(useqs)
-    table = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx)
     otab, _, _ = O.build_mphf(k, lambda: iter(O.Record(str(i), s.decode()) for i, s in enumerate(useqs)))
     ot = O.COracleTable(otab.mphf_to_hash, otab.mphf_to_value)
     reads = [g[i * 1000 : i * 1000 + 5000].tobytes() for i in range(50)] + [g.tobytes()]
     buf, off = pack_sequences(reads)
-    res = table.label_reads(buf, off, k)
     o_off, o_ids, _, _ = ot.label_reads(buf, off, k)
-    assert np.array_equal(res["ids_off"], o_off) and np.array_equal(res["ids"], o_ids)
-    assert res["n_labels"] > 100_000
+    for side in (False, True):
+        table = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx, side=side)
+        res = table.label_reads(buf, off, k)
+        assert np.array_equal(res["ids_off"], o_off) and np.array_equal(res["ids"], o_ids), side
+        assert res["n_labels"] > 100_000
 
 
 # ---------------------------------------------------------------- K5/K6: queries
@@ -600,6 +620,12 @@ def test_full_size_properties(ctx, O):
     # per-k-mer path: histogram total == hits == the label path's hits
     lk = table.lookup_sequences(seq_f, off, k, n_ids=max_id + 1, want_ids=False, to_host=False)
     assert lk["n_hits"] == a["n_hits"] and int(lk["count_by_id"].to(torch.int64).sum()) == a["n_hits"]
+    # the experimental side-array label kernel gives the same labels at full size
+    del a1, a2, lk
+    table_s = cd.build_table(side=True)
+    c = table_s.label_reads(seq_f, off, k, to_host=False)
+    assert torch.equal(c["ids_off"], a["ids_off"]) and torch.equal(c["ids"], a["ids"]) and c["n_hits"] == a["n_hits"]
+    del table_s, c
     # oracle cross-check on a sample of reads through an independent path
     rng = np.random.default_rng(0)
     pick = np.sort(rng.choice(n_reads, 3000, replace=False))
