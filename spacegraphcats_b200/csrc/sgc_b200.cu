@@ -85,14 +85,19 @@ struct Geo {
 // HBM actually moves per random access on B200: measured).  A key lives at probe
 // step s >= 0 from its home bucket hb: steps 1..3 are the other buckets of the home line, steps
 // 4.. walk the following lines.  It sits in the FIRST bucket of that sequence that had a free slot
-// when it arrived and slots are never freed, so a lookup stops at the first bucket that is not
-// full.  aux = index of the k-mer in the table's unitig-ordered side array (AUX_NONE if none).
+// when it arrived and slots are never freed, so a walk stops at the first bucket that is not
+// full -- and it only starts if the home bucket's overflow bit says that some key homed there
+// lives elsewhere (a miss in an un-flagged home bucket costs ONE sector even when it is full).
+// aux[30:0] = index of the k-mer in the table's unitig-ordered side array (AUX_NONE if none);
+// aux[31] of slot 0 = the bucket's overflow bit.
 struct __align__(16) Entry {
     unsigned long long key;
     unsigned int val;  // VAL_EMPTY = free slot, VAL_MULTI = dropped hash, else unitig id
-    unsigned int aux;  // position g of this k-mer in the side array, or AUX_NONE
+    unsigned int aux;  // side-array position (31 bits) | overflow bit (slot 0)
 };
-constexpr uint32_t AUX_NONE = 0xFFFFFFFFu;
+constexpr uint32_t AUX_NONE = 0x7FFFFFFFu;
+constexpr uint32_t AUX_MASK = 0x7FFFFFFFu;
+constexpr uint32_t OVF_BIT = 0x80000000u;
 struct __align__(32) Bucket {
     Entry e[2];
 };
@@ -204,10 +209,12 @@ __device__ __forceinline__ bool cas_entry(Entry* p, const Entry& expect, const E
 __device__ __forceinline__ uint32_t resolve_val(uint32_t v) { return v >= VAL_MULTI ? SGC_MISS : v; }
 
 __device__ __forceinline__ bool bucket_match(const Entry& e0, const Entry& e1, uint64_t h, uint32_t& out, uint32_t& aux) {
-    if (e0.key == h && e0.val != VAL_EMPTY) { out = resolve_val(e0.val); aux = e0.aux; return true; }
-    if (e1.key == h && e1.val != VAL_EMPTY) { out = resolve_val(e1.val); aux = e1.aux; return true; }
+    if (e0.key == h && e0.val != VAL_EMPTY) { out = resolve_val(e0.val); aux = e0.aux & AUX_MASK; return true; }
+    if (e1.key == h && e1.val != VAL_EMPTY) { out = resolve_val(e1.val); aux = e1.aux & AUX_MASK; return true; }
     return false;
 }
+// true when some key whose home is this bucket was placed in a later bucket
+__device__ __forceinline__ bool bucket_overflowed(const Entry& e0) { return (e0.aux & OVF_BIT) != 0; }
 __device__ __forceinline__ bool bucket_match(const Entry& e0, const Entry& e1, uint64_t h, uint32_t& out) {
     uint32_t aux;
     return bucket_match(e0, e1, h, out, aux);
@@ -250,7 +257,7 @@ __device__ __forceinline__ uint32_t table_lookup(const Bucket* tbl, uint32_t nb,
     uint32_t out;
     if (bucket_match(e0, e1, h, out, aux)) return out;
     aux = AUX_NONE;
-    if (!bucket_full(e0, e1)) return SGC_MISS;
+    if (!bucket_overflowed(e0)) return SGC_MISS;
     return lookup_slow(tbl, nlines, hb, h, aux);
 }
 __device__ __forceinline__ uint32_t table_lookup(const Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, uint64_t h) {
@@ -268,7 +275,7 @@ __device__ void table_insert(Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, 
                              Scalars* scal) {
     const uint32_t hb = home_bucket(h, nb, hs);
     const Entry empty{0ULL, VAL_EMPTY, 0u};
-    const Entry mine{h, id, aux};
+    const Entry mine{h, id, aux & AUX_MASK};
     const uint32_t max_steps = nlines > (1u << 20) ? (4u << 20) : nlines * 4u;
     for (uint32_t step = 0; step < max_steps; step++) {
         Bucket* bp = tbl + probe_bucket(hb, step, nlines);
@@ -278,7 +285,11 @@ __device__ void table_insert(Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, 
             load_entry_volatile(&bp->e[s], e);
             if (e.val == VAL_EMPTY) {
                 Entry old;
-                if (cas_entry(&bp->e[s], empty, mine, old)) return;
+                if (cas_entry(&bp->e[s], empty, mine, old)) {
+                    // the home bucket is full (its slot 0 is occupied for good): flag it as overflowed
+                    if (step) atomicOr(&tbl[hb].e[0].aux, OVF_BIT);
+                    return;
+                }
                 e = old;  // somebody else claimed the slot first: examine what they wrote
             }
             if (e.key == h) {
@@ -765,7 +776,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                     if (!bucket_match(p_e0, p_e1, p_h[0], v, g)) {
                         v = SGC_MISS;
                         g = AUX_NONE;
-                        if (bucket_full(p_e0, p_e1) && !(a.debug & 2)) v = lookup_slow(a.tbl, a.nlines, p_b0, p_h[0], g);
+                        if (bucket_overflowed(p_e0) && !(a.debug & 2)) v = lookup_slow(a.tbl, a.nlines, p_b0, p_h[0], g);
                     }
                     ids[0] = v;
                     pending = ((1u << p_nv) - 1u) & ~1u;  // k-mers 1..nv-1 until proven otherwise
@@ -806,7 +817,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                         if ((pending >> d) & 1u) {
                             uint32_t v, aux;
                             if (bucket_match(q0[d - 1], q1[d - 1], p_h[d], v)) ids[d] = v;
-                            else if (bucket_full(q0[d - 1], q1[d - 1])) ids[d] = lookup_slow(a.tbl, a.nlines, qb[d - 1], p_h[d], aux);
+                            else if (bucket_overflowed(q0[d - 1])) ids[d] = lookup_slow(a.tbl, a.nlines, qb[d - 1], p_h[d], aux);
                         }
                     }
                 }
@@ -854,7 +865,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                     if (p_active && t < p_nv) {
                         uint32_t v;
                         if (bucket_match(p_e0[t], p_e1[t], p_h[t], v)) ids[t] = v;
-                        else if (bucket_full(p_e0[t], p_e1[t])) slow |= 1u << t;
+                        else if (bucket_overflowed(p_e0[t])) slow |= 1u << t;
                     }
                 }
                 while (slow) {  // ~6 % of lookups: the key is not in its home bucket; one trip per key
@@ -981,10 +992,10 @@ __global__ void lookup_kernel(const Bucket* tbl, uint32_t nb, uint32_t nlines, i
         load_bucket_nc(tbl + b1, c0, c1);
         uint32_t v;
         uint32_t aux;
-        if (!bucket_match(a0, a1, h0, v)) v = bucket_full(a0, a1) ? lookup_slow(tbl, nlines, b0, h0, aux) : SGC_MISS;
+        if (!bucket_match(a0, a1, h0, v)) v = bucket_overflowed(a0) ? lookup_slow(tbl, nlines, b0, h0, aux) : SGC_MISS;
         out[i] = v;
         if (j < n) {
-            if (!bucket_match(c0, c1, h1, v)) v = bucket_full(c0, c1) ? lookup_slow(tbl, nlines, b1, h1, aux) : SGC_MISS;
+            if (!bucket_match(c0, c1, h1, v)) v = bucket_overflowed(c0) ? lookup_slow(tbl, nlines, b1, h1, aux) : SGC_MISS;
             out[j] = v;
         }
     }
@@ -1642,7 +1653,7 @@ int sgc_table_enable_side(sgc_table* t) {
     sgc_ctx* c = t->ctx;
     TRY(set_device(c));
     const int64_t cap = std::max<int64_t>(t->max_entries, 64);
-    if (cap >= (int64_t)AUX_NONE) return fail(SGC_ERR_CAPACITY, "side array limited to 2^32-2 records");
+    if (cap >= (int64_t)AUX_NONE) return fail(SGC_ERR_CAPACITY, "side array limited to 2^31-2 records");
     cudaError_t e = cudaMalloc(&t->side, (size_t)cap * sizeof(uint4));
     if (e != cudaSuccess) {
         t->side = nullptr;
