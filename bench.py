@@ -158,16 +158,17 @@ def run_reference(args):
     g.build()
     from oracle import oracle as O
 
-    threads = O.lib().sgc_oracle_num_threads()
+    # all host cores, explicitly: torchrun exports OMP_NUM_THREADS=1 to every rank
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     n_kmers, n_reads = args.cpu_kmers, args.cpu_reads
     log("[reference] building CPU table (%d unitig k-mers) and %d reads ..." % (n_kmers, n_reads))
     table, buf, off = cpu_workload(n_kmers, n_reads)
     step_kmers = n_reads * (READ_LEN - KSIZE + 1)
     for _ in range(args.warmup):
-        table.label_reads_checksum(buf, off, KSIZE, threads=0)
+        table.label_reads_checksum(buf, off, KSIZE, threads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        table.label_reads_checksum(buf, off, KSIZE, threads=0)
+        table.label_reads_checksum(buf, off, KSIZE, threads=threads)
     dt = time.perf_counter() - t0
     value = step_kmers * args.steps / dt
     sample = ("oracle port (oracle/sgc_oracle.c, OpenMP): %d x 150-bp reads per step against a %d-k-mer "
@@ -429,10 +430,10 @@ def main():
     if world == 1 and not args.no_cpu:
         from oracle import oracle as O
 
-        threads = O.lib().sgc_oracle_num_threads()
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         log("[cpu_baseline] building the scaled-down CPU workload ...")
         ctab, cbuf, coff = cpu_workload(args.cpu_kmers, args.cpu_reads)
-        rate, nk_tot, secs, reps = cpu_time_sample(ctab, cbuf, coff, 0, args.cpu_seconds)
+        rate, nk_tot, secs, reps = cpu_time_sample(ctab, cbuf, coff, threads, args.cpu_seconds)
         cpu = {"value": rate, "unit": "k-mers/s", "cores": threads, "kind": "port",
                "sample": "%d passes over %d 150-bp reads (%.2e k-mers, %.1f s) against a %d-k-mer synthetic cDBG table; "
                          "oracle/sgc_oracle.c fused hash+lookup+per-read distinct, OpenMP" % (reps, args.cpu_reads, nk_tot, secs, args.cpu_kmers)}
