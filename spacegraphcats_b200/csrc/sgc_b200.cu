@@ -141,7 +141,6 @@ struct TileArgs {
     uint4* side;
     unsigned long long side_base;   // MODE_INSERT: first record of this batch
     unsigned long long side_n;      // MODE_LABEL_SIDE: number of records
-    int debug;                      // experiment switches (results become wrong): 1 = no pending probes, 2 = no anchor slow path
     // MODE_LOOKUP
     uint32_t* kmer_ids;
     uint32_t* count_by_id;
@@ -776,7 +775,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                     if (!bucket_match(p_e0, p_e1, p_h[0], v, g)) {
                         v = SGC_MISS;
                         g = AUX_NONE;
-                        if (bucket_overflowed(p_e0) && !(a.debug & 2)) v = lookup_slow(a.tbl, a.nlines, p_b0, p_h[0], g);
+                        if (bucket_overflowed(p_e0)) v = lookup_slow(a.tbl, a.nlines, p_b0, p_h[0], g);
                     }
                     ids[0] = v;
                     pending = ((1u << p_nv) - 1u) & ~1u;  // k-mers 1..nv-1 until proven otherwise
@@ -804,7 +803,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                         }
                     }
                 }
-                if (pending && !(a.debug & 1)) {  // own probes, all issued before any is consumed
+                if (pending) {  // own probes, all issued before any is consumed
                     Entry q0[3], q1[3];
                     uint32_t qb[3];
 #pragma unroll
@@ -1384,7 +1383,12 @@ int launch_tile_k(sgc_ctx* c, const TileArgs& a) {
         CU(cudaEventCreate(&e1));
         CU(cudaEventRecord(e0, c->stream));
     }
-    tile_kernel<K, MODE><<<c->num_sms * blocks_per_sm, NT, smem, c->stream>>>(a);
+    int ctas = blocks_per_sm;
+    if (const char* lim = getenv("SGC_CTAS_PER_SM")) {  // experiment knob
+        int v = atoi(lim);
+        if (v >= 1 && v < ctas) ctas = v;
+    }
+    tile_kernel<K, MODE><<<c->num_sms * ctas, NT, smem, c->stream>>>(a);
     c->launches++;
     CU(cudaGetLastError());
     if (c->timing) {
@@ -1875,7 +1879,6 @@ int sgc_label_reads_launch(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes
             }
             a.side = t->side;
             a.side_n = (unsigned long long)t->side_fill;
-            if (const char* dbg = getenv("SGC_SIDE_DEBUG")) a.debug = atoi(dbg);
             TRY(launch_tile<MODE_LABEL_SIDE>(c, a));
         } else {
             TRY(launch_tile<MODE_LABEL>(c, a));
