@@ -159,7 +159,8 @@ int sgc_label_reads(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes, const
                     int64_t nseq, int k, int64_t* d_ids_off, uint32_t* d_ids_out, int64_t ids_cap,
                     int32_t* d_status, int64_t* h_n_kmers, int64_t* h_n_hits, int64_t* h_n_labels);
 /* asynchronous two-step form of the same (for pipelined callers): _launch enqueues the
- * work, _finish synchronises and reports; the outputs are valid after _finish. */
+ * work, _finish synchronises and reports; the outputs are valid after _finish.  No other call on
+ * the same context may be made between the two (they share the context's scratch memory). */
 int sgc_label_reads_launch(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes,
                            const int64_t* d_off, int64_t nseq, int k, int64_t* d_ids_off,
                            uint32_t* d_ids_out, int64_t ids_cap, int32_t* d_status);

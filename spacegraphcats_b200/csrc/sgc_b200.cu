@@ -1371,7 +1371,9 @@ int make_plan(sgc_ctx* c, const int64_t* d_off, int64_t nseq, int64_t seq_bytes,
 template <int K, int MODE>
 int launch_tile_k(sgc_ctx* c, const TileArgs& a) {
     size_t smem = sizeof(WarpTile<K>) * WPB;
-    static thread_local int blocks_per_sm = 0;
+    // per device: the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
+    static thread_local int blocks_per_sm_of[64] = {0};
+    int& blocks_per_sm = blocks_per_sm_of[c->device & 63];
     if (!blocks_per_sm) {
         CU(cudaFuncSetAttribute(tile_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, tile_kernel<K, MODE>, NT, smem));
@@ -1531,6 +1533,11 @@ void sgc_ctx_destroy(sgc_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto& ev : c->timed) {
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    c->timed.clear();
     DevBuf* bufs[] = {&c->nk, &c->nseg, &c->seg_first, &c->kmer_off, &c->seg_map, &c->cub_tmp,
                       &c->pairs_a, &c->pairs_b, &c->tmp_hash, &c->tmp_id, &c->tmp_idx, &c->cursor};
     for (DevBuf* b : bufs)

@@ -781,3 +781,70 @@ def test_batched_queries_k31_pseudo_unitigs_vs_oracle(ctx, O):
     o_off, o_ids, o_nk, o_nh = O.COracleTable(otab.mphf_to_hash, otab.mphf_to_value).label_reads(rbuf, roff, k)
     assert np.array_equal(lab["ids_off"], o_off) and np.array_equal(lab["ids"], o_ids)
     assert (lab["n_kmers"], lab["n_hits"]) == (o_nk, o_nh)
+
+
+# ---------------------------------------------------------------- C-ABI error behaviour
+def test_abi_error_paths(ctx):
+    """Every failure is a negative status + message, never an exception from the library or a crash."""
+    import ctypes
+
+    import torch
+
+    from spacegraphcats_b200 import _lib
+    from spacegraphcats_b200.device import DeviceTable, pack_sequences
+
+    L = ctx._L
+    buf, off = pack_sequences(["ACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT"] * 3)
+    d_seq, d_off = ctx.to_device(buf), ctx.to_device(off)
+    d_out = ctx.empty(200, torch.int64)
+    d_koff = ctx.empty(4, torch.int64)
+    tot = ctypes.c_int64(0)
+
+    def msg():
+        return L.sgc_last_error().decode()
+
+    # k out of range
+    for k in (0, 256, -3):
+        rc = L.sgc_hash_batch(ctx._h, ctx.ptr(d_seq), d_seq.numel(), ctx.ptr(d_off), 3, k, ctx.ptr(d_out), 200,
+                              ctx.ptr(d_koff), None, ctypes.byref(tot))
+        assert rc == _lib.SGC_ERR_ARG and "k must be" in msg()
+    # output too small: reports the needed size, writes nothing
+    rc = L.sgc_hash_batch(ctx._h, ctx.ptr(d_seq), d_seq.numel(), ctx.ptr(d_off), 3, 21, ctx.ptr(d_out), 10,
+                          ctx.ptr(d_koff), None, ctypes.byref(tot))
+    assert rc == _lib.SGC_ERR_CAPACITY and tot.value == 60
+    # NULL handles
+    assert L.sgc_hash_batch(None, None, 0, None, 0, 21, None, 0, None, None, None) == _lib.SGC_ERR_ARG
+    assert L.sgc_lookup(None, None, 0, None) == _lib.SGC_ERR_ARG
+    assert L.sgc_label_reads_finish(None, None, None, None) == _lib.SGC_ERR_ARG
+    # device index out of range
+    h = ctypes.c_void_p()
+    assert L.sgc_ctx_create(99, None, ctypes.byref(h)) == _lib.SGC_ERR_ARG and not h.value
+    # finish without launch
+    t = DeviceTable(ctx, 1000)
+    assert L.sgc_label_reads_finish(t._h, None, None, None) == _lib.SGC_ERR_ARG and "no label call pending" in msg()
+    # ranks must be a power of two
+    d_boff = ctx.empty(8, torch.int64)
+    rc = L.sgc_partition_pairs(ctx._h, ctx.ptr(d_out), None, 10, 3, ctx.ptr(d_out), None, ctx.ptr(d_out), ctx.ptr(d_boff), None)
+    assert rc == _lib.SGC_ERR_ARG and "power of two" in msg()
+    # table load out of range
+    assert L.sgc_table_create(ctx._h, 1000, ctypes.c_float(5.0), ctypes.byref(h)) == _lib.SGC_ERR_ARG
+    # ids above SGC_MAX_ID are rejected
+    with pytest.raises(_lib.SgcError):
+        t.insert_pairs(np.array([1, 2], np.uint64), np.array([5, 0xFFFFFFFE], np.uint32))
+    # label buffer too small: the Python layer retries with the size the library reports
+    big = DeviceTable(ctx, 10000)
+    rng = np.random.default_rng(12)
+    seqs = [rand_seq(rng, 200) for _ in range(50)]
+    ub, uo = pack_sequences([s[a : a + 31] for s in seqs for a in range(0, 170)])  # one unitig per k-mer
+    big.insert_sequences(ub, uo, 31)
+    rb, ro = pack_sequences(seqs)
+    res = big.label_reads(rb, ro, 31, ids_cap=4)
+    assert res["n_labels"] > 4 and len(res["ids"]) == res["n_labels"]
+    # two contexts on one device coexist
+    from spacegraphcats_b200.device import Context
+
+    c2 = Context(ctx.device_index)
+    h2, _, _ = c2.hash_batch(buf, off, 21)
+    h1, _, _ = ctx.hash_batch(buf, off, 21)
+    assert np.array_equal(h1, h2)
+    c2.close()
