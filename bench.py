@@ -15,7 +15,9 @@ k-mers hit (cdbg/index_reads.py:143-152).  One STEP = one batch of 2^24 reads (2
          cores) on a bounded, scaled-down sample of the same workload
 
 N > 1 (torchrun): every rank holds the full table and labels its own read batches (weak scaling,
-no data-path collective); the time is the max over ranks.
+no data-path collective); the time is the max over ranks.  ``--table partitioned`` instead runs the
+hash-range partitioned table of configs[4] (exchange fused into the kernels over NVLink peer memory;
+``partitioned-nccl`` = the same regions through NCCL all-to-all) and reports the NVLink roofline.
 """
 import argparse
 import ctypes
@@ -218,6 +220,76 @@ def bind_to_gpu_numa_node(index):
     return 0
 
 
+def run_partitioned(args, rank, world, local):
+    """BASELINE.json configs[4] shape: --table-kmers unitig k-mers in TOTAL, hash-range partitioned over
+    the ranks; every rank labels its own read batches through request/reply exchanges."""
+    import torch
+    import torch.distributed as dist
+
+    from spacegraphcats_b200.device import Context
+    from spacegraphcats_b200.parallel import DeviceEngine, PartitionedIndex, shard_range
+    from spacegraphcats_b200.synth import SyntheticCdbg
+
+    if world < 2:
+        raise SystemExit("--table partitioned needs torchrun with >= 2 ranks")
+    ctx = Context(local)
+    t0 = time.time()
+    cdbg = SyntheticCdbg(ctx, args.table_kmers, KSIZE, seed=1)  # same genome / unitigs on every rank
+    ulo, uhi = shard_range(cdbg.n_unitigs, rank, world)
+    with torch.cuda.stream(ctx.stream):
+        b0, b1 = int(cdbg.uoff[ulo].item()), int(cdbg.uoff[uhi].item())
+        useq = cdbg.useq[b0:b1]
+        uoff = (cdbg.uoff[ulo:uhi + 1] - b0).contiguous()
+        ids = torch.arange(ulo, uhi, dtype=torch.int32, device=ctx.device)
+    p2p = args.table == "partitioned"
+    idx = PartitionedIndex(DeviceEngine(ctx), p2p=p2p).build(useq, uoff, KSIZE, ids)
+    ctx.sync()
+    log("[rank %d] partitioned build %.1fs: %d hashes (%.2f GB) on this rank" % (rank, time.time() - t0, idx.n_local, idx.table.nbytes / 1e9))
+    n_reads = args.batch_reads
+    step_kmers = n_reads * (READ_LEN - KSIZE + 1)
+    nb = max(1, min(2, args.steps + args.warmup))
+    batches = [cdbg.reads(n_reads, READ_LEN, seed=1000 * (rank + 1) + 3 + b, err_ppm=ERR_PPM) for b in range(nb)]
+    ctx.sync()
+    for i in range(args.warmup):
+        res = idx.label_reads(*batches[i % nb], KSIZE)
+    launches0 = ctx.launches
+    dist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local) as clocks:
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            res = idx.label_reads(*batches[(args.warmup + i) % nb], KSIZE)
+        ctx.sync()
+        dist.barrier()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=ctx.device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    if rank == 0:
+        value = world * step_kmers * args.steps / dt
+        link_bytes = (world - 1) / world * 12.0 * step_kmers  # per GPU and direction (8 B out + 4 B back)
+        achieved = link_bytes * args.steps / dt / 1e9
+        line = {
+            "metric": "k-mers hashed+looked-up/sec (index_reads)", "value": value, "unit": "k-mers/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "synthetic cDBG, %d unitig k-mers k=%d hash-range partitioned across %d B200 "
+                                   "(BASELINE.json configs[4] shape), 150bp reads labelled by index_reads" % (args.table_kmers, KSIZE, world),
+                       "ksize": KSIZE, "read_len": READ_LEN, "reads_per_rank_step": n_reads, "table": args.table,
+                       "exchange": "P2P stores into peer inboxes over NVLink (CUDA IPC)" if p2p else "NCCL all-to-all"},
+            "labels_per_read": int(res[1].numel()) / n_reads, "clocks": clocks.summary(), "e2e": None,
+            "gpu_launches": int(ctx.launches - launches0),
+            "roofline": {"bound": "nvlink", "achieved": achieved, "peak": 770.0, "unit": "GB/s", "frac": achieved / 770.0,
+                         "traffic": None, "peak_source": "measured peer copy, B200_PROFILING.md",
+                         "note": "(R-1)/R x 12 B per k-mer per GPU and direction over the whole step; the step is bound by "
+                                 "the un-overlapped hash / probe / gather kernels, not by the link (DESIGN.md section 6)"},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
 # --------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -231,6 +303,9 @@ def main():
     ap.add_argument("--cpu-kmers", type=int, default=20_000_000)
     ap.add_argument("--cpu-reads", type=int, default=400_000)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--table", default="replicated", choices=["replicated", "partitioned", "partitioned-nccl"],
+                    help="replicated (configs[3], default) or hash-range partitioned across the ranks (configs[4]; "
+                         "exchange fused into the kernels over NVLink peer memory, or through NCCL all-to-all)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -260,6 +335,9 @@ def main():
     from spacegraphcats_b200.device import Context
     from spacegraphcats_b200.synth import SyntheticCdbg
     from spacegraphcats_b200._lib import check
+
+    if args.table != "replicated":
+        return run_partitioned(args, rank, world, local)
 
     ctx = Context(local)
     L = ctx._L
