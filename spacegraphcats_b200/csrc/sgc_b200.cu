@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -114,7 +115,7 @@ struct Scalars {
     unsigned int round_ctr;
     unsigned int max_id;
     int err;  // bit 0: table full, bit 1: id out of range
-    int pad;
+    int bad_offsets;  // set by the plan when an offset pair is negative, decreasing or past seq_bytes
 };
 
 struct TileArgs {
@@ -303,14 +304,19 @@ __device__ void table_insert(Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, 
 // ----------------------------------------------------------------------------------
 // plan kernels: per-sequence k-mer / segment counts and the segment map
 // ----------------------------------------------------------------------------------
-__global__ void plan_count_kernel(const int64_t* __restrict__ off, int64_t nseq, int k,
-                                  int64_t* __restrict__ nk_out, int64_t* __restrict__ nseg_out) {
+__global__ void plan_count_kernel(const int64_t* __restrict__ off, int64_t nseq, int k, int64_t seq_bytes,
+                                  int64_t* __restrict__ nk_out, int64_t* __restrict__ nseg_out, Scalars* scal) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s > nseq) return;
     int64_t nk = 0;
     if (s < nseq) {
-        nk = off[s + 1] - off[s] - k + 1;
-        if (nk < 0) nk = 0;
+        const int64_t o0 = off[s], o1 = off[s + 1];
+        if (o0 < 0 || o1 < o0 || o1 > seq_bytes) {
+            atomicOr(&scal->bad_offsets, 1);  // never touch bytes outside the caller's buffer
+        } else {
+            nk = o1 - o0 - k + 1;
+            if (nk < 0) nk = 0;
+        }
     }
     nk_out[s] = nk;
     nseg_out[s] = (nk + SEG_K - 1) / SEG_K;
@@ -1314,8 +1320,8 @@ int set_device(sgc_ctx* c) {
     return SGC_OK;
 }
 
-int zero_scalars(sgc_ctx* c) {
-    CU(cudaMemsetAsync(c->d_scal, 0, sizeof(Scalars), c->stream));
+int zero_scalars(sgc_ctx* c) {  // everything except bad_offsets, which the plan owns
+    CU(cudaMemsetAsync(c->d_scal, 0, offsetof(Scalars, bad_offsets), c->stream));
     return SGC_OK;
 }
 
@@ -1346,8 +1352,9 @@ int make_plan(sgc_ctx* c, const int64_t* d_off, int64_t nseq, int64_t seq_bytes,
     }
     const int64_t max_segs = nseq + seq_bytes / SEG_K + 1;
     TRY(ensure(c, c->seg_map, (size_t)max_segs * 8));
-    plan_count_kernel<<<grid_for((int64_t)n1, 256, 1 << 30), 256, 0, c->stream>>>(d_off, nseq, k, (int64_t*)c->nk.p,
-                                                                               (int64_t*)c->nseg.p);
+    CU(cudaMemsetAsync(&c->d_scal->bad_offsets, 0, sizeof(int), c->stream));
+    plan_count_kernel<<<grid_for((int64_t)n1, 256, 1 << 30), 256, 0, c->stream>>>(
+        d_off, nseq, k, seq_bytes, (int64_t*)c->nk.p, (int64_t*)c->nseg.p, c->d_scal);
     c->launches++;
     size_t tb = 0;
     CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, (int64_t*)c->nk.p, d_kmer_off, (int64_t)n1, c->stream));
@@ -1440,8 +1447,16 @@ void table_args(TileArgs& a, sgc_table* t) {
 }
 
 int device_err_check(sgc_ctx* c) {
+    if (c->h_scal->bad_offsets)
+        return fail(SGC_ERR_ARG, "sequence offsets are negative, decreasing or run past seq_bytes (those sequences were skipped)");
     if (c->h_scal->err & 1) return fail(SGC_ERR_CAPACITY, "k-mer table is full");
     if (c->h_scal->err & 2) return fail(SGC_ERR_ARG, "unitig id above SGC_MAX_ID");
+    return SGC_OK;
+}
+
+int bad_offsets_check(sgc_ctx* c) {
+    if (c->h_scal->bad_offsets)
+        return fail(SGC_ERR_ARG, "sequence offsets are negative, decreasing or run past seq_bytes (those sequences were skipped)");
     return SGC_OK;
 }
 
@@ -1477,6 +1492,7 @@ int pairs_to_csr(sgc_ctx* c, int64_t n, int64_t nseq, int64_t* d_ids_off, uint32
     }
     TRY(fetch_scalars(c));
     if (h_n_labels) *h_n_labels = c->h_scal->n_unique;
+    TRY(bad_offsets_check(c));
     if (c->h_scal->n_unique > ids_cap)
         return fail(SGC_ERR_CAPACITY, "ids_cap %lld < %lld distinct (sequence, id) labels", (long long)ids_cap,
                     (long long)c->h_scal->n_unique);
@@ -1570,6 +1586,8 @@ int sgc_hash_batch(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, const in
     TRY(make_plan(c, d_off, nseq, seq_bytes, k, d_kmer_off, &p));
     int64_t total = -1;
     if (hash_cap < seq_bytes || h_total_kmers) {
+        TRY(fetch_scalars(c));
+        TRY(bad_offsets_check(c));
         CU(cudaMemcpyAsync(&c->h_scal->n_unique, p.kmer_off + nseq, 8, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         total = c->h_scal->n_unique;
@@ -1597,6 +1615,8 @@ int sgc_minhash_batch(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, const
     TRY(make_plan(c, d_off, nseq, seq_bytes, k, d_kmer_off, &p));
     int64_t total = -1;
     if ((d_hash_out && hash_cap < seq_bytes) || h_total_kmers) {
+        TRY(fetch_scalars(c));
+        TRY(bad_offsets_check(c));
         CU(cudaMemcpyAsync(&c->h_scal->n_unique, p.kmer_off + nseq, 8, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         total = c->h_scal->n_unique;
@@ -1851,6 +1871,7 @@ int sgc_lookup_sequences(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes, 
         TRY(fetch_scalars(c));
         if (h_n_hits) *h_n_hits = (int64_t)c->h_scal->n_hits;
         if (h_n_kmers) *h_n_kmers = (int64_t)(c->h_scal->n_hits + c->h_scal->n_miss);
+        TRY(bad_offsets_check(c));
     }
     return SGC_OK;
 }
@@ -1912,6 +1933,7 @@ int sgc_label_reads_finish(sgc_table* t, int64_t* h_n_kmers, int64_t* h_n_hits, 
     const unsigned long long hits = c->h_scal->n_hits, miss = c->h_scal->n_miss;
     if (h_n_hits) *h_n_hits = (int64_t)hits;
     if (h_n_kmers) *h_n_kmers = (int64_t)(hits + miss);
+    TRY(bad_offsets_check(c));
     if (n_pairs > t->label_pairs_cap) {
         if (h_n_labels) *h_n_labels = (int64_t)n_pairs;
         return fail(SGC_ERR_CAPACITY, "candidate buffer %llu < %llu (retry with ids_cap >= %llu)", t->label_pairs_cap,
@@ -2084,7 +2106,8 @@ static int partition_hashes_impl(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_b
     }
     unsigned long long counts[32];
     CU(cudaMemcpyAsync(counts, c->cursor.p, 32 * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    TRY(fetch_scalars(c));
+    TRY(bad_offsets_check(c));
     for (int r = 0; r < n_ranks; r++) {
         h_counts[r] = (int64_t)counts[r];
         if ((int64_t)counts[r] > send_cap)

@@ -840,6 +840,13 @@ def test_abi_error_paths(ctx):
     rb, ro = pack_sequences(seqs)
     res = big.label_reads(rb, ro, 31, ids_cap=4)
     assert res["n_labels"] > 4 and len(res["ids"]) == res["n_labels"]
+    # offsets that run past the buffer (or go backwards) are reported, and nothing outside it is read
+    bad_off = ctx.to_device(np.array([0, 40, 10_000_000, 10_000_040], np.int64))
+    rc = L.sgc_hash_batch(ctx._h, ctx.ptr(d_seq), d_seq.numel(), ctx.ptr(bad_off), 3, 21, ctx.ptr(d_out), 200,
+                          ctx.ptr(d_koff), None, ctypes.byref(tot))
+    assert rc == _lib.SGC_ERR_ARG and "offsets" in msg()
+    with pytest.raises(_lib.SgcError):
+        big.label_reads(rb, np.array([0, 100, 50, len(rb)], np.int64), 31)
     # two contexts on one device coexist
     from spacegraphcats_b200.device import Context
 
