@@ -67,6 +67,7 @@ constexpr int WPB = NT / 32;    // warps per CTA; every warp runs its own rounds
 constexpr int SPW = 8;          // segments staged per warp round (4 lanes stage one segment)
 constexpr int SEG_K = 256;      // k-mers per segment
 constexpr int PAIR_BUF = 128;   // label keys staged per warp before one global reservation
+constexpr int QCAP = 256;       // MODE_LABEL_SIDE: k-mers queued per warp for a dense table probe
 constexpr unsigned long long SEQ_MASK = (1ULL << 40) - 1ULL;
 
 constexpr uint32_t VAL_EMPTY = 0xFFFFFFFFu;
@@ -452,6 +453,59 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
         }
     };
 
+    // MODE_LABEL_SIDE: per-warp queue of k-mers that still need their own table probe
+    unsigned long long* qh = nullptr;
+    uint32_t* qs = nullptr;
+    unsigned q_fill = 0;  // warp-uniform
+    if constexpr (MODE == MODE_LABEL_SIDE) {
+        unsigned char* qbase = smem_raw + sizeof(WarpTile<K>) * WPB;
+        qh = reinterpret_cast<unsigned long long*>(qbase) + (threadIdx.x >> 5) * QCAP;
+        qs = reinterpret_cast<uint32_t*>(qbase + (size_t)WPB * QCAP * 8) + (threadIdx.x >> 5) * QCAP;
+    }
+    // probe the queued k-mers densely: one item per lane, probe of item j+32 in flight while item j is
+    // resolved; hits become (sequence, id) keys right away (no neighbour to compare with here, except
+    // the previous lane's item)
+    auto drain_queue = [&]() {
+        if constexpr (MODE == MODE_LABEL_SIDE) {
+            bool d_act = false;
+            uint64_t d_h = 0;
+            uint32_t d_sq = 0, d_b = 0;
+            Entry d_e0, d_e1;
+            auto settle = [&]() {
+                uint32_t id = SGC_MISS;
+                if (d_act) {
+                    uint32_t v, aux;
+                    if (bucket_match(d_e0, d_e1, d_h, v)) id = v;
+                    else if (bucket_overflowed(d_e0)) id = lookup_slow(a.tbl, a.nlines, d_b, d_h, aux);
+                    if (id != SGC_MISS) my_hits++; else my_miss++;
+                }
+                const unsigned long long key = ((unsigned long long)d_sq << 32) | id;
+                const unsigned long long prevk = __shfl_up_sync(0xffffffffu, key, 1);
+                const bool has = d_act && id != SGC_MISS && !(lane > 0 && prevk == key);
+                const unsigned m = __ballot_sync(0xffffffffu, has);
+                if (m) {
+                    const unsigned total = __popc(m);
+                    if (pair_fill + total > PAIR_BUF) flush_pairs();
+                    if (has) wt.pairs[pair_fill + __popc(m & ((1u << lane) - 1u))] = key;
+                    pair_fill += total;
+                }
+            };
+            for (unsigned j0 = 0; j0 < q_fill; j0 += 32) {
+                const unsigned j = j0 + lane;
+                const bool act = j < q_fill;
+                const uint64_t h = act ? qh[j] : 0ULL;
+                const uint32_t sq = act ? qs[j] : 0u;
+                if (j0 > 0) settle();
+                d_act = act; d_h = h; d_sq = sq;
+                d_b = act ? home_bucket(h, a.nbuckets, a.home_shift) : 0u;
+                load_bucket_nc(a.tbl + d_b, d_e0, d_e1);
+            }
+            if (q_fill) settle();
+            __syncwarp();
+            q_fill = 0;
+        }
+    };
+
     // dynamic round scheduling; the NEXT round index is always requested one round ahead
     unsigned next_round = 0;
     if (lane == 0) next_round = atomicAdd(&a.scal->round_ctr, 1u);
@@ -765,8 +819,9 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
             // hash returns, fixed up after the build).  Consecutive k-mers of a read are consecutive
             // k-mers of the unitig, on one strand or the other, so k-mer t is looked for at side[g+t] and
             // side[g-t]: a full 64-bit hash match there IS the table's answer for that hash.  Anything
-            // not matched (sequencing errors, unitig ends, anchor missing) does its own table probe, so
-            // the result is exactly what per-k-mer probing gives.  Neighbouring threads share side lines.
+            // not matched (sequencing errors, unitig ends, anchor missing) is queued per warp and probed
+            // later DENSELY (every lane busy, probes pipelined), so the result is exactly what per-k-mer
+            // probing gives.  Neighbouring threads share side lines.
             bool p_active = false;
             int p_sg = 0, p_i = 0, p_nv = 0;
             uint64_t p_h[4] = {0, 0, 0, 0};
@@ -808,28 +863,35 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                             }
                         }
                     }
+#pragma unroll
+                    for (int t = 0; t < 4; t++)
+                        if (t < p_nv && !((pending >> t) & 1u)) { if (ids[t] != SGC_MISS) my_hits++; else my_miss++; }
                 }
-                if (pending) {  // own probes, all issued before any is consumed
-                    Entry q0[3], q1[3];
-                    uint32_t qb[3];
+                // queue the unresolved k-mers of this warp iteration (at most 96; room was made before)
+                {
+                    const unsigned np = __popc(pending);
+                    unsigned incl = np;
 #pragma unroll
-                    for (int d = 1; d < 4; d++) {
-                        qb[d - 1] = (pending >> d) & 1u ? home_bucket(p_h[d], a.nbuckets, a.home_shift) : 0u;
-                        if ((pending >> d) & 1u) load_bucket_nc(a.tbl + qb[d - 1], q0[d - 1], q1[d - 1]);
+                    for (int d = 1; d < 32; d <<= 1) {
+                        unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += v;
                     }
+                    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (total) {
+                        unsigned pos = q_fill + incl - np;
+                        const uint32_t sq = pending ? (uint32_t)wt.seq[p_sg] : 0u;
 #pragma unroll
-                    for (int d = 1; d < 4; d++) {
-                        if ((pending >> d) & 1u) {
-                            uint32_t v, aux;
-                            if (bucket_match(q0[d - 1], q1[d - 1], p_h[d], v)) ids[d] = v;
-                            else if (bucket_overflowed(q0[d - 1])) ids[d] = lookup_slow(a.tbl, a.nlines, qb[d - 1], p_h[d], aux);
+                        for (int d = 1; d < 4; d++) {
+                            if ((pending >> d) & 1u) {
+                                qh[pos] = p_h[d];
+                                qs[pos] = sq;
+                                pos++;
+                            }
                         }
+                        q_fill += total;
                     }
                 }
-#pragma unroll
-                for (int t = 0; t < 4; t++)
-                    if (p_active && t < p_nv) { if (ids[t] != SGC_MISS) my_hits++; else my_miss++; }
-                emit_candidates(ids, p_active, p_sg, p_i, p_nv);
+                emit_candidates(ids, p_active, p_sg, p_i, p_nv);  // queued k-mers count as "no id" here
             };
 
             for (int g0 = 0; g0 < G; g0 += 32) {
@@ -844,6 +906,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                     for (int t = 0; t < 4; t++) p_h[t] ^= dep;
                 }
                 if (g0 > 0) resolve();
+                if (q_fill > QCAP - 96) drain_queue();
                 p_active = active; p_sg = sg; p_i = i; p_nv = nv;
 #pragma unroll
                 for (int t = 0; t < 4; t++) p_h[t] = h[t];
@@ -851,6 +914,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                 load_bucket_nc(a.tbl + p_b0, p_e0, p_e1);
             }
             if (G > 0) resolve();
+            if (q_fill > QCAP - 96) drain_queue();
             __syncwarp();
         } else {
             // MODE_LOOKUP / MODE_LABEL, software-pipelined: the 4 table probes of a group are issued
@@ -948,6 +1012,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
         }
     }
 
+    if constexpr (MODE == MODE_LABEL_SIDE) drain_queue();
     if constexpr (MODE == MODE_LABEL || MODE == MODE_GATHER || MODE == MODE_LABEL_SIDE) {
         if (pair_fill) flush_pairs();
     }
@@ -1377,7 +1442,7 @@ int make_plan(sgc_ctx* c, const int64_t* d_off, int64_t nseq, int64_t seq_bytes,
 
 template <int K, int MODE>
 int launch_tile_k(sgc_ctx* c, const TileArgs& a) {
-    size_t smem = sizeof(WarpTile<K>) * WPB;
+    size_t smem = sizeof(WarpTile<K>) * WPB + (MODE == MODE_LABEL_SIDE ? (size_t)WPB * QCAP * 12 : 0);
     // per device: the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
     static thread_local int blocks_per_sm_of[64] = {0};
     int& blocks_per_sm = blocks_per_sm_of[c->device & 63];

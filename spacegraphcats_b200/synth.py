@@ -77,8 +77,13 @@ class SyntheticCdbg:
         ctx.sync()
         self.total_unitig_kmers = self.n_kmers + self.dup_kmers
 
-    def build_table(self, side=False):
+    def build_table(self, side=None):
+        import os
+
         from .device import DeviceTable
+
+        if side is None:
+            side = os.environ.get("SGC_SIDE") == "1"
 
         t = DeviceTable(self.ctx, self.total_unitig_kmers)
         if side:
