@@ -36,9 +36,14 @@ void run_chunk(const uint8_t* tbl, uint64_t bytes, uint64_t* sink, int threads, 
     printf("%s chunk %5d B  thr/SM %4d : %7.2f G chunks/s %7.2f G sectors/s %7.1f GB/s\n", tag, LANES * 32, threads * bps, n / LANES / best / 1e6, n / best / 1e6, n * 32 / best / 1e6);
     fflush(stdout);
 }
-int main() {
+int main(int argc, char** argv) {
+    // argv[1] = GiB to ALLOCATE (the probes always use the first 16 GiB): does the size of the
+    // allocation change the random-access rate (page size / TLB reach)?
+    uint64_t alloc = (argc > 1 ? atoll(argv[1]) : 16) * (1ULL << 30);
     uint64_t bytes = 16ULL << 30; uint8_t* tbl; uint64_t* sink;
-    CK(cudaMalloc(&tbl, bytes)); CK(cudaMalloc(&sink, 8)); CK(cudaMemset(tbl, 1, bytes));
+    if (alloc < bytes) alloc = bytes;
+    CK(cudaMalloc(&tbl, alloc)); CK(cudaMalloc(&sink, 8)); CK(cudaMemset(tbl, 1, alloc));
+    printf("allocated %.1f GiB, probing the first 16 GiB\n", alloc / 1073741824.0);
     size_t g = 0; cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity); printf("default L2 fetch granularity %zu\n", g);
     int thr_cfg[][2] = {{64, 1}, {128, 1}, {256, 1}, {256, 2}, {256, 3}, {256, 4}, {256, 6}, {256, 8}};
     for (auto& c : thr_cfg) run_chunk<1>(tbl, bytes, sink, c[0], c[1], "gran-default");

@@ -1,5 +1,11 @@
-// sgc_b200.cu -- sm_100a kernels + C-ABI (include/sgc_b200.h) for spacegraphcats'
-// k-mer -> cDBG-unitig indexing hot path.  See DESIGN.md for the data layout.
+// sgc_b200.cu -- host side and C-ABI (include/sgc_b200.h) of libsgc_b200.so, the sm_100a
+// implementation of spacegraphcats' k-mer -> cDBG-unitig indexing hot path.  Device code lives in
+//   sgc_kmer.cuh    the reference hash (2 x Murmur3_x64_128) and the k-mer window geometry
+//   sgc_layout.cuh  constants, table slot layout, device scalars, tile-kernel argument block
+//   sgc_table.cuh   table primitives (probe sequence, CAS insert with build_mphf semantics, lookup)
+//   sgc_tile.cuh    segment staging + the warp-autonomous tile kernel (all fused modes)
+//   sgc_kernels.cuh plan / stand-alone table / label-tail / dominator / K7 / generator kernels
+// See DESIGN.md for the data layout.
 //
 //   K1 kmer hash        tile_kernel<K, MODE_HASH>       (khmer get_kmer_hashes, cdbg/hashing.py:14-20)
 //   K2 table build      tile_kernel<K, MODE_INSERT>, insert_pairs_kernel
@@ -56,1260 +62,15 @@ int fail(int code, const char* fmt, ...) {
         if (r_ != SGC_OK) return r_; \
     } while (0)
 
-// ----------------------------------------------------------------------------------
-// tile geometry
-// ----------------------------------------------------------------------------------
-#ifndef SGC_PROBE_MIN_CTAS
-#define SGC_PROBE_MIN_CTAS 2
-#endif
-constexpr int NT = 256;         // threads per CTA
-constexpr int WPB = NT / 32;    // warps per CTA; every warp runs its own rounds (no block barriers)
-constexpr int SPW = 8;          // segments staged per warp round (4 lanes stage one segment)
-constexpr int SEG_K = 256;      // k-mers per segment
-constexpr int PAIR_BUF = 128;   // label keys staged per warp before one global reservation
-constexpr int QCAP = 256;       // MODE_LABEL_SIDE: k-mers queued per warp for a dense table probe
-constexpr unsigned long long SEQ_MASK = (1ULL << 40) - 1ULL;
-
-constexpr uint32_t VAL_EMPTY = 0xFFFFFFFFu;
-constexpr uint32_t VAL_MULTI = 0xFFFFFFFEu;
-
-enum Mode { MODE_HASH = 0, MODE_INSERT = 1, MODE_LOOKUP = 2, MODE_LABEL = 3, MODE_PARTITION = 4, MODE_GATHER = 5, MODE_MINHASH = 6, MODE_LABEL_SIDE = 7 };
-
-template <int K>
-struct Geo {
-    static constexpr int KMAX = K ? K : SGC_MAX_K;
-    static constexpr int SEGB = SEG_K + KMAX - 1;                 // bases in a full segment
-    static constexpr int STRIDE = ((SEGB + 32 + 15) / 16) * 16;   // bytes per staged area
-    static constexpr int WPS = STRIDE / 4;
-};
-
-// The table: 32-byte buckets of two 16-byte slots; four buckets share a 128-byte line (the unit
-// HBM actually moves per random access on B200: measured).  A key lives at probe
-// step s >= 0 from its home bucket hb: steps 1..3 are the other buckets of the home line, steps
-// 4.. walk the following lines.  It sits in the FIRST bucket of that sequence that had a free slot
-// when it arrived and slots are never freed, so a walk stops at the first bucket that is not
-// full -- and it only starts if the home bucket's overflow bit says that some key homed there
-// lives elsewhere (a miss in an un-flagged home bucket costs ONE sector even when it is full).
-// aux[30:0] = index of the k-mer in the table's unitig-ordered side array (AUX_NONE if none);
-// aux[31] of slot 0 = the bucket's overflow bit.
-struct __align__(16) Entry {
-    unsigned long long key;
-    unsigned int val;  // VAL_EMPTY = free slot, VAL_MULTI = dropped hash, else unitig id
-    unsigned int aux;  // side-array position (31 bits) | overflow bit (slot 0)
-};
-constexpr uint32_t AUX_NONE = 0x7FFFFFFFu;
-constexpr uint32_t AUX_MASK = 0x7FFFFFFFu;
-constexpr uint32_t OVF_BIT = 0x80000000u;
-struct __align__(32) Bucket {
-    Entry e[2];
-};
-
-struct Scalars {
-    unsigned long long pair_count;
-    unsigned long long n_hits;
-    unsigned long long n_miss;
-    unsigned long long n_distinct;
-    unsigned long long n_live;
-    unsigned long long n_multi;
-    unsigned long long n_export;
-    long long n_unique;
-    unsigned int round_ctr;
-    unsigned int max_id;
-    int err;  // bit 0: table full, bit 1: id out of range
-    int bad_offsets;  // set by the plan when an offset pair is negative, decreasing or past seq_bytes
-};
-
-struct TileArgs {
-    const uint8_t* seq;
-    const int64_t* off;
-    const int64_t* seg_map;
-    const int64_t* nsegs_p;
-    const int64_t* kmer_off;
-    int32_t* status;
-    Scalars* scal;
-    int k;
-    // MODE_HASH / MODE_MINHASH
-    uint64_t* hash_out;
-    unsigned long long* seq_min;    // MODE_MINHASH: per-sequence minimum (atomicMin), nullable
-    unsigned long long seed;        // MODE_MINHASH: Murmur3 seed (sourmash: 42)
-    // table (MODE_INSERT / MODE_LOOKUP / MODE_LABEL)
-    Bucket* tbl;
-    uint32_t nbuckets;
-    uint32_t nlines;
-    int home_shift;
-    const uint32_t* seq_ids;
-    uint32_t id_base;
-    // side array (unitig-ordered {hash, id} records): written by MODE_INSERT, read by MODE_LABEL_SIDE
-    uint4* side;
-    unsigned long long side_base;   // MODE_INSERT: first record of this batch
-    unsigned long long side_n;      // MODE_LABEL_SIDE: number of records
-    // MODE_LOOKUP
-    uint32_t* kmer_ids;
-    uint32_t* count_by_id;
-    // MODE_LABEL
-    unsigned long long* pairs;
-    unsigned long long pairs_cap;
-    unsigned long long zero;  // always 0 (scheduling dependency, see the pipelined probe loop)
-    // MODE_PARTITION (hash -> owner rank's send region) / MODE_GATHER (replies -> labels)
-    uint64_t* send;                 // n_ranks regions of send_cap hashes
-    uint64_t* peer_send[32];        // where owner r's requests go: send + r*send_cap locally, or the
-                                    // peer-mapped inbox of GPU r (P2P stores over NVLink)
-    unsigned long long send_region_off;  // my region inside a peer inbox (my_rank * send_cap), else 0
-    unsigned long long send_cap;
-    unsigned long long* cursor;     // n_ranks fill counters
-    uint32_t* ridx;                 // per k-mer: owner << (32 - owner_bits) | position in the owner's region
-    const uint32_t* replies;        // same layout as send, 4 bytes per request
-    int owner_bits;
-    int n_ranks;
-};
-
-// ----------------------------------------------------------------------------------
-// table primitives
-// ----------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t home_bucket(uint64_t h, uint32_t nb, int home_shift) {
-    return __umulhi((uint32_t)((h << home_shift) >> 32), nb);
-}
-
-__device__ __forceinline__ uint32_t probe_bucket(uint32_t hb, uint32_t step, uint32_t nlines) {
-    uint32_t line = (hb >> 2) + (step >> 2);
-    if (line >= nlines) line -= nlines;
-    return (line << 2) | ((hb + step) & 3u);
-}
-
-// one 32-byte sector, read-only path, no L1 allocation (random access, no reuse)
-__device__ __forceinline__ void load_bucket_nc(const Bucket* p, Entry& e0, Entry& e1) {
-    unsigned long long a, b, c, d;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
-                 : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
-                 : "l"(p));
-    e0.key = a; e0.val = (uint32_t)b; e0.aux = (uint32_t)(b >> 32);
-    e1.key = c; e1.val = (uint32_t)d; e1.aux = (uint32_t)(d >> 32);
-}
-
-// coherent variant for the build kernels (the table is being written concurrently)
-__device__ __forceinline__ void load_entry_volatile(const Entry* p, Entry& e) {
-    unsigned long long a, b;
-    asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
-    e.key = a; e.val = (uint32_t)b; e.aux = (uint32_t)(b >> 32);
-}
-
-__device__ __forceinline__ bool cas_entry(Entry* p, const Entry& expect, const Entry& desired, Entry& old) {
-    unsigned long long e0 = expect.key, e1 = ((unsigned long long)expect.aux << 32) | expect.val;
-    unsigned long long d0 = desired.key, d1 = ((unsigned long long)desired.aux << 32) | desired.val;
-    unsigned long long o0, o1;
-    asm volatile(
-        "{\n .reg .b128 e, d, o;\n mov.b128 e, {%2, %3};\n mov.b128 d, {%4, %5};\n"
-        " atom.global.relaxed.gpu.cas.b128 o, [%6], e, d;\n mov.b128 {%0, %1}, o;\n}\n"
-        : "=l"(o0), "=l"(o1)
-        : "l"(e0), "l"(e1), "l"(d0), "l"(d1), "l"(p)
-        : "memory");
-    old.key = o0; old.val = (uint32_t)o1; old.aux = (uint32_t)(o1 >> 32);
-    return o0 == e0 && o1 == e1;
-}
-
-__device__ __forceinline__ uint32_t resolve_val(uint32_t v) { return v >= VAL_MULTI ? SGC_MISS : v; }
-
-__device__ __forceinline__ bool bucket_match(const Entry& e0, const Entry& e1, uint64_t h, uint32_t& out, uint32_t& aux) {
-    if (e0.key == h && e0.val != VAL_EMPTY) { out = resolve_val(e0.val); aux = e0.aux & AUX_MASK; return true; }
-    if (e1.key == h && e1.val != VAL_EMPTY) { out = resolve_val(e1.val); aux = e1.aux & AUX_MASK; return true; }
-    return false;
-}
-// true when some key whose home is this bucket was placed in a later bucket
-__device__ __forceinline__ bool bucket_overflowed(const Entry& e0) { return (e0.aux & OVF_BIT) != 0; }
-__device__ __forceinline__ bool bucket_match(const Entry& e0, const Entry& e1, uint64_t h, uint32_t& out) {
-    uint32_t aux;
-    return bucket_match(e0, e1, h, out, aux);
-}
-__device__ __forceinline__ bool bucket_full(const Entry& e0, const Entry& e1) {
-    return e0.val != VAL_EMPTY && e1.val != VAL_EMPTY;
-}
-
-// Slow path of a lookup: the home bucket is full and does not hold the key.  The other three
-// buckets of the home line are read together (the line is already in L2: HBM moved all 128 bytes),
-// then, rarely, the following lines; the walk ends at the first bucket that is not full.
-__device__ __forceinline__ uint32_t lookup_slow(const Bucket* tbl, uint32_t nlines, uint32_t hb, uint64_t h,
-                                                uint32_t& aux) {
-    Entry a0, a1, b0, b1, c0, c1;
-    load_bucket_nc(tbl + probe_bucket(hb, 1, nlines), a0, a1);
-    load_bucket_nc(tbl + probe_bucket(hb, 2, nlines), b0, b1);
-    load_bucket_nc(tbl + probe_bucket(hb, 3, nlines), c0, c1);
-    uint32_t out;
-    aux = AUX_NONE;
-    if (bucket_match(a0, a1, h, out, aux)) return out;
-    if (!bucket_full(a0, a1)) return SGC_MISS;
-    if (bucket_match(b0, b1, h, out, aux)) return out;
-    if (!bucket_full(b0, b1)) return SGC_MISS;
-    if (bucket_match(c0, c1, h, out, aux)) return out;
-    if (!bucket_full(c0, c1)) return SGC_MISS;
-    const uint32_t max_steps = nlines > (1u << 20) ? (4u << 20) : nlines * 4u;
-    for (uint32_t s = 4; s < max_steps; s++) {
-        load_bucket_nc(tbl + probe_bucket(hb, s, nlines), a0, a1);
-        if (bucket_match(a0, a1, h, out, aux)) return out;
-        if (!bucket_full(a0, a1)) return SGC_MISS;
-    }
-    return SGC_MISS;
-}
-
-__device__ __forceinline__ uint32_t table_lookup(const Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, uint64_t h,
-                                                 uint32_t& aux) {
-    uint32_t hb = home_bucket(h, nb, hs);
-    Entry e0, e1;
-    load_bucket_nc(tbl + hb, e0, e1);
-    uint32_t out;
-    if (bucket_match(e0, e1, h, out, aux)) return out;
-    aux = AUX_NONE;
-    if (!bucket_overflowed(e0)) return SGC_MISS;
-    return lookup_slow(tbl, nlines, hb, h, aux);
-}
-__device__ __forceinline__ uint32_t table_lookup(const Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, uint64_t h) {
-    uint32_t aux;
-    return table_lookup(tbl, nb, nlines, hs, h, aux);
-}
-
-// build_mphf insertion semantics (cdbg/index_cdbg_by_kmer.py:40-57, 88-89):
-//   new hash -> stored with id;  same hash, same id -> no-op;
-//   same hash, different id -> the hash is dropped for good (VAL_MULTI).
-// The outcome is independent of the order in which threads arrive: slots only ever go from
-// empty to occupied, every thread walks the same probe sequence, and a lost CAS re-examines
-// what the winner wrote.
-__device__ void table_insert(Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, uint64_t h, uint32_t id, uint32_t aux,
-                             Scalars* scal) {
-    const uint32_t hb = home_bucket(h, nb, hs);
-    const Entry empty{0ULL, VAL_EMPTY, 0u};
-    const Entry mine{h, id, aux & AUX_MASK};
-    const uint32_t max_steps = nlines > (1u << 20) ? (4u << 20) : nlines * 4u;
-    for (uint32_t step = 0; step < max_steps; step++) {
-        Bucket* bp = tbl + probe_bucket(hb, step, nlines);
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-            Entry e;
-            load_entry_volatile(&bp->e[s], e);
-            if (e.val == VAL_EMPTY) {
-                Entry old;
-                if (cas_entry(&bp->e[s], empty, mine, old)) {
-                    // the home bucket is full (its slot 0 is occupied for good): flag it as overflowed
-                    if (step) atomicOr(&tbl[hb].e[0].aux, OVF_BIT);
-                    return;
-                }
-                e = old;  // somebody else claimed the slot first: examine what they wrote
-            }
-            if (e.key == h) {
-                if (e.val != id && e.val != VAL_MULTI) atomicExch(&bp->e[s].val, VAL_MULTI);
-                return;
-            }
-        }
-    }
-    atomicOr(&scal->err, 1);
-}
-
-// ----------------------------------------------------------------------------------
-// plan kernels: per-sequence k-mer / segment counts and the segment map
-// ----------------------------------------------------------------------------------
-__global__ void plan_count_kernel(const int64_t* __restrict__ off, int64_t nseq, int k, int64_t seq_bytes,
-                                  int64_t* __restrict__ nk_out, int64_t* __restrict__ nseg_out, Scalars* scal) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s > nseq) return;
-    int64_t nk = 0;
-    if (s < nseq) {
-        const int64_t o0 = off[s], o1 = off[s + 1];
-        if (o0 < 0 || o1 < o0 || o1 > seq_bytes) {
-            atomicOr(&scal->bad_offsets, 1);  // never touch bytes outside the caller's buffer
-        } else {
-            nk = o1 - o0 - k + 1;
-            if (nk < 0) nk = 0;
-        }
-    }
-    nk_out[s] = nk;
-    nseg_out[s] = (nk + SEG_K - 1) / SEG_K;
-}
-
-__global__ void plan_expand_kernel(const int64_t* __restrict__ seg_first, int64_t nseq,
-                                   int64_t* __restrict__ seg_map) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nseq) return;
-    int64_t a = seg_first[s], b = seg_first[s + 1];
-    for (int64_t j = a; j < b; j++) seg_map[j] = s | ((j - a) << 40);
-}
-
-// ----------------------------------------------------------------------------------
-// staging helpers
-// ----------------------------------------------------------------------------------
-// bytes F[f .. f+4) of a segment whose Ls bases start at global byte address `base`; bytes outside
-// [0, Ls) read as 0 and no aligned word that lies wholly outside the segment is touched.
-__device__ __forceinline__ uint32_t load_window4(uintptr_t base, int f, int Ls, uint32_t& mask) {
-    const int lo_clip = f < 0 ? -f : 0;
-    const int hi_clip = f + 4 > Ls ? f + 4 - Ls : 0;
-    if (lo_clip >= 4 || hi_clip >= 4) { mask = 0; return 0; }
-    mask = (0xFFFFFFFFu << (8 * lo_clip)) & (0xFFFFFFFFu >> (8 * hi_clip));
-    const uintptr_t addr = base + (intptr_t)f;
-    const int s = (int)(addr & 3);
-    const uintptr_t a0 = addr - s;
-    const uintptr_t first = base, last = base + (uintptr_t)Ls;  // valid byte range [first, last)
-    uint32_t lo = 0, hi = 0;
-    if (a0 + 4 > first && a0 < last) lo = __ldg((const uint32_t*)a0);
-    if (s && a0 + 8 > first && a0 + 4 < last) hi = __ldg((const uint32_t*)(a0 + 4));
-    return sgc::funnel_bytes(lo, hi, s) & mask;
-}
-
-// reverse complement of 4 packed bases (byte-reversed, A<->T, C<->G); ok = every byte selected by
-// mask is one of A, C, G, T.  Bytes that are not pass through unchanged (oracle rule).
-__device__ __forceinline__ uint32_t revcomp_word(uint32_t u, uint32_t mask, bool& ok) {
-    // 2-bit code per base from ASCII bits 1..2: A=0 C=1 T=2 G=3
-    const uint32_t code = (u >> 1) & 0x03030303u;
-    const uint32_t t = code | (code >> 4);
-    const uint32_t sel = (t & 0xFFu) | ((t >> 8) & 0xFF00u);
-    const uint32_t expect = __byte_perm(0x47544341u, 0u, sel);   // "ACTG"[code]
-    uint32_t comp = __byte_perm(0x43414754u, 0u, sel);           // "TGAC"[code]
-    ok = ((expect ^ u) & mask) == 0;
-    if (!ok) {
-        comp = 0;
-#pragma unroll
-        for (int b = 0; b < 4; b++) comp |= (uint32_t)sgc::comp_base((uint8_t)(u >> (8 * b))) << (8 * b);
-    }
-    return __byte_perm(comp & mask, 0u, 0x0123u);
-}
-
-// ----------------------------------------------------------------------------------
-// the tile kernel.  Every WARP runs its own rounds: fetch SPW segments, stage their forward and
-// reverse-complement bytes in its slice of shared memory (4 lanes per segment), then each lane
-// hashes groups of 4 consecutive k-mers and feeds them to the mode's sink.  No block barriers:
-// warps drift apart, so one warp's exposed latencies (round fetch, staging loads, table probes)
-// are covered by the other warps of the SM.
-// ----------------------------------------------------------------------------------
-template <int K>
-struct WarpTile {
-    uint32_t F[SPW * Geo<K>::WPS];
-    uint32_t R[SPW * Geo<K>::WPS];
-    unsigned long long pairs[PAIR_BUF];
-    long long start[SPW];
-    long long seq[SPW];
-    long long kout[SPW];
-    int nk[SPW];
-    int gpre[SPW + 1];
-    int pad[3];
-    unsigned wcnt[32];              // MODE_PARTITION: per-owner counts of one warp iteration
-    unsigned wpre[32];              // ... their exclusive prefix (slot of the owner's run in the staging area)
-    uint64_t* dst[PAIR_BUF];        // ... destination address of every staged hash
-    unsigned long long wbase[32];   // ... and the reserved base positions in the owners' regions
-};
-
-template <int K, int MODE>
-__global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP || MODE == MODE_LABEL_SIDE) ? SGC_PROBE_MIN_CTAS : 1) tile_kernel(const TileArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int WPS = Geo<K>::WPS;
-    const int lane = threadIdx.x & 31;
-    WarpTile<K>& wt = reinterpret_cast<WarpTile<K>*>(smem_raw)[threadIdx.x >> 5];
-    const int k = K ? K : a.k;
-    const int64_t nsegs = *a.nsegs_p;
-    const int64_t nrounds = (nsegs + SPW - 1) / SPW;
-    unsigned long long my_hits = 0, my_miss = 0;
-    unsigned pair_fill = 0;  // warp-uniform: keys waiting in wt.pairs
-
-    auto flush_pairs = [&]() {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&a.scal->pair_count, (unsigned long long)pair_fill);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for (unsigned j = lane; j < pair_fill; j += 32)
-            if (base + j < a.pairs_cap) a.pairs[base + j] = wt.pairs[j];
-        __syncwarp();
-        pair_fill = 0;
-    };
-
-    // K4 candidate rule shared by MODE_LABEL and MODE_GATHER: a hit is a candidate (sequence, id) key
-    // unless the previous k-mer of the same segment has the same id (known through a warp shuffle;
-    // the first k-mer of a lane-0 group is conservatively a candidate).  All 32 lanes must call this.
-    auto emit_candidates = [&](const uint32_t (&ids)[4], bool active, int sg, int i, int nv) {
-        const uint32_t prev_lane = __shfl_up_sync(0xffffffffu, ids[3], 1);
-        unsigned long long keys[4] = {0, 0, 0, 0};
-        unsigned nc = 0;
-        if (active) {
-            const unsigned long long sq = (unsigned long long)wt.seq[sg] << 32;
-            uint32_t prev = (i > 0 && lane > 0) ? prev_lane : SGC_MISS;
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                if (t < nv && ids[t] != SGC_MISS && ids[t] != prev) {
-#pragma unroll
-                    for (int u = 0; u < 4; u++)  // constant indices keep keys[] in registers
-                        if (u == (int)nc) keys[u] = sq | ids[t];
-                    nc++;
-                }
-                prev = ids[t];
-            }
-        }
-        unsigned incl = nc;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += v;
-        }
-        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total) {
-            if (pair_fill + total > PAIR_BUF) flush_pairs();
-            unsigned pos = pair_fill + incl - nc;
-#pragma unroll
-            for (unsigned j = 0; j < 4; j++)
-                if (j < nc) wt.pairs[pos++] = keys[j];
-            pair_fill += total;
-        }
-    };
-
-    // MODE_LABEL_SIDE: per-warp queue of k-mers that still need their own table probe
-    unsigned long long* qh = nullptr;
-    uint32_t* qs = nullptr;
-    unsigned q_fill = 0;  // warp-uniform
-    if constexpr (MODE == MODE_LABEL_SIDE) {
-        unsigned char* qbase = smem_raw + sizeof(WarpTile<K>) * WPB;
-        qh = reinterpret_cast<unsigned long long*>(qbase) + (threadIdx.x >> 5) * QCAP;
-        qs = reinterpret_cast<uint32_t*>(qbase + (size_t)WPB * QCAP * 8) + (threadIdx.x >> 5) * QCAP;
-    }
-    // probe the queued k-mers densely: one item per lane, probe of item j+32 in flight while item j is
-    // resolved; hits become (sequence, id) keys right away (no neighbour to compare with here, except
-    // the previous lane's item)
-    auto drain_queue = [&]() {
-        if constexpr (MODE == MODE_LABEL_SIDE) {
-            bool d_act = false;
-            uint64_t d_h = 0;
-            uint32_t d_sq = 0, d_b = 0;
-            Entry d_e0, d_e1;
-            auto settle = [&]() {
-                uint32_t id = SGC_MISS;
-                if (d_act) {
-                    uint32_t v, aux;
-                    if (bucket_match(d_e0, d_e1, d_h, v)) id = v;
-                    else if (bucket_overflowed(d_e0)) id = lookup_slow(a.tbl, a.nlines, d_b, d_h, aux);
-                    if (id != SGC_MISS) my_hits++; else my_miss++;
-                }
-                const unsigned long long key = ((unsigned long long)d_sq << 32) | id;
-                const unsigned long long prevk = __shfl_up_sync(0xffffffffu, key, 1);
-                const bool has = d_act && id != SGC_MISS && !(lane > 0 && prevk == key);
-                const unsigned m = __ballot_sync(0xffffffffu, has);
-                if (m) {
-                    const unsigned total = __popc(m);
-                    if (pair_fill + total > PAIR_BUF) flush_pairs();
-                    if (has) wt.pairs[pair_fill + __popc(m & ((1u << lane) - 1u))] = key;
-                    pair_fill += total;
-                }
-            };
-            for (unsigned j0 = 0; j0 < q_fill; j0 += 32) {
-                const unsigned j = j0 + lane;
-                const bool act = j < q_fill;
-                const uint64_t h = act ? qh[j] : 0ULL;
-                const uint32_t sq = act ? qs[j] : 0u;
-                if (j0 > 0) settle();
-                d_act = act; d_h = h; d_sq = sq;
-                d_b = act ? home_bucket(h, a.nbuckets, a.home_shift) : 0u;
-                load_bucket_nc(a.tbl + d_b, d_e0, d_e1);
-            }
-            if (q_fill) settle();
-            __syncwarp();
-            q_fill = 0;
-        }
-    };
-
-    // dynamic round scheduling; the NEXT round index is always requested one round ahead
-    unsigned next_round = 0;
-    if (lane == 0) next_round = atomicAdd(&a.scal->round_ctr, 1u);
-
-    for (;;) {
-        const unsigned round = __shfl_sync(0xffffffffu, next_round, 0);
-        if ((int64_t)round >= nrounds) break;
-        if (lane == 0) next_round = atomicAdd(&a.scal->round_ctr, 1u);
-        const int64_t seg0 = (int64_t)round * SPW;
-
-        // ---- descriptors (lanes 0..SPW-1) ----
-        {
-            int nk = 0;
-            long long start = 0, sq = 0, kout = 0;
-            const int64_t g = seg0 + lane;
-            if (lane < SPW && g < nsegs) {
-                const unsigned long long e = (unsigned long long)a.seg_map[g];
-                sq = (long long)(e & SEQ_MASK);
-                const long long sn = (long long)(e >> 40);
-                const long long o0 = a.off[sq], o1 = a.off[sq + 1];
-                const long long q0 = sn * SEG_K;
-                const long long rem = o1 - o0 - k + 1 - q0;
-                nk = (int)(rem < SEG_K ? rem : SEG_K);
-                start = o0 + q0;
-                if (a.kmer_off) kout = a.kmer_off[sq] + q0;
-            }
-            int incl = (nk + 3) >> 2;
-#pragma unroll
-            for (int d = 1; d < SPW; d <<= 1) {
-                int v = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += v;
-            }
-            if (lane < SPW) {
-                wt.start[lane] = start;
-                wt.seq[lane] = sq;
-                wt.kout[lane] = kout;
-                wt.nk[lane] = nk;
-                wt.gpre[lane + 1] = incl;
-            }
-            if (lane == 0) wt.gpre[0] = 0;
-        }
-        __syncwarp();
-
-        // ---- stage forward + reverse-complement words straight from global memory ----
-        if constexpr (MODE != MODE_GATHER) {
-            const int sg = lane >> 2, sub = lane & 3;
-            const int nk = wt.nk[sg];
-            if (nk) {
-                const int Ls = nk + k - 1;
-                const uintptr_t base = (uintptr_t)a.seq + (uintptr_t)wt.start[sg];
-                uint32_t* Fs = wt.F + sg * WPS;
-                uint32_t* Rs = wt.R + sg * WPS;
-                const int p = sgc::rc_pad(nk);
-                bool all_ok = true;
-                for (int w = sub; 4 * w < Ls; w += 4) {
-                    uint32_t mask;
-                    Fs[w] = load_window4(base, 4 * w, Ls, mask);
-                }
-                // R word m holds R[4m-4-p .. +4) = revcomp of F[Ls-4m+p .. +4)
-                const int nrw = (Ls + 4 + p + 3) >> 2;
-                for (int m = sub; m < nrw; m += 4) {
-                    uint32_t mask;
-                    const uint32_t u = load_window4(base, Ls - 4 * m + p, Ls, mask);
-                    bool ok;
-                    Rs[m] = revcomp_word(u, mask, ok);
-                    all_ok &= ok;
-                }
-                if (!all_ok && a.status) atomicOr(&a.status[wt.seq[sg]], 1);
-            }
-        }
-        __syncwarp();
-
-        // ---- hash + sink ----
-        const int G = wt.gpre[SPW];
-
-        // locate group g (segment sg, first k-mer i, nv valid k-mers) and hash its 4 k-mers
-        auto locate_and_hash = [&](int g, int& sg, int& i, int& nv, uint64_t (&h)[4]) {
-            int lo = 0;  // largest sg with gpre[sg] <= g
-#pragma unroll
-            for (int step = SPW / 2; step > 0; step >>= 1)
-                if (wt.gpre[lo + step] <= g) lo += step;
-            sg = lo;
-            i = (g - wt.gpre[sg]) << 2;
-            const int nk = wt.nk[sg];
-            nv = nk - i < 4 ? nk - i : 4;
-            const uint32_t* Fs = wt.F + sg * WPS;
-            const uint32_t* Rs = wt.R + sg * WPS;
-            if constexpr (K != 0) {
-                constexpr int NWIN = sgc::KW<K ? K : 1>::NWIN;
-                uint32_t fw[NWIN], rw[NWIN];
-                const uint32_t* fp = Fs + (i >> 2);
-                const uint32_t* rp = Rs + sgc::rc_group_word(nk, i);
-#pragma unroll
-                for (int j = 0; j < NWIN; j++) {
-                    fw[j] = fp[j];
-                    rw[j] = rp[j];
-                }
-#pragma unroll
-                for (int t = 0; t < 4; t++) h[t] = sgc::hash_group_kmer<K ? K : 1>(fw, rw, t);
-            } else {
-                for (int t = 0; t < nv; t++) {
-                    int q = i + t;
-                    h[t] = sgc::murmur3_h1_stream(Fs, q, k) ^
-                           sgc::murmur3_h1_stream(Rs, sgc::rc_byte_of(nk, nk - 1 - q), k);
-                }
-            }
-        };
-
-        if constexpr (MODE == MODE_MINHASH) {
-            // sourmash-style hash: Murmur3(min(kmer, revcomp), seed); all hashes and/or the per-sequence
-            // minimum (MinHash n=1 of cdbg/sort_bcalm_unitigs.py:56-128)
-            for (int g0 = 0; g0 < G; g0 += 32) {
-                const int g = g0 + lane;
-                if (g >= G) continue;
-                int lo = 0;
-#pragma unroll
-                for (int step = SPW / 2; step > 0; step >>= 1)
-                    if (wt.gpre[lo + step] <= g) lo += step;
-                const int sg = lo, i = (g - wt.gpre[sg]) << 2;
-                const int nk = wt.nk[sg];
-                const int nv = nk - i < 4 ? nk - i : 4;
-                const uint32_t* Fs = wt.F + sg * WPS;
-                const uint32_t* Rs = wt.R + sg * WPS;
-                uint64_t h[4] = {~0ULL, ~0ULL, ~0ULL, ~0ULL};
-                if constexpr (K != 0) {
-                    constexpr int NWIN = sgc::KW<K ? K : 1>::NWIN;
-                    uint32_t fw[NWIN], rw[NWIN];
-                    const uint32_t* fp = Fs + (i >> 2);
-                    const uint32_t* rp = Rs + sgc::rc_group_word(nk, i);
-#pragma unroll
-                    for (int j = 0; j < NWIN; j++) {
-                        fw[j] = fp[j];
-                        rw[j] = rp[j];
-                    }
-#pragma unroll
-                    for (int t = 0; t < 4; t++)
-                        if (t < nv) h[t] = sgc::minhash_group_kmer<K ? K : 1>(fw, rw, t, a.seed);
-                } else {
-                    for (int t = 0; t < nv; t++) {
-                        const int q = i + t, rq = sgc::rc_byte_of(nk, nk - 1 - q);
-                        h[t] = sgc::stream_less(Rs, rq, Fs, q, k) ? sgc::murmur3_h1_stream(Rs, rq, k, a.seed)
-                                                                  : sgc::murmur3_h1_stream(Fs, q, k, a.seed);
-                    }
-                }
-                if (a.hash_out) {
-                    uint64_t* o = a.hash_out + wt.kout[sg] + i;
-#pragma unroll
-                    for (int t = 0; t < 4; t++)
-                        if (t < nv) o[t] = h[t];
-                }
-                if (a.seq_min) {
-                    uint64_t m = h[0];
-#pragma unroll
-                    for (int t = 1; t < 4; t++) m = h[t] < m ? h[t] : m;
-                    atomicMin(&a.seq_min[wt.seq[sg]], (unsigned long long)m);
-                }
-            }
-        } else if constexpr (MODE == MODE_HASH || MODE == MODE_INSERT) {
-            for (int g0 = 0; g0 < G; g0 += 32) {
-                const int g = g0 + lane;
-                if (g >= G) continue;
-                int sg, i, nv;
-                uint64_t h[4] = {0, 0, 0, 0};
-                locate_and_hash(g, sg, i, nv, h);
-                if constexpr (MODE == MODE_HASH) {
-                    uint64_t* o = a.hash_out + wt.kout[sg] + i;
-#pragma unroll
-                    for (int t = 0; t < 4; t++)
-                        if (t < nv) o[t] = h[t];
-                } else {
-                    long long sq = wt.seq[sg];
-                    uint32_t id = a.seq_ids ? a.seq_ids[sq] : a.id_base + (uint32_t)sq;
-                    if (id > SGC_MAX_ID) atomicOr(&a.scal->err, 2);
-                    else {
-                        const unsigned long long g0 = a.side_base + (unsigned long long)(wt.kout[sg] + i);
-                        for (int t = 0; t < nv; t++) {
-                            uint32_t aux = AUX_NONE;
-                            if (a.side) {  // unitig-ordered record; its id is fixed up after the build
-                                aux = (uint32_t)(g0 + t);
-                                a.side[g0 + t] = make_uint4((uint32_t)h[t], (uint32_t)(h[t] >> 32), id, 0u);
-                            }
-                            table_insert(a.tbl, a.nbuckets, a.nlines, a.home_shift, h[t], id, aux, a.scal);
-                        }
-                    }
-                }
-            }
-        } else if constexpr (MODE == MODE_PARTITION) {
-            // K7 request side: every hash goes to the send region of its owner rank (top owner_bits
-            // bits).  Positions are reserved per warp iteration (<=128 k-mers): lanes count owners in
-            // shared memory, one lane per owner reserves a run in that owner's region, so each owner
-            // receives runs of consecutive hashes.  ridx remembers where every k-mer's reply will be.
-            const int sh = 32 - a.owner_bits;
-            for (int g0 = 0; g0 < G; g0 += 32) {
-                const int g = g0 + lane;
-                const bool active = g < G;
-                int sg = 0, i = 0, nv = 0;
-                uint64_t h[4] = {0, 0, 0, 0};
-                if (active) locate_and_hash(g, sg, i, nv, h);
-                if (lane < a.n_ranks) wt.wcnt[lane] = 0;
-                __syncwarp();
-                uint32_t own[4], rank[4];
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    own[t] = a.owner_bits ? (uint32_t)(h[t] >> (64 - a.owner_bits)) : 0u;
-                    rank[t] = (active && t < nv) ? atomicAdd(&wt.wcnt[own[t]], 1u) : 0u;
-                }
-                __syncwarp();
-                {   // one lane per owner: reserve the run in the owner's region, prefix for the staging slots
-                    const unsigned c = lane < a.n_ranks ? wt.wcnt[lane] : 0u;
-                    unsigned incl = c;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
-                        if (lane >= d) incl += v;
-                    }
-                    if (lane < a.n_ranks) {
-                        wt.wpre[lane] = incl - c;
-                        wt.wbase[lane] = c ? atomicAdd(&a.cursor[lane], (unsigned long long)c) : 0ULL;
-                    }
-                }
-                __syncwarp();
-                // Stage the <=128 hashes of this iteration grouped by owner (reusing the idle label
-                // staging area: 128 hashes + 128 destination addresses), then copy them out with
-                // consecutive lanes on consecutive addresses: each owner gets its run as full-width
-                // coalesced stores -- what NVLink wants when the destination is a peer GPU's inbox.
-                unsigned long long* stage_h = wt.pairs;                       // PAIR_BUF = 128 entries
-                if (active) {
-                    const long long ko = wt.kout[sg] + i;
-#pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        if (t < nv) {
-                            const unsigned long long pos = wt.wbase[own[t]] + rank[t];
-                            a.ridx[ko + t] = (a.owner_bits ? (own[t] << sh) : 0u) | (uint32_t)pos;
-                        }
-                    }
-                }
-                __syncwarp();
-                if (a.n_ranks <= 2) {
-                    // few owners: runs are long enough for direct stores (measured faster at R = 2)
-                    if (active) {
-#pragma unroll
-                        for (int t = 0; t < 4; t++) {
-                            if (t < nv) {
-                                const unsigned long long pos = wt.wbase[own[t]] + rank[t];
-                                if (pos < a.send_cap) a.peer_send[own[t]][a.send_region_off + pos] = h[t];
-                            }
-                        }
-                    }
-                } else {
-                    if (active) {
-#pragma unroll
-                        for (int t = 0; t < 4; t++) {
-                            if (t < nv) {
-                                const unsigned slot = wt.wpre[own[t]] + rank[t];
-                                const unsigned long long pos = wt.wbase[own[t]] + rank[t];
-                                stage_h[slot] = h[t];
-                                wt.dst[slot] = pos < a.send_cap ? a.peer_send[own[t]] + a.send_region_off + pos : nullptr;
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    const unsigned total = wt.wpre[a.n_ranks - 1] + wt.wcnt[a.n_ranks - 1];
-                    for (unsigned j = lane; j < total; j += 32) {
-                        uint64_t* d = wt.dst[j];
-                        if (d) *d = stage_h[j];
-                    }
-                }
-                __syncwarp();
-            }
-        } else if constexpr (MODE == MODE_GATHER) {
-            // K7 reply side: ids come from the owners' replies instead of local probes; same K4 rule
-            const int sh = 32 - a.owner_bits;
-            const uint32_t pmask = a.owner_bits ? ((1u << sh) - 1u) : 0xFFFFFFFFu;
-            for (int g0 = 0; g0 < G; g0 += 32) {
-                const int g = g0 + lane;
-                const bool active = g < G;
-                int sg = 0, i = 0, nv = 0;
-                uint32_t ids[4] = {SGC_MISS, SGC_MISS, SGC_MISS, SGC_MISS};
-                if (active) {
-                    int lo = 0;
-#pragma unroll
-                    for (int step = SPW / 2; step > 0; step >>= 1)
-                        if (wt.gpre[lo + step] <= g) lo += step;
-                    sg = lo;
-                    i = (g - wt.gpre[sg]) << 2;
-                    const int nk = wt.nk[sg];
-                    nv = nk - i < 4 ? nk - i : 4;
-                    const long long ko = wt.kout[sg] + i;
-#pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        if (t < nv) {
-                            const uint32_t r = a.ridx[ko + t];
-                            const unsigned long long own = a.owner_bits ? (r >> sh) : 0u;
-                            ids[t] = a.replies[own * a.send_cap + (r & pmask)];
-                            if (ids[t] != SGC_MISS) my_hits++; else my_miss++;
-                        }
-                    }
-                }
-                if (a.kmer_ids && active) {
-                    uint32_t* o = a.kmer_ids + wt.kout[sg] + i;
-#pragma unroll
-                    for (int t = 0; t < 4; t++)
-                        if (t < nv) o[t] = ids[t];
-                }
-                emit_candidates(ids, active, sg, i, nv);
-            }
-        } else if constexpr (MODE == MODE_LABEL_SIDE) {
-            // K4 with fewer HBM lines per k-mer.  Only the FIRST k-mer of a group (the anchor) probes the
-            // hash table (software-pipelined like MODE_LABEL).  Its slot carries g, the k-mer's position in
-            // the table's unitig-ordered side array of {hash, id} records (id = what a table lookup of that
-            // hash returns, fixed up after the build).  Consecutive k-mers of a read are consecutive
-            // k-mers of the unitig, on one strand or the other, so k-mer t is looked for at side[g+t] and
-            // side[g-t]: a full 64-bit hash match there IS the table's answer for that hash.  Anything
-            // not matched (sequencing errors, unitig ends, anchor missing) is queued per warp and probed
-            // later DENSELY (every lane busy, probes pipelined), so the result is exactly what per-k-mer
-            // probing gives.  Neighbouring threads share side lines.
-            bool p_active = false;
-            int p_sg = 0, p_i = 0, p_nv = 0;
-            uint64_t p_h[4] = {0, 0, 0, 0};
-            uint32_t p_b0 = 0;
-            Entry p_e0, p_e1;
-
-            auto resolve = [&]() {
-                uint32_t ids[4] = {SGC_MISS, SGC_MISS, SGC_MISS, SGC_MISS};
-                unsigned pending = 0;
-                if (p_active) {
-                    uint32_t v = SGC_MISS, g = AUX_NONE;
-                    if (!bucket_match(p_e0, p_e1, p_h[0], v, g)) {
-                        v = SGC_MISS;
-                        g = AUX_NONE;
-                        if (bucket_overflowed(p_e0)) v = lookup_slow(a.tbl, a.nlines, p_b0, p_h[0], g);
-                    }
-                    ids[0] = v;
-                    pending = ((1u << p_nv) - 1u) & ~1u;  // k-mers 1..nv-1 until proven otherwise
-                    if (g != AUX_NONE) {
-                        uint4 up[3], um[3];
-#pragma unroll
-                        for (int d = 1; d < 4; d++) {
-                            const bool hi_ok = d < p_nv && (unsigned long long)g + d < a.side_n;
-                            const bool lo_ok = d < p_nv && g >= (uint32_t)d;
-                            up[d - 1] = hi_ok ? __ldg(a.side + g + d) : make_uint4(0, 0, SGC_MISS, 1);
-                            um[d - 1] = lo_ok ? __ldg(a.side + g - d) : make_uint4(0, 0, SGC_MISS, 1);
-                        }
-#pragma unroll
-                        for (int d = 1; d < 4; d++) {
-                            if (d < p_nv) {
-                                const uint32_t lo = (uint32_t)p_h[d], hi = (uint32_t)(p_h[d] >> 32);
-                                if (up[d - 1].x == lo && up[d - 1].y == hi && up[d - 1].w == 0) {
-                                    ids[d] = up[d - 1].z;
-                                    pending &= ~(1u << d);
-                                } else if (um[d - 1].x == lo && um[d - 1].y == hi && um[d - 1].w == 0) {
-                                    ids[d] = um[d - 1].z;
-                                    pending &= ~(1u << d);
-                                }
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int t = 0; t < 4; t++)
-                        if (t < p_nv && !((pending >> t) & 1u)) { if (ids[t] != SGC_MISS) my_hits++; else my_miss++; }
-                }
-                // queue the unresolved k-mers of this warp iteration (at most 96; room was made before)
-                {
-                    const unsigned np = __popc(pending);
-                    unsigned incl = np;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
-                        if (lane >= d) incl += v;
-                    }
-                    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-                    if (total) {
-                        unsigned pos = q_fill + incl - np;
-                        const uint32_t sq = pending ? (uint32_t)wt.seq[p_sg] : 0u;
-#pragma unroll
-                        for (int d = 1; d < 4; d++) {
-                            if ((pending >> d) & 1u) {
-                                qh[pos] = p_h[d];
-                                qs[pos] = sq;
-                                pos++;
-                            }
-                        }
-                        q_fill += total;
-                    }
-                }
-                emit_candidates(ids, p_active, p_sg, p_i, p_nv);  // queued k-mers count as "no id" here
-            };
-
-            for (int g0 = 0; g0 < G; g0 += 32) {
-                const int g = g0 + lane;
-                const bool active = g < G;
-                int sg = 0, i = 0, nv = 0;
-                uint64_t h[4] = {0, 0, 0, 0};
-                if (active) locate_and_hash(g, sg, i, nv, h);   // the previous group's anchor probe is in flight here
-                {
-                    const uint64_t dep = (h[0] ^ h[1] ^ h[2] ^ h[3]) & a.zero;  // see MODE_LABEL
-#pragma unroll
-                    for (int t = 0; t < 4; t++) p_h[t] ^= dep;
-                }
-                if (g0 > 0) resolve();
-                if (q_fill > QCAP - 96) drain_queue();
-                p_active = active; p_sg = sg; p_i = i; p_nv = nv;
-#pragma unroll
-                for (int t = 0; t < 4; t++) p_h[t] = h[t];
-                p_b0 = active ? home_bucket(h[0], a.nbuckets, a.home_shift) : 0u;
-                load_bucket_nc(a.tbl + p_b0, p_e0, p_e1);
-            }
-            if (G > 0) resolve();
-            if (q_fill > QCAP - 96) drain_queue();
-            __syncwarp();
-        } else {
-            // MODE_LOOKUP / MODE_LABEL, software-pipelined: the 4 table probes of a group are issued
-            // and left in flight while the NEXT group's 8 Murmur3 evaluations run; they are resolved
-            // one iteration later.  Integer pipe and HBM latency overlap inside a thread.
-            bool p_active = false;
-            int p_sg = 0, p_i = 0, p_nv = 0;
-            uint64_t p_h[4] = {0, 0, 0, 0};
-            uint32_t p_b[4] = {0, 0, 0, 0};
-            Entry p_e0[4], p_e1[4];
-
-            auto resolve = [&]() {
-                uint32_t ids[4] = {SGC_MISS, SGC_MISS, SGC_MISS, SGC_MISS};
-                unsigned slow = 0;
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    if (p_active && t < p_nv) {
-                        uint32_t v;
-                        if (bucket_match(p_e0[t], p_e1[t], p_h[t], v)) ids[t] = v;
-                        else if (bucket_overflowed(p_e0[t])) slow |= 1u << t;
-                    }
-                }
-                while (slow) {  // ~6 % of lookups: the key is not in its home bucket; one trip per key
-                    const int t = __ffs(slow) - 1;
-                    slow &= slow - 1;
-                    const uint64_t hk = t == 0 ? p_h[0] : t == 1 ? p_h[1] : t == 2 ? p_h[2] : p_h[3];
-                    const uint32_t hb = t == 0 ? p_b[0] : t == 1 ? p_b[1] : t == 2 ? p_b[2] : p_b[3];
-                    uint32_t aux_unused;
-                    const uint32_t v = lookup_slow(a.tbl, a.nlines, hb, hk, aux_unused);
-#pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if (u == t) ids[u] = v;
-                }
-#pragma unroll
-                for (int t = 0; t < 4; t++)
-                    if (p_active && t < p_nv) { if (ids[t] != SGC_MISS) my_hits++; else my_miss++; }
-
-                if constexpr (MODE == MODE_LOOKUP) {
-                    if (p_active) {
-                        if (a.kmer_ids) {
-                            uint32_t* o = a.kmer_ids + wt.kout[p_sg] + p_i;
-#pragma unroll
-                            for (int t = 0; t < 4; t++)
-                                if (t < p_nv) o[t] = ids[t];
-                        }
-                        if (a.count_by_id) {
-                            // run-length aggregate within the group before touching L2
-#pragma unroll
-                            for (int t = 0; t < 4; t++) {
-                                if (t < p_nv && ids[t] != SGC_MISS) {
-                                    unsigned run = 1;
-                                    bool counted = false;
-#pragma unroll
-                                    for (int u = 0; u < 4; u++) {
-                                        if (u < t && ids[u] == ids[t]) counted = true;
-                                        if (u > t && u < p_nv && ids[u] == ids[t]) run++;
-                                    }
-                                    if (!counted) atomicAdd(&a.count_by_id[ids[t]], run);
-                                }
-                            }
-                        }
-                    }
-                } else {
-                    emit_candidates(ids, p_active, p_sg, p_i, p_nv);
-                }
-            };
-
-            for (int g0 = 0; g0 < G; g0 += 32) {
-                const int g = g0 + lane;
-                const bool active = g < G;
-                int sg = 0, i = 0, nv = 0;
-                uint64_t h[4] = {0, 0, 0, 0};
-                if (active) locate_and_hash(g, sg, i, nv, h);   // previous group's probes are in flight here
-                // Order the resolve AFTER the hash computation in the instruction stream: a.zero is
-                // always 0 but only known at run time, so the compares below truly depend on the new
-                // hashes and neither nvcc nor ptxas can sink the Murmur3 code under the resolve.
-                {
-                    const uint64_t dep = (h[0] ^ h[1] ^ h[2] ^ h[3]) & a.zero;
-#pragma unroll
-                    for (int t = 0; t < 4; t++) p_h[t] ^= dep;
-                }
-                if (g0 > 0) resolve();
-                p_active = active; p_sg = sg; p_i = i; p_nv = nv;
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    p_h[t] = h[t];
-                    // lanes / k-mers with nothing to look up probe bucket 0 (an L2 hit) so that the
-                    // loads are unconditional and land directly in the pipeline registers
-                    p_b[t] = (active && t < nv) ? home_bucket(h[t], a.nbuckets, a.home_shift) : 0u;
-                    load_bucket_nc(a.tbl + p_b[t], p_e0[t], p_e1[t]);
-                }
-            }
-            if (G > 0) resolve();
-            __syncwarp();
-        }
-    }
-
-    if constexpr (MODE == MODE_LABEL_SIDE) drain_queue();
-    if constexpr (MODE == MODE_LABEL || MODE == MODE_GATHER || MODE == MODE_LABEL_SIDE) {
-        if (pair_fill) flush_pairs();
-    }
-    if constexpr (MODE == MODE_LOOKUP || MODE == MODE_LABEL || MODE == MODE_GATHER || MODE == MODE_LABEL_SIDE) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            my_hits += __shfl_xor_sync(0xffffffffu, my_hits, d);
-            my_miss += __shfl_xor_sync(0xffffffffu, my_miss, d);
-        }
-        if (lane == 0) {
-            if (my_hits) atomicAdd(&a.scal->n_hits, my_hits);
-            if (my_miss) atomicAdd(&a.scal->n_miss, my_miss);
-        }
-    }
-}
-
-// ----------------------------------------------------------------------------------
-// stand-alone table kernels
-// ----------------------------------------------------------------------------------
-__global__ void table_clear_kernel(Bucket* tbl, uint32_t nb) {
-    const Entry empty{0ULL, VAL_EMPTY, 0u};
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (uint64_t)nb * 2;
-         i += (uint64_t)gridDim.x * blockDim.x)
-        reinterpret_cast<Entry*>(tbl)[i] = empty;
-}
-
-__global__ void insert_pairs_kernel(Bucket* tbl, uint32_t nb, uint32_t nlines, int hs,
-                                    const uint64_t* __restrict__ hash, const uint32_t* __restrict__ id, int64_t n,
-                                    Scalars* scal) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t v = id[i];
-        if (v > SGC_MAX_ID) atomicOr(&scal->err, 2);
-        else table_insert(tbl, nb, nlines, hs, hash[i], v, AUX_NONE, scal);
-    }
-}
-
-__global__ void lookup_kernel(const Bucket* tbl, uint32_t nb, uint32_t nlines, int hs,
-                              const uint64_t* __restrict__ hash, int64_t n, uint32_t* __restrict__ out) {
-    // two probes in flight per thread
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
-        const int64_t j = i + stride;
-        const uint64_t h0 = hash[i], h1 = j < n ? hash[j] : 0;
-        const uint32_t b0 = home_bucket(h0, nb, hs), b1 = j < n ? home_bucket(h1, nb, hs) : 0u;
-        Entry a0, a1, c0, c1;
-        load_bucket_nc(tbl + b0, a0, a1);
-        load_bucket_nc(tbl + b1, c0, c1);
-        uint32_t v;
-        uint32_t aux;
-        if (!bucket_match(a0, a1, h0, v)) v = bucket_overflowed(a0) ? lookup_slow(tbl, nlines, b0, h0, aux) : SGC_MISS;
-        out[i] = v;
-        if (j < n) {
-            if (!bucket_match(c0, c1, h1, v)) v = bucket_overflowed(c0) ? lookup_slow(tbl, nlines, b1, h1, aux) : SGC_MISS;
-            out[j] = v;
-        }
-    }
-}
-
-// get_unique_values: count_by_id[id]++ per present hash.  With distinct != 0 the input is
-// sorted and a hash equal to its predecessor is skipped.
-__global__ void count_kernel(const Bucket* tbl, uint32_t nb, uint32_t nlines, int hs,
-                             const uint64_t* __restrict__ hash, int64_t n, int distinct, uint32_t* count_by_id,
-                             Scalars* scal) {
-    unsigned long long miss = 0, nd = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        uint64_t h = hash[i];
-        if (distinct && i > 0 && hash[i - 1] == h) continue;
-        nd++;
-        uint32_t v = table_lookup(tbl, nb, nlines, hs, h);
-        if (v == SGC_MISS) miss++;
-        else atomicAdd(&count_by_id[v], 1u);
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        miss += __shfl_xor_sync(0xffffffffu, miss, d);
-        nd += __shfl_xor_sync(0xffffffffu, nd, d);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (miss) atomicAdd(&scal->n_miss, miss);
-        if (nd) atomicAdd(&scal->n_distinct, nd);
-    }
-}
-
-__global__ void table_stats_kernel(const Bucket* tbl, uint32_t nb, Scalars* scal) {
-    unsigned long long live = 0, multi = 0;
-    unsigned mx = 0;
-    const Entry* e = reinterpret_cast<const Entry*>(tbl);
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (uint64_t)nb * 2;
-         i += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t v = e[i].val;
-        if (v == VAL_MULTI) multi++;
-        else if (v != VAL_EMPTY) {
-            live++;
-            mx = v > mx ? v : mx;
-        }
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        live += __shfl_xor_sync(0xffffffffu, live, d);
-        multi += __shfl_xor_sync(0xffffffffu, multi, d);
-        unsigned o = __shfl_xor_sync(0xffffffffu, mx, d);
-        mx = o > mx ? o : mx;
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (live) atomicAdd(&scal->n_live, live);
-        if (multi) atomicAdd(&scal->n_multi, multi);
-        if (mx) atomicMax(&scal->max_id, mx);
-    }
-}
-
-// side[g].id := what a table lookup of side[g].hash returns (MISS for dropped hashes), so that a
-// hash match against a side record is by construction the table's own answer
-__global__ void side_fixup_kernel(const Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, uint4* side, uint64_t n) {
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (uint64_t)gridDim.x * blockDim.x) {
-        uint4 r = side[g];
-        const uint64_t h = ((uint64_t)r.y << 32) | r.x;
-        r.z = table_lookup(tbl, nb, nlines, hs, h);
-        r.w = 0;
-        side[g] = r;
-    }
-}
-
-__global__ void table_export_kernel(const Bucket* tbl, uint32_t nb, uint64_t* hash_out, uint32_t* id_out,
-                                    unsigned long long cap, Scalars* scal) {
-    const Entry* e = reinterpret_cast<const Entry*>(tbl);
-    const uint64_t total = (uint64_t)nb * 2;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t rounds = (total + stride - 1) / stride;
-    const int lane = threadIdx.x & 31;
-    for (uint64_t r = 0; r < rounds; r++) {
-        uint64_t i = r * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        Entry x{0ULL, VAL_EMPTY, 0u};
-        if (i < total) x = e[i];
-        bool live = x.val < VAL_MULTI;
-        unsigned m = __ballot_sync(0xffffffffu, live);
-        if (m) {
-            unsigned long long base = 0;
-            int leader = __ffs(m) - 1;
-            if (lane == leader) base = atomicAdd(&scal->n_export, (unsigned long long)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (live) {
-                unsigned long long p = base + __popc(m & ((1u << lane) - 1u));
-                if (p < cap) {
-                    hash_out[p] = x.key;
-                    id_out[p] = x.val;
-                }
-            }
-        }
-    }
-}
-
-// ----------------------------------------------------------------------------------
-// label tail: unique (seq, id) keys -> CSR
-// ----------------------------------------------------------------------------------
-__global__ void csr_count_kernel(const unsigned long long* __restrict__ uniq, const long long* __restrict__ n_p,
-                                 unsigned long long* ids_off, uint32_t* ids_out, int64_t ids_cap) {
-    const int64_t n = *n_p;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
-        unsigned long long key = uniq[j];
-        atomicAdd(&ids_off[(key >> 32) + 1], 1ULL);
-        if (j < ids_cap) ids_out[j] = (uint32_t)key;
-    }
-}
-
-// per-k-mer ids (already looked up, possibly on other ranks) -> candidate (seq, id) keys
-__global__ void ids_to_pairs_kernel(const uint32_t* __restrict__ kmer_ids, const int64_t* __restrict__ kmer_off,
-                                    int64_t nseq, unsigned long long* pairs, unsigned long long cap, Scalars* scal) {
-    unsigned long long hits = 0;
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nseq; s += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t prev = SGC_MISS;
-        for (int64_t j = kmer_off[s]; j < kmer_off[s + 1]; j++) {
-            uint32_t v = kmer_ids[j];
-            if (v != SGC_MISS) {
-                hits++;
-                if (v != prev) {
-                    unsigned long long p = atomicAdd(&scal->pair_count, 1ULL);
-                    if (p < cap) pairs[p] = ((unsigned long long)s << 32) | v;
-                }
-            }
-            prev = v;
-        }
-    }
-    if (hits) atomicAdd(&scal->n_hits, hits);
-}
-
-// ----------------------------------------------------------------------------------
-// K6: per-dominator sums, one launch per catlas level
-// ----------------------------------------------------------------------------------
-__global__ void dom_level_kernel(const uint32_t* __restrict__ src, const int64_t* __restrict__ member_off,
-                                 const uint32_t* __restrict__ member, const uint32_t* __restrict__ nodes,
-                                 int64_t n, uint32_t* node_count) {
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    uint32_t v = nodes[j];
-    uint32_t s = 0;
-    for (int64_t m = member_off[v]; m < member_off[v + 1]; m++) s += src[member[m]];
-    node_count[v] = s;
-}
-
-// ----------------------------------------------------------------------------------
-// K7 helpers
-// ----------------------------------------------------------------------------------
-__global__ void iota_kernel(int64_t* p, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = i;
-}
-
-// sorted by the top `bits` bits: bucket_off[r] = first index whose owner >= r
-__global__ void bucket_bounds_kernel(const uint64_t* __restrict__ sorted, int64_t n, int bits, int n_ranks,
-                                     int64_t* bucket_off) {
-    int r = threadIdx.x;
-    if (r > n_ranks) return;
-    if (r == n_ranks) { bucket_off[r] = n; return; }
-    int64_t lo = 0, hi = n;
-    while (lo < hi) {
-        int64_t mid = (lo + hi) >> 1;
-        unsigned owner = bits ? (unsigned)(sorted[mid] >> (64 - bits)) : 0u;
-        if (owner < (unsigned)r) lo = mid + 1; else hi = mid;
-    }
-    bucket_off[r] = lo;
-}
-
-__global__ void gather_u32_kernel(const uint32_t* __restrict__ in, const int64_t* __restrict__ perm, int64_t n,
-                                  uint32_t* out, int scatter) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        if (scatter) out[perm[i]] = in[i];
-        else out[i] = in[perm[i]];
-    }
-}
-
-// ----------------------------------------------------------------------------------
-// synthetic workload generators (bench / tests only)
-// ----------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
-    x += 0x9E3779B97F4A7C15ULL;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
-    return x ^ (x >> 31);
-}
-
-__global__ void synth_genome_kernel(uint8_t* out, int64_t n, uint64_t seed) {
-    // 32 bases per 64-bit draw
-    const int64_t nw = (n + 31) / 32;
-    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += (int64_t)gridDim.x * blockDim.x) {
-        uint64_t r = splitmix64(seed * 0xD1342543DE82EF95ULL + (uint64_t)w);
-        for (int j = 0; j < 32; j++) {
-            int64_t i = w * 32 + j;
-            if (i < n) out[i] = "ACGT"[(r >> (2 * j)) & 3];
-        }
-    }
-}
-
-// read r = genome[p .. p+len) at a uniform position, reverse-complemented when bit 0 of its
-// draw is set (rc_half), each base substituted by one of the 3 others with prob err_ppm/1e6.
-__global__ void synth_reads_kernel(const uint8_t* __restrict__ genome, int64_t glen, int64_t nreads, int read_len,
-                                   uint64_t seed, uint32_t err_ppm, int rc_half, uint8_t* out, int64_t* off) {
-    const int64_t total = nreads * read_len;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t r = i / read_len;
-        int j = (int)(i - r * read_len);
-        uint64_t d = splitmix64(seed ^ splitmix64((uint64_t)r));
-        int64_t p = (int64_t)((d >> 1) % (uint64_t)(glen - read_len + 1));
-        const bool rc = rc_half && (d & 1);
-        // errors are drawn in GENOME orientation, so the rc_half=0 and rc_half=1 versions of a batch
-        // are exact reverse complements of each other read by read
-        const int gj = rc ? read_len - 1 - j : j;
-        uint8_t b = genome[p + gj];
-        const uint64_t e = splitmix64(seed * 31 + 7 + (uint64_t)(r * read_len + gj));
-        if ((uint32_t)(e % 1000000ULL) < err_ppm) {
-            int cur = b == 'A' ? 0 : b == 'C' ? 1 : b == 'G' ? 2 : 3;
-            b = "ACGT"[(cur + 1 + (int)((e >> 40) % 3)) & 3];
-        }
-        if (rc) b = sgc::comp_base(b);
-        out[i] = b;
-        if (j == 0) off[r] = r * (int64_t)read_len;
-        if (i == total - 1) off[nreads] = total;
-    }
-}
-
-// unitig j = genome[cuts[j] .. cuts[j+1] + k - 1), written at out_off[j] = cuts[j] + j*(k-1)
-__global__ void synth_unitigs_kernel(const uint8_t* __restrict__ genome, const int64_t* __restrict__ cuts, int64_t n,
-                                     int k, uint8_t* out, int64_t* out_off) {
-    const int64_t total = cuts[n] - cuts[0] + n * (int64_t)(k - 1);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        // largest j with cuts[j]-cuts[0] + j*(k-1) <= i
-        int64_t lo = 0, hi = n - 1;
-        while (lo < hi) {
-            int64_t mid = (lo + hi + 1) >> 1;
-            if (cuts[mid] - cuts[0] + mid * (int64_t)(k - 1) <= i) lo = mid; else hi = mid - 1;
-        }
-        int64_t o = cuts[lo] - cuts[0] + lo * (int64_t)(k - 1);
-        out[i] = genome[cuts[lo] + (i - o)];
-        if (i == o) out_off[lo] = o;
-        if (i == total - 1) out_off[n] = total;
-    }
-}
-
 }  // namespace
+
+#include "sgc_layout.cuh"
+#include "sgc_table.cuh"
+#include "sgc_tile.cuh"
+#include "sgc_kernels.cuh"
+
+using namespace sgc::dev;
+
 
 // ====================================================================================
 // host side

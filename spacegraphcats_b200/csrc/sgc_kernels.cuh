@@ -1,0 +1,322 @@
+// sgc_kernels.cuh -- plan kernels, stand-alone table kernels, label tail, per-dominator sums, K7 helpers and the synthetic workload generators.
+// Part of libsgc_b200.so (device code; included by sgc_b200.cu only).
+#pragma once
+#include "sgc_kmer.cuh"
+#include "sgc_table.cuh"
+
+namespace sgc {
+namespace dev {
+
+// ----------------------------------------------------------------------------------
+// plan kernels: per-sequence k-mer / segment counts and the segment map
+// ----------------------------------------------------------------------------------
+__global__ void plan_count_kernel(const int64_t* __restrict__ off, int64_t nseq, int k, int64_t seq_bytes,
+                                  int64_t* __restrict__ nk_out, int64_t* __restrict__ nseg_out, Scalars* scal) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > nseq) return;
+    int64_t nk = 0;
+    if (s < nseq) {
+        const int64_t o0 = off[s], o1 = off[s + 1];
+        if (o0 < 0 || o1 < o0 || o1 > seq_bytes) {
+            atomicOr(&scal->bad_offsets, 1);  // never touch bytes outside the caller's buffer
+        } else {
+            nk = o1 - o0 - k + 1;
+            if (nk < 0) nk = 0;
+        }
+    }
+    nk_out[s] = nk;
+    nseg_out[s] = (nk + SEG_K - 1) / SEG_K;
+}
+
+__global__ void plan_expand_kernel(const int64_t* __restrict__ seg_first, int64_t nseq,
+                                   int64_t* __restrict__ seg_map) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseq) return;
+    int64_t a = seg_first[s], b = seg_first[s + 1];
+    for (int64_t j = a; j < b; j++) seg_map[j] = s | ((j - a) << 40);
+}
+
+
+// ----------------------------------------------------------------------------------
+// stand-alone table kernels
+// ----------------------------------------------------------------------------------
+__global__ void table_clear_kernel(Bucket* tbl, uint32_t nb) {
+    const Entry empty{0ULL, VAL_EMPTY, 0u};
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (uint64_t)nb * 2;
+         i += (uint64_t)gridDim.x * blockDim.x)
+        reinterpret_cast<Entry*>(tbl)[i] = empty;
+}
+
+__global__ void insert_pairs_kernel(Bucket* tbl, uint32_t nb, uint32_t nlines, int hs,
+                                    const uint64_t* __restrict__ hash, const uint32_t* __restrict__ id, int64_t n,
+                                    Scalars* scal) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t v = id[i];
+        if (v > SGC_MAX_ID) atomicOr(&scal->err, 2);
+        else table_insert(tbl, nb, nlines, hs, hash[i], v, AUX_NONE, scal);
+    }
+}
+
+__global__ void lookup_kernel(const Bucket* tbl, uint32_t nb, uint32_t nlines, int hs,
+                              const uint64_t* __restrict__ hash, int64_t n, uint32_t* __restrict__ out) {
+    // two probes in flight per thread
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
+        const int64_t j = i + stride;
+        const uint64_t h0 = hash[i], h1 = j < n ? hash[j] : 0;
+        const uint32_t b0 = home_bucket(h0, nb, hs), b1 = j < n ? home_bucket(h1, nb, hs) : 0u;
+        Entry a0, a1, c0, c1;
+        load_bucket_nc(tbl + b0, a0, a1);
+        load_bucket_nc(tbl + b1, c0, c1);
+        uint32_t v;
+        uint32_t aux;
+        if (!bucket_match(a0, a1, h0, v)) v = bucket_overflowed(a0) ? lookup_slow(tbl, nlines, b0, h0, aux) : SGC_MISS;
+        out[i] = v;
+        if (j < n) {
+            if (!bucket_match(c0, c1, h1, v)) v = bucket_overflowed(c0) ? lookup_slow(tbl, nlines, b1, h1, aux) : SGC_MISS;
+            out[j] = v;
+        }
+    }
+}
+
+// get_unique_values: count_by_id[id]++ per present hash.  With distinct != 0 the input is
+// sorted and a hash equal to its predecessor is skipped.
+__global__ void count_kernel(const Bucket* tbl, uint32_t nb, uint32_t nlines, int hs,
+                             const uint64_t* __restrict__ hash, int64_t n, int distinct, uint32_t* count_by_id,
+                             Scalars* scal) {
+    unsigned long long miss = 0, nd = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t h = hash[i];
+        if (distinct && i > 0 && hash[i - 1] == h) continue;
+        nd++;
+        uint32_t v = table_lookup(tbl, nb, nlines, hs, h);
+        if (v == SGC_MISS) miss++;
+        else atomicAdd(&count_by_id[v], 1u);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        miss += __shfl_xor_sync(0xffffffffu, miss, d);
+        nd += __shfl_xor_sync(0xffffffffu, nd, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (miss) atomicAdd(&scal->n_miss, miss);
+        if (nd) atomicAdd(&scal->n_distinct, nd);
+    }
+}
+
+__global__ void table_stats_kernel(const Bucket* tbl, uint32_t nb, Scalars* scal) {
+    unsigned long long live = 0, multi = 0;
+    unsigned mx = 0;
+    const Entry* e = reinterpret_cast<const Entry*>(tbl);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (uint64_t)nb * 2;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t v = e[i].val;
+        if (v == VAL_MULTI) multi++;
+        else if (v != VAL_EMPTY) {
+            live++;
+            mx = v > mx ? v : mx;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        live += __shfl_xor_sync(0xffffffffu, live, d);
+        multi += __shfl_xor_sync(0xffffffffu, multi, d);
+        unsigned o = __shfl_xor_sync(0xffffffffu, mx, d);
+        mx = o > mx ? o : mx;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (live) atomicAdd(&scal->n_live, live);
+        if (multi) atomicAdd(&scal->n_multi, multi);
+        if (mx) atomicMax(&scal->max_id, mx);
+    }
+}
+
+// side[g].id := what a table lookup of side[g].hash returns (MISS for dropped hashes), so that a
+// hash match against a side record is by construction the table's own answer
+__global__ void side_fixup_kernel(const Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, uint4* side, uint64_t n) {
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 r = side[g];
+        const uint64_t h = ((uint64_t)r.y << 32) | r.x;
+        r.z = table_lookup(tbl, nb, nlines, hs, h);
+        r.w = 0;
+        side[g] = r;
+    }
+}
+
+__global__ void table_export_kernel(const Bucket* tbl, uint32_t nb, uint64_t* hash_out, uint32_t* id_out,
+                                    unsigned long long cap, Scalars* scal) {
+    const Entry* e = reinterpret_cast<const Entry*>(tbl);
+    const uint64_t total = (uint64_t)nb * 2;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (total + stride - 1) / stride;
+    const int lane = threadIdx.x & 31;
+    for (uint64_t r = 0; r < rounds; r++) {
+        uint64_t i = r * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        Entry x{0ULL, VAL_EMPTY, 0u};
+        if (i < total) x = e[i];
+        bool live = x.val < VAL_MULTI;
+        unsigned m = __ballot_sync(0xffffffffu, live);
+        if (m) {
+            unsigned long long base = 0;
+            int leader = __ffs(m) - 1;
+            if (lane == leader) base = atomicAdd(&scal->n_export, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (live) {
+                unsigned long long p = base + __popc(m & ((1u << lane) - 1u));
+                if (p < cap) {
+                    hash_out[p] = x.key;
+                    id_out[p] = x.val;
+                }
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// label tail: unique (seq, id) keys -> CSR
+// ----------------------------------------------------------------------------------
+__global__ void csr_count_kernel(const unsigned long long* __restrict__ uniq, const long long* __restrict__ n_p,
+                                 unsigned long long* ids_off, uint32_t* ids_out, int64_t ids_cap) {
+    const int64_t n = *n_p;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long key = uniq[j];
+        atomicAdd(&ids_off[(key >> 32) + 1], 1ULL);
+        if (j < ids_cap) ids_out[j] = (uint32_t)key;
+    }
+}
+
+// per-k-mer ids (already looked up, possibly on other ranks) -> candidate (seq, id) keys
+__global__ void ids_to_pairs_kernel(const uint32_t* __restrict__ kmer_ids, const int64_t* __restrict__ kmer_off,
+                                    int64_t nseq, unsigned long long* pairs, unsigned long long cap, Scalars* scal) {
+    unsigned long long hits = 0;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nseq; s += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t prev = SGC_MISS;
+        for (int64_t j = kmer_off[s]; j < kmer_off[s + 1]; j++) {
+            uint32_t v = kmer_ids[j];
+            if (v != SGC_MISS) {
+                hits++;
+                if (v != prev) {
+                    unsigned long long p = atomicAdd(&scal->pair_count, 1ULL);
+                    if (p < cap) pairs[p] = ((unsigned long long)s << 32) | v;
+                }
+            }
+            prev = v;
+        }
+    }
+    if (hits) atomicAdd(&scal->n_hits, hits);
+}
+
+// ----------------------------------------------------------------------------------
+// K6: per-dominator sums, one launch per catlas level
+// ----------------------------------------------------------------------------------
+__global__ void dom_level_kernel(const uint32_t* __restrict__ src, const int64_t* __restrict__ member_off,
+                                 const uint32_t* __restrict__ member, const uint32_t* __restrict__ nodes,
+                                 int64_t n, uint32_t* node_count) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t v = nodes[j];
+    uint32_t s = 0;
+    for (int64_t m = member_off[v]; m < member_off[v + 1]; m++) s += src[member[m]];
+    node_count[v] = s;
+}
+
+// ----------------------------------------------------------------------------------
+// K7 helpers
+// ----------------------------------------------------------------------------------
+__global__ void iota_kernel(int64_t* p, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = i;
+}
+
+// sorted by the top `bits` bits: bucket_off[r] = first index whose owner >= r
+__global__ void bucket_bounds_kernel(const uint64_t* __restrict__ sorted, int64_t n, int bits, int n_ranks,
+                                     int64_t* bucket_off) {
+    int r = threadIdx.x;
+    if (r > n_ranks) return;
+    if (r == n_ranks) { bucket_off[r] = n; return; }
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        unsigned owner = bits ? (unsigned)(sorted[mid] >> (64 - bits)) : 0u;
+        if (owner < (unsigned)r) lo = mid + 1; else hi = mid;
+    }
+    bucket_off[r] = lo;
+}
+
+__global__ void gather_u32_kernel(const uint32_t* __restrict__ in, const int64_t* __restrict__ perm, int64_t n,
+                                  uint32_t* out, int scatter) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (scatter) out[perm[i]] = in[i];
+        else out[i] = in[perm[i]];
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// synthetic workload generators (bench / tests only)
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+__global__ void synth_genome_kernel(uint8_t* out, int64_t n, uint64_t seed) {
+    // 32 bases per 64-bit draw
+    const int64_t nw = (n + 31) / 32;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t r = splitmix64(seed * 0xD1342543DE82EF95ULL + (uint64_t)w);
+        for (int j = 0; j < 32; j++) {
+            int64_t i = w * 32 + j;
+            if (i < n) out[i] = "ACGT"[(r >> (2 * j)) & 3];
+        }
+    }
+}
+
+// read r = genome[p .. p+len) at a uniform position, reverse-complemented when bit 0 of its
+// draw is set (rc_half), each base substituted by one of the 3 others with prob err_ppm/1e6.
+__global__ void synth_reads_kernel(const uint8_t* __restrict__ genome, int64_t glen, int64_t nreads, int read_len,
+                                   uint64_t seed, uint32_t err_ppm, int rc_half, uint8_t* out, int64_t* off) {
+    const int64_t total = nreads * read_len;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / read_len;
+        int j = (int)(i - r * read_len);
+        uint64_t d = splitmix64(seed ^ splitmix64((uint64_t)r));
+        int64_t p = (int64_t)((d >> 1) % (uint64_t)(glen - read_len + 1));
+        const bool rc = rc_half && (d & 1);
+        // errors are drawn in GENOME orientation, so the rc_half=0 and rc_half=1 versions of a batch
+        // are exact reverse complements of each other read by read
+        const int gj = rc ? read_len - 1 - j : j;
+        uint8_t b = genome[p + gj];
+        const uint64_t e = splitmix64(seed * 31 + 7 + (uint64_t)(r * read_len + gj));
+        if ((uint32_t)(e % 1000000ULL) < err_ppm) {
+            int cur = b == 'A' ? 0 : b == 'C' ? 1 : b == 'G' ? 2 : 3;
+            b = "ACGT"[(cur + 1 + (int)((e >> 40) % 3)) & 3];
+        }
+        if (rc) b = sgc::comp_base(b);
+        out[i] = b;
+        if (j == 0) off[r] = r * (int64_t)read_len;
+        if (i == total - 1) off[nreads] = total;
+    }
+}
+
+// unitig j = genome[cuts[j] .. cuts[j+1] + k - 1), written at out_off[j] = cuts[j] + j*(k-1)
+__global__ void synth_unitigs_kernel(const uint8_t* __restrict__ genome, const int64_t* __restrict__ cuts, int64_t n,
+                                     int k, uint8_t* out, int64_t* out_off) {
+    const int64_t total = cuts[n] - cuts[0] + n * (int64_t)(k - 1);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        // largest j with cuts[j]-cuts[0] + j*(k-1) <= i
+        int64_t lo = 0, hi = n - 1;
+        while (lo < hi) {
+            int64_t mid = (lo + hi + 1) >> 1;
+            if (cuts[mid] - cuts[0] + mid * (int64_t)(k - 1) <= i) lo = mid; else hi = mid - 1;
+        }
+        int64_t o = cuts[lo] - cuts[0] + lo * (int64_t)(k - 1);
+        out[i] = genome[cuts[lo] + (i - o)];
+        if (i == o) out_off[lo] = o;
+        if (i == total - 1) out_off[n] = total;
+    }
+}
+
+
+}  // namespace dev
+}  // namespace sgc

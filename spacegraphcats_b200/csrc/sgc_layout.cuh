@@ -1,0 +1,120 @@
+// sgc_layout.cuh -- tile geometry constants, the table slot layout, device scalars and the tile kernel argument block.
+// Part of libsgc_b200.so (device code; included by sgc_b200.cu only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/sgc_b200.h"
+
+namespace sgc {
+namespace dev {
+
+// ----------------------------------------------------------------------------------
+// tile geometry
+// ----------------------------------------------------------------------------------
+#ifndef SGC_PROBE_MIN_CTAS
+#define SGC_PROBE_MIN_CTAS 2
+#endif
+constexpr int NT = 256;         // threads per CTA
+constexpr int WPB = NT / 32;    // warps per CTA; every warp runs its own rounds (no block barriers)
+constexpr int SPW = 8;          // segments staged per warp round (4 lanes stage one segment)
+constexpr int SEG_K = 256;      // k-mers per segment
+constexpr int PAIR_BUF = 128;   // label keys staged per warp before one global reservation
+constexpr int QCAP = 256;       // MODE_LABEL_SIDE: k-mers queued per warp for a dense table probe
+constexpr unsigned long long SEQ_MASK = (1ULL << 40) - 1ULL;
+
+constexpr uint32_t VAL_EMPTY = 0xFFFFFFFFu;
+constexpr uint32_t VAL_MULTI = 0xFFFFFFFEu;
+
+enum Mode { MODE_HASH = 0, MODE_INSERT = 1, MODE_LOOKUP = 2, MODE_LABEL = 3, MODE_PARTITION = 4, MODE_GATHER = 5, MODE_MINHASH = 6, MODE_LABEL_SIDE = 7 };
+
+template <int K>
+struct Geo {
+    static constexpr int KMAX = K ? K : SGC_MAX_K;
+    static constexpr int SEGB = SEG_K + KMAX - 1;                 // bases in a full segment
+    static constexpr int STRIDE = ((SEGB + 32 + 15) / 16) * 16;   // bytes per staged area
+    static constexpr int WPS = STRIDE / 4;
+};
+
+// The table: 32-byte buckets of two 16-byte slots; four buckets share a 128-byte line (the unit
+// HBM actually moves per random access on B200: measured).  A key lives at probe
+// step s >= 0 from its home bucket hb: steps 1..3 are the other buckets of the home line, steps
+// 4.. walk the following lines.  It sits in the FIRST bucket of that sequence that had a free slot
+// when it arrived and slots are never freed, so a walk stops at the first bucket that is not
+// full -- and it only starts if the home bucket's overflow bit says that some key homed there
+// lives elsewhere (a miss in an un-flagged home bucket costs ONE sector even when it is full).
+// aux[30:0] = index of the k-mer in the table's unitig-ordered side array (AUX_NONE if none);
+// aux[31] of slot 0 = the bucket's overflow bit.
+struct __align__(16) Entry {
+    unsigned long long key;
+    unsigned int val;  // VAL_EMPTY = free slot, VAL_MULTI = dropped hash, else unitig id
+    unsigned int aux;  // side-array position (31 bits) | overflow bit (slot 0)
+};
+constexpr uint32_t AUX_NONE = 0x7FFFFFFFu;
+constexpr uint32_t AUX_MASK = 0x7FFFFFFFu;
+constexpr uint32_t OVF_BIT = 0x80000000u;
+struct __align__(32) Bucket {
+    Entry e[2];
+};
+
+struct Scalars {
+    unsigned long long pair_count;
+    unsigned long long n_hits;
+    unsigned long long n_miss;
+    unsigned long long n_distinct;
+    unsigned long long n_live;
+    unsigned long long n_multi;
+    unsigned long long n_export;
+    long long n_unique;
+    unsigned int round_ctr;
+    unsigned int max_id;
+    int err;  // bit 0: table full, bit 1: id out of range
+    int bad_offsets;  // set by the plan when an offset pair is negative, decreasing or past seq_bytes
+};
+
+struct TileArgs {
+    const uint8_t* seq;
+    const int64_t* off;
+    const int64_t* seg_map;
+    const int64_t* nsegs_p;
+    const int64_t* kmer_off;
+    int32_t* status;
+    Scalars* scal;
+    int k;
+    // MODE_HASH / MODE_MINHASH
+    uint64_t* hash_out;
+    unsigned long long* seq_min;    // MODE_MINHASH: per-sequence minimum (atomicMin), nullable
+    unsigned long long seed;        // MODE_MINHASH: Murmur3 seed (sourmash: 42)
+    // table (MODE_INSERT / MODE_LOOKUP / MODE_LABEL)
+    Bucket* tbl;
+    uint32_t nbuckets;
+    uint32_t nlines;
+    int home_shift;
+    const uint32_t* seq_ids;
+    uint32_t id_base;
+    // side array (unitig-ordered {hash, id} records): written by MODE_INSERT, read by MODE_LABEL_SIDE
+    uint4* side;
+    unsigned long long side_base;   // MODE_INSERT: first record of this batch
+    unsigned long long side_n;      // MODE_LABEL_SIDE: number of records
+    // MODE_LOOKUP
+    uint32_t* kmer_ids;
+    uint32_t* count_by_id;
+    // MODE_LABEL
+    unsigned long long* pairs;
+    unsigned long long pairs_cap;
+    unsigned long long zero;  // always 0 (scheduling dependency, see the pipelined probe loop)
+    // MODE_PARTITION (hash -> owner rank's send region) / MODE_GATHER (replies -> labels)
+    uint64_t* send;                 // n_ranks regions of send_cap hashes
+    uint64_t* peer_send[32];        // where owner r's requests go: send + r*send_cap locally, or the
+                                    // peer-mapped inbox of GPU r (P2P stores over NVLink)
+    unsigned long long send_region_off;  // my region inside a peer inbox (my_rank * send_cap), else 0
+    unsigned long long send_cap;
+    unsigned long long* cursor;     // n_ranks fill counters
+    uint32_t* ridx;                 // per k-mer: owner << (32 - owner_bits) | position in the owner's region
+    const uint32_t* replies;        // same layout as send, 4 bytes per request
+    int owner_bits;
+    int n_ranks;
+};
+
+
+}  // namespace dev
+}  // namespace sgc

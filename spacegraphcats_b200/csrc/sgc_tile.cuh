@@ -1,0 +1,710 @@
+// sgc_tile.cuh -- segment staging and the warp-autonomous tile kernel (hash / insert / lookup / label / partition / gather / minhash modes).
+// Part of libsgc_b200.so (device code; included by sgc_b200.cu only).
+#pragma once
+#include "sgc_kmer.cuh"
+#include "sgc_table.cuh"
+
+namespace sgc {
+namespace dev {
+
+// ----------------------------------------------------------------------------------
+// staging helpers
+// ----------------------------------------------------------------------------------
+// bytes F[f .. f+4) of a segment whose Ls bases start at global byte address `base`; bytes outside
+// [0, Ls) read as 0 and no aligned word that lies wholly outside the segment is touched.
+__device__ __forceinline__ uint32_t load_window4(uintptr_t base, int f, int Ls, uint32_t& mask) {
+    const int lo_clip = f < 0 ? -f : 0;
+    const int hi_clip = f + 4 > Ls ? f + 4 - Ls : 0;
+    if (lo_clip >= 4 || hi_clip >= 4) { mask = 0; return 0; }
+    mask = (0xFFFFFFFFu << (8 * lo_clip)) & (0xFFFFFFFFu >> (8 * hi_clip));
+    const uintptr_t addr = base + (intptr_t)f;
+    const int s = (int)(addr & 3);
+    const uintptr_t a0 = addr - s;
+    const uintptr_t first = base, last = base + (uintptr_t)Ls;  // valid byte range [first, last)
+    uint32_t lo = 0, hi = 0;
+    if (a0 + 4 > first && a0 < last) lo = __ldg((const uint32_t*)a0);
+    if (s && a0 + 8 > first && a0 + 4 < last) hi = __ldg((const uint32_t*)(a0 + 4));
+    return sgc::funnel_bytes(lo, hi, s) & mask;
+}
+
+// reverse complement of 4 packed bases (byte-reversed, A<->T, C<->G); ok = every byte selected by
+// mask is one of A, C, G, T.  Bytes that are not pass through unchanged (oracle rule).
+__device__ __forceinline__ uint32_t revcomp_word(uint32_t u, uint32_t mask, bool& ok) {
+    // 2-bit code per base from ASCII bits 1..2: A=0 C=1 T=2 G=3
+    const uint32_t code = (u >> 1) & 0x03030303u;
+    const uint32_t t = code | (code >> 4);
+    const uint32_t sel = (t & 0xFFu) | ((t >> 8) & 0xFF00u);
+    const uint32_t expect = __byte_perm(0x47544341u, 0u, sel);   // "ACTG"[code]
+    uint32_t comp = __byte_perm(0x43414754u, 0u, sel);           // "TGAC"[code]
+    ok = ((expect ^ u) & mask) == 0;
+    if (!ok) {
+        comp = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) comp |= (uint32_t)sgc::comp_base((uint8_t)(u >> (8 * b))) << (8 * b);
+    }
+    return __byte_perm(comp & mask, 0u, 0x0123u);
+}
+
+// ----------------------------------------------------------------------------------
+// the tile kernel.  Every WARP runs its own rounds: fetch SPW segments, stage their forward and
+// reverse-complement bytes in its slice of shared memory (4 lanes per segment), then each lane
+// hashes groups of 4 consecutive k-mers and feeds them to the mode's sink.  No block barriers:
+// warps drift apart, so one warp's exposed latencies (round fetch, staging loads, table probes)
+// are covered by the other warps of the SM.
+// ----------------------------------------------------------------------------------
+template <int K>
+struct WarpTile {
+    uint32_t F[SPW * Geo<K>::WPS];
+    uint32_t R[SPW * Geo<K>::WPS];
+    unsigned long long pairs[PAIR_BUF];
+    long long start[SPW];
+    long long seq[SPW];
+    long long kout[SPW];
+    int nk[SPW];
+    int gpre[SPW + 1];
+    int pad[3];
+    unsigned wcnt[32];              // MODE_PARTITION: per-owner counts of one warp iteration
+    unsigned wpre[32];              // ... their exclusive prefix (slot of the owner's run in the staging area)
+    uint64_t* dst[PAIR_BUF];        // ... destination address of every staged hash
+    unsigned long long wbase[32];   // ... and the reserved base positions in the owners' regions
+};
+
+template <int K, int MODE>
+__global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP || MODE == MODE_LABEL_SIDE) ? SGC_PROBE_MIN_CTAS : 1) tile_kernel(const TileArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int WPS = Geo<K>::WPS;
+    const int lane = threadIdx.x & 31;
+    WarpTile<K>& wt = reinterpret_cast<WarpTile<K>*>(smem_raw)[threadIdx.x >> 5];
+    const int k = K ? K : a.k;
+    const int64_t nsegs = *a.nsegs_p;
+    const int64_t nrounds = (nsegs + SPW - 1) / SPW;
+    unsigned long long my_hits = 0, my_miss = 0;
+    unsigned pair_fill = 0;  // warp-uniform: keys waiting in wt.pairs
+
+    auto flush_pairs = [&]() {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&a.scal->pair_count, (unsigned long long)pair_fill);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (unsigned j = lane; j < pair_fill; j += 32)
+            if (base + j < a.pairs_cap) a.pairs[base + j] = wt.pairs[j];
+        __syncwarp();
+        pair_fill = 0;
+    };
+
+    // K4 candidate rule shared by MODE_LABEL and MODE_GATHER: a hit is a candidate (sequence, id) key
+    // unless the previous k-mer of the same segment has the same id (known through a warp shuffle;
+    // the first k-mer of a lane-0 group is conservatively a candidate).  All 32 lanes must call this.
+    auto emit_candidates = [&](const uint32_t (&ids)[4], bool active, int sg, int i, int nv) {
+        const uint32_t prev_lane = __shfl_up_sync(0xffffffffu, ids[3], 1);
+        unsigned long long keys[4] = {0, 0, 0, 0};
+        unsigned nc = 0;
+        if (active) {
+            const unsigned long long sq = (unsigned long long)wt.seq[sg] << 32;
+            uint32_t prev = (i > 0 && lane > 0) ? prev_lane : SGC_MISS;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                if (t < nv && ids[t] != SGC_MISS && ids[t] != prev) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++)  // constant indices keep keys[] in registers
+                        if (u == (int)nc) keys[u] = sq | ids[t];
+                    nc++;
+                }
+                prev = ids[t];
+            }
+        }
+        unsigned incl = nc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {
+            if (pair_fill + total > PAIR_BUF) flush_pairs();
+            unsigned pos = pair_fill + incl - nc;
+#pragma unroll
+            for (unsigned j = 0; j < 4; j++)
+                if (j < nc) wt.pairs[pos++] = keys[j];
+            pair_fill += total;
+        }
+    };
+
+    // MODE_LABEL_SIDE: per-warp queue of k-mers that still need their own table probe
+    unsigned long long* qh = nullptr;
+    uint32_t* qs = nullptr;
+    unsigned q_fill = 0;  // warp-uniform
+    if constexpr (MODE == MODE_LABEL_SIDE) {
+        unsigned char* qbase = smem_raw + sizeof(WarpTile<K>) * WPB;
+        qh = reinterpret_cast<unsigned long long*>(qbase) + (threadIdx.x >> 5) * QCAP;
+        qs = reinterpret_cast<uint32_t*>(qbase + (size_t)WPB * QCAP * 8) + (threadIdx.x >> 5) * QCAP;
+    }
+    // probe the queued k-mers densely: one item per lane, probe of item j+32 in flight while item j is
+    // resolved; hits become (sequence, id) keys right away (no neighbour to compare with here, except
+    // the previous lane's item)
+    auto drain_queue = [&]() {
+        if constexpr (MODE == MODE_LABEL_SIDE) {
+            bool d_act = false;
+            uint64_t d_h = 0;
+            uint32_t d_sq = 0, d_b = 0;
+            Entry d_e0, d_e1;
+            auto settle = [&]() {
+                uint32_t id = SGC_MISS;
+                if (d_act) {
+                    uint32_t v, aux;
+                    if (bucket_match(d_e0, d_e1, d_h, v)) id = v;
+                    else if (bucket_overflowed(d_e0)) id = lookup_slow(a.tbl, a.nlines, d_b, d_h, aux);
+                    if (id != SGC_MISS) my_hits++; else my_miss++;
+                }
+                const unsigned long long key = ((unsigned long long)d_sq << 32) | id;
+                const unsigned long long prevk = __shfl_up_sync(0xffffffffu, key, 1);
+                const bool has = d_act && id != SGC_MISS && !(lane > 0 && prevk == key);
+                const unsigned m = __ballot_sync(0xffffffffu, has);
+                if (m) {
+                    const unsigned total = __popc(m);
+                    if (pair_fill + total > PAIR_BUF) flush_pairs();
+                    if (has) wt.pairs[pair_fill + __popc(m & ((1u << lane) - 1u))] = key;
+                    pair_fill += total;
+                }
+            };
+            for (unsigned j0 = 0; j0 < q_fill; j0 += 32) {
+                const unsigned j = j0 + lane;
+                const bool act = j < q_fill;
+                const uint64_t h = act ? qh[j] : 0ULL;
+                const uint32_t sq = act ? qs[j] : 0u;
+                if (j0 > 0) settle();
+                d_act = act; d_h = h; d_sq = sq;
+                d_b = act ? home_bucket(h, a.nbuckets, a.home_shift) : 0u;
+                load_bucket_nc(a.tbl + d_b, d_e0, d_e1);
+            }
+            if (q_fill) settle();
+            __syncwarp();
+            q_fill = 0;
+        }
+    };
+
+    // dynamic round scheduling; the NEXT round index is always requested one round ahead
+    unsigned next_round = 0;
+    if (lane == 0) next_round = atomicAdd(&a.scal->round_ctr, 1u);
+
+    for (;;) {
+        const unsigned round = __shfl_sync(0xffffffffu, next_round, 0);
+        if ((int64_t)round >= nrounds) break;
+        if (lane == 0) next_round = atomicAdd(&a.scal->round_ctr, 1u);
+        const int64_t seg0 = (int64_t)round * SPW;
+
+        // ---- descriptors (lanes 0..SPW-1) ----
+        {
+            int nk = 0;
+            long long start = 0, sq = 0, kout = 0;
+            const int64_t g = seg0 + lane;
+            if (lane < SPW && g < nsegs) {
+                const unsigned long long e = (unsigned long long)a.seg_map[g];
+                sq = (long long)(e & SEQ_MASK);
+                const long long sn = (long long)(e >> 40);
+                const long long o0 = a.off[sq], o1 = a.off[sq + 1];
+                const long long q0 = sn * SEG_K;
+                const long long rem = o1 - o0 - k + 1 - q0;
+                nk = (int)(rem < SEG_K ? rem : SEG_K);
+                start = o0 + q0;
+                if (a.kmer_off) kout = a.kmer_off[sq] + q0;
+            }
+            int incl = (nk + 3) >> 2;
+#pragma unroll
+            for (int d = 1; d < SPW; d <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            if (lane < SPW) {
+                wt.start[lane] = start;
+                wt.seq[lane] = sq;
+                wt.kout[lane] = kout;
+                wt.nk[lane] = nk;
+                wt.gpre[lane + 1] = incl;
+            }
+            if (lane == 0) wt.gpre[0] = 0;
+        }
+        __syncwarp();
+
+        // ---- stage forward + reverse-complement words straight from global memory ----
+        if constexpr (MODE != MODE_GATHER) {
+            const int sg = lane >> 2, sub = lane & 3;
+            const int nk = wt.nk[sg];
+            if (nk) {
+                const int Ls = nk + k - 1;
+                const uintptr_t base = (uintptr_t)a.seq + (uintptr_t)wt.start[sg];
+                uint32_t* Fs = wt.F + sg * WPS;
+                uint32_t* Rs = wt.R + sg * WPS;
+                const int p = sgc::rc_pad(nk);
+                bool all_ok = true;
+                for (int w = sub; 4 * w < Ls; w += 4) {
+                    uint32_t mask;
+                    Fs[w] = load_window4(base, 4 * w, Ls, mask);
+                }
+                // R word m holds R[4m-4-p .. +4) = revcomp of F[Ls-4m+p .. +4)
+                const int nrw = (Ls + 4 + p + 3) >> 2;
+                for (int m = sub; m < nrw; m += 4) {
+                    uint32_t mask;
+                    const uint32_t u = load_window4(base, Ls - 4 * m + p, Ls, mask);
+                    bool ok;
+                    Rs[m] = revcomp_word(u, mask, ok);
+                    all_ok &= ok;
+                }
+                if (!all_ok && a.status) atomicOr(&a.status[wt.seq[sg]], 1);
+            }
+        }
+        __syncwarp();
+
+        // ---- hash + sink ----
+        const int G = wt.gpre[SPW];
+
+        // locate group g (segment sg, first k-mer i, nv valid k-mers) and hash its 4 k-mers
+        auto locate_and_hash = [&](int g, int& sg, int& i, int& nv, uint64_t (&h)[4]) {
+            int lo = 0;  // largest sg with gpre[sg] <= g
+#pragma unroll
+            for (int step = SPW / 2; step > 0; step >>= 1)
+                if (wt.gpre[lo + step] <= g) lo += step;
+            sg = lo;
+            i = (g - wt.gpre[sg]) << 2;
+            const int nk = wt.nk[sg];
+            nv = nk - i < 4 ? nk - i : 4;
+            const uint32_t* Fs = wt.F + sg * WPS;
+            const uint32_t* Rs = wt.R + sg * WPS;
+            if constexpr (K != 0) {
+                constexpr int NWIN = sgc::KW<K ? K : 1>::NWIN;
+                uint32_t fw[NWIN], rw[NWIN];
+                const uint32_t* fp = Fs + (i >> 2);
+                const uint32_t* rp = Rs + sgc::rc_group_word(nk, i);
+#pragma unroll
+                for (int j = 0; j < NWIN; j++) {
+                    fw[j] = fp[j];
+                    rw[j] = rp[j];
+                }
+#pragma unroll
+                for (int t = 0; t < 4; t++) h[t] = sgc::hash_group_kmer<K ? K : 1>(fw, rw, t);
+            } else {
+                for (int t = 0; t < nv; t++) {
+                    int q = i + t;
+                    h[t] = sgc::murmur3_h1_stream(Fs, q, k) ^
+                           sgc::murmur3_h1_stream(Rs, sgc::rc_byte_of(nk, nk - 1 - q), k);
+                }
+            }
+        };
+
+        if constexpr (MODE == MODE_MINHASH) {
+            // sourmash-style hash: Murmur3(min(kmer, revcomp), seed); all hashes and/or the per-sequence
+            // minimum (MinHash n=1 of cdbg/sort_bcalm_unitigs.py:56-128)
+            for (int g0 = 0; g0 < G; g0 += 32) {
+                const int g = g0 + lane;
+                if (g >= G) continue;
+                int lo = 0;
+#pragma unroll
+                for (int step = SPW / 2; step > 0; step >>= 1)
+                    if (wt.gpre[lo + step] <= g) lo += step;
+                const int sg = lo, i = (g - wt.gpre[sg]) << 2;
+                const int nk = wt.nk[sg];
+                const int nv = nk - i < 4 ? nk - i : 4;
+                const uint32_t* Fs = wt.F + sg * WPS;
+                const uint32_t* Rs = wt.R + sg * WPS;
+                uint64_t h[4] = {~0ULL, ~0ULL, ~0ULL, ~0ULL};
+                if constexpr (K != 0) {
+                    constexpr int NWIN = sgc::KW<K ? K : 1>::NWIN;
+                    uint32_t fw[NWIN], rw[NWIN];
+                    const uint32_t* fp = Fs + (i >> 2);
+                    const uint32_t* rp = Rs + sgc::rc_group_word(nk, i);
+#pragma unroll
+                    for (int j = 0; j < NWIN; j++) {
+                        fw[j] = fp[j];
+                        rw[j] = rp[j];
+                    }
+#pragma unroll
+                    for (int t = 0; t < 4; t++)
+                        if (t < nv) h[t] = sgc::minhash_group_kmer<K ? K : 1>(fw, rw, t, a.seed);
+                } else {
+                    for (int t = 0; t < nv; t++) {
+                        const int q = i + t, rq = sgc::rc_byte_of(nk, nk - 1 - q);
+                        h[t] = sgc::stream_less(Rs, rq, Fs, q, k) ? sgc::murmur3_h1_stream(Rs, rq, k, a.seed)
+                                                                  : sgc::murmur3_h1_stream(Fs, q, k, a.seed);
+                    }
+                }
+                if (a.hash_out) {
+                    uint64_t* o = a.hash_out + wt.kout[sg] + i;
+#pragma unroll
+                    for (int t = 0; t < 4; t++)
+                        if (t < nv) o[t] = h[t];
+                }
+                if (a.seq_min) {
+                    uint64_t m = h[0];
+#pragma unroll
+                    for (int t = 1; t < 4; t++) m = h[t] < m ? h[t] : m;
+                    atomicMin(&a.seq_min[wt.seq[sg]], (unsigned long long)m);
+                }
+            }
+        } else if constexpr (MODE == MODE_HASH || MODE == MODE_INSERT) {
+            for (int g0 = 0; g0 < G; g0 += 32) {
+                const int g = g0 + lane;
+                if (g >= G) continue;
+                int sg, i, nv;
+                uint64_t h[4] = {0, 0, 0, 0};
+                locate_and_hash(g, sg, i, nv, h);
+                if constexpr (MODE == MODE_HASH) {
+                    uint64_t* o = a.hash_out + wt.kout[sg] + i;
+#pragma unroll
+                    for (int t = 0; t < 4; t++)
+                        if (t < nv) o[t] = h[t];
+                } else {
+                    long long sq = wt.seq[sg];
+                    uint32_t id = a.seq_ids ? a.seq_ids[sq] : a.id_base + (uint32_t)sq;
+                    if (id > SGC_MAX_ID) atomicOr(&a.scal->err, 2);
+                    else {
+                        const unsigned long long g0 = a.side_base + (unsigned long long)(wt.kout[sg] + i);
+                        for (int t = 0; t < nv; t++) {
+                            uint32_t aux = AUX_NONE;
+                            if (a.side) {  // unitig-ordered record; its id is fixed up after the build
+                                aux = (uint32_t)(g0 + t);
+                                a.side[g0 + t] = make_uint4((uint32_t)h[t], (uint32_t)(h[t] >> 32), id, 0u);
+                            }
+                            table_insert(a.tbl, a.nbuckets, a.nlines, a.home_shift, h[t], id, aux, a.scal);
+                        }
+                    }
+                }
+            }
+        } else if constexpr (MODE == MODE_PARTITION) {
+            // K7 request side: every hash goes to the send region of its owner rank (top owner_bits
+            // bits).  Positions are reserved per warp iteration (<=128 k-mers): lanes count owners in
+            // shared memory, one lane per owner reserves a run in that owner's region, so each owner
+            // receives runs of consecutive hashes.  ridx remembers where every k-mer's reply will be.
+            const int sh = 32 - a.owner_bits;
+            for (int g0 = 0; g0 < G; g0 += 32) {
+                const int g = g0 + lane;
+                const bool active = g < G;
+                int sg = 0, i = 0, nv = 0;
+                uint64_t h[4] = {0, 0, 0, 0};
+                if (active) locate_and_hash(g, sg, i, nv, h);
+                if (lane < a.n_ranks) wt.wcnt[lane] = 0;
+                __syncwarp();
+                uint32_t own[4], rank[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    own[t] = a.owner_bits ? (uint32_t)(h[t] >> (64 - a.owner_bits)) : 0u;
+                    rank[t] = (active && t < nv) ? atomicAdd(&wt.wcnt[own[t]], 1u) : 0u;
+                }
+                __syncwarp();
+                {   // one lane per owner: reserve the run in the owner's region, prefix for the staging slots
+                    const unsigned c = lane < a.n_ranks ? wt.wcnt[lane] : 0u;
+                    unsigned incl = c;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += v;
+                    }
+                    if (lane < a.n_ranks) {
+                        wt.wpre[lane] = incl - c;
+                        wt.wbase[lane] = c ? atomicAdd(&a.cursor[lane], (unsigned long long)c) : 0ULL;
+                    }
+                }
+                __syncwarp();
+                // Stage the <=128 hashes of this iteration grouped by owner (reusing the idle label
+                // staging area: 128 hashes + 128 destination addresses), then copy them out with
+                // consecutive lanes on consecutive addresses: each owner gets its run as full-width
+                // coalesced stores -- what NVLink wants when the destination is a peer GPU's inbox.
+                unsigned long long* stage_h = wt.pairs;                       // PAIR_BUF = 128 entries
+                if (active) {
+                    const long long ko = wt.kout[sg] + i;
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        if (t < nv) {
+                            const unsigned long long pos = wt.wbase[own[t]] + rank[t];
+                            a.ridx[ko + t] = (a.owner_bits ? (own[t] << sh) : 0u) | (uint32_t)pos;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (a.n_ranks <= 2) {
+                    // few owners: runs are long enough for direct stores (measured faster at R = 2)
+                    if (active) {
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            if (t < nv) {
+                                const unsigned long long pos = wt.wbase[own[t]] + rank[t];
+                                if (pos < a.send_cap) a.peer_send[own[t]][a.send_region_off + pos] = h[t];
+                            }
+                        }
+                    }
+                } else {
+                    if (active) {
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            if (t < nv) {
+                                const unsigned slot = wt.wpre[own[t]] + rank[t];
+                                const unsigned long long pos = wt.wbase[own[t]] + rank[t];
+                                stage_h[slot] = h[t];
+                                wt.dst[slot] = pos < a.send_cap ? a.peer_send[own[t]] + a.send_region_off + pos : nullptr;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    const unsigned total = wt.wpre[a.n_ranks - 1] + wt.wcnt[a.n_ranks - 1];
+                    for (unsigned j = lane; j < total; j += 32) {
+                        uint64_t* d = wt.dst[j];
+                        if (d) *d = stage_h[j];
+                    }
+                }
+                __syncwarp();
+            }
+        } else if constexpr (MODE == MODE_GATHER) {
+            // K7 reply side: ids come from the owners' replies instead of local probes; same K4 rule
+            const int sh = 32 - a.owner_bits;
+            const uint32_t pmask = a.owner_bits ? ((1u << sh) - 1u) : 0xFFFFFFFFu;
+            for (int g0 = 0; g0 < G; g0 += 32) {
+                const int g = g0 + lane;
+                const bool active = g < G;
+                int sg = 0, i = 0, nv = 0;
+                uint32_t ids[4] = {SGC_MISS, SGC_MISS, SGC_MISS, SGC_MISS};
+                if (active) {
+                    int lo = 0;
+#pragma unroll
+                    for (int step = SPW / 2; step > 0; step >>= 1)
+                        if (wt.gpre[lo + step] <= g) lo += step;
+                    sg = lo;
+                    i = (g - wt.gpre[sg]) << 2;
+                    const int nk = wt.nk[sg];
+                    nv = nk - i < 4 ? nk - i : 4;
+                    const long long ko = wt.kout[sg] + i;
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        if (t < nv) {
+                            const uint32_t r = a.ridx[ko + t];
+                            const unsigned long long own = a.owner_bits ? (r >> sh) : 0u;
+                            ids[t] = a.replies[own * a.send_cap + (r & pmask)];
+                            if (ids[t] != SGC_MISS) my_hits++; else my_miss++;
+                        }
+                    }
+                }
+                if (a.kmer_ids && active) {
+                    uint32_t* o = a.kmer_ids + wt.kout[sg] + i;
+#pragma unroll
+                    for (int t = 0; t < 4; t++)
+                        if (t < nv) o[t] = ids[t];
+                }
+                emit_candidates(ids, active, sg, i, nv);
+            }
+        } else if constexpr (MODE == MODE_LABEL_SIDE) {
+            // K4 with fewer HBM lines per k-mer.  Only the FIRST k-mer of a group (the anchor) probes the
+            // hash table (software-pipelined like MODE_LABEL).  Its slot carries g, the k-mer's position in
+            // the table's unitig-ordered side array of {hash, id} records (id = what a table lookup of that
+            // hash returns, fixed up after the build).  Consecutive k-mers of a read are consecutive
+            // k-mers of the unitig, on one strand or the other, so k-mer t is looked for at side[g+t] and
+            // side[g-t]: a full 64-bit hash match there IS the table's answer for that hash.  Anything
+            // not matched (sequencing errors, unitig ends, anchor missing) is queued per warp and probed
+            // later DENSELY (every lane busy, probes pipelined), so the result is exactly what per-k-mer
+            // probing gives.  Neighbouring threads share side lines.
+            bool p_active = false;
+            int p_sg = 0, p_i = 0, p_nv = 0;
+            uint64_t p_h[4] = {0, 0, 0, 0};
+            uint32_t p_b0 = 0;
+            Entry p_e0, p_e1;
+
+            auto resolve = [&]() {
+                uint32_t ids[4] = {SGC_MISS, SGC_MISS, SGC_MISS, SGC_MISS};
+                unsigned pending = 0;
+                if (p_active) {
+                    uint32_t v = SGC_MISS, g = AUX_NONE;
+                    if (!bucket_match(p_e0, p_e1, p_h[0], v, g)) {
+                        v = SGC_MISS;
+                        g = AUX_NONE;
+                        if (bucket_overflowed(p_e0)) v = lookup_slow(a.tbl, a.nlines, p_b0, p_h[0], g);
+                    }
+                    ids[0] = v;
+                    pending = ((1u << p_nv) - 1u) & ~1u;  // k-mers 1..nv-1 until proven otherwise
+                    if (g != AUX_NONE) {
+                        uint4 up[3], um[3];
+#pragma unroll
+                        for (int d = 1; d < 4; d++) {
+                            const bool hi_ok = d < p_nv && (unsigned long long)g + d < a.side_n;
+                            const bool lo_ok = d < p_nv && g >= (uint32_t)d;
+                            up[d - 1] = hi_ok ? __ldg(a.side + g + d) : make_uint4(0, 0, SGC_MISS, 1);
+                            um[d - 1] = lo_ok ? __ldg(a.side + g - d) : make_uint4(0, 0, SGC_MISS, 1);
+                        }
+#pragma unroll
+                        for (int d = 1; d < 4; d++) {
+                            if (d < p_nv) {
+                                const uint32_t lo = (uint32_t)p_h[d], hi = (uint32_t)(p_h[d] >> 32);
+                                if (up[d - 1].x == lo && up[d - 1].y == hi && up[d - 1].w == 0) {
+                                    ids[d] = up[d - 1].z;
+                                    pending &= ~(1u << d);
+                                } else if (um[d - 1].x == lo && um[d - 1].y == hi && um[d - 1].w == 0) {
+                                    ids[d] = um[d - 1].z;
+                                    pending &= ~(1u << d);
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < 4; t++)
+                        if (t < p_nv && !((pending >> t) & 1u)) { if (ids[t] != SGC_MISS) my_hits++; else my_miss++; }
+                }
+                // queue the unresolved k-mers of this warp iteration (at most 96; room was made before)
+                {
+                    const unsigned np = __popc(pending);
+                    unsigned incl = np;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += v;
+                    }
+                    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (total) {
+                        unsigned pos = q_fill + incl - np;
+                        const uint32_t sq = pending ? (uint32_t)wt.seq[p_sg] : 0u;
+#pragma unroll
+                        for (int d = 1; d < 4; d++) {
+                            if ((pending >> d) & 1u) {
+                                qh[pos] = p_h[d];
+                                qs[pos] = sq;
+                                pos++;
+                            }
+                        }
+                        q_fill += total;
+                    }
+                }
+                emit_candidates(ids, p_active, p_sg, p_i, p_nv);  // queued k-mers count as "no id" here
+            };
+
+            for (int g0 = 0; g0 < G; g0 += 32) {
+                const int g = g0 + lane;
+                const bool active = g < G;
+                int sg = 0, i = 0, nv = 0;
+                uint64_t h[4] = {0, 0, 0, 0};
+                if (active) locate_and_hash(g, sg, i, nv, h);   // the previous group's anchor probe is in flight here
+                {
+                    const uint64_t dep = (h[0] ^ h[1] ^ h[2] ^ h[3]) & a.zero;  // see MODE_LABEL
+#pragma unroll
+                    for (int t = 0; t < 4; t++) p_h[t] ^= dep;
+                }
+                if (g0 > 0) resolve();
+                if (q_fill > QCAP - 96) drain_queue();
+                p_active = active; p_sg = sg; p_i = i; p_nv = nv;
+#pragma unroll
+                for (int t = 0; t < 4; t++) p_h[t] = h[t];
+                p_b0 = active ? home_bucket(h[0], a.nbuckets, a.home_shift) : 0u;
+                load_bucket_nc(a.tbl + p_b0, p_e0, p_e1);
+            }
+            if (G > 0) resolve();
+            if (q_fill > QCAP - 96) drain_queue();
+            __syncwarp();
+        } else {
+            // MODE_LOOKUP / MODE_LABEL, software-pipelined: the 4 table probes of a group are issued
+            // and left in flight while the NEXT group's 8 Murmur3 evaluations run; they are resolved
+            // one iteration later.  Integer pipe and HBM latency overlap inside a thread.
+            bool p_active = false;
+            int p_sg = 0, p_i = 0, p_nv = 0;
+            uint64_t p_h[4] = {0, 0, 0, 0};
+            uint32_t p_b[4] = {0, 0, 0, 0};
+            Entry p_e0[4], p_e1[4];
+
+            auto resolve = [&]() {
+                uint32_t ids[4] = {SGC_MISS, SGC_MISS, SGC_MISS, SGC_MISS};
+                unsigned slow = 0;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    if (p_active && t < p_nv) {
+                        uint32_t v;
+                        if (bucket_match(p_e0[t], p_e1[t], p_h[t], v)) ids[t] = v;
+                        else if (bucket_overflowed(p_e0[t])) slow |= 1u << t;
+                    }
+                }
+                while (slow) {  // ~6 % of lookups: the key is not in its home bucket; one trip per key
+                    const int t = __ffs(slow) - 1;
+                    slow &= slow - 1;
+                    const uint64_t hk = t == 0 ? p_h[0] : t == 1 ? p_h[1] : t == 2 ? p_h[2] : p_h[3];
+                    const uint32_t hb = t == 0 ? p_b[0] : t == 1 ? p_b[1] : t == 2 ? p_b[2] : p_b[3];
+                    uint32_t aux_unused;
+                    const uint32_t v = lookup_slow(a.tbl, a.nlines, hb, hk, aux_unused);
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (u == t) ids[u] = v;
+                }
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+                    if (p_active && t < p_nv) { if (ids[t] != SGC_MISS) my_hits++; else my_miss++; }
+
+                if constexpr (MODE == MODE_LOOKUP) {
+                    if (p_active) {
+                        if (a.kmer_ids) {
+                            uint32_t* o = a.kmer_ids + wt.kout[p_sg] + p_i;
+#pragma unroll
+                            for (int t = 0; t < 4; t++)
+                                if (t < p_nv) o[t] = ids[t];
+                        }
+                        if (a.count_by_id) {
+                            // run-length aggregate within the group before touching L2
+#pragma unroll
+                            for (int t = 0; t < 4; t++) {
+                                if (t < p_nv && ids[t] != SGC_MISS) {
+                                    unsigned run = 1;
+                                    bool counted = false;
+#pragma unroll
+                                    for (int u = 0; u < 4; u++) {
+                                        if (u < t && ids[u] == ids[t]) counted = true;
+                                        if (u > t && u < p_nv && ids[u] == ids[t]) run++;
+                                    }
+                                    if (!counted) atomicAdd(&a.count_by_id[ids[t]], run);
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    emit_candidates(ids, p_active, p_sg, p_i, p_nv);
+                }
+            };
+
+            for (int g0 = 0; g0 < G; g0 += 32) {
+                const int g = g0 + lane;
+                const bool active = g < G;
+                int sg = 0, i = 0, nv = 0;
+                uint64_t h[4] = {0, 0, 0, 0};
+                if (active) locate_and_hash(g, sg, i, nv, h);   // previous group's probes are in flight here
+                // Order the resolve AFTER the hash computation in the instruction stream: a.zero is
+                // always 0 but only known at run time, so the compares below truly depend on the new
+                // hashes and neither nvcc nor ptxas can sink the Murmur3 code under the resolve.
+                {
+                    const uint64_t dep = (h[0] ^ h[1] ^ h[2] ^ h[3]) & a.zero;
+#pragma unroll
+                    for (int t = 0; t < 4; t++) p_h[t] ^= dep;
+                }
+                if (g0 > 0) resolve();
+                p_active = active; p_sg = sg; p_i = i; p_nv = nv;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    p_h[t] = h[t];
+                    // lanes / k-mers with nothing to look up probe bucket 0 (an L2 hit) so that the
+                    // loads are unconditional and land directly in the pipeline registers
+                    p_b[t] = (active && t < nv) ? home_bucket(h[t], a.nbuckets, a.home_shift) : 0u;
+                    load_bucket_nc(a.tbl + p_b[t], p_e0[t], p_e1[t]);
+                }
+            }
+            if (G > 0) resolve();
+            __syncwarp();
+        }
+    }
+
+    if constexpr (MODE == MODE_LABEL_SIDE) drain_queue();
+    if constexpr (MODE == MODE_LABEL || MODE == MODE_GATHER || MODE == MODE_LABEL_SIDE) {
+        if (pair_fill) flush_pairs();
+    }
+    if constexpr (MODE == MODE_LOOKUP || MODE == MODE_LABEL || MODE == MODE_GATHER || MODE == MODE_LABEL_SIDE) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            my_hits += __shfl_xor_sync(0xffffffffu, my_hits, d);
+            my_miss += __shfl_xor_sync(0xffffffffu, my_miss, d);
+        }
+        if (lane == 0) {
+            if (my_hits) atomicAdd(&a.scal->n_hits, my_hits);
+            if (my_miss) atomicAdd(&a.scal->n_miss, my_miss);
+        }
+    }
+}
+
+
+}  // namespace dev
+}  // namespace sgc
