@@ -21,54 +21,96 @@ DEFAULT_KSIZE = 31
 BATCH_READS = 1 << 22
 
 
+def pair_flags(names, elig, ignore_paired=False):
+    """Vectorised pairing test of index_reads.py:124-141 for every record: is it the mate of
+    ``last_record`` (the latest earlier record that was long enough)?  -> (paired bool[n], last int64[n]).
+    Name comparisons go through 64-bit string hashes and every positive is re-checked on the strings."""
+    n = len(names)
+    idx = np.where(elig, np.arange(n, dtype=np.int64), -1)
+    last = np.full(n, -1, np.int64)
+    if n > 1 and not ignore_paired:
+        last[1:] = np.maximum.accumulate(idx)[:-1]
+    if n == 0 or ignore_paired:
+        return np.zeros(n, bool), last
+    h_full = np.fromiter((hash(s) for s in names), np.int64, n)
+    h_base = np.fromiter((hash(s[:-2]) for s in names), np.int64, n)
+    e1 = np.fromiter((s.endswith("/1") for s in names), bool, n)
+    e2 = np.fromiter((s.endswith("/2") for s in names), bool, n)
+    nlen = np.fromiter((len(s) for s in names), np.int64, n)
+    j = np.maximum(last, 0)
+    slash = e1[j] & e2
+    cand = (last >= 0) & np.where(slash, (h_base[j] == h_base) & (nlen[j] > 2), (h_full[j] == h_full) & (nlen[j] > 0))
+    for i in np.flatnonzero(cand).tolist():  # exactness: hashes only pre-filter
+        a, b = names[last[i]], names[i]
+        if a.endswith("/1") and b.endswith("/2"):
+            ok = a[:-2] == b[:-2] and len(a) > 2
+        else:
+            ok = a == b and bool(a)
+        if not ok:
+            cand[i] = False
+    return cand, last
+
+
+def _expand(lo, hi):
+    """concatenated index ranges [lo[i], hi[i]) and the owner i of every element"""
+    ln = hi - lo
+    tot = int(ln.sum())
+    owner = np.repeat(np.arange(len(lo), dtype=np.int64), ln)
+    start = np.repeat(np.cumsum(ln) - ln, ln)
+    return np.repeat(lo, ln) + (np.arange(tot, dtype=np.int64) - start), owner
+
+
+def rows_from_labels(names, lens, offsets, ids_off, ids, ksize, ignore_paired=False):
+    """The host half of the index_reads loop (index_reads.py:105-167), vectorised: given every
+    read's distinct unitig ids (CSR) produce the rows the reference INSERTs.
+
+    State of the reference loop after record i: S_i = (paired_i ? S_{i-1} : {}) | (long_i ? ids_i : {}),
+    i.e. the union of the ids of the records since the last record that was NOT paired; a record long
+    enough emits S_i under its own offset and, when paired, under its mate's offset as well.
+    -> (rows_offset, rows_id, n_paired, first_paired)"""
+    n = len(names)
+    lens = np.asarray(lens, np.int64)
+    offsets = np.asarray(offsets, np.int64)
+    ids_off = np.asarray(ids_off, np.int64)
+    ids = np.asarray(ids, np.int64)
+    elig = lens >= ksize
+    paired, last = pair_flags(names, elig, ignore_paired)
+    n_paired = int(paired.sum())
+    first_paired = int(np.flatnonzero(paired)[0]) if n_paired else -1
+    # run start c(i): the latest record <= i that is not paired
+    c = np.maximum.accumulate(np.where(~paired, np.arange(n, dtype=np.int64), 0)) if n else np.zeros(0, np.int64)
+    sel = np.flatnonzero(elig)
+    lo, hi, own_lo = ids_off[c[sel]], ids_off[sel + 1], ids_off[sel]
+    simple = lo == own_lo  # nothing inherited: the read's own ids, already distinct and ascending
+    pos_s, own_s = _expand(own_lo[simple], hi[simple])
+    rid_s, rrec_s = ids[pos_s], sel[simple][own_s]
+    pos_m, own_m = _expand(lo[~simple], hi[~simple])
+    if len(pos_m):
+        key = np.unique(np.stack([sel[~simple][own_m], ids[pos_m]], 1), axis=0)  # union per record
+        rrec_m, rid_m = key[:, 0], key[:, 1]
+    else:
+        rrec_m, rid_m = np.zeros(0, np.int64), np.zeros(0, np.int64)
+    rrec = np.concatenate([rrec_s, rrec_m])
+    rid = np.concatenate([rid_s, rid_m])
+    mate = paired[rrec]
+    rows_o = np.concatenate([offsets[rrec], offsets[last[rrec[mate]]]])
+    rows_i = np.concatenate([rid, rid[mate]])
+    return rows_o, rows_i, n_paired, first_paired
+
+
 def label_records(names, seq, seq_off, offsets, kmer_idx, ksize, ignore_paired=False):
-    """The loop of index_reads.py:105-167 over an in-memory batch.
+    """The loop of index_reads.py:105-167 over an in-memory batch: ONE fused GPU pass for the per-read
+    ids, then the vectorised host rules.
 
     -> (rows_offset int64[m], rows_id int64[m], n_paired, set_of_all_ids, first_paired).
     ``rows_*`` are the rows the reference INSERTs (as a multiset; duplicates included, cf.
     :156-157); ``first_paired`` is the index of the first read found paired (-1: none)."""
-    n = len(names)
     res = kmer_idx.table.label_reads(seq, seq_off, ksize)
     if res["status"].any():
         bad = int(np.flatnonzero(res["status"])[0])
         raise ValueError("Invalid base in read %r" % names[bad])
-    ids_off, ids = res["ids_off"], res["ids"].astype(np.int64)
-    lens = np.diff(seq_off)
-
-    rows_o, rows_i = [], []
-    n_paired = 0
-    first_paired = -1
-    last = -1  # index of last_record
-    cur = ()  # cdbg_ids carried from the mate
-    for i in range(n):
-        paired = False
-        if last >= 0:
-            a, b = names[last], names[i]
-            if a.endswith("/1") and b.endswith("/2"):
-                paired = a[:-2] == b[:-2] and len(a) > 2
-            elif a == b and a:
-                paired = True
-        if paired:
-            n_paired += 1
-            if first_paired < 0:
-                first_paired = i
-        else:
-            cur = ()
-        if lens[i] < ksize:
-            continue
-        mine = ids[ids_off[i] : ids_off[i + 1]]
-        cur = np.union1d(cur, mine) if len(cur) else mine
-        if len(cur):
-            if paired:
-                rows_o.append(np.repeat(np.array([offsets[last], offsets[i]], np.int64), len(cur)))
-                rows_i.append(np.tile(cur, 2))
-            else:
-                rows_o.append(np.full(len(cur), offsets[i], np.int64))
-                rows_i.append(cur)
-        if not ignore_paired:
-            last = i
-    ro = np.concatenate(rows_o) if rows_o else np.zeros(0, np.int64)
-    ri = np.concatenate(rows_i) if rows_i else np.zeros(0, np.int64)
+    ro, ri, n_paired, first_paired = rows_from_labels(names, np.diff(seq_off), offsets, res["ids_off"], res["ids"], ksize,
+                                                      ignore_paired)
     return ro, ri, n_paired, set(np.unique(ri).tolist()), first_paired
 
 

@@ -147,3 +147,35 @@ def test_bgzf_roundtrip_and_record_offsets(tmp_path):
     names2, seq2, off2, pos2 = bgzf.parse_records(np.frombuffer(fa, np.uint8))
     assert names2 == names and np.array_equal(seq2, seq) and np.array_equal(off2, off)
     assert all(fa[p : p + 1] == b">" for p in pos2.tolist())
+
+
+def test_index_reads_host_rules_vectorised_vs_oracle_loop():
+    """rows_from_labels (the vectorised pairing / carry-over rules of index_reads.py:105-167) against
+    the oracle's literal restatement of the reference loop, on names that exercise every branch:
+    /1-/2 mates, equal names, chains of equal names, short reads between mates, empty names."""
+    from oracle import oracle as O
+    from spacegraphcats_b200.cdbg.index_reads import rows_from_labels
+
+    rng = np.random.default_rng(8)
+    k = 21
+    genome = "".join("ACGT"[i] for i in rng.integers(0, 4, 30000))
+    pieces = [genome[a : a + 60 + k - 1] for a in range(0, len(genome) - k + 1, 60)]
+    table, _, _ = O.build_mphf(k, lambda: iter(O.Record(str(i), s) for i, s in enumerate(pieces)))
+    ctab = O.COracleTable(table.mphf_to_hash, table.mphf_to_value)
+    names_pool = ["a/1", "a/2", "b/1", "c/2", "same", "same", "same", "/1", "/2", "", "", "x", "q/1", "short", "q/2",
+                  "r/1", "r/2", "r/2", "t/1", "t/1"]
+    recs = []
+    for rep in range(40):
+        for nm in names_pool:
+            ln = 5 if nm == "short" or rng.random() < 0.1 else int(rng.integers(k, 400))
+            p = int(rng.integers(0, len(genome) - 400))
+            recs.append(O.Record(nm if rng.random() < 0.8 else nm + str(rep), genome[p : p + ln]))
+    offs = (np.arange(len(recs), dtype=np.int64) * 1000 + 17).tolist()
+    buf, off = O.pack_sequences([r.sequence for r in recs])
+    ioff, ids, _, _ = ctab.label_reads(buf, off, k)
+    for ignore in (False, True):
+        want, n_paired, total = O.label_reads(zip(recs, offs), table, k, ignore_paired=ignore)
+        ro, ri, got_paired, first = rows_from_labels([r.name for r in recs], np.diff(off), offs, ioff, ids, k, ignore)
+        assert sorted(zip(ro.tolist(), ri.tolist())) == sorted(want)
+        assert got_paired == n_paired and (first >= 0) == (n_paired > 0)
+        assert n_paired > 0 or ignore
