@@ -162,7 +162,7 @@ int fetch_scalars(sgc_ctx* c) {
 struct Plan {
     const int64_t* kmer_off;
     const int64_t* seg_first;
-    const int64_t* seg_map;
+    const SegDesc* segdesc;
     const int64_t* nsegs_p;
 };
 
@@ -177,7 +177,7 @@ int make_plan(sgc_ctx* c, const int64_t* d_off, int64_t nseq, int64_t seq_bytes,
         d_kmer_off = (int64_t*)c->kmer_off.p;
     }
     const int64_t max_segs = nseq + seq_bytes / SEG_K + 1;
-    TRY(ensure(c, c->seg_map, (size_t)max_segs * 8));
+    TRY(ensure(c, c->seg_map, (size_t)max_segs * sizeof(SegDesc)));
     CU(cudaMemsetAsync(&c->d_scal->bad_offsets, 0, sizeof(int), c->stream));
     plan_count_kernel<<<grid_for((int64_t)n1, 256, 1 << 30), 256, 0, c->stream>>>(
         d_off, nseq, k, seq_bytes, (int64_t*)c->nk.p, (int64_t*)c->nseg.p, c->d_scal);
@@ -189,14 +189,14 @@ int make_plan(sgc_ctx* c, const int64_t* d_off, int64_t nseq, int64_t seq_bytes,
     CU(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tb, (int64_t*)c->nseg.p, (int64_t*)c->seg_first.p, (int64_t)n1,
                                      c->stream));
     if (nseq > 0) {
-        plan_expand_kernel<<<grid_for(nseq, 256, 1 << 30), 256, 0, c->stream>>>((int64_t*)c->seg_first.p, nseq,
-                                                                              (int64_t*)c->seg_map.p);
+        plan_expand_kernel<<<grid_for(nseq, 256, 1 << 30), 256, 0, c->stream>>>(
+            (int64_t*)c->seg_first.p, d_off, d_kmer_off, nseq, k, (SegDesc*)c->seg_map.p);
         c->launches++;
     }
     CU(cudaGetLastError());
     plan->kmer_off = d_kmer_off;
     plan->seg_first = (int64_t*)c->seg_first.p;
-    plan->seg_map = (int64_t*)c->seg_map.p;
+    plan->segdesc = (const SegDesc*)c->seg_map.p;
     plan->nsegs_p = (int64_t*)c->seg_first.p + nseq;
     return SGC_OK;
 }
@@ -256,7 +256,7 @@ TileArgs base_args(sgc_ctx* c, const uint8_t* d_seq, const int64_t* d_off, int k
     memset(&a, 0, sizeof(a));
     a.seq = d_seq;
     a.off = d_off;
-    a.seg_map = p.seg_map;
+    a.segdesc = p.segdesc;
     a.nsegs_p = p.nsegs_p;
     a.kmer_off = p.kmer_off;
     a.status = d_status;

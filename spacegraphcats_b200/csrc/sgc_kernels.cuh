@@ -28,12 +28,24 @@ __global__ void plan_count_kernel(const int64_t* __restrict__ off, int64_t nseq,
     nseg_out[s] = (nk + SEG_K - 1) / SEG_K;
 }
 
-__global__ void plan_expand_kernel(const int64_t* __restrict__ seg_first, int64_t nseq,
-                                   int64_t* __restrict__ seg_map) {
+__global__ void plan_expand_kernel(const int64_t* __restrict__ seg_first, const int64_t* __restrict__ off,
+                                   const int64_t* __restrict__ kmer_off, int64_t nseq, int k,
+                                   SegDesc* __restrict__ segdesc) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nseq) return;
-    int64_t a = seg_first[s], b = seg_first[s + 1];
-    for (int64_t j = a; j < b; j++) seg_map[j] = s | ((j - a) << 40);
+    const int64_t a = seg_first[s], b = seg_first[s + 1];
+    if (a == b) return;
+    const int64_t o0 = off[s], nkseq = off[s + 1] - o0 - k + 1, ko = kmer_off[s];
+    for (int64_t j = a; j < b; j++) {
+        const int64_t q0 = (j - a) * SEG_K;
+        SegDesc d;
+        d.start = o0 + q0;
+        d.kout = ko + q0;
+        d.seq = (unsigned int)s;
+        d.nk = (int)(nkseq - q0 < SEG_K ? nkseq - q0 : SEG_K);
+        d.pad[0] = d.pad[1] = 0;
+        segdesc[j] = d;
+    }
 }
 
 

@@ -16,7 +16,7 @@ namespace dev {
 #endif
 constexpr int NT = 256;         // threads per CTA
 constexpr int WPB = NT / 32;    // warps per CTA; every warp runs its own rounds (no block barriers)
-constexpr int SPW = 8;          // segments staged per warp round (4 lanes stage one segment)
+constexpr int SPW = 4;          // segments staged per warp round (8 lanes stage one segment)
 constexpr int SEG_K = 256;      // k-mers per segment
 constexpr int PAIR_BUF = 128;   // label keys staged per warp before one global reservation
 constexpr int QCAP = 256;       // MODE_LABEL_SIDE: k-mers queued per warp for a dense table probe
@@ -56,6 +56,17 @@ struct __align__(32) Bucket {
     Entry e[2];
 };
 
+// One segment (<= SEG_K consecutive k-mers of one sequence), precomputed by the plan so that the
+// tile kernel can fetch it with one independent asynchronous copy (no dependent loads).
+struct __align__(16) SegDesc {
+    long long start;   // byte offset of the segment's first base in the sequence buffer
+    long long kout;    // global index of its first k-mer
+    unsigned int seq;  // sequence index
+    int nk;            // k-mers in this segment (0 = nothing to do)
+    unsigned int pad[2];
+};
+static_assert(sizeof(SegDesc) == 32, "SegDesc is copied as two 16-byte cp.async");
+
 struct Scalars {
     unsigned long long pair_count;
     unsigned long long n_hits;
@@ -74,7 +85,7 @@ struct Scalars {
 struct TileArgs {
     const uint8_t* seq;
     const int64_t* off;
-    const int64_t* seg_map;
+    const SegDesc* segdesc;
     const int64_t* nsegs_p;
     const int64_t* kmer_off;
     int32_t* status;

@@ -27,6 +27,26 @@ __device__ __forceinline__ uint32_t load_window4(uintptr_t base, int f, int Ls, 
     return sgc::funnel_bytes(lo, hi, s) & mask;
 }
 
+// bytes F[f .. f+4) of a segment of Ls bases that sits at byte offset r0 of a raw shared-memory copy;
+// bytes outside [0, Ls) read as 0
+__device__ __forceinline__ uint32_t raw_window4(const uint32_t* raw, int r0, int f, int Ls, uint32_t& mask) {
+    const int lo_clip = f < 0 ? -f : 0;
+    const int hi_clip = f + 4 > Ls ? f + 4 - Ls : 0;
+    if (lo_clip >= 4 || hi_clip >= 4) { mask = 0; return 0; }
+    mask = (0xFFFFFFFFu << (8 * lo_clip)) & (0xFFFFFFFFu >> (8 * hi_clip));
+    const int b = r0 + f + 16;  // raw copies start 16 bytes into their slot, so b - (b & 3) >= 0 for f >= -3
+    const int s = b & 3, w = b >> 2;
+    return sgc::funnel_bytes(raw[w], raw[w + 1], s) & mask;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // reverse complement of 4 packed bases (byte-reversed, A<->T, C<->G); ok = every byte selected by
 // mask is one of A, C, G, T.  Bytes that are not pass through unchanged (oracle rule).
 __device__ __forceinline__ uint32_t revcomp_word(uint32_t u, uint32_t mask, bool& ok) {
@@ -46,8 +66,9 @@ __device__ __forceinline__ uint32_t revcomp_word(uint32_t u, uint32_t mask, bool
 }
 
 // ----------------------------------------------------------------------------------
-// the tile kernel.  Every WARP runs its own rounds: fetch SPW segments, stage their forward and
-// reverse-complement bytes in its slice of shared memory (4 lanes per segment), then each lane
+// the tile kernel.  Every WARP runs its own rounds: fetch SPW segments (asynchronous copies, two
+// rounds deep), stage their forward and reverse-complement bytes in its slice of shared memory
+// (8 lanes per segment), then each lane
 // hashes groups of 4 consecutive k-mers and feeds them to the mode's sink.  No block barriers:
 // warps drift apart, so one warp's exposed latencies (round fetch, staging loads, table probes)
 // are covered by the other warps of the SM.
@@ -56,6 +77,8 @@ template <int K>
 struct WarpTile {
     uint32_t F[SPW * Geo<K>::WPS];
     uint32_t R[SPW * Geo<K>::WPS];
+    uint32_t RAW[2][SPW * Geo<K>::WPS];  // 16-byte-aligned raw copies of the segments (cp.async), double-buffered
+    SegDesc D[3][SPW];                   // prefetched descriptors of this round and the next two
     unsigned long long pairs[PAIR_BUF];
     long long start[SPW];
     long long seq[SPW];
@@ -182,31 +205,81 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
         }
     };
 
-    // dynamic round scheduling; the NEXT round index is always requested one round ahead
-    unsigned next_round = 0;
-    if (lane == 0) next_round = atomicAdd(&a.scal->round_ctr, 1u);
+    // ------------------------------------------------------------------------------------------
+    // Round pipeline.  A warp claims rounds (SPW segments each) from one atomic counter, always three
+    // ahead, and keeps two asynchronous copies in flight while it works on round r:
+    //   descriptors of round r+2  (cp.async of SPW SegDesc, 32 bytes each)
+    //   raw bytes of round r+1    (cp.async of the 16-byte chunks that cover each segment)
+    // both issued at the top of round r and waited for at its end, so they have a whole round to land;
+    // the staging of round r itself (re-alignment + reverse complement) reads shared memory only.
+    // ------------------------------------------------------------------------------------------
+    auto claim_round = [&]() -> unsigned {
+        unsigned r = 0;
+        if (lane == 0) r = atomicAdd(&a.scal->round_ctr, 1u);
+        return __shfl_sync(0xffffffffu, r, 0);
+    };
+    auto prefetch_desc = [&](int slot, unsigned round) {
+        if (lane < 2 * SPW) {
+            const int sgi = lane >> 1, half = lane & 1;
+            const int64_t g = (int64_t)round * SPW + sgi;
+            unsigned char* dst = reinterpret_cast<unsigned char*>(&wt.D[slot][sgi]) + 16 * half;
+            if ((int64_t)round < nrounds && g < nsegs) {
+                cp_async16(dst, reinterpret_cast<const unsigned char*>(a.segdesc + g) + 16 * half);
+            } else {
+                *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);  // nk = 0: nothing to do
+            }
+        }
+    };
+    auto prefetch_raw = [&](int buf, int slot) {
+        if constexpr (MODE != MODE_GATHER) {
+            const int sgi = lane >> 3, sub = lane & 7;
+            const SegDesc& d = wt.D[slot][sgi];
+            if (d.nk > 0) {
+                const int Ls = d.nk + k - 1;
+                const uintptr_t g0 = (uintptr_t)a.seq + (uintptr_t)d.start;
+                const uintptr_t a0 = g0 & ~(uintptr_t)15;
+                const int nchunks = (int)(((g0 + (uintptr_t)Ls + 15) & ~(uintptr_t)15) - a0) >> 4;
+                unsigned char* dst = reinterpret_cast<unsigned char*>(wt.RAW[buf] + sgi * WPS) + 16;
+                for (int c = sub; c < nchunks; c += 8)
+                    cp_async16(dst + 16 * c, reinterpret_cast<const void*>(a0 + 16 * (uintptr_t)c));
+            }
+        }
+    };
 
-    for (;;) {
-        const unsigned round = __shfl_sync(0xffffffffu, next_round, 0);
+    unsigned rq0 = claim_round(), rq1 = claim_round(), rq2 = claim_round();
+    // prologue: descriptors of the first two rounds, raw bytes of the first
+    prefetch_desc(0, rq0);
+    prefetch_desc(1, rq1);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncwarp();
+    prefetch_raw(0, 0);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncwarp();
+
+    for (unsigned it = 0;; it++) {
+        const unsigned round = rq0;
         if ((int64_t)round >= nrounds) break;
-        if (lane == 0) next_round = atomicAdd(&a.scal->round_ctr, 1u);
-        const int64_t seg0 = (int64_t)round * SPW;
+        const int cur = it % 3, nxt = (it + 1) % 3, nx2 = (it + 2) % 3, buf = it & 1;
+        // top of the round: launch the copies for the next rounds
+        prefetch_desc(nx2, rq2);
+        prefetch_raw(buf ^ 1, nxt);
+        cp_async_commit();
+        rq0 = rq1;
+        rq1 = rq2;
+        rq2 = claim_round();
 
-        // ---- descriptors (lanes 0..SPW-1) ----
+        // ---- descriptors of THIS round (arrived a round ago) ----
         {
             int nk = 0;
-            long long start = 0, sq = 0, kout = 0;
-            const int64_t g = seg0 + lane;
-            if (lane < SPW && g < nsegs) {
-                const unsigned long long e = (unsigned long long)a.seg_map[g];
-                sq = (long long)(e & SEQ_MASK);
-                const long long sn = (long long)(e >> 40);
-                const long long o0 = a.off[sq], o1 = a.off[sq + 1];
-                const long long q0 = sn * SEG_K;
-                const long long rem = o1 - o0 - k + 1 - q0;
-                nk = (int)(rem < SEG_K ? rem : SEG_K);
-                start = o0 + q0;
-                if (a.kmer_off) kout = a.kmer_off[sq] + q0;
+            if (lane < SPW) {
+                const SegDesc d = wt.D[cur][lane];
+                nk = d.nk;
+                wt.start[lane] = d.start;
+                wt.seq[lane] = (long long)d.seq;
+                wt.kout[lane] = d.kout;
+                wt.nk[lane] = nk;
             }
             int incl = (nk + 3) >> 2;
 #pragma unroll
@@ -214,37 +287,32 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                 int v = __shfl_up_sync(0xffffffffu, incl, d);
                 if (lane >= d) incl += v;
             }
-            if (lane < SPW) {
-                wt.start[lane] = start;
-                wt.seq[lane] = sq;
-                wt.kout[lane] = kout;
-                wt.nk[lane] = nk;
-                wt.gpre[lane + 1] = incl;
-            }
+            if (lane < SPW) wt.gpre[lane + 1] = incl;
             if (lane == 0) wt.gpre[0] = 0;
         }
         __syncwarp();
 
-        // ---- stage forward + reverse-complement words straight from global memory ----
+        // ---- stage forward + reverse-complement words from the raw copy (shared memory only) ----
         if constexpr (MODE != MODE_GATHER) {
-            const int sg = lane >> 2, sub = lane & 3;
+            const int sg = lane >> 3, sub = lane & 7;
             const int nk = wt.nk[sg];
             if (nk) {
                 const int Ls = nk + k - 1;
-                const uintptr_t base = (uintptr_t)a.seq + (uintptr_t)wt.start[sg];
+                const int r0 = (int)(((uintptr_t)a.seq + (uintptr_t)wt.start[sg]) & 15);
+                const uint32_t* raw = wt.RAW[buf] + sg * WPS;
                 uint32_t* Fs = wt.F + sg * WPS;
                 uint32_t* Rs = wt.R + sg * WPS;
                 const int p = sgc::rc_pad(nk);
                 bool all_ok = true;
-                for (int w = sub; 4 * w < Ls; w += 4) {
+                for (int w = sub; 4 * w < Ls; w += 8) {
                     uint32_t mask;
-                    Fs[w] = load_window4(base, 4 * w, Ls, mask);
+                    Fs[w] = raw_window4(raw, r0, 4 * w, Ls, mask);
                 }
                 // R word m holds R[4m-4-p .. +4) = revcomp of F[Ls-4m+p .. +4)
                 const int nrw = (Ls + 4 + p + 3) >> 2;
-                for (int m = sub; m < nrw; m += 4) {
+                for (int m = sub; m < nrw; m += 8) {
                     uint32_t mask;
-                    const uint32_t u = load_window4(base, Ls - 4 * m + p, Ls, mask);
+                    const uint32_t u = raw_window4(raw, r0, Ls - 4 * m + p, Ls, mask);
                     bool ok;
                     Rs[m] = revcomp_word(u, mask, ok);
                     all_ok &= ok;
@@ -686,7 +754,12 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
             if (G > 0) resolve();
             __syncwarp();
         }
+
+        // end of the round: the copies launched at its top (next round's bytes, next-next descriptors)
+        cp_async_wait_all();
+        __syncwarp();
     }
+    cp_async_wait_all();  // copies launched for rounds past the end (none carry data) must not outlive the CTA
 
     if constexpr (MODE == MODE_LABEL_SIDE) drain_queue();
     if constexpr (MODE == MODE_LABEL || MODE == MODE_GATHER || MODE == MODE_LABEL_SIDE) {
