@@ -29,6 +29,48 @@ class QueryResult:
         # here is where we go from the dominators to the actual cDBG nodes (:34)
         self.shadow = catlas.shadow(doms)
 
+    def response_curve_lines(self):
+        """The ``*.response.txt`` curve (search_utils.output_response_curve, search/search_utils.py:268-329):
+        level-1 dominators with matches, by decreasing matched k-mers, with cumulative containment and
+        overhead.  The per-dominator match counts and sizes are the K6 sums already on hand."""
+        q, cat = self.query, self.catalog_sizes()
+        curve = []
+        for node, level in self.catlas.levels.items():
+            if level == 1:
+                n_cont = q.catlas_match_counts.get(node, 0)
+                if n_cont:
+                    curve.append((n_cont, cat[node] - n_cont, node))
+        curve.sort(reverse=True)
+        total = sum(c[0] for c in curve)
+        lines = ["sum_cont relative_cont relative_overhead sum_cont2 sum_oh catlas_id"]
+        step = max(int(len(curve) / 200), 1)
+        sofar = total_oh = 0
+        for pos, (n_cont, n_oh, node) in enumerate(curve):
+            sofar += n_cont
+            total_oh += n_oh
+            if pos % step == 0 or pos + 1 == len(curve):
+                lines.append("{} {} {} {} {} {}".format(sofar, sofar / total, total_oh / total, n_cont, n_oh, node))
+        return lines
+
+    def catalog_sizes(self):
+        sizes = getattr(self.catlas, "index_sizes", None)
+        if sizes is None:
+            self.catlas.decorate_with_index_sizes(self.kmer_idx)
+            sizes = self.catlas.index_sizes
+        return sizes
+
+    def summary(self):
+        """The index-derived columns of the ``results.csv`` row (query_by_sequence.py:91-124): bp and
+        contigs of the neighbourhood, number of query k-mers and the three upper bounds.  The two
+        sourmash columns (containment, similarity of the retrieved contigs) stay on the CPU reference."""
+        k = self.kmer_idx.ksize
+        bp = sum(self.kmer_idx.get_cdbg_size(c) + k - 1 for c in self.shadow)
+        best, cdbg_oh, catlas_oh = (self.query.con_sim_upper_bounds(self.catlas, self.kmer_idx)
+                                    if self.query.n_kmers else (0.0, 0, 0))
+        return {"bp": bp, "contigs": len(self.shadow), "ksize": k, "num_query_kmers": self.query.n_kmers,
+                "best_containment": best, "cdbg_min_overhead": cdbg_oh, "catlas_min_overhead": catlas_oh,
+                "catlas_name": self.catlas_name}
+
     # the two id lists QueryOutput.write saves (:126-132)
     def cdbg_ids_lines(self):
         return [str(x) for x in sorted(self.shadow)]

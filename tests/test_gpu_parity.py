@@ -404,6 +404,14 @@ def test_query_dory_head_matches_reference_outputs(O, dory, dory_index, dory_cat
         assert sorted(ln.strip() for ln in fp) == sorted(out.frontier_lines())
     assert dory_catlas.index_sizes == O.build_catlas_node_sizes(ref_sizes, ocat)
     assert q.con_sim_upper_bounds(dory_catlas, dory_index)[0] == 1.0
+    # the reference's response curve and the index-derived columns of its results.csv row
+    with open(golden_path("dory_k21_r1_search", "dory-head.fa.response.txt")) as fp:
+        assert [ln.rstrip("\n") for ln in fp] == out.response_curve_lines()
+    with open(golden_path("dory_k21_r1_search", "results.csv")) as fp:
+        row = [ln.strip().split(",") for ln in fp][1]
+    sm = out.summary()
+    assert [str(sm[c]) for c in ("bp", "contigs", "ksize", "num_query_kmers", "best_containment", "cdbg_min_overhead",
+                                 "catlas_min_overhead", "catlas_name")] == row[3:]
 
 
 def test_query_nomatch(dory_index, dory_catlas):
@@ -414,6 +422,13 @@ def test_query_nomatch(dory_index, dory_catlas):
     out = q.execute(dory_catlas, dory_index)
     assert q.n_kmers == 8 and q.cdbg_match_counts == {} and q.catlas_match_counts == {}
     assert out.doms == set() and out.shadow == set()
+    with open(golden_path("dory_k21_r1_search", "random-query-nomatch.fa.response.txt")) as fp:
+        assert [ln.rstrip("\n") for ln in fp] == out.response_curve_lines()
+    with open(golden_path("dory_k21_r1_search", "results.csv")) as fp:
+        row = [ln.strip().split(",") for ln in fp][2]
+    sm = out.summary()
+    assert [str(sm[c]) for c in ("bp", "contigs", "ksize", "num_query_kmers", "best_containment", "cdbg_min_overhead",
+                                 "catlas_min_overhead", "catlas_name")] == row[3:]
 
 
 def test_dominator_abundance_totals(O, dory, dory_index, dory_catlas):
