@@ -870,3 +870,45 @@ def test_abi_error_paths(ctx):
     h1, _, _ = ctx.hash_batch(buf, off, 21)
     assert np.array_equal(h1, h2)
     c2.close()
+
+
+# ---------------------------------------------------------------- randomized properties (hypothesis)
+def test_hypothesis_hash_and_label_vs_oracle(ctx, O):
+    """Random batches (random k in 1..64, ragged lengths incl. empty, occasional non-ACGT bytes):
+    hashes, status flags and per-read labels (both label kernels) against the oracle."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+
+    from spacegraphcats_b200.cdbg.hashing import GpuKmerTable
+    from spacegraphcats_b200.device import pack_sequences
+
+    base = st.text(alphabet="ACGT", min_size=0, max_size=300)
+    dirty = st.text(alphabet="ACGTNacgt", min_size=0, max_size=80)
+    seqs_st = st.lists(st.one_of(base, base, base, dirty), min_size=0, max_size=40)
+
+    @settings(max_examples=40, deadline=None, derandomize=True, database=None, suppress_health_check=list(HealthCheck))
+    @given(seqs=seqs_st, k=st.integers(min_value=1, max_value=64), side=st.booleans())
+    def run(seqs, k, side):
+        buf, off = pack_sequences(seqs)
+        h, koff, status = ctx.hash_batch(buf, off, k)
+        want, woff = O.hash_batch(buf, off, k)
+        assert np.array_equal(koff, woff) and np.array_equal(h, want)
+        # flagged <=> the sequence has k-mers and some base is not A/C/G/T
+        assert status.tolist() == [int(len(s) >= k and any(c not in "ACGT" for c in s)) for s in seqs]
+        clean = [s for s in seqs if all(c in "ACGT" for c in s)]
+        unitigs = [s for s in clean[: max(1, len(clean) // 2)] if len(s) >= k]
+        if not unitigs:
+            return
+        ubuf, uoff = pack_sequences(unitigs)
+        table = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx, side=side)
+        otab, _, _ = O.build_mphf(k, lambda: iter(O.Record(str(i), s) for i, s in enumerate(unitigs)))
+        assert len(table) == len(otab)
+        cbuf, coff = pack_sequences(clean)
+        lab = table.label_reads(cbuf, coff, k)
+        if len(otab) == 0:
+            assert lab["n_hits"] == 0 and lab["n_labels"] == 0
+            return
+        o_off, o_ids, o_nk, o_nh = O.COracleTable(otab.mphf_to_hash, otab.mphf_to_value).label_reads(cbuf, coff, k)
+        assert (lab["n_kmers"], lab["n_hits"]) == (o_nk, o_nh)
+        assert np.array_equal(lab["ids_off"], o_off) and np.array_equal(lab["ids"], o_ids)
+
+    run()
