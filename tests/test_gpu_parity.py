@@ -900,14 +900,21 @@ def test_hypothesis_hash_and_label_vs_oracle(ctx, O):
             return
         ubuf, uoff = pack_sequences(unitigs)
         table = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx, side=side)
-        otab, _, _ = O.build_mphf(k, lambda: iter(O.Record(str(i), s) for i, s in enumerate(unitigs)))
-        assert len(table) == len(otab)
+        # build_mphf's table without its closing asserts (they reject inputs whose last unitig loses all
+        # of its k-mers, which random tiny inputs do produce): hashes under two ids are dropped
+        uh, ukoff = O.hash_batch(ubuf, uoff, k)
+        uid = np.repeat(np.arange(len(unitigs), dtype=np.uint32), np.diff(ukoff))
+        pairs = np.unique(np.stack([uh, uid.astype(np.uint64)], 1), axis=0)
+        hs, cnt = np.unique(pairs[:, 0], return_counts=True)
+        keep = np.isin(pairs[:, 0], hs[cnt == 1])
+        oh, ov = pairs[keep, 0], pairs[keep, 1].astype(np.uint32)
+        assert len(table) == len(oh) and table.stats()[1] == int((cnt > 1).sum())
         cbuf, coff = pack_sequences(clean)
         lab = table.label_reads(cbuf, coff, k)
-        if len(otab) == 0:
+        if len(oh) == 0:
             assert lab["n_hits"] == 0 and lab["n_labels"] == 0
             return
-        o_off, o_ids, o_nk, o_nh = O.COracleTable(otab.mphf_to_hash, otab.mphf_to_value).label_reads(cbuf, coff, k)
+        o_off, o_ids, o_nk, o_nh = O.COracleTable(oh, ov).label_reads(cbuf, coff, k)
         assert (lab["n_kmers"], lab["n_hits"]) == (o_nk, o_nh)
         assert np.array_equal(lab["ids_off"], o_off) and np.array_equal(lab["ids"], o_ids)
 
