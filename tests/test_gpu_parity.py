@@ -230,6 +230,30 @@ def test_build_mphf_multicounts_vs_oracle(ctx, O):
     assert (table.lookup_many(dropped) == 0xFFFFFFFF).all()
 
 
+def test_hash_value_zero_is_a_legal_key(ctx, O):
+    """Even-k palindromes hash to 0 (h ^ h): 0 must be insertable, found, and never confused with
+    an empty slot; a hash that is absent next to it stays a miss."""
+    from spacegraphcats_b200.cdbg.hashing import GpuKmerTable
+    from spacegraphcats_b200.device import pack_sequences
+
+    pal = "ACGT" * 8  # k = 32: its own reverse complement
+    assert O.hash_kmer_py(pal) == 0
+    rng = np.random.default_rng(3)
+    useqs = [rand_seq(rng, 200), pal + "T", rand_seq(rng, 90)]  # unitig 1 holds the palindrome + one more 32-mer
+    ubuf, uoff = pack_sequences(useqs)
+    for side in (False, True):
+        t = GpuKmerTable.from_sequences(ubuf, uoff, 32, ctx=ctx, side=side)
+        assert t[0] == 1 and t[1] is None
+        got = t.lookup_many(np.array([0, 1, 2**64 - 1], np.uint64))
+        assert got.tolist() == [1, 0xFFFFFFFF, 0xFFFFFFFF]
+        rb, ro = pack_sequences([pal, "G" + pal, rand_seq(rng, 64)])
+        lab = t.label_reads(rb, ro, 32)
+        assert lab["ids"][lab["ids_off"][0] : lab["ids_off"][1]].tolist() == [1]
+        assert 1 in lab["ids"][lab["ids_off"][1] : lab["ids_off"][2]].tolist()
+    e = GpuKmerTable.from_pairs(np.array([5], np.uint64), np.array([7], np.uint32), ctx=ctx)
+    assert e[0] is None and e[5] == 7  # an EMPTY slot has key 0 but is not the key 0
+
+
 def test_table_full_is_an_error(ctx):
     from spacegraphcats_b200.device import DeviceTable
     from spacegraphcats_b200._lib import SgcCapacityError
