@@ -255,6 +255,36 @@ int sgc_synth_reads(sgc_ctx* ctx, const uint8_t* d_genome, int64_t glen, int64_t
 int sgc_synth_unitigs(sgc_ctx* ctx, const uint8_t* d_genome, const int64_t* d_cuts, int64_t n, int k,
                       int64_t out_bytes, uint8_t* d_out, int64_t* d_out_off);
 
+/* ---------------------------------------------------------------------------------------------
+ * BBHash (boomphf) minimal perfect hash -- the on-disk form of the reference's index.
+ *
+ * Replaces bbhash.PyMPHF(keys, n, num_threads=4, gamma=1.0) + mphf.save()/load_mphf() as used by
+ * bbhash_table.BBHashTable (reference cdbg/hashing.py:8,30-37; index_cdbg_by_kmer.py:63-64,105):
+ * the dump produced by sgc_mphf_dump is byte-compatible with boomphf's `contigs.mphf`, and
+ * sgc_mphf_order produces `mphf_to_hash` / `mphf_to_value` of `contigs.indices`, so an index
+ * built here loads in an unmodified CPU install.  Lookups of this library never need it.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct sgc_mphf sgc_mphf;
+#define SGC_MPHF_NOT_FOUND 0xFFFFFFFFFFFFFFFFull
+
+/* d_keys: n DISTINCT 64-bit keys on the device (duplicates never settle and end in the final map).
+ * gamma >= 1.0 (reference: 1.0), 2 <= nb_levels <= 64 (boomphf: 25).  Synchronises. */
+int sgc_mphf_build(sgc_ctx* ctx, const uint64_t* d_keys, int64_t n, double gamma, int nb_levels, sgc_mphf** out);
+/* parse a boomphf dump held in host memory (the bytes of a reference `contigs.mphf`) */
+int sgc_mphf_load(sgc_ctx* ctx, const void* h_buf, int64_t bytes, sgc_mphf** out);
+int sgc_mphf_free(sgc_mphf* m);
+/* h_info[0..3] = nelem, nb_levels, lastbitsetrank, keys held by the final map; *h_gamma nullable */
+int sgc_mphf_info(sgc_mphf* m, int64_t* h_info, double* h_gamma);
+/* d_index[i] = MPHF index of d_keys[i]; keys outside the build set give an arbitrary index < nelem or
+ * SGC_MPHF_NOT_FOUND (an MPHF has no membership test; callers compare mphf_to_hash[index]).  Asynchronous. */
+int sgc_mphf_lookup(sgc_mphf* m, const uint64_t* d_keys, int64_t n, uint64_t* d_index);
+/* d_hash_out[index(key)] = key, d_val_out[index(key)] = value for the n == nelem build keys.
+ * SGC_ERR_ARG if a key does not map below nelem.  Synchronises. */
+int sgc_mphf_order(sgc_mphf* m, const uint64_t* d_keys, const uint32_t* d_vals, int64_t n, uint64_t* d_hash_out,
+                   uint32_t* d_val_out);
+int sgc_mphf_dump_bytes(sgc_mphf* m, int64_t* h_bytes);
+int sgc_mphf_dump(sgc_mphf* m, void* h_buf, int64_t bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Time the device BBHash build / lookup / dump at a few key counts (not a bench line)."""
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, ".")
+import __graft_entry__ as g  # noqa: E402
+
+g.build()
+from spacegraphcats_b200.device import DeviceMphf, get_context  # noqa: E402
+
+ctx = get_context(0)
+for lg in [int(a) for a in sys.argv[1:]] or [24, 26, 29]:
+    n = 1 << lg
+    gen = torch.Generator(device="cuda").manual_seed(lg)
+    keys = torch.unique(torch.randint(-(2**63), 2**63 - 1, (n,), dtype=torch.int64, device="cuda", generator=gen))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    m = DeviceMphf.build(ctx, keys)
+    ctx.sync()
+    t1 = time.perf_counter()
+    idx = m.lookup(keys, to_host=False)
+    ctx.sync()
+    t2 = time.perf_counter()
+    raw = m.dumps()
+    t3 = time.perf_counter()
+    print(f"n=2^{lg} ({keys.numel()}): build {1e3*(t1-t0):.1f} ms ({keys.numel()/(t1-t0)/1e6:.0f} M keys/s), "
+          f"lookup {1e3*(t2-t1):.1f} ms ({keys.numel()/(t2-t1)/1e9:.2f} G/s), dump {len(raw)/1e6:.1f} MB in {1e3*(t3-t2):.0f} ms, "
+          f"final {m.info()['n_final']}", flush=True)
+    m.close()
+    del keys, idx
+    torch.cuda.empty_cache()

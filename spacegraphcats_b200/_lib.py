@@ -79,6 +79,14 @@ PROTOTYPES = {
     "sgc_synth_genome": (_i32, [_vp, _vp, _i64, ctypes.c_uint64]),
     "sgc_synth_reads": (_i32, [_vp, _vp, _i64, _i64, _i32, ctypes.c_uint64, _u32, _i32, _vp, _vp]),
     "sgc_synth_unitigs": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp]),
+    "sgc_mphf_build": (_i32, [_vp, _vp, _i64, ctypes.c_double, _i32, ctypes.POINTER(_vp)]),
+    "sgc_mphf_load": (_i32, [_vp, _vp, _i64, ctypes.POINTER(_vp)]),
+    "sgc_mphf_free": (_i32, [_vp]),
+    "sgc_mphf_info": (_i32, [_vp, _pi64, ctypes.POINTER(ctypes.c_double)]),
+    "sgc_mphf_lookup": (_i32, [_vp, _vp, _i64, _vp]),
+    "sgc_mphf_order": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "sgc_mphf_dump_bytes": (_i32, [_vp, _pi64]),
+    "sgc_mphf_dump": (_i32, [_vp, _vp, _i64]),
 }
 
 _lib = None

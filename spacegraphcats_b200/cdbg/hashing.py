@@ -12,7 +12,7 @@ import pickle
 
 import numpy as np
 
-from ..device import DeviceTable, get_context, pack_sequences
+from ..device import DeviceMphf, DeviceTable, get_context, pack_sequences
 from .._lib import SGC_MISS, SGC_MAX_K
 
 UNSET_VALUE = 2**32 - 1  # the reference's BBHashTable "unset" value (index_cdbg_by_kmer.py:24)
@@ -186,13 +186,21 @@ class GpuKmerTable:
 
     # ---- persistence (the reference's on-disk trio, hashing.py:109-130) -------
     def save(self, mphf_filename, array_filename):
-        h, v = self._pairs()
+        """BBHashTable.save: a boomphf dump of the live hashes plus the hash / id arrays in MPHF
+        order, i.e. files the reference's own ``BBHashTable.load`` accepts.  The MPHF is built on
+        the device (sgc_mphf_build); this package's ``load`` only needs the arrays."""
+        self._flush()
+        d_h, d_v = self._dev.export(to_host=False)
+        mphf = DeviceMphf.build(self._dev.ctx, d_h)
+        try:
+            h, v = mphf.order(d_h, d_v) if d_h.numel() else (np.zeros(0, np.uint64), np.zeros(0, np.uint32))
+            raw = mphf.dumps()
+        finally:
+            mphf.close()
         with open(array_filename, "wb") as fp:
             np.savez_compressed(fp, mphf_to_hash=h, mphf_to_value=v)
-        # The reference stores a boomphf dump here; lookups never need it (the arrays carry
-        # the whole map), so a marker file keeps the Snakemake output contract.
         with open(mphf_filename, "wb") as fp:
-            fp.write(b"SGC_B200_NO_MPHF\n%d\n" % len(h))
+            fp.write(raw)
 
     @classmethod
     def load(cls, mphf_filename, array_filename, ctx=None):

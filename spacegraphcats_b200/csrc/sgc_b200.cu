@@ -15,6 +15,7 @@
 //   K5 per-unitig count count_kernel, tile_kernel<K, MODE_LOOKUP> (get_unique_values, hashing.py:67-69)
 //   K6 per-dominator    dom_level_kernel                (count_catlas_matches, hashing.py:71-107)
 //   K7 owner bucketing  partition kernels               (new: hash-range partition across GPUs)
+//   K8 BBHash writer    mphf_* kernels (sgc_mphf.cuh)   (bbhash.PyMPHF + save, the on-disk contigs.mphf)
 //
 // No CPU fallback: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
@@ -25,6 +26,7 @@
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <utility>
@@ -68,6 +70,7 @@ int fail(int code, const char* fmt, ...) {
 #include "sgc_table.cuh"
 #include "sgc_tile.cuh"
 #include "sgc_kernels.cuh"
+#include "sgc_mphf.cuh"
 
 using namespace sgc::dev;
 
@@ -1130,6 +1133,374 @@ int sgc_synth_unitigs(sgc_ctx* c, const uint8_t* d_genome, const int64_t* d_cuts
                                                                                        d_out_off);
     c->launches++;
     CU(cudaGetLastError());
+    return SGC_OK;
+}
+
+// ---------------------------------------------------------------------------- K8: BBHash (boomphf) dump
+}  // extern "C"
+
+struct sgc_mphf {
+    sgc_ctx* ctx = nullptr;
+    double gamma = 1.0;
+    uint64_t nelem = 0, lastbitsetrank = 0;
+    MphfLevels lv{};
+    uint64_t total_words = 0;  // concatenated level words, every level padded to a multiple of 8
+    uint64_t* bits = nullptr;
+    uint64_t* ranks = nullptr;  // total_words / 8
+    uint64_t* final_keys = nullptr;
+    uint64_t* final_vals = nullptr;
+    int64_t n_final = 0;
+};
+
+namespace {
+
+inline uint64_t mphf_nchar(uint64_t size) { return 1 + size / 64; }  // boomphf bitVector: one spare word
+
+// level sizes exactly as boomphf computes them (constructor and load both call this)
+void mphf_level_sizes(uint64_t nelem, double gamma, int nb_levels, MphfLevels& lv) {
+    lv.nb_levels = nb_levels;
+    double gn = gamma * (double)nelem;
+    double proba = nelem ? 1.0 - std::pow((gn - 1.0) / gn, (double)(nelem - 1)) : 0.0;
+    uint64_t domain = (uint64_t)std::ceil((double)nelem * gamma);
+    for (int l = 0; l < nb_levels; ++l) {
+        uint64_t s = nelem ? (((uint64_t)((double)domain * std::pow(proba, (double)l)) + 63) / 64) * 64 : 0;
+        lv.size[l] = s ? s : 64;
+    }
+}
+
+void mphf_layout(sgc_mphf* m) {
+    uint64_t w = 0;
+    for (int l = 0; l < m->lv.nb_levels; ++l) {
+        m->lv.woff[l] = w;
+        w += (mphf_nchar(m->lv.size[l]) + 7) / 8 * 8;
+    }
+    m->total_words = w;
+}
+
+MphfView mphf_view(const sgc_mphf* m) {
+    MphfView v;
+    v.lv = m->lv;
+    v.bits = m->bits;
+    v.ranks = m->ranks;
+    v.final_keys = m->final_keys;
+    v.final_vals = m->final_vals;
+    v.n_final = m->n_final;
+    v.lastbitsetrank = m->lastbitsetrank;
+    return v;
+}
+
+void mphf_release(sgc_mphf* m) {
+    if (!m) return;
+    cudaFree(m->bits);
+    cudaFree(m->ranks);
+    cudaFree(m->final_keys);
+    cudaFree(m->final_vals);
+    delete m;
+}
+
+struct ScopedFree {  // build-time temporaries
+    void* p = nullptr;
+    ~ScopedFree() { if (p) cudaFree(p); }
+};
+
+int mphf_build_impl(sgc_ctx* c, sgc_mphf* m, const uint64_t* d_keys, int64_t n) {
+    const int cap = c->num_sms * 16;
+    cudaStream_t st = c->stream;
+    CU(cudaMalloc(&m->bits, m->total_words * 8));
+    CU(cudaMalloc(&m->ranks, m->total_words / 8 * 8));
+    CU(cudaMemsetAsync(m->bits, 0, m->total_words * 8, st));
+    ScopedFree coll, alive_a, alive_b, counter;
+    uint64_t coll_words = mphf_nchar(m->lv.size[0]);
+    for (int l = 1; l < m->lv.nb_levels; ++l) coll_words = std::max(coll_words, mphf_nchar(m->lv.size[l]));
+    CU(cudaMalloc(&coll.p, coll_words * 8));
+    CU(cudaMemsetAsync(coll.p, 0, coll_words * 8, st));
+    CU(cudaMalloc(&counter.p, 8));
+
+    const uint64_t* cur = d_keys;
+    int64_t n_cur = n;
+    for (int l = 0; l < m->lv.nb_levels - 1 && n_cur > 0; ++l) {
+        uint64_t* lbits = m->bits + m->lv.woff[l];
+        uint64_t size = m->lv.size[l];
+        mphf_mark_kernel<<<grid_for(n_cur, 256, cap), 256, 0, st>>>(cur, n_cur, l, size, (uint32_t*)lbits,
+                                                                   (uint32_t*)coll.p);
+        mphf_settle_kernel<<<grid_for((int64_t)(size / 64), 256, cap), 256, 0, st>>>(lbits, (uint64_t*)coll.p,
+                                                                                  (long long)(size / 64));
+        // survivors alternate between two buffers; the first is sized n, the second after level 0
+        ScopedFree& dst = (l & 1) ? alive_b : alive_a;
+        if (!dst.p) CU(cudaMalloc(&dst.p, (size_t)std::max<int64_t>(n_cur, 1) * 8));
+        CU(cudaMemsetAsync(counter.p, 0, 8, st));
+        mphf_filter_kernel<<<grid_for(n_cur, 256, cap), 256, 0, st>>>(cur, n_cur, l, size, lbits, (uint64_t*)dst.p,
+                                                                     (unsigned long long*)counter.p);
+        c->launches += 3;
+        CU(cudaGetLastError());
+        unsigned long long left = 0;
+        CU(cudaMemcpyAsync(&left, counter.p, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        cur = (const uint64_t*)dst.p;
+        n_cur = (int64_t)left;
+    }
+
+    // rank samples: exclusive scan of the 512-bit block popcounts over the concatenated levels
+    int64_t nblocks = (int64_t)(m->total_words / 8);
+    mphf_block_popc_kernel<<<grid_for(nblocks, 256, cap), 256, 0, st>>>(m->bits, nblocks, m->ranks);
+    c->launches++;
+    size_t tb = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, m->ranks, m->ranks, nblocks, st));
+    TRY(ensure(c, c->cub_tmp, tb));
+    uint64_t last_rank = 0, last_pop = 0;
+    // total set bits = scanned value of the last block + its own popcount (the spare word keeps it zero)
+    CU(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tb, m->ranks, m->ranks, nblocks, st));
+    CU(cudaMemcpyAsync(&last_rank, m->ranks + nblocks - 1, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    {
+        uint64_t h_last[8];
+        CU(cudaMemcpy(h_last, m->bits + (nblocks - 1) * 8, 64, cudaMemcpyDeviceToHost));
+        for (int j = 0; j < 8; ++j) last_pop += (uint64_t)__builtin_popcountll(h_last[j]);
+    }
+    m->lastbitsetrank = last_rank + last_pop;
+
+    // leftovers of the last bitset level: explicit final map, keys ascending, value = position
+    m->n_final = n_cur;
+    if (n_cur > 0) {
+        CU(cudaMalloc(&m->final_keys, (size_t)n_cur * 8));
+        CU(cudaMalloc(&m->final_vals, (size_t)n_cur * 8));
+        CU(cub::DeviceRadixSort::SortKeys(nullptr, tb, cur, m->final_keys, n_cur, 0, 64, st));
+        TRY(ensure(c, c->cub_tmp, tb));
+        CU(cub::DeviceRadixSort::SortKeys(c->cub_tmp.p, tb, cur, m->final_keys, n_cur, 0, 64, st));
+        iota_u64_kernel<<<grid_for(n_cur, 256, cap), 256, 0, st>>>(m->final_vals, n_cur);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(st));
+    return SGC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sgc_mphf_build(sgc_ctx* c, const uint64_t* d_keys, int64_t n, double gamma, int nb_levels, sgc_mphf** out) {
+    if (!c || !out) return fail(SGC_ERR_ARG, "ctx/out is NULL");
+    *out = nullptr;
+    if (n < 0 || (n > 0 && !d_keys)) return fail(SGC_ERR_ARG, "bad key array");
+    if (!(gamma >= 1.0)) return fail(SGC_ERR_ARG, "gamma must be >= 1.0 (got %g)", gamma);
+    if (nb_levels < 2 || nb_levels > MPHF_MAX_LEVELS)
+        return fail(SGC_ERR_ARG, "nb_levels must be in [2, %d] (got %d)", MPHF_MAX_LEVELS, nb_levels);
+    TRY(set_device(c));
+    sgc_mphf* m = new (std::nothrow) sgc_mphf();
+    if (!m) return fail(SGC_ERR_NOMEM, "out of host memory");
+    m->ctx = c;
+    m->gamma = gamma;
+    m->nelem = (uint64_t)n;
+    mphf_level_sizes(m->nelem, gamma, nb_levels, m->lv);
+    mphf_layout(m);
+    int rc = mphf_build_impl(c, m, d_keys, n);
+    if (rc != SGC_OK) {
+        mphf_release(m);
+        return rc;
+    }
+    *out = m;
+    return SGC_OK;
+}
+
+int sgc_mphf_load(sgc_ctx* c, const void* h_buf, int64_t bytes, sgc_mphf** out) {
+    if (!c || !out || !h_buf) return fail(SGC_ERR_ARG, "ctx/buffer/out is NULL");
+    *out = nullptr;
+    const uint8_t* p = (const uint8_t*)h_buf;
+    int64_t off = 0;
+    auto need = [&](int64_t nb) { return nb >= 0 && off + nb <= bytes; };
+    if (!need(28)) return fail(SGC_ERR_ARG, "mphf dump truncated (header)");
+    double gamma;
+    int32_t nb_levels;
+    uint64_t last, nelem;
+    memcpy(&gamma, p, 8);
+    memcpy(&nb_levels, p + 8, 4);
+    memcpy(&last, p + 12, 8);
+    memcpy(&nelem, p + 20, 8);
+    off = 28;
+    if (nb_levels < 2 || nb_levels > MPHF_MAX_LEVELS) return fail(SGC_ERR_ARG, "mphf dump: nb_levels %d", nb_levels);
+    TRY(set_device(c));
+    sgc_mphf* m = new (std::nothrow) sgc_mphf();
+    if (!m) return fail(SGC_ERR_NOMEM, "out of host memory");
+    m->ctx = c;
+    m->gamma = gamma;
+    m->nelem = nelem;
+    m->lastbitsetrank = last;
+    m->lv.nb_levels = nb_levels;
+    // first pass: level geometry
+    struct Span { int64_t words_at, nchar, ranks_at, nranks; };
+    std::vector<Span> spans((size_t)nb_levels);
+    for (int l = 0; l < nb_levels; ++l) {
+        uint64_t size, nchar, nranks;
+        if (!need(16)) { mphf_release(m); return fail(SGC_ERR_ARG, "mphf dump truncated (level %d)", l); }
+        memcpy(&size, p + off, 8);
+        memcpy(&nchar, p + off + 8, 8);
+        off += 16;
+        if (size % 64 || nchar != mphf_nchar(size) || !need((int64_t)nchar * 8 + 8)) {
+            mphf_release(m);
+            return fail(SGC_ERR_ARG, "mphf dump: level %d has size %llu, %llu words", l, (unsigned long long)size,
+                        (unsigned long long)nchar);
+        }
+        spans[l].words_at = off;
+        spans[l].nchar = (int64_t)nchar;
+        off += (int64_t)nchar * 8;
+        memcpy(&nranks, p + off, 8);
+        off += 8;
+        if (nranks != (nchar + 7) / 8 || !need((int64_t)nranks * 8)) {
+            mphf_release(m);
+            return fail(SGC_ERR_ARG, "mphf dump: level %d has %llu rank samples", l, (unsigned long long)nranks);
+        }
+        spans[l].ranks_at = off;
+        spans[l].nranks = (int64_t)nranks;
+        off += (int64_t)nranks * 8;
+        m->lv.size[l] = size;
+    }
+    mphf_layout(m);
+    uint64_t nfinal = 0;
+    if (!need(8)) { mphf_release(m); return fail(SGC_ERR_ARG, "mphf dump truncated (final map)"); }
+    memcpy(&nfinal, p + off, 8);
+    off += 8;
+    if (nfinal > (uint64_t)(bytes - off) / 16 || off + (int64_t)nfinal * 16 != bytes) {
+        mphf_release(m);
+        return fail(SGC_ERR_ARG, "mphf dump: final map of %llu entries does not match the file size",
+                    (unsigned long long)nfinal);
+    }
+    std::vector<uint64_t> hb(m->total_words, 0), hr(m->total_words / 8, 0);
+    for (int l = 0; l < nb_levels; ++l) {
+        memcpy(hb.data() + m->lv.woff[l], p + spans[l].words_at, (size_t)spans[l].nchar * 8);
+        memcpy(hr.data() + m->lv.woff[l] / 8, p + spans[l].ranks_at, (size_t)spans[l].nranks * 8);
+    }
+    std::vector<std::pair<uint64_t, uint64_t>> fin((size_t)nfinal);
+    for (uint64_t i = 0; i < nfinal; ++i) {
+        memcpy(&fin[i].first, p + off + i * 16, 8);
+        memcpy(&fin[i].second, p + off + i * 16 + 8, 8);
+    }
+    std::sort(fin.begin(), fin.end());
+    auto bail = [&](cudaError_t e, const char* what) {
+        mphf_release(m);
+        return fail(SGC_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc(&m->bits, m->total_words * 8)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&m->ranks, m->total_words)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMemcpy(m->bits, hb.data(), m->total_words * 8, cudaMemcpyHostToDevice)) != cudaSuccess)
+        return bail(e, "cudaMemcpy");
+    if ((e = cudaMemcpy(m->ranks, hr.data(), m->total_words, cudaMemcpyHostToDevice)) != cudaSuccess)
+        return bail(e, "cudaMemcpy");
+    m->n_final = (int64_t)nfinal;
+    if (nfinal) {
+        std::vector<uint64_t> fk(nfinal), fv(nfinal);
+        for (uint64_t i = 0; i < nfinal; ++i) { fk[i] = fin[i].first; fv[i] = fin[i].second; }
+        if ((e = cudaMalloc(&m->final_keys, nfinal * 8)) != cudaSuccess) return bail(e, "cudaMalloc");
+        if ((e = cudaMalloc(&m->final_vals, nfinal * 8)) != cudaSuccess) return bail(e, "cudaMalloc");
+        if ((e = cudaMemcpy(m->final_keys, fk.data(), nfinal * 8, cudaMemcpyHostToDevice)) != cudaSuccess)
+            return bail(e, "cudaMemcpy");
+        if ((e = cudaMemcpy(m->final_vals, fv.data(), nfinal * 8, cudaMemcpyHostToDevice)) != cudaSuccess)
+            return bail(e, "cudaMemcpy");
+    }
+    *out = m;
+    return SGC_OK;
+}
+
+int sgc_mphf_free(sgc_mphf* m) {
+    if (!m) return SGC_OK;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    mphf_release(m);
+    return SGC_OK;
+}
+
+int sgc_mphf_info(sgc_mphf* m, int64_t* h_info, double* h_gamma) {
+    if (!m || !h_info) return fail(SGC_ERR_ARG, "mphf/info is NULL");
+    h_info[0] = (int64_t)m->nelem;
+    h_info[1] = m->lv.nb_levels;
+    h_info[2] = (int64_t)m->lastbitsetrank;
+    h_info[3] = m->n_final;
+    if (h_gamma) *h_gamma = m->gamma;
+    return SGC_OK;
+}
+
+int sgc_mphf_lookup(sgc_mphf* m, const uint64_t* d_keys, int64_t n, uint64_t* d_index) {
+    if (!m) return fail(SGC_ERR_ARG, "mphf is NULL");
+    if (n < 0) return fail(SGC_ERR_ARG, "n < 0");
+    if (n == 0) return SGC_OK;
+    sgc_ctx* c = m->ctx;
+    TRY(set_device(c));
+    mphf_lookup_kernel<<<grid_for(n, 256, c->num_sms * 16), 256, 0, c->stream>>>(mphf_view(m), d_keys, n, d_index);
+    c->launches++;
+    CU(cudaGetLastError());
+    return SGC_OK;
+}
+
+int sgc_mphf_order(sgc_mphf* m, const uint64_t* d_keys, const uint32_t* d_vals, int64_t n, uint64_t* d_hash_out,
+                   uint32_t* d_val_out) {
+    if (!m) return fail(SGC_ERR_ARG, "mphf is NULL");
+    if (n != (int64_t)m->nelem) return fail(SGC_ERR_ARG, "n (%lld) != nelem (%llu)", (long long)n,
+                                            (unsigned long long)m->nelem);
+    if (n == 0) return SGC_OK;
+    sgc_ctx* c = m->ctx;
+    TRY(set_device(c));
+    TRY(zero_scalars(c));
+    mphf_order_kernel<<<grid_for(n, 256, c->num_sms * 16), 256, 0, c->stream>>>(
+        mphf_view(m), d_keys, d_vals, n, m->nelem, d_hash_out, d_val_out, &c->d_scal->n_miss);
+    c->launches++;
+    CU(cudaGetLastError());
+    TRY(fetch_scalars(c));
+    if (c->h_scal->n_miss)
+        return fail(SGC_ERR_ARG, "%llu keys are not in the build set of this mphf", c->h_scal->n_miss);
+    return SGC_OK;
+}
+
+int sgc_mphf_dump_bytes(sgc_mphf* m, int64_t* h_bytes) {
+    if (!m || !h_bytes) return fail(SGC_ERR_ARG, "mphf/out is NULL");
+    int64_t b = 28;
+    for (int l = 0; l < m->lv.nb_levels; ++l) {
+        uint64_t nchar = mphf_nchar(m->lv.size[l]);
+        b += 16 + (int64_t)nchar * 8 + 8 + (int64_t)((nchar + 7) / 8) * 8;
+    }
+    b += 8 + m->n_final * 16;
+    *h_bytes = b;
+    return SGC_OK;
+}
+
+int sgc_mphf_dump(sgc_mphf* m, void* h_buf, int64_t bytes) {
+    if (!m || !h_buf) return fail(SGC_ERR_ARG, "mphf/buffer is NULL");
+    int64_t want = 0;
+    TRY(sgc_mphf_dump_bytes(m, &want));
+    if (bytes != want) return fail(SGC_ERR_ARG, "dump buffer is %lld bytes, need %lld", (long long)bytes, (long long)want);
+    sgc_ctx* c = m->ctx;
+    TRY(set_device(c));
+    CU(cudaStreamSynchronize(c->stream));
+    std::vector<uint64_t> hb(m->total_words), hr(m->total_words / 8);
+    CU(cudaMemcpy(hb.data(), m->bits, m->total_words * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(hr.data(), m->ranks, m->total_words, cudaMemcpyDeviceToHost));
+    uint8_t* p = (uint8_t*)h_buf;
+    int64_t off = 0;
+    auto put = [&](const void* src, size_t nb) { memcpy(p + off, src, nb); off += (int64_t)nb; };
+    int32_t nb_levels = m->lv.nb_levels;
+    put(&m->gamma, 8);
+    put(&nb_levels, 4);
+    put(&m->lastbitsetrank, 8);
+    put(&m->nelem, 8);
+    for (int l = 0; l < nb_levels; ++l) {
+        uint64_t size = m->lv.size[l], nchar = mphf_nchar(size), nranks = (nchar + 7) / 8;
+        put(&size, 8);
+        put(&nchar, 8);
+        put(hb.data() + m->lv.woff[l], nchar * 8);
+        put(&nranks, 8);
+        put(hr.data() + m->lv.woff[l] / 8, nranks * 8);
+    }
+    uint64_t nf = (uint64_t)m->n_final;
+    put(&nf, 8);
+    if (nf) {
+        std::vector<uint64_t> fk(nf), fv(nf);
+        CU(cudaMemcpy(fk.data(), m->final_keys, nf * 8, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(fv.data(), m->final_vals, nf * 8, cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < nf; ++i) {
+            put(&fk[i], 8);
+            put(&fv[i], 8);
+        }
+    }
     return SGC_OK;
 }
 

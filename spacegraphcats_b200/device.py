@@ -232,8 +232,9 @@ class DeviceTable:
         check(self._L.sgc_table_stats(self._h, ctypes.byref(live), ctypes.byref(multi), ctypes.byref(mx)))
         return live.value, multi.value, mx.value
 
-    def export(self):
-        """All live (hash, id) pairs sorted by hash -> (uint64[n], uint32[n]) on the host."""
+    def export(self, to_host=True):
+        """All live (hash, id) pairs sorted by hash -> (uint64[n], uint32[n]) on the host
+        (``to_host=False``: int64 / int32 CUDA tensors holding the same bits)."""
         torch = _torch()
         c = self.ctx
         live, _, _ = self.stats()
@@ -241,6 +242,8 @@ class DeviceTable:
         d_v = c.empty(max(live, 1), torch.int32)
         n = ctypes.c_int64(0)
         check(self._L.sgc_table_export(self._h, c.ptr(d_h), c.ptr(d_v), live, ctypes.byref(n)))
+        if not to_host:
+            return d_h[: n.value], d_v[: n.value]
         return c.to_host(d_h[: n.value], np.uint64), c.to_host(d_v[: n.value], np.uint32)
 
     # ---- K3 --------------------------------------------------------------
@@ -342,4 +345,83 @@ class DeviceTable:
         return out
 
 
-__all__ = ["Context", "DeviceTable", "get_context", "pack_sequences", "kmer_counts", "SGC_MISS"]
+class DeviceMphf:
+    """BBHash (boomphf) minimal perfect hash built on the GPU (``sgc_mphf``): the writer of the
+    reference's ``contigs.mphf`` (bbhash.PyMPHF + save; reference cdbg/hashing.py:8, the
+    BBHashTable it instantiates at index_cdbg_by_kmer.py:63-64)."""
+
+    NOT_FOUND = 0xFFFFFFFFFFFFFFFF
+
+    def __init__(self, ctx, handle):
+        self.ctx = ctx
+        self._L = ctx._L
+        self._h = handle
+
+    @classmethod
+    def build(cls, ctx, keys, gamma=1.0, nb_levels=25):
+        """keys: distinct uint64 hashes (numpy array or CUDA int64 tensor)."""
+        d_k = ctx.to_device(keys, np.uint64)
+        h = ctypes.c_void_p()
+        check(ctx._L.sgc_mphf_build(ctx._h, ctx.ptr(d_k), d_k.numel(), float(gamma), int(nb_levels), ctypes.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def loads(cls, ctx, raw):
+        """Parse the bytes of a boomphf dump (a reference ``contigs.mphf``)."""
+        raw = bytes(raw)
+        h = ctypes.c_void_p()
+        check(ctx._L.sgc_mphf_load(ctx._h, ctypes.c_char_p(raw), len(raw), ctypes.byref(h)))
+        return cls(ctx, h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sgc_mphf_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        a = (ctypes.c_int64 * 4)()
+        g = ctypes.c_double(0)
+        check(self._L.sgc_mphf_info(self._h, a, ctypes.byref(g)))
+        return {"nelem": a[0], "nb_levels": a[1], "lastbitsetrank": a[2], "n_final": a[3], "gamma": g.value}
+
+    def __len__(self):
+        return self.info()["nelem"]
+
+    def lookup(self, keys, to_host=True):
+        """MPHF index of every key (NOT_FOUND, or an arbitrary index, for keys outside the build set)."""
+        torch = _torch()
+        c = self.ctx
+        d_k = c.to_device(keys, np.uint64)
+        d_o = c.empty(d_k.numel(), torch.int64)
+        check(self._L.sgc_mphf_lookup(self._h, c.ptr(d_k), d_k.numel(), c.ptr(d_o)))
+        return c.to_host(d_o, np.uint64) if to_host else d_o
+
+    def order(self, keys, values):
+        """(mphf_to_hash uint64[n], mphf_to_value uint32[n]) for the build keys and their values."""
+        torch = _torch()
+        c = self.ctx
+        d_k = c.to_device(keys, np.uint64)
+        d_v = c.to_device(values, np.uint32)
+        if d_k.numel() != d_v.numel():
+            raise ValueError("keys and values differ in length")
+        d_oh = c.empty(d_k.numel(), torch.int64)
+        d_ov = c.empty(d_k.numel(), torch.int32)
+        check(self._L.sgc_mphf_order(self._h, c.ptr(d_k), c.ptr(d_v), d_k.numel(), c.ptr(d_oh), c.ptr(d_ov)))
+        return c.to_host(d_oh, np.uint64), c.to_host(d_ov, np.uint32)
+
+    def dumps(self):
+        """The boomphf dump (what ``mphf.save`` writes)."""
+        n = ctypes.c_int64(0)
+        check(self._L.sgc_mphf_dump_bytes(self._h, ctypes.byref(n)))
+        buf = ctypes.create_string_buffer(n.value)
+        check(self._L.sgc_mphf_dump(self._h, buf, n.value))
+        return buf.raw
+
+
+__all__ = ["Context", "DeviceTable", "DeviceMphf", "get_context", "pack_sequences", "kmer_counts", "SGC_MISS"]

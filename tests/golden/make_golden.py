@@ -16,6 +16,8 @@ against it:
   dory_k21_contigs.indices.npz <- .../catlas.dory_k21/contigs.indices  (verbatim; written
                                   by the reference's BBHashTable.save: mphf_to_hash u64[n],
                                   mphf_to_value u32[n] -- 212,475 (hash -> unitig id) pairs)
+  dory_k21_contigs.mphf        <- .../catlas.dory_k21/contigs.mphf  (verbatim; the boomphf dump written by the
+                                  reference's BBHashTable.save: gamma 1.0, 25 levels, 212,475 keys)
   dory_k21_contigs.sizes.json  <- .../catlas.dory_k21/contigs.sizes (pickle (k, {id: n_kmers}))
   dory_k21_r1/catlas.csv, first_doms.txt  <- .../catlas.dory_k21_r1/  (verbatim)
   dory_k21_r1_search/*         <- .../catlas.dory_k21_r1_search_oh0/  (expected query outputs)
@@ -62,6 +64,7 @@ def main():
     with open(out("dory_k21_min_hashval.json"), "w") as fp:  # sourmash n=1 MinHash (seed 42) per unitig
         json.dump({str(i): int(v) for i, v in mins}, fp)
     shutil.copyfile(ref("tests/test-data/catlas.dory_k21/contigs.indices"), out("dory_k21_contigs.indices.npz"))
+    shutil.copyfile(ref("tests/test-data/catlas.dory_k21/contigs.mphf"), out("dory_k21_contigs.mphf"))
     with open(ref("tests/test-data/catlas.dory_k21/contigs.sizes"), "rb") as fp:
         k, sizes = pickle.load(fp)
     with open(out("dory_k21_contigs.sizes.json"), "w") as fp:

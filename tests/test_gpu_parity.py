@@ -943,3 +943,119 @@ def test_hypothesis_hash_and_label_vs_oracle(ctx, O):
         assert np.array_equal(lab["ids_off"], o_off) and np.array_equal(lab["ids"], o_ids)
 
     run()
+
+
+# ---------------------------------------------------------------- K8: BBHash (boomphf) writer
+@pytest.fixture(scope="module")
+def dory_dump():
+    return open(golden_path("dory_k21_contigs.mphf"), "rb").read()
+
+
+def test_mphf_device_build_is_byte_identical_to_reference_dump(ctx, dory, dory_dump):
+    """The reference's contigs.mphf and contigs.indices for dory, rebuilt on the GPU from the keys."""
+    from spacegraphcats_b200.device import DeviceMphf
+
+    _, ref_h, ref_v, _ = dory
+    perm = np.random.default_rng(11).permutation(len(ref_h))
+    m = DeviceMphf.build(ctx, ref_h[perm])
+    assert m.info() == {"nelem": 212475, "nb_levels": 25, "lastbitsetrank": 212475, "n_final": 0, "gamma": 1.0}
+    assert m.dumps() == dory_dump
+    oh, ov = m.order(ref_h[perm], ref_v[perm])
+    assert np.array_equal(oh, ref_h) and np.array_equal(ov, ref_v)
+    m.close()
+
+
+def test_mphf_device_lookup_through_reference_dump(ctx, dory, dory_dump):
+    """mphf_to_hash[i] must look up to i through the bitsets the reference wrote."""
+    from spacegraphcats_b200.device import DeviceMphf
+
+    _, ref_h, _, _ = dory
+    m = DeviceMphf.loads(ctx, dory_dump)
+    assert np.array_equal(m.lookup(ref_h), np.arange(len(ref_h), dtype=np.uint64))
+    assert m.dumps() == dory_dump
+    m.close()
+
+
+def test_index_save_writes_the_reference_files(ctx, dory, dory_index, dory_dump, tmp_path):
+    """build_mphf from the unitig sequences + MPHF_KmerIndex.save == the files the reference wrote
+    (contigs.mphf byte for byte, contigs.indices array for array, contigs.sizes)."""
+    import pickle
+    from spacegraphcats_b200.cdbg.hashing import MPHF_KmerIndex
+
+    _, ref_h, ref_v, ref_sizes = dory
+    dory_index.save(str(tmp_path))
+    assert open(tmp_path / "contigs.mphf", "rb").read() == dory_dump
+    with np.load(tmp_path / "contigs.indices") as z:
+        assert sorted(z.files) == ["mphf_to_hash", "mphf_to_value"]
+        assert z["mphf_to_hash"].dtype == np.uint64 and z["mphf_to_value"].dtype == np.uint32
+        assert np.array_equal(z["mphf_to_hash"], ref_h) and np.array_equal(z["mphf_to_value"], ref_v)
+    with open(tmp_path / "contigs.sizes", "rb") as fp:
+        k, sizes = pickle.load(fp)
+    assert k == 21 and sizes == ref_sizes
+    again = MPHF_KmerIndex.from_directory(str(tmp_path))
+    assert len(again.table) == len(ref_h) and again.table[int(ref_h[5])] == int(ref_v[5])
+
+
+@pytest.mark.parametrize("n,levels,gamma", [(0, 25, 1.0), (1, 25, 1.0), (2, 25, 1.0), (65, 25, 1.0), (5000, 4, 1.0),
+                                            (5000, 2, 1.0), (30000, 25, 2.0), (100003, 25, 1.0)])
+def test_mphf_device_vs_oracle(ctx, n, levels, gamma):
+    from oracle import bbhash
+    from spacegraphcats_b200.device import DeviceMphf
+
+    rng = np.random.default_rng(n + levels)
+    keys = np.unique(rng.integers(0, 2**64, size=n, dtype=np.uint64))
+    want = bbhash.Mphf.build(keys, gamma=gamma, nb_levels=levels)
+    m = DeviceMphf.build(ctx, keys, gamma=gamma, nb_levels=levels)
+    assert m.info()["n_final"] == len(want.final)
+    assert m.dumps() == want.dumps()
+    idx = m.lookup(keys)
+    assert np.array_equal(idx, want.lookup(keys))
+    assert sorted(idx.tolist()) == list(range(len(keys)))
+    others = rng.integers(0, 2**64, size=1000, dtype=np.uint64)
+    assert np.array_equal(m.lookup(others), want.lookup(others))  # an MPHF answers for foreign keys too
+    m2 = DeviceMphf.loads(ctx, m.dumps())
+    assert np.array_equal(m2.lookup(keys), idx)
+    m.close(), m2.close()
+
+
+def test_mphf_large_is_a_bijection(ctx):
+    """Size-independent property at 2^26 keys: indices are exactly a permutation of 0..n-1."""
+    import torch
+    from spacegraphcats_b200.device import DeviceMphf
+
+    n = 1 << 26
+    g = torch.Generator(device="cuda").manual_seed(5)
+    keys = torch.randint(-(2**63), 2**63 - 1, (n,), dtype=torch.int64, device="cuda", generator=g)
+    keys = torch.unique(keys)
+    m = DeviceMphf.build(ctx, keys)
+    info = m.info()
+    assert info["nelem"] == keys.numel() and info["lastbitsetrank"] + info["n_final"] == keys.numel()
+    idx = m.lookup(keys, to_host=False)
+    ctx.sync()
+    srt = torch.sort(idx).values
+    assert torch.equal(srt, torch.arange(keys.numel(), dtype=torch.int64, device="cuda"))
+    m.close()
+
+
+def test_mphf_error_paths(ctx, dory_dump):
+    from spacegraphcats_b200._lib import SgcError
+    from spacegraphcats_b200.device import DeviceMphf
+
+    keys = np.arange(1, 1001, dtype=np.uint64)
+    with pytest.raises(SgcError):
+        DeviceMphf.build(ctx, keys, gamma=0.5)
+    with pytest.raises(SgcError):
+        DeviceMphf.build(ctx, keys, nb_levels=1)
+    with pytest.raises(SgcError):
+        DeviceMphf.loads(ctx, dory_dump[:-1])
+    with pytest.raises(SgcError):
+        DeviceMphf.loads(ctx, dory_dump[:1000])
+    with pytest.raises(SgcError):
+        DeviceMphf.loads(ctx, b"SGC_B200_NO_MPHF\n1\n")
+    m = DeviceMphf.build(ctx, keys)
+    with pytest.raises(SgcError):
+        m.order(keys[:10], np.zeros(10, np.uint32))  # n != nelem
+    # duplicate keys never settle: they end in the final map, the build still terminates
+    d = DeviceMphf.build(ctx, np.array([7, 7, 9], np.uint64))
+    assert d.info()["n_final"] == 2
+    m.close(), d.close()

@@ -273,3 +273,44 @@ def test_sourmash_min_hashval_all_unitigs():
     assert len(want) == 736
     for r in recs[::7] + recs[-3:]:
         assert min(O.minhash_sequence_py(r.sequence, 21)) == want[int(r.name)], r.name
+
+
+# ---- BBHash (boomphf) restatement, pinned on the reference's own contigs.mphf + contigs.indices ----
+@pytest.fixture(scope="module")
+def dory_mphf():
+    from oracle import bbhash
+
+    raw = open(golden_path("dory_k21_contigs.mphf"), "rb").read()
+    with np.load(golden_path("dory_k21_contigs.indices.npz")) as z:
+        keys, vals = z["mphf_to_hash"].astype(np.uint64), z["mphf_to_value"]
+    return bbhash, raw, keys, vals
+
+
+def test_bbhash_lookup_reproduces_reference_order(dory_mphf):
+    # mphf_to_hash[i] is the key whose MPHF index is i (BBHashTable.__setitem__): looking every key up
+    # through the level bitsets of the reference's dump must give 0..n-1 in order.
+    bbhash, raw, keys, _ = dory_mphf
+    m = bbhash.Mphf.loads(raw)
+    assert (m.gamma, m.nb_levels, m.nelem, m.lastbitsetrank) == (1.0, 25, 212475, 212475)
+    assert np.array_equal(m.lookup(keys), np.arange(len(keys), dtype=np.uint64))
+    assert m.dumps() == raw
+
+
+def test_bbhash_build_is_byte_identical_to_reference_dump(dory_mphf):
+    bbhash, raw, keys, _ = dory_mphf
+    shuffled = np.random.default_rng(7).permutation(keys)  # construction is order independent
+    assert bbhash.Mphf.build(shuffled, gamma=1.0, nb_levels=25).dumps() == raw
+
+
+def test_bbhash_small_sets_and_final_map():
+    from oracle import bbhash
+
+    rng = np.random.default_rng(3)
+    for n, levels in ((0, 25), (1, 25), (2, 25), (65, 25), (5000, 4), (5000, 2)):
+        keys = np.unique(rng.integers(0, 2**63, size=n, dtype=np.uint64))
+        m = bbhash.Mphf.build(keys, nb_levels=levels)
+        idx = m.lookup(keys)
+        assert sorted(idx.tolist()) == list(range(len(keys)))
+        assert (len(m.final) > 0) == (levels < 25 and n == 5000)
+        again = bbhash.Mphf.loads(m.dumps())
+        assert np.array_equal(again.lookup(keys), idx)
