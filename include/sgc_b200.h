@@ -285,6 +285,33 @@ int sgc_mphf_order(sgc_mphf* m, const uint64_t* d_keys, const uint32_t* d_vals, 
 int sgc_mphf_dump_bytes(sgc_mphf* m, int64_t* h_bytes);
 int sgc_mphf_dump(sgc_mphf* m, void* h_buf, int64_t bytes);
 
+/* ---------------------------------------------------------------------------------------------
+ * Host feeder for read labelling (no device work; all pointers are host pointers).
+ *
+ * Stands in for the reference's pure-Python BgzfReader (utils/bgzf/bgzf.py:458-741), its record
+ * iterators (search/search_utils.py:67-154: records and the position of each record's header line)
+ * and the mate-pairing test of cdbg/index_reads.py:124-141.  n_threads <= 0 = all hardware threads.
+ * --------------------------------------------------------------------------------------------- */
+/* Walk the BGZF block headers: compressed start and inflated size (ISIZE) of every block.
+ * cap = 0 with NULL arrays only counts.  SGC_ERR_ARG if the buffer is not a sequence of BGZF blocks. */
+int sgc_bgzf_index(const uint8_t* h_raw, int64_t raw_bytes, int64_t* h_cstart, int64_t* h_usize, int64_t cap,
+                   int64_t* h_nblocks, int64_t* h_total_bytes);
+/* Inflate all blocks in parallel into h_out (out_bytes = sum of h_usize); CRC32 of every block is checked. */
+int sgc_bgzf_inflate(const uint8_t* h_raw, int64_t raw_bytes, const int64_t* h_cstart, const int64_t* h_usize,
+                     int64_t nblocks, int n_threads, uint8_t* h_out, int64_t out_bytes);
+/* FASTA ('>') or 4-line FASTQ ('@') text: h_info[0..2] = records, total sequence bytes, format (0 FASTA, 1 FASTQ).
+ * SGC_ERR_ARG: "unknown start chr", or a FASTQ record that is not '@' ... '+' ... */
+int sgc_reads_count(const uint8_t* h_data, int64_t n, int n_threads, int64_t* h_info);
+/* h_rec_pos[r] = position of record r's header line; [h_name_lo[r], h_name_hi[r]) = its name inside
+ * h_data (header line stripped, marker removed); h_seq_off[nrec+1] / h_seq = the packed sequences
+ * (every sequence line stripped of surrounding whitespace), i.e. the (seq, off) pair sgc_label_reads takes. */
+int sgc_reads_scan(const uint8_t* h_data, int64_t n, int n_threads, int64_t nrec, int64_t seq_bytes,
+                   int64_t* h_rec_pos, int64_t* h_name_lo, int64_t* h_name_hi, int64_t* h_seq_off, uint8_t* h_seq);
+/* h_last[i] = latest earlier record with h_elig set (-1: none), h_paired[i] = record i is that record's
+ * mate ("x/1" then "x/2", or two equal non-empty names).  ignore_paired: all 0 / -1. */
+int sgc_reads_pair_flags(const uint8_t* h_data, const int64_t* h_name_lo, const int64_t* h_name_hi,
+                         const uint8_t* h_elig, int64_t nrec, int ignore_paired, uint8_t* h_paired, int64_t* h_last);
+
 #ifdef __cplusplus
 }
 #endif

@@ -411,6 +411,46 @@ def read_records(path):
     return recs
 
 
+def iterate_records(data):
+    """search/search_utils.py:67-154 (iterate_bgzf, my_fasta_iter, my_fastq_iter) over an in-memory
+    byte string: yields (Record, position of the record's first line).  ``tell()`` of the reference's
+    reader is the byte position here (the BGZF virtual offset is derived from it separately)."""
+    data = bytes(data)
+    lines, starts, pos = [], [], 0
+    while pos < len(data):  # readline()
+        e = data.find(b"\n", pos)
+        e = len(data) if e < 0 else e + 1
+        lines.append(data[pos:e].decode("ascii"))
+        starts.append(pos)
+        pos = e
+    if not data:
+        return
+    ch = chr(data[0])
+    if ch == ">":
+        i = 0
+        while i < len(lines):
+            line = lines[i].strip()
+            if not line.startswith(">"):
+                raise IOError("Bad FASTA format: no '>' at beginning of line: {}".format(line))
+            name = line[1:].strip()
+            j = i + 1
+            parts = []
+            while j < len(lines) and not lines[j].startswith(">"):
+                parts.append(lines[j].strip())
+                j += 1
+            yield Record(name, "".join(parts)), starts[i]
+            i = j
+    elif ch == "@":
+        i = 0
+        while i + 3 < len(lines):
+            assert lines[i].startswith("@"), lines[i]
+            assert lines[i + 2].strip() == "+"
+            yield Record(lines[i].strip()[1:], lines[i + 1].strip(), lines[i + 3].strip()), starts[i]
+            i += 4
+    else:
+        raise Exception("unknown start chr {}".format(ch))
+
+
 def read_unitigs_tsv(path):
     op = gzip.open if str(path).endswith(".gz") else open
     recs = []

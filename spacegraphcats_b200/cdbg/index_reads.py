@@ -7,6 +7,7 @@ pairing rules (:124-141), the too-short skip (:143-144), the sqlite schema (:72,
 the exit codes are reproduced on the host in record order.
 """
 import argparse
+import ctypes
 import os
 import sqlite3
 import sys
@@ -14,6 +15,7 @@ import time
 
 import numpy as np
 
+from .._lib import check, lib
 from ..utils import bgzf
 from .hashing import MPHF_KmerIndex
 
@@ -22,33 +24,24 @@ BATCH_READS = 1 << 22
 
 
 def pair_flags(names, elig, ignore_paired=False):
-    """Vectorised pairing test of index_reads.py:124-141 for every record: is it the mate of
-    ``last_record`` (the latest earlier record that was long enough)?  -> (paired bool[n], last int64[n]).
-    Name comparisons go through 64-bit string hashes and every positive is re-checked on the strings."""
+    """The pairing test of index_reads.py:124-141 for every record: is it the mate of ``last_record``
+    (the latest earlier record that was long enough)?  -> (paired bool[n], last int64[n]).
+    ``names``: a ``bgzf.NameTable`` (byte ranges of the read file) or a list of str; the comparison
+    itself is native (sgc_reads_pair_flags)."""
+    if not isinstance(names, bgzf.NameTable):
+        names = bgzf.NameTable.from_strings(names)
     n = len(names)
-    idx = np.where(elig, np.arange(n, dtype=np.int64), -1)
+    paired = np.zeros(n, np.uint8)
     last = np.full(n, -1, np.int64)
-    if n > 1 and not ignore_paired:
-        last[1:] = np.maximum.accumulate(idx)[:-1]
-    if n == 0 or ignore_paired:
-        return np.zeros(n, bool), last
-    h_full = np.fromiter((hash(s) for s in names), np.int64, n)
-    h_base = np.fromiter((hash(s[:-2]) for s in names), np.int64, n)
-    e1 = np.fromiter((s.endswith("/1") for s in names), bool, n)
-    e2 = np.fromiter((s.endswith("/2") for s in names), bool, n)
-    nlen = np.fromiter((len(s) for s in names), np.int64, n)
-    j = np.maximum(last, 0)
-    slash = e1[j] & e2
-    cand = (last >= 0) & np.where(slash, (h_base[j] == h_base) & (nlen[j] > 2), (h_full[j] == h_full) & (nlen[j] > 0))
-    for i in np.flatnonzero(cand).tolist():  # exactness: hashes only pre-filter
-        a, b = names[last[i]], names[i]
-        if a.endswith("/1") and b.endswith("/2"):
-            ok = a[:-2] == b[:-2] and len(a) > 2
-        else:
-            ok = a == b and bool(a)
-        if not ok:
-            cand[i] = False
-    return cand, last
+    if n:
+        data = np.ascontiguousarray(names.data, np.uint8)
+        lo = np.ascontiguousarray(names.lo, np.int64)
+        hi = np.ascontiguousarray(names.hi, np.int64)
+        el = np.ascontiguousarray(elig, np.uint8)
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+        check(lib().sgc_reads_pair_flags(vp(data), vp(lo), vp(hi), vp(el), n, int(bool(ignore_paired)), vp(paired),
+                                         vp(last)))
+    return paired.astype(bool), last
 
 
 def _expand(lo, hi):
@@ -86,8 +79,10 @@ def rows_from_labels(names, lens, offsets, ids_off, ids, ksize, ignore_paired=Fa
     rid_s, rrec_s = ids[pos_s], sel[simple][own_s]
     pos_m, own_m = _expand(lo[~simple], hi[~simple])
     if len(pos_m):
-        key = np.unique(np.stack([sel[~simple][own_m], ids[pos_m]], 1), axis=0)  # union per record
-        rrec_m, rid_m = key[:, 0], key[:, 1]
+        key = (sel[~simple][own_m] << 32) | ids[pos_m]  # union per record (ids are < 2^32)
+        key.sort()
+        key = key[np.concatenate([[True], key[1:] != key[:-1]])]
+        rrec_m, rid_m = key >> 32, key & 0xFFFFFFFF
     else:
         rrec_m, rid_m = np.zeros(0, np.int64), np.zeros(0, np.int64)
     rrec = np.concatenate([rrec_s, rrec_m])

@@ -5,6 +5,8 @@
 //   sgc_table.cuh   table primitives (probe sequence, CAS insert with build_mphf semantics, lookup)
 //   sgc_tile.cuh    segment staging + the warp-autonomous tile kernel (all fused modes)
 //   sgc_kernels.cuh plan / stand-alone table / label-tail / dominator / K7 / generator kernels
+//   sgc_mphf.cuh    BBHash (boomphf) level construction, rank samples, lookup
+//   sgc_feed.hpp    host-only feeder (BGZF inflate, FASTA/FASTQ scan, mate pairing)
 // See DESIGN.md for the data layout.
 //
 //   K1 kmer hash        tile_kernel<K, MODE_HASH>       (khmer get_kmer_hashes, cdbg/hashing.py:14-20)
@@ -1136,8 +1138,11 @@ int sgc_synth_unitigs(sgc_ctx* c, const uint8_t* d_genome, const int64_t* d_cuts
     return SGC_OK;
 }
 
-// ---------------------------------------------------------------------------- K8: BBHash (boomphf) dump
 }  // extern "C"
+
+#include "sgc_feed.hpp"  // host feeder: BGZF inflate, record scan, pairing (no device work)
+
+// ---------------------------------------------------------------------------- K8: BBHash (boomphf) dump
 
 struct sgc_mphf {
     sgc_ctx* ctx = nullptr;

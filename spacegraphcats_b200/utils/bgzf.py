@@ -5,13 +5,18 @@ on top of utils/bgzf/bgzf.py ``BgzfReader.tell`` :596-611).  A position is alway
 the block that holds its byte (a position at a block end belongs to the NEXT block, offset 0),
 which is what the reference's reader returns after ``readline``.
 
-BGZF I/O is host-side glue and stays on the CPU (north star); this is a small independent
-implementation (zlib per block), not the reference's BioPython module.
+The heavy lifting is native and multi-threaded (``csrc/sgc_feed.hpp`` behind ``sgc_bgzf_*`` /
+``sgc_reads_*``): parallel block inflate with CRC check, record scan straight into the packed
+``(seq, off)`` layout the kernels take, names kept as byte ranges instead of Python strings.
 """
+import ctypes
+import os
 import struct
 import zlib
 
 import numpy as np
+
+from .._lib import check, lib
 
 _EOF_BLOCK = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
 
@@ -22,44 +27,38 @@ def is_bgzf(path):
     return len(head) >= 18 and head[:4] == b"\x1f\x8b\x08\x04" and head[12:14] == b"BC"
 
 
-def _blocks(raw):
-    """Yield (compressed_start, compressed_size, payload_bytes) for each BGZF block."""
-    pos, n = 0, len(raw)
-    while pos < n:
-        if raw[pos : pos + 4] != b"\x1f\x8b\x08\x04":
-            raise ValueError("not a BGZF block at byte %d" % pos)
-        xlen = struct.unpack_from("<H", raw, pos + 10)[0]
-        extra = raw[pos + 12 : pos + 12 + xlen]
-        bsize, i = None, 0
-        while i + 4 <= len(extra):
-            si1, si2, slen = extra[i], extra[i + 1], struct.unpack_from("<H", extra, i + 2)[0]
-            if si1 == 66 and si2 == 67 and slen == 2:
-                bsize = struct.unpack_from("<H", extra, i + 4)[0] + 1
-            i += 4 + slen
-        if bsize is None:
-            raise ValueError("BGZF block without BC subfield at byte %d" % pos)
-        cdata = raw[pos + 12 + xlen : pos + bsize - 8]
-        payload = zlib.decompress(cdata, -15) if cdata else b""
-        yield pos, bsize, payload
-        pos += bsize
+def n_threads():
+    """Host threads for the feeder: SGC_FEED_THREADS, else the CPUs this process may run on."""
+    env = os.environ.get("SGC_FEED_THREADS")
+    if env:
+        return max(int(env), 1)
+    try:
+        return max(len(os.sched_getaffinity(0)), 1)
+    except AttributeError:
+        return max(os.cpu_count() or 1, 1)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
 
 
 class BgzfData:
     """A fully inflated BGZF file: ``data`` (uint8) and position -> virtual offset."""
 
     def __init__(self, path):
-        with open(path, "rb") as fp:
-            raw = fp.read()
-        cstart, ustart, parts, upos = [], [], [], 0
-        for cs, _, payload in _blocks(raw):
-            if payload:
-                cstart.append(cs)
-                ustart.append(upos)
-                parts.append(payload)
-                upos += len(payload)
-        self.data = np.frombuffer(b"".join(parts), np.uint8)
-        self._cstart = np.array(cstart, np.int64)
-        self._ustart = np.array(ustart, np.int64)
+        L = lib()
+        raw = np.fromfile(path, np.uint8)
+        nb, total = ctypes.c_int64(0), ctypes.c_int64(0)
+        check(L.sgc_bgzf_index(_p(raw), raw.size, None, None, 0, ctypes.byref(nb), ctypes.byref(total)))
+        cstart = np.zeros(nb.value, np.int64)
+        usize = np.zeros(nb.value, np.int64)
+        check(L.sgc_bgzf_index(_p(raw), raw.size, _p(cstart), _p(usize), nb.value, ctypes.byref(nb), ctypes.byref(total)))
+        self.data = np.empty(total.value, np.uint8)
+        check(L.sgc_bgzf_inflate(_p(raw), raw.size, _p(cstart), _p(usize), nb.value, n_threads(), _p(self.data),
+                                 total.value))
+        keep = usize > 0  # empty blocks (the EOF marker) hold no position
+        self._cstart = cstart[keep]
+        self._ustart = (np.cumsum(usize) - usize)[keep]
 
     def virtual_offsets(self, positions):
         positions = np.asarray(positions, np.int64)
@@ -102,57 +101,66 @@ def write_bgzf(path, payload, block_size=65280):
         fp.write(_EOF_BLOCK)
 
 
-def parse_records(data):
-    """Vectorised FASTA/FASTQ scan of an inflated buffer.
+class NameTable:
+    """Record names as byte ranges ``[lo[i], hi[i])`` of a uint8 buffer: no per-record Python
+    object is made until one is asked for.  Compares equal to a list of str."""
 
-    -> (names list[str], seq uint8 concatenation, seq_off int64[n+1], rec_pos int64[n])
+    def __init__(self, data, lo, hi):
+        self.data, self.lo, self.hi = data, lo, hi
+
+    @classmethod
+    def from_strings(cls, names):
+        enc = [s.encode("ascii") for s in names]
+        ln = np.fromiter((len(e) for e in enc), np.int64, len(enc))
+        hi = np.cumsum(ln)
+        return cls(np.frombuffer(b"".join(enc) or b"\0", np.uint8), hi - ln, hi)
+
+    def __len__(self):
+        return len(self.lo)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        return self.data[self.lo[i] : self.hi[i]].tobytes().decode("ascii")
+
+    def __iter__(self):
+        raw = self.data.tobytes()
+        return (raw[a:b].decode("ascii") for a, b in zip(self.lo.tolist(), self.hi.tolist()))
+
+    def tolist(self):
+        return list(self)
+
+    def __eq__(self, other):
+        if isinstance(other, NameTable):
+            other = other.tolist()
+        return self.tolist() == other
+
+
+def parse_records(data):
+    """Native FASTA/FASTQ scan of an inflated buffer (sgc_reads_count + sgc_reads_scan).
+
+    -> (names NameTable, seq uint8 concatenation, seq_off int64[n+1], rec_pos int64[n])
     ``rec_pos[i]`` is the uncompressed position of record i's header line (the position the
-    reference's iterators report: search_utils.py:88/121-124 for FASTA, :136 for FASTQ)."""
-    data = np.asarray(data, np.uint8)
+    reference's iterators report: search_utils.py:88/121-124 for FASTA, :136 for FASTQ).  Names and
+    sequence lines are stripped the way those iterators strip them."""
+    L = lib()
+    data = np.ascontiguousarray(data, np.uint8)
     if data.size == 0:
-        return [], np.zeros(0, np.uint8), np.zeros(1, np.int64), np.zeros(0, np.int64)
-    nl = np.flatnonzero(data == 10)
-    line_start = np.concatenate([[0], nl + 1])
-    line_end = np.concatenate([nl, [data.size]])  # exclusive of '\n'
-    if line_start[-1] >= data.size:  # file ends with '\n'
-        line_start, line_end = line_start[:-1], line_end[:-1]
-    # strip '\r'
-    has_cr = (line_end > line_start) & (data[np.maximum(line_end - 1, 0)] == 13)
-    line_end = line_end - has_cr
-    first = chr(data[0])
-    raw = data.tobytes()
-    if first == "@":
-        nrec = len(line_start) // 4
-        hs, he = line_start[0 : 4 * nrec : 4], line_end[0 : 4 * nrec : 4]
-        ss, se = line_start[1 : 4 * nrec : 4], line_end[1 : 4 * nrec : 4]
-        plus = data[line_start[2 : 4 * nrec : 4]]
-        if nrec and (not (data[hs] == ord("@")).all() or not (plus == ord("+")).all()):
-            raise ValueError("FASTQ records must be exactly 4 lines")
-        lens = se - ss
-        seq_off = np.zeros(nrec + 1, np.int64)
-        np.cumsum(lens, out=seq_off[1:])
-        delta = np.zeros(data.size + 1, np.int32)
-        np.add.at(delta, ss, 1)
-        np.add.at(delta, se, -1)
-        mask = np.cumsum(delta[:-1]) > 0
-        seq = data[mask]
-        names = [raw[a + 1 : b].decode("ascii").strip() for a, b in zip(hs.tolist(), he.tolist())]
-        return names, seq, seq_off, hs.astype(np.int64)
-    if first == ">":
-        is_hdr = data[line_start] == ord(">")
-        hidx = np.flatnonzero(is_hdr)
-        hs, he = line_start[hidx], line_end[hidx]
-        nrec = len(hidx)
-        # bytes of sequence lines, whitespace removed
-        delta = np.zeros(data.size + 1, np.int32)
-        np.add.at(delta, hs, 1)
-        np.add.at(delta, np.minimum(he + 1, data.size), -1)
-        in_hdr = np.cumsum(delta[:-1]) > 0
-        mask = ~in_hdr & (data != 10) & (data != 13) & (data != 32) & (data != 9)
-        seq = data[mask]
-        csum = np.concatenate([[0], np.cumsum(mask, dtype=np.int64)])
-        bounds = np.concatenate([hs, [data.size]])
-        seq_off = csum[bounds] - csum[bounds[0]]
-        names = [raw[a + 1 : b].decode("ascii").strip() for a, b in zip(hs.tolist(), he.tolist())]
-        return names, seq, seq_off.astype(np.int64), hs.astype(np.int64)
-    raise Exception("unknown start chr {}".format(first))
+        z = np.zeros(0, np.int64)
+        return NameTable(data, z, z), np.zeros(0, np.uint8), np.zeros(1, np.int64), z
+    info = np.zeros(3, np.int64)
+    nt = n_threads()
+    try:
+        check(L.sgc_reads_count(_p(data), data.size, nt, _p(info)))
+    except Exception as e:  # the reference raises a bare Exception for an unknown first byte
+        if "unknown start chr" in str(e):
+            raise Exception("unknown start chr {}".format(chr(data[0])))
+        raise ValueError(str(e))
+    nrec, nbytes = int(info[0]), int(info[1])
+    rec_pos = np.empty(nrec, np.int64)
+    lo = np.empty(nrec, np.int64)
+    hi = np.empty(nrec, np.int64)
+    seq_off = np.empty(nrec + 1, np.int64)
+    seq = np.empty(nbytes, np.uint8)
+    check(L.sgc_reads_scan(_p(data), data.size, nt, nrec, nbytes, _p(rec_pos), _p(lo), _p(hi), _p(seq_off), _p(seq)))
+    return NameTable(data, lo, hi), seq, seq_off, rec_pos

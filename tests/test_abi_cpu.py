@@ -179,3 +179,121 @@ def test_index_reads_host_rules_vectorised_vs_oracle_loop():
         assert sorted(zip(ro.tolist(), ri.tolist())) == sorted(want)
         assert got_paired == n_paired and (first >= 0) == (n_paired > 0)
         assert n_paired > 0 or ignore
+
+
+# ---- native host feeder (sgc_bgzf_* / sgc_reads_*): no GPU needed -----------------------------
+def _messy_fastq(rng, n):
+    out = []
+    for i in range(n):
+        ln = int(rng.integers(0, 300))
+        s = "".join("ACGTN"[j] for j in rng.integers(0, 5, ln))
+        eol = "\r\n" if rng.random() < 0.3 else "\n"
+        name = "r%d/%d" % (i // 2, i % 2 + 1) + (" extra words\t" if rng.random() < 0.2 else "")
+        pad = " " if rng.random() < 0.1 else ""
+        out.append("@%s%s%s%s%s+%s%s%s" % (name, eol, pad, s, pad + eol, pad, eol, "I" * ln + eol))
+    return "".join(out)
+
+
+def _messy_fasta(rng, n):
+    out = []
+    for i in range(n):
+        ln = int(rng.integers(0, 900))
+        s = "".join("ACGT"[j] for j in rng.integers(0, 4, ln))
+        eol = "\r\n" if rng.random() < 0.3 else "\n"
+        w = int(rng.integers(20, 90))
+        body = "".join(("  " if rng.random() < 0.05 else "") + s[a : a + w] + ("\t" if rng.random() < 0.05 else "") + eol
+                       for a in range(0, ln, w))
+        if rng.random() < 0.1:
+            body += eol  # blank line inside the file
+        out.append(">%s seq%d %s%s%s" % (" " if rng.random() < 0.1 else "", i, "desc " * int(rng.integers(0, 3)), eol, body))
+    return "".join(out)
+
+
+@pytest.mark.parametrize("fmt", ["fastq", "fasta"])
+@pytest.mark.parametrize("threads", ["1", "3", "8"])
+def test_native_record_scan_vs_reference_iterators(fmt, threads, monkeypatch):
+    """sgc_reads_scan against the oracle's restatement of my_fasta_iter / my_fastq_iter: names,
+    sequences and header positions, over CRLF, padded lines, blank lines, descriptions, empty
+    sequences and a last line without newline; buffers large enough that every thread owns chunks."""
+    from oracle import oracle as O
+    from spacegraphcats_b200.utils import bgzf
+
+    monkeypatch.setenv("SGC_FEED_THREADS", threads)
+    rng = np.random.default_rng(len(fmt) + int(threads))
+    for trial in range(3):
+        text = (_messy_fastq if fmt == "fastq" else _messy_fasta)(rng, 6000 if trial == 0 else int(rng.integers(1, 40)))
+        if trial == 1:
+            text = text.rstrip("\r\n")  # no trailing newline
+        data = text.encode()
+        want = list(O.iterate_records(data))
+        names, seq, off, pos = bgzf.parse_records(np.frombuffer(data, np.uint8))
+        assert len(names) == len(want)
+        assert names == [r.name for r, _ in want]
+        assert pos.tolist() == [p for _, p in want]
+        raw = seq.tobytes().decode()
+        assert [raw[off[i] : off[i + 1]] for i in range(len(want))] == [r.sequence for r, _ in want]
+
+
+def test_native_record_scan_error_paths():
+    from spacegraphcats_b200.utils import bgzf
+
+    with pytest.raises(Exception, match="unknown start chr"):
+        bgzf.parse_records(np.frombuffer(b"ACGT\n", np.uint8))
+    with pytest.raises(ValueError, match="4 lines"):
+        bgzf.parse_records(np.frombuffer(b"@a\nACGT\n+\nIIII\n@b\nACGT\nIIII\n@c\n", np.uint8))
+    n, s, o, p = bgzf.parse_records(np.zeros(0, np.uint8))
+    assert len(n) == 0 and o.tolist() == [0] and len(p) == 0
+    # an incomplete trailing record is ignored
+    n, s, o, p = bgzf.parse_records(np.frombuffer(b"@a\nACGT\n+\nIIII\n@b\nAC", np.uint8))
+    assert n == ["a"] and s.tobytes() == b"ACGT"
+
+
+def test_native_bgzf_inflate_and_corruption(tmp_path):
+    import gzip
+    from spacegraphcats_b200._lib import SgcError
+    from spacegraphcats_b200.utils import bgzf
+
+    rng = np.random.default_rng(9)
+    payload = bytes(rng.integers(65, 91, 1_500_000, dtype=np.uint8))
+    p = str(tmp_path / "x.bgz")
+    bgzf.write_bgzf(p, payload, block_size=40000)
+    src = bgzf.BgzfData(p)
+    assert src.data.tobytes() == payload == gzip.open(p, "rb").read()
+    pos = np.array([0, 39999, 40000, 40001, len(payload) - 1], np.int64)
+    vo = src.virtual_offsets(pos)
+    assert (vo & 0xFFFF).tolist() == [0, 39999, 0, 1, (len(payload) - 1) % 40000]
+    assert (vo >> 16)[1] == 0 and (vo >> 16)[2] > 0
+    raw = bytearray(open(p, "rb").read())
+    raw[len(raw) // 2] ^= 0x55  # flip bits inside some block's deflate stream
+    bad = str(tmp_path / "bad.bgz")
+    open(bad, "wb").write(bytes(raw))
+    with pytest.raises(SgcError):
+        bgzf.BgzfData(bad)
+    open(bad, "wb").write(bytes(raw[: len(raw) // 3]))  # truncated
+    with pytest.raises(SgcError):
+        bgzf.BgzfData(bad)
+
+
+def test_native_pair_flags_vs_python_rule():
+    from spacegraphcats_b200.cdbg.index_reads import pair_flags
+
+    rng = np.random.default_rng(4)
+    pool = ["a/1", "a/2", "b/1", "b/2", "c/2", "same", "", "/1", "/2", "x", "ab/1", "b/2", "a/12", "/2/2"]
+    names = [pool[i] for i in rng.integers(0, len(pool), 5000)]
+    elig = rng.random(5000) < 0.8
+    got_p, got_l = pair_flags(names, elig)
+    last = None
+    for i, nm in enumerate(names):  # index_reads.py:124-141, literally
+        is_paired = False
+        if last is not None:
+            ln = names[last]
+            if ln.endswith("/1") and nm.endswith("/2"):
+                if ln[:-2] == nm[:-2] and len(ln) > 2:
+                    is_paired = True
+            elif ln == nm and ln:
+                is_paired = True
+        assert bool(got_p[i]) == is_paired and got_l[i] == (-1 if last is None else last), i
+        if elig[i]:
+            last = i
+    p2, l2 = pair_flags(names, elig, ignore_paired=True)
+    assert not p2.any() and (l2 == -1).all()
