@@ -299,6 +299,11 @@ int sgc_bgzf_index(const uint8_t* h_raw, int64_t raw_bytes, int64_t* h_cstart, i
 /* Inflate all blocks in parallel into h_out (out_bytes = sum of h_usize); CRC32 of every block is checked. */
 int sgc_bgzf_inflate(const uint8_t* h_raw, int64_t raw_bytes, const int64_t* h_cstart, const int64_t* h_usize,
                      int64_t nblocks, int n_threads, uint8_t* h_out, int64_t out_bytes);
+/* BGZF writer (reference utils/make_bgzf.py): blocks of block_size <= 65280 input bytes, zlib level 0-9,
+ * then the EOF marker block.  h_out needs sgc_bgzf_deflate_bound(n, block_size) bytes (-1: bad argument). */
+int64_t sgc_bgzf_deflate_bound(int64_t n, int block_size);
+int sgc_bgzf_deflate(const uint8_t* h_data, int64_t n, int block_size, int level, int n_threads, uint8_t* h_out,
+                     int64_t out_cap, int64_t* h_out_bytes);
 /* FASTA ('>') or 4-line FASTQ ('@') text: h_info[0..2] = records, total sequence bytes, format (0 FASTA, 1 FASTQ).
  * SGC_ERR_ARG: "unknown start chr", or a FASTQ record that is not '@' ... '+' ... */
 int sgc_reads_count(const uint8_t* h_data, int64_t n, int n_threads, int64_t* h_info);
@@ -311,6 +316,12 @@ int sgc_reads_scan(const uint8_t* h_data, int64_t n, int n_threads, int64_t nrec
  * mate ("x/1" then "x/2", or two equal non-empty names).  ignore_paired: all 0 / -1. */
 int sgc_reads_pair_flags(const uint8_t* h_data, const int64_t* h_name_lo, const int64_t* h_name_hi,
                          const uint8_t* h_elig, int64_t nrec, int ignore_paired, uint8_t* h_paired, int64_t* h_last);
+/* The rows index_reads INSERTs (cdbg/index_reads.py:124-167), in the reference's order, from the flags
+ * above, every record's BGZF offset and the CSR of distinct ascending ids sgc_label_reads returned.
+ * cap = 0 counts only (*h_n_rows); SGC_ERR_CAPACITY when the arrays are short. */
+int sgc_reads_rows(const uint8_t* h_elig, const uint8_t* h_paired, const int64_t* h_last, const int64_t* h_offsets,
+                   const int64_t* h_ids_off, const uint32_t* h_ids, int64_t nrec, int64_t* h_rows_offset,
+                   int64_t* h_rows_id, int64_t cap, int64_t* h_n_rows);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
 """Time the device BBHash build / lookup / dump at a few key counts (not a bench line)."""
+import os
 import sys
 import time
 
@@ -17,6 +18,8 @@ for lg in [int(a) for a in sys.argv[1:]] or [24, 26, 29]:
     gen = torch.Generator(device="cuda").manual_seed(lg)
     keys = torch.unique(torch.randint(-(2**63), 2**63 - 1, (n,), dtype=torch.int64, device="cuda", generator=gen))
     torch.cuda.synchronize()
+    DeviceMphf.build(ctx, keys).close()  # warm-up: first-touch of fresh device memory
+    ctx.sync()
     t0 = time.perf_counter()
     m = DeviceMphf.build(ctx, keys)
     ctx.sync()
@@ -32,3 +35,15 @@ for lg in [int(a) for a in sys.argv[1:]] or [24, 26, 29]:
     m.close()
     del keys, idx
     torch.cuda.empty_cache()
+
+if os.environ.get("MPHF_PROF"):
+    from torch.profiler import ProfilerActivity, profile
+
+    n = 1 << int(os.environ["MPHF_PROF"])
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    keys = torch.unique(torch.randint(-(2**63), 2**63 - 1, (n,), dtype=torch.int64, device="cuda", generator=gen))
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        m = DeviceMphf.build(ctx, keys)
+        ctx.sync()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=60))

@@ -80,7 +80,10 @@ class GpuKmerTable:
         that read labelling needs one table probe per four k-mers instead of four: identical labels,
         half the HBM traffic, but no net speed-up yet."""
         t = cls(ctx)
-        n_kmers = int(np.maximum(np.diff(off) - ksize + 1, 0).sum())
+        if isinstance(off, np.ndarray) or not hasattr(off, "device"):
+            n_kmers = int(np.maximum(np.diff(off) - ksize + 1, 0).sum())
+        else:  # CUDA tensors (already resident sequences)
+            n_kmers = int((off[1:] - off[:-1] - (ksize - 1)).clamp_(min=0).sum().item())
         t._dev = DeviceTable(t.ctx, max(n_kmers, 1))
         if side:
             t._dev.enable_side()

@@ -20,6 +20,7 @@ from ..utils import bgzf
 from .hashing import MPHF_KmerIndex
 
 DEFAULT_KSIZE = 31
+TIMINGS = {}  # seconds per stage of the latest main() run (scripts/index_reads_timing.py)
 BATCH_READS = 1 << 22
 
 
@@ -44,68 +45,53 @@ def pair_flags(names, elig, ignore_paired=False):
     return paired.astype(bool), last
 
 
-def _expand(lo, hi):
-    """concatenated index ranges [lo[i], hi[i]) and the owner i of every element"""
-    ln = hi - lo
-    tot = int(ln.sum())
-    owner = np.repeat(np.arange(len(lo), dtype=np.int64), ln)
-    start = np.repeat(np.cumsum(ln) - ln, ln)
-    return np.repeat(lo, ln) + (np.arange(tot, dtype=np.int64) - start), owner
-
-
 def rows_from_labels(names, lens, offsets, ids_off, ids, ksize, ignore_paired=False):
-    """The host half of the index_reads loop (index_reads.py:105-167), vectorised: given every
-    read's distinct unitig ids (CSR) produce the rows the reference INSERTs.
+    """The host half of the index_reads loop (index_reads.py:105-167): given every read's distinct
+    unitig ids (CSR) produce the rows the reference INSERTs, in its order (native: sgc_reads_rows).
 
     State of the reference loop after record i: S_i = (paired_i ? S_{i-1} : {}) | (long_i ? ids_i : {}),
     i.e. the union of the ids of the records since the last record that was NOT paired; a record long
-    enough emits S_i under its own offset and, when paired, under its mate's offset as well.
+    enough emits S_i under its mate's offset (when paired) and under its own.
     -> (rows_offset, rows_id, n_paired, first_paired)"""
     n = len(names)
-    lens = np.asarray(lens, np.int64)
-    offsets = np.asarray(offsets, np.int64)
-    ids_off = np.asarray(ids_off, np.int64)
-    ids = np.asarray(ids, np.int64)
-    elig = lens >= ksize
+    elig = np.ascontiguousarray(np.asarray(lens, np.int64) >= ksize, np.uint8)
+    offsets = np.ascontiguousarray(offsets, np.int64)
+    ids_off = np.ascontiguousarray(ids_off, np.int64)
+    ids = np.ascontiguousarray(ids, np.uint32)
     paired, last = pair_flags(names, elig, ignore_paired)
     n_paired = int(paired.sum())
     first_paired = int(np.flatnonzero(paired)[0]) if n_paired else -1
-    # run start c(i): the latest record <= i that is not paired
-    c = np.maximum.accumulate(np.where(~paired, np.arange(n, dtype=np.int64), 0)) if n else np.zeros(0, np.int64)
-    sel = np.flatnonzero(elig)
-    lo, hi, own_lo = ids_off[c[sel]], ids_off[sel + 1], ids_off[sel]
-    simple = lo == own_lo  # nothing inherited: the read's own ids, already distinct and ascending
-    pos_s, own_s = _expand(own_lo[simple], hi[simple])
-    rid_s, rrec_s = ids[pos_s], sel[simple][own_s]
-    pos_m, own_m = _expand(lo[~simple], hi[~simple])
-    if len(pos_m):
-        key = (sel[~simple][own_m] << 32) | ids[pos_m]  # union per record (ids are < 2^32)
-        key.sort()
-        key = key[np.concatenate([[True], key[1:] != key[:-1]])]
-        rrec_m, rid_m = key >> 32, key & 0xFFFFFFFF
-    else:
-        rrec_m, rid_m = np.zeros(0, np.int64), np.zeros(0, np.int64)
-    rrec = np.concatenate([rrec_s, rrec_m])
-    rid = np.concatenate([rid_s, rid_m])
-    mate = paired[rrec]
-    rows_o = np.concatenate([offsets[rrec], offsets[last[rrec[mate]]]])
-    rows_i = np.concatenate([rid, rid[mate]])
+    pflag = np.ascontiguousarray(paired, np.uint8)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    L = lib()
+    n_rows = ctypes.c_int64(0)
+    args = (vp(elig), vp(pflag), vp(last), vp(offsets), vp(ids_off), vp(ids), n)
+    check(L.sgc_reads_rows(*args, None, None, 0, ctypes.byref(n_rows)))
+    rows_o = np.empty(n_rows.value, np.int64)
+    rows_i = np.empty(n_rows.value, np.int64)
+    if n_rows.value:
+        check(L.sgc_reads_rows(*args, vp(rows_o), vp(rows_i), n_rows.value, ctypes.byref(n_rows)))
     return rows_o, rows_i, n_paired, first_paired
 
 
-def label_records(names, seq, seq_off, offsets, kmer_idx, ksize, ignore_paired=False):
+def label_records(names, seq, seq_off, offsets, kmer_idx, ksize, ignore_paired=False, timings=None):
     """The loop of index_reads.py:105-167 over an in-memory batch: ONE fused GPU pass for the per-read
     ids, then the vectorised host rules.
 
     -> (rows_offset int64[m], rows_id int64[m], n_paired, set_of_all_ids, first_paired).
     ``rows_*`` are the rows the reference INSERTs (as a multiset; duplicates included, cf.
     :156-157); ``first_paired`` is the index of the first read found paired (-1: none)."""
+    t0 = time.time()
     res = kmer_idx.table.label_reads(seq, seq_off, ksize)
     if res["status"].any():
         bad = int(np.flatnonzero(res["status"])[0])
         raise ValueError("Invalid base in read %r" % names[bad])
+    t1 = time.time()
     ro, ri, n_paired, first_paired = rows_from_labels(names, np.diff(seq_off), offsets, res["ids_off"], res["ids"], ksize,
                                                       ignore_paired)
+    if timings is not None:
+        timings["label_gpu"] = t1 - t0
+        timings["pairing_rows"] = time.time() - t1
     return ro, ri, n_paired, set(np.unique(ri).tolist()), first_paired
 
 
@@ -140,8 +126,10 @@ def main(argv=sys.argv[1:]):
     cursor.execute("CREATE TABLE sequences (offset INTEGER, cdbg_id INTEGER)")
     db.commit()
 
+    TIMINGS.clear()
     t0 = time.time()
     kmer_idx = MPHF_KmerIndex.from_directory(args.cdbg_prefix)
+    TIMINGS["load_index"] = time.time() - t0
     assert args.ksize == kmer_idx.ksize
     print("loaded {} k-mers in index ({:.1f}s)".format(len(kmer_idx), time.time() - t0), file=sys.stderr)
 
@@ -152,15 +140,18 @@ def main(argv=sys.argv[1:]):
     print(f"walking read file: '{args.reads}'")
     t0 = time.time()
     src = bgzf.open_reads(args.reads)
+    TIMINGS["inflate"] = time.time() - t0
+    t1 = time.time()
     names, seq, seq_off, rec_pos = bgzf.parse_records(src.data)
     offsets = src.virtual_offsets(rec_pos)
+    TIMINGS["scan"] = time.time() - t1
     n = len(names)
     total_bp = int(seq_off[-1])
 
     # NB: pairing links a read to the previous one, so the whole file is labelled as one stream;
     # the GPU pass itself is batched inside the table object.
     ro, ri, n_paired, total_ids, first_paired = label_records(
-        names, seq, seq_off, offsets, kmer_idx, args.ksize, ignore_paired=args.ignore_paired
+        names, seq, seq_off, offsets, kmer_idx, args.ksize, ignore_paired=args.ignore_paired, timings=TIMINGS
     )
     if args.expect_paired:
         # the reference checks at every 5e5-bp watermark that a pair has been seen (:108-122)
@@ -169,10 +160,13 @@ def main(argv=sys.argv[1:]):
         if len(crossed) and (first_paired < 0 or first_paired >= crossed[0]):
             print("ERROR: no paired reads!? but -P/--expect-paired set. Quitting.")
             return -1
+    t1 = time.time()
     cursor.executemany(
         "INSERT INTO sequences (offset, cdbg_id) VALUES (?, ?)", zip(ro.tolist(), ri.tolist())
     )
     db.commit()
+    TIMINGS["sqlite_insert"] = time.time() - t1
+    TIMINGS["rows"] = len(ro)
 
     err = lambda s: print(s, file=sys.stderr)  # noqa: E731
     err(f"{total_bp:5.2e} bp in {n} reads")
@@ -187,9 +181,11 @@ def main(argv=sys.argv[1:]):
         err(f"ERROR: length of distinct cDBG IDs found is {len(total_ids)}")
 
     err("creating indices in database.")
+    t1 = time.time()
     cursor.execute("CREATE INDEX offset_idx ON sequences (offset)")
     cursor.execute("CREATE INDEX cdbg_id_idx ON sequences (cdbg_id)")
     db.close()
+    TIMINGS["sqlite_index"] = time.time() - t1
     print(f"done; closing {dbfilename}!")
 
     if args.expect_paired and not n_paired:

@@ -11,14 +11,11 @@ The heavy lifting is native and multi-threaded (``csrc/sgc_feed.hpp`` behind ``s
 """
 import ctypes
 import os
-import struct
-import zlib
 
 import numpy as np
 
 from .._lib import check, lib
 
-_EOF_BLOCK = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
 
 
 def is_bgzf(path):
@@ -86,19 +83,19 @@ def open_reads(path):
     return BgzfData(path) if is_bgzf(path) else PlainData(path)
 
 
-def write_bgzf(path, payload, block_size=65280):
-    """Write ``payload`` (bytes) as BGZF (used by tests and utils.make_bgzf-style conversion)."""
-    with open(path, "wb") as fp:
-        for lo in range(0, len(payload), block_size):
-            chunk = payload[lo : lo + block_size]
-            comp = zlib.compressobj(6, zlib.DEFLATED, -15)
-            cdata = comp.compress(chunk) + comp.flush()
-            bsize = len(cdata) + 25
-            fp.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00")
-            fp.write(struct.pack("<H", bsize))
-            fp.write(cdata)
-            fp.write(struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
-        fp.write(_EOF_BLOCK)
+def write_bgzf(path, payload, block_size=65280, level=6):
+    """Write ``payload`` (bytes / uint8 array) as BGZF, blocks deflated in parallel (sgc_bgzf_deflate);
+    what the reference's utils/make_bgzf.py produces."""
+    L = lib()
+    data = np.frombuffer(payload, np.uint8) if not isinstance(payload, np.ndarray) else np.ascontiguousarray(payload, np.uint8)
+    bound = L.sgc_bgzf_deflate_bound(data.size, int(block_size))
+    if bound < 0:
+        raise ValueError("block_size must be in [1, 65280]")
+    out = np.empty(bound, np.uint8)
+    nb = ctypes.c_int64(0)
+    check(L.sgc_bgzf_deflate(_p(data) if data.size else None, data.size, int(block_size), int(level), n_threads(),
+                             _p(out), bound, ctypes.byref(nb)))
+    out[: nb.value].tofile(path)
 
 
 class NameTable:

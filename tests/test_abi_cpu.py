@@ -297,3 +297,20 @@ def test_native_pair_flags_vs_python_rule():
             last = i
     p2, l2 = pair_flags(names, elig, ignore_paired=True)
     assert not p2.any() and (l2 == -1).all()
+
+
+def test_native_bgzf_writer(tmp_path):
+    import gzip
+    from spacegraphcats_b200.utils import bgzf
+
+    p = str(tmp_path / "w.bgz")
+    bgzf.write_bgzf(p, b"")
+    assert open(p, "rb").read() == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    rng = np.random.default_rng(2)
+    noise = bytes(rng.integers(0, 256, 300_000, dtype=np.uint8))  # incompressible: blocks grow, must still fit 64 KiB
+    for level in (0, 1, 6, 9):
+        bgzf.write_bgzf(p, noise, level=level)
+        assert bgzf.is_bgzf(p) and gzip.open(p, "rb").read() == noise
+        assert bgzf.BgzfData(p).data.tobytes() == noise
+    with pytest.raises(ValueError):
+        bgzf.write_bgzf(p, noise, block_size=70000)
