@@ -189,7 +189,9 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                     pair_fill += total;
                 }
             };
-            for (unsigned j0 = 0; j0 < q_fill; j0 += 32) {
+            // one trip more than there are items: the last trip only settles (every lambda of this kernel
+            // has ONE call site -- the hot loops must stay inside the 32 KB instruction cache)
+            for (unsigned j0 = 0; j0 < q_fill + 32; j0 += 32) {
                 const unsigned j = j0 + lane;
                 const bool act = j < q_fill;
                 const uint64_t h = act ? qh[j] : 0ULL;
@@ -197,9 +199,8 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                 if (j0 > 0) settle();
                 d_act = act; d_h = h; d_sq = sq;
                 d_b = act ? home_bucket(h, a.nbuckets, a.home_shift) : 0u;
-                load_bucket_nc(a.tbl + d_b, d_e0, d_e1);
+                if (j0 < q_fill) load_bucket_nc(a.tbl + d_b, d_e0, d_e1);
             }
-            if (q_fill) settle();
             __syncwarp();
             q_fill = 0;
         }
@@ -638,7 +639,11 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                 emit_candidates(ids, p_active, p_sg, p_i, p_nv);  // queued k-mers count as "no id" here
             };
 
-            for (int g0 = 0; g0 < G; g0 += 32) {
+            // one trip more than there are groups: the last trip only resolves (single call site per
+            // lambda, see drain_queue); the warp's last round also empties the queue
+            const bool last_round = (int64_t)rq0 >= nrounds;
+            const int G1 = (G > 0 || (last_round && q_fill)) ? G + 32 : 0;
+            for (int g0 = 0; g0 < G1; g0 += 32) {
                 const int g = g0 + lane;
                 const bool active = g < G;
                 int sg = 0, i = 0, nv = 0;
@@ -650,15 +655,13 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                     for (int t = 0; t < 4; t++) p_h[t] ^= dep;
                 }
                 if (g0 > 0) resolve();
-                if (q_fill > QCAP - 96) drain_queue();
+                if (q_fill > QCAP - 96 || (last_round && g0 >= G && q_fill)) drain_queue();
                 p_active = active; p_sg = sg; p_i = i; p_nv = nv;
 #pragma unroll
                 for (int t = 0; t < 4; t++) p_h[t] = h[t];
                 p_b0 = active ? home_bucket(h[0], a.nbuckets, a.home_shift) : 0u;
-                load_bucket_nc(a.tbl + p_b0, p_e0, p_e1);
+                if (g0 < G) load_bucket_nc(a.tbl + p_b0, p_e0, p_e1);
             }
-            if (G > 0) resolve();
-            if (q_fill > QCAP - 96) drain_queue();
             __syncwarp();
         } else {
             // MODE_LOOKUP / MODE_LABEL, software-pipelined: the 4 table probes of a group are issued
@@ -726,7 +729,8 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                 }
             };
 
-            for (int g0 = 0; g0 < G; g0 += 32) {
+            const int G1 = G > 0 ? G + 32 : 0;  // one trip more than there are groups: the last one only resolves
+            for (int g0 = 0; g0 < G1; g0 += 32) {
                 const int g = g0 + lane;
                 const bool active = g < G;
                 int sg = 0, i = 0, nv = 0;
@@ -748,10 +752,9 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                     // lanes / k-mers with nothing to look up probe bucket 0 (an L2 hit) so that the
                     // loads are unconditional and land directly in the pipeline registers
                     p_b[t] = (active && t < nv) ? home_bucket(h[t], a.nbuckets, a.home_shift) : 0u;
-                    load_bucket_nc(a.tbl + p_b[t], p_e0[t], p_e1[t]);
+                    if (g0 < G) load_bucket_nc(a.tbl + p_b[t], p_e0[t], p_e1[t]);
                 }
             }
-            if (G > 0) resolve();
             __syncwarp();
         }
 
@@ -761,7 +764,6 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
     }
     cp_async_wait_all();  // copies launched for rounds past the end (none carry data) must not outlive the CTA
 
-    if constexpr (MODE == MODE_LABEL_SIDE) drain_queue();
     if constexpr (MODE == MODE_LABEL || MODE == MODE_GATHER || MODE == MODE_LABEL_SIDE) {
         if (pair_fill) flush_pairs();
     }
