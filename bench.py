@@ -194,7 +194,10 @@ def workload_config(args, cpu=False):
                     "1 B200 replicated table (BASELINE.json configs[3])" % (args.table_kmers, KSIZE),
         "ksize": KSIZE, "read_len": READ_LEN, "reads_per_step": args.batch_reads,
         "kmers_per_step": args.batch_reads * (READ_LEN - KSIZE + 1), "error_rate": ERR_PPM / 1e6,
-        "table": "replicated", "l2": "inputs (2.5 GB reads/step, 21 GB table) far larger than the 126 MB L2; no flush needed",
+        "table": "replicated",
+        "label_kernel": "per-k-mer probes (SGC_SIDE=0)" if os.environ.get("SGC_SIDE", "1") == "0"
+                        else "anchor probe + unitig-ordered side array (default)",
+        "l2": "inputs (2.5 GB reads/step, 21 GB table) far larger than the 126 MB L2; no flush needed",
         **({"cpu_sample": {"table_kmers": args.cpu_kmers, "reads_per_step": args.cpu_reads}} if cpu else {}),
     }
 
@@ -494,14 +497,18 @@ def main():
     except Exception:
         pass
     roofline = {
-        "bound": "hbm", "kernel": "tile_kernel<31, MODE_LABEL>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": "hbm",
+        "kernel": "tile_kernel<31, MODE_LABEL>" if os.environ.get("SGC_SIDE", "1") == "0" else "tile_kernel<31, MODE_LABEL_SIDE>",
+        "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic, "traffic_unit": "GB per launch", "traffic_source": traffic_src,
         "peak_source": peak_src,
         "bytes_per_kmer": bytes_per_kmer, "kernel_ms": tile_s * 1e3, "kernel_launches": int(tile_n.value),
         "kernel_share_of_step": tile_ms.value / ms,
-        "note": "algorithmic bytes = read bases + ONE 32-byte table sector per k-mer + label output; the "
+        "note": "algorithmic bytes = read bases + ONE 32-byte table sector per k-mer + label output (SURVEY 8d); the "
                 "measured random-access ceiling of HBM on this part is 36-46 G accesses/s and every access moves a "
-                "128-byte line (scripts/sector_probe*.cu, profiles/)",
+                "128-byte line (scripts/sector_probe*.cu, profiles/); the default label kernel probes the table "
+                "once per four k-mers and matches the rest in a unitig-ordered side array: 64 B of HBM per k-mer "
+                "instead of 129",
     }
 
     # ---- CPU baseline on the host cores ---------------------------------------------------

@@ -15,7 +15,7 @@ import sys
 import numpy as np
 
 from ..device import get_context
-from .hashing import GpuKmerTable, MPHF_KmerIndex, UNSET_VALUE
+from .hashing import GpuKmerTable, MPHF_KmerIndex, UNSET_VALUE, side_default
 
 BATCH_BASES = 1 << 28  # unitig bases per insert launch
 
@@ -57,7 +57,7 @@ def build_mphf(ksize, records_iter_fn, ctx=None, verbose=True):
     from ..device import DeviceTable
 
     table._dev = DeviceTable(ctx, max(total_kmers, 1))
-    if os.environ.get("SGC_SIDE") == "1":  # experimental unitig-ordered side array
+    if side_default():  # unitig-ordered side array for read labelling; SGC_SIDE=0: off
         table._dev.enable_side()
     lo = 0
     while lo < n_contigs:

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                 if (j0 > 0) settle();
                 d_act = act; d_h = h; d_sq = sq;
                 d_b = act ? home_bucket(h, a.nbuckets, a.home_shift) : 0u;
-                if (j0 < q_fill) load_bucket_nc(a.tbl + d_b, d_e0, d_e1);
+                load_bucket_nc(a.tbl + d_b, d_e0, d_e1);  // unconditional (bucket 0 in the last trip)
             }
             __syncwarp();
             q_fill = 0;
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
 #pragma unroll
                 for (int t = 0; t < 4; t++) p_h[t] = h[t];
                 p_b0 = active ? home_bucket(h[0], a.nbuckets, a.home_shift) : 0u;
-                if (g0 < G) load_bucket_nc(a.tbl + p_b0, p_e0, p_e1);
+                load_bucket_nc(a.tbl + p_b0, p_e0, p_e1);  // unconditional (bucket 0 in the last trip)
             }
             __syncwarp();
         } else {
@@ -752,7 +752,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                     // lanes / k-mers with nothing to look up probe bucket 0 (an L2 hit) so that the
                     // loads are unconditional and land directly in the pipeline registers
                     p_b[t] = (active && t < nv) ? home_bucket(h[t], a.nbuckets, a.home_shift) : 0u;
-                    if (g0 < G) load_bucket_nc(a.tbl + p_b[t], p_e0[t], p_e1[t]);
+                    load_bucket_nc(a.tbl + p_b[t], p_e0[t], p_e1[t]);
                 }
             }
             __syncwarp();

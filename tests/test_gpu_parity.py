@@ -295,7 +295,7 @@ def test_label_reads_dory_vs_oracle(ctx, O, dory, dory_index, dory_reads):
     assert plain._dev.side_nbytes == 0
     res2 = plain.label_reads(buf, off, 21)
     assert np.array_equal(res2["ids_off"], o_off) and np.array_equal(res2["ids"], o_ids)
-    # ... and from a table with the experimental unitig-ordered side array (anchor probe + 64-bit
+    # ... and from a table with the unitig-ordered side array (anchor probe + 64-bit
     # hash matching against neighbouring unitig positions): identical labels
     recs = dory[0]
     ubuf, uoff = pack_sequences([r.sequence for r in recs])
@@ -322,8 +322,9 @@ def test_label_reads_synthetic_with_errors_vs_oracle(ctx, O):
     cuts = cuts[cuts < len(g) - k]
     useqs = [g[a : b + k - 1].tobytes() for a, b in zip(cuts[:-1], cuts[1:])]
     ubuf, uoff = pack_sequences(useqs)
-    table = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx, side=True)  # experimental side-array label kernel
-    table_plain = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx)  # default: every k-mer probes the table
+    table = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx)  # default: side-array label kernel
+    assert table._dev.side_nbytes > 0
+    table_plain = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx, side=False)  # every k-mer probes the table
     otab, _, _ = O.build_mphf(k, lambda: iter(O.Record(str(i), s.decode()) for i, s in enumerate(useqs)))
     ot = O.COracleTable(otab.mphf_to_hash, otab.mphf_to_value)
     assert len(table) == len(ot)
@@ -628,7 +629,8 @@ def test_full_size_properties(ctx, O):
     n_reads = int(os.environ.get("SGC_TEST_READS", 1 << 24))
     k = 31
     cd = SyntheticCdbg(ctx, n_kmers, k, seed=1)
-    table = cd.build_table()
+    SIDE_FIRST = True  # the default label kernel (side array) first, the per-k-mer one as the cross-check
+    table = cd.build_table(side=SIDE_FIRST)
     live, multi, max_id = table.stats()
     assert live + multi == n_kmers  # every genome k-mer is distinct at this size w.h.p.; duplicated unitigs drop
     assert multi == cd.dup_kmers and max_id < cd.n_unitigs - cd.n_dup  # duplicated unitigs (highest ids) vanish
@@ -659,9 +661,9 @@ def test_full_size_properties(ctx, O):
     # per-k-mer path: histogram total == hits == the label path's hits
     lk = table.lookup_sequences(seq_f, off, k, n_ids=max_id + 1, want_ids=False, to_host=False)
     assert lk["n_hits"] == a["n_hits"] and int(lk["count_by_id"].to(torch.int64).sum()) == a["n_hits"]
-    # the experimental side-array label kernel gives the same labels at full size
+    # the other label kernel (side array on <-> off) gives the same labels at full size
     del a1, a2, lk
-    table_s = cd.build_table(side=True)
+    table_s = cd.build_table(side=not SIDE_FIRST)
     c = table_s.label_reads(seq_f, off, k, to_host=False)
     assert torch.equal(c["ids_off"], a["ids_off"]) and torch.equal(c["ids"], a["ids"]) and c["n_hits"] == a["n_hits"]
     del table_s, c
