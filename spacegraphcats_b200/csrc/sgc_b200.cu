@@ -31,6 +31,7 @@
 #include <cmath>
 #include <cstring>
 #include <new>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -208,7 +209,7 @@ int make_plan(sgc_ctx* c, const int64_t* d_off, int64_t nseq, int64_t seq_bytes,
 
 template <int K, int MODE>
 int launch_tile_k(sgc_ctx* c, const TileArgs& a) {
-    size_t smem = sizeof(WarpTile<K>) * WPB + (MODE == MODE_LABEL_SIDE ? (size_t)WPB * QCAP * 12 : 0);
+    size_t smem = sizeof(WarpTile<K, MODE == MODE_PARTITION>) * WPB + (MODE == MODE_LABEL_SIDE ? (size_t)WPB * QCAP * 12 : 0);
     // per device: the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
     static thread_local int blocks_per_sm_of[64] = {0};
     int& blocks_per_sm = blocks_per_sm_of[c->device & 63];

@@ -11,15 +11,26 @@ namespace dev {
 // ----------------------------------------------------------------------------------
 // tile geometry
 // ----------------------------------------------------------------------------------
+// Resident CTAs per SM the probing kernels are compiled for.  3 x 256 threads = 24 warps per SM at 80
+// registers (the label kernels fit with at most a few spilled words): these kernels wait on dependent
+// HBM/L2 loads, and ptxas will not overlap a load with arithmetic across a loop trip or a forward branch
+// (it drains the load's scoreboard there), so the latency is hidden by resident warps instead:
+// 16 -> 24 warps took the side-array label kernel from 53 to 62 G k-mers/s; 27 warps gave no more.
 #ifndef SGC_PROBE_MIN_CTAS
-#define SGC_PROBE_MIN_CTAS 2
+#define SGC_PROBE_MIN_CTAS 3
 #endif
-constexpr int NT = 256;         // threads per CTA
+#ifndef SGC_NT
+#define SGC_NT 256
+#endif
+constexpr int NT = SGC_NT;      // threads per CTA
 constexpr int WPB = NT / 32;    // warps per CTA; every warp runs its own rounds (no block barriers)
 constexpr int SPW = 4;          // segments staged per warp round (8 lanes stage one segment)
 constexpr int SEG_K = 256;      // k-mers per segment
 constexpr int PAIR_BUF = 128;   // label keys staged per warp before one global reservation
-constexpr int QCAP = 256;       // MODE_LABEL_SIDE: k-mers queued per warp for a dense table probe
+#ifndef SGC_QCAP
+#define SGC_QCAP 192            // 3 CTAs x 8 warps x (tile + queue) must fit 227 KB of shared memory
+#endif
+constexpr int QCAP = SGC_QCAP;  // MODE_LABEL_SIDE: k-mers queued per warp for a dense table probe
 constexpr unsigned long long SEQ_MASK = (1ULL << 40) - 1ULL;
 
 constexpr uint32_t VAL_EMPTY = 0xFFFFFFFFu;

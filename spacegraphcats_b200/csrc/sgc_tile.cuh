@@ -73,8 +73,23 @@ __device__ __forceinline__ uint32_t revcomp_word(uint32_t u, uint32_t mask, bool
 // warps drift apart, so one warp's exposed latencies (round fetch, staging loads, table probes)
 // are covered by the other warps of the SM.
 // ----------------------------------------------------------------------------------
-template <int K>
-struct WarpTile {
+// MODE_PARTITION's per-owner bookkeeping; the other modes carry an empty stand-in so that it costs
+// them no shared memory (more resident warps for the probing kernels)
+struct PartitionState {
+    unsigned wcnt[32];              // per-owner counts of one warp iteration
+    unsigned wpre[32];              // ... their exclusive prefix (slot of the owner's run in the staging area)
+    uint64_t* dst[PAIR_BUF];        // ... destination address of every staged hash
+    unsigned long long wbase[32];   // ... and the reserved base positions in the owners' regions
+};
+struct NoPartitionState {
+    unsigned wcnt[1];
+    unsigned wpre[1];
+    uint64_t* dst[1];
+    unsigned long long wbase[1];
+};
+
+template <int K, bool PART = false>
+struct alignas(16) WarpTile {
     uint32_t F[SPW * Geo<K>::WPS];
     uint32_t R[SPW * Geo<K>::WPS];
     uint32_t RAW[2][SPW * Geo<K>::WPS];  // 16-byte-aligned raw copies of the segments (cp.async), double-buffered
@@ -86,10 +101,7 @@ struct WarpTile {
     int nk[SPW];
     int gpre[SPW + 1];
     int pad[3];
-    unsigned wcnt[32];              // MODE_PARTITION: per-owner counts of one warp iteration
-    unsigned wpre[32];              // ... their exclusive prefix (slot of the owner's run in the staging area)
-    uint64_t* dst[PAIR_BUF];        // ... destination address of every staged hash
-    unsigned long long wbase[32];   // ... and the reserved base positions in the owners' regions
+    typename std::conditional<PART, PartitionState, NoPartitionState>::type part;  // last: keeps the copies above aligned
 };
 
 template <int K, int MODE>
@@ -97,7 +109,8 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int WPS = Geo<K>::WPS;
     const int lane = threadIdx.x & 31;
-    WarpTile<K>& wt = reinterpret_cast<WarpTile<K>*>(smem_raw)[threadIdx.x >> 5];
+    using Tile = WarpTile<K, MODE == MODE_PARTITION>;
+    Tile& wt = reinterpret_cast<Tile*>(smem_raw)[threadIdx.x >> 5];
     const int k = K ? K : a.k;
     const int64_t nsegs = *a.nsegs_p;
     const int64_t nrounds = (nsegs + SPW - 1) / SPW;
@@ -157,7 +170,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
     uint32_t* qs = nullptr;
     unsigned q_fill = 0;  // warp-uniform
     if constexpr (MODE == MODE_LABEL_SIDE) {
-        unsigned char* qbase = smem_raw + sizeof(WarpTile<K>) * WPB;
+        unsigned char* qbase = smem_raw + sizeof(Tile) * WPB;
         qh = reinterpret_cast<unsigned long long*>(qbase) + (threadIdx.x >> 5) * QCAP;
         qs = reinterpret_cast<uint32_t*>(qbase + (size_t)WPB * QCAP * 8) + (threadIdx.x >> 5) * QCAP;
     }
@@ -449,17 +462,17 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                 int sg = 0, i = 0, nv = 0;
                 uint64_t h[4] = {0, 0, 0, 0};
                 if (active) locate_and_hash(g, sg, i, nv, h);
-                if (lane < a.n_ranks) wt.wcnt[lane] = 0;
+                if (lane < a.n_ranks) wt.part.wcnt[lane] = 0;
                 __syncwarp();
                 uint32_t own[4], rank[4];
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
                     own[t] = a.owner_bits ? (uint32_t)(h[t] >> (64 - a.owner_bits)) : 0u;
-                    rank[t] = (active && t < nv) ? atomicAdd(&wt.wcnt[own[t]], 1u) : 0u;
+                    rank[t] = (active && t < nv) ? atomicAdd(&wt.part.wcnt[own[t]], 1u) : 0u;
                 }
                 __syncwarp();
                 {   // one lane per owner: reserve the run in the owner's region, prefix for the staging slots
-                    const unsigned c = lane < a.n_ranks ? wt.wcnt[lane] : 0u;
+                    const unsigned c = lane < a.n_ranks ? wt.part.wcnt[lane] : 0u;
                     unsigned incl = c;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
@@ -467,8 +480,8 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                         if (lane >= d) incl += v;
                     }
                     if (lane < a.n_ranks) {
-                        wt.wpre[lane] = incl - c;
-                        wt.wbase[lane] = c ? atomicAdd(&a.cursor[lane], (unsigned long long)c) : 0ULL;
+                        wt.part.wpre[lane] = incl - c;
+                        wt.part.wbase[lane] = c ? atomicAdd(&a.cursor[lane], (unsigned long long)c) : 0ULL;
                     }
                 }
                 __syncwarp();
@@ -482,7 +495,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
 #pragma unroll
                     for (int t = 0; t < 4; t++) {
                         if (t < nv) {
-                            const unsigned long long pos = wt.wbase[own[t]] + rank[t];
+                            const unsigned long long pos = wt.part.wbase[own[t]] + rank[t];
                             a.ridx[ko + t] = (a.owner_bits ? (own[t] << sh) : 0u) | (uint32_t)pos;
                         }
                     }
@@ -494,7 +507,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
 #pragma unroll
                         for (int t = 0; t < 4; t++) {
                             if (t < nv) {
-                                const unsigned long long pos = wt.wbase[own[t]] + rank[t];
+                                const unsigned long long pos = wt.part.wbase[own[t]] + rank[t];
                                 if (pos < a.send_cap) a.peer_send[own[t]][a.send_region_off + pos] = h[t];
                             }
                         }
@@ -504,17 +517,17 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
 #pragma unroll
                         for (int t = 0; t < 4; t++) {
                             if (t < nv) {
-                                const unsigned slot = wt.wpre[own[t]] + rank[t];
-                                const unsigned long long pos = wt.wbase[own[t]] + rank[t];
+                                const unsigned slot = wt.part.wpre[own[t]] + rank[t];
+                                const unsigned long long pos = wt.part.wbase[own[t]] + rank[t];
                                 stage_h[slot] = h[t];
-                                wt.dst[slot] = pos < a.send_cap ? a.peer_send[own[t]] + a.send_region_off + pos : nullptr;
+                                wt.part.dst[slot] = pos < a.send_cap ? a.peer_send[own[t]] + a.send_region_off + pos : nullptr;
                             }
                         }
                     }
                     __syncwarp();
-                    const unsigned total = wt.wpre[a.n_ranks - 1] + wt.wcnt[a.n_ranks - 1];
+                    const unsigned total = wt.part.wpre[a.n_ranks - 1] + wt.part.wcnt[a.n_ranks - 1];
                     for (unsigned j = lane; j < total; j += 32) {
-                        uint64_t* d = wt.dst[j];
+                        uint64_t* d = wt.part.dst[j];
                         if (d) *d = stage_h[j];
                     }
                 }
