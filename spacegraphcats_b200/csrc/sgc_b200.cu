@@ -298,9 +298,52 @@ int bits_for(int64_t n) {  // bits needed to represent values 0..n-1
     return b;
 }
 
-// sorted-unique the candidate keys in pairs_a[0..n) and build the CSR.  Synchronises.
+int pairs_to_csr_sorted(sgc_ctx* c, int64_t n, int64_t nseq, int64_t* d_ids_off, uint32_t* d_ids_out, int64_t ids_cap,
+                        int64_t* h_n_labels);
+
+// Candidate keys in pairs_a[0..n) -> CSR of distinct ascending ids per sequence.  Synchronises.
+// Bucketed path (csr2_* kernels) when every sequence has few candidates, else the radix-sort path.
 int pairs_to_csr(sgc_ctx* c, int64_t n, int64_t nseq, int64_t* d_ids_off, uint32_t* d_ids_out, int64_t ids_cap,
                  int64_t* h_n_labels) {
+    if (n <= 0 || nseq <= 0 || getenv("SGC_CSR_SORT"))
+        return pairs_to_csr_sorted(c, n, nseq, d_ids_off, d_ids_out, ids_cap, h_n_labels);
+    const int cap = c->num_sms * 16;
+    const unsigned long long* A = (const unsigned long long*)c->pairs_a.p;
+    TRY(ensure(c, c->pairs_b, (size_t)n * 8));       // run_ids (uint32 each) live in the sort's second buffer
+    TRY(ensure(c, c->tmp_idx, (size_t)(nseq + 1) * 8));  // start[] of the candidate runs
+    uint32_t* run_ids = (uint32_t*)c->pairs_b.p;
+    long long* start = (long long*)c->tmp_idx.p;
+    unsigned long long* cnt = (unsigned long long*)d_ids_off;  // the caller's offsets double as the counters
+    CU(cudaMemsetAsync(d_ids_off, 0, (size_t)(nseq + 1) * 8, c->stream));
+    CU(cudaMemsetAsync(&c->d_scal->csr_big, 0, sizeof(unsigned int), c->stream));
+    csr2_count_kernel<<<grid_for(n, 256, cap), 256, 0, c->stream>>>(A, n, cnt);
+    size_t tb = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, (long long*)cnt, start, nseq + 1, c->stream));
+    TRY(ensure(c, c->cub_tmp, tb));
+    CU(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tb, (long long*)cnt, start, nseq + 1, c->stream));
+    csr2_scatter_kernel<<<grid_for(n, 256, cap), 256, 0, c->stream>>>(A, n, start, cnt, run_ids);
+    csr2_finalize_kernel<<<grid_for(nseq, 256, cap), 256, 0, c->stream>>>(start, nseq, run_ids, cnt, c->d_scal);
+    CU(cub::DeviceScan::InclusiveSum(nullptr, tb, d_ids_off, d_ids_off, nseq + 1, c->stream));
+    TRY(ensure(c, c->cub_tmp, tb));
+    CU(cub::DeviceScan::InclusiveSum(c->cub_tmp.p, tb, d_ids_off, d_ids_off, nseq + 1, c->stream));
+    csr2_copy_kernel<<<grid_for(nseq, 256, cap), 256, 0, c->stream>>>(start, cnt, nseq, run_ids, d_ids_out, ids_cap);
+    c->launches += 4;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&c->d_scal->n_unique, d_ids_off + nseq, 8, cudaMemcpyDeviceToDevice, c->stream));
+    TRY(fetch_scalars(c));
+    if (c->h_scal->csr_big)  // some sequence has many candidate ids (long contigs, genome-sized queries)
+        return pairs_to_csr_sorted(c, n, nseq, d_ids_off, d_ids_out, ids_cap, h_n_labels);
+    if (h_n_labels) *h_n_labels = c->h_scal->n_unique;
+    TRY(bad_offsets_check(c));
+    if (c->h_scal->n_unique > ids_cap)
+        return fail(SGC_ERR_CAPACITY, "ids_cap %lld < %lld distinct (sequence, id) labels", (long long)ids_cap,
+                    (long long)c->h_scal->n_unique);
+    return SGC_OK;
+}
+
+// the general path: radix sort + unique of the candidate keys, any number of candidates per sequence
+int pairs_to_csr_sorted(sgc_ctx* c, int64_t n, int64_t nseq, int64_t* d_ids_off, uint32_t* d_ids_out, int64_t ids_cap,
+                        int64_t* h_n_labels) {
     CU(cudaMemsetAsync(d_ids_off, 0, (size_t)(nseq + 1) * 8, c->stream));
     CU(cudaMemsetAsync(&c->d_scal->n_unique, 0, sizeof(long long), c->stream));
     if (n > 0) {

@@ -197,6 +197,75 @@ __global__ void csr_count_kernel(const unsigned long long* __restrict__ uniq, co
     }
 }
 
+// ----------------------------------------------------------------------------------
+// label tail without a global sort (the common case: a handful of candidate ids per sequence):
+// count candidates per sequence -> exclusive scan -> scatter the ids into per-sequence runs -> one
+// thread per sequence sorts and de-duplicates its run -> scan of the distinct counts -> compact copy.
+// Sequences with more than CSR_SMALL candidates raise csr_big and the caller falls back to the
+// radix-sort path (pairs_to_csr_sorted), which handles any size.
+// ----------------------------------------------------------------------------------
+constexpr int CSR_SMALL = 24;
+
+__global__ void __launch_bounds__(256) csr2_count_kernel(const unsigned long long* __restrict__ pairs, long long n,
+                                                         unsigned long long* __restrict__ cnt) {
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&cnt[pairs[j] >> 32], 1ULL);
+}
+
+// cnt[] counts down to zero again: position = start + (remaining - 1)
+__global__ void __launch_bounds__(256) csr2_scatter_kernel(const unsigned long long* __restrict__ pairs, long long n,
+                                                           const long long* __restrict__ start,
+                                                           unsigned long long* __restrict__ cnt,
+                                                           uint32_t* __restrict__ run_ids) {
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long key = pairs[j];
+        const unsigned long long s = key >> 32;
+        const unsigned long long left = atomicAdd(&cnt[s], ~0ULL);  // -1
+        run_ids[start[s] + (long long)left - 1] = (uint32_t)key;
+    }
+}
+
+// sorts + de-duplicates run s in place, writes its distinct count to ids_off[s + 1]
+__global__ void __launch_bounds__(256) csr2_finalize_kernel(const long long* __restrict__ start, long long nseq,
+                                                            uint32_t* __restrict__ run_ids,
+                                                            unsigned long long* __restrict__ ids_off, Scalars* scal) {
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < nseq; s += (long long)gridDim.x * blockDim.x) {
+        const long long b = start[s];
+        const int n = (int)(start[s + 1] - b);
+        unsigned long long nu = 0;
+        if (n > CSR_SMALL) {
+            scal->csr_big = 1u;
+        } else if (n > 0) {
+            uint32_t v[CSR_SMALL];
+            for (int j = 0; j < n; j++) {  // insertion sort: runs are a few ids long
+                const uint32_t x = run_ids[b + j];
+                int p = j;
+                while (p > 0 && v[p - 1] > x) {
+                    v[p] = v[p - 1];
+                    p--;
+                }
+                v[p] = x;
+            }
+            int w = 0;
+            for (int j = 0; j < n; j++)
+                if (j == 0 || v[j] != v[j - 1]) run_ids[b + w++] = v[j];
+            nu = (unsigned long long)w;
+        }
+        ids_off[s + 1] = nu;
+    }
+}
+
+__global__ void __launch_bounds__(256) csr2_copy_kernel(const long long* __restrict__ start,
+                                                        const unsigned long long* __restrict__ ids_off, long long nseq,
+                                                        const uint32_t* __restrict__ run_ids, uint32_t* __restrict__ ids_out,
+                                                        long long ids_cap) {
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < nseq; s += (long long)gridDim.x * blockDim.x) {
+        const long long o = (long long)ids_off[s], n = (long long)ids_off[s + 1] - o, b = start[s];
+        for (long long j = 0; j < n; j++)
+            if (o + j < ids_cap) ids_out[o + j] = run_ids[b + j];
+    }
+}
+
 // per-k-mer ids (already looked up, possibly on other ranks) -> candidate (seq, id) keys
 __global__ void ids_to_pairs_kernel(const uint32_t* __restrict__ kmer_ids, const int64_t* __restrict__ kmer_off,
                                     int64_t nseq, unsigned long long* pairs, unsigned long long cap, Scalars* scal) {

@@ -89,6 +89,8 @@ struct Scalars {
     long long n_unique;
     unsigned int round_ctr;
     unsigned int max_id;
+    unsigned int csr_big;  // label tail: a sequence has more candidate ids than the per-thread path sorts
+    unsigned int pad_;
     int err;  // bit 0: table full, bit 1: id out of range
     int bad_offsets;  // set by the plan when an offset pair is negative, decreasing or past seq_bytes
 };
