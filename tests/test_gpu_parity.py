@@ -1061,3 +1061,37 @@ def test_mphf_error_paths(ctx, dory_dump):
     d = DeviceMphf.build(ctx, np.array([7, 7, 9], np.uint64))
     assert d.info()["n_final"] == 2
     m.close(), d.close()
+
+
+def test_label_tail_small_runs_and_sorted_fallback(ctx, O, monkeypatch):
+    """The label tail groups candidate ids per sequence without a global sort when every sequence has
+    few of them, and falls back to the radix-sort path as soon as one sequence has many (long contigs):
+    both must give the oracle's CSR, alone and mixed in one batch."""
+    from spacegraphcats_b200.cdbg.hashing import GpuKmerTable
+    from spacegraphcats_b200.device import pack_sequences
+
+    rng = np.random.default_rng(33)
+    k = 21
+    g = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 60_000)]
+    cuts = np.concatenate([[0], np.cumsum(rng.integers(1, 40, 5000))])
+    cuts = cuts[cuts < len(g) - k]
+    useqs = [g[a : b + k - 1].tobytes() for a, b in zip(cuts[:-1], cuts[1:])]
+    ubuf, uoff = pack_sequences(useqs)
+    otab, _, _ = O.build_mphf(k, lambda: iter(O.Record(str(i), s.decode()) for i, s in enumerate(useqs)))
+    ot = O.COracleTable(otab.mphf_to_hash, otab.mphf_to_value)
+    short = [g[p : p + 100].tobytes() for p in rng.integers(0, len(g) - 6000, 3000)]       # <= ~6 ids each
+    longs = [g[p : p + 5000].tobytes() for p in rng.integers(0, len(g) - 6000, 5)]         # hundreds of ids each
+    edge = [g[p : p + 24 * 20].tobytes() for p in rng.integers(0, len(g) - 6000, 50)]      # around the 24-id limit
+    for side in (True, False):
+        table = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx, side=side)
+        for batch in (short, short[:500] + longs + short[500:1000], edge + short[:100], longs):
+            buf, off = pack_sequences(batch)
+            o_off, o_ids, o_nk, o_nh = ot.label_reads(buf, off, k)
+            res = table.label_reads(buf, off, k)
+            assert (res["n_kmers"], res["n_hits"]) == (o_nk, o_nh)
+            assert np.array_equal(res["ids_off"], o_off) and np.array_equal(res["ids"], o_ids)
+            monkeypatch.setenv("SGC_CSR_SORT", "1")  # force the general path: same answer
+            res2 = table.label_reads(buf, off, k)
+            monkeypatch.delenv("SGC_CSR_SORT")
+            assert np.array_equal(res2["ids_off"], o_off) and np.array_equal(res2["ids"], o_ids)
+    assert max(np.diff(o_off)) > 24  # the last batch (long contigs) really exceeded the per-thread limit
