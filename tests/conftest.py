@@ -26,3 +26,12 @@ def golden():
 
 def golden_path(*p):
     return os.path.join(GOLDEN, *p)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _library_built():
+    """Every test may touch libsgc_b200.so (the host feeder runs without a GPU): build it once per
+    session (a no-op when it is up to date; nvcc cross-compiles without a GPU)."""
+    import __graft_entry__ as g
+
+    g.build()
