@@ -559,7 +559,7 @@ int sgc_table_enable_side(sgc_table* t) {
     sgc_ctx* c = t->ctx;
     TRY(set_device(c));
     const int64_t cap = std::max<int64_t>(t->max_entries, 64);
-    if (cap >= (int64_t)AUX_NONE) return fail(SGC_ERR_CAPACITY, "side array limited to 2^31-2 records");
+    if (cap >= (int64_t)AUX_NONE) return fail(SGC_ERR_CAPACITY, "side array limited to 2^30-2 records");
     cudaError_t e = cudaMalloc(&t->side, (size_t)cap * sizeof(uint4));
     if (e != cudaSuccess) {
         t->side = nullptr;

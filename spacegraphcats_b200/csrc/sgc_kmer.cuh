@@ -183,6 +183,13 @@ template <int K>
 SGC_HD uint64_t hash_group_kmer(const uint32_t* fwin, const uint32_t* rwin, int t) {
     return murmur3_h1_window<K>(fwin, t) ^ murmur3_h1_window<K>(rwin, 3 - t);
 }
+// ... and whether the forward k-mer hashes below its reverse complement (the side array's orientation bit)
+template <int K>
+SGC_HD uint64_t hash_group_kmer_ori(const uint32_t* fwin, const uint32_t* rwin, int t, bool& fwd_less) {
+    const uint64_t hf = murmur3_h1_window<K>(fwin, t), hr = murmur3_h1_window<K>(rwin, 3 - t);
+    fwd_less = hf < hr;
+    return hf ^ hr;
+}
 
 // ---------------------------------------------------------------------------
 // Runtime-k path (any 1 <= k <= 255): stream the key out of a 4-byte aligned

@@ -53,15 +53,20 @@ struct Geo {
 // when it arrived and slots are never freed, so a walk stops at the first bucket that is not
 // full -- and it only starts if the home bucket's overflow bit says that some key homed there
 // lives elsewhere (a miss in an un-flagged home bucket costs ONE sector even when it is full).
-// aux[30:0] = index of the k-mer in the table's unitig-ordered side array (AUX_NONE if none);
+// aux[29:0] = index of the k-mer in the table's unitig-ordered side array (AUX_NONE if none);
+// aux[30] = orientation of the k-mer as stored: set when Murmur3(kmer) < Murmur3(revcomp(kmer)) for
+// the k-mer as it is written in its unitig.  A read k-mer with the same hash and the same bit lies on
+// the unitig's strand (its successors are at g+1, g+2, ...), with the opposite bit on the other strand
+// (g-1, g-2, ...), so only one direction of side records has to be fetched;
 // aux[31] of slot 0 = the bucket's overflow bit.
 struct __align__(16) Entry {
     unsigned long long key;
     unsigned int val;  // VAL_EMPTY = free slot, VAL_MULTI = dropped hash, else unitig id
-    unsigned int aux;  // side-array position (31 bits) | overflow bit (slot 0)
+    unsigned int aux;  // side-array position (30 bits) | orientation bit | overflow bit (slot 0)
 };
-constexpr uint32_t AUX_NONE = 0x7FFFFFFFu;
-constexpr uint32_t AUX_MASK = 0x7FFFFFFFu;
+constexpr uint32_t AUX_NONE = 0x3FFFFFFFu;   // as a position: "no side record"
+constexpr uint32_t AUX_MASK = 0x3FFFFFFFu;
+constexpr uint32_t ORI_BIT = 0x40000000u;
 constexpr uint32_t OVF_BIT = 0x80000000u;
 struct __align__(32) Bucket {
     Entry e[2];

@@ -53,8 +53,8 @@ __device__ __forceinline__ bool cas_entry(Entry* p, const Entry& expect, const E
 __device__ __forceinline__ uint32_t resolve_val(uint32_t v) { return v >= VAL_MULTI ? SGC_MISS : v; }
 
 __device__ __forceinline__ bool bucket_match(const Entry& e0, const Entry& e1, uint64_t h, uint32_t& out, uint32_t& aux) {
-    if (e0.key == h && e0.val != VAL_EMPTY) { out = resolve_val(e0.val); aux = e0.aux & AUX_MASK; return true; }
-    if (e1.key == h && e1.val != VAL_EMPTY) { out = resolve_val(e1.val); aux = e1.aux & AUX_MASK; return true; }
+    if (e0.key == h && e0.val != VAL_EMPTY) { out = resolve_val(e0.val); aux = e0.aux & ~OVF_BIT; return true; }
+    if (e1.key == h && e1.val != VAL_EMPTY) { out = resolve_val(e1.val); aux = e1.aux & ~OVF_BIT; return true; }
     return false;
 }
 // true when some key whose home is this bucket was placed in a later bucket
@@ -119,7 +119,7 @@ __device__ void table_insert(Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, 
                              Scalars* scal) {
     const uint32_t hb = home_bucket(h, nb, hs);
     const Entry empty{0ULL, VAL_EMPTY, 0u};
-    const Entry mine{h, id, aux & AUX_MASK};
+    const Entry mine{h, id, aux & (AUX_MASK | ORI_BIT)};
     const uint32_t max_steps = nlines > (1u << 20) ? (4u << 20) : nlines * 4u;
     for (uint32_t step = 0; step < max_steps; step++) {
         Bucket* bp = tbl + probe_bucket(hb, step, nlines);

@@ -340,7 +340,9 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
         const int G = wt.gpre[SPW];
 
         // locate group g (segment sg, first k-mer i, nv valid k-mers) and hash its 4 k-mers
-        auto locate_and_hash = [&](int g, int& sg, int& i, int& nv, uint64_t (&h)[4]) {
+        // ori (MODE_INSERT / MODE_LABEL_SIDE only): bit t = forward k-mer t hashes below its reverse complement
+        constexpr bool WANT_ORI = MODE == MODE_INSERT || MODE == MODE_LABEL_SIDE;
+        auto locate_and_hash = [&](int g, int& sg, int& i, int& nv, uint64_t (&h)[4], unsigned& ori) {
             int lo = 0;  // largest sg with gpre[sg] <= g
 #pragma unroll
             for (int step = SPW / 2; step > 0; step >>= 1)
@@ -362,12 +364,22 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                     rw[j] = rp[j];
                 }
 #pragma unroll
-                for (int t = 0; t < 4; t++) h[t] = sgc::hash_group_kmer<K ? K : 1>(fw, rw, t);
+                for (int t = 0; t < 4; t++) {
+                    if constexpr (WANT_ORI) {
+                        bool fl;
+                        h[t] = sgc::hash_group_kmer_ori<K ? K : 1>(fw, rw, t, fl);
+                        ori |= (unsigned)fl << t;
+                    } else {
+                        h[t] = sgc::hash_group_kmer<K ? K : 1>(fw, rw, t);
+                    }
+                }
             } else {
                 for (int t = 0; t < nv; t++) {
                     int q = i + t;
-                    h[t] = sgc::murmur3_h1_stream(Fs, q, k) ^
-                           sgc::murmur3_h1_stream(Rs, sgc::rc_byte_of(nk, nk - 1 - q), k);
+                    const uint64_t hf = sgc::murmur3_h1_stream(Fs, q, k);
+                    const uint64_t hr = sgc::murmur3_h1_stream(Rs, sgc::rc_byte_of(nk, nk - 1 - q), k);
+                    h[t] = hf ^ hr;
+                    if constexpr (WANT_ORI) ori |= (unsigned)(hf < hr) << t;
                 }
             }
         };
@@ -427,7 +439,8 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                 if (g >= G) continue;
                 int sg, i, nv;
                 uint64_t h[4] = {0, 0, 0, 0};
-                locate_and_hash(g, sg, i, nv, h);
+                unsigned ori = 0;
+                locate_and_hash(g, sg, i, nv, h, ori);
                 if constexpr (MODE == MODE_HASH) {
                     uint64_t* o = a.hash_out + wt.kout[sg] + i;
 #pragma unroll
@@ -442,7 +455,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                         for (int t = 0; t < nv; t++) {
                             uint32_t aux = AUX_NONE;
                             if (a.side) {  // unitig-ordered record; its id is fixed up after the build
-                                aux = (uint32_t)(g0 + t);
+                                aux = (uint32_t)(g0 + t) | (((ori >> t) & 1u) ? ORI_BIT : 0u);
                                 a.side[g0 + t] = make_uint4((uint32_t)h[t], (uint32_t)(h[t] >> 32), id, 0u);
                             }
                             table_insert(a.tbl, a.nbuckets, a.nlines, a.home_shift, h[t], id, aux, a.scal);
@@ -461,7 +474,8 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                 const bool active = g < G;
                 int sg = 0, i = 0, nv = 0;
                 uint64_t h[4] = {0, 0, 0, 0};
-                if (active) locate_and_hash(g, sg, i, nv, h);
+                unsigned ori_unused = 0;
+                if (active) locate_and_hash(g, sg, i, nv, h, ori_unused);
                 if (lane < a.n_ranks) wt.part.wcnt[lane] = 0;
                 __syncwarp();
                 uint32_t own[4], rank[4];
@@ -580,42 +594,47 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
             // not matched (sequencing errors, unitig ends, anchor missing) is queued per warp and probed
             // later DENSELY (every lane busy, probes pipelined), so the result is exactly what per-k-mer
             // probing gives.  Neighbouring threads share side lines.
+            // No cross-trip pipeline here: ptxas serialises it anyway (it waits for the probe at the top
+            // of the next trip) and the state it carries costs registers that the
+            // 24-warps-per-SM build does not have.  Latency is hidden by the other resident warps.
             bool p_active = false;
             int p_sg = 0, p_i = 0, p_nv = 0;
             uint64_t p_h[4] = {0, 0, 0, 0};
             uint32_t p_b0 = 0;
+            bool p_fl = false;  // orientation bit of the anchor as the read has it
             Entry p_e0, p_e1;
 
             auto resolve = [&]() {
                 uint32_t ids[4] = {SGC_MISS, SGC_MISS, SGC_MISS, SGC_MISS};
                 unsigned pending = 0;
                 if (p_active) {
-                    uint32_t v = SGC_MISS, g = AUX_NONE;
-                    if (!bucket_match(p_e0, p_e1, p_h[0], v, g)) {
+                    uint32_t v = SGC_MISS, aux = AUX_NONE;
+                    if (!bucket_match(p_e0, p_e1, p_h[0], v, aux)) {
                         v = SGC_MISS;
-                        g = AUX_NONE;
-                        if (bucket_overflowed(p_e0)) v = lookup_slow(a.tbl, a.nlines, p_b0, p_h[0], g);
+                        aux = AUX_NONE;
+                        if (bucket_overflowed(p_e0)) v = lookup_slow(a.tbl, a.nlines, p_b0, p_h[0], aux);
                     }
                     ids[0] = v;
                     pending = ((1u << p_nv) - 1u) & ~1u;  // k-mers 1..nv-1 until proven otherwise
+                    const uint32_t g = aux & AUX_MASK;
                     if (g != AUX_NONE) {
-                        uint4 up[3], um[3];
+                        // same orientation bit as the stored k-mer: the read runs along the unitig (g+1, g+2,
+                        // g+3), else against it (g-1, ...).  A wrong guess (palindromes, repeats, colliding
+                        // hashes) only means the k-mers are not matched here and take the queue.
+                        const bool along = ((aux & ORI_BIT) != 0) == p_fl;
+                        uint4 nb[3];
 #pragma unroll
                         for (int d = 1; d < 4; d++) {
-                            const bool hi_ok = d < p_nv && (unsigned long long)g + d < a.side_n;
-                            const bool lo_ok = d < p_nv && g >= (uint32_t)d;
-                            up[d - 1] = hi_ok ? __ldg(a.side + g + d) : make_uint4(0, 0, SGC_MISS, 1);
-                            um[d - 1] = lo_ok ? __ldg(a.side + g - d) : make_uint4(0, 0, SGC_MISS, 1);
+                            const bool ok = d < p_nv && (along ? (unsigned long long)g + d < a.side_n : g >= (uint32_t)d);
+                            const long long pos = along ? (long long)g + d : (long long)g - d;
+                            nb[d - 1] = ok ? __ldg(a.side + pos) : make_uint4(0, 0, SGC_MISS, 1);
                         }
 #pragma unroll
                         for (int d = 1; d < 4; d++) {
                             if (d < p_nv) {
                                 const uint32_t lo = (uint32_t)p_h[d], hi = (uint32_t)(p_h[d] >> 32);
-                                if (up[d - 1].x == lo && up[d - 1].y == hi && up[d - 1].w == 0) {
-                                    ids[d] = up[d - 1].z;
-                                    pending &= ~(1u << d);
-                                } else if (um[d - 1].x == lo && um[d - 1].y == hi && um[d - 1].w == 0) {
-                                    ids[d] = um[d - 1].z;
+                                if (nb[d - 1].x == lo && nb[d - 1].y == hi && nb[d - 1].w == 0) {
+                                    ids[d] = nb[d - 1].z;
                                     pending &= ~(1u << d);
                                 }
                             }
@@ -652,28 +671,21 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                 emit_candidates(ids, p_active, p_sg, p_i, p_nv);  // queued k-mers count as "no id" here
             };
 
-            // one trip more than there are groups: the last trip only resolves (single call site per
-            // lambda, see drain_queue); the warp's last round also empties the queue
-            const bool last_round = (int64_t)rq0 >= nrounds;
-            const int G1 = (G > 0 || (last_round && q_fill)) ? G + 32 : 0;
+            const bool last_round = (int64_t)rq0 >= nrounds;  // the warp's last round also empties the queue
+            const int G1 = (G > 0 || !(last_round && q_fill)) ? G : 32;
             for (int g0 = 0; g0 < G1; g0 += 32) {
                 const int g = g0 + lane;
-                const bool active = g < G;
-                int sg = 0, i = 0, nv = 0;
-                uint64_t h[4] = {0, 0, 0, 0};
-                if (active) locate_and_hash(g, sg, i, nv, h);   // the previous group's anchor probe is in flight here
-                {
-                    const uint64_t dep = (h[0] ^ h[1] ^ h[2] ^ h[3]) & a.zero;  // see MODE_LABEL
+                p_active = g < G;
+                p_sg = 0; p_i = 0; p_nv = 0;
 #pragma unroll
-                    for (int t = 0; t < 4; t++) p_h[t] ^= dep;
-                }
-                if (g0 > 0) resolve();
-                if (q_fill > QCAP - 96 || (last_round && g0 >= G && q_fill)) drain_queue();
-                p_active = active; p_sg = sg; p_i = i; p_nv = nv;
-#pragma unroll
-                for (int t = 0; t < 4; t++) p_h[t] = h[t];
-                p_b0 = active ? home_bucket(h[0], a.nbuckets, a.home_shift) : 0u;
-                load_bucket_nc(a.tbl + p_b0, p_e0, p_e1);  // unconditional (bucket 0 in the last trip)
+                for (int t = 0; t < 4; t++) p_h[t] = 0;
+                unsigned ori = 0;
+                if (p_active) locate_and_hash(g, p_sg, p_i, p_nv, p_h, ori);
+                p_fl = (ori & 1u) != 0;
+                p_b0 = p_active ? home_bucket(p_h[0], a.nbuckets, a.home_shift) : 0u;
+                load_bucket_nc(a.tbl + p_b0, p_e0, p_e1);  // idle lanes probe bucket 0 (an L2 hit)
+                resolve();
+                if (q_fill > QCAP - 96 || (last_round && g0 + 32 >= G && q_fill)) drain_queue();
             }
             __syncwarp();
         } else {
@@ -748,7 +760,8 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                 const bool active = g < G;
                 int sg = 0, i = 0, nv = 0;
                 uint64_t h[4] = {0, 0, 0, 0};
-                if (active) locate_and_hash(g, sg, i, nv, h);   // previous group's probes are in flight here
+                unsigned ori_unused = 0;
+                if (active) locate_and_hash(g, sg, i, nv, h, ori_unused);   // previous group's probes are in flight here
                 // Order the resolve AFTER the hash computation in the instruction stream: a.zero is
                 // always 0 but only known at run time, so the compares below truly depend on the new
                 // hashes and neither nvcc nor ptxas can sink the Murmur3 code under the resolve.
