@@ -11,13 +11,16 @@ namespace dev {
 // ----------------------------------------------------------------------------------
 // tile geometry
 // ----------------------------------------------------------------------------------
-// Resident CTAs per SM the probing kernels are compiled for.  3 x 256 threads = 24 warps per SM at 80
-// registers (the label kernels fit with at most a few spilled words): these kernels wait on dependent
-// HBM/L2 loads, and ptxas will not overlap a load with arithmetic across a loop trip or a forward branch
-// (it drains the load's scoreboard there), so the latency is hidden by resident warps instead:
-// 16 -> 24 warps took the side-array label kernel from 53 to 62 G k-mers/s; 27 warps gave no more.
+// Resident CTAs per SM the probing kernels are compiled for.  These kernels wait on dependent HBM/L2
+// loads, and ptxas will not overlap a load with arithmetic across a loop trip or a forward branch (it
+// drains the load's scoreboard there), so the latency is hidden by resident warps instead.  The
+// side-array label kernel fits in 64 registers without spilling: 4 CTAs x 256 threads = 32 warps per SM
+// (16 warps: 53 G k-mers/s, 24: 62-67, 27: 70); the per-k-mer kernels need 80 registers: 3 CTAs.
 #ifndef SGC_PROBE_MIN_CTAS
 #define SGC_PROBE_MIN_CTAS 3
+#endif
+#ifndef SGC_SIDE_MIN_CTAS
+#define SGC_SIDE_MIN_CTAS 4
 #endif
 #ifndef SGC_NT
 #define SGC_NT 256
@@ -28,7 +31,7 @@ constexpr int SPW = 4;          // segments staged per warp round (8 lanes stage
 constexpr int SEG_K = 256;      // k-mers per segment
 constexpr int PAIR_BUF = 128;   // label keys staged per warp before one global reservation
 #ifndef SGC_QCAP
-#define SGC_QCAP 192            // 3 CTAs x 8 warps x (tile + queue) must fit 227 KB of shared memory
+#define SGC_QCAP 128            // 4 CTAs x 8 warps x (tile + queue) must fit 227 KB of shared memory
 #endif
 constexpr int QCAP = SGC_QCAP;  // MODE_LABEL_SIDE: k-mers queued per warp for a dense table probe
 constexpr unsigned long long SEQ_MASK = (1ULL << 40) - 1ULL;

@@ -92,7 +92,7 @@ template <int K, bool PART = false>
 struct alignas(16) WarpTile {
     uint32_t F[SPW * Geo<K>::WPS];
     uint32_t R[SPW * Geo<K>::WPS];
-    uint32_t RAW[2][SPW * Geo<K>::WPS];  // 16-byte-aligned raw copies of the segments (cp.async), double-buffered
+    uint32_t RAW[SPW * Geo<K>::WPS];     // 16-byte-aligned raw copies of the next round's segments (cp.async)
     SegDesc D[3][SPW];                   // prefetched descriptors of this round and the next two
     unsigned long long pairs[PAIR_BUF];
     long long start[SPW];
@@ -105,7 +105,7 @@ struct alignas(16) WarpTile {
 };
 
 template <int K, int MODE>
-__global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP || MODE == MODE_LABEL_SIDE) ? SGC_PROBE_MIN_CTAS : 1) tile_kernel(const TileArgs a) {
+__global__ void __launch_bounds__(NT, MODE == MODE_LABEL_SIDE ? SGC_SIDE_MIN_CTAS : (MODE == MODE_LABEL || MODE == MODE_LOOKUP) ? SGC_PROBE_MIN_CTAS : 1) tile_kernel(const TileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int WPS = Geo<K>::WPS;
     const int lane = threadIdx.x & 31;
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
             }
         }
     };
-    auto prefetch_raw = [&](int buf, int slot) {
+    auto prefetch_raw = [&](int slot) {
         if constexpr (MODE != MODE_GATHER) {
             const int sgi = lane >> 3, sub = lane & 7;
             const SegDesc& d = wt.D[slot][sgi];
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                 const uintptr_t g0 = (uintptr_t)a.seq + (uintptr_t)d.start;
                 const uintptr_t a0 = g0 & ~(uintptr_t)15;
                 const int nchunks = (int)(((g0 + (uintptr_t)Ls + 15) & ~(uintptr_t)15) - a0) >> 4;
-                unsigned char* dst = reinterpret_cast<unsigned char*>(wt.RAW[buf] + sgi * WPS) + 16;
+                unsigned char* dst = reinterpret_cast<unsigned char*>(wt.RAW + sgi * WPS) + 16;
                 for (int c = sub; c < nchunks; c += 8)
                     cp_async16(dst + 16 * c, reinterpret_cast<const void*>(a0 + 16 * (uintptr_t)c));
             }
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
     cp_async_commit();
     cp_async_wait_all();
     __syncwarp();
-    prefetch_raw(0, 0);
+    prefetch_raw(0);
     cp_async_commit();
     cp_async_wait_all();
     __syncwarp();
@@ -275,10 +275,10 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
     for (unsigned it = 0;; it++) {
         const unsigned round = rq0;
         if ((int64_t)round >= nrounds) break;
-        const int cur = it % 3, nxt = (it + 1) % 3, nx2 = (it + 2) % 3, buf = it & 1;
-        // top of the round: launch the copies for the next rounds
+        const int cur = it % 3, nxt = (it + 1) % 3, nx2 = (it + 2) % 3;
+        // top of the round: launch the descriptor copy for the round after next (the raw bytes of the
+        // next round follow as soon as this round's staging has released the raw area)
         prefetch_desc(nx2, rq2);
-        prefetch_raw(buf ^ 1, nxt);
         cp_async_commit();
         rq0 = rq1;
         rq1 = rq2;
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
             if (nk) {
                 const int Ls = nk + k - 1;
                 const int r0 = (int)(((uintptr_t)a.seq + (uintptr_t)wt.start[sg]) & 15);
-                const uint32_t* raw = wt.RAW[buf] + sg * WPS;
+                const uint32_t* raw = wt.RAW + sg * WPS;
                 uint32_t* Fs = wt.F + sg * WPS;
                 uint32_t* Rs = wt.R + sg * WPS;
                 const int p = sgc::rc_pad(nk);
@@ -335,6 +335,8 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
             }
         }
         __syncwarp();
+        prefetch_raw(nxt);  // lands while this round is hashed
+        cp_async_commit();
 
         // ---- hash + sink ----
         const int G = wt.gpre[SPW];
