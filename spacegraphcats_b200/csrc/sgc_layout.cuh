@@ -14,10 +14,10 @@ namespace dev {
 // Resident CTAs per SM the probing kernels are compiled for.  These kernels wait on dependent HBM/L2
 // loads, and ptxas will not overlap a load with arithmetic across a loop trip or a forward branch (it
 // drains the load's scoreboard there), so the latency is hidden by resident warps instead.  The
-// side-array label kernel fits in 64 registers without spilling: 4 CTAs x 256 threads = 32 warps per SM
-// (16 warps: 53 G k-mers/s, 24: 62-67, 27: 70); the per-k-mer kernels need 80 registers: 3 CTAs.
+// label / lookup kernels fit in 64 registers without spilling once they carry no cross-trip state:
+// 4 CTAs x 256 threads = 32 warps per SM (side-array kernel: 16 warps 53 G k-mers/s, 24: 62-67, 27: 70, 32: 71.5).
 #ifndef SGC_PROBE_MIN_CTAS
-#define SGC_PROBE_MIN_CTAS 3
+#define SGC_PROBE_MIN_CTAS 4
 #endif
 #ifndef SGC_SIDE_MIN_CTAS
 #define SGC_SIDE_MIN_CTAS 4

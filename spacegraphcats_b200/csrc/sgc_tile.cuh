@@ -691,9 +691,8 @@ __global__ void __launch_bounds__(NT, MODE == MODE_LABEL_SIDE ? SGC_SIDE_MIN_CTA
             }
             __syncwarp();
         } else {
-            // MODE_LOOKUP / MODE_LABEL, software-pipelined: the 4 table probes of a group are issued
-            // and left in flight while the NEXT group's 8 Murmur3 evaluations run; they are resolved
-            // one iteration later.  Integer pipe and HBM latency overlap inside a thread.
+            // MODE_LOOKUP / MODE_LABEL: every k-mer of a group probes its home bucket (4 loads in flight per
+            // thread), resolved right away; the latency is covered by the other resident warps.
             bool p_active = false;
             int p_sg = 0, p_i = 0, p_nv = 0;
             uint64_t p_h[4] = {0, 0, 0, 0};
@@ -756,32 +755,22 @@ __global__ void __launch_bounds__(NT, MODE == MODE_LABEL_SIDE ? SGC_SIDE_MIN_CTA
                 }
             };
 
-            const int G1 = G > 0 ? G + 32 : 0;  // one trip more than there are groups: the last one only resolves
-            for (int g0 = 0; g0 < G1; g0 += 32) {
+            // no cross-trip pipeline (see MODE_LABEL_SIDE): hash, probe, resolve inside one trip
+            for (int g0 = 0; g0 < G; g0 += 32) {
                 const int g = g0 + lane;
-                const bool active = g < G;
-                int sg = 0, i = 0, nv = 0;
-                uint64_t h[4] = {0, 0, 0, 0};
-                unsigned ori_unused = 0;
-                if (active) locate_and_hash(g, sg, i, nv, h, ori_unused);   // previous group's probes are in flight here
-                // Order the resolve AFTER the hash computation in the instruction stream: a.zero is
-                // always 0 but only known at run time, so the compares below truly depend on the new
-                // hashes and neither nvcc nor ptxas can sink the Murmur3 code under the resolve.
-                {
-                    const uint64_t dep = (h[0] ^ h[1] ^ h[2] ^ h[3]) & a.zero;
+                p_active = g < G;
+                p_sg = 0; p_i = 0; p_nv = 0;
 #pragma unroll
-                    for (int t = 0; t < 4; t++) p_h[t] ^= dep;
-                }
-                if (g0 > 0) resolve();
-                p_active = active; p_sg = sg; p_i = i; p_nv = nv;
+                for (int t = 0; t < 4; t++) p_h[t] = 0;
+                unsigned ori_unused = 0;
+                if (p_active) locate_and_hash(g, p_sg, p_i, p_nv, p_h, ori_unused);
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
-                    p_h[t] = h[t];
-                    // lanes / k-mers with nothing to look up probe bucket 0 (an L2 hit) so that the
-                    // loads are unconditional and land directly in the pipeline registers
-                    p_b[t] = (active && t < nv) ? home_bucket(h[t], a.nbuckets, a.home_shift) : 0u;
+                    // lanes / k-mers with nothing to look up probe bucket 0 (an L2 hit): no branch around the loads
+                    p_b[t] = (p_active && t < p_nv) ? home_bucket(p_h[t], a.nbuckets, a.home_shift) : 0u;
                     load_bucket_nc(a.tbl + p_b[t], p_e0[t], p_e1[t]);
                 }
+                resolve();
             }
             __syncwarp();
         }
