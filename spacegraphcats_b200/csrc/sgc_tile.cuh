@@ -104,6 +104,17 @@ struct alignas(16) WarpTile {
     typename std::conditional<PART, PartitionState, NoPartitionState>::type part;  // last: keeps the copies above aligned
 };
 
+// one global reservation for the keys a warp has staged, then a coalesced copy
+__device__ __noinline__ void flush_pairs_out(Scalars* scal, unsigned long long* pairs, unsigned long long cap,
+                                             const unsigned long long* staged, unsigned n, int lane) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&scal->pair_count, (unsigned long long)n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (unsigned j = lane; j < n; j += 32)
+        if (base + j < cap) pairs[base + j] = staged[j];
+    __syncwarp();
+}
+
 template <int K, int MODE>
 __global__ void __launch_bounds__(NT, MODE == MODE_LABEL_SIDE ? SGC_SIDE_MIN_CTAS : (MODE == MODE_LABEL || MODE == MODE_LOOKUP) ? SGC_PROBE_MIN_CTAS : 1) tile_kernel(const TileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -117,13 +128,8 @@ __global__ void __launch_bounds__(NT, MODE == MODE_LABEL_SIDE ? SGC_SIDE_MIN_CTA
     unsigned long long my_hits = 0, my_miss = 0;
     unsigned pair_fill = 0;  // warp-uniform: keys waiting in wt.pairs
 
-    auto flush_pairs = [&]() {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&a.scal->pair_count, (unsigned long long)pair_fill);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for (unsigned j = lane; j < pair_fill; j += 32)
-            if (base + j < a.pairs_cap) a.pairs[base + j] = wt.pairs[j];
-        __syncwarp();
+    auto flush_pairs = [&]() {  // cold (once per ~40 trips): kept out of line so the hot loops stay small
+        flush_pairs_out(a.scal, a.pairs, a.pairs_cap, wt.pairs, pair_fill, lane);
         pair_fill = 0;
     };
 
