@@ -16,9 +16,13 @@ from ..device import DeviceMphf, DeviceTable, get_context, pack_sequences
 from .._lib import SGC_MISS, SGC_MAX_K
 
 
-def side_default():
-    """Tables built from unitig sequences keep the unitig-ordered side array unless SGC_SIDE=0."""
-    return os.environ.get("SGC_SIDE", "1") != "0"
+SIDE_MAX_KMERS = (1 << 30) - 2  # side-array positions are 30 bits of the slot's aux word
+
+
+def side_default(n_kmers=0):
+    """Tables built from unitig sequences keep the unitig-ordered side array unless SGC_SIDE=0
+    (or the table is too large for 30-bit positions: then every k-mer probes the table)."""
+    return os.environ.get("SGC_SIDE", "1") != "0" and n_kmers < SIDE_MAX_KMERS
 
 UNSET_VALUE = 2**32 - 1  # the reference's BBHashTable "unset" value (index_cdbg_by_kmer.py:24)
 
@@ -84,13 +88,13 @@ class GpuKmerTable:
         ``side`` (default on; ``SGC_SIDE=0`` or ``side=False`` turns it off) also keeps the k-mers in
         unitig order (16 B each) so that read labelling needs one table probe per four k-mers instead
         of four: identical labels, half the HBM traffic, 1.25x the labelling rate."""
-        if side is None:
-            side = side_default()
         t = cls(ctx)
         if isinstance(off, np.ndarray) or not hasattr(off, "device"):
             n_kmers = int(np.maximum(np.diff(off) - ksize + 1, 0).sum())
         else:  # CUDA tensors (already resident sequences)
             n_kmers = int((off[1:] - off[:-1] - (ksize - 1)).clamp_(min=0).sum().item())
+        if side is None:
+            side = side_default(n_kmers)
         t._dev = DeviceTable(t.ctx, max(n_kmers, 1))
         if side:
             t._dev.enable_side()

@@ -57,7 +57,7 @@ def build_mphf(ksize, records_iter_fn, ctx=None, verbose=True):
     from ..device import DeviceTable
 
     table._dev = DeviceTable(ctx, max(total_kmers, 1))
-    if side_default():  # unitig-ordered side array for read labelling; SGC_SIDE=0: off
+    if side_default(total_kmers):  # unitig-ordered side array for read labelling; SGC_SIDE=0: off
         table._dev.enable_side()
     lo = 0
     while lo < n_contigs:

@@ -83,7 +83,7 @@ class SyntheticCdbg:
         from .device import DeviceTable
 
         if side is None:
-            side = os.environ.get("SGC_SIDE", "1") != "0"
+            side = os.environ.get("SGC_SIDE", "1") != "0" and self.total_unitig_kmers < (1 << 30) - 2
 
         t = DeviceTable(self.ctx, self.total_unitig_kmers)
         if side:
