@@ -137,38 +137,32 @@ __global__ void __launch_bounds__(NT, MODE == MODE_LABEL_SIDE ? SGC_SIDE_MIN_CTA
     // unless the previous k-mer of the same segment has the same id (known through a warp shuffle;
     // the first k-mer of a lane-0 group is conservatively a candidate).  All 32 lanes must call this.
     auto emit_candidates = [&](const uint32_t (&ids)[4], bool active, int sg, int i, int nv) {
+        // ids[] of k-mers that do not exist (t >= nv, idle lanes) or have no id yet are SGC_MISS, so the
+        // rule needs no validity tests; slots are handed out with one ballot per k-mer position (the
+        // order of the keys inside the staging buffer is irrelevant, they are grouped per sequence later)
         const uint32_t prev_lane = __shfl_up_sync(0xffffffffu, ids[3], 1);
-        unsigned long long keys[4] = {0, 0, 0, 0};
-        unsigned nc = 0;
-        if (active) {
-            const unsigned long long sq = (unsigned long long)wt.seq[sg] << 32;
-            uint32_t prev = (i > 0 && lane > 0) ? prev_lane : SGC_MISS;
+        const uint32_t prev0 = (i > 0 && lane > 0) ? prev_lane : SGC_MISS;
+        bool cand[4];
+        unsigned m[4];
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
-                if (t < nv && ids[t] != SGC_MISS && ids[t] != prev) {
-#pragma unroll
-                    for (int u = 0; u < 4; u++)  // constant indices keep keys[] in registers
-                        if (u == (int)nc) keys[u] = sq | ids[t];
-                    nc++;
-                }
-                prev = ids[t];
-            }
+        for (int t = 0; t < 4; t++) {
+            cand[t] = ids[t] != SGC_MISS && ids[t] != (t == 0 ? prev0 : ids[t - 1]);
+            m[t] = __ballot_sync(0xffffffffu, cand[t]);
         }
-        unsigned incl = nc;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += v;
-        }
-        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        const unsigned c0 = __popc(m[0]), c1 = __popc(m[1]), c2 = __popc(m[2]), c3 = __popc(m[3]);
+        const unsigned total = c0 + c1 + c2 + c3;
         if (total) {
             if (pair_fill + total > PAIR_BUF) flush_pairs();
-            unsigned pos = pair_fill + incl - nc;
+            const unsigned long long sq = (unsigned long long)wt.seq[sg] << 32;
+            const unsigned lt = (1u << lane) - 1u;
+            const unsigned base[4] = {pair_fill, pair_fill + c0, pair_fill + c0 + c1, pair_fill + c0 + c1 + c2};
 #pragma unroll
-            for (unsigned j = 0; j < 4; j++)
-                if (j < nc) wt.pairs[pos++] = keys[j];
+            for (int t = 0; t < 4; t++)
+                if (cand[t]) wt.pairs[base[t] + __popc(m[t] & lt)] = sq | ids[t];
             pair_fill += total;
         }
+        (void)active;
+        (void)nv;
     };
 
     // MODE_LABEL_SIDE: per-warp queue of k-mers that still need their own table probe
