@@ -224,8 +224,9 @@ __global__ void __launch_bounds__(NT, MODE == MODE_LABEL_SIDE ? SGC_SIDE_MIN_CTA
     // ahead, and keeps two asynchronous copies in flight while it works on round r:
     //   descriptors of round r+2  (cp.async of SPW SegDesc, 32 bytes each)
     //   raw bytes of round r+1    (cp.async of the 16-byte chunks that cover each segment)
-    // both issued at the top of round r and waited for at its end, so they have a whole round to land;
-    // the staging of round r itself (re-alignment + reverse complement) reads shared memory only.
+    // the first issued at the top of round r, the second as soon as the staging of round r has released
+    // the single raw area; both are waited for at the end of the round, so they land while it is hashed.
+    // The staging of round r itself (re-alignment + reverse complement) reads shared memory only.
     // ------------------------------------------------------------------------------------------
     auto claim_round = [&]() -> unsigned {
         unsigned r = 0;
@@ -588,13 +589,13 @@ __global__ void __launch_bounds__(NT, MODE == MODE_LABEL_SIDE ? SGC_SIDE_MIN_CTA
             }
         } else if constexpr (MODE == MODE_LABEL_SIDE) {
             // K4 with fewer HBM lines per k-mer.  Only the FIRST k-mer of a group (the anchor) probes the
-            // hash table (software-pipelined like MODE_LABEL).  Its slot carries g, the k-mer's position in
+            // hash table.  Its slot carries g, the k-mer's position in
             // the table's unitig-ordered side array of {hash, id} records (id = what a table lookup of that
             // hash returns, fixed up after the build).  Consecutive k-mers of a read are consecutive
             // k-mers of the unitig, on one strand or the other, so k-mer t is looked for at side[g+t] and
             // side[g-t]: a full 64-bit hash match there IS the table's answer for that hash.  Anything
             // not matched (sequencing errors, unitig ends, anchor missing) is queued per warp and probed
-            // later DENSELY (every lane busy, probes pipelined), so the result is exactly what per-k-mer
+            // later DENSELY (every lane busy), so the result is exactly what per-k-mer
             // probing gives.  Neighbouring threads share side lines.
             // No cross-trip pipeline here: ptxas serialises it anyway (it waits for the probe at the top
             // of the next trip) and the state it carries costs registers that the
