@@ -114,7 +114,8 @@ int64_t sgc_table_bytes(const sgc_table* t);
 /* Optional unitig-ordered side array ({hash, id} per inserted k-mer, 16 B each, up to max_entries
  * records): call before sgc_table_insert_sequences.  With it sgc_label_reads probes the hash table
  * only for the first k-mer of every group of four and matches the others by full 64-bit hash
- * equality against the neighbouring unitig positions (fewer HBM lines per k-mer, identical result). */
+ * equality against the neighbouring unitig positions (fewer HBM lines per k-mer, identical result).
+ * SGC_ERR_CAPACITY when max_entries >= 2^30 - 1 (positions are 30 bits of a slot). */
 int sgc_table_enable_side(sgc_table* t);
 int64_t sgc_table_side_bytes(const sgc_table* t);
 /* hash-range partitioned tables: the top `shift` bits of every hash stored here are the owner
