@@ -5,7 +5,6 @@ breakdown of spacegraphcats_b200.cdbg.index_reads.main.  Not a bench line; numbe
 usage: index_reads_timing.py [n_reads=4000000] [table_kmers=50000000]"""
 import json
 import os
-import pickle
 import sys
 import tempfile
 import time

@@ -8,7 +8,6 @@ the reference's ``multicounts`` rule), and the observable result -- the exact ma
 consistency asserts -- is the same.
 """
 import argparse
-import os
 import sqlite3
 import sys
 

@@ -8,7 +8,6 @@ every k-mer of G lies in exactly one unitig; k-mers per unitig = 1 + Geometric(1
 windows of G at uniform positions, half of them reverse-complemented, iid substitution errors
 (seed 3 + batch index).
 """
-import ctypes
 
 import numpy as np
 
