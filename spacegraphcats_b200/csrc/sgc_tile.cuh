@@ -228,10 +228,19 @@ __global__ void __launch_bounds__(NT, MODE == MODE_LABEL_SIDE ? SGC_SIDE_MIN_CTA
     // the single raw area; both are waited for at the end of the round, so they land while it is hashed.
     // The staging of round r itself (re-alignment + reverse complement) reads shared memory only.
     // ------------------------------------------------------------------------------------------
+    // rounds are claimed two at a time (adjacent): half as many atomics to wait for
+    unsigned round_spare = 0xFFFFFFFFu;  // warp-uniform: the second round of the last claim, if still unused
     auto claim_round = [&]() -> unsigned {
+        if (round_spare != 0xFFFFFFFFu) {
+            const unsigned r = round_spare;
+            round_spare = 0xFFFFFFFFu;
+            return r;
+        }
         unsigned r = 0;
-        if (lane == 0) r = atomicAdd(&a.scal->round_ctr, 1u);
-        return __shfl_sync(0xffffffffu, r, 0);
+        if (lane == 0) r = atomicAdd(&a.scal->round_ctr, 2u);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        round_spare = r + 1u;
+        return r;
     };
     auto prefetch_desc = [&](int slot, unsigned round) {
         if (lane < 2 * SPW) {
