@@ -300,11 +300,6 @@ int sgc_bgzf_index(const uint8_t* h_raw, int64_t raw_bytes, int64_t* h_cstart, i
 /* Inflate all blocks in parallel into h_out (out_bytes = sum of h_usize); CRC32 of every block is checked. */
 int sgc_bgzf_inflate(const uint8_t* h_raw, int64_t raw_bytes, const int64_t* h_cstart, const int64_t* h_usize,
                      int64_t nblocks, int n_threads, uint8_t* h_out, int64_t out_bytes);
-/* BGZF writer (reference utils/make_bgzf.py): blocks of block_size <= 65280 input bytes, zlib level 0-9,
- * then the EOF marker block.  h_out needs sgc_bgzf_deflate_bound(n, block_size) bytes (-1: bad argument). */
-int64_t sgc_bgzf_deflate_bound(int64_t n, int block_size);
-int sgc_bgzf_deflate(const uint8_t* h_data, int64_t n, int block_size, int level, int n_threads, uint8_t* h_out,
-                     int64_t out_cap, int64_t* h_out_bytes);
 /* FASTA ('>') or 4-line FASTQ ('@') text: h_info[0..2] = records, total sequence bytes, format (0 FASTA, 1 FASTQ).
  * SGC_ERR_ARG: "unknown start chr", or a FASTQ record that is not '@' ... '+' ... */
 int sgc_reads_count(const uint8_t* h_data, int64_t n, int n_threads, int64_t* h_info);

@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, ".")
+sys.path.insert(0, "tests")
 import __graft_entry__ as g  # noqa: E402
 
 g.build()
@@ -20,7 +21,7 @@ from spacegraphcats_b200.cdbg import index_reads  # noqa: E402
 from spacegraphcats_b200.cdbg.hashing import GpuKmerTable, MPHF_KmerIndex  # noqa: E402
 from spacegraphcats_b200.device import get_context  # noqa: E402
 from spacegraphcats_b200.synth import SyntheticCdbg  # noqa: E402
-from spacegraphcats_b200.utils import bgzf  # noqa: E402
+from bgzf_writer import write_bgzf  # noqa: E402  (test-only BGZF writer)
 
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
 n_kmers = int(sys.argv[2]) if len(sys.argv) > 2 else 50_000_000
@@ -57,7 +58,7 @@ rec[:, 4 + name_w + RL : 7 + name_w + RL] = np.frombuffer(b"\n+\n", np.uint8)
 rec[:, -1] = 10
 t0 = time.time()
 reads_path = os.path.join(tmp, "reads.fq.bgz")
-bgzf.write_bgzf(reads_path, rec.reshape(-1), level=1)
+write_bgzf(reads_path, rec.reshape(-1), level=1)
 print("reads: %d x %d bp, %.2f GB FASTQ -> %.2f GB BGZF in %.1fs" % (n_reads, RL, rec.size / 1e9,
       os.path.getsize(reads_path) / 1e9, time.time() - t0), flush=True)
 fastq_bytes = rec.size
@@ -69,7 +70,7 @@ rc = index_reads.main([tmp, reads_path, os.path.join(tmp, "reads.index"), "-k", 
 wall = time.time() - t0
 T = dict(index_reads.TIMINGS)
 T.update(rc=rc, wall=wall, n_reads=n_reads, fastq_gb=fastq_bytes / 1e9, kmers=n_reads * (RL - K + 1),
-         host_threads=bgzf.n_threads())
+         host_threads=len(os.sched_getaffinity(0)))
 print(json.dumps(T))
 front = T["inflate"] + T["scan"] + T["label_gpu"] + T["pairing_rows"]
 print("front end (inflate+scan+GPU label+pairing rows): %.2fs = %.2f M reads/s, %.2f G k-mers/s; sqlite insert+index: %.1fs"

@@ -313,76 +313,6 @@ int sgc_bgzf_inflate(const uint8_t* h_raw, int64_t raw_bytes, const int64_t* h_c
     return SGC_OK;
 }
 
-// BGZF writer (reference: utils/make_bgzf.py on top of bgzf.BgzfWriter): n bytes -> ceil(n / block_size)
-// blocks + the 28-byte EOF marker.  out_cap >= sgc_bgzf_deflate_bound(n, block_size).
-int64_t sgc_bgzf_deflate_bound(int64_t n, int block_size) {
-    if (n < 0 || block_size < 1 || block_size > 65280) return -1;
-    int64_t nblocks = (n + block_size - 1) / block_size;
-    return nblocks * (int64_t)(compressBound((uLong)block_size) + 26) + 28;
-}
-
-int sgc_bgzf_deflate(const uint8_t* h_data, int64_t n, int block_size, int level, int n_threads, uint8_t* h_out,
-                     int64_t out_cap, int64_t* h_out_bytes) {
-    if (n < 0 || (n > 0 && !h_data) || !h_out || !h_out_bytes) return fail(SGC_ERR_ARG, "bad argument");
-    if (block_size < 1 || block_size > 65280) return fail(SGC_ERR_ARG, "block_size must be in [1, 65280]");
-    if (level < 0 || level > 9) return fail(SGC_ERR_ARG, "level must be in [0, 9]");
-    if (out_cap < sgc_bgzf_deflate_bound(n, block_size)) return fail(SGC_ERR_CAPACITY, "output buffer too small");
-    int64_t nblocks = (n + block_size - 1) / block_size;
-    int64_t slot = (int64_t)compressBound((uLong)block_size) + 26;  // every block is built in its own slot
-    std::vector<int64_t> bsize((size_t)nblocks, 0);
-    std::atomic<int64_t> next{0}, bad{-1};
-    int nt = feed::pick_threads(n_threads, nblocks);
-    feed::parallel_for(nt, [&](int) {
-        z_stream zs;
-        memset(&zs, 0, sizeof(zs));
-        if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) {
-            bad.store(0);
-            return;
-        }
-        for (;;) {
-            int64_t b = next.fetch_add(1);
-            if (b >= nblocks || bad.load() >= 0) break;
-            const uint8_t* src = h_data + b * block_size;
-            int64_t len = std::min<int64_t>(block_size, n - b * block_size);
-            uint8_t* dst = h_out + b * slot;
-            deflateReset(&zs);
-            zs.next_in = const_cast<Bytef*>(src);
-            zs.avail_in = (uInt)len;
-            zs.next_out = dst + 18;
-            zs.avail_out = (uInt)(slot - 26);
-            if (deflate(&zs, Z_FINISH) != Z_STREAM_END) {
-                bad.store(b);
-                break;
-            }
-            int64_t clen = (int64_t)zs.total_out, total = clen + 26;
-            if (total > 65536) {  // cannot happen for block_size <= 65280 unless the data is incompressible beyond bound
-                bad.store(b);
-                break;
-            }
-            static const uint8_t head[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
-            memcpy(dst, head, 16);
-            dst[16] = (uint8_t)((total - 1) & 0xff);
-            dst[17] = (uint8_t)((total - 1) >> 8);
-            uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), src, (uInt)len);
-            uint8_t* tail = dst + 18 + clen;
-            for (int j = 0; j < 4; ++j) tail[j] = (uint8_t)(crc >> (8 * j));
-            for (int j = 0; j < 4; ++j) tail[4 + j] = (uint8_t)((uint32_t)len >> (8 * j));
-            bsize[(size_t)b] = total;
-        }
-        deflateEnd(&zs);
-    });
-    if (bad.load() >= 0) return fail(SGC_ERR_ARG, "BGZF block %lld does not fit a 64 KiB block", (long long)bad.load());
-    int64_t out = 0;  // close the gaps between the slots
-    for (int64_t b = 0; b < nblocks; ++b) {
-        if (out != b * slot) memmove(h_out + out, h_out + b * slot, (size_t)bsize[(size_t)b]);
-        out += bsize[(size_t)b];
-    }
-    static const uint8_t eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    memcpy(h_out + out, eof, 28);
-    *h_out_bytes = out + 28;
-    return SGC_OK;
-}
-
 // ---------------------------------------------------------------------------- records
 // h_info[0..2] = number of records, total sequence bytes, format (0 FASTA, 1 FASTQ)
 int sgc_reads_count(const uint8_t* h_data, int64_t n, int n_threads, int64_t* h_info) {

@@ -133,7 +133,6 @@ struct TileArgs {
     // MODE_LABEL
     unsigned long long* pairs;
     unsigned long long pairs_cap;
-    unsigned long long zero;  // always 0 (was a scheduling dependency of the former pipelined probe loop; unused)
     // MODE_PARTITION (hash -> owner rank's send region) / MODE_GATHER (replies -> labels)
     uint64_t* send;                 // n_ranks regions of send_cap hashes
     uint64_t* peer_send[32];        // where owner r's requests go: send + r*send_cap locally, or the

@@ -83,21 +83,6 @@ def open_reads(path):
     return BgzfData(path) if is_bgzf(path) else PlainData(path)
 
 
-def write_bgzf(path, payload, block_size=65280, level=6):
-    """Write ``payload`` (bytes / uint8 array) as BGZF, blocks deflated in parallel (sgc_bgzf_deflate);
-    what the reference's utils/make_bgzf.py produces."""
-    L = lib()
-    data = np.frombuffer(payload, np.uint8) if not isinstance(payload, np.ndarray) else np.ascontiguousarray(payload, np.uint8)
-    bound = L.sgc_bgzf_deflate_bound(data.size, int(block_size))
-    if bound < 0:
-        raise ValueError("block_size must be in [1, 65280]")
-    out = np.empty(bound, np.uint8)
-    nb = ctypes.c_int64(0)
-    check(L.sgc_bgzf_deflate(_p(data) if data.size else None, data.size, int(block_size), int(level), n_threads(),
-                             _p(out), bound, ctypes.byref(nb)))
-    out[: nb.value].tofile(path)
-
-
 class NameTable:
     """Record names as byte ranges ``[lo[i], hi[i])`` of a uint8 buffer: no per-record Python
     object is made until one is asked for.  Compares equal to a list of str."""

@@ -6,6 +6,8 @@ import os
 import sqlite3
 
 import numpy as np
+
+from bgzf_writer import write_bgzf
 import pytest
 
 from conftest import golden_path
@@ -493,7 +495,7 @@ def test_index_reads_main_dory(tmp_path, O, dory, dory_index, dory_reads):
     cdbg = _write_index(tmp_path, dory_index)
     fq = "".join("@%s\n%s\n+\n%s\n" % (r.name, r.sequence, r.quality) for r in dory_reads).encode()
     reads = str(tmp_path / "reads.bgz")
-    bgzf.write_bgzf(reads, fq)
+    write_bgzf(reads, fq)
     db = str(tmp_path / "reads.index")
     assert index_reads.main([cdbg, reads, db, "-k", "21"]) == 0
     rows = sorted(sqlite3.connect(db).execute("SELECT offset, cdbg_id FROM sequences").fetchall())
@@ -543,7 +545,7 @@ def test_index_reads_pairing_semantics(tmp_path, ctx, O, ignore_paired):
     MPHF_KmerIndex(k, table, sizes).save(str(d))
     fa = "".join(">%s\n%s\n" % (r.name, r.sequence) for r in reads).encode()
     rp = str(tmp_path / "reads.bgz")
-    bgzf.write_bgzf(rp, fa, block_size=700)
+    write_bgzf(rp, fa, block_size=700)
     db = str(tmp_path / "out.index")
     rc = index_reads.main([str(d), rp, db, "-k", str(k)] + (["-N"] if ignore_paired else []))
     rows = sorted(sqlite3.connect(db).execute("SELECT offset, cdbg_id FROM sequences").fetchall())
