@@ -1,23 +1,28 @@
 #!/usr/bin/env python
-"""bench.py -- k-mers hashed + looked-up per second on the index_reads hot path.
+"""bench.py -- k-mers hashed + looked-up per second on the index_reads hot path (+ the query half of the metric).
 
 Workload (BASELINE.json configs[3]): synthetic metagenome cDBG with
 500 M unitig k-mers (k=31) in a GPU-resident table replicated per GPU; 150-bp reads with 0.5 %
 substitution errors, half reverse-complemented, labelled with the distinct unitig ids their
-k-mers hit (cdbg/index_reads.py:143-152).  One STEP = one batch of 2^24 reads (2.01e9 k-mers,
-2.5 GB of ASCII, far larger than L2); the default 12 steps are the config's 200 M reads.
+k-mers hit (cdbg/index_reads.py:143-152).  One STEP = one batch of 2^24 reads (2.01e9 k-mers);
+the reads are held 2 bits per base (48 bytes per read, the layout the host feeder emits) and are
+expanded to ASCII inside the kernel.  The default 12 steps are the config's 200 M reads.
 
   value  k-mers/s, whole job, inputs resident in HBM, timed with CUDA events on the launch stream
-  e2e    the same through the public host API: pinned host buffers -> H2D -> kernels -> D2H of the
-         CSR labels, double-buffered; H2D / D2H bytes counted from the tensors copied
-  roofline   the tile kernel (hash + probe + label) alone, CUDA events recorded around its launches
+  e2e    the same through the product's own streaming API (GpuKmerTable.label_reads_stream, what
+         index_reads.main runs): pinned host batches -> H2D -> kernels -> D2H of the CSR labels,
+         double-buffered; H2D / D2H bytes counted from the tensors copied
+  roofline   the label kernel (hash + probe + label) alone, CUDA events recorded around its launches
+  query  the other half of the metric: batched count_cdbg_matches over many query sequences
+         (search/query_by_sequence.py:153-189): per-query distinct hashes -> {unitig: count}
   cpu_baseline / --impl reference   the CPU oracle (oracle/sgc_oracle.c, OpenMP over all host
          cores) on a bounded, scaled-down sample of the same workload
 
 N > 1 (torchrun): every rank holds the full table and labels its own read batches (weak scaling,
-no data-path collective); the time is the max over ranks.  ``--table partitioned`` instead runs the
-hash-range partitioned table of configs[4] (exchange fused into the kernels over NVLink peer memory;
-``partitioned-nccl`` = the same regions through NCCL all-to-all) and reports the NVLink roofline.
+no data-path collective); the time is the max over ranks.  The same run then ALSO builds the
+hash-range partitioned table of configs[4] (--part-kmers-per-gpu unitig k-mers per GPU; requests
+and replies stored straight into peer memory over NVLink), checks its labels against a replicated
+table and reports it as the "partitioned" sub-object with the NVLink roofline.
 """
 import argparse
 import ctypes
@@ -95,11 +100,32 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU arm
+def unitig_cuts(n_kmers, seed=2, mean=64, cap=4096):
+    """Cut points (k-mer coordinates) of the synthetic unitigs: 1 + Geometric(1/64) k-mers each, capped at
+    4096 (the same rule as spacegraphcats_b200/synth.py, restated here so that the CPU
+    arm imports nothing of the product)."""
+    rng = np.random.default_rng(seed)
+    est = int(n_kmers / mean * 1.05) + 1024
+    cuts = [np.zeros(1, np.int64)]
+    total = 0
+    while total < n_kmers:
+        sizes = np.minimum(rng.geometric(1.0 / mean, est), cap).astype(np.int64)
+        c = np.cumsum(sizes) + total
+        cuts.append(c)
+        total = int(c[-1])
+    cuts = np.concatenate(cuts)
+    cuts = cuts[cuts < n_kmers]
+    return np.concatenate([cuts, [n_kmers]]).astype(np.int64)
+
+
+def build_oracle():
+    """Compile the CPU oracle only (gcc); the product library is neither built nor loaded by the CPU arm."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+
+
 def cpu_workload(n_kmers, n_reads, seed=1):
-    """Scaled-down copy of the workload for the CPU oracle: (table pairs, reads).  Same generator
-    rules as spacegraphcats_b200/synth.py, done with numpy on the host."""
+    """Scaled-down copy of the workload for the CPU oracle: (table, reads, offsets, genome, cuts)."""
     from oracle import oracle as O
-    from spacegraphcats_b200.synth import unitig_cuts
 
     rng = np.random.default_rng(seed)
     lut = np.frombuffer(b"ACGT", np.uint8)
@@ -134,7 +160,7 @@ def cpu_workload(n_kmers, n_reads, seed=1):
     reads[rc] = comp[reads[rc]][:, ::-1]
     buf = np.ascontiguousarray(reads).reshape(-1)
     off = np.arange(n_reads + 1, dtype=np.int64) * READ_LEN
-    return table, buf, off
+    return table, buf, off, g, len(cuts) - 1
 
 
 def cpu_time_sample(table, buf, off, threads, min_seconds=10.0):
@@ -149,22 +175,40 @@ def cpu_time_sample(table, buf, off, threads, min_seconds=10.0):
     return nk_total / t_total, nk_total, t_total, reps
 
 
+def cpu_python_granularity(table, buf, off, seconds=3.0):
+    """BASELINE.md's B1: the reference's own loop shape (cdbg/index_reads.py:143-152) -- one Python call per
+    read to a native hash_sequence that returns a list of Python ints, one native get_unique_values over that
+    list, a Python set update -- on ONE thread, the reference's execution model.  -> k-mers/s"""
+    from oracle import oracle as O
+
+    ot = table
+    n = len(off) - 1
+    done, nk, t0 = 0, 0, time.perf_counter()
+    raw = buf.tobytes()
+    while time.perf_counter() - t0 < seconds and done < n:
+        seq = raw[off[done]:off[done + 1]]
+        kmers = O.hash_sequence(seq, KSIZE).tolist()          # khmer get_kmer_hashes -> list of PyLongs
+        counts = ot.get_unique_values_list(kmers)             # BBHashTable.get_unique_values -> dict
+        ids = set()
+        ids.update(counts)
+        nk += len(kmers)
+        done += 1
+    return nk / (time.perf_counter() - t0)
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path for this metric.  The reference's own natives
-    (khmer, bbhash) are absent, so this is the oracle port with all host threads."""
+    (khmer, bbhash) are absent, so this is the oracle port with all host threads.
+    Nothing of the product is imported, built or loaded here."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import __graft_entry__ as g
-
-    g.build()
-    from oracle import oracle as O
-
+    build_oracle()
     # all host cores, explicitly: torchrun exports OMP_NUM_THREADS=1 to every rank
     threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     n_kmers, n_reads = args.cpu_kmers, args.cpu_reads
     log("[reference] building CPU table (%d unitig k-mers) and %d reads ..." % (n_kmers, n_reads))
-    table, buf, off = cpu_workload(n_kmers, n_reads)
+    table, buf, off, _, _ = cpu_workload(n_kmers, n_reads)
     step_kmers = n_reads * (READ_LEN - KSIZE + 1)
     for _ in range(args.warmup):
         table.label_reads_checksum(buf, off, KSIZE, threads=threads)
@@ -175,12 +219,13 @@ def run_reference(args):
     value = step_kmers * args.steps / dt
     sample = ("oracle port (oracle/sgc_oracle.c, OpenMP): %d x 150-bp reads per step against a %d-k-mer "
               "synthetic cDBG table (scaled-down copy of the GPU workload)" % (n_reads, n_kmers))
+    cfg = workload_config(args, cpu=True)
     line = {
         "metric": "k-mers hashed+looked-up/sec (index_reads)", "value": value, "unit": "k-mers/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "impl": "reference",
-        "config": workload_config(args, cpu=True),
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": "k-mers/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -189,16 +234,28 @@ def run_reference(args):
 
 
 def workload_config(args, cpu=False):
+    if cpu:
+        # the CPU arm runs a bounded, scaled-down sample of the same workload: say so where the driver reads it
+        return {
+            "workload": "synthetic metagenome cDBG k=%d, 150bp reads labelled by index_reads (BASELINE.json configs[3] "
+                        "shape), CPU SAMPLE: %d unitig k-mers in the table, %d reads (%d k-mers) per step"
+                        % (KSIZE, args.cpu_kmers, args.cpu_reads, args.cpu_reads * (READ_LEN - KSIZE + 1)),
+            "ksize": KSIZE, "read_len": READ_LEN, "reads_per_step": args.cpu_reads,
+            "kmers_per_step": args.cpu_reads * (READ_LEN - KSIZE + 1), "error_rate": ERR_PPM / 1e6,
+            "table": "replicated", "table_kmers": args.cpu_kmers,
+            "gpu_arm_shape": {"table_kmers": args.table_kmers, "reads_per_step": args.batch_reads},
+        }
     return {
         "workload": "synthetic metagenome cDBG, %d unitig k-mers k=%d, 150bp reads labelled by index_reads, "
                     "1 B200 replicated table (BASELINE.json configs[3])" % (args.table_kmers, KSIZE),
         "ksize": KSIZE, "read_len": READ_LEN, "reads_per_step": args.batch_reads,
         "kmers_per_step": args.batch_reads * (READ_LEN - KSIZE + 1), "error_rate": ERR_PPM / 1e6,
-        "table": "replicated",
-        "label_kernel": "per-k-mer probes (SGC_SIDE=0)" if os.environ.get("SGC_SIDE", "1") == "0"
-                        else "anchor probe + unitig-ordered side array (default)",
-        "l2": "inputs (2.5 GB reads/step, 21 GB table) far larger than the 126 MB L2; no flush needed",
-        **({"cpu_sample": {"table_kmers": args.cpu_kmers, "reads_per_step": args.cpu_reads}} if cpu else {}),
+        "table": "replicated", "table_kmers": args.table_kmers,
+        "read_format": "ASCII (1 byte per base + int64 offsets)" if args.ascii else
+                       "2-bit packed, 48 bytes per 150-bp read (the host feeder's output; expanded to ASCII in the kernel)",
+        "label_kernel": "per-k-mer probes (SGC_NO_SIDE)" if os.environ.get("SGC_NO_SIDE") else
+                        "label8: one table probe per 8 k-mers + unitig-ordered side array of 64-bit hashes",
+        "l2": "inputs (0.8 GB packed reads/step, 27 GB table + 4 GB side array) far larger than the 126 MB L2; no flush needed",
     }
 
 
@@ -223,74 +280,110 @@ def bind_to_gpu_numa_node(index):
     return 0
 
 
-def run_partitioned(args, rank, world, local):
-    """BASELINE.json configs[4] shape: --table-kmers unitig k-mers in TOTAL, hash-range partitioned over
-    the ranks; every rank labels its own read batches through request/reply exchanges."""
+def partitioned_arm(args, ctx, rank, world):
+    """BASELINE.json configs[4]: a cDBG of world x --part-kmers-per-gpu unitig k-mers, hash-range partitioned over
+    the ranks (every rank owns one range); every rank labels its own read batches, requests and replies
+    stored straight into the owners' / requesters' memory over NVLink.  The labels of one batch are checked
+    against a REPLICATED table of the same cDBG built on every rank.  -> dict (rank 0) / None"""
     import torch
     import torch.distributed as dist
 
-    from spacegraphcats_b200.device import Context
+    from spacegraphcats_b200.device import DeviceTable
     from spacegraphcats_b200.parallel import DeviceEngine, PartitionedIndex, shard_range
     from spacegraphcats_b200.synth import SyntheticCdbg
 
-    if world < 2:
-        raise SystemExit("--table partitioned needs torchrun with >= 2 ranks")
-    ctx = Context(local)
+    total_kmers = args.part_kmers_per_gpu * world
     t0 = time.time()
-    cdbg = SyntheticCdbg(ctx, args.table_kmers, KSIZE, seed=1)  # same genome / unitigs on every rank
+    cdbg = SyntheticCdbg(ctx, total_kmers, KSIZE, seed=1)  # same genome / unitigs on every rank
     ulo, uhi = shard_range(cdbg.n_unitigs, rank, world)
     with torch.cuda.stream(ctx.stream):
         b0, b1 = int(cdbg.uoff[ulo].item()), int(cdbg.uoff[uhi].item())
         useq = cdbg.useq[b0:b1]
         uoff = (cdbg.uoff[ulo:uhi + 1] - b0).contiguous()
         ids = torch.arange(ulo, uhi, dtype=torch.int32, device=ctx.device)
-    p2p = args.table == "partitioned"
-    idx = PartitionedIndex(DeviceEngine(ctx), p2p=p2p).build(useq, uoff, KSIZE, ids)
+    idx = PartitionedIndex(DeviceEngine(ctx), p2p=True).build(useq, uoff, KSIZE, ids)
     ctx.sync()
-    log("[rank %d] partitioned build %.1fs: %d hashes (%.2f GB) on this rank" % (rank, time.time() - t0, idx.n_local, idx.table.nbytes / 1e9))
-    n_reads = args.batch_reads
+    log("[rank %d] partitioned build %.1fs: %d of %d hashes (%.2f GB) on this rank"
+        % (rank, time.time() - t0, idx.n_local, total_kmers, idx.table.nbytes / 1e9))
+    n_reads = args.part_reads
     step_kmers = n_reads * (READ_LEN - KSIZE + 1)
-    nb = max(1, min(2, args.steps + args.warmup))
+    nb = 2
     batches = [cdbg.reads(n_reads, READ_LEN, seed=1000 * (rank + 1) + 3 + b, err_ppm=ERR_PPM) for b in range(nb)]
     ctx.sync()
-    for i in range(args.warmup):
+    warm = max(args.warmup, 1)
+    res = None
+    for i in range(warm):
         res = idx.label_reads(*batches[i % nb], KSIZE)
+    check_batch = (warm - 1) % nb
     launches0 = ctx.launches
     dist.barrier()
     torch.cuda.synchronize()
-    with ClockSampler(local) as clocks:
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            res = idx.label_reads(*batches[(args.warmup + i) % nb], KSIZE)
-        ctx.sync()
-        dist.barrier()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for i in range(args.part_steps):
+        idx.label_reads(*batches[(warm + i) % nb], KSIZE)
+    ctx.sync()
+    dist.barrier()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    launches = ctx.launches - launches0
     t = torch.tensor([dt], dtype=torch.float64, device=ctx.device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
-    if rank == 0:
-        value = world * step_kmers * args.steps / dt
-        link_bytes = (world - 1) / world * 12.0 * step_kmers  # per GPU and direction (8 B out + 4 B back)
-        achieved = link_bytes * args.steps / dt / 1e9
-        line = {
-            "metric": "k-mers hashed+looked-up/sec (index_reads)", "value": value, "unit": "k-mers/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "synthetic cDBG, %d unitig k-mers k=%d hash-range partitioned across %d B200 "
-                                   "(BASELINE.json configs[4] shape), 150bp reads labelled by index_reads" % (args.table_kmers, KSIZE, world),
-                       "ksize": KSIZE, "read_len": READ_LEN, "reads_per_rank_step": n_reads, "table": args.table,
-                       "exchange": "P2P stores into peer inboxes over NVLink (CUDA IPC)" if p2p else "NCCL all-to-all"},
-            "labels_per_read": int(res[1].numel()) / n_reads, "clocks": clocks.summary(), "e2e": None,
-            "gpu_launches": int(ctx.launches - launches0),
-            "roofline": {"bound": "nvlink", "achieved": achieved, "peak": 770.0, "unit": "GB/s", "frac": achieved / 770.0,
-                         "traffic": None, "peak_source": "measured peer copy, B200_PROFILING.md",
-                         "note": "(R-1)/R x 12 B per k-mer per GPU and direction over the whole step; the step is bound by "
-                                 "the un-overlapped hash / probe / gather kernels, not by the link (DESIGN.md section 6)"},
-            "cpu_baseline": None,
-        }
-        print(json.dumps(line), flush=True)
-    dist.destroy_process_group()
+    # parity: the same batch against a replicated table of the whole cDBG on this GPU (per-k-mer probing; packed
+    # denser than the working tables so that the 8-GPU case, 4e9 hashes, fits next to the shard)
+    ok = None
+    if not args.no_part_check:
+        t1 = time.time()
+        rep = DeviceTable(ctx, cdbg.total_unitig_kmers, load=1.3)
+        rep.insert_sequences(cdbg.useq, cdbg.uoff, KSIZE)
+        ref = rep.label_reads(*batches[check_batch], KSIZE, to_host=False)
+        same = torch.equal(ref["ids_off"], res[0]) and torch.equal(ref["ids"], res[1])
+        okt = torch.tensor([1 if same else 0], device=ctx.device)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        ok = bool(okt.item())
+        rep.close()
+        log("[rank %d] partitioned labels == replicated labels: %s (check %.1fs)" % (rank, same, time.time() - t1))
+    labels_per_read = int(res[1].numel()) / n_reads
+    table_bytes = idx.table.nbytes
+    idx.close()
+    del cdbg
+    if rank != 0:
+        return None
+    value = world * step_kmers * args.part_steps / dt
+    link_bytes = (world - 1) / world * 12.0 * step_kmers  # per GPU and direction (8 B request + 4 B reply)
+    achieved = link_bytes * args.part_steps / dt / 1e9
+    return {
+        "value": value, "unit": "k-mers/s", "per_gpu": value / world, "ms_per_step": dt / args.part_steps * 1e3,
+        "steps": args.part_steps, "table_kmers": total_kmers, "table_kmers_per_gpu": args.part_kmers_per_gpu,
+        "table_bytes_per_gpu": table_bytes, "reads_per_rank_step": n_reads, "labels_per_read": labels_per_read,
+        "labels_identical_to_replicated": ok, "gpu_launches": int(launches),
+        "exchange": "requests / replies stored straight into peer memory over NVLink (CUDA IPC), no NCCL on the data path",
+        "workload": "synthetic cDBG, %d unitig k-mers k=%d hash-range partitioned across %d B200 (BASELINE.json configs[4]), "
+                    "150bp reads labelled by index_reads" % (total_kmers, KSIZE, world),
+        "roofline": {"bound": "nvlink", "achieved": achieved, "peak": 770.0, "unit": "GB/s", "frac": achieved / 770.0,
+                     "peak_source": "measured peer copy, B200_PROFILING.md",
+                     "note": "(R-1)/R x 12 B per k-mer per GPU and direction over the whole step (SURVEY 8d: 73 G k-mers/s "
+                             "per GPU at R=8); every k-mer is one random 128-byte HBM line on its owner, which caps a GPU "
+                             "at the measured 36-46 G random lines/s whatever the link does"},
+    }
+
+
+def query_arm(args, ctx, table, cdbg, rank, world):
+    """count_cdbg_matches half of the metric (filled in below once the batched query path is in place)."""
+    return None
+
+
+def source_digest():
+    """sha256 over the kernel sources: ties profiles/ncu_traffic.json to the code it was captured from."""
+    import hashlib
+
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "spacegraphcats_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".hpp")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -302,13 +395,21 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--table-kmers", type=int, default=500_000_000)
     ap.add_argument("--batch-reads", type=int, default=1 << 24)
-    ap.add_argument("--distinct-batches", type=int, default=4, help="device-resident read batches cycled through")
+    ap.add_argument("--distinct-batches", type=int, default=4, help="read batches cycled through")
     ap.add_argument("--cpu-kmers", type=int, default=20_000_000)
     ap.add_argument("--cpu-reads", type=int, default=400_000)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--table", default="replicated", choices=["replicated", "partitioned", "partitioned-nccl"],
-                    help="replicated (configs[3], default) or hash-range partitioned across the ranks (configs[4]; "
-                         "exchange fused into the kernels over NVLink peer memory, or through NCCL all-to-all)")
+    ap.add_argument("--ascii", action="store_true", help="feed ASCII reads + int64 offsets instead of 2-bit packed records")
+    ap.add_argument("--part-kmers-per-gpu", type=int, default=500_000_000,
+                    help="N >= 2: unitig k-mers per GPU of the hash-range partitioned table (configs[4]: 4e9 over 8 GPUs)")
+    ap.add_argument("--part-reads", type=int, default=1 << 22, help="reads per rank and step of the partitioned arm")
+    ap.add_argument("--part-steps", type=int, default=10)
+    ap.add_argument("--no-partitioned", action="store_true")
+    ap.add_argument("--no-part-check", action="store_true")
+    ap.add_argument("--query-kmers", type=int, default=500_000, help="k-mers per query sequence (acido-chunk shape)")
+    ap.add_argument("--queries", type=int, default=512, help="query sequences per step of the query arm")
+    ap.add_argument("--query-steps", type=int, default=10)
+    ap.add_argument("--no-query", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -335,36 +436,55 @@ def main():
         g.build()
     if world > 1:
         dist.barrier()
+    from spacegraphcats_b200.cdbg.hashing import GpuKmerTable
     from spacegraphcats_b200.device import Context
     from spacegraphcats_b200.synth import SyntheticCdbg
     from spacegraphcats_b200._lib import check
-
-    if args.table != "replicated":
-        return run_partitioned(args, rank, world, local)
 
     ctx = Context(local)
     L = ctx._L
     t0 = time.time()
     cdbg = SyntheticCdbg(ctx, args.table_kmers, KSIZE, seed=1)
-    table = cdbg.build_table()
-    live, multi, max_id = table.stats()
-    log("[rank %d] cDBG: %d unitigs, table %d live hashes (%d multicount) in %.2f GB, built in %.1fs"
-        % (rank, cdbg.n_unitigs, live, multi, table.nbytes / 1e9, time.time() - t0))
+    dev_table = cdbg.build_table()
+    table = GpuKmerTable(ctx)
+    table._dev = dev_table  # the product object whose streaming API the e2e arm calls
+    live, multi, max_id = dev_table.stats()
+    TABLE_BYTES.append(dev_table.nbytes + dev_table.side_nbytes)
+    log("[rank %d] cDBG: %d unitigs, table %d live hashes (%d multicount) in %.2f GB (+%.2f GB side array), built in %.1fs"
+        % (rank, cdbg.n_unitigs, live, multi, dev_table.nbytes / 1e9, dev_table.side_nbytes / 1e9, time.time() - t0))
     nb = max(1, min(args.distinct_batches, args.steps + args.warmup))
-    batches = [cdbg.reads(args.batch_reads, READ_LEN, seed=1000 * (rank + 1) + 3 + b, err_ppm=ERR_PPM) for b in range(nb)]
-    ctx.sync()
     n_reads = args.batch_reads
     step_kmers = n_reads * (READ_LEN - KSIZE + 1)
     ids_cap = 6 * n_reads
+    # device-resident batches: ASCII reads from the generator, packed 2 bits per base on the device
+    batches = []
+    for b in range(nb):
+        seq, off = cdbg.reads(n_reads, READ_LEN, seed=1000 * (rank + 1) + 3 + b, err_ppm=ERR_PPM)
+        if args.ascii:
+            batches.append((seq, off))
+        else:
+            pk, ln, st = ctx.pack_reads(seq, off)
+            assert not bool(st.any().item())
+            batches.append((pk.clone(), None))
+            del seq, off, pk, ln, st
+    ctx.sync()
+    torch.cuda.empty_cache()
     d_ids_off = ctx.empty(n_reads + 1, torch.int64)
     d_ids = ctx.empty(ids_cap, torch.int32)
     d_stat = ctx.empty(n_reads, torch.int32)
 
-    def label(seq, off):
+    def label(batch):
         nk, nh, nl = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
-        check(L.sgc_label_reads(table._h, ctx.ptr(seq), seq.numel(), ctx.ptr(off), n_reads, KSIZE, ctx.ptr(d_ids_off),
-                                ctx.ptr(d_ids), ids_cap, ctx.ptr(d_stat), ctypes.byref(nk), ctypes.byref(nh),
-                                ctypes.byref(nl)))
+        if args.ascii:
+            seq, off = batch
+            check(L.sgc_label_reads(dev_table._h, ctx.ptr(seq), seq.numel(), ctx.ptr(off), n_reads, KSIZE, ctx.ptr(d_ids_off),
+                                    ctx.ptr(d_ids), ids_cap, ctx.ptr(d_stat), ctypes.byref(nk), ctypes.byref(nh),
+                                    ctypes.byref(nl)))
+        else:
+            pk = batch[0]
+            check(L.sgc_label_reads_packed(dev_table._h, ctx.ptr(pk), pk.numel(), None, READ_LEN, n_reads, KSIZE,
+                                           ctx.ptr(d_ids_off), ctx.ptr(d_ids), ids_cap, ctypes.byref(nk), ctypes.byref(nh),
+                                           ctypes.byref(nl)))
         return nk.value, nh.value, nl.value
 
     def barrier():
@@ -375,7 +495,7 @@ def main():
     # ---- value: device-resident inputs ------------------------------------------------
     args.warmup = max(args.warmup, 1)  # at least one untimed step (context / allocator / attribute set-up)
     for i in range(args.warmup):
-        stats = label(*batches[i % nb])
+        stats = label(batches[i % nb])
     assert stats[0] == step_kmers, stats
     launches0 = ctx.launches
     check(L.sgc_ctx_set_timing(ctx._h, 1))
@@ -386,7 +506,7 @@ def main():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(ctx.stream)
         for i in range(args.steps):
-            stats = label(*batches[(args.warmup + i) % nb])
+            stats = label(batches[(args.warmup + i) % nb])
         ev1.record(ctx.stream)
         barrier()
     ms = ev0.elapsed_time(ev1)
@@ -402,76 +522,77 @@ def main():
     hit_frac = stats[1] / stats[0]
     labels_per_read = stats[2] / n_reads
 
-    # ---- e2e: host buffers, H2D + kernels + D2H inside the timed region -----------------
+    # ---- e2e: pinned host batches through the product's streaming API ---------------------------
     e2e = None
     if not args.no_e2e:
-        nh_b = 2
-        h_seq = [torch.empty(n_reads * READ_LEN, dtype=torch.uint8).pin_memory() for _ in range(nh_b)]
-        h_off = [torch.empty(n_reads + 1, dtype=torch.int64).pin_memory() for _ in range(nh_b)]
+        nh_b = min(2, nb)
+        host_batches = []
         for b in range(nh_b):
-            h_seq[b].copy_(batches[b % nb][0])
-            h_off[b].copy_(batches[b % nb][1])
-        h_ids_off = [torch.empty(n_reads + 1, dtype=torch.int64).pin_memory() for _ in range(2)]
-        h_ids = [torch.empty(ids_cap, dtype=torch.int32).pin_memory() for _ in range(2)]
-        d_seq = [ctx.empty(n_reads * READ_LEN, torch.uint8) for _ in range(2)]
-        d_off = [ctx.empty(n_reads + 1, torch.int64) for _ in range(2)]
-        o_ids_off = [ctx.empty(n_reads + 1, torch.int64) for _ in range(2)]
-        o_ids = [ctx.empty(ids_cap, torch.int32) for _ in range(2)]
-        copy_stream = torch.cuda.Stream(device=ctx.device)
-        back_stream = torch.cuda.Stream(device=ctx.device)
-        copied = [torch.cuda.Event() for _ in range(2)]
-        returned = [torch.cuda.Event() for _ in range(2)]
+            if args.ascii:
+                hs = torch.empty(n_reads * READ_LEN, dtype=torch.uint8).pin_memory()
+                ho = torch.empty(n_reads + 1, dtype=torch.int64).pin_memory()
+                hs.copy_(batches[b][0])
+                ho.copy_(batches[b][1])
+                host_batches.append({"seq": hs, "off": ho})
+            else:
+                hp = torch.empty(batches[b][0].numel(), dtype=torch.uint8).pin_memory()
+                hp.copy_(batches[b][0])
+                host_batches.append({"packed": hp, "nseq": n_reads, "lengths": None, "uniform_len": READ_LEN})
         torch.cuda.synchronize()
-
-        def h2d(i):
-            s = i % 2
-            with torch.cuda.stream(copy_stream):
-                d_seq[s].copy_(h_seq[i % nh_b], non_blocking=True)
-                d_off[s].copy_(h_off[i % nh_b], non_blocking=True)
-                copied[s].record(copy_stream)
-
-        def label_into(s):
-            nk, nh, nl = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
-            check(L.sgc_label_reads(table._h, ctx.ptr(d_seq[s]), d_seq[s].numel(), ctx.ptr(d_off[s]), n_reads, KSIZE,
-                                    ctx.ptr(o_ids_off[s]), ctx.ptr(o_ids[s]), ids_cap, ctx.ptr(d_stat), ctypes.byref(nk),
-                                    ctypes.byref(nh), ctypes.byref(nl)))
-            return nl.value
+        h2d = (n_reads * READ_LEN + (n_reads + 1) * 8) if args.ascii else int(host_batches[0]["packed"].numel())
 
         def e2e_steps(n):
-            """H2D of step i+1 and D2H of step i-1 overlap the kernels of step i."""
-            h2d(0)
-            tot_labels = 0
-            for i in range(n):
-                s = i % 2
-                ctx.stream.wait_event(copied[s])
-                ctx.stream.wait_event(returned[s])  # outputs of step i-2 have left this buffer
-                if i + 1 < n:
-                    h2d(i + 1)
-                nl = label_into(s)  # returns when the kernels of step i are done (host sync inside)
-                with torch.cuda.stream(back_stream):
-                    h_ids_off[s].copy_(o_ids_off[s], non_blocking=True)
-                    h_ids[s][:nl].copy_(o_ids[s][:nl], non_blocking=True)
-                    returned[s].record(back_stream)
-                tot_labels += nl
-            back_stream.synchronize()
-            return tot_labels
+            tot_labels, tot_kmers, acc = 0, 0, 0
+            gen = (host_batches[i % nh_b] for i in range(n))
+            for _, res in table.label_reads_stream(gen, KSIZE, ids_per_read=6, prefetch=False):
+                tot_labels += res["n_labels"]
+                tot_kmers += res["n_kmers"]
+                acc ^= int(res["ids_off"][-1]) ^ int(res["ids"][-1])  # the host reads the result it was given
+            return tot_labels, tot_kmers
 
-        e2e_steps(min(2, args.warmup))
+        e2e_steps(min(3, args.warmup + 1))
         barrier()
         t0 = time.perf_counter()
-        tot_labels = e2e_steps(args.steps)
+        tot_labels, tot_kmers = e2e_steps(args.steps)
         barrier()
         dt = time.perf_counter() - t0
+        assert tot_kmers == step_kmers * args.steps
         t = torch.tensor([dt], dtype=torch.float64, device=ctx.device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
         e2e = {
             "value": world * step_kmers * args.steps / dt, "unit": "k-mers/s",
-            "h2d_bytes_per_step": int(n_reads * READ_LEN + (n_reads + 1) * 8),
+            "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int((n_reads + 1) * 8 + tot_labels // args.steps * 4),
-            "ms_per_step": dt / args.steps * 1e3, "pipeline": "double-buffered H2D on a copy stream",
+            "ms_per_step": dt / args.steps * 1e3,
+            "api": "GpuKmerTable.label_reads_stream (pinned double buffers, H2D / kernels / D2H of consecutive batches "
+                   "overlapped; the loop index_reads.main runs)",
         }
+        del host_batches
+
+    # ---- the other half of the metric: batched count_cdbg_matches --------------------------------
+    query = None
+    if not args.no_query:
+        try:
+            query = query_arm(args, ctx, table, cdbg, rank, world)
+        except Exception as e:  # noqa: BLE001  (the headline line must still be printed)
+            log("[query arm failed] %r" % (e,))
+            query = {"error": repr(e)}
+
+    # ---- configs[4]: hash-range partitioned table (N >= 2), after the replicated table has been freed ----
+    partitioned = None
+    if world > 1 and not args.no_partitioned:
+        del batches, d_ids, d_ids_off, d_stat
+        table._dev = None
+        dev_table.close()
+        del cdbg
+        torch.cuda.empty_cache()
+        try:
+            partitioned = partitioned_arm(args, ctx, rank, world)
+        except Exception as e:  # noqa: BLE001
+            log("[rank %d] partitioned arm failed: %r" % (rank, e))
+            partitioned = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:
@@ -486,44 +607,60 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    bytes_per_kmer = READ_LEN / (READ_LEN - KSIZE + 1) + SECTOR + 4.0 * labels_per_read / (READ_LEN - KSIZE + 1)
+    nkr = READ_LEN - KSIZE + 1
+    # SURVEY 8(d)'s per-unit figure: L/(L-k+1) B of sequence + ONE 32-byte table sector + 4 B of id per k-mer
+    survey_bytes = READ_LEN / nkr + SECTOR + 4.0
+    # what this launch strictly needs: the read as it is stored + one sector + the labels it writes
+    in_bytes = READ_LEN / nkr if args.ascii else 48.0 / nkr
+    strict_bytes = in_bytes + SECTOR + 4.0 * labels_per_read / nkr
     tile_s = tile_ms.value / 1e3 / max(tile_n.value, 1)
-    achieved = bytes_per_kmer * step_kmers / tile_s / 1e9
+    achieved = survey_bytes * step_kmers / tile_s / 1e9
     traffic, traffic_src = None, None
-    try:  # DRAM bytes per k-mer of this kernel from the committed ncu --set full capture
+    try:  # DRAM bytes per k-mer of this kernel from the committed ncu --set full capture OF THESE SOURCES
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        traffic = float(tj["dram_bytes_per_kmer"]) * step_kmers / 1e9
-        traffic_src = tj.get("source")
+        if tj.get("source_digest") == source_digest():
+            traffic = float(tj["dram_bytes_per_kmer"]) * step_kmers / 1e9
+            traffic_src = tj.get("source")
+        else:
+            traffic_src = "profiles/ncu_traffic.json was captured from other kernel sources (digest %s != %s): not quoted" % (
+                tj.get("source_digest"), source_digest())
     except Exception:
         pass
     roofline = {
         "bound": "hbm",
-        "kernel": "tile_kernel<31, MODE_LABEL>" if os.environ.get("SGC_SIDE", "1") == "0" else "tile_kernel<31, MODE_LABEL_SIDE>",
+        "kernel": "tile_kernel<31, MODE_LABEL>" if os.environ.get("SGC_NO_SIDE") else
+                  ("label8_kernel<31, ascii>" if args.ascii else "label8_kernel<31, packed>"),
         "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic, "traffic_unit": "GB per launch", "traffic_source": traffic_src,
         "peak_source": peak_src,
-        "bytes_per_kmer": bytes_per_kmer, "kernel_ms": tile_s * 1e3, "kernel_launches": int(tile_n.value),
+        "bytes_per_kmer": survey_bytes, "kernel_ms": tile_s * 1e3, "kernel_launches": int(tile_n.value),
+        "kernel_kmers_per_s": step_kmers / tile_s,
         "kernel_share_of_step": tile_ms.value / ms,
-        "note": "algorithmic bytes = read bases + ONE 32-byte table sector per k-mer + label output (SURVEY 8d); the "
-                "measured random-access ceiling of HBM on this part is 36-46 G accesses/s and every access moves a "
-                "128-byte line (scripts/sector_probe*.cu, profiles/); the default label kernel probes the table "
-                "once per four k-mers and matches the rest in a unitig-ordered side array: 64 B of HBM per k-mer "
-                "instead of 129",
+        "frac_strict": strict_bytes * step_kmers / tile_s / 1e9 / peak, "bytes_per_kmer_strict": strict_bytes,
+        "note": "achieved = SURVEY 8(d)'s algorithmic figure (150/120 B of sequence + ONE 32-byte table sector + 4 B of "
+                "id per k-mer = 37.25 B) x k-mers per launch / measured kernel time; frac_strict counts only what this "
+                "launch needs (packed read bytes + one sector + the labels written).  HBM on this part serves 36-46 G "
+                "random lines/s and moves 128 bytes per access (scripts/sector_probe*.cu, profiles/); the kernel "
+                "probes the table once per eight k-mers and matches the rest in a unitig-ordered side array",
     }
 
     # ---- CPU baseline on the host cores ---------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        from oracle import oracle as O
-
         threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         log("[cpu_baseline] building the scaled-down CPU workload ...")
-        ctab, cbuf, coff = cpu_workload(args.cpu_kmers, args.cpu_reads)
+        build_oracle()
+        ctab, cbuf, coff, _, _ = cpu_workload(args.cpu_kmers, args.cpu_reads)
         rate, nk_tot, secs, reps = cpu_time_sample(ctab, cbuf, coff, threads, args.cpu_seconds)
         # the reference itself is single-threaded (one Python process per snakemake rule): same pass on 1 core
         n1 = max(1, args.cpu_reads // 8)
         rate1, _, _, _ = cpu_time_sample(ctab, cbuf[: n1 * READ_LEN], coff[: n1 + 1], 1, 2.0)
+        rate_py = cpu_python_granularity(ctab, cbuf, coff, 3.0)
         cpu = {"value": rate, "unit": "k-mers/s", "cores": threads, "kind": "port", "single_thread_value": rate1,
+               "reference_python_value": rate_py,
+               "reference_python_note": "1 thread, the reference's own loop shape (cdbg/index_reads.py:143-152): per read "
+                                        "one native hash call returning a list of Python ints + one native "
+                                        "get_unique_values over it + a set update",
                "sample": "%d passes over %d 150-bp reads (%.2e k-mers, %.1f s) against a %d-k-mer synthetic cDBG table; "
                          "oracle/sgc_oracle.c fused hash+lookup+per-read distinct, OpenMP" % (reps, args.cpu_reads, nk_tot, secs, args.cpu_kmers)}
 
@@ -533,13 +670,20 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": workload_config(args),
         "hit_fraction": hit_frac, "labels_per_read": labels_per_read,
-        "table_bytes": table.nbytes, "table_entries": live,
+        "table_bytes": dev_table_bytes(live), "table_entries": live,
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(gpu_launches),
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu, "query": query, "partitioned": partitioned,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def dev_table_bytes(live):
+    return int(TABLE_BYTES[0]) if TABLE_BYTES else None
+
+
+TABLE_BYTES = []
 
 
 if __name__ == "__main__":

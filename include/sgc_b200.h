@@ -89,7 +89,7 @@ int sgc_minhash_batch(sgc_ctx* ctx, const uint8_t* d_seq, int64_t seq_bytes, con
  * K2 -- replaces BBHashTable() + .initialize(list(all_kmers)) + table[kmer] = cdbg_id,
  * i.e. build_mphf(), cdbg/index_cdbg_by_kmer.py:27-115.
  * sgc_table_create sizes an empty table for up to max_entries distinct hashes; load = expected
- * hashes per 32-byte bucket (0 = default 0.75; memory = 32 B * max_entries / load).
+ * hashes per 32-byte bucket (0 = default 0.6; memory = 32 B * max_entries / load).
  * Insertion semantics are build_mphf's: a hash inserted with two DIFFERENT ids is
  * dropped from the map for good (multicount, :40-57); the same (hash, id) again is a no-op.
  */
@@ -111,11 +111,13 @@ int sgc_table_stats(sgc_table* t, int64_t* h_live, int64_t* h_multi, uint32_t* h
 int sgc_table_export(sgc_table* t, uint64_t* d_hash_out, uint32_t* d_id_out, int64_t cap,
                      int64_t* h_n_out);
 int64_t sgc_table_bytes(const sgc_table* t);
-/* Optional unitig-ordered side array ({hash, id} per inserted k-mer, 16 B each, up to max_entries
- * records): call before sgc_table_insert_sequences.  With it sgc_label_reads probes the hash table
- * only for the first k-mer of every group of four and matches the others by full 64-bit hash
- * equality against the neighbouring unitig positions (fewer HBM lines per k-mer, identical result).
- * SGC_ERR_CAPACITY when max_entries >= 2^30 - 1 (positions are 30 bits of a slot). */
+/* Optional unitig-ordered side array (the 64-bit hash of every inserted k-mer in unitig order, 8 B each, plus
+ * one "break" bit per k-mer; up to max_entries records): call before sgc_table_insert_sequences.  With it
+ * sgc_label_reads probes the hash table only for the first k-mer of every group of eight and matches the
+ * other seven by full 64-bit hash equality against the neighbouring unitig positions; a matched k-mer
+ * inherits the anchor's id only when no break bit (= "a table lookup answers differently for the two
+ * neighbouring positions") lies in between, everything else is probed individually: identical result,
+ * fewer HBM lines per k-mer.  SGC_ERR_CAPACITY when max_entries >= 2^30 - 1 (positions are 30 bits of a slot). */
 int sgc_table_enable_side(sgc_table* t);
 int64_t sgc_table_side_bytes(const sgc_table* t);
 /* hash-range partitioned tables: the top `shift` bits of every hash stored here are the owner
@@ -167,6 +169,29 @@ int sgc_label_reads_launch(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes
                            uint32_t* d_ids_out, int64_t ids_cap, int32_t* d_status);
 int sgc_label_reads_finish(sgc_table* t, int64_t* h_n_kmers, int64_t* h_n_hits,
                            int64_t* h_n_labels);
+/*
+ * The same step on 2-BIT PACKED reads (a quarter of the bytes over PCIe and HBM): A=0 C=1 G=2 T=3, base b
+ * of record s in bits 2(b%4).. of byte 16*U(s) + b/4 where U(s) = sum over earlier records of
+ * ceil(len/64) -- every record starts on a 16-byte boundary.  Lengths in bases: d_len[nseq] (int32), or
+ * NULL when every record has uniform_len bases (nothing but the packed bytes crosses the bus then).
+ * The kernel expands the codes back to the ASCII words the reference hash is defined on, so the labels are
+ * those of sgc_label_reads on the unpacked reads.  Packed records cannot carry non-ACGT bytes: the packer
+ * (sgc_pack_reads on the host, sgc_pack_reads_device) reports such records and the caller applies the
+ * reference policy (khmer raises; cdbg/index_reads.py:147-150).  _launch/_finish pair like above.
+ */
+int64_t sgc_packed_bytes(const int32_t* h_len, int uniform_len, int64_t nseq); /* -1: bad argument */
+int sgc_label_reads_packed_launch(sgc_table* t, const uint8_t* d_packed, int64_t packed_bytes,
+                                  const int32_t* d_len, int uniform_len, int64_t nseq, int k,
+                                  int64_t* d_ids_off, uint32_t* d_ids_out, int64_t ids_cap);
+int sgc_label_reads_packed(sgc_table* t, const uint8_t* d_packed, int64_t packed_bytes,
+                           const int32_t* d_len, int uniform_len, int64_t nseq, int k,
+                           int64_t* d_ids_off, uint32_t* d_ids_out, int64_t ids_cap,
+                           int64_t* h_n_kmers, int64_t* h_n_hits, int64_t* h_n_labels);
+/* ASCII (d_seq, d_off) already on the device -> packed records + d_len (nullable) + d_status (nullable,
+ * bit 0 = non-ACGT byte, packed as A).  *h_packed_bytes = bytes written.  Synchronises. */
+int sgc_pack_reads_device(sgc_ctx* ctx, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off,
+                          int64_t nseq, uint8_t* d_packed, int64_t packed_cap, int32_t* d_len,
+                          int32_t* d_status, int64_t* h_packed_bytes);
 
 /*
  * K6 -- replaces MPHF_KmerIndex.count_catlas_matches / build_catlas_node_sizes,
@@ -308,6 +333,10 @@ int sgc_reads_count(const uint8_t* h_data, int64_t n, int n_threads, int64_t* h_
  * (every sequence line stripped of surrounding whitespace), i.e. the (seq, off) pair sgc_label_reads takes. */
 int sgc_reads_scan(const uint8_t* h_data, int64_t n, int n_threads, int64_t nrec, int64_t seq_bytes,
                    int64_t* h_rec_pos, int64_t* h_name_lo, int64_t* h_name_hi, int64_t* h_seq_off, uint8_t* h_seq);
+/* Host packer for sgc_label_reads_packed: (h_seq, h_off) as produced by sgc_reads_scan -> packed records,
+ * h_len[nseq], h_bad[nseq] (nullable; 1 = the record holds a byte other than A/C/G/T, packed as A). */
+int sgc_pack_reads(const uint8_t* h_seq, const int64_t* h_off, int64_t nseq, int n_threads, uint8_t* h_packed,
+                   int64_t packed_cap, int32_t* h_len, uint8_t* h_bad, int64_t* h_packed_bytes);
 /* h_last[i] = latest earlier record with h_elig set (-1: none), h_paired[i] = record i is that record's
  * mate ("x/1" then "x/2", or two equal non-empty names).  ignore_paired: all 0 / -1. */
 int sgc_reads_pair_flags(const uint8_t* h_data, const int64_t* h_name_lo, const int64_t* h_name_hi,

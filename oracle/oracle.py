@@ -260,6 +260,15 @@ class COracleTable:
         miss = lib().sgc_oracle_count_matches(self._t, _ptr(hashes), len(hashes), _ptr(cnt)) if len(hashes) else 0
         return cnt, miss
 
+    def get_unique_values_list(self, hashes):
+        """BBHashTable.get_unique_values at the reference's granularity: any Python iterable of ints in,
+        ``{id: count}`` out (bbhash_table iterates the iterable in Cython; cdbg/hashing.py:67-69)."""
+        h = np.fromiter(hashes, np.uint64)
+        ids = self.lookup(h)
+        ids = ids[ids != 0xFFFFFFFF]
+        u, c = np.unique(ids, return_counts=True)
+        return dict(zip(u.tolist(), c.tolist()))
+
     def label_reads(self, buf, off, ksize, threads=0):
         nseq = len(off) - 1
         ids_off = np.zeros(nseq + 1, np.int64)

@@ -86,8 +86,8 @@ class GpuKmerTable:
         """build_mphf's two passes fused: hash every unitig k-mer and insert it under the
         unitig's id; hashes seen under two different ids are dropped (multicounts).
         ``side`` (default on; ``SGC_SIDE=0`` or ``side=False`` turns it off) also keeps the k-mers in
-        unitig order (16 B each) so that read labelling needs one table probe per four k-mers instead
-        of four: identical labels, half the HBM traffic, 1.25x the labelling rate."""
+        unitig order (8 B + 1 bit each) so that read labelling needs one table probe per eight k-mers
+        instead of eight: identical labels, a third of the HBM traffic."""
         t = cls(ctx)
         if isinstance(off, np.ndarray) or not hasattr(off, "device"):
             n_kmers = int(np.maximum(np.diff(off) - ksize + 1, 0).sum())
@@ -190,9 +190,16 @@ class GpuKmerTable:
         nz = np.flatnonzero(counts)
         return dict(zip(nz.tolist(), counts[nz].tolist()))
 
-    def label_reads(self, buf, off, ksize):
+    def label_reads(self, buf, off, ksize, packed=False):
         self._flush()
-        return self._dev.label_reads(buf, off, ksize)
+        return self._dev.label_reads(buf, off, ksize, packed=packed)
+
+    def label_reads_stream(self, batches, ksize, **kw):
+        """Pipelined labelling of a stream of host batches (pinned double buffers, H2D / kernels / D2H of
+        consecutive batches overlapped): see :meth:`DeviceTable.label_stream`.  What ``index_reads.main``
+        and ``bench.py``'s end-to-end arm run."""
+        self._flush()
+        return self._dev.label_stream(batches, ksize, **kw)
 
     def lookup_sequences(self, buf, off, ksize, n_ids=0, want_ids=True):
         self._flush()

@@ -4,6 +4,7 @@
 //   sgc_layout.cuh  constants, table slot layout, device scalars, tile-kernel argument block
 //   sgc_table.cuh   table primitives (probe sequence, CAS insert with build_mphf semantics, lookup)
 //   sgc_tile.cuh    segment staging + the warp-autonomous tile kernel (all fused modes)
+//   sgc_label8.cuh  the read-labelling kernel over the unitig-ordered side array (ASCII or 2-bit packed reads)
 //   sgc_kernels.cuh plan / stand-alone table / label-tail / dominator / K7 / generator kernels
 //   sgc_mphf.cuh    BBHash (boomphf) level construction, rank samples, lookup
 //   sgc_feed.hpp    host-only feeder (BGZF inflate, FASTA/FASTQ scan, mate pairing)
@@ -72,6 +73,7 @@ int fail(int code, const char* fmt, ...) {
 #include "sgc_layout.cuh"
 #include "sgc_table.cuh"
 #include "sgc_tile.cuh"
+#include "sgc_label8.cuh"
 #include "sgc_kernels.cuh"
 #include "sgc_mphf.cuh"
 
@@ -95,6 +97,7 @@ struct sgc_ctx {
     Scalars* d_scal = nullptr;
     Scalars* h_scal = nullptr;  // pinned
     DevBuf nk, nseg, seg_first, kmer_off, seg_map, cub_tmp, pairs_a, pairs_b, tmp_hash, tmp_id, tmp_idx, cursor;
+    DevBuf units, unit_off, base_off, unpacked;  // packed-read plans
     // optional CUDA-event timing of the tile kernel (bench.py roofline leg)
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
@@ -107,10 +110,13 @@ struct sgc_table {
     uint32_t nlines = 0;
     int home_shift = 0;
     int64_t max_entries = 0;
-    // unitig-ordered side array of {hash, id} records (tables built from sequences)
-    uint4* side = nullptr;
+    // unitig-ordered side array of 64-bit hashes (tables built from sequences) + break bits
+    unsigned long long* side_alloc = nullptr;  // SIDE_PAD records of padding on either end
+    uint32_t* brk = nullptr;
+    int64_t brk_words = 0;
     int64_t side_cap = 0, side_fill = 0;
     bool side_dirty = false;
+    unsigned long long* side8() const { return side_alloc ? side_alloc + SIDE_PAD : nullptr; }
     // pending label call
     bool label_pending = false;
     int64_t label_nseq = 0;
@@ -173,7 +179,7 @@ struct Plan {
 };
 
 int make_plan(sgc_ctx* c, const int64_t* d_off, int64_t nseq, int64_t seq_bytes, int k, int64_t* d_kmer_off,
-              Plan* plan) {
+              Plan* plan, int seg_k = SEG_K) {
     const size_t n1 = (size_t)nseq + 1;
     TRY(ensure(c, c->nk, n1 * 8));
     TRY(ensure(c, c->nseg, n1 * 8));
@@ -182,11 +188,11 @@ int make_plan(sgc_ctx* c, const int64_t* d_off, int64_t nseq, int64_t seq_bytes,
         TRY(ensure(c, c->kmer_off, n1 * 8));
         d_kmer_off = (int64_t*)c->kmer_off.p;
     }
-    const int64_t max_segs = nseq + seq_bytes / SEG_K + 1;
+    const int64_t max_segs = nseq + seq_bytes / seg_k + 1;
     TRY(ensure(c, c->seg_map, (size_t)max_segs * sizeof(SegDesc)));
     CU(cudaMemsetAsync(&c->d_scal->bad_offsets, 0, sizeof(int), c->stream));
     plan_count_kernel<<<grid_for((int64_t)n1, 256, 1 << 30), 256, 0, c->stream>>>(
-        d_off, nseq, k, seq_bytes, (int64_t*)c->nk.p, (int64_t*)c->nseg.p, c->d_scal);
+        d_off, nseq, k, seq_bytes, seg_k, (int64_t*)c->nk.p, (int64_t*)c->nseg.p, c->d_scal);
     c->launches++;
     size_t tb = 0;
     CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, (int64_t*)c->nk.p, d_kmer_off, (int64_t)n1, c->stream));
@@ -196,7 +202,7 @@ int make_plan(sgc_ctx* c, const int64_t* d_off, int64_t nseq, int64_t seq_bytes,
                                      c->stream));
     if (nseq > 0) {
         plan_expand_kernel<<<grid_for(nseq, 256, 1 << 30), 256, 0, c->stream>>>(
-            (int64_t*)c->seg_first.p, d_off, d_kmer_off, nseq, k, (SegDesc*)c->seg_map.p);
+            (int64_t*)c->seg_first.p, d_off, d_kmer_off, nseq, k, seg_k, (SegDesc*)c->seg_map.p);
         c->launches++;
     }
     CU(cudaGetLastError());
@@ -209,7 +215,7 @@ int make_plan(sgc_ctx* c, const int64_t* d_off, int64_t nseq, int64_t seq_bytes,
 
 template <int K, int MODE>
 int launch_tile_k(sgc_ctx* c, const TileArgs& a) {
-    size_t smem = sizeof(WarpTile<K, MODE == MODE_PARTITION>) * WPB + (MODE == MODE_LABEL_SIDE ? (size_t)WPB * QCAP * 12 : 0);
+    size_t smem = sizeof(WarpTile<K, MODE == MODE_PARTITION>) * WPB;
     // per device: the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
     static thread_local int blocks_per_sm_of[64] = {0};
     int& blocks_per_sm = blocks_per_sm_of[c->device & 63];
@@ -430,7 +436,8 @@ void sgc_ctx_destroy(sgc_ctx* c) {
     }
     c->timed.clear();
     DevBuf* bufs[] = {&c->nk, &c->nseg, &c->seg_first, &c->kmer_off, &c->seg_map, &c->cub_tmp,
-                      &c->pairs_a, &c->pairs_b, &c->tmp_hash, &c->tmp_id, &c->tmp_idx, &c->cursor};
+                      &c->pairs_a, &c->pairs_b, &c->tmp_hash, &c->tmp_id, &c->tmp_idx, &c->cursor,
+                      &c->units, &c->unit_off, &c->base_off, &c->unpacked};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->d_scal) cudaFree(c->d_scal);
@@ -517,8 +524,13 @@ int sgc_table_create(sgc_ctx* c, int64_t max_entries, float load, sgc_table** ou
     if (max_entries < 0) return fail(SGC_ERR_ARG, "max_entries < 0");
     TRY(set_device(c));
     // 32-byte buckets of two 16-byte slots, four per 128-byte line; `load` = expected hashes per
-    // bucket (default 0.75: ~4 % of lookups leave their home bucket, still inside the home line)
-    if (!(load > 0.0f)) load = 0.75f;
+    // bucket (default 0.6: ~2.3 % of the home buckets overflow; at 0.75 it was 4 %, and since one lane that
+    // leaves its home bucket drags its whole warp through the walk, the label kernel ran 3 % slower)
+    if (!(load > 0.0f)) {
+        const char* env = getenv("SGC_TABLE_LOAD");  // experiment knob
+        load = env ? (float)atof(env) : 0.6f;
+        if (!(load > 0.0f)) load = 0.6f;
+    }
     if (load > 1.6f) return fail(SGC_ERR_ARG, "table load %.2f too high (max 1.6 hashes per 2-slot bucket)", load);
     int64_t nb = (int64_t)((double)std::max<int64_t>(max_entries, 64) / load) + 4;
     nb = (nb + 3) & ~(int64_t)3;
@@ -547,7 +559,8 @@ void sgc_table_free(sgc_table* t) {
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
     if (t->buckets) cudaFree(t->buckets);
-    if (t->side) cudaFree(t->side);
+    if (t->side_alloc) cudaFree(t->side_alloc);
+    if (t->brk) cudaFree(t->brk);
     delete t;
 }
 
@@ -555,23 +568,32 @@ int64_t sgc_table_bytes(const sgc_table* t) { return t ? (int64_t)t->nbuckets * 
 
 int sgc_table_enable_side(sgc_table* t) {
     if (!t) return fail(SGC_ERR_ARG, "table is NULL");
-    if (t->side) return SGC_OK;
+    if (t->side_alloc) return SGC_OK;
     sgc_ctx* c = t->ctx;
     TRY(set_device(c));
     const int64_t cap = std::max<int64_t>(t->max_entries, 64);
     if (cap >= (int64_t)AUX_NONE) return fail(SGC_ERR_CAPACITY, "side array limited to 2^30-2 records");
-    cudaError_t e = cudaMalloc(&t->side, (size_t)cap * sizeof(uint4));
+    const size_t side_bytes = (size_t)(cap + 2 * SIDE_PAD) * 8;
+    const int64_t words = ((cap + BRK_PAD + 31) >> 5) + 2;
+    cudaError_t e = cudaMalloc(&t->side_alloc, side_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&t->brk, (size_t)words * 4);
     if (e != cudaSuccess) {
-        t->side = nullptr;
-        return fail(SGC_ERR_NOMEM, "cudaMalloc(%zu) for the side array failed: %s", (size_t)cap * sizeof(uint4),
-                    cudaGetErrorString(e));
+        if (t->side_alloc) cudaFree(t->side_alloc);
+        t->side_alloc = nullptr;
+        t->brk = nullptr;
+        return fail(SGC_ERR_NOMEM, "cudaMalloc(%zu) for the side array failed: %s", side_bytes, cudaGetErrorString(e));
     }
+    CU(cudaMemsetAsync(t->side_alloc, 0, side_bytes, c->stream));   // padding records (never inherited: break bits)
+    CU(cudaMemsetAsync(t->brk, 0xFF, (size_t)words * 4, c->stream));
+    t->brk_words = words;
     t->side_cap = cap;
     t->side_fill = 0;
     return SGC_OK;
 }
 
-int64_t sgc_table_side_bytes(const sgc_table* t) { return t && t->side ? t->side_cap * (int64_t)sizeof(uint4) : 0; }
+int64_t sgc_table_side_bytes(const sgc_table* t) {
+    return t && t->side_alloc ? (t->side_cap + 2 * SIDE_PAD) * 8 + t->brk_words * 4 : 0;
+}
 
 int sgc_table_set_home_shift(sgc_table* t, int shift) {
     if (!t || shift < 0 || shift > 16) return fail(SGC_ERR_ARG, "bad home shift");
@@ -605,7 +627,7 @@ int sgc_table_insert_sequences(sgc_table* t, const uint8_t* d_seq, int64_t seq_b
     Plan p;
     TRY(make_plan(c, d_off, nseq, seq_bytes, k, nullptr, &p));
     int64_t total = 0;
-    if (t->side) {
+    if (t->side_alloc) {
         CU(cudaMemcpyAsync(&c->h_scal->n_unique, p.kmer_off + nseq, 8, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         total = c->h_scal->n_unique;
@@ -618,11 +640,11 @@ int sgc_table_insert_sequences(sgc_table* t, const uint8_t* d_seq, int64_t seq_b
     table_args(a, t);
     a.seq_ids = d_ids;
     a.id_base = id_base;
-    a.side = t->side;
+    a.side8 = t->side8();
     a.side_base = (unsigned long long)t->side_fill;
     TRY(launch_tile<MODE_INSERT>(c, a));
     TRY(fetch_scalars(c));
-    if (t->side) {
+    if (t->side_alloc) {
         t->side_fill += total;
         t->side_dirty = true;
     }
@@ -752,6 +774,164 @@ int sgc_lookup_sequences(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes, 
 }
 
 // ---------------------------------------------------------------------------- K4
+}  // extern "C"
+
+namespace {
+
+template <int K, bool PACKED>
+int launch_label8_k(sgc_ctx* c, const Label8Args& a) {
+    const size_t smem = sizeof(WarpTile8<K>) * WPB8;
+    static thread_local int blocks_per_sm_of[64] = {0};
+    int& blocks_per_sm = blocks_per_sm_of[c->device & 63];
+    if (!blocks_per_sm) {
+        CU(cudaFuncSetAttribute(label8_kernel<K, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, label8_kernel<K, PACKED>, NT8, smem));
+        if (blocks_per_sm < 1) return fail(SGC_ERR_CUDA, "label kernel does not fit on an SM (smem %zu)", smem);
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->timing) {
+        CU(cudaEventCreate(&e0));
+        CU(cudaEventCreate(&e1));
+        CU(cudaEventRecord(e0, c->stream));
+    }
+    int ctas = blocks_per_sm;
+    if (const char* lim = getenv("SGC_CTAS_PER_SM")) {  // experiment knob
+        int v = atoi(lim);
+        if (v >= 1 && v < ctas) ctas = v;
+    }
+    label8_kernel<K, PACKED><<<c->num_sms * ctas, NT8, smem, c->stream>>>(a);
+    c->launches++;
+    CU(cudaGetLastError());
+    if (c->timing) {
+        CU(cudaEventRecord(e1, c->stream));
+        c->timed.emplace_back(e0, e1);
+    }
+    return SGC_OK;
+}
+
+template <bool PACKED>
+int launch_label8(sgc_ctx* c, const Label8Args& a) {
+    switch (a.k) {
+        case 21: return launch_label8_k<21, PACKED>(c, a);
+        case 31: return launch_label8_k<31, PACKED>(c, a);
+        default: return launch_label8_k<0, PACKED>(c, a);
+    }
+}
+
+// break bits of the side array (once after the build; the ids are a temporary)
+int side_finalize(sgc_table* t) {
+    sgc_ctx* c = t->ctx;
+    if (!t->side_dirty) return SGC_OK;
+    const uint64_t n = (uint64_t)t->side_fill;
+    TRY(ensure(c, c->tmp_id, (size_t)std::max<uint64_t>(n, 1) * 4));
+    side_ids_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(t->buckets, t->nbuckets, t->nlines, t->home_shift, t->side8(), n,
+                                                          (uint32_t*)c->tmp_id.p);
+    side_brk_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>((const uint32_t*)c->tmp_id.p, n, BRK_PAD, t->brk,
+                                                          (uint64_t)t->brk_words);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    t->side_dirty = false;
+    return SGC_OK;
+}
+
+bool use_side(const sgc_table* t) { return t->side_alloc && t->side_fill > 0 && !getenv("SGC_NO_SIDE"); }
+
+int label_common_prologue(sgc_table* t, int64_t nseq, int64_t ids_cap, unsigned long long* pairs_cap_out) {
+    sgc_ctx* c = t->ctx;
+    // candidate (sequence, id) keys: a few per read in practice; start from ids_cap and a floor
+    unsigned long long pairs_cap = (unsigned long long)std::max<int64_t>(std::max<int64_t>(ids_cap * 2, nseq * 4), 4096);
+    TRY(ensure(c, c->pairs_a, (size_t)pairs_cap * 8));
+    *pairs_cap_out = c->pairs_a.cap / 8;
+    return zero_scalars(c);
+}
+
+void label8_args(Label8Args& a, sgc_table* t, const uint8_t* seq, const Plan& p, int k, int32_t* d_status,
+                 unsigned long long pairs_cap) {
+    sgc_ctx* c = t->ctx;
+    memset(&a, 0, sizeof(a));
+    a.seq = seq;
+    a.segdesc = p.segdesc;
+    a.nsegs_p = p.nsegs_p;
+    a.status = d_status;
+    a.scal = c->d_scal;
+    a.k = k;
+    a.tbl = t->buckets;
+    a.nbuckets = t->nbuckets;
+    a.nlines = t->nlines;
+    a.home_shift = t->home_shift;
+    a.side8 = t->side8();
+    a.brk = t->brk;
+    a.pairs = (unsigned long long*)c->pairs_a.p;
+    a.pairs_cap = pairs_cap;
+}
+
+// the label8 kernel counts hits only: n_miss = (k-mers of the plan) - n_hits, computed on the device
+int label8_misses(sgc_ctx* c, const Plan& p, int64_t nseq) {
+    misses_from_total_kernel<<<1, 1, 0, c->stream>>>(p.kmer_off + nseq, c->d_scal);
+    c->launches++;
+    CU(cudaGetLastError());
+    return SGC_OK;
+}
+
+void label_pending(sgc_table* t, int64_t nseq, int64_t* d_ids_off, uint32_t* d_ids_out, int64_t ids_cap,
+                   unsigned long long pairs_cap) {
+    t->label_pending = true;
+    t->label_nseq = nseq;
+    t->label_ids_off = d_ids_off;
+    t->label_ids_out = d_ids_out;
+    t->label_ids_cap = ids_cap;
+    t->label_pairs_cap = pairs_cap;
+}
+
+// geometry of a batch of packed records: k-mer offsets, segment offsets, 16-byte unit offsets, (optionally)
+// base offsets; the segment map points into the packed buffer
+int make_packed_plan(sgc_ctx* c, const int32_t* d_len, int uniform_len, int64_t nseq, int64_t packed_bytes, int k,
+                     int seg_k, bool want_base_off, Plan* plan) {
+    const size_t n1 = (size_t)nseq + 1;
+    TRY(ensure(c, c->nk, n1 * 8));
+    TRY(ensure(c, c->nseg, n1 * 8));
+    TRY(ensure(c, c->seg_first, n1 * 8));
+    TRY(ensure(c, c->kmer_off, n1 * 8));
+    TRY(ensure(c, c->units, n1 * 8));
+    TRY(ensure(c, c->unit_off, n1 * 8));
+    // every 16-byte unit holds 64 bases: at most one segment per started unit pair (seg_k = 128) plus one per record
+    const int64_t max_segs = nseq + packed_bytes * 4 / seg_k + 1;
+    TRY(ensure(c, c->seg_map, (size_t)max_segs * sizeof(SegDesc)));
+    CU(cudaMemsetAsync(&c->d_scal->bad_offsets, 0, sizeof(int), c->stream));
+    packed_count_kernel<<<grid_for((int64_t)n1, 256, 1 << 30), 256, 0, c->stream>>>(
+        d_len, uniform_len, nseq, k, seg_k, (int64_t*)c->nk.p, (int64_t*)c->nseg.p, (int64_t*)c->units.p, c->d_scal);
+    c->launches++;
+    size_t tb = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, (int64_t*)c->nk.p, (int64_t*)c->kmer_off.p, (int64_t)n1, c->stream));
+    TRY(ensure(c, c->cub_tmp, tb));
+    CU(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tb, (int64_t*)c->nk.p, (int64_t*)c->kmer_off.p, (int64_t)n1, c->stream));
+    CU(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tb, (int64_t*)c->nseg.p, (int64_t*)c->seg_first.p, (int64_t)n1, c->stream));
+    CU(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tb, (int64_t*)c->units.p, (int64_t*)c->unit_off.p, (int64_t)n1, c->stream));
+    if (nseq > 0) {
+        packed_expand_kernel<<<grid_for(nseq, 256, 1 << 30), 256, 0, c->stream>>>(
+            (int64_t*)c->seg_first.p, (int64_t*)c->unit_off.p, (int64_t*)c->nk.p, (int64_t*)c->kmer_off.p, nseq, seg_k,
+            packed_bytes, (SegDesc*)c->seg_map.p, c->d_scal);
+        c->launches++;
+    }
+    if (want_base_off) {  // offsets in bases (the ASCII layout): scan of len
+        TRY(ensure(c, c->base_off, n1 * 8));
+        len_to_i64_kernel<<<grid_for((int64_t)n1, 256, 1 << 30), 256, 0, c->stream>>>(d_len, uniform_len, nseq,
+                                                                                    (int64_t*)c->nk.p);
+        c->launches++;
+        CU(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tb, (int64_t*)c->nk.p, (int64_t*)c->base_off.p, (int64_t)n1, c->stream));
+    }
+    CU(cudaGetLastError());
+    plan->kmer_off = (int64_t*)c->kmer_off.p;
+    plan->seg_first = (int64_t*)c->seg_first.p;
+    plan->segdesc = (const SegDesc*)c->seg_map.p;
+    plan->nsegs_p = (int64_t*)c->seg_first.p + nseq;
+    return SGC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int sgc_label_reads_launch(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off, int64_t nseq,
                            int k, int64_t* d_ids_off, uint32_t* d_ids_out, int64_t ids_cap, int32_t* d_status) {
     if (!t) return fail(SGC_ERR_ARG, "table is NULL");
@@ -761,39 +941,126 @@ int sgc_label_reads_launch(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes
     if (ids_cap < 0) return fail(SGC_ERR_ARG, "ids_cap < 0");
     TRY(set_device(c));
     if (d_status) CU(cudaMemsetAsync(d_status, 0, (size_t)nseq * 4, c->stream));
+    const bool side = use_side(t);
     Plan p;
-    TRY(make_plan(c, d_off, nseq, seq_bytes, k, nullptr, &p));
-    // candidate (sequence, id) keys: a few per read in practice; start from ids_cap and a floor
-    unsigned long long pairs_cap = (unsigned long long)std::max<int64_t>(std::max<int64_t>(ids_cap * 2, nseq * 4), 4096);
-    TRY(ensure(c, c->pairs_a, (size_t)pairs_cap * 8));
-    pairs_cap = c->pairs_a.cap / 8;
-    TRY(zero_scalars(c));
+    TRY(make_plan(c, d_off, nseq, seq_bytes, k, nullptr, &p, side ? SEG_K8 : SEG_K));
+    unsigned long long pairs_cap = 0;
+    TRY(label_common_prologue(t, nseq, ids_cap, &pairs_cap));
     if (nseq > 0) {
-        TileArgs a = base_args(c, d_seq, d_off, k, p, d_status);
-        table_args(a, t);
-        a.pairs = (unsigned long long*)c->pairs_a.p;
-        a.pairs_cap = pairs_cap;
-        if (t->side && t->side_fill > 0 && !getenv("SGC_NO_SIDE")) {
-            if (t->side_dirty) {
-                side_fixup_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(t->buckets, t->nbuckets, t->nlines, t->home_shift,
-                                                                        t->side, (uint64_t)t->side_fill);
-                c->launches++;
-                t->side_dirty = false;
-            }
-            a.side = t->side;
-            a.side_n = (unsigned long long)t->side_fill;
-            TRY(launch_tile<MODE_LABEL_SIDE>(c, a));
+        if (side) {
+            TRY(side_finalize(t));
+            Label8Args a;
+            label8_args(a, t, d_seq, p, k, d_status, pairs_cap);
+            TRY(launch_label8<false>(c, a));
+            TRY(label8_misses(c, p, nseq));
         } else {
+            TileArgs a = base_args(c, d_seq, d_off, k, p, d_status);
+            table_args(a, t);
+            a.pairs = (unsigned long long*)c->pairs_a.p;
+            a.pairs_cap = pairs_cap;
             TRY(launch_tile<MODE_LABEL>(c, a));
         }
     }
     CU(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(Scalars), cudaMemcpyDeviceToHost, c->stream));
-    t->label_pending = true;
-    t->label_nseq = nseq;
-    t->label_ids_off = d_ids_off;
-    t->label_ids_out = d_ids_out;
-    t->label_ids_cap = ids_cap;
-    t->label_pairs_cap = pairs_cap;
+    label_pending(t, nseq, d_ids_off, d_ids_out, ids_cap, pairs_cap);
+    return SGC_OK;
+}
+
+int64_t sgc_packed_bytes(const int32_t* h_len, int uniform_len, int64_t nseq) {
+    if (nseq < 0) return -1;
+    if (!h_len) return uniform_len < 0 ? -1 : nseq * (int64_t)((uniform_len + 63) / 64) * 16;
+    int64_t units = 0;
+    for (int64_t s = 0; s < nseq; s++) {
+        if (h_len[s] < 0) return -1;
+        units += ((int64_t)h_len[s] + 63) / 64;
+    }
+    return units * 16;
+}
+
+int sgc_label_reads_packed_launch(sgc_table* t, const uint8_t* d_packed, int64_t packed_bytes, const int32_t* d_len,
+                                  int uniform_len, int64_t nseq, int k, int64_t* d_ids_off, uint32_t* d_ids_out,
+                                  int64_t ids_cap) {
+    if (!t) return fail(SGC_ERR_ARG, "table is NULL");
+    sgc_ctx* c = t->ctx;
+    if (k < 1 || k > SGC_MAX_K) return fail(SGC_ERR_ARG, "k must be in 1..%d (got %d)", SGC_MAX_K, k);
+    if (nseq < 0 || packed_bytes < 0 || nseq >= (int64_t)1 << 32) return fail(SGC_ERR_ARG, "bad size");
+    if (!d_packed && packed_bytes > 0) return fail(SGC_ERR_ARG, "d_packed is NULL");
+    if (((uintptr_t)d_packed & 15) != 0) return fail(SGC_ERR_ARG, "d_packed must be 16-byte aligned");
+    if (!d_len && uniform_len < 0) return fail(SGC_ERR_ARG, "need d_len or uniform_len >= 0");
+    if (!d_ids_off) return fail(SGC_ERR_ARG, "d_ids_off is NULL");
+    if (ids_cap < 0) return fail(SGC_ERR_ARG, "ids_cap < 0");
+    TRY(set_device(c));
+    const bool side = use_side(t);
+    Plan p;
+    TRY(make_packed_plan(c, d_len, uniform_len, nseq, packed_bytes, k, SEG_K8, !side, &p));
+    unsigned long long pairs_cap = 0;
+    TRY(label_common_prologue(t, nseq, ids_cap, &pairs_cap));
+    if (nseq > 0) {
+        if (side) {
+            TRY(side_finalize(t));
+            Label8Args a;
+            label8_args(a, t, d_packed, p, k, nullptr, pairs_cap);
+            TRY(launch_label8<true>(c, a));
+            TRY(label8_misses(c, p, nseq));
+        } else {
+            // table without a side array (loaded from (hash, id) pairs): expand to ASCII, per-k-mer probing
+            TRY(ensure(c, c->unpacked, (size_t)std::max<int64_t>(packed_bytes * 4, 16)));
+            unpack_reads_kernel<<<c->num_sms * 16, 256, 0, c->stream>>>((const uint32_t*)d_packed, (const int64_t*)c->base_off.p,
+                                                                       (const int64_t*)c->unit_off.p, nseq,
+                                                                       (uint8_t*)c->unpacked.p);
+            c->launches++;
+            Plan pa;
+            TRY(make_plan(c, (const int64_t*)c->base_off.p, nseq, packed_bytes * 4, k, nullptr, &pa));
+            TileArgs a = base_args(c, (const uint8_t*)c->unpacked.p, (const int64_t*)c->base_off.p, k, pa, nullptr);
+            table_args(a, t);
+            a.pairs = (unsigned long long*)c->pairs_a.p;
+            a.pairs_cap = pairs_cap;
+            TRY(launch_tile<MODE_LABEL>(c, a));
+        }
+    }
+    CU(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(Scalars), cudaMemcpyDeviceToHost, c->stream));
+    label_pending(t, nseq, d_ids_off, d_ids_out, ids_cap, pairs_cap);
+    return SGC_OK;
+}
+
+int sgc_label_reads_packed(sgc_table* t, const uint8_t* d_packed, int64_t packed_bytes, const int32_t* d_len,
+                           int uniform_len, int64_t nseq, int k, int64_t* d_ids_off, uint32_t* d_ids_out,
+                           int64_t ids_cap, int64_t* h_n_kmers, int64_t* h_n_hits, int64_t* h_n_labels) {
+    TRY(sgc_label_reads_packed_launch(t, d_packed, packed_bytes, d_len, uniform_len, nseq, k, d_ids_off, d_ids_out, ids_cap));
+    return sgc_label_reads_finish(t, h_n_kmers, h_n_hits, h_n_labels);
+}
+
+// ASCII (seq, off) on the device -> packed records (tests / bench; the host feeder packs with sgc_pack_reads)
+int sgc_pack_reads_device(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off, int64_t nseq,
+                          uint8_t* d_packed, int64_t packed_cap, int32_t* d_len, int32_t* d_status, int64_t* h_packed_bytes) {
+    if (!c) return fail(SGC_ERR_ARG, "ctx is NULL");
+    TRY(check_seq_args(d_seq, seq_bytes, d_off, nseq, 1));
+    if (!h_packed_bytes) return fail(SGC_ERR_ARG, "h_packed_bytes is NULL");
+    TRY(set_device(c));
+    const size_t n1 = (size_t)nseq + 1;
+    TRY(ensure(c, c->units, n1 * 8));
+    TRY(ensure(c, c->unit_off, n1 * 8));
+    CU(cudaMemsetAsync(&c->d_scal->bad_offsets, 0, sizeof(int), c->stream));
+    off_to_units_kernel<<<grid_for((int64_t)n1, 256, 1 << 30), 256, 0, c->stream>>>(d_off, nseq, seq_bytes, (int64_t*)c->units.p,
+                                                                                  d_len, c->d_scal);
+    c->launches++;
+    size_t tb = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, (int64_t*)c->units.p, (int64_t*)c->unit_off.p, (int64_t)n1, c->stream));
+    TRY(ensure(c, c->cub_tmp, tb));
+    CU(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tb, (int64_t*)c->units.p, (int64_t*)c->unit_off.p, (int64_t)n1, c->stream));
+    int64_t units = 0;
+    CU(cudaMemcpyAsync(&units, (int64_t*)c->unit_off.p + nseq, 8, cudaMemcpyDeviceToHost, c->stream));
+    TRY(fetch_scalars(c));
+    TRY(bad_offsets_check(c));
+    *h_packed_bytes = units * 16;
+    if (units * 16 > packed_cap) return fail(SGC_ERR_CAPACITY, "packed_cap %lld < %lld bytes", (long long)packed_cap, (long long)(units * 16));
+    if (d_status) CU(cudaMemsetAsync(d_status, 0, (size_t)nseq * 4, c->stream));
+    if (units > 0) {
+        pack_reads_kernel<<<grid_for(units * 4, 256, c->num_sms * 16), 256, 0, c->stream>>>(
+            d_seq, d_off, (const int64_t*)c->unit_off.p, nseq, (uint32_t*)d_packed, units * 4, d_status);
+        c->launches++;
+    }
+    CU(cudaGetLastError());
     return SGC_OK;
 }
 

@@ -313,6 +313,58 @@ int sgc_bgzf_inflate(const uint8_t* h_raw, int64_t raw_bytes, const int64_t* h_c
     return SGC_OK;
 }
 
+// ---------------------------------------------------------------------------- 2-bit packing
+// ASCII (seq, off) -> packed records for sgc_label_reads_packed: A=0 C=1 G=2 T=3, base b of record s in bits
+// 2(b%4).. of byte 16*unit_off[s] + b/4, every record padded to a multiple of 16 bytes (64 bases).
+// h_len[s] = length in bases; h_bad[s] (nullable) = 1 when the record holds a byte other than A/C/G/T (packed
+// as A: the caller applies the reference's policy -- khmer raises on such reads).  A quarter of the bytes
+// cross PCIe and HBM; the kernel expands them back to the ASCII words the reference hash is defined on.
+int sgc_pack_reads(const uint8_t* h_seq, const int64_t* h_off, int64_t nseq, int n_threads, uint8_t* h_packed,
+                   int64_t packed_cap, int32_t* h_len, uint8_t* h_bad, int64_t* h_packed_bytes) {
+    if (nseq < 0 || !h_off || !h_packed_bytes || (nseq > 0 && !h_len)) return fail(SGC_ERR_ARG, "bad argument");
+    std::vector<int64_t> uoff((size_t)nseq + 1, 0);
+    for (int64_t s = 0; s < nseq; ++s) {
+        const int64_t L = h_off[s + 1] - h_off[s];
+        if (L < 0 || L > 0x7FFFFFFF) return fail(SGC_ERR_ARG, "bad offsets at record %lld", (long long)s);
+        uoff[(size_t)s + 1] = uoff[(size_t)s] + (L + 63) / 64;
+    }
+    const int64_t total = uoff[(size_t)nseq] * 16;
+    *h_packed_bytes = total;
+    if (total > packed_cap) return fail(SGC_ERR_CAPACITY, "packed_cap %lld < %lld bytes", (long long)packed_cap, (long long)total);
+    if (total > 0 && (!h_packed || !h_seq)) return fail(SGC_ERR_ARG, "NULL buffer");
+    static const struct Lut { uint8_t v[256]; Lut() { memset(v, 4, 256); v['A'] = 0; v['C'] = 1; v['G'] = 2; v['T'] = 3; } } lut;
+    const int nt = feed::pick_threads(n_threads, std::max<int64_t>(nseq >> 10, 1));
+    feed::parallel_for(nt, [&](int t) {
+        const int64_t s0 = nseq * t / nt, s1 = nseq * (t + 1) / nt;
+        for (int64_t s = s0; s < s1; ++s) {
+            const uint8_t* src = h_seq + h_off[s];
+            const int64_t L = h_off[s + 1] - h_off[s];
+            uint8_t* dst = h_packed + uoff[(size_t)s] * 16;
+            const int64_t nbytes = (uoff[(size_t)s + 1] - uoff[(size_t)s]) * 16;
+            uint8_t bad = 0;
+            int64_t b = 0, o = 0;
+            for (; b + 4 <= L; b += 4, ++o) {
+                const uint8_t c0 = lut.v[src[b]], c1 = lut.v[src[b + 1]], c2 = lut.v[src[b + 2]], c3 = lut.v[src[b + 3]];
+                bad |= (uint8_t)((c0 | c1 | c2 | c3) & 4);
+                dst[o] = (uint8_t)((c0 & 3) | ((c1 & 3) << 2) | ((c2 & 3) << 4) | ((c3 & 3) << 6));
+            }
+            if (b < L) {
+                uint8_t x = 0;
+                for (int j = 0; b + j < L; ++j) {
+                    const uint8_t c = lut.v[src[b + j]];
+                    bad |= (uint8_t)(c & 4);
+                    x |= (uint8_t)((c & 3) << (2 * j));
+                }
+                dst[o++] = x;
+            }
+            if (o < nbytes) memset(dst + o, 0, (size_t)(nbytes - o));
+            h_len[s] = (int32_t)L;
+            if (h_bad) h_bad[s] = bad ? 1 : 0;
+        }
+    });
+    return SGC_OK;
+}
+
 // ---------------------------------------------------------------------------- records
 // h_info[0..2] = number of records, total sequence bytes, format (0 FASTA, 1 FASTQ)
 int sgc_reads_count(const uint8_t* h_data, int64_t n, int n_threads, int64_t* h_info) {

@@ -10,7 +10,7 @@ namespace dev {
 // ----------------------------------------------------------------------------------
 // plan kernels: per-sequence k-mer / segment counts and the segment map
 // ----------------------------------------------------------------------------------
-__global__ void plan_count_kernel(const int64_t* __restrict__ off, int64_t nseq, int k, int64_t seq_bytes,
+__global__ void plan_count_kernel(const int64_t* __restrict__ off, int64_t nseq, int k, int64_t seq_bytes, int seg_k,
                                   int64_t* __restrict__ nk_out, int64_t* __restrict__ nseg_out, Scalars* scal) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s > nseq) return;
@@ -25,11 +25,11 @@ __global__ void plan_count_kernel(const int64_t* __restrict__ off, int64_t nseq,
         }
     }
     nk_out[s] = nk;
-    nseg_out[s] = (nk + SEG_K - 1) / SEG_K;
+    nseg_out[s] = (nk + seg_k - 1) / seg_k;
 }
 
 __global__ void plan_expand_kernel(const int64_t* __restrict__ seg_first, const int64_t* __restrict__ off,
-                                   const int64_t* __restrict__ kmer_off, int64_t nseq, int k,
+                                   const int64_t* __restrict__ kmer_off, int64_t nseq, int k, int seg_k,
                                    SegDesc* __restrict__ segdesc) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nseq) return;
@@ -37,12 +37,12 @@ __global__ void plan_expand_kernel(const int64_t* __restrict__ seg_first, const 
     if (a == b) return;
     const int64_t o0 = off[s], nkseq = off[s + 1] - o0 - k + 1, ko = kmer_off[s];
     for (int64_t j = a; j < b; j++) {
-        const int64_t q0 = (j - a) * SEG_K;
+        const int64_t q0 = (j - a) * seg_k;
         SegDesc d;
         d.start = o0 + q0;
         d.kout = ko + q0;
         d.seq = (unsigned int)s;
-        d.nk = (int)(nkseq - q0 < SEG_K ? nkseq - q0 : SEG_K);
+        d.nk = (int)(nkseq - q0 < seg_k ? nkseq - q0 : seg_k);
         d.pad[0] = d.pad[1] = 0;
         segdesc[j] = d;
     }
@@ -143,15 +143,29 @@ __global__ void table_stats_kernel(const Bucket* tbl, uint32_t nb, Scalars* scal
     }
 }
 
-// side[g].id := what a table lookup of side[g].hash returns (MISS for dropped hashes), so that a
-// hash match against a side record is by construction the table's own answer
-__global__ void side_fixup_kernel(const Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, uint4* side, uint64_t n) {
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (uint64_t)gridDim.x * blockDim.x) {
-        uint4 r = side[g];
-        const uint64_t h = ((uint64_t)r.y << 32) | r.x;
-        r.z = table_lookup(tbl, nb, nlines, hs, h);
-        r.w = 0;
-        side[g] = r;
+__global__ void misses_from_total_kernel(const int64_t* __restrict__ total, Scalars* scal) {
+    scal->n_miss = (unsigned long long)*total - scal->n_hits;
+}
+
+// Side-array finalisation (after the build): ids[p] = what a table lookup of side8[p] returns ...
+__global__ void side_ids_kernel(const Bucket* tbl, uint32_t nb, uint32_t nlines, int hs,
+                                const unsigned long long* __restrict__ side8, uint64_t n, uint32_t* __restrict__ ids) {
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (uint64_t)gridDim.x * blockDim.x)
+        ids[g] = table_lookup(tbl, nb, nlines, hs, side8[g]);
+}
+// ... and the break bits: bit pad + p is set when p is outside [0, n), p == 0, or ids[p] != ids[p-1].
+// A k-mer that matches side8[q] may inherit the id found for side8[g] iff no break lies in (g, q]
+// (q > g) resp. (q, g] (q < g): then the table gives both hashes the same answer.
+__global__ void side_brk_kernel(const uint32_t* __restrict__ ids, uint64_t n, int pad, uint32_t* __restrict__ brk,
+                                uint64_t nwords) {
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t bits = 0;
+        for (int b = 0; b < 32; b++) {
+            const long long p = (long long)(w * 32 + b) - pad;
+            const bool brk_here = p <= 0 || p >= (long long)n || ids[p] != ids[p - 1];
+            bits |= (uint32_t)brk_here << b;
+        }
+        brk[w] = bits;
     }
 }
 
@@ -204,7 +218,7 @@ __global__ void csr_count_kernel(const unsigned long long* __restrict__ uniq, co
 // Sequences with more than CSR_SMALL candidates raise csr_big and the caller falls back to the
 // radix-sort path (pairs_to_csr_sorted), which handles any size.
 // ----------------------------------------------------------------------------------
-constexpr int CSR_SMALL = 24;
+constexpr int CSR_SMALL = 160;  // any 150-bp read fits (<= 120 k-mers, a few duplicates of a candidate)
 
 __global__ void __launch_bounds__(256) csr2_count_kernel(const unsigned long long* __restrict__ pairs, long long n,
                                                          unsigned long long* __restrict__ cnt) {
@@ -395,6 +409,122 @@ __global__ void synth_unitigs_kernel(const uint8_t* __restrict__ genome, const i
         out[i] = genome[cuts[lo] + (i - o)];
         if (i == o) out_off[lo] = o;
         if (i == total - 1) out_off[n] = total;
+    }
+}
+
+
+// ----------------------------------------------------------------------------------
+// 2-bit packed reads (A=0 C=1 G=2 T=3; base b of record s in bits 2(b%4).. of byte poff[s] + b/4;
+// records start on 16-byte boundaries)
+// ----------------------------------------------------------------------------------
+// per-sequence length (len[s], or uniform_len when len is NULL) -> k-mers, segments, packed 16-byte units
+__global__ void packed_count_kernel(const int32_t* __restrict__ len, int uniform_len, int64_t nseq, int k, int seg_k,
+                                    int64_t* __restrict__ nk_out, int64_t* __restrict__ nseg_out,
+                                    int64_t* __restrict__ units_out, Scalars* scal) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > nseq) return;
+    int64_t nk = 0, units = 0;
+    if (s < nseq) {
+        const int64_t L = len ? (int64_t)len[s] : (int64_t)uniform_len;
+        if (L < 0) atomicOr(&scal->bad_offsets, 1);
+        else {
+            nk = L - k + 1 > 0 ? L - k + 1 : 0;
+            units = (L + 63) / 64;
+        }
+    }
+    nk_out[s] = nk;
+    nseg_out[s] = (nk + seg_k - 1) / seg_k;
+    units_out[s] = units;
+}
+
+// segment map of packed records: start = byte offset of the segment's first base (seg_k % 64 == 0, so it
+// stays 16-byte aligned)
+__global__ void packed_expand_kernel(const int64_t* __restrict__ seg_first, const int64_t* __restrict__ unit_off,
+                                     const int64_t* __restrict__ nk_arr, const int64_t* __restrict__ kmer_off,
+                                     int64_t nseq, int seg_k, int64_t packed_bytes, SegDesc* __restrict__ segdesc,
+                                     Scalars* scal) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseq) return;
+    const int64_t a = seg_first[s], b = seg_first[s + 1];
+    if (unit_off[s + 1] * 16 > packed_bytes) atomicOr(&scal->bad_offsets, 1);
+    if (a == b) return;
+    const int64_t nkseq = nk_arr[s], ko = kmer_off[s], p0 = unit_off[s] * 16;
+    for (int64_t j = a; j < b; j++) {
+        const int64_t q0 = (j - a) * seg_k;
+        SegDesc d;
+        d.start = p0 + q0 / 4;
+        d.kout = ko + q0;
+        d.seq = (unsigned int)s;
+        d.nk = unit_off[s + 1] * 16 > packed_bytes ? 0 : (int)(nkseq - q0 < seg_k ? nkseq - q0 : seg_k);
+        d.pad[0] = d.pad[1] = 0;
+        segdesc[j] = d;
+    }
+}
+
+__global__ void len_to_i64_kernel(const int32_t* __restrict__ len, int uniform_len, int64_t nseq, int64_t* __restrict__ out) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > nseq) return;
+    out[s] = s < nseq ? (len ? (int64_t)len[s] : (int64_t)uniform_len) : 0;
+}
+
+// base offsets -> 16-byte units per record (and the int32 lengths the packed API takes)
+__global__ void off_to_units_kernel(const int64_t* __restrict__ off, int64_t nseq, int64_t seq_bytes,
+                                    int64_t* __restrict__ units, int32_t* len_out, Scalars* scal) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > nseq) return;
+    int64_t u = 0;
+    if (s < nseq) {
+        const int64_t o0 = off[s], o1 = off[s + 1];
+        if (o0 < 0 || o1 < o0 || o1 > seq_bytes || o1 - o0 > 0x7FFFFFFF) atomicOr(&scal->bad_offsets, 1);
+        else {
+            u = (o1 - o0 + 63) / 64;
+            if (len_out) len_out[s] = (int32_t)(o1 - o0);
+        }
+    }
+    units[s] = u;
+}
+
+// ASCII (seq, off) on the device -> packed records; status[s] bit 0 = a byte other than A/C/G/T (packed as A).
+// One thread per packed 32-bit word (16 bases).
+__global__ void pack_reads_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
+                                  const int64_t* __restrict__ unit_off, int64_t nseq, uint32_t* __restrict__ packed,
+                                  int64_t total_words, int32_t* status) {
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total_words; w += (int64_t)gridDim.x * blockDim.x) {
+        // record of word w: largest s with unit_off[s] * 4 <= w
+        int64_t lo = 0, hi = nseq - 1;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi + 1) >> 1;
+            if (unit_off[mid] * 4 <= w) lo = mid; else hi = mid - 1;
+        }
+        const int64_t b0 = (w - unit_off[lo] * 4) * 16, L = off[lo + 1] - off[lo];
+        uint32_t x = 0;
+        bool bad = false;
+        for (int j = 0; j < 16; j++) {
+            if (b0 + j < L) {
+                const uint8_t c = seq[off[lo] + b0 + j];
+                const uint32_t code = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+                if (code > 3u) bad = true;
+                x |= (code & 3u) << (2 * j);
+            }
+        }
+        packed[w] = x;
+        if (bad && status) atomicOr(&status[lo], 1);
+    }
+}
+
+// packed records -> ASCII (seq, off) (general fallback for tables without a side array)
+__global__ void unpack_reads_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ off,
+                                    const int64_t* __restrict__ unit_off, int64_t nseq, uint8_t* __restrict__ seq) {
+    const int64_t total = off[nseq];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = nseq - 1;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi + 1) >> 1;
+            if (off[mid] <= i) lo = mid; else hi = mid - 1;
+        }
+        const int64_t b = i - off[lo];
+        const uint32_t x = packed[unit_off[lo] * 4 + (b >> 4)];
+        seq[i] = "ACGT"[(x >> (2 * (b & 15))) & 3u];
     }
 }
 

@@ -19,9 +19,6 @@ namespace dev {
 #ifndef SGC_PROBE_MIN_CTAS
 #define SGC_PROBE_MIN_CTAS 4
 #endif
-#ifndef SGC_SIDE_MIN_CTAS
-#define SGC_SIDE_MIN_CTAS 4
-#endif
 #ifndef SGC_NT
 #define SGC_NT 256
 #endif
@@ -30,16 +27,12 @@ constexpr int WPB = NT / 32;    // warps per CTA; every warp runs its own rounds
 constexpr int SPW = 4;          // segments staged per warp round (8 lanes stage one segment)
 constexpr int SEG_K = 256;      // k-mers per segment
 constexpr int PAIR_BUF = 128;   // label keys staged per warp before one global reservation
-#ifndef SGC_QCAP
-#define SGC_QCAP 128            // 4 CTAs x 8 warps x (tile + queue) must fit 227 KB of shared memory
-#endif
-constexpr int QCAP = SGC_QCAP;  // MODE_LABEL_SIDE: k-mers queued per warp for a dense table probe
 constexpr unsigned long long SEQ_MASK = (1ULL << 40) - 1ULL;
 
 constexpr uint32_t VAL_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t VAL_MULTI = 0xFFFFFFFEu;
 
-enum Mode { MODE_HASH = 0, MODE_INSERT = 1, MODE_LOOKUP = 2, MODE_LABEL = 3, MODE_PARTITION = 4, MODE_GATHER = 5, MODE_MINHASH = 6, MODE_LABEL_SIDE = 7 };
+enum Mode { MODE_HASH = 0, MODE_INSERT = 1, MODE_LOOKUP = 2, MODE_LABEL = 3, MODE_PARTITION = 4, MODE_GATHER = 5, MODE_MINHASH = 6 };
 
 template <int K>
 struct Geo {
@@ -123,10 +116,9 @@ struct TileArgs {
     int home_shift;
     const uint32_t* seq_ids;
     uint32_t id_base;
-    // side array (unitig-ordered {hash, id} records): written by MODE_INSERT, read by MODE_LABEL_SIDE
-    uint4* side;
+    // side array (unitig-ordered 64-bit hashes): written by MODE_INSERT, read by label8_kernel
+    unsigned long long* side8;
     unsigned long long side_base;   // MODE_INSERT: first record of this batch
-    unsigned long long side_n;      // MODE_LABEL_SIDE: number of records
     // MODE_LOOKUP
     uint32_t* kmer_ids;
     uint32_t* count_by_id;

@@ -116,7 +116,7 @@ __device__ __noinline__ void flush_pairs_out(Scalars* scal, unsigned long long* 
 }
 
 template <int K, int MODE>
-__global__ void __launch_bounds__(NT, MODE == MODE_LABEL_SIDE ? SGC_SIDE_MIN_CTAS : (MODE == MODE_LABEL || MODE == MODE_LOOKUP) ? SGC_PROBE_MIN_CTAS : 1) tile_kernel(const TileArgs a) {
+__global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP) ? SGC_PROBE_MIN_CTAS : 1) tile_kernel(const TileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int WPS = Geo<K>::WPS;
     const int lane = threadIdx.x & 31;
@@ -163,60 +163,6 @@ __global__ void __launch_bounds__(NT, MODE == MODE_LABEL_SIDE ? SGC_SIDE_MIN_CTA
         }
         (void)active;
         (void)nv;
-    };
-
-    // MODE_LABEL_SIDE: per-warp queue of k-mers that still need their own table probe
-    unsigned long long* qh = nullptr;
-    uint32_t* qs = nullptr;
-    unsigned q_fill = 0;  // warp-uniform
-    if constexpr (MODE == MODE_LABEL_SIDE) {
-        unsigned char* qbase = smem_raw + sizeof(Tile) * WPB;
-        qh = reinterpret_cast<unsigned long long*>(qbase) + (threadIdx.x >> 5) * QCAP;
-        qs = reinterpret_cast<uint32_t*>(qbase + (size_t)WPB * QCAP * 8) + (threadIdx.x >> 5) * QCAP;
-    }
-    // probe the queued k-mers densely: one item per lane, probe of item j+32 in flight while item j is
-    // resolved; hits become (sequence, id) keys right away (no neighbour to compare with here, except
-    // the previous lane's item)
-    auto drain_queue = [&]() {
-        if constexpr (MODE == MODE_LABEL_SIDE) {
-            bool d_act = false;
-            uint64_t d_h = 0;
-            uint32_t d_sq = 0, d_b = 0;
-            Entry d_e0, d_e1;
-            auto settle = [&]() {
-                uint32_t id = SGC_MISS;
-                if (d_act) {
-                    uint32_t v, aux;
-                    if (bucket_match(d_e0, d_e1, d_h, v)) id = v;
-                    else if (bucket_overflowed(d_e0)) id = lookup_slow(a.tbl, a.nlines, d_b, d_h, aux);
-                    if (id != SGC_MISS) my_hits++; else my_miss++;
-                }
-                const unsigned long long key = ((unsigned long long)d_sq << 32) | id;
-                const unsigned long long prevk = __shfl_up_sync(0xffffffffu, key, 1);
-                const bool has = d_act && id != SGC_MISS && !(lane > 0 && prevk == key);
-                const unsigned m = __ballot_sync(0xffffffffu, has);
-                if (m) {
-                    const unsigned total = __popc(m);
-                    if (pair_fill + total > PAIR_BUF) flush_pairs();
-                    if (has) wt.pairs[pair_fill + __popc(m & ((1u << lane) - 1u))] = key;
-                    pair_fill += total;
-                }
-            };
-            // one trip more than there are items: the last trip only settles (every lambda of this kernel
-            // has ONE call site -- the hot loops must stay inside the 32 KB instruction cache)
-            for (unsigned j0 = 0; j0 < q_fill + 32; j0 += 32) {
-                const unsigned j = j0 + lane;
-                const bool act = j < q_fill;
-                const uint64_t h = act ? qh[j] : 0ULL;
-                const uint32_t sq = act ? qs[j] : 0u;
-                if (j0 > 0) settle();
-                d_act = act; d_h = h; d_sq = sq;
-                d_b = act ? home_bucket(h, a.nbuckets, a.home_shift) : 0u;
-                load_bucket_nc(a.tbl + d_b, d_e0, d_e1);  // unconditional (bucket 0 in the last trip)
-            }
-            __syncwarp();
-            q_fill = 0;
-        }
     };
 
     // ------------------------------------------------------------------------------------------
@@ -352,8 +298,8 @@ __global__ void __launch_bounds__(NT, MODE == MODE_LABEL_SIDE ? SGC_SIDE_MIN_CTA
         const int G = wt.gpre[SPW];
 
         // locate group g (segment sg, first k-mer i, nv valid k-mers) and hash its 4 k-mers
-        // ori (MODE_INSERT / MODE_LABEL_SIDE only): bit t = forward k-mer t hashes below its reverse complement
-        constexpr bool WANT_ORI = MODE == MODE_INSERT || MODE == MODE_LABEL_SIDE;
+        // ori (MODE_INSERT only): bit t = forward k-mer t hashes below its reverse complement
+        constexpr bool WANT_ORI = MODE == MODE_INSERT;
         auto locate_and_hash = [&](int g, int& sg, int& i, int& nv, uint64_t (&h)[4], unsigned& ori) {
             int lo = 0;  // largest sg with gpre[sg] <= g
 #pragma unroll
@@ -466,9 +412,9 @@ __global__ void __launch_bounds__(NT, MODE == MODE_LABEL_SIDE ? SGC_SIDE_MIN_CTA
                         const unsigned long long g0 = a.side_base + (unsigned long long)(wt.kout[sg] + i);
                         for (int t = 0; t < nv; t++) {
                             uint32_t aux = AUX_NONE;
-                            if (a.side) {  // unitig-ordered record; its id is fixed up after the build
+                            if (a.side8) {  // unitig-ordered record of the hash (sgc_label8.cuh reads them)
                                 aux = (uint32_t)(g0 + t) | (((ori >> t) & 1u) ? ORI_BIT : 0u);
-                                a.side[g0 + t] = make_uint4((uint32_t)h[t], (uint32_t)(h[t] >> 32), id, 0u);
+                                a.side8[g0 + t] = h[t];
                             }
                             table_insert(a.tbl, a.nbuckets, a.nlines, a.home_shift, h[t], id, aux, a.scal);
                         }
@@ -596,110 +542,6 @@ __global__ void __launch_bounds__(NT, MODE == MODE_LABEL_SIDE ? SGC_SIDE_MIN_CTA
                 }
                 emit_candidates(ids, active, sg, i, nv);
             }
-        } else if constexpr (MODE == MODE_LABEL_SIDE) {
-            // K4 with fewer HBM lines per k-mer.  Only the FIRST k-mer of a group (the anchor) probes the
-            // hash table.  Its slot carries g, the k-mer's position in
-            // the table's unitig-ordered side array of {hash, id} records (id = what a table lookup of that
-            // hash returns, fixed up after the build).  Consecutive k-mers of a read are consecutive
-            // k-mers of the unitig, on one strand or the other, so k-mer t is looked for at side[g+t] and
-            // side[g-t]: a full 64-bit hash match there IS the table's answer for that hash.  Anything
-            // not matched (sequencing errors, unitig ends, anchor missing) is queued per warp and probed
-            // later DENSELY (every lane busy), so the result is exactly what per-k-mer
-            // probing gives.  Neighbouring threads share side lines.
-            // No cross-trip pipeline here: ptxas serialises it anyway (it waits for the probe at the top
-            // of the next trip) and the state it carries costs registers that the
-            // 24-warps-per-SM build does not have.  Latency is hidden by the other resident warps.
-            bool p_active = false;
-            int p_sg = 0, p_i = 0, p_nv = 0;
-            uint64_t p_h[4] = {0, 0, 0, 0};
-            uint32_t p_b0 = 0;
-            bool p_fl = false;  // orientation bit of the anchor as the read has it
-            Entry p_e0, p_e1;
-
-            auto resolve = [&]() {
-                uint32_t ids[4] = {SGC_MISS, SGC_MISS, SGC_MISS, SGC_MISS};
-                unsigned pending = 0;
-                if (p_active) {
-                    uint32_t v = SGC_MISS, aux = AUX_NONE;
-                    if (!bucket_match(p_e0, p_e1, p_h[0], v, aux)) {
-                        v = SGC_MISS;
-                        aux = AUX_NONE;
-                        if (bucket_overflowed(p_e0)) v = lookup_slow(a.tbl, a.nlines, p_b0, p_h[0], aux);
-                    }
-                    ids[0] = v;
-                    pending = ((1u << p_nv) - 1u) & ~1u;  // k-mers 1..nv-1 until proven otherwise
-                    const uint32_t g = aux & AUX_MASK;
-                    if (g != AUX_NONE) {
-                        // same orientation bit as the stored k-mer: the read runs along the unitig (g+1, g+2,
-                        // g+3), else against it (g-1, ...).  A wrong guess (palindromes, repeats, colliding
-                        // hashes) only means the k-mers are not matched here and take the queue.
-                        const bool along = ((aux & ORI_BIT) != 0) == p_fl;
-                        uint4 nb[3];
-#pragma unroll
-                        for (int d = 1; d < 4; d++) {
-                            const bool ok = d < p_nv && (along ? (unsigned long long)g + d < a.side_n : g >= (uint32_t)d);
-                            const long long pos = along ? (long long)g + d : (long long)g - d;
-                            nb[d - 1] = ok ? __ldg(a.side + pos) : make_uint4(0, 0, SGC_MISS, 1);
-                        }
-#pragma unroll
-                        for (int d = 1; d < 4; d++) {
-                            if (d < p_nv) {
-                                const uint32_t lo = (uint32_t)p_h[d], hi = (uint32_t)(p_h[d] >> 32);
-                                if (nb[d - 1].x == lo && nb[d - 1].y == hi && nb[d - 1].w == 0) {
-                                    ids[d] = nb[d - 1].z;
-                                    pending &= ~(1u << d);
-                                }
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int t = 0; t < 4; t++)
-                        if (t < p_nv && !((pending >> t) & 1u)) { if (ids[t] != SGC_MISS) my_hits++; else my_miss++; }
-                }
-                // queue the unresolved k-mers of this warp iteration (at most 96; room was made before)
-                {
-                    const unsigned np = __popc(pending);
-                    unsigned incl = np;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
-                        if (lane >= d) incl += v;
-                    }
-                    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-                    if (total) {
-                        unsigned pos = q_fill + incl - np;
-                        const uint32_t sq = pending ? (uint32_t)wt.seq[p_sg] : 0u;
-#pragma unroll
-                        for (int d = 1; d < 4; d++) {
-                            if ((pending >> d) & 1u) {
-                                qh[pos] = p_h[d];
-                                qs[pos] = sq;
-                                pos++;
-                            }
-                        }
-                        q_fill += total;
-                    }
-                }
-                emit_candidates(ids, p_active, p_sg, p_i, p_nv);  // queued k-mers count as "no id" here
-            };
-
-            const bool last_round = (int64_t)rq0 >= nrounds;  // the warp's last round also empties the queue
-            const int G1 = (G > 0 || !(last_round && q_fill)) ? G : 32;
-            for (int g0 = 0; g0 < G1; g0 += 32) {
-                const int g = g0 + lane;
-                p_active = g < G;
-                p_sg = 0; p_i = 0; p_nv = 0;
-#pragma unroll
-                for (int t = 0; t < 4; t++) p_h[t] = 0;
-                unsigned ori = 0;
-                if (p_active) locate_and_hash(g, p_sg, p_i, p_nv, p_h, ori);
-                p_fl = (ori & 1u) != 0;
-                p_b0 = p_active ? home_bucket(p_h[0], a.nbuckets, a.home_shift) : 0u;
-                load_bucket_nc(a.tbl + p_b0, p_e0, p_e1);  // idle lanes probe bucket 0 (an L2 hit)
-                resolve();
-                if (q_fill > QCAP - 96 || (last_round && g0 + 32 >= G && q_fill)) drain_queue();
-            }
-            __syncwarp();
         } else {
             // MODE_LOOKUP / MODE_LABEL: every k-mer of a group probes its home bucket (4 loads in flight per
             // thread), resolved right away; the latency is covered by the other resident warps.
@@ -765,7 +607,7 @@ __global__ void __launch_bounds__(NT, MODE == MODE_LABEL_SIDE ? SGC_SIDE_MIN_CTA
                 }
             };
 
-            // no cross-trip pipeline (see MODE_LABEL_SIDE): hash, probe, resolve inside one trip
+            // no cross-trip pipeline (ptxas serialises it anyway): hash, probe, resolve inside one trip
             for (int g0 = 0; g0 < G; g0 += 32) {
                 const int g = g0 + lane;
                 p_active = g < G;
@@ -791,10 +633,10 @@ __global__ void __launch_bounds__(NT, MODE == MODE_LABEL_SIDE ? SGC_SIDE_MIN_CTA
     }
     cp_async_wait_all();  // copies launched for rounds past the end (none carry data) must not outlive the CTA
 
-    if constexpr (MODE == MODE_LABEL || MODE == MODE_GATHER || MODE == MODE_LABEL_SIDE) {
+    if constexpr (MODE == MODE_LABEL || MODE == MODE_GATHER) {
         if (pair_fill) flush_pairs();
     }
-    if constexpr (MODE == MODE_LOOKUP || MODE == MODE_LABEL || MODE == MODE_GATHER || MODE == MODE_LABEL_SIDE) {
+    if constexpr (MODE == MODE_LOOKUP || MODE == MODE_LABEL || MODE == MODE_GATHER) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             my_hits += __shfl_xor_sync(0xffffffffu, my_hits, d);

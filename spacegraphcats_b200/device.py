@@ -31,6 +31,25 @@ def pack_sequences(seqs):
     return buf, off
 
 
+def pack_reads_host(buf, off, n_threads=0):
+    """ASCII (uint8 concatenation, int64 offsets) -> 2-bit packed records for ``label_reads_packed``
+    (sgc_pack_reads).  -> (packed uint8[...], lengths int32[n], bad bool[n]); ``bad`` marks records
+    holding a byte other than A/C/G/T (packed as A; the caller applies the reference's policy)."""
+    L = _lib.lib()
+    buf = np.ascontiguousarray(buf, np.uint8)
+    off = np.ascontiguousarray(off, np.int64)
+    n = len(off) - 1
+    lens = np.diff(off)
+    cap = int(((lens + 63) // 64).sum()) * 16
+    packed = np.empty(max(cap, 16), np.uint8)
+    h_len = np.zeros(max(n, 1), np.int32)
+    bad = np.zeros(max(n, 1), np.uint8)
+    nb = ctypes.c_int64(0)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    check(L.sgc_pack_reads(vp(buf), vp(off), n, int(n_threads), vp(packed), cap, vp(h_len), vp(bad), ctypes.byref(nb)))
+    return packed[: nb.value], h_len[:n], bad[:n].astype(bool)
+
+
 def kmer_counts(off, ksize):
     """per-sequence k-mer counts max(0, L-k+1) from offsets (host)."""
     return np.maximum(np.diff(np.asarray(off, np.int64)) - int(ksize) + 1, 0)
@@ -135,6 +154,22 @@ class Context:
             self.to_host(d_stat) if d_stat is not None else None,
         )
 
+    def pack_reads(self, seq, off):
+        """ASCII reads on the device (or host arrays, uploaded) -> 2-bit packed records on the device.
+        -> (packed uint8 tensor, lengths int32 tensor, status int32 tensor)"""
+        torch = _torch()
+        d_seq = self.to_device(seq, np.uint8)
+        d_off = self.to_device(off, np.int64)
+        nseq = d_off.numel() - 1
+        cap = (d_seq.numel() // 4 + 16 * nseq + 16 + 15) // 16 * 16  # every record rounds up to 16 bytes
+        d_packed = self.empty(cap, torch.uint8)
+        d_len = self.empty(max(nseq, 1), torch.int32)
+        d_stat = self.empty(max(nseq, 1), torch.int32)
+        nb = ctypes.c_int64(0)
+        check(self._L.sgc_pack_reads_device(self._h, self.ptr(d_seq), d_seq.numel(), self.ptr(d_off), nseq,
+                                            self.ptr(d_packed), cap, self.ptr(d_len), self.ptr(d_stat), ctypes.byref(nb)))
+        return d_packed[: nb.value], d_len[:nseq], d_stat[:nseq]
+
     # ---- K6 --------------------------------------------------------------
     def count_doms(self, d_count_by_id, member_off, member, level_nodes, level_off, n_nodes):
         torch = _torch()
@@ -202,7 +237,7 @@ class DeviceTable:
         check(self._L.sgc_table_insert_pairs(self._h, c.ptr(d_h), c.ptr(d_v), d_h.numel()))
 
     def enable_side(self):
-        """Allocate the unitig-ordered side array (16 B per k-mer); must precede insert_sequences."""
+        """Allocate the unitig-ordered side array (8 B + 1 bit per k-mer); must precede insert_sequences."""
         check(self._L.sgc_table_enable_side(self._h))
 
     @property
@@ -309,14 +344,21 @@ class DeviceTable:
         return out
 
     # ---- K4 --------------------------------------------------------------
-    def label_reads(self, seq, off, ksize, ids_cap=None, to_host=True):
+    def label_reads(self, seq, off, ksize, ids_cap=None, to_host=True, packed=False):
         """index_reads' per-read step: distinct unitig ids per sequence as CSR.
-        -> dict(ids_off i64[nseq+1], ids u32[n_labels], status, n_kmers, n_hits)"""
+        -> dict(ids_off i64[nseq+1], ids u32[n_labels], status, n_kmers, n_hits)
+        ``packed=True`` first packs the reads 2 bits per base on the device and labels the packed
+        records (the path the streaming feeder uses; same labels)."""
         torch = _torch()
         c = self.ctx
         d_seq = c.to_device(seq, np.uint8)
         d_off = c.to_device(off, np.int64)
         nseq = d_off.numel() - 1
+        if packed:
+            d_packed, d_len, d_stat = c.pack_reads(d_seq, d_off)
+            out = self.label_reads_packed(d_packed, nseq, ksize, lengths=d_len, ids_cap=ids_cap, to_host=to_host)
+            out["status"] = c.to_host(d_stat) if to_host else d_stat
+            return out
         nbytes = d_seq.numel()
         cap = int(ids_cap) if ids_cap is not None else max(4 * nseq, 1024)
         d_stat = c.empty(nseq, torch.int32)
@@ -343,6 +385,212 @@ class DeviceTable:
         else:
             out.update(ids_off=d_ioff, ids=d_ids, status=d_stat)
         return out
+
+    def label_reads_packed(self, packed, nseq, ksize, lengths=None, uniform_len=-1, ids_cap=None, to_host=True):
+        """The same step on 2-bit packed records (``pack_reads_host`` / ``Context.pack_reads`` layout).
+        ``lengths``: int32 per record, or None with ``uniform_len`` when all records have that many bases."""
+        torch = _torch()
+        c = self.ctx
+        d_packed = c.to_device(packed, np.uint8)
+        d_len = c.to_device(lengths, np.int32) if lengths is not None else None
+        nseq = int(nseq)
+        cap = int(ids_cap) if ids_cap is not None else max(4 * nseq, 1024)
+        d_ioff = c.empty(nseq + 1, torch.int64)
+        for _ in range(8):
+            d_ids = c.empty(cap, torch.int32)
+            nk, nh, nl = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+            try:
+                check(
+                    self._L.sgc_label_reads_packed(
+                        self._h, c.ptr(d_packed), d_packed.numel(), c.ptr(d_len) if d_len is not None else None,
+                        int(uniform_len), nseq, int(ksize), c.ptr(d_ioff), c.ptr(d_ids), cap,
+                        ctypes.byref(nk), ctypes.byref(nh), ctypes.byref(nl),
+                    )
+                )
+                break
+            except SgcCapacityError:
+                cap = max(2 * cap, int(nl.value) + 1024)
+        else:
+            raise RuntimeError("label_reads_packed: could not size the label buffer")
+        d_ids = d_ids[: nl.value]
+        out = {"n_kmers": nk.value, "n_hits": nh.value, "n_labels": nl.value}
+        if to_host:
+            out.update(ids_off=c.to_host(d_ioff), ids=c.to_host(d_ids, np.uint32))
+        else:
+            out.update(ids_off=d_ioff, ids=d_ids)
+        return out
+
+    # ---- K4, streaming ------------------------------------------------------
+    def label_stream(self, batches, ksize, ids_per_read=6, prefetch=True):
+        """Label a stream of HOST batches with the uploads, the kernels and the downloads of consecutive
+        batches overlapped (the loop of cdbg/index_reads.py:105-167 with the per-read arithmetic on the GPU):
+        while the kernels of batch i run, batch i+1 is copied to the device on a copy stream and the labels
+        of batch i-1 return to pinned host memory on a third stream.  Memory is bounded by two batches.
+
+        ``batches`` yields dicts, either ``{"packed": uint8, "nseq": n, "lengths": int32 or None,
+        "uniform_len": L}`` (2-bit packed records, :func:`pack_reads_host` layout; the fast path) or
+        ``{"seq": uint8, "off": int64}`` (ASCII).  Arrays may be numpy arrays or torch CPU tensors; pinned
+        tensors are copied asynchronously.  Extra keys are passed through.
+        Yields ``(batch, result)`` in order, ``result = dict(ids_off, ids, n_kmers, n_hits, n_labels[,
+        status])`` with numpy views of pinned buffers that stay valid until the NEXT-BUT-ONE batch is
+        yielded (copy what must live longer).  With ``prefetch`` the batches are pulled from the iterable on
+        a helper thread, so the host-side preparation of batch i+1 (inflate, scan, pack: native code that
+        releases the GIL) overlaps the GPU work of batch i."""
+        torch = _torch()
+        c = self.ctx
+        L = self._L
+        if getattr(self, "_stream_state", None) is None:
+            self._stream_state = ([_StreamSlot(), _StreamSlot()], torch.cuda.Stream(device=c.device),
+                                  torch.cuda.Stream(device=c.device))
+        slots, copy_stream, back_stream = self._stream_state
+        for s in slots:
+            s.copied, s.returned = torch.cuda.Event(), torch.cuda.Event()
+            s.returned.record(back_stream)
+
+        def as_tensor(a, dtype):
+            if isinstance(a, torch.Tensor):
+                return a
+            a = np.ascontiguousarray(a)
+            if a.dtype == np.uint32:
+                a = a.view(np.int32)
+            t = torch.from_numpy(a)
+            assert t.dtype == dtype, (t.dtype, dtype)
+            return t
+
+        def upload(slot, b):
+            with torch.cuda.stream(copy_stream):
+                if "packed" in b:
+                    hp = as_tensor(b["packed"], torch.uint8)
+                    slot.dev(c, "packed", hp.numel(), torch.uint8)[: hp.numel()].copy_(hp, non_blocking=True)
+                    if b.get("lengths") is not None:
+                        hl = as_tensor(b["lengths"], torch.int32)
+                        slot.dev(c, "len", hl.numel(), torch.int32)[: hl.numel()].copy_(hl, non_blocking=True)
+                else:
+                    hs, ho = as_tensor(b["seq"], torch.uint8), as_tensor(b["off"], torch.int64)
+                    slot.dev(c, "seq", hs.numel(), torch.uint8)[: hs.numel()].copy_(hs, non_blocking=True)
+                    slot.dev(c, "off", ho.numel(), torch.int64)[: ho.numel()].copy_(ho, non_blocking=True)
+                slot.copied.record(copy_stream)
+
+        def nseq_of(b):
+            return int(b["nseq"]) if "packed" in b else int(len(b["off"]) - 1)
+
+        def launch(slot, b, cap):
+            n = nseq_of(b)
+            d_ioff = slot.dev(c, "ids_off", n + 1, torch.int64)
+            d_ids = slot.dev(c, "ids", cap, torch.int32)
+            if "packed" in b:
+                nb = int(b["packed"].numel() if isinstance(b["packed"], torch.Tensor) else len(b["packed"]))
+                d_len = slot.d_in["len"] if b.get("lengths") is not None else None
+                check(L.sgc_label_reads_packed_launch(self._h, c.ptr(slot.d_in["packed"]), nb,
+                                                      c.ptr(d_len) if d_len is not None else None,
+                                                      int(b.get("uniform_len", -1)), n, int(ksize), c.ptr(d_ioff),
+                                                      c.ptr(d_ids), d_ids.numel()))
+            else:
+                nb = int(b["seq"].numel() if isinstance(b["seq"], torch.Tensor) else len(b["seq"]))
+                d_stat = slot.dev(c, "status", max(n, 1), torch.int32)
+                check(L.sgc_label_reads_launch(self._h, c.ptr(slot.d_in["seq"]), nb, c.ptr(slot.d_in["off"]), n,
+                                               int(ksize), c.ptr(d_ioff), c.ptr(d_ids), d_ids.numel(), c.ptr(d_stat)))
+
+        def finish(slot, b):
+            nk, nh, nl = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+            try:
+                check(L.sgc_label_reads_finish(self._h, ctypes.byref(nk), ctypes.byref(nh), ctypes.byref(nl)))
+            except SgcCapacityError:  # more labels than the output holds: size it for the real count and redo
+                launch(slot, b, int(nl.value) + 1024)
+                check(L.sgc_label_reads_finish(self._h, ctypes.byref(nk), ctypes.byref(nh), ctypes.byref(nl)))
+            return nk.value, nh.value, nl.value
+
+        def download(slot, b, stats):
+            n, nl = nseq_of(b), stats[2]
+            done = torch.cuda.Event()
+            done.record(c.stream)
+            h_ioff = slot.host(torch, "ids_off", n + 1, torch.int64)
+            h_ids = slot.host(torch, "ids", max(nl, 1), torch.int32)
+            h_stat = slot.host(torch, "status", max(n, 1), torch.int32) if "packed" not in b else None
+            with torch.cuda.stream(back_stream):
+                back_stream.wait_event(done)
+                h_ioff[: n + 1].copy_(slot.d_in["ids_off"][: n + 1], non_blocking=True)
+                if nl:
+                    h_ids[:nl].copy_(slot.d_in["ids"][:nl], non_blocking=True)
+                if h_stat is not None and n:
+                    h_stat[:n].copy_(slot.d_in["status"][:n], non_blocking=True)
+                slot.returned.record(back_stream)
+            res = {"n_kmers": stats[0], "n_hits": stats[1], "n_labels": nl,
+                   "ids_off": h_ioff[: n + 1].numpy(), "ids": h_ids[:nl].numpy().view(np.uint32)}
+            if h_stat is not None:
+                res["status"] = h_stat[:n].numpy()
+            return res
+
+        it = _prefetch_iter(batches) if prefetch else iter(batches)
+        cur = next(it, None)
+        if cur is None:
+            return
+        upload(slots[0], cur)
+        prev, idx = None, 0
+        while cur is not None:
+            slot = slots[idx % 2]
+            c.stream.wait_event(slot.copied)
+            c.stream.wait_event(slot.returned)  # the labels of batch idx-2 have left this slot's output buffers
+            launch(slot, cur, max(int(ids_per_read * nseq_of(cur)), 1024))
+            nxt = next(it, None)
+            if nxt is not None:
+                upload(slots[(idx + 1) % 2], nxt)  # that slot's kernels (batch idx-1) have finished: finish() synchronised
+            if prev is not None:
+                prev[0].returned.synchronize()
+                yield prev[1], prev[2]  # the consumer works on batch idx-1 while the GPU labels batch idx
+            stats = finish(slot, cur)
+            prev = (slot, cur, download(slot, cur, stats))
+            cur, idx = nxt, idx + 1
+        prev[0].returned.synchronize()
+        yield prev[1], prev[2]
+
+
+def _prefetch_iter(iterable, depth=2):
+    """Pull items from ``iterable`` on a helper thread, ``depth`` ahead (the producer's native calls release the GIL)."""
+    import queue
+    import threading
+
+    q = queue.Queue(maxsize=depth)
+    end = object()
+
+    def run():
+        try:
+            for x in iterable:
+                q.put(x)
+            q.put(end)
+        except BaseException as e:  # noqa: BLE001  (re-raised in the consumer)
+            q.put(e)
+
+    threading.Thread(target=run, daemon=True).start()
+    while True:
+        x = q.get()
+        if x is end:
+            return
+        if isinstance(x, BaseException):
+            raise x
+        yield x
+
+
+class _StreamSlot:
+    """Device input/output buffers of one in-flight batch of :meth:`DeviceTable.label_stream`."""
+
+    def __init__(self):
+        self.d_in = {}      # name -> CUDA tensor (grown on demand)
+        self.h_out = {}     # name -> pinned host tensor
+        self.copied = None  # H2D of this slot's inputs has finished
+        self.returned = None  # D2H of this slot's previous outputs has finished
+
+    def dev(self, ctx, name, n, dtype):
+        t = self.d_in.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = self.d_in[name] = ctx.empty(max(int(n * 1.25) + 16, 16), dtype)
+        return t
+
+    def host(self, torch, name, n, dtype):
+        t = self.h_out.get(name)
+        if t is None or t.numel() < n:
+            t = self.h_out[name] = torch.empty(max(int(n * 1.25) + 16, 16), dtype=dtype).pin_memory()
+        return t
 
 
 class DeviceMphf:
@@ -424,4 +672,4 @@ class DeviceMphf:
         return buf.raw
 
 
-__all__ = ["Context", "DeviceTable", "DeviceMphf", "get_context", "pack_sequences", "kmer_counts", "SGC_MISS"]
+__all__ = ["Context", "DeviceTable", "DeviceMphf", "get_context", "pack_sequences", "pack_reads_host", "kmer_counts", "SGC_MISS"]

@@ -296,6 +296,15 @@ class PartitionedIndex:
         self.table = None
         self.n_local = 0
 
+    def close(self):
+        """Unmap / free the peer buffers (collective: every rank must call it) and the local table."""
+        for pb in ([self._peers] if self._peers is not None else []) + list(self._peers2 or ()):
+            pb.close()
+        self._peers, self._peers2 = None, None
+        if self.table is not None and hasattr(self.table, "close"):
+            self.table.close()
+        self.table = None
+
     def build(self, seq, off, ksize, ids):
         """Every rank passes ITS shard of the unitigs (ids are global cDBG ids)."""
         e = self.engine

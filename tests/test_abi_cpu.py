@@ -314,3 +314,33 @@ def test_bgzf_reader_on_python_written_blocks(tmp_path):
         write_bgzf(p, noise, level=level)
         assert bgzf.is_bgzf(p) and gzip.open(p, "rb").read() == noise
         assert bgzf.BgzfData(p).data.tobytes() == noise
+
+
+def test_host_packer_layout_and_bad_base_flags():
+    """sgc_pack_reads: 2 bits per base, A=0 C=1 G=2 T=3, records padded to 16 bytes; non-ACGT flagged."""
+    from spacegraphcats_b200.device import pack_reads_host, pack_sequences
+
+    rng = np.random.default_rng(4)
+    seqs = ["", "A", "ACGT" * 16, "ACGT" * 16 + "T", "ACGNT", "acgt"] + [
+        "".join("ACGT"[c] for c in rng.integers(0, 4, int(n))) for n in rng.integers(0, 400, 200)
+    ]
+    buf, off = pack_sequences(seqs)
+    for threads in (1, 3):
+        pk, ln, bad = pack_reads_host(buf, off, n_threads=threads)
+        assert ln.tolist() == [len(s) for s in seqs]
+        assert bad.tolist() == [any(c not in "ACGT" for c in s) for s in seqs]
+        pos = 0
+        for s in seqs:
+            nb = (len(s) + 63) // 64 * 16
+            rec = pk[pos:pos + nb]
+            pos += nb
+            dec = "".join("ACGT"[(int(rec[b // 4]) >> (2 * (b % 4))) & 3] for b in range(len(s)))
+            assert dec == "".join(c if c in "ACGT" else "A" for c in s)
+            assert not rec[(len(s) + 3) // 4:].any()  # padding is zero
+        assert pos == len(pk)
+    from spacegraphcats_b200._lib import lib
+
+    L = lib()
+    assert L.sgc_packed_bytes(None, 150, 10) == 10 * 48
+    lens = np.array([0, 1, 64, 65], np.int32)
+    assert L.sgc_packed_bytes(lens.ctypes.data_as(ctypes.c_void_p), -1, 4) == (0 + 1 + 1 + 2) * 16

@@ -306,6 +306,11 @@ def test_label_reads_dory_vs_oracle(ctx, O, dory, dory_index, dory_reads):
     res3 = sided.label_reads(buf, off, 21)
     assert np.array_equal(res3["ids_off"], o_off) and np.array_equal(res3["ids"], o_ids)
     assert (res3["n_kmers"], res3["n_hits"]) == (o_nk, o_nh)
+    # 2-bit packed input (what the streaming feeder uploads): same labels from both kinds of table
+    for t in (sided, plain):
+        res4 = t.label_reads(buf, off, 21, packed=True)
+        assert np.array_equal(res4["ids_off"], o_off) and np.array_equal(res4["ids"], o_ids)
+        assert (res4["n_kmers"], res4["n_hits"]) == (o_nk, o_nh) and not res4["status"].any()
 
 
 def test_label_reads_synthetic_with_errors_vs_oracle(ctx, O):
@@ -349,6 +354,24 @@ def test_label_reads_synthetic_with_errors_vs_oracle(ctx, O):
     res_p = table_plain.label_reads(buf, off, k)  # per-k-mer probing kernel (no side array)
     assert np.array_equal(res_p["ids_off"], o_off) and np.array_equal(res_p["ids"], o_ids)
     assert (res_p["n_kmers"], res_p["n_hits"]) == (o_nk, o_nh)
+    # 2-bit packed input: host packer == device packer, and the same labels
+    from spacegraphcats_b200.device import pack_reads_host
+
+    pk, ln, bad = pack_reads_host(buf, off)
+    d_pk, d_ln, d_st = ctx.pack_reads(buf, off)
+    assert np.array_equal(ctx.to_host(d_pk), pk) and np.array_equal(ctx.to_host(d_ln), ln) and not bad.any()
+    assert not ctx.to_host(d_st).any()
+    res_k = table._dev.label_reads_packed(pk, len(reads), k, lengths=ln)
+    assert np.array_equal(res_k["ids_off"], o_off) and np.array_equal(res_k["ids"], o_ids)
+    assert (res_k["n_kmers"], res_k["n_hits"]) == (o_nk, o_nh)
+    # uniform-length batch without a length array
+    uni = [r for r in reads if len(r) == 150]
+    ub, uo = pack_sequences(uni)
+    upk, _, _ = pack_reads_host(ub, uo)
+    res_u = table._dev.label_reads_packed(upk, len(uni), k, uniform_len=150)
+    u_off, u_ids, u_nk, u_nh = ot.label_reads(ub, uo, k)
+    assert np.array_equal(res_u["ids_off"], u_off) and np.array_equal(res_u["ids"], u_ids)
+    assert (res_u["n_kmers"], res_u["n_hits"]) == (u_nk, u_nh)
     # the same through per-k-mer ids (count_dominator_abundance shape) and the K4 tail alone
     lk = table.lookup_sequences(buf, off, k, n_ids=len(useqs))
     oh2, ooff2 = O.hash_batch(buf, off, k)
@@ -356,6 +379,56 @@ def test_label_reads_synthetic_with_errors_vs_oracle(ctx, O):
     assert np.array_equal(lk["kmer_off"], ooff2) and np.array_equal(lk["kmer_ids"], want_ids)
     cnt, miss = ot.count_matches(oh2, len(useqs))
     assert np.array_equal(lk["count_by_id"], cnt) and lk["n_kmers"] - lk["n_hits"] == miss
+
+
+def test_label_stream_matches_one_shot_labelling(ctx, O):
+    """The pipelined host-batch API (pinned double buffers, packed or ASCII input) returns, batch by batch,
+    exactly what one-shot label_reads returns; an undersized label buffer is re-sized and redone."""
+    import torch
+
+    from spacegraphcats_b200.cdbg.hashing import GpuKmerTable
+    from spacegraphcats_b200.device import pack_reads_host, pack_sequences
+
+    rng = np.random.default_rng(5)
+    k = 31
+    lut = np.frombuffer(b"ACGT", np.uint8)
+    g = lut[rng.integers(0, 4, 200_000)]
+    cuts = np.concatenate([[0], np.cumsum(rng.integers(1, 150, 4000))])
+    cuts = cuts[cuts < len(g) - k]
+    ubuf, uoff = pack_sequences([g[a : b + k - 1].tobytes() for a, b in zip(cuts[:-1], cuts[1:])])
+    table = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx)
+    batches, want = [], []
+    for b in range(5):
+        n = int(rng.integers(1, 3000))
+        reads = []
+        for i in range(n):
+            ln = 150 if b % 2 == 0 else int(rng.integers(0, 300))
+            p = int(rng.integers(0, len(g) - 300))
+            r = g[p : p + ln].copy()
+            err = rng.random(ln) < 0.01
+            r[err] = lut[rng.integers(0, 4, int(err.sum()))]
+            reads.append(r.tobytes())
+        buf, off = pack_sequences(reads)
+        want.append(table.label_reads(buf, off, k))
+        if b == 3:  # ASCII batch, pageable numpy
+            batches.append({"seq": buf, "off": off, "tag": b})
+        else:
+            pk, ln, bad = pack_reads_host(buf, off)
+            assert not bad.any()
+            hp = torch.from_numpy(pk.copy()).pin_memory() if b != 1 else pk
+            if b % 2 == 0:
+                batches.append({"packed": hp, "nseq": n, "lengths": None, "uniform_len": 150, "tag": b})
+            else:
+                batches.append({"packed": hp, "nseq": n, "lengths": ln, "tag": b})
+    for kw in ({}, {"ids_per_read": 0.01}, {"prefetch": False}):
+        got = []
+        for batch, res in table.label_reads_stream(iter(batches), k, **kw):
+            got.append((batch["tag"], res["ids_off"].copy(), res["ids"].copy(), res["n_kmers"], res["n_hits"]))
+        assert [t for t, *_ in got] == [0, 1, 2, 3, 4]
+        for (_, ioff, ids, nk, nh), w in zip(got, want):
+            assert np.array_equal(ioff, w["ids_off"]) and np.array_equal(ids, w["ids"])
+            assert (nk, nh) == (w["n_kmers"], w["n_hits"])
+    assert list(table.label_reads_stream(iter([]), k)) == []
 
 
 def test_label_reads_many_ids_per_read_overflows_staging(ctx, O):
@@ -376,9 +449,10 @@ def test_label_reads_many_ids_per_read_overflows_staging(ctx, O):
     o_off, o_ids, _, _ = ot.label_reads(buf, off, k)
     for side in (False, True):
         table = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx, side=side)
-        res = table.label_reads(buf, off, k)
-        assert np.array_equal(res["ids_off"], o_off) and np.array_equal(res["ids"], o_ids), side
-        assert res["n_labels"] > 100_000
+        for packed in (False, True):
+            res = table.label_reads(buf, off, k, packed=packed)
+            assert np.array_equal(res["ids_off"], o_off) and np.array_equal(res["ids"], o_ids), (side, packed)
+            assert res["n_labels"] > 100_000
 
 
 # ---------------------------------------------------------------- K5/K6: queries
@@ -945,6 +1019,9 @@ def test_hypothesis_hash_and_label_vs_oracle(ctx, O):
         o_off, o_ids, o_nk, o_nh = O.COracleTable(oh, ov).label_reads(cbuf, coff, k)
         assert (lab["n_kmers"], lab["n_hits"]) == (o_nk, o_nh)
         assert np.array_equal(lab["ids_off"], o_off) and np.array_equal(lab["ids"], o_ids)
+        labp = table.label_reads(cbuf, coff, k, packed=True)
+        assert (labp["n_kmers"], labp["n_hits"]) == (o_nk, o_nh)
+        assert np.array_equal(labp["ids_off"], o_off) and np.array_equal(labp["ids"], o_ids)
 
     run()
 
@@ -1083,7 +1160,7 @@ def test_label_tail_small_runs_and_sorted_fallback(ctx, O, monkeypatch):
     ot = O.COracleTable(otab.mphf_to_hash, otab.mphf_to_value)
     short = [g[p : p + 100].tobytes() for p in rng.integers(0, len(g) - 6000, 3000)]       # <= ~6 ids each
     longs = [g[p : p + 5000].tobytes() for p in rng.integers(0, len(g) - 6000, 5)]         # hundreds of ids each
-    edge = [g[p : p + 24 * 20].tobytes() for p in rng.integers(0, len(g) - 6000, 50)]      # around the 24-id limit
+    edge = [g[p : p + 160 * 20].tobytes() for p in rng.integers(0, len(g) - 6000, 50)]     # around the 160-id limit
     for side in (True, False):
         table = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx, side=side)
         for batch in (short, short[:500] + longs + short[500:1000], edge + short[:100], longs):
