@@ -260,6 +260,28 @@ int sgc_partition_hashes_p2p(sgc_ctx* ctx, const uint8_t* d_seq, int64_t seq_byt
 int sgc_lookup_regions_p2p(sgc_table* t, const uint64_t* d_inbox, const int64_t* h_counts_from,
                            int64_t region_cap, int n_ranks, int my_rank, uint32_t* const* h_peer_replies,
                            int ctas_per_sm /* 0 = fill the GPU; 1..7 = leave room for a concurrent kernel */);
+/*
+ * The whole labelling step against the partitioned table as ONE call with no host round trip between its
+ * kernels: the ranks synchronise through flags in peer memory (NVLink) instead of count exchanges and barriers.
+ *   request kernel : hash + store every hash into its owner's inbox; its last warp writes this rank's
+ *                    per-owner counts and the step's epoch into the owners' mailboxes
+ *   serve kernel   : per source region, waits for that rank's stamp, probes, stores every id straight into the
+ *                    requester's reply buffer; its last CTA stamps the requesters' reply buffers
+ *   gather kernel  : waits for every owner's stamp, replies -> per-read labels (outputs like sgc_label_reads)
+ * h_peer_*[r] = rank r's buffer mapped into this process (CUDA IPC; [my_rank] = the local one): inbox
+ * (n_ranks x region_cap hashes), replies (n_ranks x region_cap ids), mail_count (n_ranks uint64), mail_stamp
+ * and reply_stamp (n_ranks uint32, zero-initialised).  epoch = 1, 2, ... identical on every rank.  Waits are
+ * bounded (~4 s): a missing peer ends in SGC_ERR_CUDA, never in a hung GPU.  *h_flags (nullable): bit 2 = a
+ * region overflowed region_cap (SGC_ERR_CAPACITY), bit 3 = time-out; the caller makes the retry collective.
+ */
+int sgc_label_reads_partitioned(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off,
+                                int64_t nseq, int k, int n_ranks, int my_rank, uint32_t epoch,
+                                uint64_t* const* h_peer_inboxes, uint32_t* const* h_peer_replies,
+                                uint64_t* const* h_peer_mail_count, uint32_t* const* h_peer_mail_stamp,
+                                uint32_t* const* h_peer_reply_stamp, int64_t region_cap, uint32_t* d_ridx,
+                                int64_t ridx_cap, int64_t* d_ids_off, uint32_t* d_ids_out, int64_t ids_cap,
+                                int32_t* d_status, int64_t* h_n_kmers, int64_t* h_n_hits, int64_t* h_n_labels,
+                                int32_t* h_flags);
 int sgc_peer_alloc(sgc_ctx* ctx, int64_t bytes, void** d_ptr, uint8_t* h_handle64);
 int sgc_peer_open(sgc_ctx* ctx, const uint8_t* h_handle64, void** d_ptr);
 int sgc_peer_close(sgc_ctx* ctx, void* d_ptr);

@@ -74,6 +74,8 @@ PROTOTYPES = {
     "sgc_partition_hashes": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _pi64]),
     "sgc_partition_hashes_p2p": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _pi64]),
     "sgc_lookup_regions_p2p": (_i32, [_vp, _vp, _pi64, _i64, _i32, _i32, _vp, _i32]),
+    "sgc_label_reads_partitioned": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _u32, _vp, _vp, _vp, _vp, _vp, _i64,
+                                            _vp, _i64, _vp, _vp, _i64, _vp, _pi64, _pi64, _pi64, ctypes.POINTER(ctypes.c_int32)]),
     "sgc_peer_alloc": (_i32, [_vp, _i64, ctypes.POINTER(_vp), _vp]),
     "sgc_peer_open": (_i32, [_vp, _vp, ctypes.POINTER(_vp)]),
     "sgc_peer_close": (_i32, [_vp, _vp]),

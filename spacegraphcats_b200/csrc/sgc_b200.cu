@@ -1250,11 +1250,10 @@ static int partition_hashes_impl(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_b
     CU(cudaMemcpyAsync(counts, c->cursor.p, 32 * 8, cudaMemcpyDeviceToHost, c->stream));
     TRY(fetch_scalars(c));
     TRY(bad_offsets_check(c));
-    for (int r = 0; r < n_ranks; r++) {
-        h_counts[r] = (int64_t)counts[r];
+    for (int r = 0; r < n_ranks; r++) h_counts[r] = (int64_t)counts[r];  // every owner, so that a retry can size for the maximum
+    for (int r = 0; r < n_ranks; r++)
         if ((int64_t)counts[r] > send_cap)
             return fail(SGC_ERR_CAPACITY, "send_cap %lld < %llu hashes for owner %d", (long long)send_cap, counts[r], r);
-    }
     return SGC_OK;
 }
 
@@ -1306,6 +1305,7 @@ int sgc_peer_alloc(sgc_ctx* c, int64_t bytes, void** d_ptr, uint8_t* h_handle64)
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaError_t e = cudaMalloc(d_ptr, (size_t)bytes);
     if (e != cudaSuccess) return fail(SGC_ERR_NOMEM, "cudaMalloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e));
+    CU(cudaMemset(*d_ptr, 0, (size_t)bytes));  // mailboxes must start at zero (epochs count from 1)
     cudaIpcMemHandle_t hnd;
     CU(cudaIpcGetMemHandle(&hnd, *d_ptr));
     memcpy(h_handle64, &hnd, 64);
@@ -1370,6 +1370,109 @@ int sgc_labels_from_replies(sgc_ctx* c, const int64_t* d_off, int64_t nseq, int6
     const unsigned long long n_pairs = c->h_scal->pair_count;
     if (h_n_hits) *h_n_hits = (int64_t)c->h_scal->n_hits;
     if (h_n_kmers) *h_n_kmers = (int64_t)(c->h_scal->n_hits + c->h_scal->n_miss);
+    if (n_pairs > pairs_cap) {
+        if (h_n_labels) *h_n_labels = (int64_t)n_pairs;
+        return fail(SGC_ERR_CAPACITY, "candidate buffer %llu < %llu", pairs_cap, n_pairs);
+    }
+    return pairs_to_csr(c, (int64_t)n_pairs, nseq, d_ids_off, d_ids_out, ids_cap, h_n_labels);
+}
+
+// One whole labelling step against the hash-range partitioned table with NO host round trip between its
+// kernels (flag protocol over NVLink peer memory): request kernel (hash + stores into the owners' inboxes,
+// then counts + epoch stamp into their mailboxes), serve kernel (waits per source region for the stamp, probes,
+// stores the ids into the requesters' reply buffers, stamps them), gather kernel (waits for every owner's
+// stamp, replies -> labels), label tail.  Every rank calls it with the same epoch (1, 2, ...).
+int sgc_label_reads_partitioned(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off, int64_t nseq,
+                                int k, int n_ranks, int my_rank, uint32_t epoch, uint64_t* const* h_peer_inboxes,
+                                uint32_t* const* h_peer_replies, uint64_t* const* h_peer_mail_count,
+                                uint32_t* const* h_peer_mail_stamp, uint32_t* const* h_peer_reply_stamp,
+                                int64_t region_cap, uint32_t* d_ridx, int64_t ridx_cap, int64_t* d_ids_off,
+                                uint32_t* d_ids_out, int64_t ids_cap, int32_t* d_status, int64_t* h_n_kmers,
+                                int64_t* h_n_hits, int64_t* h_n_labels, int32_t* h_flags) {
+    if (!t) return fail(SGC_ERR_ARG, "table is NULL");
+    sgc_ctx* c = t->ctx;
+    const int bits = log2_ranks(n_ranks);
+    if (bits < 0 || n_ranks > 32) return fail(SGC_ERR_ARG, "n_ranks must be a power of two <= 32 (got %d)", n_ranks);
+    if (my_rank < 0 || my_rank >= n_ranks || epoch == 0) return fail(SGC_ERR_ARG, "bad rank / epoch");
+    if (!h_peer_inboxes || !h_peer_replies || !h_peer_mail_count || !h_peer_mail_stamp || !h_peer_reply_stamp)
+        return fail(SGC_ERR_ARG, "NULL peer table");
+    TRY(check_seq_args(d_seq, seq_bytes, d_off, nseq, k));
+    if (region_cap <= 0 || region_cap >= ((int64_t)1 << (32 - bits))) return fail(SGC_ERR_ARG, "bad region_cap");
+    if (ridx_cap < seq_bytes) return fail(SGC_ERR_ARG, "ridx_cap must be >= seq_bytes (an upper bound of the k-mers)");
+    if (!d_ids_off || ids_cap < 0 || !d_ridx) return fail(SGC_ERR_ARG, "bad label buffers");
+    if (h_flags) *h_flags = 0;
+    TRY(set_device(c));
+    if (d_status) CU(cudaMemsetAsync(d_status, 0, (size_t)nseq * 4, c->stream));
+    Plan p;
+    TRY(make_plan(c, d_off, nseq, seq_bytes, k, nullptr, &p));
+    TRY(ensure(c, c->cursor, 32 * 8));
+    CU(cudaMemsetAsync(c->cursor.p, 0, 32 * 8, c->stream));
+    unsigned long long pairs_cap = (unsigned long long)std::max<int64_t>(std::max<int64_t>(ids_cap * 2, nseq * 4), 4096);
+    TRY(ensure(c, c->pairs_a, (size_t)pairs_cap * 8));
+    pairs_cap = c->pairs_a.cap / 8;
+    TRY(zero_scalars(c));
+    {   // requests
+        TileArgs a = base_args(c, d_seq, d_off, k, p, d_status);
+        a.send_cap = (unsigned long long)region_cap;
+        for (int r = 0; r < n_ranks; r++) {
+            a.peer_send[r] = h_peer_inboxes[r];
+            a.peer_mail_count[r] = (unsigned long long*)h_peer_mail_count[r];
+            a.peer_mail_stamp[r] = h_peer_mail_stamp[r];
+        }
+        a.send_region_off = (unsigned long long)my_rank * (unsigned long long)region_cap;
+        a.cursor = (unsigned long long*)c->cursor.p;
+        a.ridx = d_ridx;
+        a.owner_bits = bits;
+        a.n_ranks = n_ranks;
+        a.my_rank = my_rank;
+        a.epoch = epoch;
+        TRY(launch_tile<MODE_PARTITION>(c, a));
+    }
+    {   // owner side
+        ServeArgs sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.tbl = t->buckets;
+        sa.nbuckets = t->nbuckets;
+        sa.nlines = t->nlines;
+        sa.home_shift = t->home_shift;
+        sa.inbox = h_peer_inboxes[my_rank];
+        sa.region_cap = (unsigned long long)region_cap;
+        sa.mail_count = (const unsigned long long*)h_peer_mail_count[my_rank];
+        sa.mail_stamp = h_peer_mail_stamp[my_rank];
+        for (int r = 0; r < n_ranks; r++) {
+            sa.peer_replies[r] = h_peer_replies[r];
+            sa.peer_reply_stamp[r] = h_peer_reply_stamp[r];
+        }
+        sa.scal = c->d_scal;
+        sa.n_ranks = n_ranks;
+        sa.my_rank = my_rank;
+        sa.epoch = epoch;
+        serve_regions_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(sa);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    if (nseq > 0) {   // replies -> labels
+        CU(cudaMemsetAsync(&c->d_scal->round_ctr, 0, sizeof(unsigned int), c->stream));
+        TileArgs a = base_args(c, nullptr, d_off, k, p, nullptr);
+        a.pairs = (unsigned long long*)c->pairs_a.p;
+        a.pairs_cap = pairs_cap;
+        a.ridx = d_ridx;
+        a.replies = h_peer_replies[my_rank];
+        a.send_cap = (unsigned long long)region_cap;
+        a.owner_bits = bits;
+        a.n_ranks = n_ranks;
+        a.reply_stamp = h_peer_reply_stamp[my_rank];
+        a.epoch = epoch;
+        TRY(launch_tile<MODE_GATHER>(c, a));
+    }
+    TRY(fetch_scalars(c));
+    const unsigned long long n_pairs = c->h_scal->pair_count;
+    if (h_n_hits) *h_n_hits = (int64_t)c->h_scal->n_hits;
+    if (h_n_kmers) *h_n_kmers = (int64_t)(c->h_scal->n_hits + c->h_scal->n_miss);
+    if (h_flags) *h_flags = c->h_scal->err;
+    TRY(bad_offsets_check(c));
+    if (c->h_scal->err & 8) return fail(SGC_ERR_CUDA, "partitioned step: a peer GPU's stamp did not arrive (protocol time-out)");
+    if (c->h_scal->err & 4) return fail(SGC_ERR_CAPACITY, "partitioned step: a request region overflowed region_cap %lld", (long long)region_cap);
     if (n_pairs > pairs_cap) {
         if (h_n_labels) *h_n_labels = (int64_t)n_pairs;
         return fail(SGC_ERR_CAPACITY, "candidate buffer %llu < %llu", pairs_cap, n_pairs);

@@ -3,6 +3,7 @@
 #pragma once
 #include "sgc_kmer.cuh"
 #include "sgc_table.cuh"
+#include "sgc_tile.cuh"
 
 namespace sgc {
 namespace dev {
@@ -342,6 +343,69 @@ __global__ void gather_u32_kernel(const uint32_t* __restrict__ in, const int64_t
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         if (scatter) out[perm[i]] = in[i];
         else out[i] = in[perm[i]];
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// K7 owner side, flag protocol: probe every source rank's region of my inbox as soon as that rank has
+// stamped it (count + epoch in my mailbox), store each id straight into the requester's reply buffer
+// (peer memory), and stamp the requesters' reply buffers once everything has been stored.
+// ----------------------------------------------------------------------------------
+struct ServeArgs {
+    const Bucket* tbl;
+    uint32_t nbuckets, nlines;
+    int home_shift;
+    const uint64_t* inbox;             // n_ranks regions of region_cap hashes (local)
+    unsigned long long region_cap;
+    const unsigned long long* mail_count;  // local mailbox: count from rank s
+    const unsigned int* mail_stamp;        // ... stamped with the epoch when rank s's requests are all here
+    uint32_t* peer_replies[32];        // requester s's reply buffer (my region: [my_rank * region_cap ..))
+    unsigned int* peer_reply_stamp[32];
+    Scalars* scal;
+    int n_ranks, my_rank;
+    unsigned int epoch;
+};
+
+__global__ void __launch_bounds__(256) serve_regions_kernel(const ServeArgs a) {
+    __shared__ unsigned long long s_n;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int j = 0; j < a.n_ranks; j++) {
+        const int s = (a.my_rank + j) % a.n_ranks;  // own region first: it needs no link
+        if (threadIdx.x == 0) {
+            spin_until_equal(a.mail_stamp + s, a.epoch, &a.scal->err);
+            unsigned long long n = *reinterpret_cast<const volatile unsigned long long*>(a.mail_count + s);
+            s_n = n > a.region_cap ? a.region_cap : n;
+        }
+        __syncthreads();
+        const int64_t n = (int64_t)s_n;
+        const uint64_t* hash = a.inbox + (size_t)s * a.region_cap;
+        uint32_t* out = a.peer_replies[s] + (size_t)a.my_rank * a.region_cap;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
+            const int64_t i2 = i + stride;
+            const uint64_t h0 = hash[i], h1 = i2 < n ? hash[i2] : 0;
+            const uint32_t b0 = home_bucket(h0, a.nbuckets, a.home_shift), b1 = i2 < n ? home_bucket(h1, a.nbuckets, a.home_shift) : 0u;
+            Entry x0, x1, y0, y1;
+            load_bucket_nc(a.tbl + b0, x0, x1);
+            load_bucket_nc(a.tbl + b1, y0, y1);
+            uint32_t v, aux;
+            if (!bucket_match(x0, x1, h0, v)) v = bucket_overflowed(x0) ? lookup_slow(a.tbl, a.nlines, b0, h0, aux) : SGC_MISS;
+            out[i] = v;
+            if (i2 < n) {
+                if (!bucket_match(y0, y1, h1, v)) v = bucket_overflowed(y0) ? lookup_slow(a.tbl, a.nlines, b1, h1, aux) : SGC_MISS;
+                out[i2] = v;
+            }
+        }
+        __syncthreads();  // s_n is rewritten for the next region
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(&a.scal->done_ctr2, 1u);
+        if (prev == gridDim.x - 1u) {  // the last CTA: every reply of this rank has been stored
+            __threadfence_system();
+            for (int s = 0; s < a.n_ranks; s++)
+                *reinterpret_cast<volatile unsigned int*>(a.peer_reply_stamp[s] + a.my_rank) = a.epoch;
+        }
     }
 }
 

@@ -91,6 +91,8 @@ struct Scalars {
     unsigned int round_ctr;
     unsigned int max_id;
     unsigned int csr_big;  // label tail: a sequence has more candidate ids than the per-thread path sorts
+    unsigned int done_ctr;   // flag protocol of the partitioned path: warps of the request kernel that have finished
+    unsigned int done_ctr2;  // ... CTAs of the owner-side probe kernel that have finished
     unsigned int pad_;
     int err;  // bit 0: table full, bit 1: id out of range
     int bad_offsets;  // set by the plan when an offset pair is negative, decreasing or past seq_bytes
@@ -136,6 +138,14 @@ struct TileArgs {
     const uint32_t* replies;        // same layout as send, 4 bytes per request
     int owner_bits;
     int n_ranks;
+    // flag protocol (sgc_label_reads_partitioned): no host round trip between request, probe and gather kernels.
+    // The last warp of the request kernel publishes this rank's per-owner counts and the step's epoch into every
+    // owner's mailbox (peer memory); the gather kernel waits until every owner has stamped its replies.
+    unsigned long long* peer_mail_count[32];  // owner r's count mailbox (my slot: [my_rank])
+    unsigned int* peer_mail_stamp[32];        // owner r's request stamps
+    const unsigned int* reply_stamp;          // LOCAL: reply_stamp[r] == epoch once owner r has stored all my replies
+    int my_rank;
+    unsigned int epoch;                       // 0 = flag protocol off
 };
 
 

@@ -47,6 +47,20 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// Wait until a flag written by another GPU (peer store over NVLink) reaches `want`; bounded, so that a
+// protocol error ends in an error bit (8) instead of a hung GPU.
+__device__ __forceinline__ void spin_until_equal(const unsigned int* flag, unsigned int want, int* err) {
+    const long long t0 = clock64();
+    while (*reinterpret_cast<const volatile unsigned int*>(flag) != want) {
+        if (clock64() - t0 > (1LL << 33)) {  // ~4 s at 2 GHz
+            atomicOr(err, 8);
+            break;
+        }
+        __nanosleep(200);
+    }
+    __threadfence_system();  // acquire: what was stored before the flag is visible now
+}
+
 // reverse complement of 4 packed bases (byte-reversed, A<->T, C<->G); ok = every byte selected by
 // mask is one of A, C, G, T.  Bytes that are not pass through unchanged (oracle rule).
 __device__ __forceinline__ uint32_t revcomp_word(uint32_t u, uint32_t mask, bool& ok) {
@@ -216,6 +230,11 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
         }
     };
 
+    if constexpr (MODE == MODE_GATHER) {
+        // flag protocol: every owner stamps my reply buffer when all its replies to me have been stored
+        if (a.epoch && lane < a.n_ranks) spin_until_equal(a.reply_stamp + lane, a.epoch, &a.scal->err);
+        __syncwarp();
+    }
     unsigned rq0 = claim_round(), rq1 = claim_round(), rq2 = claim_round();
     // prologue: descriptors of the first two rounds, raw bytes of the first
     prefetch_desc(0, rq0);
@@ -635,6 +654,27 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
 
     if constexpr (MODE == MODE_LABEL || MODE == MODE_GATHER) {
         if (pair_fill) flush_pairs();
+    }
+    if constexpr (MODE == MODE_PARTITION) {
+        if (a.epoch) {
+            // flag protocol: the LAST warp of the grid to get here knows that every hash of this rank has been
+            // stored (each warp fences its peer stores before it counts itself); it publishes the per-owner
+            // counts and then the epoch stamp into the owners' mailboxes
+            __threadfence_system();
+            unsigned prev = 0;
+            if (lane == 0) prev = atomicAdd(&a.scal->done_ctr, 1u);
+            prev = __shfl_sync(0xffffffffu, prev, 0);
+            if (prev == gridDim.x * (unsigned)WPB - 1u) {
+                __threadfence();
+                if (lane < a.n_ranks) {
+                    const unsigned long long cnt = *reinterpret_cast<volatile unsigned long long*>(a.cursor + lane);
+                    if (cnt > a.send_cap) atomicOr(&a.scal->err, 4);  // a region overflowed: the step is void
+                    *reinterpret_cast<volatile unsigned long long*>(a.peer_mail_count[lane] + a.my_rank) = cnt;
+                    __threadfence_system();
+                    *reinterpret_cast<volatile unsigned int*>(a.peer_mail_stamp[lane] + a.my_rank) = a.epoch;
+                }
+            }
+        }
     }
     if constexpr (MODE == MODE_LOOKUP || MODE == MODE_LABEL || MODE == MODE_GATHER) {
 #pragma unroll

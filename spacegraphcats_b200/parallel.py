@@ -227,9 +227,12 @@ class DeviceEngine:
 
 
 class PeerBuffers:
-    """This rank's inbox (R regions of region_cap hashes) and reply buffer (R regions of region_cap
-    ids), allocated by the library and mapped into every other rank's process with CUDA IPC, so
-    kernels store requests / replies straight into the destination GPU over NVLink."""
+    """This rank's inbox (R regions of region_cap hashes), reply buffer (R regions of region_cap ids) and
+    mailbox (per source rank: request count, request stamp, reply stamp), allocated by the library and mapped
+    into every other rank's process with CUDA IPC, so kernels store requests / replies / flags straight into
+    the destination GPU over NVLink."""
+
+    KINDS = ("inbox", "replies", "mail_count", "mail_stamp", "reply_stamp")
 
     def __init__(self, ctx, group, region_cap):
         import torch.distributed as dist
@@ -240,29 +243,34 @@ class PeerBuffers:
         L = ctx._L
         self._own = []
         handles = []
-        for nbytes in (self.world * self.region_cap * 8, self.world * self.region_cap * 4):
+        sizes = (self.world * self.region_cap * 8, self.world * self.region_cap * 4, 256, 256, 256)
+        for nbytes in sizes:
             ptr = ctypes.c_void_p()
             hnd = (ctypes.c_uint8 * 64)()
             check(L.sgc_peer_alloc(ctx._h, nbytes, ctypes.byref(ptr), hnd))
             self._own.append(ptr)
             handles.append(bytes(hnd))
+        ctx.sync()  # sgc_peer_alloc zeroes what it allocates: mailboxes start at zero, epochs count from 1
         everyone = [None] * self.world
         dist.all_gather_object(everyone, handles, group=group)
         self._opened = []
-        self.inbox_ptrs = (ctypes.c_void_p * self.world)()
-        self.reply_ptrs = (ctypes.c_void_p * self.world)()
+        self.ptrs = {kind: (ctypes.c_void_p * self.world)() for kind in self.KINDS}
         for r in range(self.world):
-            for which, arr in ((0, self.inbox_ptrs), (1, self.reply_ptrs)):
+            for which, kind in enumerate(self.KINDS):
                 if r == self.rank:
-                    arr[r] = self._own[which].value
+                    self.ptrs[kind][r] = self._own[which].value
                 else:
                     ptr = ctypes.c_void_p()
                     hnd = (ctypes.c_uint8 * 64).from_buffer_copy(everyone[r][which])
                     check(L.sgc_peer_open(ctx._h, hnd, ctypes.byref(ptr)))
                     self._opened.append(ptr)
-                    arr[r] = ptr.value
+                    self.ptrs[kind][r] = ptr.value
+        self.inbox_ptrs = self.ptrs["inbox"]
+        self.reply_ptrs = self.ptrs["replies"]
         self.inbox = self._own[0]
         self.replies = self._own[1]
+        self.epoch = 0
+        dist.barrier(group=group)  # every mailbox is zeroed and mapped before anybody stamps one
 
     def close(self):
         import torch.distributed as dist
@@ -288,6 +296,7 @@ class PartitionedIndex:
         self.group = group
         self.p2p = bool(p2p)  # fuse the exchange into the kernels over NVLink peer memory
         self._peers = None
+        self._need_seen = 0
         self._peers2 = None  # double-buffered peer buffers of the pipelined path
         self._aux = None  # (partition context, gather context) of the pipelined path
         self.rank = dist.get_rank(group)
@@ -447,6 +456,81 @@ class PartitionedIndex:
                   flush=True)
         return ioff, ids, nh
 
+    def _collective_flags(self, *flags):
+        """MAX over the ranks of a few small ints, so that every rank takes the same error / retry decision
+        (a rank-local raise before the next collective would leave the others waiting for ever)."""
+        import torch.distributed as dist
+
+        torch = _torch()
+        c = self.engine.ctx
+        with self.engine.stream():
+            t = torch.tensor([int(f) for f in flags], dtype=torch.int64, device=c.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            return t.tolist()
+
+    def _label_reads_flags(self, seq, off, ksize):
+        """The fused path with the ranks synchronised by flags in peer memory: ONE library call per step
+        (request, serve and gather kernels back to back on the stream, no count exchange, no barrier), then
+        one tiny all-reduce that makes the error / retry decision collective."""
+        from ._lib import SgcCapacityError, SgcError
+
+        torch = _torch()
+        e, R, c = self.engine, self.world, self.engine.ctx
+        L = c._L
+        d_seq = c.to_device(seq, np.uint8)
+        d_off = c.to_device(off, np.int64)
+        nseq, n_bytes = d_off.numel() - 1, d_seq.numel()
+        need = int(max(n_bytes, 1) / R * 1.08) + 4096
+        if self._peers is None or self._need_seen < need:
+            need, = self._collective_flags(need)  # sized once for the largest batch seen so far (collective)
+            self._need_seen = need
+        else:
+            need = self._peers.region_cap
+        d_ridx = c.empty(max(n_bytes, 1), torch.int32)
+        d_stat = c.empty(max(nseq, 1), torch.int32)
+        d_ioff = c.empty(nseq + 1, torch.int64)
+        ids_cap = max(4 * nseq, 1024)
+        for _ in range(6):
+            if self._peers is None or self._peers.region_cap < need:
+                if self._peers is not None:
+                    self._peers.close()
+                self._peers = PeerBuffers(c, self.group, need)
+            pb = self._peers
+            pb.epoch += 1
+            d_ids = c.empty(ids_cap, torch.int32)
+            nk, nh, nl = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+            flags = ctypes.c_int32(0)
+            err, cap_short = None, 0
+            try:
+                check(L.sgc_label_reads_partitioned(
+                    self.table._h, c.ptr(d_seq), n_bytes, c.ptr(d_off), nseq, int(ksize), R, self.rank, pb.epoch,
+                    pb.ptrs["inbox"], pb.ptrs["replies"], pb.ptrs["mail_count"], pb.ptrs["mail_stamp"],
+                    pb.ptrs["reply_stamp"], pb.region_cap, c.ptr(d_ridx), max(n_bytes, 1), c.ptr(d_ioff), c.ptr(d_ids),
+                    ids_cap, c.ptr(d_stat), ctypes.byref(nk), ctypes.byref(nh), ctypes.byref(nl), ctypes.byref(flags)))
+            except SgcCapacityError as ex:
+                err = ex
+                cap_short = 1 if (flags.value & 4) else 2  # 1: request regions, 2: label buffer (rank-local)
+            except SgcError as ex:
+                err = ex
+            bad_base = 1 if (nseq and err is None and bool(d_stat[:nseq].any().item())) else 0
+            fatal = 1 if (err is not None and not cap_short) else 0
+            g_fatal, g_region, g_bad = self._collective_flags(fatal, 1 if cap_short == 1 else 0, bad_base)
+            if g_fatal:
+                raise err if err is not None else RuntimeError("partitioned step failed on another rank")
+            if g_bad:
+                raise ValueError("Invalid base in read")
+            if g_region:  # some rank's owner ranges are skewed: all ranks grow their buffers and redo the step
+                need = int(self._peers.region_cap * 1.5) + 4096
+                self._need_seen = need
+                continue
+            if cap_short == 2:  # only my label buffer was short; the redo is collective all the same (flags)
+                ids_cap = max(2 * ids_cap, int(nl.value) + 1024)
+            redo, = self._collective_flags(1 if cap_short == 2 else 0)
+            if redo:
+                continue
+            return d_ioff, d_ids[: nl.value], nh.value
+        raise RuntimeError("partitioned step: could not size the exchange buffers")
+
     def label_reads_pipelined(self, batches, ksize):
         """Label a list of sub-batches [(seq, off), ...] with the phases of consecutive sub-batches
         overlapped on three streams: while the owners probe sub-batch j (HBM-bound, table context),
@@ -545,6 +629,10 @@ class PartitionedIndex:
         """index_reads' per-read step against the partitioned table.
         -> (ids_off, ids, n_hits) as engine tensors"""
         if self.p2p and hasattr(self.engine, "partition_hashes"):
+            import os
+
+            if os.environ.get("SGC_PART_FLAGS", "1") != "0":
+                return self._label_reads_flags(seq, off, ksize)
             return self._label_reads_p2p(seq, off, ksize)
         if hasattr(self.engine, "partition_hashes"):
             return self._label_reads_fused(seq, off, ksize)

@@ -813,11 +813,13 @@ def test_partitioned_two_gpus_p2p_and_nccl_match_replicated():
         pytest.skip("needs 2 GPUs")
     from conftest import ROOT
 
-    for extra in (["--p2p"], []):
+    # flag protocol (default: one call per step, ranks synchronised through peer-memory stamps), the host-mediated
+    # P2P path (counts exchange + barrier) and the NCCL all-to-all baseline
+    for extra, env in ((["--p2p"], {}), (["--p2p"], {"SGC_PART_FLAGS": "0"}), ([], {})):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                "127.0.0.1", "--master-port", "29547", os.path.join(ROOT, "scripts", "partitioned_run.py"),
-               "--table-kmers", "2e7", "--reads", "3e5", "--steps", "2", "--check"] + extra
-        out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+               "--table-kmers", "2e7", "--reads", "3e5", "--steps", "3", "--check"] + extra
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, **env})
         assert out.returncode == 0, out.stderr[-2000:]
         assert "labels identical to the replicated table on every rank: True" in out.stdout
 
