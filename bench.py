@@ -369,8 +369,141 @@ def partitioned_arm(args, ctx, rank, world):
 
 
 def query_arm(args, ctx, table, cdbg, rank, world):
-    """count_cdbg_matches half of the metric (filled in below once the batched query path is in place)."""
-    return None
+    """The count_cdbg_matches half of the metric (BASELINE.json configs[2] shape, scaled up): --queries query
+    sequences of --query-kmers k-mers each (the acido-chunk size), cut from the cDBG's genome with the read error
+    model, answered as ONE batch per step by sgc_query_count_batch: per query its SET of k-mer hashes ->
+    {unitig: count} (search/query_by_sequence.py:153-189).  Every rank runs its own queries (weak scaling)."""
+    import torch
+    import torch.distributed as dist
+
+    L = ctx._L
+    dev = table._dev
+    nq, qlen = args.queries, args.query_kmers + KSIZE - 1
+    step_kmers = nq * args.query_kmers
+    nb = 2
+    batches = [cdbg.reads(nq, qlen, seed=7000 * (rank + 1) + b, err_ppm=ERR_PPM) for b in range(nb)]
+    d_sq = ctx.to_device(np.arange(nq, dtype=np.int32))
+    d_qd = ctx.empty(nq, torch.int64)
+    cap = max(step_kmers // 16, 1 << 16)
+    d_keys, d_cnt = ctx.empty(cap, torch.int64), ctx.empty(cap, torch.int32)
+    ctx.sync()
+
+    def run(seq, off):
+        npairs, nk, nh = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+        from spacegraphcats_b200._lib import check
+
+        check(L.sgc_query_count_batch(dev._h, ctx.ptr(seq), seq.numel(), ctx.ptr(off), nq, ctx.ptr(d_sq), nq, KSIZE,
+                                      ctx.ptr(d_keys), ctx.ptr(d_cnt), cap, ctx.ptr(d_qd), None, ctypes.byref(npairs),
+                                      ctypes.byref(nk), ctypes.byref(nh)))
+        return npairs.value, nk.value, nh.value
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(2):
+        stats = run(*batches[i % nb])
+    assert stats[1] == step_kmers, stats
+    launches0 = ctx.launches
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(ctx.stream)
+    for i in range(args.query_steps):
+        stats = run(*batches[i % nb])
+    ev1.record(ctx.stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launches - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=ctx.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * step_kmers * args.query_steps / (ms / 1e3)
+    distinct = int(d_qd.sum().item())
+
+    # e2e: pinned host sequences -> H2D -> the batch call -> D2H of the (query, unitig, count) triples
+    h_seq = [torch.empty(nq * qlen, dtype=torch.uint8).pin_memory() for _ in range(nb)]
+    h_off = torch.empty(nq + 1, dtype=torch.int64).pin_memory()
+    for b in range(nb):
+        h_seq[b].copy_(batches[b][0])
+    h_off.copy_(batches[0][1])
+    torch.cuda.synchronize()
+
+    def e2e_steps(n):
+        tot = 0
+        for i in range(n):
+            res = dev.count_matches_batch(h_seq[i % nb], h_off, np.arange(nq, dtype=np.int32), nq, KSIZE)
+            tot += len(res["keys"])
+        return tot
+
+    e2e_steps(1)
+    barrier()
+    t0 = time.perf_counter()
+    tot_pairs = e2e_steps(args.query_steps)
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=ctx.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    if rank != 0:
+        return None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    bytes_per_kmer = qlen / args.query_kmers + SECTOR + 4.0  # sequence in + one table sector + the id (SURVEY 8d)
+    achieved = bytes_per_kmer * step_kmers * args.query_steps / (ms / 1e3) / 1e9
+    out = {
+        "metric": "k-mers hashed+looked-up/sec (count_cdbg_matches)", "value": value, "unit": "k-mers/s",
+        "ms_per_step": ms / args.query_steps, "steps": args.query_steps,
+        "workload": "%d query sequences x %d k-mers (k=%d, acido-chunk shape of BASELINE.json configs[2], cut from the "
+                    "synthetic cDBG's genome with 0.5 %% errors) per step against the %d-k-mer table; per query the SET "
+                    "of its k-mer hashes -> {unitig: count}" % (nq, args.query_kmers, KSIZE, args.table_kmers),
+        "queries_per_step": nq, "kmers_per_step": step_kmers, "hit_fraction": stats[2] / max(distinct, 1),
+        "distinct_fraction": distinct / step_kmers, "pairs_per_query": stats[0] / nq, "gpu_launches": int(launches),
+        "e2e": {"value": world * step_kmers * args.query_steps / dt, "unit": "k-mers/s", "ms_per_step": dt / args.query_steps * 1e3,
+                "h2d_bytes_per_step": int(nq * qlen + (nq + 1) * 8 + nq * 4),
+                "d2h_bytes_per_step": int(tot_pairs // args.query_steps * 12 + nq * 8),
+                "api": "DeviceTable.count_matches_batch (what search.query_by_sequence.query_batch calls)"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "bytes_per_kmer": bytes_per_kmer,
+                     "note": "whole batch call (hash kernel + one 4-pass radix sort of (hash, query) + the lookup/count "
+                             "pass) against sequence-in + one 32-byte sector + 4 B id per k-mer; the sort alone moves "
+                             "~100 B per k-mer, so this path is bound by its own streaming traffic, not by table probes"},
+    }
+    if not args.no_cpu and world == 1:
+        # CPU arm of the query half: the oracle's batched Query restatement (C, one query per thread) on a
+        # bounded sample against the scaled-down CPU table; also a result check of that sample's shape
+        build_oracle()
+        from oracle import oracle as O
+
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        ctab, _, _, g, _ = cpu_workload(args.cpu_kmers, 1000)
+        rng = np.random.default_rng(11)
+        cq = max(threads, 16)
+        pos = rng.integers(0, len(g) - qlen, cq)
+        seqs = np.stack([g[p:p + qlen] for p in pos])
+        err = rng.random(seqs.shape) < ERR_PPM / 1e6
+        seqs[err] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(err.sum()))]
+        buf = np.ascontiguousarray(seqs).reshape(-1)
+        off = np.arange(cq + 1, dtype=np.int64) * qlen
+        qseq = np.arange(cq + 1, dtype=np.int64)
+        t0 = time.perf_counter()
+        reps, nk_tot = 0, 0
+        while time.perf_counter() - t0 < min(args.cpu_seconds, 8.0):
+            _, _, nk = ctab.query_counts(buf, off, qseq, KSIZE, threads=threads)
+            nk_tot += nk
+            reps += 1
+        secs = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": nk_tot / secs, "unit": "k-mers/s", "cores": threads, "kind": "port",
+                               "sample": "%d passes over %d queries x %d k-mers against a %d-k-mer table; "
+                                         "oracle/sgc_oracle.c sgc_oracle_query_counts (hash, sort, unique, lookup, count; "
+                                         "one query per thread)" % (reps, cq, args.query_kmers, args.cpu_kmers)}
+    return out
 
 
 def source_digest():

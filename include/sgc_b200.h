@@ -142,6 +142,20 @@ int sgc_count_matches(sgc_table* t, const uint64_t* d_hash, int64_t n, int disti
                       int64_t* h_n_distinct);
 
 /*
+ * Batched queries -- replaces, for MANY queries in one call, Query.__init__'s `self.kmers.update(hash_sequence(...))`
+ * over all records of a query (a SET: search/query_by_sequence.py:170-176) followed by
+ * kmer_idx.count_cdbg_matches(self.kmers) (:189).  Sequence s belongs to query d_seq_query[s] (int32, grouped:
+ * all sequences of a query are consecutive).  Results: d_q_distinct[n_queries] = len(query.kmers);
+ * (d_keys_out, d_counts_out)[0 .. *h_n_pairs) = ((query << 32) | unitig id, number of the query's DISTINCT
+ * k-mers on that unitig), ascending by key -- query q's dict is its run of keys.  cap = capacity of the two
+ * output arrays (SGC_ERR_CAPACITY with *h_n_pairs = needed).  Synchronises.
+ */
+int sgc_query_count_batch(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off,
+                          int64_t nseq, const int32_t* d_seq_query, int n_queries, int k,
+                          uint64_t* d_keys_out, uint32_t* d_counts_out, int64_t cap, int64_t* d_q_distinct,
+                          int32_t* d_status, int64_t* h_n_pairs, int64_t* h_n_kmers, int64_t* h_n_hits);
+
+/*
  * Fused K1+K3+K5 -- per-k-mer get_cdbg_id with no de-duplication, the loop of
  * search/count_dominator_abundance.py:80-85.  d_kmer_ids (nullable) receives the
  * unitig id or SGC_MISS of every k-mer (laid out by d_kmer_off like sgc_hash_batch);

@@ -174,6 +174,8 @@ def lib():
         L.sgc_oracle_label_reads.argtypes = [vp, vp, vp, i64, i32, vp, vp, i64, vp, vp, i32]
         L.sgc_oracle_label_reads_checksum.restype = i64
         L.sgc_oracle_label_reads_checksum.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, i32]
+        L.sgc_oracle_query_counts.restype = i64
+        L.sgc_oracle_query_counts.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, i32]
         L.sgc_oracle_num_threads.restype = i32
         L.sgc_oracle_murmur3_x64_128.restype = None
         L.sgc_oracle_murmur3_x64_128.argtypes = [vp, i32, ctypes.c_uint32, vp]
@@ -280,6 +282,30 @@ class COracleTable:
         tot2 = lib().sgc_oracle_label_reads(self._t, _ptr(pad), _ptr(off), nseq, ksize, _ptr(ids_off), _ptr(ids), len(ids), _ptr(nk), _ptr(nh), threads)
         assert tot2 == tot
         return ids_off, ids[:tot], int(nk[0]), int(nh[0])
+
+    def query_counts(self, buf, off, qseq, ksize, threads=0):
+        """Batched Query + count_cdbg_matches in C (queries in parallel): query q owns sequences
+        [qseq[q], qseq[q+1]).  -> (list of {id: count} dicts, n_distinct per query, total k-mers)"""
+        off = np.ascontiguousarray(off, np.int64)
+        qseq = np.ascontiguousarray(qseq, np.int64)
+        nq = len(qseq) - 1
+        nk = np.maximum(np.diff(off) - int(ksize) + 1, 0)
+        per_q = np.add.reduceat(np.concatenate([nk, [0]]), qseq[:-1]) if nq else np.zeros(0, np.int64)
+        per_q = np.where(np.diff(qseq) > 0, per_q, 0) if nq else per_q
+        kq = np.zeros(nq + 1, np.int64)
+        np.cumsum(per_q, out=kq[1:])
+        out_ids = np.zeros(max(int(kq[-1]), 1), np.uint32)
+        out_cnt = np.zeros(max(int(kq[-1]), 1), np.uint32)
+        n_pairs = np.zeros(max(nq, 1), np.int64)
+        n_dist = np.zeros(max(nq, 1), np.int64)
+        pad = buf if len(buf) else np.zeros(1, np.uint8)
+        total = lib().sgc_oracle_query_counts(self._t, _ptr(pad), _ptr(off), _ptr(qseq), nq, int(ksize), _ptr(kq), _ptr(out_ids),
+                                              _ptr(out_cnt), _ptr(n_pairs), _ptr(n_dist), threads)
+        dicts = []
+        for q in range(nq):
+            a, n = int(kq[q]), int(n_pairs[q])
+            dicts.append(dict(zip(out_ids[a:a + n].tolist(), out_cnt[a:a + n].tolist())))
+        return dicts, n_dist[:nq], int(total)
 
     def label_reads_checksum(self, buf, off, ksize, threads=0):
         cs = np.zeros(1, np.uint64)

@@ -363,6 +363,65 @@ int64_t sgc_oracle_label_reads_checksum(const sgc_oracle_table *t, const uint8_t
     return tot_k;
 }
 
+/* Batched queries: query q owns the sequences [qseq[q], qseq[q+1]) of (seq, off).  Per query the SET of the
+ * k-mer hashes of its records (search/query_by_sequence.py:170-176) is looked up and counted per unitig
+ * (kmer_idx.count_cdbg_matches, :189).  Output per query q, stored from index kq[q] (kq = the query's first
+ * k-mer index, a worst-case-sized region): ids ascending in out_ids, their counts in out_cnt, n_pairs[q] of
+ * them; n_distinct[q] = size of the set.  Queries run in parallel (OpenMP); returns the total k-mers. */
+static int cmp_u64(const void *a, const void *b) {
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return x < y ? -1 : x > y;
+}
+
+int64_t sgc_oracle_query_counts(const sgc_oracle_table *t, const uint8_t *seq, const int64_t *off,
+                                const int64_t *qseq, int64_t nq, int k, const int64_t *kq, uint32_t *out_ids,
+                                uint32_t *out_cnt, int64_t *n_pairs, int64_t *n_distinct, int threads) {
+    int64_t total = 0;
+    if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total)
+    for (int64_t q = 0; q < nq; q++) {
+        int64_t nk = 0;
+        for (int64_t s = qseq[q]; s < qseq[q + 1]; s++) {
+            int64_t L = off[s + 1] - off[s];
+            if (L >= k) nk += L - k + 1;
+        }
+        n_pairs[q] = 0;
+        n_distinct[q] = 0;
+        total += nk;
+        if (nk == 0) continue;
+        uint64_t *h = (uint64_t *)malloc((size_t)nk * 8);
+        int64_t w = 0;
+        for (int64_t s = qseq[q]; s < qseq[q + 1]; s++) {
+            int64_t L = off[s + 1] - off[s];
+            if (L >= k) w += sgc_oracle_hash_sequence(seq + off[s], L, k, h + w);
+        }
+        qsort(h, (size_t)nk, 8, cmp_u64);
+        uint32_t *ids = out_ids + kq[q];
+        int64_t nd = 0, nh = 0;
+        for (int64_t i = 0; i < nk; i++) {
+            if (i && h[i] == h[i - 1]) continue;
+            nd++;
+            uint32_t v = table_get(t, h[i]);
+            if (v != SGC_ORACLE_MISS) ids[nh++] = v;
+        }
+        free(h);
+        qsort(ids, (size_t)nh, 4, cmp_u32);
+        uint32_t *cnt = out_cnt + kq[q];
+        int64_t np = 0;
+        for (int64_t i = 0; i < nh; i++) {
+            if (np && ids[np - 1] == ids[i]) cnt[np - 1]++;
+            else {
+                ids[np] = ids[i];
+                cnt[np] = 1;
+                np++;
+            }
+        }
+        n_pairs[q] = np;
+        n_distinct[q] = nd;
+    }
+    return total;
+}
+
 int sgc_oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -57,6 +57,7 @@ PROTOTYPES = {
     "sgc_table_side_bytes": (_i64, [_vp]),
     "sgc_lookup": (_i32, [_vp, _vp, _i64, _vp]),
     "sgc_count_matches": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _pi64, _pi64]),
+    "sgc_query_count_batch": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _pi64, _pi64, _pi64]),
     "sgc_lookup_sequences": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _i64, _vp, _pi64, _pi64]),
     "sgc_label_reads": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _pi64, _pi64, _pi64]),
     "sgc_label_reads_launch": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _i64, _vp]),

@@ -190,6 +190,32 @@ class GpuKmerTable:
         nz = np.flatnonzero(counts)
         return dict(zip(nz.tolist(), counts[nz].tolist()))
 
+    def count_matches_batch(self, queries, ksize):
+        """Batched ``Query`` + ``count_cdbg_matches`` (search/query_by_sequence.py:153-189): ``queries`` is a list
+        of queries, each a list of sequences (str / bytes; those shorter than k contribute nothing, :174).
+        One hash launch, one sort, one lookup/count pass for ALL queries.
+        -> list of ``(cdbg_match_counts dict, number of distinct query k-mers)``, one per query."""
+        self._flush()
+        seqs, seq_query = [], []
+        for qi, q in enumerate(queries):
+            for s in q:
+                seqs.append(s)
+                seq_query.append(qi)
+        buf, off = pack_sequences(seqs)
+        res = self._dev.count_matches_batch(buf, off, np.array(seq_query, np.int32), len(queries), ksize)
+        if res["status"].any():
+            bad = int(np.flatnonzero(res["status"])[0])
+            raise ValueError("Invalid base in read (sequence %d of query %d)" % (bad, seq_query[bad]))
+        keys, counts = res["keys"], res["counts"]
+        qs = (keys >> np.uint64(32)).astype(np.int64)
+        ids = (keys & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        bounds = np.searchsorted(qs, np.arange(len(queries) + 1))
+        out = []
+        for qi in range(len(queries)):
+            a, b = int(bounds[qi]), int(bounds[qi + 1])
+            out.append((dict(zip(ids[a:b].tolist(), counts[a:b].tolist())), int(res["q_distinct"][qi])))
+        return out
+
     def label_reads(self, buf, off, ksize, packed=False):
         self._flush()
         return self._dev.label_reads(buf, off, ksize, packed=packed)

@@ -98,6 +98,7 @@ struct sgc_ctx {
     Scalars* h_scal = nullptr;  // pinned
     DevBuf nk, nseg, seg_first, kmer_off, seg_map, cub_tmp, pairs_a, pairs_b, tmp_hash, tmp_id, tmp_idx, cursor;
     DevBuf units, unit_off, base_off, unpacked;  // packed-read plans
+    DevBuf q_hash2, q_id, q_id2, q_mapk, q_mapc;  // batched queries
     // optional CUDA-event timing of the tile kernel (bench.py roofline leg)
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
@@ -437,7 +438,8 @@ void sgc_ctx_destroy(sgc_ctx* c) {
     c->timed.clear();
     DevBuf* bufs[] = {&c->nk, &c->nseg, &c->seg_first, &c->kmer_off, &c->seg_map, &c->cub_tmp,
                       &c->pairs_a, &c->pairs_b, &c->tmp_hash, &c->tmp_id, &c->tmp_idx, &c->cursor,
-                      &c->units, &c->unit_off, &c->base_off, &c->unpacked};
+                      &c->units, &c->unit_off, &c->base_off, &c->unpacked,
+                      &c->q_hash2, &c->q_id, &c->q_id2, &c->q_mapk, &c->q_mapc};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->d_scal) cudaFree(c->d_scal);
@@ -735,6 +737,101 @@ int sgc_count_matches(sgc_table* t, const uint64_t* d_hash, int64_t n, int disti
         TRY(fetch_scalars(c));
         if (h_n_miss) *h_n_miss = (int64_t)c->h_scal->n_miss;
         if (h_n_distinct) *h_n_distinct = (int64_t)c->h_scal->n_distinct;
+    }
+    return SGC_OK;
+}
+
+// Batched Query.__init__ + count_cdbg_matches (search/query_by_sequence.py:153-189) over MANY queries in one
+// call: hash every record of every query (one launch), one stable radix sort of all hashes on their top 32
+// bits with the query index as the value, then one pass that drops each query's duplicate hashes, looks the
+// rest up (sorted hashes walk the table in bucket order) and counts them per (query, unitig).
+int sgc_query_count_batch(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off, int64_t nseq,
+                          const int32_t* d_seq_query, int n_queries, int k, uint64_t* d_keys_out, uint32_t* d_counts_out,
+                          int64_t cap, int64_t* d_q_distinct, int32_t* d_status, int64_t* h_n_pairs, int64_t* h_n_kmers,
+                          int64_t* h_n_hits) {
+    if (!t) return fail(SGC_ERR_ARG, "table is NULL");
+    sgc_ctx* c = t->ctx;
+    TRY(check_seq_args(d_seq, seq_bytes, d_off, nseq, k));
+    if (n_queries < 0 || cap < 0 || (nseq > 0 && !d_seq_query) || !d_q_distinct || !h_n_pairs)
+        return fail(SGC_ERR_ARG, "bad argument");
+    TRY(set_device(c));
+    if (d_status) CU(cudaMemsetAsync(d_status, 0, (size_t)nseq * 4, c->stream));
+    if (n_queries) CU(cudaMemsetAsync(d_q_distinct, 0, (size_t)n_queries * 8, c->stream));
+    *h_n_pairs = 0;
+    if (h_n_kmers) *h_n_kmers = 0;
+    if (h_n_hits) *h_n_hits = 0;
+    if (nseq == 0) return SGC_OK;
+    Plan p;
+    TRY(make_plan(c, d_off, nseq, seq_bytes, k, nullptr, &p));
+    TRY(fetch_scalars(c));
+    TRY(bad_offsets_check(c));
+    CU(cudaMemcpyAsync(&c->h_scal->n_unique, p.kmer_off + nseq, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const int64_t n = c->h_scal->n_unique;
+    if (h_n_kmers) *h_n_kmers = n;
+    if (n == 0) return SGC_OK;
+    if (n >= ((int64_t)1 << 32)) return fail(SGC_ERR_ARG, "at most 2^32-1 k-mers per query batch");
+    TRY(ensure(c, c->tmp_hash, (size_t)n * 8));
+    TRY(ensure(c, c->q_hash2, (size_t)n * 8));
+    TRY(ensure(c, c->q_id, (size_t)n * 4));
+    TRY(ensure(c, c->q_id2, (size_t)n * 4));
+    TRY(zero_scalars(c));
+    {
+        TileArgs a = base_args(c, d_seq, d_off, k, p, d_status);
+        a.hash_out = (uint64_t*)c->tmp_hash.p;
+        TRY(launch_tile<MODE_HASH>(c, a));
+    }
+    kmer_query_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(p.kmer_off, d_seq_query, nseq, (uint32_t*)c->q_id.p);
+    c->launches++;
+    size_t tb = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, (uint64_t*)c->tmp_hash.p, (uint64_t*)c->q_hash2.p, (uint32_t*)c->q_id.p,
+                                       (uint32_t*)c->q_id2.p, n, 32, 64, c->stream));
+    TRY(ensure(c, c->cub_tmp, tb));
+    CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, (uint64_t*)c->tmp_hash.p, (uint64_t*)c->q_hash2.p, (uint32_t*)c->q_id.p,
+                                       (uint32_t*)c->q_id2.p, n, 32, 64, c->stream));
+    // scratch map (query, unitig) -> count.  A query touches far fewer unitigs than it has k-mers (a unitig holds
+    // tens of k-mers), so the map starts at n/32 slots -- small enough to stay in the 126 MB L2, where its atomics
+    // are cheap -- and the pass is redone with 4x the slots if it fills beyond 5/8 (worst case: n slots)
+    uint64_t slots = 1u << 16;
+    while ((int64_t)slots < n / 32 + 1024) slots <<= 1;
+    for (int attempt = 0; attempt < 5; attempt++, slots <<= 2) {
+        TRY(ensure(c, c->q_mapk, (size_t)slots * 8));
+        TRY(ensure(c, c->q_mapc, (size_t)slots * 4));
+        qmap_clear_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>((unsigned long long*)c->q_mapk.p, (uint32_t*)c->q_mapc.p, slots);
+        CU(cudaMemsetAsync(d_q_distinct, 0, (size_t)n_queries * 8, c->stream));
+        TRY(zero_scalars(c));
+        const size_t hist_bytes = n_queries <= QHIST_MAX ? (size_t)n_queries * 4 : 0;
+        query_count_kernel<<<grid_for(n, 256, c->num_sms * 8), 256, hist_bytes, c->stream>>>(
+            t->buckets, t->nbuckets, t->nlines, t->home_shift, (const uint64_t*)c->q_hash2.p, (const uint32_t*)c->q_id2.p, n,
+            (unsigned long long*)d_q_distinct, n_queries, (unsigned long long*)c->q_mapk.p, (uint32_t*)c->q_mapc.p, slots - 1,
+            c->d_scal);
+        c->launches += 2;
+        CU(cudaGetLastError());
+        TRY(fetch_scalars(c));
+        if (!(c->h_scal->err & 1)) break;
+        if (attempt == 4) return fail(SGC_ERR_CAPACITY, "query count map overflow");
+    }
+    if (h_n_hits) *h_n_hits = (int64_t)c->h_scal->n_hits;
+    // live map entries -> (key, count) sorted by (query, unitig)
+    TRY(ensure(c, c->tmp_hash, (size_t)std::max<int64_t>(cap, 1) * 8));  // the hashes are no longer needed
+    TRY(ensure(c, c->tmp_id, (size_t)std::max<int64_t>(cap, 1) * 4));
+    qmap_compact_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>((const unsigned long long*)c->q_mapk.p, (const uint32_t*)c->q_mapc.p,
+                                                              slots, (unsigned long long*)c->tmp_hash.p, (uint32_t*)c->tmp_id.p,
+                                                              (unsigned long long)cap, c->d_scal);
+    c->launches++;
+    CU(cudaGetLastError());
+    TRY(fetch_scalars(c));
+    const int64_t np = (int64_t)c->h_scal->n_export;
+    *h_n_pairs = np;
+    if (np > cap) return fail(SGC_ERR_CAPACITY, "cap %lld < %lld (query, unitig) pairs", (long long)cap, (long long)np);
+    if (np > 0) {
+        const int end_bit = std::min(64, 32 + std::max(1, bits_for(std::max(n_queries, 1))));
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, (uint64_t*)c->tmp_hash.p, d_keys_out, (uint32_t*)c->tmp_id.p, d_counts_out,
+                                           np, 0, end_bit, c->stream));
+        TRY(ensure(c, c->cub_tmp, tb));
+        CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, (uint64_t*)c->tmp_hash.p, d_keys_out, (uint32_t*)c->tmp_id.p,
+                                           d_counts_out, np, 0, end_bit, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
     }
     return SGC_OK;
 }

@@ -92,8 +92,14 @@ class Context:
         """numpy array / CUDA tensor -> CUDA tensor on this context's device (stream-ordered)."""
         torch = _torch()
         if isinstance(a, torch.Tensor):
+            if a.device.type == "cpu":  # host tensor (pinned memory copies asynchronously on the context's stream)
+                with torch.cuda.stream(self.stream):
+                    return a.contiguous().to(self.device, non_blocking=True)
             if a.device != self.device:
                 raise ValueError("tensor lives on %s, context on %s" % (a.device, self.device))
+            # the caller's stream produced it: order the context's stream after that work (ADVICE: stream safety)
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            a.record_stream(self.stream)
             return a.contiguous()
         a = np.ascontiguousarray(a, dtype=dtype)
         if a.dtype == np.uint64:
@@ -308,6 +314,38 @@ class DeviceTable:
         )
         cnt = c.to_host(d_cnt, np.uint32) if to_host else d_cnt
         return cnt, miss.value, nd.value
+
+    def count_matches_batch(self, seq, off, seq_query, n_queries, ksize):
+        """Batched ``Query`` + ``count_cdbg_matches``: sequence ``s`` belongs to query ``seq_query[s]`` (grouped).
+        -> dict(keys u64 (query << 32 | unitig id, ascending), counts u32, q_distinct i64[n_queries],
+        status i32[nseq], n_kmers, n_hits): per query the number of its DISTINCT k-mer hashes on each unitig
+        (search/query_by_sequence.py:170-176, :189)."""
+        torch = _torch()
+        c = self.ctx
+        d_seq = c.to_device(seq, np.uint8)
+        d_off = c.to_device(off, np.int64)
+        d_sq = c.to_device(seq_query, np.int32)
+        nseq = d_off.numel() - 1
+        d_qd = c.empty(max(int(n_queries), 1), torch.int64)
+        d_stat = c.empty(max(nseq, 1), torch.int32)
+        cap = max(d_seq.numel() // 16, 1 << 16)
+        for _ in range(6):
+            d_keys = c.empty(cap, torch.int64)
+            d_cnt = c.empty(cap, torch.int32)
+            npairs, nk, nh = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+            try:
+                check(self._L.sgc_query_count_batch(self._h, c.ptr(d_seq), d_seq.numel(), c.ptr(d_off), nseq, c.ptr(d_sq),
+                                                    int(n_queries), int(ksize), c.ptr(d_keys), c.ptr(d_cnt), cap, c.ptr(d_qd),
+                                                    c.ptr(d_stat), ctypes.byref(npairs), ctypes.byref(nk), ctypes.byref(nh)))
+                break
+            except SgcCapacityError:
+                cap = int(npairs.value) + 1024
+        else:
+            raise RuntimeError("count_matches_batch: could not size the output")
+        n = npairs.value
+        return {"keys": c.to_host(d_keys[:n], np.uint64), "counts": c.to_host(d_cnt[:n], np.uint32),
+                "q_distinct": c.to_host(d_qd[: int(n_queries)]), "status": c.to_host(d_stat[:nseq]),
+                "n_kmers": nk.value, "n_hits": nh.value}
 
     def lookup_sequences(self, seq, off, ksize, n_ids=0, want_ids=True, to_host=True):
         """Fused hash + lookup of every k-mer.  -> dict(kmer_ids, kmer_off, count_by_id, status, n_kmers, n_hits)"""

@@ -92,42 +92,31 @@ def pseudo_unitigs(sequences, ksize, piece_kmers=100):
 
 def query_batch(query_files, ksize, catlas, kmer_idx, scaled=None, catlas_name=None, debug=False):
     """Batched ``Query(...)`` + ``execute`` over many query files (BASELINE.json configs[2]: batched
-    count_cdbg_matches over many query sequences).  All records of all queries are hashed in ONE
-    kernel launch; each query's distinct-hash set and per-unitig counts come from its slice of the
-    device-resident hash array.  -> list of (Query, QueryResult or None when catlas is None)."""
-    from ..cdbg.hashing import get_context, pack_sequences
-
-    ctx = get_context()
-    queries, seqs, spans = [], [], []
+    count_cdbg_matches over many query sequences).  ALL records of ALL queries go through one hash launch,
+    one device sort and one lookup/count pass (``sgc_query_count_batch``): per query the distinct-hash set and
+    its per-unitig counts, exactly ``Query.__init__`` :170-176 + ``count_cdbg_matches`` :189.
+    -> list of (Query, QueryResult or None when catlas is None)."""
+    queries, per_query = [], []
     for qf in query_files:
         q = Query.__new__(Query)
         q.filename, q.ksize, q.name, q.catlas_name, q.debug, q.sig = qf, int(ksize), None, catlas_name, debug, None
-        lo = len(seqs)
+        seqs = []
         for record in read_records(qf):
             if q.name is None:
                 q.name = record.name
             if len(record.sequence) >= q.ksize:
                 seqs.append(record.sequence)
-        spans.append((lo, len(seqs)))
+        q._seqs = seqs
+        per_query.append(seqs)
         queries.append(q)
-    buf, off = pack_sequences(seqs)
-    d_hashes, d_koff, d_status = ctx.hash_batch(buf, off, ksize, to_host=False)
-    if d_status is not None and d_status.numel() and bool(d_status.any().item()):
-        raise ValueError("Invalid base in read (query batch)")
-    koff = ctx.to_host(d_koff)
+    counted = kmer_idx.table.count_matches_batch(per_query, ksize)
     out = []
-    for q, (lo, hi) in zip(queries, spans):
-        q._ctx, q._kmers, q._n_distinct = ctx, None, None
-        q._d_hashes = d_hashes[int(koff[lo]) : int(koff[hi])]
-        q.cdbg_match_counts = q.catlas_match_counts = None
-        if catlas is not None:
-            out.append((q, q.execute(catlas, kmer_idx)))
-        else:
-            counts, _, nd = kmer_idx.table.count_matches_array(q._d_hashes, distinct=True)
-            q._n_distinct = nd
-            nz = np.flatnonzero(counts)
-            q.cdbg_match_counts = dict(zip(nz.tolist(), counts[nz].tolist()))
-            out.append((q, None))
+    for q, (counts, n_distinct) in zip(queries, counted):
+        q._ctx, q._kmers, q._d_hashes = get_context(), None, None
+        q._n_distinct = n_distinct
+        q.cdbg_match_counts = counts
+        q.catlas_match_counts = None
+        out.append((q, q.finish(catlas, kmer_idx) if catlas is not None else None))
     return out
 
 
@@ -163,6 +152,9 @@ class Query:
     @property
     def kmers(self):
         if self._kmers is None:
+            if self._d_hashes is None:  # built by query_batch: hash this query's records on demand
+                buf, off = pack_sequences(self._seqs)
+                self._d_hashes, _, _ = self._ctx.hash_batch(buf, off, self.ksize, to_host=False)
             h = self._ctx.to_host(self._d_hashes, np.uint64)
             self._kmers = set(np.unique(h).tolist())
             self._n_distinct = len(self._kmers)
@@ -183,6 +175,10 @@ class Query:
         self._n_distinct = n_distinct
         nz = np.flatnonzero(counts)
         self.cdbg_match_counts = dict(zip(nz.tolist(), counts[nz].tolist()))  # :189
+        return self.finish(catlas, kmer_idx)
+
+    def finish(self, catlas, kmer_idx):
+        """``execute`` after ``cdbg_match_counts`` is known (:191-227)."""
         for k, v in self.cdbg_match_counts.items():  # :191-192
             assert v <= kmer_idx.get_cdbg_size(k), k
 

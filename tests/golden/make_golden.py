@@ -86,7 +86,7 @@ def main():
         shutil.copyfile(ref("data", f), out("data", f))
     for f in ("dory-subset.fq", "dory-subset.fa", "shew-os223-200k.fa"):
         gz_copy(ref("data", f), out("data", f + ".gz"))
-    for f in ("twofoo-genes.fa.gz", "acido-chunk1.fa.gz", "acido-chunk2.fa.gz"):
+    for f in ("twofoo-genes.fa.gz",) + tuple("acido-chunk%d.fa.gz" % i for i in range(1, 9)):
         shutil.copyfile(ref("data", f), out("data", f))
     for f in ("twofoo-short-paired-test.fa.gz", "twofoo-short-reads.fa.gz", "63.short.fa.gz", "2.short.fa.gz", "47.short.fa.gz"):
         shutil.copyfile(ref("tests/test-data", f), out("data", f))

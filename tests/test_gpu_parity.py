@@ -879,8 +879,9 @@ def test_batched_queries_k31_pseudo_unitigs_vs_oracle(ctx, O):
     assert sizes == osizes and len(table) == len(otab)
     assert table.stats()[1] == n_multi
 
-    qfiles = [data(f) for f in ("shew-os223-200k.fa.gz", "acido-chunk1.fa.gz", "acido-chunk2.fa.gz", "2.short.fa.gz",
-                                "47.short.fa.gz", "63.short.fa.gz", "twofoo-genes.fa.gz")]
+    # configs[2] in full: shew-os223-200k + all eight acido chunks, plus the twofoo queries, as ONE batch
+    qfiles = [data(f) for f in ("shew-os223-200k.fa.gz",) + tuple("acido-chunk%d.fa.gz" % i for i in range(1, 9)) +
+              ("2.short.fa.gz", "47.short.fa.gz", "63.short.fa.gz", "twofoo-genes.fa.gz")]
     res = query_batch(qfiles, k, None, idx)
     containment = {}
     for (q, _), qf in zip(res, qfiles):
@@ -900,6 +901,42 @@ def test_batched_queries_k31_pseudo_unitigs_vs_oracle(ctx, O):
     o_off, o_ids, o_nk, o_nh = O.COracleTable(otab.mphf_to_hash, otab.mphf_to_value).label_reads(rbuf, roff, k)
     assert np.array_equal(lab["ids_off"], o_off) and np.array_equal(lab["ids"], o_ids)
     assert (lab["n_kmers"], lab["n_hits"]) == (o_nk, o_nh)
+
+
+def test_count_matches_batch_sets_per_query(ctx, O):
+    """sgc_query_count_batch: every query is a SET of hashes (duplicates inside a record, across the records of a
+    query and palindromic / reverse-complement repeats count once), the same k-mer in two queries counts in
+    both, empty queries and queries of too-short records give empty dicts; against the oracle's Query."""
+    from spacegraphcats_b200.cdbg.hashing import GpuKmerTable
+    from spacegraphcats_b200.device import pack_sequences
+
+    rng = np.random.default_rng(77)
+    for k in (21, 31, 12):
+        lut = np.frombuffer(b"ACGT", np.uint8)
+        g = lut[rng.integers(0, 4, 30_000)].tobytes().decode()
+        cuts = list(range(0, len(g) - k, 97))
+        useqs = [g[a : a + 97 + k - 1] for a in cuts]
+        ubuf, uoff = pack_sequences(useqs)
+        table = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx)
+        otab, _, _ = O.build_mphf(k, lambda: iter(O.Record(str(i), s) for i, s in enumerate(useqs)))
+        rc = O.revcomp(g[500:900].encode()).decode()
+        queries = [
+            [g[100:400], g[100:400], g[350:600]],            # duplicates inside and across records
+            [],                                              # no records at all
+            [g[100:400], rc, g[500:900]],                    # a region and its reverse complement: same hashes
+            ["ACGT"[: k - 1], "A"],                          # only records shorter than k
+            ["A" * (k + 40), "ACGT" * 40],                   # low complexity: many identical hashes
+            [g[5000:25000]],                                 # one long record
+            [lut[rng.integers(0, 4, 3000)].tobytes().decode()],  # unrelated sequence: no (or chance) matches
+        ]
+        got = table.count_matches_batch(queries, k)
+        assert len(got) == len(queries)
+        for qi, (q, (counts, n_distinct)) in enumerate(zip(queries, got)):
+            okm = O.query_kmers([O.Record("r", s) for s in q], k)
+            want = O.count_cdbg_matches(otab, okm)
+            assert n_distinct == len(okm), (k, qi)
+            assert counts == want, (k, qi)
+    assert table.count_matches_batch([], 21) == []
 
 
 # ---------------------------------------------------------------- C-ABI error behaviour
