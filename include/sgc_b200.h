@@ -364,6 +364,9 @@ int sgc_bgzf_inflate(const uint8_t* h_raw, int64_t raw_bytes, const int64_t* h_c
 /* FASTA ('>') or 4-line FASTQ ('@') text: h_info[0..2] = records, total sequence bytes, format (0 FASTA, 1 FASTQ).
  * SGC_ERR_ARG: "unknown start chr", or a FASTQ record that is not '@' ... '+' ... */
 int sgc_reads_count(const uint8_t* h_data, int64_t n, int n_threads, int64_t* h_info);
+/* Streaming in bounded memory: *h_cut = end of the last complete record of a buffer that may stop inside one
+ * (FASTQ: a multiple of 4 lines; FASTA: the start of the last header line).  0 = no complete record. */
+int sgc_reads_cut(const uint8_t* h_data, int64_t n, int n_threads, int64_t* h_cut);
 /* h_rec_pos[r] = position of record r's header line; [h_name_lo[r], h_name_hi[r]) = its name inside
  * h_data (header line stripped, marker removed); h_seq_off[nrec+1] / h_seq = the packed sequences
  * (every sequence line stripped of surrounding whitespace), i.e. the (seq, off) pair sgc_label_reads takes. */

@@ -98,6 +98,7 @@ PROTOTYPES = {
     "sgc_bgzf_index": (_i32, [_vp, _i64, _vp, _vp, _i64, _pi64, _pi64]),
     "sgc_bgzf_inflate": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _vp, _i64]),
     "sgc_reads_count": (_i32, [_vp, _i64, _i32, _vp]),
+    "sgc_reads_cut": (_i32, [_vp, _i64, _i32, _pi64]),
     "sgc_reads_scan": (_i32, [_vp, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "sgc_reads_pair_flags": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "sgc_reads_rows": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _pi64]),

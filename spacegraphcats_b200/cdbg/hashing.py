@@ -375,8 +375,40 @@ class MPHF_KmerIndex:
 
     @classmethod
     def from_directory(cls, location):
-        "Load a kmer index written by this package or by the reference (hashing.py:119-130)."
-        table = GpuKmerTable.load(os.path.join(location, "contigs.mphf"), os.path.join(location, "contigs.indices"))
+        """Load a kmer index written by this package or by the reference (hashing.py:119-130).
+
+        ``contigs.indices`` holds the (hash, id) pairs in MPHF order: enough for exact lookups, but without the
+        unitig order the fast read-labelling kernel needs.  When the unitig database the index was built from
+        lies next to it (``bcalm.unitigs.db``, the layout conf/Snakefile:288-301 produces) the table is rebuilt
+        from those sequences instead -- one fused hash+insert pass on the GPU -- and checked against the stored
+        pairs count; otherwise (or if they disagree) the pairs are loaded as they are."""
         with open(os.path.join(location, "contigs.sizes"), "rb") as fp:
             ksize, sizes = pickle.load(fp)
+        table = None
+        db = os.path.join(location, "bcalm.unitigs.db")
+        if os.path.exists(db) and os.environ.get("SGC_B200_REBUILD_FROM_UNITIGS", "1") != "0":
+            table = cls._table_from_unitig_db(db, ksize, os.path.join(location, "contigs.indices"))
+        if table is None:
+            table = GpuKmerTable.load(os.path.join(location, "contigs.mphf"), os.path.join(location, "contigs.indices"))
         return cls(ksize, table, sizes)
+
+    @staticmethod
+    def _table_from_unitig_db(db_path, ksize, indices_path):
+        import sqlite3
+
+        try:
+            con = sqlite3.connect("file:%s?mode=ro" % db_path, uri=True)
+            rows = con.execute("SELECT id, sequence FROM sequences ORDER BY id").fetchall()
+            con.close()
+        except sqlite3.Error:
+            return None
+        if not rows:
+            return None
+        buf, off = pack_sequences([r[1] for r in rows])
+        ids = np.array([int(r[0]) for r in rows], np.uint32)
+        table = GpuKmerTable.from_sequences(buf, off, ksize, ids=ids)
+        with np.load(indices_path) as z:
+            n_stored = int((z["mphf_to_value"] != UNSET_VALUE).sum())
+        if len(table) != n_stored or table._build_status.any():
+            return None  # not the unitigs this index was built from
+        return table

@@ -21,7 +21,6 @@ from .hashing import MPHF_KmerIndex
 
 DEFAULT_KSIZE = 31
 TIMINGS = {}  # seconds per stage of the latest main() run (scripts/index_reads_timing.py)
-BATCH_READS = 1 << 22
 
 
 def pair_flags(names, elig, ignore_paired=False):
@@ -95,6 +94,80 @@ def label_records(names, seq, seq_off, offsets, kmer_idx, ksize, ignore_paired=F
     return ro, ri, n_paired, set(np.unique(ri).tolist()), first_paired
 
 
+def invalid_base_policy():
+    """What to do with a read that holds a byte other than A/C/G/T.  ``raise`` (default) follows khmer, which
+    throws on such reads; ``skip`` (SGC_B200_INVALID_BASES=skip) follows the comment at index_reads.py:149-150
+    ("if reads have 'N' in them, they will not appear in cDBG"): the read is kept in the stream -- pairing and
+    offsets are unchanged -- but contributes no unitig ids."""
+    v = os.environ.get("SGC_B200_INVALID_BASES", "raise").lower()
+    if v not in ("raise", "skip"):
+        raise ValueError("SGC_B200_INVALID_BASES must be 'raise' or 'skip'")
+    return v
+
+
+def record_batches(reads_path, ksize, ignore_paired=False, chunk_bytes=None, timings=None, policy="raise"):
+    """Walk a read file in bounded memory and yield batches of records ready for ``label_reads_stream``:
+    dicts with the 2-bit packed reads (``packed``, ``nseq``, ``lengths``) plus the host-side columns the row
+    rules need (``names``, ``lens``, ``offsets``) and ``bad`` (records with a non-ACGT byte).
+
+    A batch always ends just BEFORE a record that is long enough and is not the mate of its predecessor: the
+    pairing state of index_reads.py:124-141 (``last_record``, the carried id set) is empty at that point, so
+    batches can be labelled and turned into rows independently.  The held-back records open the next batch."""
+    from ..device import pack_reads_host
+
+    if chunk_bytes is None:
+        chunk_bytes = int(float(os.environ.get("SGC_INDEX_READS_BATCH_MB", "512")) * (1 << 20))
+    stream = bgzf.ReadStream(reads_path, chunk_bytes)
+    tm = timings if timings is not None else {}
+    carry, carry_g = np.zeros(0, np.uint8), 0
+    chunks = stream.chunks()
+    nxt = next(chunks, None)
+    while nxt is not None:
+        t0 = time.time()
+        data, gstart = nxt
+        nxt = next(chunks, None)
+        tm["inflate"] = tm.get("inflate", 0.0) + time.time() - t0
+        last = nxt is None
+        if len(carry):
+            data = np.concatenate([carry, data])
+            gstart = carry_g
+        t1 = time.time()
+        names, seq, seq_off, rec_pos = bgzf.parse_records(data)
+        n = len(names)
+        lens = np.diff(seq_off)
+        cut = n
+        if not last:
+            # hold back from the last record that is long enough and unpaired (it resets the pairing state)
+            elig = lens >= ksize
+            paired, _ = pair_flags(names, elig, ignore_paired)
+            safe = np.flatnonzero(elig & ~paired)
+            safe = safe[safe > 0]
+            if len(safe) == 0:  # no safe boundary in this chunk (pathological): grow it with the next one
+                carry, carry_g = data, gstart
+                continue
+            cut = int(safe[-1])
+            carry, carry_g = data[rec_pos[cut]:].copy(), gstart + int(rec_pos[cut])
+        else:
+            carry = np.zeros(0, np.uint8)
+        tm["scan"] = tm.get("scan", 0.0) + time.time() - t1
+        t2 = time.time()
+        sub_off = seq_off[: cut + 1]
+        packed, plen, bad = pack_reads_host(seq[: int(sub_off[-1])], sub_off, n_threads=bgzf.n_threads())
+        if bad.any():
+            if policy == "raise":
+                raise ValueError("Invalid base in read %r" % names[int(np.flatnonzero(bad)[0])])
+            # skip: the record stays in the stream (pairing, offsets) but is packed with length 0: no k-mers
+            sub_lens = lens[:cut]
+            keep = np.repeat(~bad, sub_lens)
+            off2 = np.zeros(cut + 1, np.int64)
+            np.cumsum(np.where(bad, 0, sub_lens), out=off2[1:])
+            packed, plen, _ = pack_reads_host(seq[: int(sub_off[-1])][keep], off2, n_threads=bgzf.n_threads())
+        tm["pack"] = tm.get("pack", 0.0) + time.time() - t2
+        sub_names = bgzf.NameTable(names.data, names.lo[:cut], names.hi[:cut])
+        yield {"packed": packed, "nseq": cut, "lengths": plen, "names": sub_names, "lens": lens[:cut], "bad": bad,
+               "offsets": stream.virtual_offsets(gstart + rec_pos[:cut])}
+
+
 def main(argv=sys.argv[1:]):
     p = argparse.ArgumentParser()
     p.add_argument("cdbg_prefix", help="cDBG prefix")
@@ -139,46 +212,62 @@ def main(argv=sys.argv[1:]):
 
     print(f"walking read file: '{args.reads}'")
     t0 = time.time()
-    src = bgzf.open_reads(args.reads)
-    TIMINGS["inflate"] = time.time() - t0
-    t1 = time.time()
-    names, seq, seq_off, rec_pos = bgzf.parse_records(src.data)
-    offsets = src.virtual_offsets(rec_pos)
-    TIMINGS["scan"] = time.time() - t1
-    n = len(names)
-    total_bp = int(seq_off[-1])
+    policy = invalid_base_policy()
+    watermark = 5e5  # the reference checks for pairs every 5e5 bp; only the first crossing can fail (:107-122)
+    n = total_bp = n_paired = n_rows = n_batches = n_skipped = 0
+    first_paired_seen = False
+    seen = np.zeros(0, bool)  # unitig ids that received reads
 
-    # NB: pairing links a read to the previous one, so the whole file is labelled as one stream;
-    # the GPU pass itself is batched inside the table object.
-    ro, ri, n_paired, total_ids, first_paired = label_records(
-        names, seq, seq_off, offsets, kmer_idx, args.ksize, ignore_paired=args.ignore_paired, timings=TIMINGS
-    )
-    if args.expect_paired:
-        # the reference checks at every 5e5-bp watermark that a pair has been seen (:108-122)
-        before = np.cumsum(np.diff(seq_off)) - np.diff(seq_off)
-        crossed = np.flatnonzero(before >= 5e5)
-        if len(crossed) and (first_paired < 0 or first_paired >= crossed[0]):
-            print("ERROR: no paired reads!? but -P/--expect-paired set. Quitting.")
-            return -1
-    t1 = time.time()
-    cursor.executemany(
-        "INSERT INTO sequences (offset, cdbg_id) VALUES (?, ?)", zip(ro.tolist(), ri.tolist())
-    )
+    batches = lambda: record_batches(args.reads, args.ksize, args.ignore_paired, timings=TIMINGS, policy=policy)  # noqa: E731
+
+    # the GPU labels batch i while the helper thread inflates / scans / packs batch i+1 and this thread turns
+    # the labels of batch i-1 into rows: memory is bounded by a few batches whatever the size of the read file
+    for batch, res in kmer_idx.table.label_reads_stream(batches(), args.ksize):
+        t1 = time.time()
+        lens = batch["lens"]
+        n_skipped += int(batch["bad"].sum())  # such a read keeps its place in the stream (it can be a mate) but has no ids
+        ro, ri, npair, first_paired = rows_from_labels(batch["names"], lens, batch["offsets"], res["ids_off"], res["ids"],
+                                                        args.ksize, args.ignore_paired)
+        if args.expect_paired and not first_paired_seen:
+            before = total_bp + np.cumsum(lens) - lens
+            crossed = np.flatnonzero(before >= watermark)
+            if len(crossed) and (first_paired < 0 or first_paired >= crossed[0]):
+                print("ERROR: no paired reads!? but -P/--expect-paired set. Quitting.")
+                return -1
+            if first_paired >= 0:
+                first_paired_seen = True
+        TIMINGS["pairing_rows"] = TIMINGS.get("pairing_rows", 0.0) + time.time() - t1
+        t1 = time.time()
+        cursor.executemany("INSERT INTO sequences (offset, cdbg_id) VALUES (?, ?)", zip(ro.tolist(), ri.tolist()))
+        TIMINGS["sqlite_insert"] = TIMINGS.get("sqlite_insert", 0.0) + time.time() - t1
+        if len(ri):
+            top = int(ri.max()) + 1
+            if top > len(seen):
+                seen = np.concatenate([seen, np.zeros(top - len(seen), bool)])
+            seen[np.unique(ri)] = True
+        n += len(lens)
+        total_bp += int(lens.sum())
+        n_paired += npair
+        n_rows += len(ro)
+        n_batches += 1
     db.commit()
-    TIMINGS["sqlite_insert"] = time.time() - t1
-    TIMINGS["rows"] = len(ro)
+    TIMINGS["rows"] = n_rows
+    TIMINGS["batches"] = n_batches
 
     err = lambda s: print(s, file=sys.stderr)  # noqa: E731
+    n_ids = int(seen.sum())
     err(f"{total_bp:5.2e} bp in {n} reads")
     err(f"{2*n_paired} paired of {n} reads; {n-2*n_paired} singletons")
-    err(f"found reads for {len(total_ids)} cDBG IDs")
+    if n_skipped:
+        err(f"{n_skipped} reads with non-ACGT bases contributed no cDBG IDs (SGC_B200_INVALID_BASES=skip)")
+    err(f"found reads for {n_ids} cDBG IDs")
     err(f"{time.time() - t0:.1f}s seconds total")
 
     fail_exit = False
-    if not total_ids or max(total_ids) + 1 != len(total_ids):
+    if not n_ids or len(seen) != n_ids:
         fail_exit = True
-        err("ERROR: max cDBG ID found is {}, different from:".format(max(total_ids) if total_ids else None))
-        err(f"ERROR: length of distinct cDBG IDs found is {len(total_ids)}")
+        err("ERROR: max cDBG ID found is {}, different from:".format(len(seen) - 1 if len(seen) else None))
+        err(f"ERROR: length of distinct cDBG IDs found is {n_ids}")
 
     err("creating indices in database.")
     t1 = time.time()

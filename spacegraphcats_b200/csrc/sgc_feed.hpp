@@ -396,6 +396,45 @@ int sgc_reads_count(const uint8_t* h_data, int64_t n, int n_threads, int64_t* h_
 }
 
 // Fills rec_pos / name_lo / name_hi (nrec each), seq_off (nrec + 1) and the packed sequence bytes.
+// End of the last COMPLETE record of a buffer that may stop in the middle of one (streaming reads in bounded
+// memory: the tail from *h_cut on is carried over to the next chunk).  FASTQ: records are exactly 4 lines, so
+// the cut is the start of line 4*floor(L/4) (L = complete lines); FASTA: the start of the last header line
+// (the record it opens ends only at the next header or at the end of the file).  *h_cut = 0: no complete record.
+int sgc_reads_cut(const uint8_t* h_data, int64_t n, int n_threads, int64_t* h_cut) {
+    if (n < 0 || (n > 0 && !h_data) || !h_cut) return fail(SGC_ERR_ARG, "bad argument");
+    *h_cut = 0;
+    if (n == 0) return SGC_OK;
+    if (h_data[0] == '@') {
+        const int nt = feed::pick_threads(n_threads, std::max<int64_t>(n >> 20, 1));
+        std::vector<int64_t> cnt((size_t)nt, 0);
+        feed::parallel_for(nt, [&](int t) { cnt[(size_t)t] = feed::count_newlines(h_data, n * t / nt, n * (t + 1) / nt); });
+        int64_t lines = 0;
+        for (int64_t c : cnt) lines += c;
+        int64_t drop = lines % 4;  // complete lines of the unfinished record
+        int64_t pos = n;           // walk back over the partial line and `drop` complete lines
+        if (h_data[n - 1] != '\n') {
+            while (pos > 0 && h_data[pos - 1] != '\n') --pos;
+        }
+        for (int64_t d = 0; d < drop; ++d) {
+            --pos;  // the newline that ends this line
+            while (pos > 0 && h_data[pos - 1] != '\n') --pos;
+        }
+        *h_cut = pos;
+        return SGC_OK;
+    }
+    if (h_data[0] == '>') {
+        int64_t pos = n;
+        for (;;) {  // start of the line that holds pos-1
+            while (pos > 0 && h_data[pos - 1] != '\n') --pos;
+            if (pos == 0 || h_data[pos] == '>') break;   // pos < n here: a line start
+            --pos;
+        }
+        *h_cut = (pos < n && h_data[pos] == '>') ? pos : 0;
+        return SGC_OK;
+    }
+    return fail(SGC_ERR_ARG, "unknown start chr %c", (char)h_data[0]);
+}
+
 int sgc_reads_scan(const uint8_t* h_data, int64_t n, int n_threads, int64_t nrec, int64_t seq_bytes,
                    int64_t* h_rec_pos, int64_t* h_name_lo, int64_t* h_name_hi, int64_t* h_seq_off, uint8_t* h_seq) {
     if (n < 0 || (n > 0 && !h_data) || nrec < 0 || seq_bytes < 0 || !h_seq_off) return fail(SGC_ERR_ARG, "bad argument");

@@ -83,6 +83,79 @@ def open_reads(path):
     return BgzfData(path) if is_bgzf(path) else PlainData(path)
 
 
+
+class ReadStream:
+    """Bounded-memory walk over a read file: ``chunks()`` yields ``(data uint8, gstart)`` pieces that each hold
+    only COMPLETE records (``gstart`` = uncompressed position of ``data[0]`` in the file), ``virtual_offsets``
+    maps uncompressed positions to what the reference's reader reports (BGZF virtual offsets, or plain positions).
+
+    BGZF files are memory-mapped and inflated ``chunk_bytes`` of blocks at a time (native, multi-threaded); the
+    unfinished record at the end of a chunk is carried over to the next one.  Plain / gzip files are one chunk."""
+
+    def __init__(self, path, chunk_bytes=512 << 20):
+        self.path, self.chunk_bytes = path, int(chunk_bytes)
+        self.bgzf = is_bgzf(path)
+        if self.bgzf:
+            L = lib()
+            self._raw = np.memmap(path, np.uint8, mode="r")
+            nb, total = ctypes.c_int64(0), ctypes.c_int64(0)
+            check(L.sgc_bgzf_index(_p(self._raw), self._raw.size, None, None, 0, ctypes.byref(nb), ctypes.byref(total)))
+            self._cstart_all = np.zeros(nb.value, np.int64)
+            self._usize_all = np.zeros(nb.value, np.int64)
+            check(L.sgc_bgzf_index(_p(self._raw), self._raw.size, _p(self._cstart_all), _p(self._usize_all), nb.value,
+                                   ctypes.byref(nb), ctypes.byref(total)))
+            self.total_bytes = int(total.value)
+            keep = self._usize_all > 0  # empty blocks (the EOF marker) hold no position
+            self._cstart = self._cstart_all[keep]
+            self._ustart = (np.cumsum(self._usize_all) - self._usize_all)[keep]
+        else:
+            self._plain = PlainData(path)
+            self.total_bytes = int(self._plain.data.size)
+
+    def virtual_offsets(self, positions):
+        positions = np.asarray(positions, np.int64)
+        if not self.bgzf:
+            return positions
+        b = np.searchsorted(self._ustart, positions, side="right") - 1
+        return (self._cstart[b] << 16) | (positions - self._ustart[b])
+
+    def chunks(self):
+        if not self.bgzf:
+            yield self._plain.data, 0
+            return
+        L = lib()
+        nblocks = len(self._usize_all)
+        carry = np.zeros(0, np.uint8)
+        b0, gpos = 0, 0  # next block, its uncompressed position
+        while b0 < nblocks:
+            b1, size = b0, 0
+            while b1 < nblocks and (size < self.chunk_bytes or b1 == b0):
+                size += int(self._usize_all[b1])
+                b1 += 1
+            buf = np.empty(len(carry) + size, np.uint8)
+            buf[: len(carry)] = carry
+            if size:
+                check(L.sgc_bgzf_inflate(_p(self._raw), self._raw.size, _p(self._cstart_all[b0:b1]), _p(self._usize_all[b0:b1]),
+                                         b1 - b0, n_threads(), _p(buf[len(carry):]), size))
+            gstart = gpos - len(carry)
+            gpos += size
+            b0 = b1
+            if b0 >= nblocks:  # end of the file: whatever is left is the last record(s)
+                if buf.size:
+                    yield buf, gstart
+                return
+            cut = ctypes.c_int64(0)
+            if buf.size:
+                try:
+                    check(L.sgc_reads_cut(_p(buf), buf.size, n_threads(), ctypes.byref(cut)))
+                except Exception as e:
+                    if "unknown start chr" in str(e):
+                        raise Exception("unknown start chr {}".format(chr(buf[0])))
+                    raise
+            if cut.value:
+                yield buf[: cut.value], gstart
+            carry = buf[cut.value:].copy()
+
 class NameTable:
     """Record names as byte ranges ``[lo[i], hi[i])`` of a uint8 buffer: no per-record Python
     object is made until one is asked for.  Compares equal to a list of str."""

@@ -583,10 +583,14 @@ def test_index_reads_main_dory(tmp_path, O, dory, dory_index, dory_reads):
     assert index_reads.main([cdbg, reads, db, "-P", "-N"]) == -1
 
 
+@pytest.mark.parametrize("batch_mb", [None, "0.0005"])
 @pytest.mark.parametrize("ignore_paired", [False, True])
-def test_index_reads_pairing_semantics(tmp_path, ctx, O, ignore_paired):
+def test_index_reads_pairing_semantics(tmp_path, ctx, O, ignore_paired, batch_mb, monkeypatch):
     """Pairing rules of index_reads.py:124-141 (/1,/2 names, equal names, short mates) on the
-    reference's own pairing fixture plus synthetic corner cases, against the oracle loop."""
+    reference's own pairing fixture plus synthetic corner cases, against the oracle loop -- as one batch and
+    streamed in ~0.5 KB batches (bounded memory: mates and the pairing state must survive every batch cut)."""
+    if batch_mb:
+        monkeypatch.setenv("SGC_INDEX_READS_BATCH_MB", batch_mb)
     from spacegraphcats_b200.cdbg import index_reads
     from spacegraphcats_b200.cdbg.hashing import MPHF_KmerIndex
     from spacegraphcats_b200.cdbg.index_cdbg_by_kmer import build_mphf
@@ -622,6 +626,7 @@ def test_index_reads_pairing_semantics(tmp_path, ctx, O, ignore_paired):
     write_bgzf(rp, fa, block_size=700)
     db = str(tmp_path / "out.index")
     rc = index_reads.main([str(d), rp, db, "-k", str(k)] + (["-N"] if ignore_paired else []))
+    assert (index_reads.TIMINGS["batches"] == 1) if not batch_mb else (index_reads.TIMINGS["batches"] > 2)
     rows = sorted(sqlite3.connect(db).execute("SELECT offset, cdbg_id FROM sequences").fetchall())
     src = bgzf.open_reads(rp)
     names, _, _, pos = bgzf.parse_records(src.data)
@@ -632,6 +637,98 @@ def test_index_reads_pairing_semantics(tmp_path, ctx, O, ignore_paired):
     assert rows == sorted(want)
     assert (n_paired > 0) != ignore_paired
     assert rc == (0 if max(total) + 1 == len(total) else -1)
+
+
+def test_index_reads_many_batches_fastq_and_invalid_base_policy(tmp_path, ctx, O, monkeypatch):
+    """index_reads.main over a FASTQ file cut into many small batches (paired reads straddling the cuts), and the
+    two policies for reads with non-ACGT bases: raise (default, khmer) or keep the read in the stream without ids
+    (SGC_B200_INVALID_BASES=skip, the behaviour the comment at index_reads.py:149-150 assumes)."""
+    from spacegraphcats_b200.cdbg import index_reads
+    from spacegraphcats_b200.cdbg.hashing import MPHF_KmerIndex
+    from spacegraphcats_b200.cdbg.index_cdbg_by_kmer import build_mphf
+    from spacegraphcats_b200.utils import bgzf
+
+    k = 21
+    rng = np.random.default_rng(12)
+    genome = rand_seq(rng, 20000)
+    pieces = [genome[a : a + 80 + k - 1] for a in range(0, len(genome) - k + 1, 80)]
+    urecs = [O.Record(str(i), s) for i, s in enumerate(pieces)]
+    table, sizes = build_mphf(k, lambda: iter(urecs), ctx=ctx, verbose=False)
+    d = tmp_path / "cdbg"
+    d.mkdir()
+    MPHF_KmerIndex(k, table, sizes).save(str(d))
+    reads = []
+    for i in range(600):
+        p = int(rng.integers(0, len(genome) - 400))
+        ln = int(rng.integers(10, 200))
+        reads.append(O.Record("r%d/1" % i, genome[p : p + ln], "I" * ln))
+        if i % 3:
+            reads.append(O.Record("r%d/2" % i, genome[p + 150 : p + 150 + ln], "I" * ln))
+    clean = list(reads)
+    reads[10] = O.Record(reads[10].name, reads[10].sequence[:40] + "N" + reads[10].sequence[41:], reads[10].quality)
+    reads[11] = O.Record(reads[11].name, "N" * len(reads[11].sequence), reads[11].quality)
+    otab, _, _ = O.build_mphf(k, lambda: iter(urecs))
+    db = str(tmp_path / "out.index")
+    monkeypatch.setenv("SGC_INDEX_READS_BATCH_MB", "0.01")
+    for recs, policy in ((clean, None), (reads, "skip"), (reads, None)):
+        fq = "".join("@%s\n%s\n+\n%s\n" % (r.name, r.sequence, r.quality) for r in recs).encode()
+        rp = str(tmp_path / "reads.bgz")
+        write_bgzf(rp, fq, block_size=2000)
+        if policy:
+            monkeypatch.setenv("SGC_B200_INVALID_BASES", policy)
+        else:
+            monkeypatch.delenv("SGC_B200_INVALID_BASES", raising=False)
+        if recs is reads and policy is None:
+            with pytest.raises(ValueError):
+                index_reads.main([str(d), rp, db, "-k", str(k)])
+            continue
+        rc = index_reads.main([str(d), rp, db, "-k", str(k)])
+        assert index_reads.TIMINGS["batches"] > 5
+        rows = sorted(sqlite3.connect(db).execute("SELECT offset, cdbg_id FROM sequences").fetchall())
+        src = bgzf.open_reads(rp)
+        _, _, _, pos = bgzf.parse_records(src.data)
+        offs = src.virtual_offsets(pos).tolist()
+        hash_fn = (lambda s, kk: ([] if "N" in (s if isinstance(s, str) else s.decode()) else O.hash_sequence(s, kk)))
+        want, n_paired, total = O.label_reads(zip(recs, offs), otab, k, hash_fn=hash_fn)
+        assert rows == sorted(want) and n_paired > 100
+        assert rc == (0 if max(total) + 1 == len(total) else -1)
+
+
+def test_from_directory_rebuilds_the_side_array_from_the_unitig_db(tmp_path, ctx, O, dory, dory_index, dory_reads):
+    """An index directory that also holds bcalm.unitigs.db (the Snakefile layout) is loaded WITH the
+    unitig-ordered side array, so `python -m ...index_reads cdbg_dir ...` runs the fast label kernel; without the
+    database, or with one that does not match the stored pairs, the pairs are loaded as they are."""
+    from spacegraphcats_b200.cdbg.hashing import MPHF_KmerIndex
+    from spacegraphcats_b200.device import pack_sequences
+
+    recs, ref_h, ref_v, _ = dory
+    d = tmp_path / "dory_k21"
+    d.mkdir()
+    dory_index.save(str(d))
+    buf, off = pack_sequences([r.sequence for r in dory_reads])
+    o_off, o_ids, _, _ = O.COracleTable(ref_h, ref_v).label_reads(buf, off, 21)
+
+    plain = MPHF_KmerIndex.from_directory(str(d))
+    assert plain.table._dev.side_nbytes == 0
+
+    def write_db(records):
+        p = str(d / "bcalm.unitigs.db")
+        if os.path.exists(p):
+            os.unlink(p)
+        con = sqlite3.connect(p)
+        con.execute("CREATE TABLE sequences (id INTEGER PRIMARY KEY, sequence TEXT, offset INTEGER, min_hashval TEXT, abund FLOAT)")
+        con.executemany("INSERT INTO sequences (id, sequence) VALUES (?, ?)", [(int(r.name), r.sequence) for r in records])
+        con.commit()
+        con.close()
+
+    write_db(recs)
+    sided = MPHF_KmerIndex.from_directory(str(d))
+    assert sided.table._dev.side_nbytes > 0 and len(sided) == len(plain) == 212475
+    for idx in (plain, sided):
+        res = idx.table.label_reads(buf, off, 21)
+        assert np.array_equal(res["ids_off"], o_off) and np.array_equal(res["ids"], o_ids)
+    write_db(recs[:-5])  # not the unitigs of this index: fall back to the stored pairs
+    assert MPHF_KmerIndex.from_directory(str(d)).table._dev.side_nbytes == 0
 
 
 # ---------------------------------------------------------------- K7: partitioned pipeline
