@@ -376,8 +376,9 @@ class OracleTable:
         return t
 
 
-def build_mphf(ksize, records_iter_fn, hash_fn=hash_sequence):
-    """index_cdbg_by_kmer.py:27-115.  Returns (OracleTable, sizes, n_multicounts)."""
+def build_mphf(ksize, records_iter_fn, hash_fn=hash_sequence, table_cls=None):
+    """index_cdbg_by_kmer.py:27-115.  Returns (OracleTable, sizes, n_multicounts).  ``table_cls``: any class with
+    the BBHashTable surface (the tests drive the library's ctypes binding through this very loop)."""
     seen, multi = set(), set()
     n = -1
     for n, rec in enumerate(records_iter_fn()):
@@ -386,8 +387,8 @@ def build_mphf(ksize, records_iter_fn, hash_fn=hash_sequence):
         seen |= these  # :47
     n_contigs = n + 1
     seen -= multi  # :52-57
-    table = OracleTable()
-    table.initialize(seen)  # :63-64
+    table = (table_cls or OracleTable)()
+    table.initialize(list(seen))  # :63-64
     sizes = {}
     max_id = 0
     for n, rec in enumerate(records_iter_fn()):

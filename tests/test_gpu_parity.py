@@ -1036,6 +1036,51 @@ def test_count_matches_batch_sets_per_query(ctx, O):
     assert table.count_matches_batch([], 21) == []
 
 
+# ---------------------------------------------------------------- the reference-side binding
+def test_reference_side_binding_drives_the_reference_loops(tmp_path, O, dory):
+    """tests/refshim/sgc_b200_binding.py -- the raw ctypes stand-in for ``khmer`` / ``bbhash_table`` a reference
+    maintainer would add -- driven through the reference's build_mphf loop
+    (index_cdbg_by_kmer.py:27-115, restated in oracle.build_mphf; the reference's own file runs on the same shim
+    surface in tests/test_refshim_cpu.py where /root/reference exists): KATs of test_dory_workflow.py:195-199,
+    the whole table, get_unique_values semantics, save / load, and the reference-format files it writes."""
+    import sys
+
+    from conftest import ROOT
+
+    sys.path.insert(0, os.path.join(ROOT, "tests", "refshim"))
+    try:
+        import sgc_b200_binding as B
+    finally:
+        sys.path.pop(0)
+    recs, ref_h, ref_v, ref_sizes = dory
+    nt = B.Nodetable(21, 1, 1)
+    assert nt.get_kmer_hashes("GACCAAAGGCTTACGGTGAGC") == [10218271035842461694]
+    assert nt.get_kmer_hashes(recs[5].sequence) == O.hash_sequence(recs[5].sequence, 21).tolist()
+    with pytest.raises(ValueError):
+        nt.get_kmer_hashes("ACGT")
+    with pytest.raises(ValueError):
+        nt.get_kmer_hashes("ACGTN" * 10)
+    hash_fn = lambda s, k: B.Nodetable(k, 1, 1).get_kmer_hashes(s)  # noqa: E731
+    table, sizes, n_multi = O.build_mphf(21, lambda: iter(recs), hash_fn=hash_fn, table_cls=B.BBHashTable)
+    assert sizes == ref_sizes and n_multi == 0 and len(table) == 212475
+    assert table[10218271035842461694] == 118 and table[8436068710919520258] == 118
+    assert table[13994045974119358468] == 118 and table[11971930231572094512] == 187 and table[12345] is None
+    order = np.argsort(ref_h)
+    assert np.array_equal(table.mphf_to_hash, ref_h[order]) and np.array_equal(table.mphf_to_value, ref_v[order])
+    assert int(max(table.mphf_to_value)) == 735  # index_cdbg_by_kmer.py:106
+    q = nt.get_kmer_hashes(recs[118].sequence[:60])
+    assert table.get_unique_values(q + q + [7]) == {118: 2 * len(q)}
+    assert table.get_unique_values(set(q)) == {118: len(q)} and table.get_unique_values([]) == {}
+    with pytest.raises(ValueError):
+        table.get_unique_values(q + [7], require_exist=True)
+    mphf, arr = str(tmp_path / "contigs.mphf"), str(tmp_path / "contigs.indices")
+    table.save(mphf, arr)
+    assert open(mphf, "rb").read() == open(golden_path("dory_k21_contigs.mphf"), "rb").read()  # byte-identical boomphf dump
+    again = B.BBHashTable.load(mphf, arr)
+    assert len(again) == 212475 and again[11971930231572094512] == 187
+    assert again.get_unique_values(q) == {118: len(q)}
+
+
 # ---------------------------------------------------------------- C-ABI error behaviour
 def test_abi_error_paths(ctx):
     """Every failure is a negative status + message, never an exception from the library or a crash."""
