@@ -4,7 +4,7 @@
 //   sgc_layout.cuh  constants, table slot layout, device scalars, tile-kernel argument block
 //   sgc_table.cuh   table primitives (probe sequence, CAS insert with build_mphf semantics, lookup)
 //   sgc_tile.cuh    segment staging + the warp-autonomous tile kernel (all fused modes)
-//   sgc_label8.cuh  the read-labelling kernel over the unitig-ordered side array (ASCII or 2-bit packed reads)
+//   sgc_labelseq.cuh  the read-labelling kernel over the unitig sequence store (ASCII or 2-bit packed reads)
 //   sgc_kernels.cuh plan / stand-alone table / label-tail / dominator / K7 / generator kernels
 //   sgc_mphf.cuh    BBHash (boomphf) level construction, rank samples, lookup
 //   sgc_feed.hpp    host-only feeder (BGZF inflate, FASTA/FASTQ scan, mate pairing)
@@ -73,7 +73,7 @@ int fail(int code, const char* fmt, ...) {
 #include "sgc_layout.cuh"
 #include "sgc_table.cuh"
 #include "sgc_tile.cuh"
-#include "sgc_label8.cuh"
+#include "sgc_labelseq.cuh"
 #include "sgc_kernels.cuh"
 #include "sgc_mphf.cuh"
 
@@ -111,13 +111,14 @@ struct sgc_table {
     uint32_t nlines = 0;
     int home_shift = 0;
     int64_t max_entries = 0;
-    // unitig-ordered side array of 64-bit hashes (tables built from sequences) + break bits
-    unsigned long long* side_alloc = nullptr;  // SIDE_PAD records of padding on either end
+    // unitig sequence store (tables built from sequences): every inserted sequence buffer, 2 bits per base,
+    // + one break bit per base position (sgc_labelseq.cuh)
+    bool store_on = false;
+    uint32_t* useq_alloc = nullptr;  // USEQ_PAD words of padding on either end
     uint32_t* brk = nullptr;
     int64_t brk_words = 0;
-    int64_t side_cap = 0, side_fill = 0;
-    bool side_dirty = false;
-    unsigned long long* side8() const { return side_alloc ? side_alloc + SIDE_PAD : nullptr; }
+    int64_t store_cap = 0, store_fill = 0;  // in bases; batches start at multiples of 64
+    uint32_t* useq() const { return useq_alloc ? useq_alloc + USEQ_PAD : nullptr; }
     // pending label call
     bool label_pending = false;
     int64_t label_nseq = 0;
@@ -561,7 +562,7 @@ void sgc_table_free(sgc_table* t) {
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
     if (t->buckets) cudaFree(t->buckets);
-    if (t->side_alloc) cudaFree(t->side_alloc);
+    if (t->useq_alloc) cudaFree(t->useq_alloc);
     if (t->brk) cudaFree(t->brk);
     delete t;
 }
@@ -570,31 +571,12 @@ int64_t sgc_table_bytes(const sgc_table* t) { return t ? (int64_t)t->nbuckets * 
 
 int sgc_table_enable_side(sgc_table* t) {
     if (!t) return fail(SGC_ERR_ARG, "table is NULL");
-    if (t->side_alloc) return SGC_OK;
-    sgc_ctx* c = t->ctx;
-    TRY(set_device(c));
-    const int64_t cap = std::max<int64_t>(t->max_entries, 64);
-    if (cap >= (int64_t)AUX_NONE) return fail(SGC_ERR_CAPACITY, "side array limited to 2^30-2 records");
-    const size_t side_bytes = (size_t)(cap + 2 * SIDE_PAD) * 8;
-    const int64_t words = ((cap + BRK_PAD + 31) >> 5) + 2;
-    cudaError_t e = cudaMalloc(&t->side_alloc, side_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&t->brk, (size_t)words * 4);
-    if (e != cudaSuccess) {
-        if (t->side_alloc) cudaFree(t->side_alloc);
-        t->side_alloc = nullptr;
-        t->brk = nullptr;
-        return fail(SGC_ERR_NOMEM, "cudaMalloc(%zu) for the side array failed: %s", side_bytes, cudaGetErrorString(e));
-    }
-    CU(cudaMemsetAsync(t->side_alloc, 0, side_bytes, c->stream));   // padding records (never inherited: break bits)
-    CU(cudaMemsetAsync(t->brk, 0xFF, (size_t)words * 4, c->stream));
-    t->brk_words = words;
-    t->side_cap = cap;
-    t->side_fill = 0;
+    t->store_on = true;  // allocated (and grown) by sgc_table_insert_sequences
     return SGC_OK;
 }
 
 int64_t sgc_table_side_bytes(const sgc_table* t) {
-    return t && t->side_alloc ? (t->side_cap + 2 * SIDE_PAD) * 8 + t->brk_words * 4 : 0;
+    return t && t->useq_alloc ? (t->store_cap / 16 + 2 * USEQ_PAD) * 4 + t->brk_words * 4 : 0;
 }
 
 int sgc_table_set_home_shift(sgc_table* t, int shift) {
@@ -602,6 +584,45 @@ int sgc_table_set_home_shift(sgc_table* t, int shift) {
     t->home_shift = shift;
     return SGC_OK;
 }
+
+namespace {
+// room for `bases` more positions in the table's sequence store (grows by reallocation; the break bits of
+// the new part start out set)
+int store_reserve(sgc_table* t, int64_t bases) {
+    sgc_ctx* c = t->ctx;
+    const int64_t need = t->store_fill + ((bases + 63) & ~(int64_t)63);
+    if (need + 64 >= (int64_t)AUX_NONE)
+        return fail(SGC_ERR_CAPACITY, "unitig sequence store limited to 2^30 bases per table (needs %lld)", (long long)need);
+    if (need <= t->store_cap) return SGC_OK;
+    int64_t cap = std::max<int64_t>(need, t->store_cap + t->store_cap / 2);
+    cap = std::min<int64_t>((cap + 1023) & ~(int64_t)1023, ((int64_t)AUX_NONE - 64) & ~(int64_t)63);
+    const int64_t uwords = cap / 16 + 2 * USEQ_PAD;
+    const int64_t bwords = ((cap + BRK_PAD + 31) >> 5) + 2;
+    uint32_t *nu = nullptr, *nb = nullptr;
+    CU(cudaStreamSynchronize(c->stream));
+    cudaError_t e = cudaMalloc(&nu, (size_t)uwords * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&nb, (size_t)bwords * 4);
+    if (e != cudaSuccess) {
+        if (nu) cudaFree(nu);
+        return fail(SGC_ERR_NOMEM, "cudaMalloc(%zu) for the unitig sequence store failed: %s", (size_t)uwords * 4,
+                    cudaGetErrorString(e));
+    }
+    CU(cudaMemsetAsync(nu, 0, (size_t)uwords * 4, c->stream));
+    CU(cudaMemsetAsync(nb, 0xFF, (size_t)bwords * 4, c->stream));
+    if (t->useq_alloc) {
+        CU(cudaMemcpyAsync(nu, t->useq_alloc, (size_t)(t->store_fill / 16 + USEQ_PAD) * 4, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(nb, t->brk, (size_t)((t->store_fill + BRK_PAD) >> 5) * 4, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(t->useq_alloc);
+        cudaFree(t->brk);
+    }
+    t->useq_alloc = nu;
+    t->brk = nb;
+    t->brk_words = bwords;
+    t->store_cap = cap;
+    return SGC_OK;
+}
+}  // namespace
 
 int sgc_table_insert_pairs(sgc_table* t, const uint64_t* d_hash, const uint32_t* d_id, int64_t n) {
     if (!t) return fail(SGC_ERR_ARG, "table is NULL");
@@ -611,7 +632,8 @@ int sgc_table_insert_pairs(sgc_table* t, const uint64_t* d_hash, const uint32_t*
     TRY(set_device(c));
     TRY(zero_scalars(c));
     insert_pairs_kernel<<<grid_for(n, 256, c->num_sms * 8), 256, 0, c->stream>>>(t->buckets, t->nbuckets, t->nlines,
-                                                                               t->home_shift, d_hash, d_id, n, c->d_scal);
+                                                                               t->home_shift, d_hash, d_id, n, c->d_scal,
+                                                                               t->brk);
     c->launches++;
     CU(cudaGetLastError());
     TRY(fetch_scalars(c));
@@ -628,28 +650,26 @@ int sgc_table_insert_sequences(sgc_table* t, const uint8_t* d_seq, int64_t seq_b
     if (nseq == 0) return SGC_OK;
     Plan p;
     TRY(make_plan(c, d_off, nseq, seq_bytes, k, nullptr, &p));
-    int64_t total = 0;
-    if (t->side_alloc) {
-        CU(cudaMemcpyAsync(&c->h_scal->n_unique, p.kmer_off + nseq, 8, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        total = c->h_scal->n_unique;
-        if (t->side_fill + total > t->side_cap || t->side_fill + total >= (int64_t)AUX_NONE)
-            return fail(SGC_ERR_CAPACITY, "side array of %lld records cannot take %lld more", (long long)t->side_cap,
-                        (long long)total);
+    if (t->store_on) {
+        // the batch's bases, 2 bits each, at the next 64-base boundary of the store; break bits cleared where a
+        // k-mer follows a k-mer of the same sequence (the insert kernel sets more: multicounts, repeats)
+        TRY(store_reserve(t, seq_bytes));
+        const int64_t nw = (seq_bytes + 15) / 16, nbw = (seq_bytes + 31) / 32;
+        useq_pack_kernel<<<grid_for(nw, 256, c->num_sms * 16), 256, 0, c->stream>>>(d_seq, seq_bytes, t->useq() + t->store_fill / 16, nw);
+        useq_brk_kernel<<<grid_for(nbw, 256, c->num_sms * 16), 256, 0, c->stream>>>(d_off, nseq, k, t->brk + ((t->store_fill + BRK_PAD) >> 5), nbw);
+        c->launches += 2;
+        CU(cudaGetLastError());
     }
     TRY(zero_scalars(c));
     TileArgs a = base_args(c, d_seq, d_off, k, p, d_status);
     table_args(a, t);
     a.seq_ids = d_ids;
     a.id_base = id_base;
-    a.side8 = t->side8();
-    a.side_base = (unsigned long long)t->side_fill;
+    a.brk = t->store_on ? t->brk : nullptr;
+    a.upos_base = (unsigned long long)t->store_fill;
     TRY(launch_tile<MODE_INSERT>(c, a));
     TRY(fetch_scalars(c));
-    if (t->side_alloc) {
-        t->side_fill += total;
-        t->side_dirty = true;
-    }
+    if (t->store_on) t->store_fill += (seq_bytes + 63) & ~(int64_t)63;
     return device_err_check(c);
 }
 
@@ -876,13 +896,13 @@ int sgc_lookup_sequences(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes, 
 namespace {
 
 template <int K, bool PACKED>
-int launch_label8_k(sgc_ctx* c, const Label8Args& a) {
-    const size_t smem = sizeof(WarpTile8<K>) * WPB8;
+int launch_labelseq_k(sgc_ctx* c, const LabelSeqArgs& a) {
+    const size_t smem = sizeof(WarpTileS<K, PACKED>) * WPBS;
     static thread_local int blocks_per_sm_of[64] = {0};
     int& blocks_per_sm = blocks_per_sm_of[c->device & 63];
     if (!blocks_per_sm) {
-        CU(cudaFuncSetAttribute(label8_kernel<K, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, label8_kernel<K, PACKED>, NT8, smem));
+        CU(cudaFuncSetAttribute(labelseq_kernel<K, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, labelseq_kernel<K, PACKED>, NTS, smem));
         if (blocks_per_sm < 1) return fail(SGC_ERR_CUDA, "label kernel does not fit on an SM (smem %zu)", smem);
     }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -896,7 +916,7 @@ int launch_label8_k(sgc_ctx* c, const Label8Args& a) {
         int v = atoi(lim);
         if (v >= 1 && v < ctas) ctas = v;
     }
-    label8_kernel<K, PACKED><<<c->num_sms * ctas, NT8, smem, c->stream>>>(a);
+    labelseq_kernel<K, PACKED><<<c->num_sms * ctas, NTS, smem, c->stream>>>(a);
     c->launches++;
     CU(cudaGetLastError());
     if (c->timing) {
@@ -907,31 +927,15 @@ int launch_label8_k(sgc_ctx* c, const Label8Args& a) {
 }
 
 template <bool PACKED>
-int launch_label8(sgc_ctx* c, const Label8Args& a) {
+int launch_labelseq(sgc_ctx* c, const LabelSeqArgs& a) {
     switch (a.k) {
-        case 21: return launch_label8_k<21, PACKED>(c, a);
-        case 31: return launch_label8_k<31, PACKED>(c, a);
-        default: return launch_label8_k<0, PACKED>(c, a);
+        case 21: return launch_labelseq_k<21, PACKED>(c, a);
+        case 31: return launch_labelseq_k<31, PACKED>(c, a);
+        default: return launch_labelseq_k<0, PACKED>(c, a);
     }
 }
 
-// break bits of the side array (once after the build; the ids are a temporary)
-int side_finalize(sgc_table* t) {
-    sgc_ctx* c = t->ctx;
-    if (!t->side_dirty) return SGC_OK;
-    const uint64_t n = (uint64_t)t->side_fill;
-    TRY(ensure(c, c->tmp_id, (size_t)std::max<uint64_t>(n, 1) * 4));
-    side_ids_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(t->buckets, t->nbuckets, t->nlines, t->home_shift, t->side8(), n,
-                                                          (uint32_t*)c->tmp_id.p);
-    side_brk_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>((const uint32_t*)c->tmp_id.p, n, BRK_PAD, t->brk,
-                                                          (uint64_t)t->brk_words);
-    c->launches += 2;
-    CU(cudaGetLastError());
-    t->side_dirty = false;
-    return SGC_OK;
-}
-
-bool use_side(const sgc_table* t) { return t->side_alloc && t->side_fill > 0 && !getenv("SGC_NO_SIDE"); }
+bool use_side(const sgc_table* t) { return t->useq_alloc && t->store_fill > 0 && !getenv("SGC_NO_SIDE"); }
 
 int label_common_prologue(sgc_table* t, int64_t nseq, int64_t ids_cap, unsigned long long* pairs_cap_out) {
     sgc_ctx* c = t->ctx;
@@ -942,7 +946,7 @@ int label_common_prologue(sgc_table* t, int64_t nseq, int64_t ids_cap, unsigned 
     return zero_scalars(c);
 }
 
-void label8_args(Label8Args& a, sgc_table* t, const uint8_t* seq, const Plan& p, int k, int32_t* d_status,
+void labelseq_args(LabelSeqArgs& a, sgc_table* t, const uint8_t* seq, const Plan& p, int k, int32_t* d_status,
                  unsigned long long pairs_cap) {
     sgc_ctx* c = t->ctx;
     memset(&a, 0, sizeof(a));
@@ -956,14 +960,14 @@ void label8_args(Label8Args& a, sgc_table* t, const uint8_t* seq, const Plan& p,
     a.nbuckets = t->nbuckets;
     a.nlines = t->nlines;
     a.home_shift = t->home_shift;
-    a.side8 = t->side8();
+    a.useq = t->useq();
     a.brk = t->brk;
     a.pairs = (unsigned long long*)c->pairs_a.p;
     a.pairs_cap = pairs_cap;
 }
 
-// the label8 kernel counts hits only: n_miss = (k-mers of the plan) - n_hits, computed on the device
-int label8_misses(sgc_ctx* c, const Plan& p, int64_t nseq) {
+// the labelseq kernel counts hits only: n_miss = (k-mers of the plan) - n_hits, computed on the device
+int labelseq_misses(sgc_ctx* c, const Plan& p, int64_t nseq) {
     misses_from_total_kernel<<<1, 1, 0, c->stream>>>(p.kmer_off + nseq, c->d_scal);
     c->launches++;
     CU(cudaGetLastError());
@@ -1040,16 +1044,15 @@ int sgc_label_reads_launch(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes
     if (d_status) CU(cudaMemsetAsync(d_status, 0, (size_t)nseq * 4, c->stream));
     const bool side = use_side(t);
     Plan p;
-    TRY(make_plan(c, d_off, nseq, seq_bytes, k, nullptr, &p, side ? SEG_K8 : SEG_K));
+    TRY(make_plan(c, d_off, nseq, seq_bytes, k, nullptr, &p, side ? SEG_KS : SEG_K));
     unsigned long long pairs_cap = 0;
     TRY(label_common_prologue(t, nseq, ids_cap, &pairs_cap));
     if (nseq > 0) {
         if (side) {
-            TRY(side_finalize(t));
-            Label8Args a;
-            label8_args(a, t, d_seq, p, k, d_status, pairs_cap);
-            TRY(launch_label8<false>(c, a));
-            TRY(label8_misses(c, p, nseq));
+            LabelSeqArgs a;
+            labelseq_args(a, t, d_seq, p, k, d_status, pairs_cap);
+            TRY(launch_labelseq<false>(c, a));
+            TRY(labelseq_misses(c, p, nseq));
         } else {
             TileArgs a = base_args(c, d_seq, d_off, k, p, d_status);
             table_args(a, t);
@@ -1089,16 +1092,15 @@ int sgc_label_reads_packed_launch(sgc_table* t, const uint8_t* d_packed, int64_t
     TRY(set_device(c));
     const bool side = use_side(t);
     Plan p;
-    TRY(make_packed_plan(c, d_len, uniform_len, nseq, packed_bytes, k, SEG_K8, !side, &p));
+    TRY(make_packed_plan(c, d_len, uniform_len, nseq, packed_bytes, k, SEG_KS, !side, &p));
     unsigned long long pairs_cap = 0;
     TRY(label_common_prologue(t, nseq, ids_cap, &pairs_cap));
     if (nseq > 0) {
         if (side) {
-            TRY(side_finalize(t));
-            Label8Args a;
-            label8_args(a, t, d_packed, p, k, nullptr, pairs_cap);
-            TRY(launch_label8<true>(c, a));
-            TRY(label8_misses(c, p, nseq));
+            LabelSeqArgs a;
+            labelseq_args(a, t, d_packed, p, k, nullptr, pairs_cap);
+            TRY(launch_labelseq<true>(c, a));
+            TRY(labelseq_misses(c, p, nseq));
         } else {
             // table without a side array (loaded from (hash, id) pairs): expand to ASCII, per-k-mer probing
             TRY(ensure(c, c->unpacked, (size_t)std::max<int64_t>(packed_bytes * 4, 16)));

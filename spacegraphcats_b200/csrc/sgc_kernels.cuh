@@ -62,11 +62,11 @@ __global__ void table_clear_kernel(Bucket* tbl, uint32_t nb) {
 
 __global__ void insert_pairs_kernel(Bucket* tbl, uint32_t nb, uint32_t nlines, int hs,
                                     const uint64_t* __restrict__ hash, const uint32_t* __restrict__ id, int64_t n,
-                                    Scalars* scal) {
+                                    Scalars* scal, uint32_t* brk) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         uint32_t v = id[i];
         if (v > SGC_MAX_ID) atomicOr(&scal->err, 2);
-        else table_insert(tbl, nb, nlines, hs, hash[i], v, AUX_NONE, scal);
+        else table_insert(tbl, nb, nlines, hs, hash[i], v, AUX_NONE, scal, brk);
     }
 }
 
@@ -146,28 +146,6 @@ __global__ void table_stats_kernel(const Bucket* tbl, uint32_t nb, Scalars* scal
 
 __global__ void misses_from_total_kernel(const int64_t* __restrict__ total, Scalars* scal) {
     scal->n_miss = (unsigned long long)*total - scal->n_hits;
-}
-
-// Side-array finalisation (after the build): ids[p] = what a table lookup of side8[p] returns ...
-__global__ void side_ids_kernel(const Bucket* tbl, uint32_t nb, uint32_t nlines, int hs,
-                                const unsigned long long* __restrict__ side8, uint64_t n, uint32_t* __restrict__ ids) {
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (uint64_t)gridDim.x * blockDim.x)
-        ids[g] = table_lookup(tbl, nb, nlines, hs, side8[g]);
-}
-// ... and the break bits: bit pad + p is set when p is outside [0, n), p == 0, or ids[p] != ids[p-1].
-// A k-mer that matches side8[q] may inherit the id found for side8[g] iff no break lies in (g, q]
-// (q > g) resp. (q, g] (q < g): then the table gives both hashes the same answer.
-__global__ void side_brk_kernel(const uint32_t* __restrict__ ids, uint64_t n, int pad, uint32_t* __restrict__ brk,
-                                uint64_t nwords) {
-    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t bits = 0;
-        for (int b = 0; b < 32; b++) {
-            const long long p = (long long)(w * 32 + b) - pad;
-            const bool brk_here = p <= 0 || p >= (long long)n || ids[p] != ids[p - 1];
-            bits |= (uint32_t)brk_here << b;
-        }
-        brk[w] = bits;
-    }
 }
 
 __global__ void table_export_kernel(const Bucket* tbl, uint32_t nb, uint64_t* hash_out, uint32_t* id_out,

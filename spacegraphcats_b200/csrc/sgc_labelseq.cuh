@@ -1,0 +1,536 @@
+// sgc_labelseq.cuh -- the read-labelling kernel (K1+K3+K4 fused: hash, table probe, per-read unitig ids)
+// for tables that carry the unitig SEQUENCE STORE, and the kernels that build the store.  Part of
+// libsgc_b200.so (device code; included by sgc_b200.cu only).  Reference semantics:
+// cdbg/index_reads.py:143-152 (hash_sequence + count_cdbg_matches per read; only the KEYS of the returned
+// dict are used).
+//
+// The idea: consecutive k-mers of a read are consecutive k-mers of a unitig, on either strand.  So only ONE
+// k-mer in sixteen (the anchor of a group) is hashed and looked up in the table.  Its slot says where that
+// k-mer lies in the table's store of unitig sequences (2 bits per base, every inserted sequence buffer
+// concatenated) and on which strand; the fifteen followers are settled by comparing the read's own 2-bit
+// bases with the store -- 46 bases, three 32-bit words, one XOR each.  A follower whose k bases equal the
+// store's has, by construction, the hash of that store position, and the BREAK bits say whether a table
+// lookup of that position's hash returns the anchor's id (brk[p] is set at the first k-mer of every
+// sequence, at every position that holds no k-mer, at every k-mer whose hash the table keeps under another
+// position, and at every dropped multicount hash -- set by the build, sgc_table.cuh:table_insert).  Whatever
+// is not settled that way -- sequencing errors, unitig ends, a missing anchor -- is queued and then hashed
+// and probed like an anchor, one item per lane.  The labels are therefore exactly those of per-k-mer probing
+// (tile_kernel<K, MODE_LABEL>), with a quarter of the hashes and of the table lines.
+//
+// Layout of the work
+//   * a warp round is SPW segments of <= 128 k-mers (a 150-bp read is one segment); its work items are the
+//     anchors of the round's groups followed by whatever they queue; 32 items per trip, every lane: locate,
+//     hash (2 x Murmur3 over the staged ASCII words, any byte alignment), probe the home bucket, then
+//     anchors: compare with the store and queue the unsettled followers; all: emit (sequence, id) keys.
+//   * PACKED = true: the reads arrive 2 bits per base (A=0 C=1 G=2 T=3, base b of a record in bits
+//     2(b%4).. of byte b/4, every record 16-byte aligned) and are expanded to the ASCII words the reference
+//     hash is defined on while they are staged (PRMT on "ACGT"); ASCII input is packed the other way.
+#pragma once
+#include "sgc_kmer.cuh"
+#include "sgc_table.cuh"
+#include "sgc_tile.cuh"
+
+namespace sgc {
+namespace dev {
+
+constexpr int SEG_KS = 128;   // k-mers per segment of the labelseq plan
+constexpr int GK = 16;        // k-mers per group: one anchor, fifteen followers
+constexpr int PAIRS_S = 64;   // candidate keys staged per warp before one global reservation
+constexpr int FOFF = 4;       // staged forward words start 4 words into their slot
+constexpr int USEQ_PAD = 8;   // words (128 bases) of zero padding on either end of the sequence store
+#ifndef SGC_LS_NT
+#define SGC_LS_NT 256
+#endif
+#ifndef SGC_LS_MIN_CTAS
+#define SGC_LS_MIN_CTAS 4
+#endif
+#ifndef SGC_LS_SPW
+#define SGC_LS_SPW 4
+#endif
+constexpr int NTS = SGC_LS_NT;    // threads per CTA of the labelseq kernel
+constexpr int WPBS = NTS / 32;
+
+template <int K, bool PACKED>
+struct GeoS {
+    static constexpr int KMAX = K ? K : SGC_MAX_K;
+    static constexpr int SPW = K ? SGC_LS_SPW : 4;                 // segments per warp round
+    static constexpr int LPS = 32 / SPW;                            // lanes staging one segment
+    static constexpr int SEGB = SEG_KS + KMAX - 1;                  // bases of a full segment
+    static constexpr int STRIDE = ((SEGB + 32 + 15) / 16) * 16;     // bytes per staged ASCII area
+    static constexpr int WPS = STRIDE / 4;
+    static constexpr int PWS = (SEGB + 15) / 16 + 4;                // 2-bit words per segment (+ slack for window reads)
+    static constexpr int RAWW = PACKED ? ((SEGB + 63) / 64) * 4 : WPS;  // words of the raw copy of a segment
+    static constexpr int QCAP = SPW * SEG_KS;                       // a round queues at most its own k-mers
+    static_assert(32 % SPW == 0, "lanes per segment");
+};
+
+struct LabelSeqArgs {
+    const uint8_t* seq;       // ASCII bases, or packed 2-bit records
+    const SegDesc* segdesc;
+    const int64_t* nsegs_p;
+    int32_t* status;          // ASCII only (packed input is validated by the packer)
+    Scalars* scal;
+    int k;
+    const Bucket* tbl;
+    uint32_t nbuckets;
+    uint32_t nlines;
+    int home_shift;
+    const uint32_t* useq;     // word of store position 0 (USEQ_PAD words of padding before it)
+    const uint32_t* brk;      // bit BRK_PAD + p = break before position p
+    unsigned long long* pairs;
+    unsigned long long pairs_cap;
+};
+
+template <int K, bool PACKED>
+struct alignas(16) WarpTileS {
+    using G = GeoS<K, PACKED>;
+    uint32_t F[G::SPW * G::WPS];
+    uint32_t R[G::SPW * G::WPS];
+    uint32_t RAW[G::SPW * G::RAWW];
+    uint32_t P[G::SPW * G::PWS];       // the round's segments, 2 bits per base
+    SegDesc D[3][G::SPW];
+    unsigned long long pairs[PAIRS_S];
+    unsigned short q[G::QCAP];         // queued k-mers of this round: segment << 8 | k-mer index
+    int gpre[G::SPW + 1];
+    unsigned qfill;
+    unsigned segbad;                   // bit sg: segment sg holds a byte that is not A/C/G/T (ASCII input)
+    unsigned pad_[1];
+};
+
+// the walk past a full home bucket, out of line
+__device__ __noinline__ uint32_t lookup_slow_call(const Bucket* tbl, uint32_t nlines, uint32_t hb, uint64_t h, uint32_t* aux) {
+    uint32_t ax = AUX_NONE;
+    const uint32_t v = lookup_slow(tbl, nlines, hb, h, ax);
+    *aux = ax;
+    return v;
+}
+
+// 16 packed bases (one 32-bit word, 2 bits each) -> four words of ASCII
+__device__ __forceinline__ uint4 expand_packed16(uint32_t x) {
+    auto spread = [](uint32_t h) {  // 16 bits -> 8 nibbles holding one 2-bit code each
+        uint32_t t = (h | (h << 8)) & 0x00FF00FFu;
+        t = (t | (t << 4)) & 0x0F0F0F0Fu;
+        return (t | (t << 2)) & 0x33333333u;
+    };
+    const uint32_t lo = spread(x & 0xFFFFu), hi = spread(x >> 16);
+    const uint32_t acgt = 0x54474341u;  // "ACGT"
+    return make_uint4(__byte_perm(acgt, 0u, lo), __byte_perm(acgt, 0u, lo >> 16), __byte_perm(acgt, 0u, hi),
+                      __byte_perm(acgt, 0u, hi >> 16));
+}
+
+// four ASCII bases -> 8 bits (A=0 C=1 G=2 T=3; any other byte gives some code: the caller knows it is invalid)
+__host__ __device__ __forceinline__ uint32_t pack_ascii4(uint32_t u) {
+    const uint32_t c = ((u >> 1) & 0x03030303u) ^ ((u >> 2) & 0x01010101u);
+    return (c | (c >> 6) | (c >> 12) | (c >> 18)) & 0xFFu;
+}
+
+// ----------------------------------------------------------------------------------
+// build side of the sequence store
+// ----------------------------------------------------------------------------------
+// word w of the batch = bases [16w, 16w+16) of its ASCII buffer (bytes past the end read as 'A')
+__global__ void useq_pack_kernel(const uint8_t* __restrict__ seq, int64_t seq_bytes, uint32_t* __restrict__ out, int64_t nwords) {
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t x = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t u = 0x41414141u;
+            const int64_t b = 16 * w + 4 * j;
+            if (b + 4 <= seq_bytes && ((uintptr_t)(seq + b) & 3) == 0) u = __ldg(reinterpret_cast<const uint32_t*>(seq + b));
+            else {
+                u = 0;
+                for (int t = 0; t < 4; t++) u |= (uint32_t)(b + t < seq_bytes ? seq[b + t] : (uint8_t)'A') << (8 * t);
+            }
+            x |= pack_ascii4(u) << (8 * j);
+        }
+        out[w] = x;
+    }
+}
+
+// break bits of one batch: cleared exactly where position p and p-1 are k-mers of the same sequence (the build
+// kernel sets more of them afterwards: table_insert).  word0 = first break word of the batch (its bit 0 = byte 0
+// of the batch's sequence buffer), nwords = words covering the buffer.
+__global__ void useq_brk_kernel(const int64_t* __restrict__ off, int64_t nseq, int k, uint32_t* __restrict__ brk_words, int64_t nwords) {
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t o0 = 32 * w;
+        int64_t lo = -1, hi = nseq;  // largest s with off[s] <= o0 (-1 if none)
+        while (hi - lo > 1) {
+            const int64_t mid = lo + (hi - lo) / 2;
+            if (off[mid] <= o0) lo = mid; else hi = mid;
+        }
+        int64_t s = lo;
+        uint32_t bits = 0xFFFFFFFFu;
+        for (int b = 0; b < 32; b++) {
+            const int64_t o = o0 + b;
+            while (s + 1 < nseq && off[s + 1] <= o) s++;
+            if (s >= 0) {
+                const int64_t r = o - off[s], nk = off[s + 1] - off[s] - k + 1;
+                if (r >= 1 && r < nk) bits &= ~(1u << b);
+            }
+        }
+        brk_words[w] = bits;
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// the kernel
+// ----------------------------------------------------------------------------------
+template <int K, bool PACKED>
+__global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const LabelSeqArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using G = GeoS<K, PACKED>;
+    constexpr int SPW = G::SPW, LPS = G::LPS, WPS = G::WPS, PWS = G::PWS, RAWW = G::RAWW;
+    const int lane = threadIdx.x & 31;
+    using Tile = WarpTileS<K, PACKED>;
+    Tile& wt = reinterpret_cast<Tile*>(smem_raw)[threadIdx.x >> 5];
+    const int k = K ? K : a.k;
+    const int64_t nsegs = *a.nsegs_p;
+    const int64_t nrounds = (nsegs + SPW - 1) / SPW;
+    unsigned my_hits = 0;                // per lane: a launch is far below 2^32 k-mers per lane
+    unsigned pair_fill = 0;              // warp-uniform: keys waiting in wt.pairs
+
+    auto flush_pairs = [&]() {  // cold: out of line
+        flush_pairs_out(a.scal, a.pairs, a.pairs_cap, wt.pairs, pair_fill, lane);
+        pair_fill = 0;
+    };
+    // one candidate (sequence, id) key per lane at most; the order of the keys is irrelevant (they are
+    // grouped per sequence by the label tail)
+    auto push_key = [&](bool has, unsigned long long key) {
+        const unsigned m = __ballot_sync(0xffffffffu, has);
+        if (m) {
+            const unsigned total = __popc(m);
+            if (pair_fill + total > PAIRS_S) flush_pairs();
+            if (has) wt.pairs[pair_fill + __popc(m & ((1u << lane) - 1u))] = key;
+            pair_fill += total;
+        }
+    };
+
+    unsigned round_spare = 0xFFFFFFFFu;
+    auto claim_round = [&]() -> unsigned {  // rounds are claimed two at a time
+        if (round_spare != 0xFFFFFFFFu) {
+            const unsigned r = round_spare;
+            round_spare = 0xFFFFFFFFu;
+            return r;
+        }
+        unsigned r = 0;
+        if (lane == 0) r = atomicAdd(&a.scal->round_ctr, 2u);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        round_spare = r + 1u;
+        return r;
+    };
+    auto prefetch_desc = [&](int slot, unsigned round) {
+        if (lane < 2 * SPW) {
+            const int sgi = lane >> 1, half = lane & 1;
+            const int64_t g = (int64_t)round * SPW + sgi;
+            unsigned char* dst = reinterpret_cast<unsigned char*>(&wt.D[slot][sgi]) + 16 * half;
+            if ((int64_t)round < nrounds && g < nsegs) {
+                cp_async16(dst, reinterpret_cast<const unsigned char*>(a.segdesc + g) + 16 * half);
+            } else {
+                *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);  // nk = 0: nothing to do
+            }
+        }
+    };
+    auto prefetch_raw = [&](int slot) {
+        const int sgi = lane / LPS, sub = lane % LPS;
+        const SegDesc& d = wt.D[slot][sgi];
+        if (d.nk > 0) {
+            const int Ls = d.nk + k - 1;
+            if constexpr (PACKED) {  // records are 16-byte aligned and a segment starts 32 bytes after the last
+                const int nchunks = (((Ls + 3) >> 2) + 15) >> 4;
+                unsigned char* dst = reinterpret_cast<unsigned char*>(wt.RAW + sgi * RAWW);
+                const unsigned char* src = a.seq + d.start;
+                for (int c = sub; c < nchunks; c += LPS) cp_async16(dst + 16 * c, src + 16 * c);
+            } else {
+                const uintptr_t g0 = (uintptr_t)a.seq + (uintptr_t)d.start;
+                const uintptr_t a0 = g0 & ~(uintptr_t)15;
+                const int nchunks = (int)(((g0 + (uintptr_t)Ls + 15) & ~(uintptr_t)15) - a0) >> 4;
+                unsigned char* dst = reinterpret_cast<unsigned char*>(wt.RAW + sgi * RAWW) + 16;
+                for (int c = sub; c < nchunks; c += LPS)
+                    cp_async16(dst + 16 * c, reinterpret_cast<const void*>(a0 + 16 * (uintptr_t)c));
+            }
+        }
+    };
+
+    unsigned rq0 = claim_round(), rq1 = claim_round(), rq2 = claim_round();
+    prefetch_desc(0, rq0);
+    prefetch_desc(1, rq1);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncwarp();
+    prefetch_raw(0);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncwarp();
+
+    for (unsigned it = 0;; it++) {
+        const unsigned round = rq0;
+        if ((int64_t)round >= nrounds) break;
+        const int cur = it % 3;
+        const int nxt = (it + 1) % 3, nx2 = (it + 2) % 3;
+        prefetch_desc(nx2, rq2);  // descriptors of the round after next
+        cp_async_commit();
+        rq0 = rq1;
+        rq1 = rq2;
+        rq2 = claim_round();
+
+        // ---- group prefix of this round's segments ----
+        {
+            const int nk = lane < SPW ? wt.D[cur][lane].nk : 0;
+            int incl = (nk + GK - 1) / GK;
+#pragma unroll
+            for (int d = 1; d < SPW; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            if (lane < SPW) wt.gpre[lane + 1] = incl;
+            if (lane == 0) {
+                wt.gpre[0] = 0;
+                wt.qfill = 0;
+                wt.segbad = 0;
+            }
+        }
+        __syncwarp();
+
+        // ---- stage forward + reverse-complement ASCII words and the 2-bit words (LPS lanes per segment) ----
+        {
+            const int sg = lane / LPS, sub = lane % LPS;
+            const SegDesc& d = wt.D[cur][sg];
+            const int nk = d.nk;
+            const int Ls = nk + k - 1;
+            uint32_t* Fs = wt.F + sg * WPS + FOFF;
+            uint32_t* Ps = wt.P + sg * PWS;
+            const int npw = (Ls + 15) >> 4;
+            if (nk) {
+                if constexpr (PACKED) {
+                    const uint32_t* pk = wt.RAW + sg * RAWW;
+                    for (int j = sub; j < npw; j += LPS) {
+                        const uint32_t x = pk[j];
+                        Ps[j] = x;
+                        *reinterpret_cast<uint4*>(Fs + 4 * j) = expand_packed16(x);
+                    }
+                } else {
+                    const int r0 = (int)(((uintptr_t)a.seq + (uintptr_t)d.start) & 15);
+                    const int s = r0 & 3;
+                    const uint32_t* rw0 = wt.RAW + sg * RAWW + 4 + (r0 >> 2);  // raw copies start 16 bytes into their slot
+                    uint32_t bad = 0;
+                    for (int w = sub; 4 * w < Ls; w += LPS) {
+                        const uint32_t u = sgc::funnel_bytes(rw0[w], rw0[w + 1], s);
+                        Fs[w] = u;
+                        // every byte must be one of A C G T: "ACTG"[bits 1..2 of the byte] == the byte
+                        const uint32_t code = (u >> 1) & 0x03030303u;
+                        const uint32_t sel = __byte_perm(code | (code >> 4), 0u, 0x4420u);
+                        const int nval = Ls - 4 * w;
+                        const uint32_t mask = nval >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nval)) - 1u);
+                        bad |= (__byte_perm(0x47544341u, 0u, sel) ^ u) & mask;
+                    }
+                    if (bad) {
+                        if (a.status) atomicOr(&a.status[d.seq], 1);
+                        atomicOr(&wt.segbad, 1u << sg);  // its followers are hashed like everybody else
+                    }
+                }
+            }
+            __syncwarp();
+            if (nk) {
+                // R word m holds R[4m-4-p .. +4) = reverse complement of F[Ls-4m+p .. +4)
+                const int p = sgc::rc_pad(nk);
+                const int nrw = (Ls + 4 + p + 3) >> 2;
+                uint32_t* Rs = wt.R + sg * WPS;
+                const uint32_t* Fw = wt.F + sg * WPS;  // F byte f lives at byte 16 + f of this slot (f >= -7 here)
+                for (int m = sub; m < nrw; m += LPS) {
+                    const int b = 16 + Ls - 4 * m + p;
+                    const uint32_t u = sgc::funnel_bytes(Fw[b >> 2], Fw[(b >> 2) + 1], b & 3);
+                    // complement and reverse in one PRMT: nibbles of the selector = the 2-bit codes, last base first
+                    const uint32_t code = (u >> 1) & 0x03030303u;
+                    const uint32_t sel = __byte_perm(code | (code << 12), 0u, 0x4413u);
+                    Rs[m] = __byte_perm(0x43414754u, 0u, sel);  // "TGAC"[code]
+                }
+                if constexpr (!PACKED) {
+                    for (int j = sub; j < npw; j += LPS)
+                        Ps[j] = pack_ascii4(Fs[4 * j]) | (pack_ascii4(Fs[4 * j + 1]) << 8) | (pack_ascii4(Fs[4 * j + 2]) << 16) |
+                                (pack_ascii4(Fs[4 * j + 3]) << 24);
+                }
+            }
+        }
+        __syncwarp();
+        prefetch_raw(nxt);  // lands while this round is worked on
+        cp_async_commit();
+
+        // ---- the round's work items: anchors [0, ng), then the queue ----
+        // warp-uniform state is re-read from shared memory where it is used (volatile: not hoisted)
+        const volatile int* gpre = wt.gpre;
+        const volatile unsigned* qfill_p = &wt.qfill;
+        // (a trip takes the next <= 32 items that exist when it starts; what it queues is seen by the next one)
+        for (int t0 = 0, t1 = 0;; t0 = t1) {
+            const int ng = gpre[SPW];
+            const int nq = (int)*qfill_p;
+            if (t0 >= ng + nq) break;
+            t1 = t0 + 32 < ng + nq ? t0 + 32 : ng + nq;
+            const int item = t0 + lane;
+            const bool act = item < ng + nq, anchor = item < ng;
+            int sg = 0, q = 0;
+            if (anchor) {
+#pragma unroll
+                for (int s = 1; s < SPW; s++) sg += item >= gpre[s];
+                q = (item - gpre[sg]) * GK;
+            } else if (act) {
+                const unsigned u = wt.q[item - ng];
+                sg = (int)(u >> 8);
+                q = (int)(u & 0xFFu);
+            }
+            const SegDesc& d = wt.D[cur][sg];
+            const int nk = d.nk;
+            const uint32_t* Fs = wt.F + sg * WPS + FOFF;
+            const uint32_t* Rs = wt.R + sg * WPS;
+
+            // hash of k-mer q of segment sg (idle lanes hash k-mer 0 of segment 0: staged or stale words, unused)
+            uint64_t hf, hr;
+            const int rb = sgc::rc_byte_of(nk, nk - 1 - q);
+            if constexpr (K != 0) {
+                hf = sgc::murmur3_h1_window<K ? K : 1>(Fs + (q >> 2), q & 3);
+                hr = sgc::murmur3_h1_window<K ? K : 1>(Rs + (rb >> 2), rb & 3);
+            } else {
+                hf = act ? sgc::murmur3_h1_stream(Fs, q, k) : 0ULL;
+                hr = act ? sgc::murmur3_h1_stream(Rs, rb, k) : 0ULL;
+            }
+            const uint64_t h = hf ^ hr;
+            const uint32_t hb = act ? home_bucket(h, a.nbuckets, a.home_shift) : 0u;
+            Entry e0, e1;
+            load_bucket_nc(a.tbl + hb, e0, e1);  // idle lanes probe bucket 0 (an L2 hit)
+            uint32_t v = SGC_MISS, aux = AUX_NONE;
+            if (act) {
+                if (!bucket_match(e0, e1, h, v, aux)) {
+                    v = SGC_MISS;
+                    aux = AUX_NONE;
+                    if (bucket_overflowed(e0)) v = lookup_slow_call(a.tbl, a.nlines, hb, h, &aux);
+                }
+            }
+            unsigned nhit = v != SGC_MISS;
+
+            if (t0 < ng) {  // warp-uniform: this trip holds anchors
+                unsigned pending = 0;
+                if (anchor) {
+                    const int nv = nk - q < GK ? nk - q : GK;
+                    const unsigned valid = (1u << nv) - 1u;
+                    const uint32_t gp = aux & AUX_MASK;
+                    const bool has_g = v != SGC_MISS && gp != AUX_NONE && !((wt.segbad >> sg) & 1u);
+                    unsigned m = 1u;
+                    if (has_g) {
+                        const bool along = ((aux & ORI_BIT) != 0) == (hf < hr);
+                        // break bits of positions gp-15 .. gp+16
+                        const uint32_t bi = gp + (uint32_t)(BRK_PAD - (GK - 1));
+                        const uint32_t w0 = __ldg(a.brk + (bi >> 5)), w1 = __ldg(a.brk + (bi >> 5) + 1);
+                        unsigned clean;
+                        if constexpr (K != 0) {
+                            constexpr int WL = GK - 1 + (K ? K : 1);   // bases of a full window
+                            constexpr int NWD = (WL + 15) / 16;
+                            static_assert(NWD <= 3 || K == 0, "window words");
+                            const uint32_t* Pw = wt.P + sg * PWS + (q >> 4);  // q % 16 == 0
+                            const int wsi = (int)gp - (along ? 0 : GK - 1);     // first store position of the window
+                            const uint32_t* up = a.useq + (wsi >> 4);
+                            const int sh = 2 * (wsi & 15);
+                            uint32_t u[NWD + 1], un[NWD], rd[NWD];
+#pragma unroll
+                            for (int j = 0; j <= NWD; j++) u[j] = __ldg(up + j);
+#pragma unroll
+                            for (int j = 0; j < NWD; j++) {
+                                rd[j] = Pw[j];
+                                un[j] = __funnelshift_r(u[j], u[j + 1], sh);
+                            }
+                            if (!along) {  // reverse complement of the WL-base window
+                                uint32_t r[NWD + 1];
+#pragma unroll
+                                for (int j = 0; j < NWD; j++) r[j] = __brev(un[NWD - 1 - j]);
+                                r[NWD] = 0u;
+                                constexpr int RS = 32 * NWD - 2 * WL;
+#pragma unroll
+                                for (int j = 0; j < NWD; j++) {
+                                    const uint32_t x = __funnelshift_r(r[j], r[j + 1], RS);
+                                    un[j] = ~(((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1));
+                                }
+                            }
+                            // mismatching bases among the nv-1+K the group really has: first (f) and last (l)
+                            const int wn = nv - 1 + K;
+                            int f = WL + GK, l = -1;
+#pragma unroll
+                            for (int j = NWD - 1; j >= 0; j--) {
+                                uint32_t x = rd[j] ^ un[j];
+                                x = (x | (x >> 1)) & 0x55555555u;
+                                const int nb = wn - 16 * j;
+                                if (nb < 16) x &= nb > 0 ? (1u << (2 * nb)) - 1u : 0u;
+                                if (x) {
+                                    f = 16 * j + ((__ffs((int)x) - 1) >> 1);
+                                    if (l < 0) l = 16 * j + ((31 - __clz((int)x)) >> 1);
+                                }
+                            }
+                            // follower d is clean when its k bases avoid every mismatch: d + K - 1 < f, or d > l
+                            const unsigned clean_a = f >= K ? (f - K + 1 >= GK ? 0xFFFFu : (1u << (f - K + 1)) - 1u) : 0u;
+                            const unsigned clean_b = l < 0 ? 0xFFFFu : (l >= GK - 1 ? 0u : (0xFFFFu << (l + 1)) & 0xFFFFu);
+                            clean = clean_a | clean_b;
+                        } else {
+                            // any k: walk the bases until the first mismatch
+                            const uint32_t* Pw = wt.P + sg * PWS;
+                            const int wn = nv - 1 + k;
+                            int f = wn;
+                            for (int j = 0; j < wn; j++) {
+                                const int rbp = q + j;
+                                const uint32_t rbase = (Pw[rbp >> 4] >> (2 * (rbp & 15))) & 3u;
+                                const int pos = along ? (int)gp + j : (int)gp + k - 1 - j;
+                                uint32_t ub = (__ldg(a.useq + (pos >> 4)) >> (2 * (pos & 15))) & 3u;
+                                if (!along) ub ^= 3u;
+                                if (rbase != ub) {
+                                    f = j;
+                                    break;
+                                }
+                            }
+                            clean = f >= k ? (f - k + 1 >= GK ? 0xFFFFu : (1u << (f - k + 1)) - 1u) : 0u;
+                        }
+                        const uint32_t bits = __funnelshift_r(w0, w1, bi & 31u);  // bit b = position gp-15+b
+                        // followers 1..lim may inherit: no break in (gp, gp+d] resp. (gp-d, gp]
+                        const unsigned lim = along ? (unsigned)__ffs((int)((bits >> 16) | 0x8000u)) - 1u
+                                                   : (unsigned)__clz((int)((bits << 16) | 0x10000u));
+                        m = ((clean & ((2u << lim) - 1u)) | 1u) & valid;
+                        nhit = (unsigned)__popc(m);
+                    }
+                    pending = valid & ~m;
+                }
+                // queue what the store did not settle (in item order: a read's k-mers stay neighbours)
+                const int cnt = __popc(pending);
+                int incl = cnt;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const int x = __shfl_up_sync(0xffffffffu, incl, dd);
+                    if (lane >= dd) incl += x;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                if (total) {
+                    int pos = nq + incl - cnt;
+                    while (pending) {
+                        const int dd = __ffs((int)pending) - 1;
+                        pending &= pending - 1u;
+                        wt.q[pos++] = (unsigned short)((sg << 8) | (q + dd));
+                    }
+                    __syncwarp();
+                    if (lane == 0) wt.qfill = (unsigned)(nq + total);
+                }
+            }
+            my_hits += nhit;
+            // a hit is a candidate label unless the previous item gives the same (sequence, id)
+            const unsigned long long key = ((unsigned long long)d.seq << 32) | v;
+            const unsigned long long prevk = __shfl_up_sync(0xffffffffu, key, 1);
+            push_key(v != SGC_MISS && !(lane > 0 && prevk == key), key);
+            __syncwarp();
+        }
+
+        cp_async_wait_all();  // next round's bytes, next-next descriptors
+        __syncwarp();
+    }
+    cp_async_wait_all();
+
+    if (pair_fill) flush_pairs();
+    unsigned long long hits = my_hits;  // the host derives the misses from the plan's k-mer total
+#pragma unroll
+    for (int dd = 16; dd > 0; dd >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, dd);
+    if (lane == 0 && hits) atomicAdd(&a.scal->n_hits, hits);
+}
+
+}  // namespace dev
+}  // namespace sgc

@@ -49,16 +49,16 @@ struct Geo {
 // when it arrived and slots are never freed, so a walk stops at the first bucket that is not
 // full -- and it only starts if the home bucket's overflow bit says that some key homed there
 // lives elsewhere (a miss in an un-flagged home bucket costs ONE sector even when it is full).
-// aux[29:0] = index of the k-mer in the table's unitig-ordered side array (AUX_NONE if none);
+// aux[29:0] = position of the k-mer's first base in the table's unitig sequence store (AUX_NONE if none);
 // aux[30] = orientation of the k-mer as stored: set when Murmur3(kmer) < Murmur3(revcomp(kmer)) for
 // the k-mer as it is written in its unitig.  A read k-mer with the same hash and the same bit lies on
 // the unitig's strand (its successors are at g+1, g+2, ...), with the opposite bit on the other strand
-// (g-1, g-2, ...), so only one direction of side records has to be fetched;
+// (g-1, g-2, ...), so the read is compared with the store in one direction only;
 // aux[31] of slot 0 = the bucket's overflow bit.
 struct __align__(16) Entry {
     unsigned long long key;
     unsigned int val;  // VAL_EMPTY = free slot, VAL_MULTI = dropped hash, else unitig id
-    unsigned int aux;  // side-array position (30 bits) | orientation bit | overflow bit (slot 0)
+    unsigned int aux;  // sequence-store position (30 bits) | orientation bit | overflow bit (slot 0)
 };
 constexpr uint32_t AUX_NONE = 0x3FFFFFFFu;   // as a position: "no side record"
 constexpr uint32_t AUX_MASK = 0x3FFFFFFFu;
@@ -118,9 +118,9 @@ struct TileArgs {
     int home_shift;
     const uint32_t* seq_ids;
     uint32_t id_base;
-    // side array (unitig-ordered 64-bit hashes): written by MODE_INSERT, read by label8_kernel
-    unsigned long long* side8;
-    unsigned long long side_base;   // MODE_INSERT: first record of this batch
+    // unitig sequence store (sgc_labelseq.cuh): MODE_INSERT records every k-mer's store position in its slot
+    uint32_t* brk;                  // break bits of the store (NULL: table without a store)
+    unsigned long long upos_base;   // MODE_INSERT: store position of byte 0 of this batch's sequence buffer
     // MODE_LOOKUP
     uint32_t* kmer_ids;
     uint32_t* count_by_id;

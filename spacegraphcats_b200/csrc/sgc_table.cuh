@@ -109,14 +109,27 @@ __device__ __forceinline__ uint32_t table_lookup(const Bucket* tbl, uint32_t nb,
     return table_lookup(tbl, nb, nlines, hs, h, aux);
 }
 
+// break bit of store position p (sgc_labelseq.cuh): set = "a k-mer that sequence-matches position p must not
+// inherit the id found for position p-1 (resp. p+1 when walking down)"
+constexpr int BRK_PAD = 32;  // bit index of position 0 in the break-bit array
+__device__ __forceinline__ void brk_mark(uint32_t* brk, uint32_t pos) {
+    const uint32_t b0 = pos + (uint32_t)BRK_PAD, b1 = b0 + 1u;
+    atomicOr(brk + (b0 >> 5), 1u << (b0 & 31u));
+    atomicOr(brk + (b1 >> 5), 1u << (b1 & 31u));
+}
+
 // build_mphf insertion semantics (cdbg/index_cdbg_by_kmer.py:40-57, 88-89):
 //   new hash -> stored with id;  same hash, same id -> no-op;
 //   same hash, different id -> the hash is dropped for good (VAL_MULTI).
 // The outcome is independent of the order in which threads arrive: slots only ever go from
 // empty to occupied, every thread walks the same probe sequence, and a lost CAS re-examines
 // what the winner wrote.
+// brk (nullable) = break bits of the table's unitig sequence store: a k-mer whose hash is already in the
+// table under another position fences its own position off (it is not the one the slot points to), and a
+// hash that becomes a multicount fences the slot's position off too -- so whatever lies between two break
+// bits is a run of k-mers whose slots point at themselves and hold their unitig's id.
 __device__ void table_insert(Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, uint64_t h, uint32_t id, uint32_t aux,
-                             Scalars* scal) {
+                             Scalars* scal, uint32_t* brk = nullptr) {
     const uint32_t hb = home_bucket(h, nb, hs);
     const Entry empty{0ULL, VAL_EMPTY, 0u};
     const Entry mine{h, id, aux & (AUX_MASK | ORI_BIT)};
@@ -137,7 +150,12 @@ __device__ void table_insert(Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, 
                 e = old;  // somebody else claimed the slot first: examine what they wrote
             }
             if (e.key == h) {
-                if (e.val != id && e.val != VAL_MULTI) atomicExch(&bp->e[s].val, VAL_MULTI);
+                const uint32_t mypos = aux & AUX_MASK, slotpos = e.aux & AUX_MASK;
+                if (brk && mypos != AUX_NONE && mypos != slotpos) brk_mark(brk, mypos);
+                if (e.val != id) {
+                    if (e.val != VAL_MULTI) atomicExch(&bp->e[s].val, VAL_MULTI);
+                    if (brk && slotpos != AUX_NONE) brk_mark(brk, slotpos);
+                }
                 return;
             }
         }

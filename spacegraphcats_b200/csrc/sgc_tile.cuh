@@ -307,6 +307,12 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                     all_ok &= ok;
                 }
                 if (!all_ok && a.status) atomicOr(&a.status[wt.seq[sg]], 1);
+                if constexpr (MODE == MODE_INSERT) {
+                    // a unitig with a byte that is not A/C/G/T has no 2-bit form: nothing may be matched against
+                    // this stretch of the sequence store (its k-mers are still found by their hashes)
+                    if (!all_ok && a.brk)
+                        for (int q = 0; q <= nk; q++) brk_mark(a.brk, (uint32_t)(a.upos_base + (unsigned long long)(wt.start[sg] + q)));
+                }
             }
         }
         __syncwarp();
@@ -428,14 +434,13 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                     uint32_t id = a.seq_ids ? a.seq_ids[sq] : a.id_base + (uint32_t)sq;
                     if (id > SGC_MAX_ID) atomicOr(&a.scal->err, 2);
                     else {
-                        const unsigned long long g0 = a.side_base + (unsigned long long)(wt.kout[sg] + i);
+                        // position of the k-mer in the table's unitig sequence store = store offset of this batch
+                        // + byte offset of its first base in the batch (sgc_labelseq.cuh matches reads against it)
+                        const unsigned long long g0 = a.upos_base + (unsigned long long)(wt.start[sg] + i);
                         for (int t = 0; t < nv; t++) {
                             uint32_t aux = AUX_NONE;
-                            if (a.side8) {  // unitig-ordered record of the hash (sgc_label8.cuh reads them)
-                                aux = (uint32_t)(g0 + t) | (((ori >> t) & 1u) ? ORI_BIT : 0u);
-                                a.side8[g0 + t] = h[t];
-                            }
-                            table_insert(a.tbl, a.nbuckets, a.nlines, a.home_shift, h[t], id, aux, a.scal);
+                            if (a.brk) aux = (uint32_t)(g0 + t) | (((ori >> t) & 1u) ? ORI_BIT : 0u);
+                            table_insert(a.tbl, a.nbuckets, a.nlines, a.home_shift, h[t], id, aux, a.scal, a.brk);
                         }
                     }
                 }
