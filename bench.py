@@ -254,8 +254,8 @@ def workload_config(args, cpu=False):
         "read_format": "ASCII (1 byte per base + int64 offsets)" if args.ascii else
                        "2-bit packed, 48 bytes per 150-bp read (the host feeder's output; expanded to ASCII in the kernel)",
         "label_kernel": "per-k-mer probes (SGC_NO_SIDE)" if os.environ.get("SGC_NO_SIDE") else
-                        "label8: one table probe per 8 k-mers + unitig-ordered side array of 64-bit hashes",
-        "l2": "inputs (0.8 GB packed reads/step, 27 GB table + 4 GB side array) far larger than the 126 MB L2; no flush needed",
+                        "labelseq: one hashed+probed anchor per 16 k-mers, followers settled by comparing the read's 2-bit bases with the table's unitig sequence store; unsettled k-mers hashed+probed one per lane",
+        "l2": "inputs (0.8 GB packed reads/step, 27 GB table + 0.3 GB unitig sequence store) far larger than the 126 MB L2; no flush needed",
     }
 
 
@@ -583,7 +583,7 @@ def main():
     table._dev = dev_table  # the product object whose streaming API the e2e arm calls
     live, multi, max_id = dev_table.stats()
     TABLE_BYTES.append(dev_table.nbytes + dev_table.side_nbytes)
-    log("[rank %d] cDBG: %d unitigs, table %d live hashes (%d multicount) in %.2f GB (+%.2f GB side array), built in %.1fs"
+    log("[rank %d] cDBG: %d unitigs, table %d live hashes (%d multicount) in %.2f GB (+%.2f GB unitig sequence store), built in %.1fs"
         % (rank, cdbg.n_unitigs, live, multi, dev_table.nbytes / 1e9, dev_table.side_nbytes / 1e9, time.time() - t0))
     nb = max(1, min(args.distinct_batches, args.steps + args.warmup))
     n_reads = args.batch_reads
@@ -762,7 +762,7 @@ def main():
     roofline = {
         "bound": "hbm",
         "kernel": "tile_kernel<31, MODE_LABEL>" if os.environ.get("SGC_NO_SIDE") else
-                  ("label8_kernel<31, ascii>" if args.ascii else "label8_kernel<31, packed>"),
+                  ("labelseq_kernel<31, ascii>" if args.ascii else "labelseq_kernel<31, packed>"),
         "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic, "traffic_unit": "GB per launch", "traffic_source": traffic_src,
         "peak_source": peak_src,
@@ -773,8 +773,9 @@ def main():
         "note": "achieved = SURVEY 8(d)'s algorithmic figure (150/120 B of sequence + ONE 32-byte table sector + 4 B of "
                 "id per k-mer = 37.25 B) x k-mers per launch / measured kernel time; frac_strict counts only what this "
                 "launch needs (packed read bytes + one sector + the labels written).  HBM on this part serves 36-46 G "
-                "random lines/s and moves 128 bytes per access (scripts/sector_probe*.cu, profiles/); the kernel "
-                "probes the table once per eight k-mers and matches the rest in a unitig-ordered side array",
+                "random lines/s and moves 128 bytes per access (scripts/sector_probe*.cu, profiles/); the kernel hashes "
+                "and probes one k-mer in sixteen plus the k-mers it cannot settle against the unitig sequence store "
+                "(sequencing errors, unitig ends): ~0.26 table lines per k-mer",
     }
 
     # ---- CPU baseline on the host cores ---------------------------------------------------

@@ -7,5 +7,5 @@ python bench.py --steps 8 --warmup 3 --no-cpu --no-e2e > gpurun_out/b_$TAG.json 
 python -c "
 import json; d=json.load(open('gpurun_out/b_$TAG.json')); print('value %.2f G/s  step %.2f ms  kernel %.2f ms' % (d['value']/1e9, d['ms_per_step'], d['roofline']['kernel_ms']))"
 if [ "$2" = "ncu" ]; then
-  ncu --set full --clock-control none --import-source on -k regex:label8 -s 3 -c 1 -o gpurun_out/prof_$TAG -f python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_$TAG.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:labelseq -s 3 -c 1 -o gpurun_out/prof_$TAG -f python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_$TAG.log 2>&1
 fi
