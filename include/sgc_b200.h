@@ -111,13 +111,15 @@ int sgc_table_stats(sgc_table* t, int64_t* h_live, int64_t* h_multi, uint32_t* h
 int sgc_table_export(sgc_table* t, uint64_t* d_hash_out, uint32_t* d_id_out, int64_t cap,
                      int64_t* h_n_out);
 int64_t sgc_table_bytes(const sgc_table* t);
-/* Optional unitig-ordered side array (the 64-bit hash of every inserted k-mer in unitig order, 8 B each, plus
- * one "break" bit per k-mer; up to max_entries records): call before sgc_table_insert_sequences.  With it
- * sgc_label_reads probes the hash table only for the first k-mer of every group of eight and matches the
- * other seven by full 64-bit hash equality against the neighbouring unitig positions; a matched k-mer
- * inherits the anchor's id only when no break bit (= "a table lookup answers differently for the two
- * neighbouring positions") lies in between, everything else is probed individually: identical result,
- * fewer HBM lines per k-mer.  SGC_ERR_CAPACITY when max_entries >= 2^30 - 1 (positions are 30 bits of a slot). */
+/* Optional unitig SEQUENCE STORE: every sequence buffer passed to sgc_table_insert_sequences, 2 bits per base
+ * (0.25 B per base) plus one "break" bit per base position; every slot then records where its k-mer lies in
+ * the store (30 bits) and on which strand.  Call before sgc_table_insert_sequences.  With it sgc_label_reads
+ * hashes and probes only the first k-mer of every group of sixteen; the other fifteen are settled by comparing
+ * the read's bases with the store, and inherit the anchor's id when no break bit (= "a table lookup may answer
+ * differently for this position": sequence starts, positions without a k-mer, repeated hashes, dropped
+ * multicounts) lies in between; everything else is hashed and probed individually: identical labels, a quarter
+ * of the hashes and table lines.  SGC_ERR_CAPACITY from the insert when the store would exceed 2^30 - 65 bases
+ * (positions are 30 bits of a slot).  Replaces what the reference does per k-mer at cdbg/index_reads.py:143-152. */
 int sgc_table_enable_side(sgc_table* t);
 int64_t sgc_table_side_bytes(const sgc_table* t);
 /* hash-range partitioned tables: the top `shift` bits of every hash stored here are the owner
@@ -296,6 +298,49 @@ int sgc_label_reads_partitioned(sgc_table* t, const uint8_t* d_seq, int64_t seq_
                                 int64_t ridx_cap, int64_t* d_ids_off, uint32_t* d_ids_out, int64_t ids_cap,
                                 int32_t* d_status, int64_t* h_n_kmers, int64_t* h_n_hits, int64_t* h_n_labels,
                                 int32_t* h_flags);
+/*
+ * Hash-range partitioned table PROBED WHERE IT LIES (the product path of BASELINE.json configs[4]):
+ * owner(hash) = its top log2(R) bits; every rank owns one table (same size everywhere, home shift log2 R) and
+ * maps the other ranks' bucket arrays with CUDA IPC, so the label kernel loads the 32-byte home bucket of a
+ * k-mer straight from its owner's HBM over NVLink -- no request / reply buffers, no collective in the label path.
+ * The unitig sequence store is replicated on every GPU, one shard per rank (the unitigs that rank hashed);
+ * unitig ids are dealt to the ranks in ascending ranges (h_id_bounds[r] = first id of rank r), so the shard a
+ * hit lies in follows from its id.
+ *   sgc_hash_positions      per k-mer of a shard of unitigs: hash + (position in the shard's buffer | strand bit)
+ *                           (stands for pass 1 of build_mphf, cdbg/index_cdbg_by_kmer.py:40-57, on one rank)
+ *   sgc_table_insert_triples  owner side: insert what arrived from every rank; repeated hashes / multicounts
+ *                           are returned as break marks (shard << 32 | position), *h_n_marks of them
+ *   sgc_store_build         the shard's bases, 2 bits each, into d_useq (word of position 0) and its break bits
+ *                           into d_brk (bit 32 = position 0; the caller pre-sets every bit)
+ *   sgc_store_apply_marks   set the marks of all owners in the replicated break bits (shards brk_stride_words apart)
+ *   sgc_table_create_shared like sgc_table_create, the bucket array allocated with the CUDA virtual memory
+ *                           management API so that it can be exported as a POSIX file descriptor and mapped by the
+ *                           other ranks with 2 MB pages (memory opened through legacy CUDA IPC handles serves random
+ *                           32-byte peer loads at 0.09 G/s, this at 6.8 G/s: scripts/peer_probe.cu)
+ *   sgc_table_export_fd     local pointer, mapped size and (h_fd non-NULL) a new fd of the bucket array; the host
+ *                           layer passes the fd to the other ranks (SCM_RIGHTS) and closes it
+ *   sgc_peer_import_fd      map such an fd on this context's GPU;  sgc_peer_unmap undoes it
+ *   sgc_table_set_peers     from now on sgc_label_reads* on this table probe h_bucket_ptrs[owner] and match against
+ *                           the replicated store (d_useq = word of position 0 of shard 0); n_ranks = 0 undoes it
+ */
+#define SGC_STORE_PAD_WORDS 8 /* 32-bit words of zero padding on either side of a store shard */
+#define SGC_BRK_PAD_BITS 32   /* bit index of position 0 in a shard's break-bit array */
+int sgc_hash_positions(sgc_ctx* ctx, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off, int64_t nseq, int k,
+                       uint64_t* d_hash_out, uint32_t* d_aux_out, int64_t hash_cap, int64_t* d_kmer_off,
+                       int32_t* d_status, int64_t* h_total_kmers);
+int sgc_table_insert_triples(sgc_table* t, const uint64_t* d_hash, const uint32_t* d_id, const uint32_t* d_aux, int64_t n,
+                             const uint32_t* h_id_bounds, int n_shards, uint64_t* d_marks, int64_t marks_cap,
+                             int64_t* h_n_marks);
+int sgc_store_build(sgc_ctx* ctx, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off, int64_t nseq, int k,
+                    uint32_t* d_useq, uint32_t* d_brk);
+int sgc_store_apply_marks(sgc_ctx* ctx, const uint64_t* d_marks, int64_t n, uint32_t* d_brk, int64_t brk_stride_words);
+int sgc_table_create_shared(sgc_ctx* ctx, int64_t max_entries, float load, sgc_table** out);
+int sgc_table_export_fd(sgc_table* t, void** d_ptr, int64_t* h_bytes, int* h_fd);
+int sgc_peer_import_fd(sgc_ctx* ctx, int fd, int64_t bytes, void** d_ptr);
+int sgc_peer_unmap(sgc_ctx* ctx, void* d_ptr, int64_t bytes);
+int sgc_table_set_peers(sgc_table* t, int n_ranks, const void* const* h_bucket_ptrs, const uint32_t* h_id_bounds,
+                        const uint32_t* d_useq, int64_t useq_stride_words, const uint32_t* d_brk,
+                        int64_t brk_stride_words);
 int sgc_peer_alloc(sgc_ctx* ctx, int64_t bytes, void** d_ptr, uint8_t* h_handle64);
 int sgc_peer_open(sgc_ctx* ctx, const uint8_t* h_handle64, void** d_ptr);
 int sgc_peer_close(sgc_ctx* ctx, void* d_ptr);

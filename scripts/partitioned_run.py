@@ -13,6 +13,7 @@ ap.add_argument("--reads", type=float, default=4e6)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--p2p", action="store_true", help="fuse the exchange into the kernels (NVLink peer stores)")
+ap.add_argument("--peer", action="store_true", help="probe the owners' tables over NVLink peer loads + replicated sequence store")
 ap.add_argument("--pipeline", type=int, default=0, help="with --p2p: split each step into this many sub-batches and overlap their phases")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -39,7 +40,7 @@ with torch.cuda.stream(ctx.stream):
     ids = torch.arange(ulo, uhi, dtype=torch.int32, device=ctx.device)
 eng = DeviceEngine(ctx)
 t0 = time.time()
-idx = PartitionedIndex(eng, p2p=args.p2p).build(useq, uoff, K, ids)
+idx = PartitionedIndex(eng, p2p=args.p2p, peer_probe=args.peer).build(useq, uoff, K, ids)
 ctx.sync(); dist.barrier()
 if rank == 0:
     print("partitioned build: %.2fs, rank0 holds %d hashes (%.2f GB)" % (time.time() - t0, idx.n_local, idx.table.nbytes / 1e9), flush=True)
@@ -54,9 +55,12 @@ if args.pipeline > 1:
         subs = [(seq[j * per * 150:(j + 1) * per * 150], (off[j * per:(j + 1) * per + 1] - off[j * per]).contiguous())
                 for j in range(args.pipeline)]
     ctx.sync()
+import ctypes
+trace = bool(os.environ.get("SGC_TRACE"))
 for it in range(args.steps + 1):
     if it == 1:
         dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+        if trace: ctx._L.sgc_ctx_set_timing(ctx._h, 1)
     if subs is not None:
         parts = idx.label_reads_pipelined(subs, K)
         continue
@@ -68,8 +72,14 @@ if subs is not None:
     for p in parts[1:]:
         offs.append(p[0][1:] + base); base += int(p[0][-1])
     res = (torch.cat(offs), ids_all, sum(p[2] for p in parts))
-ctx.sync(); dist.barrier(); torch.cuda.synchronize()
+ctx.sync()
+t_mine = time.perf_counter() - t0
+dist.barrier(); torch.cuda.synchronize()
 dt = time.perf_counter() - t0
+if trace:
+    ms, n = ctypes.c_double(0), ctypes.c_int64(0)
+    ctx._L.sgc_ctx_tile_ms(ctx._h, ctypes.byref(ms), ctypes.byref(n))
+    print("[rank %d] my loop %.1f ms; label kernel: %d launches, %.2f ms each" % (rank, t_mine * 1e3, n.value, ms.value / max(n.value, 1)), flush=True)
 t = torch.tensor([dt], dtype=torch.float64, device=ctx.device); dist.all_reduce(t, op=dist.ReduceOp.MAX)
 rate = world * n_reads * 120 * args.steps / float(t.item())
 if args.check:
@@ -78,7 +88,8 @@ if args.check:
     ok = torch.equal(ref["ids_off"], res[0]) and torch.equal(ref["ids"], res[1])
     okt = torch.tensor([1 if ok else 0], device=ctx.device); dist.all_reduce(okt, op=dist.ReduceOp.MIN)
     if rank == 0: print("labels identical to the replicated table on every rank:", bool(okt.item()), flush=True)
+idx.close()
 if rank == 0:
-    print(json.dumps({"mode": ("partitioned-p2p-pipelined%d" % args.pipeline if args.pipeline > 1 else "partitioned-p2p") if args.p2p else "partitioned-nccl", "n_gpus": world, "table_kmers": n_kmers, "reads_per_rank_step": n_reads,
+    print(json.dumps({"mode": "partitioned-peer-probe" if args.peer else ("partitioned-p2p-pipelined%d" % args.pipeline if args.pipeline > 1 else "partitioned-p2p") if args.p2p else "partitioned-nccl", "n_gpus": world, "table_kmers": n_kmers, "reads_per_rank_step": n_reads,
                       "value": rate, "unit": "k-mers/s", "ms_per_step": float(t.item()) / args.steps * 1e3}), flush=True)
 dist.destroy_process_group()

@@ -77,6 +77,15 @@ PROTOTYPES = {
     "sgc_lookup_regions_p2p": (_i32, [_vp, _vp, _pi64, _i64, _i32, _i32, _vp, _i32]),
     "sgc_label_reads_partitioned": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _u32, _vp, _vp, _vp, _vp, _vp, _i64,
                                             _vp, _i64, _vp, _vp, _i64, _vp, _pi64, _pi64, _pi64, ctypes.POINTER(ctypes.c_int32)]),
+    "sgc_hash_positions": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _pi64]),
+    "sgc_table_insert_triples": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp, _i64, _pi64]),
+    "sgc_store_build": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp]),
+    "sgc_store_apply_marks": (_i32, [_vp, _vp, _i64, _vp, _i64]),
+    "sgc_table_create_shared": (_i32, [_vp, _i64, ctypes.c_float, ctypes.POINTER(_vp)]),
+    "sgc_table_export_fd": (_i32, [_vp, ctypes.POINTER(_vp), _pi64, ctypes.POINTER(ctypes.c_int)]),
+    "sgc_peer_import_fd": (_i32, [_vp, _i32, _i64, ctypes.POINTER(_vp)]),
+    "sgc_peer_unmap": (_i32, [_vp, _vp, _i64]),
+    "sgc_table_set_peers": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _vp, _i64]),
     "sgc_peer_alloc": (_i32, [_vp, _i64, ctypes.POINTER(_vp), _vp]),
     "sgc_peer_open": (_i32, [_vp, _vp, ctypes.POINTER(_vp)]),
     "sgc_peer_close": (_i32, [_vp, _vp]),
@@ -103,6 +112,9 @@ PROTOTYPES = {
     "sgc_reads_pair_flags": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "sgc_reads_rows": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _pi64]),
 }
+
+STORE_PAD_WORDS = 8  # SGC_STORE_PAD_WORDS
+BRK_PAD_BITS = 32  # SGC_BRK_PAD_BITS
 
 _lib = None
 

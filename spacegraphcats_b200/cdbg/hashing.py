@@ -16,13 +16,13 @@ from ..device import DeviceMphf, DeviceTable, get_context, pack_sequences
 from .._lib import SGC_MISS, SGC_MAX_K
 
 
-SIDE_MAX_KMERS = (1 << 30) - 2  # side-array positions are 30 bits of the slot's aux word
+STORE_MAX_BASES = (1 << 30) - 129  # positions in the unitig sequence store are 30 bits of the slot's aux word
 
 
-def side_default(n_kmers=0):
-    """Tables built from unitig sequences keep the unitig-ordered side array unless SGC_SIDE=0
-    (or the table is too large for 30-bit positions: then every k-mer probes the table)."""
-    return os.environ.get("SGC_SIDE", "1") != "0" and n_kmers < SIDE_MAX_KMERS
+def side_default(n_bases=0):
+    """Tables built from unitig sequences keep the unitig sequence store (0.25 B + 1 bit per base) unless
+    SGC_SIDE=0 or the sequences are too long for 30-bit positions: then every k-mer probes the table."""
+    return os.environ.get("SGC_SIDE", "1") != "0" and n_bases < STORE_MAX_BASES
 
 UNSET_VALUE = 2**32 - 1  # the reference's BBHashTable "unset" value (index_cdbg_by_kmer.py:24)
 
@@ -85,16 +85,16 @@ class GpuKmerTable:
     def from_sequences(cls, buf, off, ksize, ids=None, ctx=None, side=None):
         """build_mphf's two passes fused: hash every unitig k-mer and insert it under the
         unitig's id; hashes seen under two different ids are dropped (multicounts).
-        ``side`` (default on; ``SGC_SIDE=0`` or ``side=False`` turns it off) also keeps the k-mers in
-        unitig order (8 B + 1 bit each) so that read labelling needs one table probe per eight k-mers
-        instead of eight: identical labels, a third of the HBM traffic."""
+        ``side`` (default on; ``SGC_SIDE=0`` or ``side=False`` turns it off) also keeps the unitig sequences
+        themselves, 2 bits per base, so that read labelling hashes and probes one k-mer in sixteen and settles
+        the others by comparing bases: identical labels, a quarter of the hashes and table lines."""
         t = cls(ctx)
         if isinstance(off, np.ndarray) or not hasattr(off, "device"):
             n_kmers = int(np.maximum(np.diff(off) - ksize + 1, 0).sum())
         else:  # CUDA tensors (already resident sequences)
             n_kmers = int((off[1:] - off[:-1] - (ksize - 1)).clamp_(min=0).sum().item())
         if side is None:
-            side = side_default(n_kmers)
+            side = side_default(int(buf.numel()) if hasattr(buf, "numel") else len(buf))
         t._dev = DeviceTable(t.ctx, max(n_kmers, 1))
         if side:
             t._dev.enable_side()

@@ -56,7 +56,10 @@ def build_mphf(ksize, records_iter_fn, ctx=None, verbose=True):
     from ..device import DeviceTable
 
     table._dev = DeviceTable(ctx, max(total_kmers, 1))
-    if side_default(total_kmers):  # unitig-ordered side array for read labelling; SGC_SIDE=0: off
+    total_bases = int(lengths.sum())
+    # unitig sequence store for read labelling (SGC_SIDE=0: off); every batch starts at a
+    # 64-base boundary of the store
+    if side_default(total_bases + 64 * (total_bases // BATCH_BASES + n_contigs // 1024 + 2)):
         table._dev.enable_side()
     lo = 0
     while lo < n_contigs:

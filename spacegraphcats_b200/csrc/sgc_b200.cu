@@ -21,6 +21,7 @@
 //   K8 BBHash writer    mphf_* kernels (sgc_mphf.cuh)   (bbhash.PyMPHF + save, the on-disk contigs.mphf)
 //
 // No CPU fallback: every entry point needs a CUDA device.
+#include <cuda.h>  // driver API types only: the entry points are resolved at run time (no link-time libcuda)
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 
@@ -119,6 +120,19 @@ struct sgc_table {
     int64_t brk_words = 0;
     int64_t store_cap = 0, store_fill = 0;  // in bases; batches start at multiples of 64
     uint32_t* useq() const { return useq_alloc ? useq_alloc + USEQ_PAD : nullptr; }
+    // bucket array allocated with the virtual memory management API (sgc_table_create_shared): it can be mapped
+    // into other processes with 2 MB pages (legacy CUDA IPC maps small pages: random peer loads run 75x slower)
+    bool vmm = false;
+    unsigned long long vmm_handle = 0;
+    size_t vmm_bytes = 0;
+    // hash-range partitioned table probed over peer memory (sgc_table_set_peers): every owner's bucket array,
+    // the store replicated on this GPU (one shard per rank) and the id range of every shard
+    int peer_n = 0;
+    const Bucket* peer_tbl[32] = {nullptr};
+    uint32_t id_bounds[33] = {0};
+    const uint32_t* peer_useq = nullptr;
+    const uint32_t* peer_brk = nullptr;
+    int64_t peer_ustride = 0, peer_bstride = 0;
     // pending label call
     bool label_pending = false;
     int64_t label_nseq = 0;
@@ -459,9 +473,11 @@ void* sgc_ctx_stream(sgc_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int64_t sgc_ctx_launches(const sgc_ctx* c) { return c ? c->launches : 0; }
 
 // ---------------------------------------------------------------------------- K1
-int sgc_hash_batch(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off, int64_t nseq, int k,
-                   uint64_t* d_hash_out, int64_t hash_cap, int64_t* d_kmer_off, int32_t* d_status,
-                   int64_t* h_total_kmers) {
+}  // extern "C"
+namespace {
+int hash_batch_impl(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off, int64_t nseq, int k,
+                    uint64_t* d_hash_out, uint32_t* d_aux_out, int64_t hash_cap, int64_t* d_kmer_off, int32_t* d_status,
+                    int64_t* h_total_kmers) {
     if (!c) return fail(SGC_ERR_ARG, "ctx is NULL");
     TRY(check_seq_args(d_seq, seq_bytes, d_off, nseq, k));
     TRY(set_device(c));
@@ -486,7 +502,27 @@ int sgc_hash_batch(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, const in
     TRY(zero_scalars(c));
     TileArgs a = base_args(c, d_seq, d_off, k, p, d_status);
     a.hash_out = d_hash_out;
+    a.aux_out = d_aux_out;
     return launch_tile<MODE_HASH>(c, a);
+}
+}  // namespace
+extern "C" {
+
+int sgc_hash_batch(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off, int64_t nseq, int k,
+                   uint64_t* d_hash_out, int64_t hash_cap, int64_t* d_kmer_off, int32_t* d_status,
+                   int64_t* h_total_kmers) {
+    return hash_batch_impl(c, d_seq, seq_bytes, d_off, nseq, k, d_hash_out, nullptr, hash_cap, d_kmer_off, d_status,
+                           h_total_kmers);
+}
+
+int sgc_hash_positions(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off, int64_t nseq, int k,
+                       uint64_t* d_hash_out, uint32_t* d_aux_out, int64_t hash_cap, int64_t* d_kmer_off, int32_t* d_status,
+                       int64_t* h_total_kmers) {
+    if (!d_aux_out) return fail(SGC_ERR_ARG, "d_aux_out is NULL");
+    if (seq_bytes + 64 >= (int64_t)AUX_NONE)
+        return fail(SGC_ERR_CAPACITY, "a store shard is limited to 2^30 bases (got %lld)", (long long)seq_bytes);
+    return hash_batch_impl(c, d_seq, seq_bytes, d_off, nseq, k, d_hash_out, d_aux_out, hash_cap, d_kmer_off, d_status,
+                           h_total_kmers);
 }
 
 // sourmash-style MinHash primitives (rows f3 / f4 of SURVEY.md 8f)
@@ -520,8 +556,103 @@ int sgc_minhash_batch(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, const
     return launch_tile<MODE_MINHASH>(c, a);
 }
 
+// ---------------------------------------------------------------------------- shareable device memory
+}  // extern "C"
+namespace {
+struct VmmApi {
+    CUresult (*create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*reserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*addr_free)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*set_access)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    CUresult (*export_fd)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+    CUresult (*import_fd)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType) = nullptr;
+    CUresult (*granularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    bool ok = false;
+};
+const VmmApi* vmm_api() {
+    static VmmApi api;
+    static bool tried = false;
+    if (tried) return api.ok ? &api : nullptr;
+    tried = true;
+    auto get = [](const char* name, void** fn) {
+        cudaDriverEntryPointQueryResult q;
+        return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+    };
+    api.ok = get("cuMemCreate", (void**)&api.create) && get("cuMemRelease", (void**)&api.release) &&
+             get("cuMemAddressReserve", (void**)&api.reserve) && get("cuMemAddressFree", (void**)&api.addr_free) &&
+             get("cuMemMap", (void**)&api.map) && get("cuMemUnmap", (void**)&api.unmap) &&
+             get("cuMemSetAccess", (void**)&api.set_access) &&
+             get("cuMemExportToShareableHandle", (void**)&api.export_fd) &&
+             get("cuMemImportFromShareableHandle", (void**)&api.import_fd) &&
+             get("cuMemGetAllocationGranularity", (void**)&api.granularity);
+    return api.ok ? &api : nullptr;
+}
+#define CD(x)                                                                                  \
+    do {                                                                                       \
+        CUresult r_ = (x);                                                                     \
+        if (r_ != CUDA_SUCCESS) return fail(SGC_ERR_CUDA, "%s failed: CUresult %d", #x, (int)r_); \
+    } while (0)
+
+CUmemAllocationProp vmm_prop(int device) {
+    CUmemAllocationProp prop;
+    memset(&prop, 0, sizeof(prop));
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    return prop;
+}
+int vmm_map(const VmmApi* v, int device, CUmemGenericAllocationHandle h, size_t bytes, size_t gran, void** out) {
+    CUdeviceptr p = 0;
+    CD(v->reserve(&p, bytes, gran, 0, 0));
+    CD(v->map(p, bytes, 0, h, 0));
+    CUmemAccessDesc ad;
+    memset(&ad, 0, sizeof(ad));
+    ad.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    ad.location.id = device;
+    ad.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    CD(v->set_access(p, bytes, &ad, 1));
+    *out = (void*)p;
+    return SGC_OK;
+}
+// physical memory on the context's GPU, mapped here, exportable as a POSIX fd
+int vmm_alloc(sgc_ctx* c, size_t want, void** ptr, unsigned long long* handle, size_t* bytes) {
+    const VmmApi* v = vmm_api();
+    if (!v) return fail(SGC_ERR_CUDA, "the CUDA driver does not offer the virtual memory management API");
+    CUmemAllocationProp prop = vmm_prop(c->device);
+    size_t gran = 0;
+    CD(v->granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+    if (gran < ((size_t)1 << 21)) gran = (size_t)1 << 21;
+    const size_t sz = (want + gran - 1) / gran * gran;
+    CUmemGenericAllocationHandle h;
+    CUresult r = v->create(&h, sz, &prop, 0);
+    if (r != CUDA_SUCCESS) return fail(SGC_ERR_NOMEM, "cuMemCreate(%zu) failed: CUresult %d", sz, (int)r);
+    int rc = vmm_map(v, c->device, h, sz, gran, ptr);
+    if (rc != SGC_OK) {
+        v->release(h);
+        return rc;
+    }
+    *handle = (unsigned long long)h;
+    *bytes = sz;
+    return SGC_OK;
+}
+void vmm_free(void* ptr, unsigned long long handle, size_t bytes) {
+    const VmmApi* v = vmm_api();
+    if (!v || !ptr) return;
+    v->unmap((CUdeviceptr)ptr, bytes);
+    v->addr_free((CUdeviceptr)ptr, bytes);
+    v->release((CUmemGenericAllocationHandle)handle);
+}
+}  // namespace
+extern "C" {
+
 // ---------------------------------------------------------------------------- K2
-int sgc_table_create(sgc_ctx* c, int64_t max_entries, float load, sgc_table** out) {
+}  // extern "C"
+namespace {
+int table_create(sgc_ctx* c, int64_t max_entries, float load, bool shared, sgc_table** out) {
     if (!c || !out) return fail(SGC_ERR_ARG, "NULL argument");
     *out = nullptr;
     if (max_entries < 0) return fail(SGC_ERR_ARG, "max_entries < 0");
@@ -544,11 +675,22 @@ int sgc_table_create(sgc_ctx* c, int64_t max_entries, float load, sgc_table** ou
     t->nbuckets = (uint32_t)nb;
     t->nlines = (uint32_t)(nb / 4);
     t->max_entries = max_entries;
-    cudaError_t e = cudaMalloc(&t->buckets, (size_t)nb * sizeof(Bucket));
-    if (e != cudaSuccess) {
-        delete t;
-        return fail(SGC_ERR_NOMEM, "cudaMalloc(%zu) for the k-mer table failed: %s", (size_t)nb * sizeof(Bucket),
-                    cudaGetErrorString(e));
+    if (shared) {
+        void* p = nullptr;
+        int rc = vmm_alloc(c, (size_t)nb * sizeof(Bucket), &p, &t->vmm_handle, &t->vmm_bytes);
+        if (rc != SGC_OK) {
+            delete t;
+            return rc;
+        }
+        t->buckets = (Bucket*)p;
+        t->vmm = true;
+    } else {
+        cudaError_t e = cudaMalloc(&t->buckets, (size_t)nb * sizeof(Bucket));
+        if (e != cudaSuccess) {
+            delete t;
+            return fail(SGC_ERR_NOMEM, "cudaMalloc(%zu) for the k-mer table failed: %s", (size_t)nb * sizeof(Bucket),
+                        cudaGetErrorString(e));
+        }
     }
     table_clear_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(t->buckets, t->nbuckets);
     c->launches++;
@@ -556,12 +698,22 @@ int sgc_table_create(sgc_ctx* c, int64_t max_entries, float load, sgc_table** ou
     *out = t;
     return SGC_OK;
 }
+}  // namespace
+extern "C" {
+
+int sgc_table_create(sgc_ctx* c, int64_t max_entries, float load, sgc_table** out) {
+    return table_create(c, max_entries, load, false, out);
+}
+int sgc_table_create_shared(sgc_ctx* c, int64_t max_entries, float load, sgc_table** out) {
+    return table_create(c, max_entries, load, true, out);
+}
 
 void sgc_table_free(sgc_table* t) {
     if (!t) return;
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
-    if (t->buckets) cudaFree(t->buckets);
+    if (t->buckets && t->vmm) vmm_free(t->buckets, t->vmm_handle, t->vmm_bytes);
+    else if (t->buckets) cudaFree(t->buckets);
     if (t->useq_alloc) cudaFree(t->useq_alloc);
     if (t->brk) cudaFree(t->brk);
     delete t;
@@ -895,14 +1047,14 @@ int sgc_lookup_sequences(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes, 
 
 namespace {
 
-template <int K, bool PACKED>
+template <int K, bool PACKED, bool PEER>
 int launch_labelseq_k(sgc_ctx* c, const LabelSeqArgs& a) {
     const size_t smem = sizeof(WarpTileS<K, PACKED>) * WPBS;
     static thread_local int blocks_per_sm_of[64] = {0};
     int& blocks_per_sm = blocks_per_sm_of[c->device & 63];
     if (!blocks_per_sm) {
-        CU(cudaFuncSetAttribute(labelseq_kernel<K, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, labelseq_kernel<K, PACKED>, NTS, smem));
+        CU(cudaFuncSetAttribute(labelseq_kernel<K, PACKED, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, labelseq_kernel<K, PACKED, PEER>, NTS, smem));
         if (blocks_per_sm < 1) return fail(SGC_ERR_CUDA, "label kernel does not fit on an SM (smem %zu)", smem);
     }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -916,7 +1068,7 @@ int launch_labelseq_k(sgc_ctx* c, const LabelSeqArgs& a) {
         int v = atoi(lim);
         if (v >= 1 && v < ctas) ctas = v;
     }
-    labelseq_kernel<K, PACKED><<<c->num_sms * ctas, NTS, smem, c->stream>>>(a);
+    labelseq_kernel<K, PACKED, PEER><<<c->num_sms * ctas, NTS, smem, c->stream>>>(a);
     c->launches++;
     CU(cudaGetLastError());
     if (c->timing) {
@@ -928,14 +1080,23 @@ int launch_labelseq_k(sgc_ctx* c, const LabelSeqArgs& a) {
 
 template <bool PACKED>
 int launch_labelseq(sgc_ctx* c, const LabelSeqArgs& a) {
+    if (a.n_shards > 1) {  // the table is partitioned: probes go to the owner GPU's buckets over NVLink
+        switch (a.k) {
+            case 21: return launch_labelseq_k<21, PACKED, true>(c, a);
+            case 31: return launch_labelseq_k<31, PACKED, true>(c, a);
+            default: return launch_labelseq_k<0, PACKED, true>(c, a);
+        }
+    }
     switch (a.k) {
-        case 21: return launch_labelseq_k<21, PACKED>(c, a);
-        case 31: return launch_labelseq_k<31, PACKED>(c, a);
-        default: return launch_labelseq_k<0, PACKED>(c, a);
+        case 21: return launch_labelseq_k<21, PACKED, false>(c, a);
+        case 31: return launch_labelseq_k<31, PACKED, false>(c, a);
+        default: return launch_labelseq_k<0, PACKED, false>(c, a);
     }
 }
 
-bool use_side(const sgc_table* t) { return t->useq_alloc && t->store_fill > 0 && !getenv("SGC_NO_SIDE"); }
+bool use_side(const sgc_table* t) {
+    return ((t->useq_alloc && t->store_fill > 0) || t->peer_n > 0) && !getenv("SGC_NO_SIDE");
+}
 
 int label_common_prologue(sgc_table* t, int64_t nseq, int64_t ids_cap, unsigned long long* pairs_cap_out) {
     sgc_ctx* c = t->ctx;
@@ -962,6 +1123,18 @@ void labelseq_args(LabelSeqArgs& a, sgc_table* t, const uint8_t* seq, const Plan
     a.home_shift = t->home_shift;
     a.useq = t->useq();
     a.brk = t->brk;
+    if (t->peer_n > 0) {
+        a.useq = t->peer_useq;
+        a.brk = t->peer_brk;
+        a.ustride = t->peer_ustride;
+        a.bstride = t->peer_bstride;
+        a.n_shards = t->peer_n;
+        for (int r = 0; r < t->peer_n; r++) a.peer_tbl[r] = t->peer_tbl[r];
+        for (int r = 0; r <= t->peer_n; r++) a.id_bounds[r] = t->id_bounds[r];
+        int b = 0;
+        while ((1 << b) < t->peer_n) b++;
+        a.owner_bits = b;
+    }
     a.pairs = (unsigned long long*)c->pairs_a.p;
     a.pairs_cap = pairs_cap;
 }
@@ -1434,6 +1607,123 @@ int sgc_peer_free(sgc_ctx* c, void* d_ptr) {
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaFree(d_ptr));
     }
+    return SGC_OK;
+}
+
+// ---- partitioned table probed over peer memory ----
+int sgc_table_export_fd(sgc_table* t, void** d_ptr, int64_t* h_bytes, int* h_fd) {
+    if (!t || !d_ptr) return fail(SGC_ERR_ARG, "bad argument");
+    TRY(set_device(t->ctx));
+    *d_ptr = t->buckets;
+    if (h_bytes) *h_bytes = t->vmm ? (int64_t)t->vmm_bytes : (int64_t)t->nbuckets * (int64_t)sizeof(Bucket);
+    if (h_fd) {
+        if (!t->vmm) return fail(SGC_ERR_ARG, "only tables made by sgc_table_create_shared can be exported");
+        const VmmApi* v = vmm_api();
+        int fd = -1;
+        CD(v->export_fd(&fd, (CUmemGenericAllocationHandle)t->vmm_handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+        *h_fd = fd;
+    }
+    return SGC_OK;
+}
+
+int sgc_peer_import_fd(sgc_ctx* c, int fd, int64_t bytes, void** d_ptr) {
+    if (!c || !d_ptr || bytes <= 0 || fd < 0) return fail(SGC_ERR_ARG, "bad argument");
+    TRY(set_device(c));
+    const VmmApi* v = vmm_api();
+    if (!v) return fail(SGC_ERR_CUDA, "the CUDA driver does not offer the virtual memory management API");
+    CUmemGenericAllocationHandle h;
+    CD(v->import_fd(&h, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+    int rc = vmm_map(v, c->device, h, (size_t)bytes, (size_t)1 << 21, d_ptr);
+    v->release(h);  // the mapping keeps the memory alive
+    return rc;
+}
+
+int sgc_peer_unmap(sgc_ctx* c, void* d_ptr, int64_t bytes) {
+    if (!c) return fail(SGC_ERR_ARG, "ctx is NULL");
+    TRY(set_device(c));
+    const VmmApi* v = vmm_api();
+    if (v && d_ptr) {
+        CU(cudaStreamSynchronize(c->stream));
+        v->unmap((CUdeviceptr)d_ptr, (size_t)bytes);
+        v->addr_free((CUdeviceptr)d_ptr, (size_t)bytes);
+    }
+    return SGC_OK;
+}
+
+int sgc_table_insert_triples(sgc_table* t, const uint64_t* d_hash, const uint32_t* d_id, const uint32_t* d_aux, int64_t n,
+                             const uint32_t* h_id_bounds, int n_shards, uint64_t* d_marks, int64_t marks_cap,
+                             int64_t* h_n_marks) {
+    if (!t) return fail(SGC_ERR_ARG, "table is NULL");
+    if (n < 0 || n_shards < 1 || n_shards > 32 || !h_id_bounds || marks_cap < 0) return fail(SGC_ERR_ARG, "bad argument");
+    if (h_n_marks) *h_n_marks = 0;
+    if (n == 0) return SGC_OK;
+    sgc_ctx* c = t->ctx;
+    TRY(set_device(c));
+    TRY(zero_scalars(c));
+    BrkSink sink;
+    sink.list = (unsigned long long*)d_marks;
+    sink.list_n = &c->d_scal->n_export;
+    sink.list_cap = (unsigned long long)marks_cap;
+    sink.n_shards = n_shards;
+    for (int r = 0; r <= n_shards; r++) sink.bounds[r] = h_id_bounds[r];
+    insert_triples_kernel<<<grid_for(n, 256, c->num_sms * 8), 256, 0, c->stream>>>(t->buckets, t->nbuckets, t->nlines,
+                                                                                 t->home_shift, d_hash, d_id, d_aux, n,
+                                                                                 c->d_scal, sink);
+    c->launches++;
+    CU(cudaGetLastError());
+    TRY(fetch_scalars(c));
+    if (h_n_marks) *h_n_marks = (int64_t)c->h_scal->n_export;
+    TRY(device_err_check(c));
+    if ((int64_t)c->h_scal->n_export > marks_cap)
+        return fail(SGC_ERR_CAPACITY, "%lld break marks do not fit the list of %lld", (long long)c->h_scal->n_export,
+                    (long long)marks_cap);
+    return SGC_OK;
+}
+
+int sgc_store_build(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off, int64_t nseq, int k,
+                    uint32_t* d_useq, uint32_t* d_brk) {
+    if (!c || !d_useq || !d_brk) return fail(SGC_ERR_ARG, "bad argument");
+    TRY(check_seq_args(d_seq, seq_bytes, d_off, nseq, k));
+    TRY(set_device(c));
+    if (seq_bytes == 0) return SGC_OK;
+    const int64_t nw = (seq_bytes + 15) / 16, nbw = (seq_bytes + 31) / 32;
+    useq_pack_kernel<<<grid_for(nw, 256, c->num_sms * 16), 256, 0, c->stream>>>(d_seq, seq_bytes, d_useq, nw);
+    useq_brk_kernel<<<grid_for(nbw, 256, c->num_sms * 16), 256, 0, c->stream>>>(d_off, nseq, k, d_brk + (BRK_PAD >> 5), nbw);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    return SGC_OK;
+}
+
+int sgc_store_apply_marks(sgc_ctx* c, const uint64_t* d_marks, int64_t n, uint32_t* d_brk, int64_t brk_stride_words) {
+    if (!c || n < 0 || (n > 0 && (!d_marks || !d_brk))) return fail(SGC_ERR_ARG, "bad argument");
+    TRY(set_device(c));
+    if (n == 0) return SGC_OK;
+    apply_marks_kernel<<<grid_for(n, 256, c->num_sms * 8), 256, 0, c->stream>>>((const unsigned long long*)d_marks, n, d_brk,
+                                                                              brk_stride_words);
+    c->launches++;
+    CU(cudaGetLastError());
+    return SGC_OK;
+}
+
+int sgc_table_set_peers(sgc_table* t, int n_ranks, const void* const* h_bucket_ptrs, const uint32_t* h_id_bounds,
+                        const uint32_t* d_useq, int64_t useq_stride_words, const uint32_t* d_brk,
+                        int64_t brk_stride_words) {
+    if (!t) return fail(SGC_ERR_ARG, "table is NULL");
+    if (n_ranks == 0) {
+        t->peer_n = 0;
+        return SGC_OK;
+    }
+    if (n_ranks < 2 || n_ranks > 32 || (n_ranks & (n_ranks - 1)) || !h_bucket_ptrs || !h_id_bounds || !d_useq || !d_brk)
+        return fail(SGC_ERR_ARG, "bad argument (n_ranks must be a power of two in 2..32)");
+    if ((1 << t->home_shift) != n_ranks)
+        return fail(SGC_ERR_ARG, "the table's home shift (%d) does not match %d owners", t->home_shift, n_ranks);
+    t->peer_n = n_ranks;
+    for (int r = 0; r < n_ranks; r++) t->peer_tbl[r] = (const Bucket*)h_bucket_ptrs[r];
+    for (int r = 0; r <= n_ranks; r++) t->id_bounds[r] = h_id_bounds[r];
+    t->peer_useq = d_useq;
+    t->peer_brk = d_brk;
+    t->peer_ustride = useq_stride_words;
+    t->peer_bstride = brk_stride_words;
     return SGC_OK;
 }
 

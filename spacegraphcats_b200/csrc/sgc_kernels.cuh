@@ -63,11 +63,30 @@ __global__ void table_clear_kernel(Bucket* tbl, uint32_t nb) {
 __global__ void insert_pairs_kernel(Bucket* tbl, uint32_t nb, uint32_t nlines, int hs,
                                     const uint64_t* __restrict__ hash, const uint32_t* __restrict__ id, int64_t n,
                                     Scalars* scal, uint32_t* brk) {
+    BrkSink sink;
+    sink.brk = brk;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         uint32_t v = id[i];
         if (v > SGC_MAX_ID) atomicOr(&scal->err, 2);
-        else table_insert(tbl, nb, nlines, hs, hash[i], v, AUX_NONE, scal, brk);
+        else table_insert(tbl, nb, nlines, hs, hash[i], v, AUX_NONE, scal, sink);
     }
+}
+
+// one owner's part of a partitioned table: (hash, id, position | orientation) triples that arrived from every rank
+__global__ void insert_triples_kernel(Bucket* tbl, uint32_t nb, uint32_t nlines, int hs,
+                                      const uint64_t* __restrict__ hash, const uint32_t* __restrict__ id,
+                                      const uint32_t* __restrict__ aux, int64_t n, Scalars* scal, const BrkSink sink) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t v = id[i];
+        if (v > SGC_MAX_ID) atomicOr(&scal->err, 2);
+        else table_insert(tbl, nb, nlines, hs, hash[i], v, aux[i], scal, sink);
+    }
+}
+
+// marks of a partitioned build -> break bits of the replicated store (shard s starts stride_words after shard s-1)
+__global__ void apply_marks_kernel(const unsigned long long* __restrict__ marks, int64_t n, uint32_t* brk, int64_t stride_words) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        brk_mark(brk + (int64_t)(marks[i] >> 32) * stride_words, (uint32_t)marks[i]);
 }
 
 __global__ void lookup_kernel(const Bucket* tbl, uint32_t nb, uint32_t nlines, int hs,

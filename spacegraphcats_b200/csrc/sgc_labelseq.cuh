@@ -38,6 +38,7 @@ constexpr int GK = 16;        // k-mers per group: one anchor, fifteen followers
 constexpr int PAIRS_S = 64;   // candidate keys staged per warp before one global reservation
 constexpr int FOFF = 4;       // staged forward words start 4 words into their slot
 constexpr int USEQ_PAD = 8;   // words (128 bases) of zero padding on either end of the sequence store
+static_assert(USEQ_PAD == SGC_STORE_PAD_WORDS && BRK_PAD == SGC_BRK_PAD_BITS, "include/sgc_b200.h states the store layout");
 #ifndef SGC_LS_NT
 #define SGC_LS_NT 256
 #endif
@@ -79,6 +80,13 @@ struct LabelSeqArgs {
     const uint32_t* brk;      // bit BRK_PAD + p = break before position p
     unsigned long long* pairs;
     unsigned long long pairs_cap;
+    // PEER = true: the table is hash-range partitioned over n_shards GPUs (owner = top owner_bits bits of the hash)
+    // and probed where it lies, over NVLink peer memory; the store is replicated, one shard per rank (ustride /
+    // bstride words apart), and the shard of a hit follows from its unitig id (ids are dealt out in ranges)
+    const Bucket* peer_tbl[32];
+    uint32_t id_bounds[33];
+    long long ustride, bstride;
+    int owner_bits, n_shards;
 };
 
 template <int K, bool PACKED>
@@ -174,7 +182,7 @@ __global__ void useq_brk_kernel(const int64_t* __restrict__ off, int64_t nseq, i
 // ----------------------------------------------------------------------------------
 // the kernel
 // ----------------------------------------------------------------------------------
-template <int K, bool PACKED>
+template <int K, bool PACKED, bool PEER>
 __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const LabelSeqArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using G = GeoS<K, PACKED>;
@@ -393,14 +401,18 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
             }
             const uint64_t h = hf ^ hr;
             const uint32_t hb = act ? home_bucket(h, a.nbuckets, a.home_shift) : 0u;
+            const Bucket* tb = a.tbl;
+            if constexpr (PEER) {
+                if (act) tb = a.peer_tbl[(unsigned)(h >> (64 - a.owner_bits))];
+            }
             Entry e0, e1;
-            load_bucket_nc(a.tbl + hb, e0, e1);  // idle lanes probe bucket 0 (an L2 hit)
+            load_bucket_nc(tb + hb, e0, e1);  // idle lanes probe bucket 0 of the local table (an L2 hit)
             uint32_t v = SGC_MISS, aux = AUX_NONE;
             if (act) {
                 if (!bucket_match(e0, e1, h, v, aux)) {
                     v = SGC_MISS;
                     aux = AUX_NONE;
-                    if (bucket_overflowed(e0)) v = lookup_slow_call(a.tbl, a.nlines, hb, h, &aux);
+                    if (bucket_overflowed(e0)) v = lookup_slow_call(tb, a.nlines, hb, h, &aux);
                 }
             }
             unsigned nhit = v != SGC_MISS;
@@ -415,9 +427,17 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                     unsigned m = 1u;
                     if (has_g) {
                         const bool along = ((aux & ORI_BIT) != 0) == (hf < hr);
+                        const uint32_t* useq = a.useq;
+                        const uint32_t* brkp = a.brk;
+                        if constexpr (PEER) {  // the shard of the store this unitig lies in
+                            int shard = 0;
+                            for (int s = 1; s < a.n_shards; s++) shard += v >= a.id_bounds[s];
+                            useq += shard * a.ustride;
+                            brkp += shard * a.bstride;
+                        }
                         // break bits of positions gp-15 .. gp+16
                         const uint32_t bi = gp + (uint32_t)(BRK_PAD - (GK - 1));
-                        const uint32_t w0 = __ldg(a.brk + (bi >> 5)), w1 = __ldg(a.brk + (bi >> 5) + 1);
+                        const uint32_t w0 = __ldg(brkp + (bi >> 5)), w1 = __ldg(brkp + (bi >> 5) + 1);
                         unsigned clean;
                         if constexpr (K != 0) {
                             constexpr int WL = GK - 1 + (K ? K : 1);   // bases of a full window
@@ -425,7 +445,7 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                             static_assert(NWD <= 3 || K == 0, "window words");
                             const uint32_t* Pw = wt.P + sg * PWS + (q >> 4);  // q % 16 == 0
                             const int wsi = (int)gp - (along ? 0 : GK - 1);     // first store position of the window
-                            const uint32_t* up = a.useq + (wsi >> 4);
+                            const uint32_t* up = useq + (wsi >> 4);
                             const int sh = 2 * (wsi & 15);
                             uint32_t u[NWD + 1], un[NWD], rd[NWD];
 #pragma unroll
@@ -474,7 +494,7 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                                 const int rbp = q + j;
                                 const uint32_t rbase = (Pw[rbp >> 4] >> (2 * (rbp & 15))) & 3u;
                                 const int pos = along ? (int)gp + j : (int)gp + k - 1 - j;
-                                uint32_t ub = (__ldg(a.useq + (pos >> 4)) >> (2 * (pos & 15))) & 3u;
+                                uint32_t ub = (__ldg(useq + (pos >> 4)) >> (2 * (pos & 15))) & 3u;
                                 if (!along) ub ^= 3u;
                                 if (rbase != ub) {
                                     f = j;

@@ -109,6 +109,7 @@ struct TileArgs {
     int k;
     // MODE_HASH / MODE_MINHASH
     uint64_t* hash_out;
+    uint32_t* aux_out;              // MODE_HASH, nullable: per k-mer (upos_base + byte offset of its first base) | ORI_BIT
     unsigned long long* seq_min;    // MODE_MINHASH: per-sequence minimum (atomicMin), nullable
     unsigned long long seed;        // MODE_MINHASH: Murmur3 seed (sourmash: 42)
     // table (MODE_INSERT / MODE_LOOKUP / MODE_LABEL)

@@ -128,8 +128,31 @@ __device__ __forceinline__ void brk_mark(uint32_t* brk, uint32_t pos) {
 // table under another position fences its own position off (it is not the one the slot points to), and a
 // hash that becomes a multicount fences the slot's position off too -- so whatever lies between two break
 // bits is a run of k-mers whose slots point at themselves and hold their unitig's id.
+// Where the build records its break bits: straight into the table's own store (brk), or -- building one owner's
+// part of a hash-range partitioned table, whose store is replicated on every GPU -- as a list of
+// (shard << 32 | position) marks that every rank applies afterwards.  The shard of a position is the rank whose
+// unitigs were stored there; unitig ids are dealt to the ranks in ascending ranges, so it follows from the id.
+struct BrkSink {
+    uint32_t* brk = nullptr;
+    unsigned long long* list = nullptr;
+    unsigned long long* list_n = nullptr;
+    unsigned long long list_cap = 0;
+    uint32_t bounds[33] = {0};  // shard s holds the ids in [bounds[s], bounds[s+1])
+    int n_shards = 1;
+    __device__ __forceinline__ bool on() const { return brk != nullptr || list != nullptr; }
+    __device__ void mark(uint32_t pos, uint32_t id) const {
+        if (brk) brk_mark(brk, pos);
+        else if (list && id < VAL_MULTI) {
+            unsigned shard = 0;
+            for (int s = 1; s < n_shards; s++) shard += id >= bounds[s];
+            const unsigned long long at = atomicAdd(list_n, 1ULL);
+            if (at < list_cap) list[at] = ((unsigned long long)shard << 32) | pos;
+        }
+    }
+};
+
 __device__ void table_insert(Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, uint64_t h, uint32_t id, uint32_t aux,
-                             Scalars* scal, uint32_t* brk = nullptr) {
+                             Scalars* scal, const BrkSink& sink) {
     const uint32_t hb = home_bucket(h, nb, hs);
     const Entry empty{0ULL, VAL_EMPTY, 0u};
     const Entry mine{h, id, aux & (AUX_MASK | ORI_BIT)};
@@ -151,10 +174,12 @@ __device__ void table_insert(Bucket* tbl, uint32_t nb, uint32_t nlines, int hs, 
             }
             if (e.key == h) {
                 const uint32_t mypos = aux & AUX_MASK, slotpos = e.aux & AUX_MASK;
-                if (brk && mypos != AUX_NONE && mypos != slotpos) brk_mark(brk, mypos);
+                const bool marks = sink.on();
+                if (marks && mypos != AUX_NONE && mypos != slotpos) sink.mark(mypos, id);
                 if (e.val != id) {
                     if (e.val != VAL_MULTI) atomicExch(&bp->e[s].val, VAL_MULTI);
-                    if (brk && slotpos != AUX_NONE) brk_mark(brk, slotpos);
+                    // (a slot that is a multicount already had its position fenced off by whoever made it one)
+                    if (marks && slotpos != AUX_NONE) sink.mark(slotpos, e.val);
                 }
                 return;
             }

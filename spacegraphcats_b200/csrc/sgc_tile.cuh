@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
 
         // locate group g (segment sg, first k-mer i, nv valid k-mers) and hash its 4 k-mers
         // ori (MODE_INSERT only): bit t = forward k-mer t hashes below its reverse complement
-        constexpr bool WANT_ORI = MODE == MODE_INSERT;
+        constexpr bool WANT_ORI = MODE == MODE_INSERT || MODE == MODE_HASH;
         auto locate_and_hash = [&](int g, int& sg, int& i, int& nv, uint64_t (&h)[4], unsigned& ori) {
             int lo = 0;  // largest sg with gpre[sg] <= g
 #pragma unroll
@@ -429,6 +429,12 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
 #pragma unroll
                     for (int t = 0; t < 4; t++)
                         if (t < nv) o[t] = h[t];
+                    if (a.aux_out) {  // position of the k-mer in its sequence buffer | orientation (partitioned build)
+                        const uint32_t p0 = (uint32_t)(a.upos_base + (unsigned long long)(wt.start[sg] + i));
+#pragma unroll
+                        for (int t = 0; t < 4; t++)
+                            if (t < nv) a.aux_out[wt.kout[sg] + i + t] = (p0 + t) | (((ori >> t) & 1u) ? ORI_BIT : 0u);
+                    }
                 } else {
                     long long sq = wt.seq[sg];
                     uint32_t id = a.seq_ids ? a.seq_ids[sq] : a.id_base + (uint32_t)sq;
@@ -440,7 +446,9 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP
                         for (int t = 0; t < nv; t++) {
                             uint32_t aux = AUX_NONE;
                             if (a.brk) aux = (uint32_t)(g0 + t) | (((ori >> t) & 1u) ? ORI_BIT : 0u);
-                            table_insert(a.tbl, a.nbuckets, a.nlines, a.home_shift, h[t], id, aux, a.scal, a.brk);
+                            BrkSink sink;
+                            sink.brk = a.brk;
+                            table_insert(a.tbl, a.nbuckets, a.nlines, a.home_shift, h[t], id, aux, a.scal, sink);
                         }
                     }
                 }

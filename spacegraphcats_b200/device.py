@@ -160,6 +160,26 @@ class Context:
             self.to_host(d_stat) if d_stat is not None else None,
         )
 
+    def hash_positions(self, seq, off, ksize):
+        """Per k-mer of every sequence: hash and (byte offset of its first base in ``seq`` | strand bit << 30), on
+        the device (partitioned build with a sequence store).  -> (hashes i64, aux i32, kmer_off i64, status i32)"""
+        torch = _torch()
+        d_seq = self.to_device(seq, np.uint8)
+        d_off = self.to_device(off, np.int64)
+        nseq = d_off.numel() - 1
+        nbytes = d_seq.numel()
+        cap = max(nbytes, 1)
+        d_hash = self.empty(cap, torch.int64)
+        d_aux = self.empty(cap, torch.int32)
+        d_koff = self.empty(nseq + 1, torch.int64)
+        d_stat = self.empty(max(nseq, 1), torch.int32)
+        total = ctypes.c_int64(0)
+        check(self._L.sgc_hash_positions(self._h, self.ptr(d_seq), nbytes, self.ptr(d_off), nseq, int(ksize),
+                                         self.ptr(d_hash), self.ptr(d_aux), cap, self.ptr(d_koff), self.ptr(d_stat),
+                                         ctypes.byref(total)))
+        self.sync()
+        return d_hash[: total.value], d_aux[: total.value], d_koff, d_stat[:nseq]
+
     def pack_reads(self, seq, off):
         """ASCII reads on the device (or host arrays, uploaded) -> 2-bit packed records on the device.
         -> (packed uint8 tensor, lengths int32 tensor, status int32 tensor)"""
@@ -208,11 +228,12 @@ def get_context(device=None):
 class DeviceTable:
     """GPU-resident exact map u64 k-mer hash -> u32 unitig id (``sgc_table``)."""
 
-    def __init__(self, ctx, max_entries, home_shift=0, load=0.0):
+    def __init__(self, ctx, max_entries, home_shift=0, load=0.0, shared=False):
         self.ctx = ctx
         self._L = ctx._L
         h = ctypes.c_void_p()
-        check(self._L.sgc_table_create(ctx._h, int(max_entries), float(load), ctypes.byref(h)))
+        create = self._L.sgc_table_create_shared if shared else self._L.sgc_table_create  # shared: mappable by peers
+        check(create(ctx._h, int(max_entries), float(load), ctypes.byref(h)))
         self._h = h
         self.max_entries = int(max_entries)
         if home_shift:
@@ -241,6 +262,49 @@ class DeviceTable:
         if d_h.numel() != d_v.numel():
             raise ValueError("hashes and ids differ in length")
         check(self._L.sgc_table_insert_pairs(self._h, c.ptr(d_h), c.ptr(d_v), d_h.numel()))
+
+    def insert_triples(self, hashes, ids, aux, id_bounds, marks_cap=None):
+        """Owner side of a partitioned build with a sequence store: insert (hash, id, position | strand) triples.
+        -> int64 CUDA tensor of break marks (shard << 32 | position) for the replicated store."""
+        torch = _torch()
+        c = self.ctx
+        d_h = c.to_device(hashes, np.uint64)
+        d_v = c.to_device(ids, np.uint32)
+        d_a = c.to_device(aux, np.uint32)
+        n = d_h.numel()
+        if d_v.numel() != n or d_a.numel() != n:
+            raise ValueError("hashes, ids and aux differ in length")
+        # repeated hashes are rare in a cDBG (multicounts); a list that overflows cannot be redone in place (the
+        # table has changed), so it is sized generously and an overflow is an error
+        cap = int(marks_cap) if marks_cap is not None else max(1 << 20, n // 8)
+        bounds = (ctypes.c_uint32 * len(id_bounds))(*[int(b) for b in id_bounds])
+        d_m = c.empty(cap, torch.int64)
+        nm = ctypes.c_int64(0)
+        check(self._L.sgc_table_insert_triples(self._h, c.ptr(d_h), c.ptr(d_v), c.ptr(d_a), n, bounds,
+                                               len(id_bounds) - 1, c.ptr(d_m), cap, ctypes.byref(nm)))
+        return d_m[: nm.value]
+
+    def bucket_ptr(self):
+        """-> (device pointer of the bucket array, mapped bytes)."""
+        ptr, nb = ctypes.c_void_p(), ctypes.c_int64(0)
+        check(self._L.sgc_table_export_fd(self._h, ctypes.byref(ptr), ctypes.byref(nb), None))
+        return ptr.value, nb.value
+
+    def export_fd(self):
+        """-> (pointer, mapped bytes, a NEW file descriptor of the bucket array) of a ``shared=True`` table; pass
+        the fd to the peer processes (``socket.send_fds``) and close it."""
+        ptr, nb, fd = ctypes.c_void_p(), ctypes.c_int64(0), ctypes.c_int(-1)
+        check(self._L.sgc_table_export_fd(self._h, ctypes.byref(ptr), ctypes.byref(nb), ctypes.byref(fd)))
+        return ptr.value, nb.value, fd.value
+
+    def set_peers(self, bucket_ptrs, id_bounds, useq_ptr, useq_stride_words, brk_ptr, brk_stride_words):
+        """Probe ``bucket_ptrs[owner(hash)]`` (peer-mapped bucket arrays of every rank, this one included) and match
+        against the replicated sequence store from now on (sgc_table_set_peers); the caller keeps the store alive."""
+        n = len(bucket_ptrs)
+        ptrs = (ctypes.c_void_p * n)(*[int(p) for p in bucket_ptrs])
+        bounds = (ctypes.c_uint32 * (n + 1))(*[int(b) for b in id_bounds])
+        check(self._L.sgc_table_set_peers(self._h, n, ptrs, bounds, ctypes.c_void_p(int(useq_ptr)), int(useq_stride_words),
+                                          ctypes.c_void_p(int(brk_ptr)), int(brk_stride_words)))
 
     def enable_side(self):
         """Allocate the unitig-ordered side array (8 B + 1 bit per k-mer); must precede insert_sequences."""

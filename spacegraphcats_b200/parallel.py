@@ -88,22 +88,25 @@ class DeviceEngine:
             per_kmer = torch.repeat_interleave(d_ids, (d_koff[1:] - d_koff[:-1]))
         return d_hash, per_kmer
 
-    def partition_pairs(self, d_hash, d_ids, world):
+    def partition_pairs(self, d_hash, d_ids, world, want_perm=False):
         torch = _torch()
         c = self.ctx
         n = d_hash.numel()
         oh = c.empty(n, torch.int64)
         oi = c.empty(n, torch.int32)
         d_boff = c.empty(world + 1, torch.int64)
+        d_perm = c.empty(max(n, 1), torch.int64) if want_perm else None
         h_boff = (ctypes.c_int64 * (world + 1))()
-        check(self._L.sgc_partition_pairs(c._h, c.ptr(d_hash), c.ptr(d_ids), n, world, c.ptr(oh), c.ptr(oi), None,
-                                          c.ptr(d_boff), h_boff))
+        check(self._L.sgc_partition_pairs(c._h, c.ptr(d_hash), c.ptr(d_ids), n, world, c.ptr(oh), c.ptr(oi),
+                                          c.ptr(d_perm) if want_perm else None, c.ptr(d_boff), h_boff))
+        if want_perm:
+            return oh, oi, list(h_boff), d_perm[:n]  # out[j] = in[perm[j]]
         return oh, oi, list(h_boff)
 
-    def new_table(self, n, home_shift):
+    def new_table(self, n, home_shift, shared=False):
         from .device import DeviceTable
 
-        return DeviceTable(self.ctx, max(n, 1), home_shift=home_shift)
+        return DeviceTable(self.ctx, max(n, 1), home_shift=home_shift, shared=shared)
 
     def insert_pairs(self, table, d_hash, d_ids):
         table.insert_pairs(d_hash, d_ids)
@@ -226,6 +229,49 @@ class DeviceEngine:
         return self.ctx.to_host(t, dtype)
 
 
+def exchange_fds(my_fd, rank, world, group=None):
+    """Every rank of ONE node offers a file descriptor to every other rank (SCM_RIGHTS over unix sockets).
+    -> list of world fds (None at ``rank``); the caller closes them."""
+    import os
+    import socket
+    import tempfile
+    import threading
+
+    import torch.distributed as dist
+
+    path = os.path.join(tempfile.gettempdir(), "sgc_b200_%d_%d.sock" % (os.getpid(), rank))
+    if os.path.exists(path):
+        os.unlink(path)
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    srv.bind(path)
+    srv.listen(world)
+
+    def serve():
+        for _ in range(world - 1):
+            conn, _ = srv.accept()
+            with conn:
+                socket.send_fds(conn, [b"f"], [my_fd])
+                conn.recv(1)  # the receiver holds its copy
+
+    th = threading.Thread(target=serve, daemon=True)
+    th.start()
+    paths = [None] * world
+    dist.all_gather_object(paths, path, group=group)
+    fds = [None] * world
+    for r in range(world):
+        if r == rank:
+            continue
+        with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as s:
+            s.connect(paths[r])
+            _, got, _, _ = socket.recv_fds(s, 1, 1)
+            fds[r] = got[0]
+            s.send(b"k")
+    th.join()
+    srv.close()
+    os.unlink(path)
+    return fds
+
+
 class PeerBuffers:
     """This rank's inbox (R regions of region_cap hashes), reply buffer (R regions of region_cap ids) and
     mailbox (per source rank: request count, request stamp, reply stamp), allocated by the library and mapped
@@ -289,12 +335,17 @@ class PeerBuffers:
 class PartitionedIndex:
     """k-mer -> unitig table hash-range partitioned over the ranks of a process group."""
 
-    def __init__(self, engine, group=None, p2p=False):
+    def __init__(self, engine, group=None, p2p=False, peer_probe=False):
         import torch.distributed as dist
 
         self.engine = engine
         self.group = group
         self.p2p = bool(p2p)  # fuse the exchange into the kernels over NVLink peer memory
+        # probe the owners' tables where they lie (peer loads over NVLink) and settle most k-mers against a
+        # replicated unitig sequence store: no exchange buffers, no collective in the label path
+        self.peer_probe = bool(peer_probe)
+        self._store = None  # (useq_all, brk_all) tensors of the replicated store
+        self._peer_tables = []  # peer-mapped bucket arrays (to be closed)
         self._peers = None
         self._need_seen = 0
         self._peers2 = None  # double-buffered peer buffers of the pipelined path
@@ -310,12 +361,123 @@ class PartitionedIndex:
         for pb in ([self._peers] if self._peers is not None else []) + list(self._peers2 or ()):
             pb.close()
         self._peers, self._peers2 = None, None
+        if self._peer_tables or self._store is not None:
+            import torch.distributed as dist
+
+            c = self.engine.ctx
+            c.sync()
+            dist.barrier(group=self.group)  # nobody is still probing this rank's table
+            for ptr, nbytes in self._peer_tables:
+                c._L.sgc_peer_unmap(c._h, ctypes.c_void_p(ptr), nbytes)
+            self._peer_tables, self._store = [], None
+            dist.barrier(group=self.group)  # nobody still maps our table
         if self.table is not None and hasattr(self.table, "close"):
             self.table.close()
         self.table = None
 
+    def _build_peer(self, seq, off, ksize, ids):
+        """Build for peer probing: every slot also records where its k-mer lies in the shard of the unitig
+        sequence store of the rank that hashed it; the store is replicated, the owners' tables are mapped
+        into every rank.  The unitig ids must be dealt to the ranks in ascending ranges."""
+        import torch.distributed as dist
+
+        from ._lib import BRK_PAD_BITS, STORE_PAD_WORDS
+
+        torch = _torch()
+        e, c, R = self.engine, self.engine.ctx, self.world
+        L = c._L
+        d_seq = c.to_device(seq, np.uint8)
+        d_off = c.to_device(off, np.int64)
+        d_ids = c.to_device(ids, np.uint32)
+        nseq, n_bytes = d_off.numel() - 1, d_seq.numel()
+        lo = hi = None
+        if nseq:
+            with e.stream():
+                u = d_ids.to(torch.int64) & 0xFFFFFFFF
+                lo, hi = int(u.min().item()), int(u.max().item())
+        d_hash, d_aux, d_koff, d_stat = c.hash_positions(d_seq, d_off, ksize)
+        bad = 1 if (nseq and bool(d_stat.any().item())) else 0
+        info = [None] * R
+        dist.all_gather_object(info, (lo, hi, n_bytes, bad), group=self.group)
+        if any(x[3] for x in info):
+            raise ValueError("Invalid base in read")
+        bounds, prev_hi = [], -1
+        for lo_r, hi_r, _, _ in info:
+            if lo_r is None:
+                lo_r, hi_r = prev_hi + 1, prev_hi
+            if lo_r <= prev_hi:
+                raise ValueError("a peer-probed partitioned table needs the unitig ids dealt to the ranks in ascending ranges")
+            bounds.append(lo_r)
+            prev_hi = max(prev_hi, hi_r)
+        bounds[0] = 0
+        bounds.append(0xFFFFFFFF)
+        max_bytes = max(x[2] for x in info)
+        with e.stream():
+            per_kmer = torch.repeat_interleave(d_ids, (d_koff[1:] - d_koff[:-1]))
+        bh, bi, boff, perm = e.partition_pairs(d_hash, per_kmer, R, want_perm=True)
+        with e.stream():
+            ba = d_aux[perm]
+        del d_hash, d_aux, per_kmer, perm
+        counts = [boff[r + 1] - boff[r] for r in range(R)]
+        e.sync()
+        with e.stream():
+            rh, rcounts = exchange(bh, counts, self.group)
+            ri, _ = exchange(bi, counts, self.group)
+            ra, _ = exchange(ba, counts, self.group)
+        del bh, bi, ba
+        self.n_local = int(sum(rcounts))
+        n_table, = self._collective_flags(self.n_local)  # the same geometry everywhere: one nbuckets for every owner
+        self.table = e.new_table(max(n_table, 1), self.bits, shared=True)
+        marks = self.table.insert_triples(rh, ri, ra, bounds)
+        del rh, ri, ra
+        # my shard of the store, then everybody's
+        ustride = (max_bytes + 15) // 16 + 2 * STORE_PAD_WORDS
+        bstride = (max_bytes + BRK_PAD_BITS + 31) // 32 + 2
+        with e.stream():
+            my_useq = torch.zeros(ustride, dtype=torch.int32, device=c.device)
+            my_brk = torch.full((bstride,), -1, dtype=torch.int32, device=c.device)
+        check(L.sgc_store_build(c._h, c.ptr(d_seq), n_bytes, c.ptr(d_off), nseq, int(ksize),
+                                ctypes.c_void_p(my_useq.data_ptr() + 4 * STORE_PAD_WORDS), c.ptr(my_brk)))
+        n_marks, = self._collective_flags(int(marks.numel()))
+        with e.stream():
+            useq_all = torch.empty(R * ustride, dtype=torch.int32, device=c.device)
+            brk_all = torch.empty(R * bstride, dtype=torch.int32, device=c.device)
+            dist.all_gather_into_tensor(useq_all, my_useq, group=self.group)
+            dist.all_gather_into_tensor(brk_all, my_brk, group=self.group)
+            if n_marks:
+                mine = torch.full((n_marks,), -1, dtype=torch.int64, device=c.device)  # -1 = no mark
+                mine[: marks.numel()] = marks
+                every = torch.empty(R * n_marks, dtype=torch.int64, device=c.device)
+                dist.all_gather_into_tensor(every, mine, group=self.group)
+                every = every[every >= 0].contiguous()
+        if n_marks and every.numel():
+            check(L.sgc_store_apply_marks(c._h, c.ptr(every), every.numel(), c.ptr(brk_all), bstride))
+        # everybody's bucket array, mapped with 2 MB pages (a file descriptor per table, passed between the ranks)
+        import os
+
+        ptr, nbytes, fd = self.table.export_fd()
+        fds = exchange_fds(fd, self.rank, R, self.group)
+        os.close(fd)
+        ptrs = []
+        for r in range(R):
+            if r == self.rank:
+                ptrs.append(ptr)
+            else:
+                p = ctypes.c_void_p()
+                check(L.sgc_peer_import_fd(c._h, fds[r], nbytes, ctypes.byref(p)))
+                os.close(fds[r])
+                self._peer_tables.append((p.value, nbytes))
+                ptrs.append(p.value)
+        self._store = (useq_all, brk_all)
+        self.table.set_peers(ptrs, bounds, useq_all.data_ptr() + 4 * STORE_PAD_WORDS, ustride, brk_all.data_ptr(), bstride)
+        c.sync()
+        dist.barrier(group=self.group)  # every table is complete before anybody probes it
+        return self
+
     def build(self, seq, off, ksize, ids):
         """Every rank passes ITS shard of the unitigs (ids are global cDBG ids)."""
+        if self.peer_probe:
+            return self._build_peer(seq, off, ksize, ids)
         e = self.engine
         d_hash, d_ids = e.hash_pairs(seq, off, ksize, ids)
         bh, bi, boff = e.partition_pairs(d_hash, d_ids, self.world)
@@ -628,6 +790,11 @@ class PartitionedIndex:
     def label_reads(self, seq, off, ksize):
         """index_reads' per-read step against the partitioned table.
         -> (ids_off, ids, n_hits) as engine tensors"""
+        if self.peer_probe:  # the ordinary label call: the kernel itself goes to the owners' memory
+            res = self.table.label_reads(seq, off, ksize, to_host=False)
+            if res["status"].numel() and bool(res["status"].any().item()):
+                raise ValueError("Invalid base in read")
+            return res["ids_off"], res["ids"], res["n_hits"]
         if self.p2p and hasattr(self.engine, "partition_hashes"):
             import os
 

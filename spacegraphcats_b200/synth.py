@@ -82,7 +82,9 @@ class SyntheticCdbg:
         from .device import DeviceTable
 
         if side is None:
-            side = os.environ.get("SGC_SIDE", "1") != "0" and self.total_unitig_kmers < (1 << 30) - 2
+            from .cdbg.hashing import side_default
+
+            side = side_default(int(self.useq.numel()))
 
         t = DeviceTable(self.ctx, self.total_unitig_kmers)
         if side:

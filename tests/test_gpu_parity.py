@@ -897,6 +897,96 @@ def test_fused_partition_and_gather_single_gpu(ctx, O):
     assert np.array_equal(ctx.to_host(kids, np.uint32), whole.lookup_sequences(rbuf, roff, k)["kmer_ids"])
 
 
+def test_peer_probed_partitioned_table_single_gpu(ctx, O):
+    """The peer-probe path (sgc_hash_positions / sgc_table_insert_triples / sgc_store_build / sgc_table_set_peers)
+    with R=4 owners emulated on one GPU: four unitig shards with ascending id ranges, four owner tables, the
+    store replicated; labels through every owner's handle == the oracle's.  Unitigs repeat across shards
+    (multicounts: marks must reach the replicated break bits) and inside one shard (same id)."""
+    import ctypes
+
+    import torch
+
+    from spacegraphcats_b200._lib import BRK_PAD_BITS, STORE_PAD_WORDS, check
+    from spacegraphcats_b200.device import DeviceTable, pack_sequences
+
+    rng = np.random.default_rng(81)
+    k, R = 31, 4
+    lut = np.frombuffer(b"ACGT", np.uint8)
+    g = lut[rng.integers(0, 4, 120_000)]
+    cuts = np.concatenate([[0], np.cumsum(rng.integers(1, 150, 3000))])
+    cuts = cuts[cuts < len(g) - k]
+    useqs = [g[a : b + k - 1].tobytes() for a, b in zip(cuts[:-1], cuts[1:])]
+    n = len(useqs)
+    useqs += [useqs[5], useqs[n // 2], useqs[n - 3]]  # the same unitigs under other ids: multicounts across shards
+    ids = np.arange(len(useqs), dtype=np.uint32)
+    reads = [g[p : p + int(m)].tobytes() for p, m in zip(rng.integers(0, len(g) - 700, 5000), rng.integers(0, 700, 5000))]
+    reads = [bytes(r[::-1].translate(bytes.maketrans(b"ACGT", b"TGCA"))) if i % 2 else r for i, r in enumerate(reads)]
+    rbuf, roff = pack_sequences(reads)
+    L = ctx._L
+    # the shards (ascending id ranges), their triples bucketed by owner
+    sh_lo = [len(useqs) * r // R for r in range(R + 1)]
+    bounds = [0] + sh_lo[1:R] + [0xFFFFFFFF]
+    per_owner = [[] for _ in range(R)]
+    shards = []
+    for r in range(R):
+        sbuf, soff = pack_sequences(useqs[sh_lo[r] : sh_lo[r + 1]])
+        d_seq, d_off = ctx.to_device(sbuf, np.uint8), ctx.to_device(soff, np.int64)
+        h, aux, koff, stat = ctx.hash_positions(d_seq, d_off, k)
+        assert not bool(stat.any())
+        with torch.cuda.stream(ctx.stream):
+            d_ids = ctx.to_device(ids[sh_lo[r] : sh_lo[r + 1]], np.uint32)
+            per = torch.repeat_interleave(d_ids, koff[1:] - koff[:-1])
+            owner = (h >> 62) & 3
+            for o in range(R):
+                sel = owner == o
+                per_owner[o].append((h[sel], per[sel], aux[sel]))
+        shards.append((d_seq, d_off, len(sbuf)))
+    max_bytes = max(s[2] for s in shards)
+    ustride = (max_bytes + 15) // 16 + 2 * STORE_PAD_WORDS
+    bstride = (max_bytes + BRK_PAD_BITS + 31) // 32 + 2
+    with torch.cuda.stream(ctx.stream):
+        useq_all = torch.zeros(R * ustride, dtype=torch.int32, device=ctx.device)
+        brk_all = torch.full((R * bstride,), -1, dtype=torch.int32, device=ctx.device)
+    for r, (d_seq, d_off, nb) in enumerate(shards):
+        check(L.sgc_store_build(ctx._h, ctx.ptr(d_seq), nb, ctx.ptr(d_off), d_off.numel() - 1, k,
+                                ctypes.c_void_p(useq_all.data_ptr() + 4 * (r * ustride + STORE_PAD_WORDS)),
+                                ctypes.c_void_p(brk_all.data_ptr() + 4 * r * bstride)))
+    n_max = max(sum(int(t[0].numel()) for t in per_owner[o]) for o in range(R))
+    tables, marks = [], []
+    for o in range(R):
+        t = DeviceTable(ctx, n_max, home_shift=2, shared=(o % 2 == 0))  # both kinds of bucket memory
+        with torch.cuda.stream(ctx.stream):
+            hh, vv, aa = (torch.cat([x[j] for x in per_owner[o]]) for j in range(3))
+        marks.append(t.insert_triples(hh, vv, aa, bounds))
+        tables.append(t)
+    with torch.cuda.stream(ctx.stream):
+        every = torch.cat(marks).contiguous()
+    assert every.numel() >= 6  # three repeated unitigs: both copies of each of their k-mers are fenced off
+    check(L.sgc_store_apply_marks(ctx._h, ctx.ptr(every), every.numel(), ctx.ptr(brk_all), bstride))
+    ptrs = [t.bucket_ptr()[0] for t in tables]
+    for t in tables:
+        t.set_peers(ptrs, bounds, useq_all.data_ptr() + 4 * STORE_PAD_WORDS, ustride, brk_all.data_ptr(), bstride)
+    # the oracle's answer
+    ubuf, uoff = pack_sequences(useqs)
+    hs, koff = O.hash_batch(ubuf, uoff, k)
+    pid = np.repeat(ids, np.diff(koff))
+    order = np.argsort(hs, kind="stable")
+    hs, pid = hs[order], pid[order]
+    first = np.flatnonzero(np.concatenate([[True], hs[1:] != hs[:-1]]))
+    lo_id, hi_id = np.minimum.reduceat(pid, first), np.maximum.reduceat(pid, first)
+    keep = lo_id == hi_id  # build_mphf: a hash seen under two different ids is dropped
+    assert (~keep).sum() >= 3
+    otab = O.COracleTable(hs[first][keep], lo_id[keep])
+    o_off, o_ids, o_nk, o_nh = otab.label_reads(rbuf, roff, k)
+    for packed in (False, True):
+        for t in (tables[0], tables[3]):
+            res = t.label_reads(rbuf, roff, k, packed=packed)
+            assert np.array_equal(res["ids_off"], o_off) and np.array_equal(res["ids"], o_ids), packed
+            assert (res["n_kmers"], res["n_hits"]) == (o_nk, o_nh)
+    for t in tables:
+        t.close()
+
+
 def test_partitioned_two_gpus_p2p_and_nccl_match_replicated():
     """2 ranks on 2 GPUs (skipped on a 1-GPU box): hash-range partitioned table, exchange fused into
     the kernels over NVLink peer memory (--p2p) and through NCCL all-to-all; both must give the
@@ -912,7 +1002,8 @@ def test_partitioned_two_gpus_p2p_and_nccl_match_replicated():
 
     # flag protocol (default: one call per step, ranks synchronised through peer-memory stamps), the host-mediated
     # P2P path (counts exchange + barrier) and the NCCL all-to-all baseline
-    for extra, env in ((["--p2p"], {}), (["--p2p"], {"SGC_PART_FLAGS": "0"}), ([], {})):
+    # ... and first the product path: the owners' tables probed over peer loads + the replicated sequence store
+    for extra, env in ((["--peer"], {}), (["--p2p"], {}), (["--p2p"], {"SGC_PART_FLAGS": "0"}), ([], {})):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                "127.0.0.1", "--master-port", "29547", os.path.join(ROOT, "scripts", "partitioned_run.py"),
                "--table-kmers", "2e7", "--reads", "3e5", "--steps", "3", "--check"] + extra
