@@ -301,7 +301,7 @@ def partitioned_arm(args, ctx, rank, world):
         useq = cdbg.useq[b0:b1]
         uoff = (cdbg.uoff[ulo:uhi + 1] - b0).contiguous()
         ids = torch.arange(ulo, uhi, dtype=torch.int32, device=ctx.device)
-    idx = PartitionedIndex(DeviceEngine(ctx), p2p=True).build(useq, uoff, KSIZE, ids)
+    idx = PartitionedIndex(DeviceEngine(ctx), p2p=True, peer_probe=not args.part_exchange).build(useq, uoff, KSIZE, ids)
     ctx.sync()
     log("[rank %d] partitioned build %.1fs: %d of %d hashes (%.2f GB) on this rank"
         % (rank, time.time() - t0, idx.n_local, total_kmers, idx.table.nbytes / 1e9))
@@ -357,14 +357,19 @@ def partitioned_arm(args, ctx, rank, world):
         "steps": args.part_steps, "table_kmers": total_kmers, "table_kmers_per_gpu": args.part_kmers_per_gpu,
         "table_bytes_per_gpu": table_bytes, "reads_per_rank_step": n_reads, "labels_per_read": labels_per_read,
         "labels_identical_to_replicated": ok, "gpu_launches": int(launches),
-        "exchange": "requests / replies stored straight into peer memory over NVLink (CUDA IPC), no NCCL on the data path",
+        "exchange": ("requests / replies stored straight into peer memory over NVLink (CUDA IPC), no NCCL on the data path"
+                     if args.part_exchange else
+                     "none: the label kernel loads each home bucket (32 B) straight from its owner GPU's table over NVLink "
+                     "(bucket arrays shared with cuMemCreate + POSIX fds); one k-mer in sixteen + the unsettled ones are "
+                     "probed, the rest is compared with the replicated unitig sequence store; no collective in the label path"),
         "workload": "synthetic cDBG, %d unitig k-mers k=%d hash-range partitioned across %d B200 (BASELINE.json configs[4]), "
                     "150bp reads labelled by index_reads" % (total_kmers, KSIZE, world),
         "roofline": {"bound": "nvlink", "achieved": achieved, "peak": 770.0, "unit": "GB/s", "frac": achieved / 770.0,
                      "peak_source": "measured peer copy, B200_PROFILING.md",
-                     "note": "(R-1)/R x 12 B per k-mer per GPU and direction over the whole step (SURVEY 8d: 73 G k-mers/s "
-                             "per GPU at R=8); every k-mer is one random 128-byte HBM line on its owner, which caps a GPU "
-                             "at the measured 36-46 G random lines/s whatever the link does"},
+                     "note": "achieved = SURVEY 8d's algorithmic figure, (R-1)/R x 12 B per k-mer per GPU and direction, over "
+                             "the whole step (73 G k-mers/s per GPU at R=8).  What the link really carries here is one 32-byte "
+                             "load per PROBED k-mer (~0.25 per k-mer); a B200 serves 6.8 G random 32-byte loads/s from "
+                             "another process's memory over NVLink (scripts/peer_probe.cu, profiles/r02_peer_probe_microbench.txt)"},
     }
 
 
@@ -538,6 +543,8 @@ def main():
     ap.add_argument("--part-reads", type=int, default=1 << 22, help="reads per rank and step of the partitioned arm")
     ap.add_argument("--part-steps", type=int, default=10)
     ap.add_argument("--no-partitioned", action="store_true")
+    ap.add_argument("--part-exchange", action="store_true",
+                    help="partitioned arm through the request / reply exchange of round 1 instead of peer probing")
     ap.add_argument("--no-part-check", action="store_true")
     ap.add_argument("--query-kmers", type=int, default=500_000, help="k-mers per query sequence (acido-chunk shape)")
     ap.add_argument("--queries", type=int, default=512, help="query sequences per step of the query arm")
