@@ -13,9 +13,13 @@
 // lookup of that position's hash returns the anchor's id (brk[p] is set at the first k-mer of every
 // sequence, at every position that holds no k-mer, at every k-mer whose hash the table keeps under another
 // position, and at every dropped multicount hash -- set by the build, sgc_table.cuh:table_insert).  Whatever
-// is not settled that way -- sequencing errors, unitig ends, a missing anchor -- is queued and then hashed
-// and probed like an anchor, one item per lane.  The labels are therefore exactly those of per-k-mer probing
-// (tile_kernel<K, MODE_LABEL>), with a quarter of the hashes and of the table lines.
+// is not settled that way is queued as follow-up work of the same round: a k-mer that overlaps a mismatching
+// base (a sequencing error) is hashed and probed on its own; the k-mers past a break (the read runs on into the
+// next unitig) become a RUN of their own, anchored at the first k-mer past the break; and when the anchor itself
+// is missing, the run is turned around once and anchored at its far end (an error early in the anchor leaves the
+// last followers intact).  Every k-mer is thus either probed or proven equal to a store position whose lookup
+// result is known: the labels are exactly those of per-k-mer probing (tile_kernel<K, MODE_LABEL>), with about a
+// fifth of the hashes and of the table lines.
 //
 // Layout of the work
 //   * a warp round is SPW segments of <= 128 k-mers (a 150-bp read is one segment); its work items are the
@@ -48,6 +52,9 @@ static_assert(USEQ_PAD == SGC_STORE_PAD_WORDS && BRK_PAD == SGC_BRK_PAD_BITS, "i
 #ifndef SGC_LS_SPW
 #define SGC_LS_SPW 4
 #endif
+#ifndef SGC_LS_REANCHOR
+#define SGC_LS_REANCHOR 1   // 0: every unsettled k-mer is probed on its own (no follow-up runs)
+#endif
 constexpr int NTS = SGC_LS_NT;    // threads per CTA of the labelseq kernel
 constexpr int WPBS = NTS / 32;
 
@@ -63,6 +70,7 @@ struct GeoS {
     static constexpr int RAWW = PACKED ? ((SEGB + 63) / 64) * 4 : WPS;  // words of the raw copy of a segment
     static constexpr int QCAP = SPW * SEG_KS;                       // a round queues at most its own k-mers
     static_assert(32 % SPW == 0, "lanes per segment");
+    static_assert(SPW <= 4 && SEG_KS <= 128 && GK <= 16, "a queued run is 15 bits: k-mer 7, segment 2, followers 4, back, flagged");
 };
 
 struct LabelSeqArgs {
@@ -98,7 +106,7 @@ struct alignas(16) WarpTileS {
     uint32_t P[G::SPW * G::PWS];       // the round's segments, 2 bits per base
     SegDesc D[3][G::SPW];
     unsigned long long pairs[PAIRS_S];
-    unsigned short q[G::QCAP];         // queued k-mers of this round: segment << 8 | k-mer index
+    unsigned short q[G::QCAP];         // queued runs of this round: k-mer | segment << 7 | followers << 9 | back << 13 | flagged << 14
     int gpre[G::SPW + 1];
     unsigned qfill;
     unsigned segbad;                   // bit sg: segment sg holds a byte that is not A/C/G/T (ASCII input)
@@ -373,30 +381,38 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
             if (t0 >= ng + nq) break;
             t1 = t0 + 32 < ng + nq ? t0 + 32 : ng + nq;
             const int item = t0 + lane;
-            const bool act = item < ng + nq, anchor = item < ng;
-            int sg = 0, q = 0;
-            if (anchor) {
+            const bool act = item < ng + nq;
+            // an item is a RUN: its anchor k-mer qa (hashed and probed here) and n-1 followers, the k-mers after
+            // it (back = false) or before it (back = true); flagged = a miss may not turn the run around again
+            int sg = 0, qa = 0, n = 1;
+            bool back = false, flagged = false;
+            if (item < ng) {
 #pragma unroll
                 for (int s = 1; s < SPW; s++) sg += item >= gpre[s];
-                q = (item - gpre[sg]) * GK;
+                qa = (item - gpre[sg]) * GK;
+                n = GK;
             } else if (act) {
                 const unsigned u = wt.q[item - ng];
-                sg = (int)(u >> 8);
-                q = (int)(u & 0xFFu);
+                qa = (int)(u & 127u);
+                sg = (int)((u >> 7) & 3u);
+                n = (int)((u >> 9) & 15u) + 1;
+                back = (u >> 13) & 1u;
+                flagged = (u >> 14) & 1u;
             }
             const SegDesc& d = wt.D[cur][sg];
             const int nk = d.nk;
+            if (item < ng && nk - qa < GK) n = nk - qa;
             const uint32_t* Fs = wt.F + sg * WPS + FOFF;
             const uint32_t* Rs = wt.R + sg * WPS;
 
-            // hash of k-mer q of segment sg (idle lanes hash k-mer 0 of segment 0: staged or stale words, unused)
+            // hash of k-mer qa of segment sg (idle lanes hash k-mer 0 of segment 0: staged or stale words, unused)
             uint64_t hf, hr;
-            const int rb = sgc::rc_byte_of(nk, nk - 1 - q);
+            const int rb = sgc::rc_byte_of(nk, nk - 1 - qa);
             if constexpr (K != 0) {
-                hf = sgc::murmur3_h1_window<K ? K : 1>(Fs + (q >> 2), q & 3);
+                hf = sgc::murmur3_h1_window<K ? K : 1>(Fs + (qa >> 2), qa & 3);
                 hr = sgc::murmur3_h1_window<K ? K : 1>(Rs + (rb >> 2), rb & 3);
             } else {
-                hf = act ? sgc::murmur3_h1_stream(Fs, q, k) : 0ULL;
+                hf = act ? sgc::murmur3_h1_stream(Fs, qa, k) : 0ULL;
                 hr = act ? sgc::murmur3_h1_stream(Rs, rb, k) : 0ULL;
             }
             const uint64_t h = hf ^ hr;
@@ -417,14 +433,17 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
             }
             unsigned nhit = v != SGC_MISS;
 
-            if (t0 < ng) {  // warp-uniform: this trip holds anchors
-                unsigned pending = 0;
-                if (anchor) {
-                    const int nv = nk - q < GK ? nk - q : GK;
-                    const unsigned valid = (1u << nv) - 1u;
+            const bool is_run = act && n > 1;
+            if (__any_sync(0xffffffffu, is_run)) {  // warp-uniform: this trip holds runs
+                unsigned singles = 0;          // followers to probe one by one, bit i = k-mer lo + i
+                unsigned run_item = 0u;        // a follow-up run (encoded, bit 15 set) or 0
+                int lo = qa;
+                if (is_run) {
+                    lo = back ? qa - (n - 1) : qa;
+                    const int ao = back ? n - 1 : 0;            // the anchor's place in the window of k-mers lo .. lo+n-1
+                    const unsigned valid = (1u << n) - 1u;
                     const uint32_t gp = aux & AUX_MASK;
                     const bool has_g = v != SGC_MISS && gp != AUX_NONE && !((wt.segbad >> sg) & 1u);
-                    unsigned m = 1u;
                     if (has_g) {
                         const bool along = ((aux & ORI_BIT) != 0) == (hf < hr);
                         const uint32_t* useq = a.useq;
@@ -438,21 +457,26 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                         // break bits of positions gp-15 .. gp+16
                         const uint32_t bi = gp + (uint32_t)(BRK_PAD - (GK - 1));
                         const uint32_t w0 = __ldg(brkp + (bi >> 5)), w1 = __ldg(brkp + (bi >> 5) + 1);
-                        unsigned clean;
+                        unsigned clean;  // bit i: the k bases of k-mer lo+i equal the store's
                         if constexpr (K != 0) {
                             constexpr int WL = GK - 1 + (K ? K : 1);   // bases of a full window
                             constexpr int NWD = (WL + 15) / 16;
                             static_assert(NWD <= 3 || K == 0, "window words");
-                            const uint32_t* Pw = wt.P + sg * PWS + (q >> 4);  // q % 16 == 0
-                            const int wsi = (int)gp - (along ? 0 : GK - 1);     // first store position of the window
+                            // read k-mer lo+i lies at store position gp + (i - ao) (along) or gp - (i - ao): the window's
+                            // base j is store base wsi + j, resp. the complement of store base wsi + WL - 1 - j
+                            const int wsi = along ? (int)gp - ao : (int)gp + ao - (GK - 1);
                             const uint32_t* up = useq + (wsi >> 4);
                             const int sh = 2 * (wsi & 15);
-                            uint32_t u[NWD + 1], un[NWD], rd[NWD];
+                            const uint32_t* Pw = wt.P + sg * PWS + (lo >> 4);
+                            const int rsh = 2 * (lo & 15);
+                            uint32_t u[NWD + 1], pw[NWD + 1], un[NWD], rd[NWD];
 #pragma unroll
                             for (int j = 0; j <= NWD; j++) u[j] = __ldg(up + j);
 #pragma unroll
+                            for (int j = 0; j <= NWD; j++) pw[j] = Pw[j];
+#pragma unroll
                             for (int j = 0; j < NWD; j++) {
-                                rd[j] = Pw[j];
+                                rd[j] = __funnelshift_r(pw[j], pw[j + 1], rsh);
                                 un[j] = __funnelshift_r(u[j], u[j + 1], sh);
                             }
                             if (!along) {  // reverse complement of the WL-base window
@@ -467,8 +491,8 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                                     un[j] = ~(((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1));
                                 }
                             }
-                            // mismatching bases among the nv-1+K the group really has: first (f) and last (l)
-                            const int wn = nv - 1 + K;
+                            // mismatching bases among the n-1+K the run really has: first (f) and last (l)
+                            const int wn = n - 1 + K;
                             int f = WL + GK, l = -1;
 #pragma unroll
                             for (int j = NWD - 1; j >= 0; j--) {
@@ -481,19 +505,20 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                                     if (l < 0) l = 16 * j + ((31 - __clz((int)x)) >> 1);
                                 }
                             }
-                            // follower d is clean when its k bases avoid every mismatch: d + K - 1 < f, or d > l
+                            // k-mer i is clean when its k bases avoid every mismatch: i + K - 1 < f, or i > l
                             const unsigned clean_a = f >= K ? (f - K + 1 >= GK ? 0xFFFFu : (1u << (f - K + 1)) - 1u) : 0u;
                             const unsigned clean_b = l < 0 ? 0xFFFFu : (l >= GK - 1 ? 0u : (0xFFFFu << (l + 1)) & 0xFFFFu);
                             clean = clean_a | clean_b;
                         } else {
-                            // any k: walk the bases until the first mismatch
+                            // any k: walk the bases away from the anchor until the first mismatch
                             const uint32_t* Pw = wt.P + sg * PWS;
-                            const int wn = nv - 1 + k;
+                            const int wn = n - 1 + k;
                             int f = wn;
                             for (int j = 0; j < wn; j++) {
-                                const int rbp = q + j;
+                                const int t = back ? k - 1 - j : j;        // base offset from the anchor's first base
+                                const int rbp = qa + t;
                                 const uint32_t rbase = (Pw[rbp >> 4] >> (2 * (rbp & 15))) & 3u;
-                                const int pos = along ? (int)gp + j : (int)gp + k - 1 - j;
+                                const int pos = along ? (int)gp + t : (int)gp + k - 1 - t;
                                 uint32_t ub = (__ldg(useq + (pos >> 4)) >> (2 * (pos & 15))) & 3u;
                                 if (!along) ub ^= 3u;
                                 if (rbase != ub) {
@@ -501,19 +526,45 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                                     break;
                                 }
                             }
-                            clean = f >= k ? (f - k + 1 >= GK ? 0xFFFFu : (1u << (f - k + 1)) - 1u) : 0u;
+                            // the anchor and its first c-1 followers are clean; as bits of the window lo .. lo+n-1
+                            const int c = f >= k ? (f - k + 1 >= n ? n : f - k + 1) : 0;
+                            const unsigned pre = (1u << c) - 1u;
+                            clean = back ? pre << (n - c) : pre;
                         }
                         const uint32_t bits = __funnelshift_r(w0, w1, bi & 31u);  // bit b = position gp-15+b
-                        // followers 1..lim may inherit: no break in (gp, gp+d] resp. (gp-d, gp]
-                        const unsigned lim = along ? (unsigned)__ffs((int)((bits >> 16) | 0x8000u)) - 1u
-                                                   : (unsigned)__clz((int)((bits << 16) | 0x10000u));
-                        m = ((clean & ((2u << lim) - 1u)) | 1u) & valid;
-                        nhit = (unsigned)__popc(m);
+                        // the lim followers next to the anchor may inherit its id: no break in (gp, gp+d] resp. (gp-d, gp]
+                        const unsigned lim = along != back ? (unsigned)__ffs((int)((bits >> 16) | 0x8000u)) - 1u
+                                                           : (unsigned)__clz((int)((bits << 16) | 0x10000u));
+                        const unsigned inh = back ? ((int)lim >= n - 1 ? valid : valid & ~((1u << (n - 1 - (int)lim)) - 1u))
+                                                  : ((2u << lim) - 1u) & valid;
+                        const unsigned settled = ((clean & inh) | (1u << ao)) & valid;
+                        nhit = (unsigned)__popc(settled);
+                        singles = inh & ~settled;
+#if SGC_LS_REANCHOR
+                        if (valid & ~inh) {  // the k-mers past the break: a run of their own, anchored next to the break
+                            const int n2 = n - 1 - (int)lim;
+                            const int qa2 = back ? qa - ((int)lim + 1) : qa + (int)lim + 1;
+                            run_item = 0x8000u | (flagged ? 1u << 14 : 0u) | (back ? 1u << 13 : 0u) | ((unsigned)(n2 - 1) << 9) |
+                                       ((unsigned)sg << 7) | (unsigned)qa2;
+                        }
+#else
+                        singles |= valid & ~inh;
+#endif
+                    } else {
+                        // no anchor: the far end of the run may be one (a sequencing error early in the anchor leaves
+                        // the last followers intact); a second miss probes what is left one by one
+#if SGC_LS_REANCHOR
+                        if (!flagged && n > 2 && !((wt.segbad >> sg) & 1u) && (v == SGC_MISS)) {
+                            const int qa2 = back ? qa - (n - 1) : qa + (n - 1);
+                            run_item = 0x8000u | (1u << 14) | (back ? 0u : 1u << 13) | ((unsigned)(n - 2) << 9) | ((unsigned)sg << 7) |
+                                       (unsigned)qa2;
+                        } else
+#endif
+                            singles = valid & ~(1u << ao);
                     }
-                    pending = valid & ~m;
                 }
                 // queue what the store did not settle (in item order: a read's k-mers stay neighbours)
-                const int cnt = __popc(pending);
+                const int cnt = __popc(singles) + (run_item ? 1 : 0);
                 int incl = cnt;
 #pragma unroll
                 for (int dd = 1; dd < 32; dd <<= 1) {
@@ -523,11 +574,13 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
                 if (total) {
                     int pos = nq + incl - cnt;
-                    while (pending) {
-                        const int dd = __ffs((int)pending) - 1;
-                        pending &= pending - 1u;
-                        wt.q[pos++] = (unsigned short)((sg << 8) | (q + dd));
+                    const unsigned one = (1u << 14) | ((unsigned)sg << 7);
+                    while (singles) {
+                        const int dd = __ffs((int)singles) - 1;
+                        singles &= singles - 1u;
+                        wt.q[pos++] = (unsigned short)(one | (unsigned)(lo + dd));
                     }
+                    if (run_item) wt.q[pos] = (unsigned short)(run_item & 0x7FFFu);
                     __syncwarp();
                     if (lane == 0) wt.qfill = (unsigned)(nq + total);
                 }

@@ -806,3 +806,96 @@ class PartitionedIndex:
         kmer_ids, koff = self.lookup_sequences(seq, off, ksize)
         nseq = koff.numel() - 1 if hasattr(koff, "numel") else len(koff) - 1
         return self.engine.labels_from_ids(kmer_ids, koff, nseq)
+
+
+# ----------------------------------------------------------------------------------------------
+# Replicated table, sharded queries ("query batches shard naturally")
+# ----------------------------------------------------------------------------------------------
+def allgather_var(t, group=None):
+    """All-gather of 1-D tensors of different lengths (same dtype / device on every rank).
+    -> list of world tensors (rank order).  Two collectives: the lengths, then the rows padded to the longest."""
+    torch = _torch()
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+    ns = [torch.empty_like(n) for _ in range(world)]
+    dist.all_gather(ns, n, group=group)
+    ns = [int(x.item()) for x in ns]
+    m = max(ns + [1])
+    pad = torch.zeros(m, dtype=t.dtype, device=t.device)
+    pad[: t.numel()] = t
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    return [o[:c] for o, c in zip(out, ns)]
+
+
+def allreduce_counts(counts, group=None):
+    """Per-unitig count vectors of the ranks' shards -> their sum on every rank, in place
+    (``ncclAllReduce(sum, u32[n_ids])`` of SURVEY.md 8e; u32 travels as i32, the sum wraps the same way)."""
+    torch = _torch()
+    import torch.distributed as dist
+
+    v = counts.view(torch.int32) if counts.dtype != torch.int32 else counts
+    dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group)
+    return counts
+
+
+def count_matches_batch_sharded(count_batch, queries, ksize, device=None, group=None):
+    """``count_cdbg_matches`` of many queries on R ranks that all hold the (replicated) table: rank r answers
+    the contiguous range ``shard_range(len(queries), r, R)`` -- a query's k-mer SET must be formed on one rank,
+    so whole queries are the unit -- and the sparse per-query results are all-gathered, so every rank returns
+    the complete list.  search/query_by_sequence.py:153-189 for every query; SURVEY.md 8e.
+
+    ``count_batch(list of queries, ksize)`` -> list of (``{unitig: count}``, n_distinct) is the per-rank
+    engine: ``GpuKmerTable.count_matches_batch`` in the product, an oracle-backed callable in the gloo tests.
+    ``device``: where the exchanged arrays live (the rank's GPU under NCCL, None = CPU under gloo)."""
+    torch = _torch()
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lo, hi = shard_range(len(queries), rank, world)
+    mine = count_batch(queries[lo:hi], ksize) if hi > lo else []
+    npairs = np.array([len(c) for c, _ in mine], np.int64)
+    ids = np.fromiter((i for c, _ in mine for i in c.keys()), np.int64, int(npairs.sum()))
+    cnt = np.fromiter((v for c, _ in mine for v in c.values()), np.int64, int(npairs.sum()))
+    nd = np.array([d for _, d in mine], np.int64)
+
+    def dev(a):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        return t.to(device) if device is not None else t
+
+    g_np, g_ids, g_cnt, g_nd = (allgather_var(dev(a), group) for a in (npairs, ids, cnt, nd))
+    out = []
+    for r in range(world):
+        rnp, rids, rcnt, rnd = (x[r].cpu().numpy() for x in (g_np, g_ids, g_cnt, g_nd))
+        o = np.concatenate([[0], np.cumsum(rnp)])
+        for j in range(len(rnp)):
+            a, b = int(o[j]), int(o[j + 1])
+            out.append((dict(zip(rids[a:b].tolist(), rcnt[a:b].tolist())), int(rnd[j])))
+    assert len(out) == len(queries)
+    return out
+
+
+def abundance_sharded(lookup_counts, buf, off, ksize, n_ids, device=None, group=None):
+    """Per-unitig k-mer abundance of a read set on R ranks with replicated tables (the loop of
+    search/count_dominator_abundance.py:80-97, no de-duplication): rank r looks up the k-mers of its contiguous
+    range of sequences, the u32[n_ids] count vectors are summed with one all-reduce.
+
+    ``lookup_counts(buf, off, ksize, n_ids)`` -> (count_by_id u32[n_ids] numpy, n_kmers, n_hits) for a shard.
+    -> (count_by_id numpy u32[n_ids], n_kmers, n_hits) of the whole set, on every rank."""
+    torch = _torch()
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    off = np.asarray(off, np.int64)
+    lo, hi = shard_range(len(off) - 1, rank, world)
+    sub = np.asarray(buf)[off[lo]: off[hi]]
+    cnt, nk, nh = lookup_counts(sub, off[lo: hi + 1] - off[lo], ksize, n_ids)
+    t = torch.from_numpy(np.ascontiguousarray(cnt, np.uint32).view(np.int32).copy())
+    tot = torch.tensor([nk, nh], dtype=torch.int64)
+    if device is not None:
+        t, tot = t.to(device), tot.to(device)
+    allreduce_counts(t, group)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy().view(np.uint32), int(tot[0].item()), int(tot[1].item())
