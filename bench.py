@@ -427,6 +427,37 @@ def query_arm(args, ctx, table, cdbg, rank, world):
     value = world * step_kmers * args.query_steps / (ms / 1e3)
     distinct = int(d_qd.sum().item())
 
+    # N >= 2: the same steps with the sparse results all-gathered, so that every rank ends up with the answers of
+    # ALL ranks' queries (query batches shard across the ranks; parallel.count_matches_batch_sharded is
+    # the host-level form of this step)
+    sharded = None
+    if world > 1:
+        from spacegraphcats_b200.parallel import allgather_var
+
+        def sharded_step(i):
+            npairs, _, _ = run(*batches[i % nb])
+            with torch.cuda.stream(ctx.stream):
+                ks = allgather_var(d_keys[:npairs], None)
+                cs = allgather_var(d_cnt[:npairs], None)
+                qd = [torch.empty_like(d_qd) for _ in range(world)]
+                dist.all_gather(qd, d_qd)
+            return sum(int(k.numel()) for k in ks), cs, qd
+
+        sharded_step(0)
+        barrier()
+        ev0.record(ctx.stream)
+        for i in range(args.query_steps):
+            tot_pairs_all, _, _ = sharded_step(i)
+        ev1.record(ctx.stream)
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=ctx.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sms = float(t.item())
+        sharded = {"value": world * step_kmers * args.query_steps / (sms / 1e3), "unit": "k-mers/s",
+                   "ms_per_step": sms / args.query_steps, "pairs_gathered_per_step": int(tot_pairs_all),
+                   "collective": "all_gather (NCCL) of every rank's (query << 32 | unitig, count) pairs and per-query "
+                                 "distinct counts; no collective on the lookup path (replicated table)"}
+
     # e2e: pinned host sequences -> H2D -> the batch call -> D2H of the (query, unitig, count) triples
     h_seq = [torch.empty(nq * qlen, dtype=torch.uint8).pin_memory() for _ in range(nb)]
     h_off = torch.empty(nq + 1, dtype=torch.int64).pin_memory()
@@ -470,6 +501,7 @@ def query_arm(args, ctx, table, cdbg, rank, world):
                     "of its k-mer hashes -> {unitig: count}" % (nq, args.query_kmers, KSIZE, args.table_kmers),
         "queries_per_step": nq, "kmers_per_step": step_kmers, "hit_fraction": stats[2] / max(distinct, 1),
         "distinct_fraction": distinct / step_kmers, "pairs_per_query": stats[0] / nq, "gpu_launches": int(launches),
+        "sharded_with_gather": sharded,
         "e2e": {"value": world * step_kmers * args.query_steps / dt, "unit": "k-mers/s", "ms_per_step": dt / args.query_steps * 1e3,
                 "h2d_bytes_per_step": int(nq * qlen + (nq + 1) * 8 + nq * 4),
                 "d2h_bytes_per_step": int(tot_pairs // args.query_steps * 12 + nq * 8),

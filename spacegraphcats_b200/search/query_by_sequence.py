@@ -90,11 +90,12 @@ def pseudo_unitigs(sequences, ksize, piece_kmers=100):
     return out
 
 
-def query_batch(query_files, ksize, catlas, kmer_idx, scaled=None, catlas_name=None, debug=False):
+def query_batch(query_files, ksize, catlas, kmer_idx, scaled=None, catlas_name=None, debug=False, distributed=False):
     """Batched ``Query(...)`` + ``execute`` over many query files (BASELINE.json configs[2]: batched
     count_cdbg_matches over many query sequences).  ALL records of ALL queries go through one hash launch,
     one device sort and one lookup/count pass (``sgc_query_count_batch``): per query the distinct-hash set and
     its per-unitig counts, exactly ``Query.__init__`` :170-176 + ``count_cdbg_matches`` :189.
+    ``distributed=True`` (inside an initialised ``torch.distributed`` job): the queries are sharded over the ranks.
     -> list of (Query, QueryResult or None when catlas is None)."""
     queries, per_query = [], []
     for qf in query_files:
@@ -109,7 +110,15 @@ def query_batch(query_files, ksize, catlas, kmer_idx, scaled=None, catlas_name=N
         q._seqs = seqs
         per_query.append(seqs)
         queries.append(q)
-    counted = kmer_idx.table.count_matches_batch(per_query, ksize)
+    if distributed:
+        # one process per GPU, every rank holds the table: rank r counts its contiguous range of the queries and
+        # the sparse results are all-gathered (parallel.count_matches_batch_sharded)
+        from ..parallel import count_matches_batch_sharded
+
+        counted = count_matches_batch_sharded(kmer_idx.table.count_matches_batch, per_query, ksize,
+                                              device=get_context().device)
+    else:
+        counted = kmer_idx.table.count_matches_batch(per_query, ksize)
     out = []
     for q, (counts, n_distinct) in zip(queries, counted):
         q._ctx, q._kmers, q._d_hashes = get_context(), None, None

@@ -1012,6 +1012,25 @@ def test_partitioned_two_gpus_p2p_and_nccl_match_replicated():
         assert "labels identical to the replicated table on every rank: True" in out.stdout
 
 
+def test_sharded_queries_and_abundance_nccl(tmp_path):
+    """SURVEY 8e, replicated table: query_batch(distributed=True) shards whole queries over the ranks and all-gathers
+    the sparse results; abundance_sharded all-reduces the per-unitig count vectors.  One rank per visible GPU (up to
+    2; a 1-GPU box runs the same NCCL code path with world size 1)."""
+    import subprocess
+    import sys
+
+    import torch
+
+    from conftest import ROOT
+
+    n = min(torch.cuda.device_count(), 2)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
+           "127.0.0.1", "--master-port", "29549", os.path.join(ROOT, "scripts", "sharded_query_run.py"), str(tmp_path)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "sharded queries identical to the single-process batch on every rank: True" in out.stdout
+
+
 # ---------------------------------------------------------------- next rows f3 / f4: sourmash-style hashing
 def test_unitig_min_hashvals_match_reference_sqlite_column(ctx, dory):
     """All 736 ``min_hashval`` values the reference stored for the dory unitigs

@@ -187,3 +187,82 @@ def test_shard_range_covers_everything():
     assert [log2_ranks(w) for w in (1, 2, 4, 8)] == [0, 1, 2, 3]
     with pytest.raises(ValueError):
         log2_ranks(3)
+
+
+# ----------------------------------------------------------------------------------------------
+# replicated table, sharded queries / abundance: whole queries per rank, sparse results
+# all-gathered; per-unitig count vectors all-reduced
+# ----------------------------------------------------------------------------------------------
+def _oracle_table():
+    from oracle import oracle as O
+
+    k, useqs, reads = _workload()
+    otab, _, _ = O.build_mphf(k, lambda: iter(O.Record(str(i), s.decode()) for i, s in enumerate(useqs)))
+    return O, k, len(useqs), O.COracleTable(otab.mphf_to_hash, otab.mphf_to_value), reads
+
+
+def _queries(reads):
+    # 7 queries of several records each (one shorter than k, one empty query): uneven over 2 ranks
+    qs = [reads[0:40], reads[40:41], [], reads[41:200], [b"ACGT"], reads[200:420] + reads[0:10], reads[420:600]]
+    return [list(q) for q in qs]
+
+
+def _count_batch_oracle(O, ot):
+    def count_batch(queries, ksize):
+        seqs = [s for q in queries for s in q]
+        qseq = np.concatenate([[0], np.cumsum([len(q) for q in queries])]).astype(np.int64)
+        buf, off = O.pack_sequences(seqs) if seqs else (np.zeros(0, np.uint8), np.zeros(1, np.int64))
+        dicts, nd, _ = ot.query_counts(buf, off, qseq, ksize)
+        return [(d, int(n)) for d, n in zip(dicts, nd)]
+
+    return count_batch
+
+
+def _worker_queries(rank, world, port, q):
+    import sys
+
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from spacegraphcats_b200.parallel import abundance_sharded, count_matches_batch_sharded
+
+        O, k, n_ids, ot, reads = _oracle_table()
+        res = count_matches_batch_sharded(_count_batch_oracle(O, ot), _queries(reads), k)
+
+        def lookup_counts(buf, off, ksize, n):
+            h, _ = O.hash_batch(np.asarray(buf), np.asarray(off), ksize)
+            cnt, miss = ot.count_matches(h, n)
+            return cnt, len(h), len(h) - int(miss)
+
+        buf, off = O.pack_sequences(reads)
+        cnt, nk, nh = abundance_sharded(lookup_counts, buf, off, k, n_ids)
+        q.put((rank, res, cnt.tolist(), nk, nh))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_sharded_queries_and_abundance_world2_gloo_match_single_process():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_queries, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=150) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+
+    O, k, n_ids, ot, reads = _oracle_table()
+    want = _count_batch_oracle(O, ot)(_queries(reads), k)
+    assert any(len(d) > 3 for d, _ in want) and want[2] == ({}, 0) and want[4] == ({}, 0)
+    buf, off = O.pack_sequences(reads)
+    h, _ = O.hash_batch(buf, off, k)
+    w_cnt, w_miss = ot.count_matches(h, n_ids)
+    for rank, res, cnt, nk, nh in results:  # every rank holds the complete answer
+        assert res == want
+        assert cnt == w_cnt.tolist() and nk == len(h) and nh == len(h) - int(w_miss)
