@@ -100,6 +100,7 @@ struct sgc_ctx {
     DevBuf nk, nseg, seg_first, kmer_off, seg_map, cub_tmp, pairs_a, pairs_b, tmp_hash, tmp_id, tmp_idx, cursor;
     DevBuf units, unit_off, base_off, unpacked;  // packed-read plans
     DevBuf q_hash2, q_id, q_id2, q_mapk, q_mapc;  // batched queries
+    DevBuf iv_a, iv_b, iv_c, iv_d;                // batched queries through the sequence store: interval keys / values
     // optional CUDA-event timing of the tile kernel (bench.py roofline leg)
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
@@ -454,7 +455,7 @@ void sgc_ctx_destroy(sgc_ctx* c) {
     DevBuf* bufs[] = {&c->nk, &c->nseg, &c->seg_first, &c->kmer_off, &c->seg_map, &c->cub_tmp,
                       &c->pairs_a, &c->pairs_b, &c->tmp_hash, &c->tmp_id, &c->tmp_idx, &c->cursor,
                       &c->units, &c->unit_off, &c->base_off, &c->unpacked,
-                      &c->q_hash2, &c->q_id, &c->q_id2, &c->q_mapk, &c->q_mapc};
+                      &c->q_hash2, &c->q_id, &c->q_id2, &c->q_mapk, &c->q_mapc, &c->iv_a, &c->iv_b, &c->iv_c, &c->iv_d};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->d_scal) cudaFree(c->d_scal);
@@ -917,6 +918,150 @@ int sgc_count_matches(sgc_table* t, const uint64_t* d_hash, int64_t n, int disti
 // call: hash every record of every query (one launch), one stable radix sort of all hashes on their top 32
 // bits with the query index as the value, then one pass that drops each query's duplicate hashes, looks the
 // rest up (sorted hashes walk the table in bucket order) and counts them per (query, unitig).
+}  // extern "C"
+
+namespace {
+
+struct MaxU64 {
+    __host__ __device__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a > b ? a : b; }
+};
+struct SumU32 {
+    __host__ __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a + b; }
+};
+
+bool use_side(const sgc_table* t);
+void labelseq_args(LabelSeqArgs& a, sgc_table* t, const uint8_t* seq, const Plan& p, int k, int32_t* d_status,
+                   unsigned long long pairs_cap);
+
+int launch_labelseq_query(sgc_ctx* c, const LabelSeqArgs& a);  // defined next to launch_labelseq
+
+// The batched query through the unitig sequence store (sgc_labelseq.cuh, QUERY): no k-mer hash ever reaches HBM.
+// The label kernel's runs give, per query, intervals of store positions (one 16-byte record per settled run instead
+// of one hash per k-mer) and the hashes of the k-mers the table does not hold; the number of distinct matching
+// hashes of a query on a unitig is the size of the union of its intervals there.
+//   intervals: sort by (query, first position) -> running maximum of the ends -> uncovered length of every interval
+//              -> reduce by (query, unitig) -> sort the pairs -> merge
+//   misses:    sort by query, stable sort by the hashes' top 32 bits -> first occurrences per (hash, query)
+// *fallback = true (nothing written): some hit has no store position (a table also filled hash by hash).
+int query_count_batch_store(sgc_table* t, const uint8_t* d_seq, const int64_t* d_off, int64_t nseq, const Plan& p, int64_t n,
+                            const int32_t* d_seq_query, int n_queries, int k, uint64_t* d_keys_out, uint32_t* d_counts_out,
+                            int64_t cap, int64_t* d_q_distinct, int32_t* d_status, int64_t* h_n_pairs, int64_t* h_n_hits,
+                            bool* fallback) {
+    sgc_ctx* c = t->ctx;
+    *fallback = false;
+    const int qbits = std::max(1, bits_for(std::max(n_queries, 1)));
+    unsigned long long iv_cap = (unsigned long long)(n / 4 + 4096), ms_cap = (unsigned long long)(n / 4 + 4096);
+    int64_t n_iv = 0, n_ms = 0;
+    for (int attempt = 0;; attempt++) {
+        TRY(ensure(c, c->iv_a, (size_t)iv_cap * 8));
+        TRY(ensure(c, c->iv_b, (size_t)iv_cap * 8));
+        TRY(ensure(c, c->iv_c, (size_t)iv_cap * 8));
+        TRY(ensure(c, c->iv_d, (size_t)iv_cap * 8));
+        TRY(ensure(c, c->q_id, (size_t)iv_cap * 4));
+        TRY(ensure(c, c->q_id2, (size_t)iv_cap * 4));
+        TRY(ensure(c, c->tmp_hash, (size_t)ms_cap * 8));
+        TRY(ensure(c, c->q_hash2, (size_t)ms_cap * 8));
+        TRY(ensure(c, c->q_mapc, (size_t)ms_cap * 4));
+        TRY(ensure(c, c->tmp_id, (size_t)ms_cap * 4));
+        TRY(zero_scalars(c));
+        if (d_status) CU(cudaMemsetAsync(d_status, 0, (size_t)nseq * 4, c->stream));
+        LabelSeqArgs a;
+        labelseq_args(a, t, d_seq, p, k, d_status, 0);
+        a.pairs = nullptr;
+        a.seq_query = d_seq_query;
+        a.iv_key = (unsigned long long*)c->iv_a.p;
+        a.iv_val = (unsigned long long*)c->iv_b.p;
+        a.iv_cap = iv_cap;
+        a.miss_hash = (unsigned long long*)c->tmp_hash.p;
+        a.miss_q = (uint32_t*)c->q_mapc.p;
+        a.miss_cap = ms_cap;
+        TRY(launch_labelseq_query(c, a));
+        TRY(fetch_scalars(c));
+        if (c->h_scal->err & ERR_QUERY_NOPOS) {
+            *fallback = true;
+            return SGC_OK;
+        }
+        n_iv = (int64_t)c->h_scal->n_export;
+        n_ms = (int64_t)c->h_scal->n_live;
+        if (!(c->h_scal->err & ERR_QUERY_CAP)) break;
+        if (attempt == 1) return fail(SGC_ERR_CAPACITY, "query interval buffers overflowed twice");
+        iv_cap = (unsigned long long)n_iv + 1024;   // the counters ran on past the caps: they are the true sizes
+        ms_cap = (unsigned long long)n_ms + 1024;
+    }
+    CU(cudaMemsetAsync(&c->d_scal->n_hits, 0, 8, c->stream));
+    int64_t np = 0;
+    size_t tb = 0;
+    if (n_iv > 0) {
+        unsigned long long *A = (unsigned long long*)c->iv_a.p, *B = (unsigned long long*)c->iv_b.p,
+                           *C = (unsigned long long*)c->iv_c.p, *D = (unsigned long long*)c->iv_d.p;
+        uint32_t *cnt = (uint32_t*)c->q_id.p, *cnt2 = (uint32_t*)c->q_id2.p;
+        const int end_bit = std::min(64, 32 + qbits);
+        // (A, B) -> sorted (C, D)
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, A, C, B, D, n_iv, 0, end_bit, c->stream));
+        TRY(ensure(c, c->cub_tmp, tb));
+        CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, A, C, B, D, n_iv, 0, end_bit, c->stream));
+        iv_end_kernel<<<grid_for(n_iv, 256, c->num_sms * 8), 256, 0, c->stream>>>(C, D, n_iv, A);
+        CU(cub::DeviceScan::ExclusiveScan(nullptr, tb, A, B, MaxU64(), 0ULL, n_iv, c->stream));
+        TRY(ensure(c, c->cub_tmp, tb));
+        CU(cub::DeviceScan::ExclusiveScan(c->cub_tmp.p, tb, A, B, MaxU64(), 0ULL, n_iv, c->stream));
+        iv_union_kernel<<<grid_for(n_iv, 256, c->num_sms * 8), 256, 0, c->stream>>>(C, D, B, n_iv, A, cnt);
+        c->launches += 2;
+        // runs of equal (query, unitig): A / cnt -> C / cnt2
+        long long* d_runs = &c->d_scal->n_unique;
+        CU(cub::DeviceReduce::ReduceByKey(nullptr, tb, A, C, cnt, cnt2, d_runs, SumU32(), n_iv, c->stream));
+        TRY(ensure(c, c->cub_tmp, tb));
+        CU(cub::DeviceReduce::ReduceByKey(c->cub_tmp.p, tb, A, C, cnt, cnt2, d_runs, SumU32(), n_iv, c->stream));
+        TRY(fetch_scalars(c));
+        const int64_t nruns = c->h_scal->n_unique;
+        // a unitig may occupy several ranges of the store (the same id given to several sequences): sort + merge
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, C, A, cnt2, cnt, nruns, 0, end_bit, c->stream));
+        TRY(ensure(c, c->cub_tmp, tb));
+        CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, C, A, cnt2, cnt, nruns, 0, end_bit, c->stream));
+        CU(cub::DeviceReduce::ReduceByKey(nullptr, tb, A, C, cnt, cnt2, d_runs, SumU32(), nruns, c->stream));
+        TRY(ensure(c, c->cub_tmp, tb));
+        CU(cub::DeviceReduce::ReduceByKey(c->cub_tmp.p, tb, A, C, cnt, cnt2, d_runs, SumU32(), nruns, c->stream));
+        TRY(fetch_scalars(c));
+        np = c->h_scal->n_unique;
+        *h_n_pairs = np;
+        if (np > cap) return fail(SGC_ERR_CAPACITY, "cap %lld < %lld (query, unitig) pairs", (long long)cap, (long long)np);
+        CU(cudaMemcpyAsync(d_keys_out, C, (size_t)np * 8, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(d_counts_out, cnt2, (size_t)np * 4, cudaMemcpyDeviceToDevice, c->stream));
+        pairs_tally_kernel<<<grid_for(np, 256, c->num_sms * 8), 256, 0, c->stream>>>(
+            (const unsigned long long*)d_keys_out, d_counts_out, np, (unsigned long long*)d_q_distinct, c->d_scal);
+        c->launches++;
+    }
+    if (n_ms > 0) {
+        uint64_t *H = (uint64_t*)c->tmp_hash.p, *H2 = (uint64_t*)c->q_hash2.p;
+        uint32_t *Q = (uint32_t*)c->q_mapc.p, *Q2 = (uint32_t*)c->tmp_id.p;
+        if (n_queries > 1) {  // by query (H, Q) -> (H2, Q2), then stably by hash -> (H, Q)
+            CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, Q, Q2, H, H2, n_ms, 0, qbits, c->stream));
+            TRY(ensure(c, c->cub_tmp, tb));
+            CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, Q, Q2, H, H2, n_ms, 0, qbits, c->stream));
+            CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, H2, H, Q2, Q, n_ms, 32, 64, c->stream));
+            TRY(ensure(c, c->cub_tmp, tb));
+            CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, H2, H, Q2, Q, n_ms, 32, 64, c->stream));
+        } else {
+            CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, H, H2, Q, Q2, n_ms, 32, 64, c->stream));
+            TRY(ensure(c, c->cub_tmp, tb));
+            CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, H, H2, Q, Q2, n_ms, 32, 64, c->stream));
+            std::swap(H, H2);
+            std::swap(Q, Q2);
+        }
+        const size_t hist_bytes = n_queries <= QHIST_MAX ? (size_t)n_queries * 4 : 0;
+        miss_distinct_kernel<<<grid_for(n_ms, 256, c->num_sms * 8), 256, hist_bytes, c->stream>>>(
+            H, Q, n_ms, (unsigned long long*)d_q_distinct, n_queries);
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    TRY(fetch_scalars(c));
+    if (h_n_hits) *h_n_hits = (int64_t)c->h_scal->n_hits;
+    return SGC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int sgc_query_count_batch(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off, int64_t nseq,
                           const int32_t* d_seq_query, int n_queries, int k, uint64_t* d_keys_out, uint32_t* d_counts_out,
                           int64_t cap, int64_t* d_q_distinct, int32_t* d_status, int64_t* h_n_pairs, int64_t* h_n_kmers,
@@ -943,6 +1088,18 @@ int sgc_query_count_batch(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes,
     if (h_n_kmers) *h_n_kmers = n;
     if (n == 0) return SGC_OK;
     if (n >= ((int64_t)1 << 32)) return fail(SGC_ERR_ARG, "at most 2^32-1 k-mers per query batch");
+    if (use_side(t) && t->peer_n == 0 && !getenv("SGC_QUERY_SORT")) {
+        // the table carries the unitig sequence store: intervals of store positions instead of sorted hashes
+        Plan ps;
+        TRY(make_plan(c, d_off, nseq, seq_bytes, k, nullptr, &ps, SEG_KS));
+        bool fallback = false;
+        TRY(query_count_batch_store(t, d_seq, d_off, nseq, ps, n, d_seq_query, n_queries, k, d_keys_out, d_counts_out, cap,
+                                    d_q_distinct, d_status, h_n_pairs, h_n_hits, &fallback));
+        if (!fallback) return SGC_OK;
+        if (d_status) CU(cudaMemsetAsync(d_status, 0, (size_t)nseq * 4, c->stream));
+        CU(cudaMemsetAsync(d_q_distinct, 0, (size_t)n_queries * 8, c->stream));
+        TRY(make_plan(c, d_off, nseq, seq_bytes, k, nullptr, &p));
+    }
     TRY(ensure(c, c->tmp_hash, (size_t)n * 8));
     TRY(ensure(c, c->q_hash2, (size_t)n * 8));
     TRY(ensure(c, c->q_id, (size_t)n * 4));
@@ -1047,14 +1204,14 @@ int sgc_lookup_sequences(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes, 
 
 namespace {
 
-template <int K, bool PACKED, bool PEER>
+template <int K, bool PACKED, bool PEER, bool QUERY = false>
 int launch_labelseq_k(sgc_ctx* c, const LabelSeqArgs& a) {
     const size_t smem = sizeof(WarpTileS<K, PACKED>) * WPBS;
     static thread_local int blocks_per_sm_of[64] = {0};
     int& blocks_per_sm = blocks_per_sm_of[c->device & 63];
     if (!blocks_per_sm) {
-        CU(cudaFuncSetAttribute(labelseq_kernel<K, PACKED, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, labelseq_kernel<K, PACKED, PEER>, NTS, smem));
+        CU(cudaFuncSetAttribute(labelseq_kernel<K, PACKED, PEER, QUERY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, labelseq_kernel<K, PACKED, PEER, QUERY>, NTS, smem));
         if (blocks_per_sm < 1) return fail(SGC_ERR_CUDA, "label kernel does not fit on an SM (smem %zu)", smem);
     }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1068,7 +1225,7 @@ int launch_labelseq_k(sgc_ctx* c, const LabelSeqArgs& a) {
         int v = atoi(lim);
         if (v >= 1 && v < ctas) ctas = v;
     }
-    labelseq_kernel<K, PACKED, PEER><<<c->num_sms * ctas, NTS, smem, c->stream>>>(a);
+    labelseq_kernel<K, PACKED, PEER, QUERY><<<c->num_sms * ctas, NTS, smem, c->stream>>>(a);
     c->launches++;
     CU(cudaGetLastError());
     if (c->timing) {
@@ -1076,6 +1233,14 @@ int launch_labelseq_k(sgc_ctx* c, const LabelSeqArgs& a) {
         c->timed.emplace_back(e0, e1);
     }
     return SGC_OK;
+}
+
+int launch_labelseq_query(sgc_ctx* c, const LabelSeqArgs& a) {
+    switch (a.k) {
+        case 21: return launch_labelseq_k<21, false, false, true>(c, a);
+        case 31: return launch_labelseq_k<31, false, false, true>(c, a);
+        default: return launch_labelseq_k<0, false, false, true>(c, a);
+    }
 }
 
 template <bool PACKED>

@@ -444,6 +444,73 @@ __global__ void __launch_bounds__(256) query_count_kernel(const Bucket* tbl, uin
     }
 }
 
+// ---- the store-position form of the batched query (labelseq_kernel<.., QUERY>) ----
+// intervals sorted by key = query << 32 | first position; val = length << 32 | unitig id.
+// e[i] = query << 32 | end (exclusive) -- a running maximum of e over the sorted intervals is, in its high word, the
+// query of the latest interval and, in its low word, how far that query's earlier intervals reach.
+__global__ void iv_end_kernel(const unsigned long long* __restrict__ key, const unsigned long long* __restrict__ val, int64_t n,
+                              unsigned long long* __restrict__ e) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        e[i] = key[i] + (val[i] >> 32);  // positions are 30 bits: the sum stays inside the low word
+}
+// the part of interval i that no earlier interval of its query covers -> (query << 32 | unitig, length)
+__global__ void iv_union_kernel(const unsigned long long* __restrict__ key, const unsigned long long* __restrict__ val,
+                                const unsigned long long* __restrict__ pmax, int64_t n, unsigned long long* __restrict__ key2,
+                                uint32_t* __restrict__ cnt) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long k = key[i], v = val[i], pm = pmax[i];
+        const uint32_t start = (uint32_t)k, end = start + (uint32_t)(v >> 32);
+        uint32_t from = start;
+        if ((pm >> 32) == (k >> 32) && (uint32_t)pm > from) from = (uint32_t)pm;
+        key2[i] = (k & 0xFFFFFFFF00000000ULL) | (v & 0xFFFFFFFFULL);
+        cnt[i] = end > from ? end - from : 0u;
+    }
+}
+// final (query << 32 | unitig, count) pairs -> per-query distinct matching k-mers and the total
+__global__ void pairs_tally_kernel(const unsigned long long* __restrict__ key, const uint32_t* __restrict__ cnt, int64_t n,
+                                   unsigned long long* q_distinct, Scalars* scal) {
+    unsigned long long hits = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        atomicAdd(&q_distinct[key[i] >> 32], (unsigned long long)cnt[i]);
+        hits += cnt[i];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, d);
+    if ((threadIdx.x & 31) == 0 && hits) atomicAdd(&scal->n_hits, hits);
+}
+// hs / qs: the missing k-mers' hashes and queries, sorted by query and then STABLY by the hashes' top 32 bits: inside
+// a run of equal top bits the elements of one query are neighbours ... of equal full hashes, ordered by query
+__global__ void __launch_bounds__(256) miss_distinct_kernel(const uint64_t* __restrict__ hs, const uint32_t* __restrict__ qs,
+                                                            int64_t n, unsigned long long* q_distinct, int n_queries) {
+    extern __shared__ unsigned int s_hist[];
+    const bool use_smem = n_queries <= QHIST_MAX;
+    if (use_smem) {
+        for (int j = threadIdx.x; j < n_queries; j += blockDim.x) s_hist[j] = 0u;
+        __syncthreads();
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t h = hs[i];
+        const uint32_t q = qs[i];
+        bool dup = false;
+        // elements with the same full hash AND an earlier-or-equal query come before i in its run; the nearest one
+        // with the same hash has the largest such query
+        for (int64_t j = i - 1; j >= 0 && (hs[j] >> 32) == (h >> 32); j--) {
+            if (hs[j] == h) {
+                dup = qs[j] == q;
+                break;
+            }
+        }
+        if (dup) continue;
+        if (use_smem) atomicAdd(&s_hist[q], 1u);
+        else atomicAdd(&q_distinct[q], 1ULL);
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < n_queries; j += blockDim.x)
+            if (s_hist[j]) atomicAdd(&q_distinct[j], (unsigned long long)s_hist[j]);
+    }
+}
+
 __global__ void qmap_compact_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ cnt, uint64_t slots,
                                     unsigned long long* out_keys, uint32_t* out_cnt, unsigned long long cap, Scalars* scal) {
     const int lane = threadIdx.x & 31;

@@ -95,7 +95,22 @@ struct LabelSeqArgs {
     uint32_t id_bounds[33];
     long long ustride, bstride;
     int owner_bits, n_shards;
+    // QUERY = true (sgc_query_count_batch): instead of per-read labels the kernel writes, per settled run, the
+    // INTERVAL of store positions its k-mers lie at -- iv_key = query << 32 | first position, iv_val = length << 32 |
+    // unitig id; scal->n_export counts them -- and every k-mer that is not in the table as (hash, query) --
+    // scal->n_live counts those.  Two store positions never hold the same hash under a clear break bit and the
+    // position a probe returns is the one the table keeps for that hash, so the number of DISTINCT matching hashes
+    // of a query on a unitig is the size of the union of its intervals there (search/query_by_sequence.py:170-189).
+    const int32_t* seq_query;
+    unsigned long long* iv_key;
+    unsigned long long* iv_val;
+    unsigned long long iv_cap;
+    unsigned long long* miss_hash;
+    uint32_t* miss_q;
+    unsigned long long miss_cap;
 };
+constexpr int ERR_QUERY_CAP = 4;      // Scalars::err bit: iv_cap / miss_cap too small
+constexpr int ERR_QUERY_NOPOS = 8;    // Scalars::err bit: a hit without a store position (table filled hash by hash)
 
 template <int K, bool PACKED>
 struct alignas(16) WarpTileS {
@@ -190,7 +205,7 @@ __global__ void useq_brk_kernel(const int64_t* __restrict__ off, int64_t nseq, i
 // ----------------------------------------------------------------------------------
 // the kernel
 // ----------------------------------------------------------------------------------
-template <int K, bool PACKED, bool PEER>
+template <int K, bool PACKED, bool PEER, bool QUERY = false>
 __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const LabelSeqArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using G = GeoS<K, PACKED>;
@@ -432,6 +447,11 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                 }
             }
             unsigned nhit = v != SGC_MISS;
+            // QUERY: the settled k-mers of this item, as bits of the window lo .. lo+n-1 whose anchor (bit ao) lies at
+            // store position aux & AUX_MASK; k-mer lo+i lies at that position + (i - ao) (along) or - (i - ao)
+            unsigned q_settled = v != SGC_MISS ? 1u : 0u;
+            int q_ao = 0;
+            bool q_along = true;
 
             const bool is_run = act && n > 1;
             if (__any_sync(0xffffffffu, is_run)) {  // warp-uniform: this trip holds runs
@@ -539,6 +559,9 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                                                   : ((2u << lim) - 1u) & valid;
                         const unsigned settled = ((clean & inh) | (1u << ao)) & valid;
                         nhit = (unsigned)__popc(settled);
+                        q_settled = settled;
+                        q_ao = ao;
+                        q_along = along;
                         singles = inh & ~settled;
 #if SGC_LS_REANCHOR
                         if (valid & ~inh) {  // the k-mers past the break: a run of their own, anchored next to the break
@@ -586,10 +609,68 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                 }
             }
             my_hits += nhit;
-            // a hit is a candidate label unless the previous item gives the same (sequence, id)
-            const unsigned long long key = ((unsigned long long)d.seq << 32) | v;
-            const unsigned long long prevk = __shfl_up_sync(0xffffffffu, key, 1);
-            push_key(v != SGC_MISS && !(lane > 0 && prevk == key), key);
+            if constexpr (QUERY) {
+                const uint32_t qid = act ? (uint32_t)__ldg(a.seq_query + d.seq) : 0u;
+                // k-mers the table does not hold: (hash, query), de-duplicated later
+                const bool miss = act && v == SGC_MISS;
+                const unsigned mm = __ballot_sync(0xffffffffu, miss);
+                if (mm) {
+                    unsigned long long base = 0;
+                    const int leader = __ffs((int)mm) - 1;
+                    if (lane == leader) base = atomicAdd(&a.scal->n_live, (unsigned long long)__popc(mm));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (miss) {
+                        const unsigned long long pos = base + (unsigned)__popc(mm & ((1u << lane) - 1u));
+                        if (pos < a.miss_cap) {
+                            a.miss_hash[pos] = h;
+                            a.miss_q[pos] = qid;
+                        } else {
+                            atomicOr(&a.scal->err, ERR_QUERY_CAP);
+                        }
+                    }
+                }
+                // settled k-mers: one interval of store positions per run of set bits
+                const uint32_t gp = aux & AUX_MASK;
+                if (q_settled && gp == AUX_NONE) {
+                    atomicOr(&a.scal->err, ERR_QUERY_NOPOS);
+                    q_settled = 0u;
+                }
+                const int cnt = __popc(q_settled & ~(q_settled << 1));  // runs of set bits
+                int incl = cnt;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const int x = __shfl_up_sync(0xffffffffu, incl, dd);
+                    if (lane >= dd) incl += x;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                if (total) {
+                    unsigned long long base = 0;
+                    if (lane == 31) base = atomicAdd(&a.scal->n_export, (unsigned long long)total);
+                    base = __shfl_sync(0xffffffffu, base, 31);
+                    unsigned long long pos = base + (unsigned)(incl - cnt);
+                    unsigned m = q_settled;
+                    while (m) {
+                        const int i0 = __ffs((int)m) - 1;
+                        const unsigned above = ~(m >> i0);                 // first clear bit at or above i0
+                        const int len = __ffs((int)above) - 1;
+                        m &= ~(((1u << len) - 1u) << i0);
+                        const int i1 = i0 + len - 1;
+                        const int first = q_along ? (int)gp + (i0 - q_ao) : (int)gp - (i1 - q_ao);
+                        if (pos < a.iv_cap) {
+                            a.iv_key[pos] = ((unsigned long long)qid << 32) | (unsigned)first;
+                            a.iv_val[pos] = ((unsigned long long)len << 32) | v;
+                        } else {
+                            atomicOr(&a.scal->err, ERR_QUERY_CAP);
+                        }
+                        pos++;
+                    }
+                }
+            } else {
+                // a hit is a candidate label unless the previous item gives the same (sequence, id)
+                const unsigned long long key = ((unsigned long long)d.seq << 32) | v;
+                const unsigned long long prevk = __shfl_up_sync(0xffffffffu, key, 1);
+                push_key(v != SGC_MISS && !(lane > 0 && prevk == key), key);
+            }
             __syncwarp();
         }
 
