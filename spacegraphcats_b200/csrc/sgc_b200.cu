@@ -950,7 +950,9 @@ int query_count_batch_store(sgc_table* t, const uint8_t* d_seq, const int64_t* d
     sgc_ctx* c = t->ctx;
     *fallback = false;
     const int qbits = std::max(1, bits_for(std::max(n_queries, 1)));
-    unsigned long long iv_cap = (unsigned long long)(n / 4 + 4096), ms_cap = (unsigned long long)(n / 4 + 4096);
+    // every warp of the grid may leave one chunk partly used (it is filled with copies, sgc_labelseq.cuh)
+    const unsigned long long slack = (unsigned long long)c->num_sms * SGC_LS_MIN_CTAS * WPBS * QCHUNK + 4096;
+    unsigned long long iv_cap = (unsigned long long)(n / 4) + slack, ms_cap = (unsigned long long)(n / 4) + slack;
     int64_t n_iv = 0, n_ms = 0;
     for (int attempt = 0;; attempt++) {
         TRY(ensure(c, c->iv_a, (size_t)iv_cap * 8));
@@ -985,8 +987,8 @@ int query_count_batch_store(sgc_table* t, const uint8_t* d_seq, const int64_t* d
         n_ms = (int64_t)c->h_scal->n_live;
         if (!(c->h_scal->err & ERR_QUERY_CAP)) break;
         if (attempt == 1) return fail(SGC_ERR_CAPACITY, "query interval buffers overflowed twice");
-        iv_cap = (unsigned long long)n_iv + 1024;   // the counters ran on past the caps: they are the true sizes
-        ms_cap = (unsigned long long)n_ms + 1024;
+        // at most one record per k-mer, a tenth of every chunk abandoned at worst (a trip writes < 96 records)
+        iv_cap = ms_cap = (unsigned long long)n + (unsigned long long)n / 8 + slack;
     }
     CU(cudaMemsetAsync(&c->d_scal->n_hits, 0, 8, c->stream));
     int64_t np = 0;
@@ -1026,8 +1028,8 @@ int query_count_batch_store(sgc_table* t, const uint8_t* d_seq, const int64_t* d
         if (np > cap) return fail(SGC_ERR_CAPACITY, "cap %lld < %lld (query, unitig) pairs", (long long)cap, (long long)np);
         CU(cudaMemcpyAsync(d_keys_out, C, (size_t)np * 8, cudaMemcpyDeviceToDevice, c->stream));
         CU(cudaMemcpyAsync(d_counts_out, cnt2, (size_t)np * 4, cudaMemcpyDeviceToDevice, c->stream));
-        pairs_tally_kernel<<<grid_for(np, 256, c->num_sms * 8), 256, 0, c->stream>>>(
-            (const unsigned long long*)d_keys_out, d_counts_out, np, (unsigned long long*)d_q_distinct, c->d_scal);
+        pairs_tally_kernel<<<grid_for(np, 256, c->num_sms * 4), 256, n_queries <= QHIST_MAX ? (size_t)n_queries * 4 : 0, c->stream>>>(
+            (const unsigned long long*)d_keys_out, d_counts_out, np, (unsigned long long*)d_q_distinct, n_queries, c->d_scal);
         c->launches++;
     }
     if (n_ms > 0) {
@@ -1078,22 +1080,21 @@ int sgc_query_count_batch(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes,
     if (h_n_kmers) *h_n_kmers = 0;
     if (h_n_hits) *h_n_hits = 0;
     if (nseq == 0) return SGC_OK;
+    const bool store = use_side(t) && t->peer_n == 0 && !getenv("SGC_QUERY_SORT");
     Plan p;
-    TRY(make_plan(c, d_off, nseq, seq_bytes, k, nullptr, &p));
-    TRY(fetch_scalars(c));
-    TRY(bad_offsets_check(c));
-    CU(cudaMemcpyAsync(&c->h_scal->n_unique, p.kmer_off + nseq, 8, cudaMemcpyDeviceToHost, c->stream));
+    TRY(make_plan(c, d_off, nseq, seq_bytes, k, nullptr, &p, store ? SEG_KS : SEG_K));
+    CU(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(Scalars), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&c->h_scal->n_unique, p.kmer_off + nseq, 8, cudaMemcpyDeviceToHost, c->stream));  // (after the scalars)
     CU(cudaStreamSynchronize(c->stream));
+    TRY(bad_offsets_check(c));
     const int64_t n = c->h_scal->n_unique;
     if (h_n_kmers) *h_n_kmers = n;
     if (n == 0) return SGC_OK;
     if (n >= ((int64_t)1 << 32)) return fail(SGC_ERR_ARG, "at most 2^32-1 k-mers per query batch");
-    if (use_side(t) && t->peer_n == 0 && !getenv("SGC_QUERY_SORT")) {
+    if (store) {
         // the table carries the unitig sequence store: intervals of store positions instead of sorted hashes
-        Plan ps;
-        TRY(make_plan(c, d_off, nseq, seq_bytes, k, nullptr, &ps, SEG_KS));
         bool fallback = false;
-        TRY(query_count_batch_store(t, d_seq, d_off, nseq, ps, n, d_seq_query, n_queries, k, d_keys_out, d_counts_out, cap,
+        TRY(query_count_batch_store(t, d_seq, d_off, nseq, p, n, d_seq_query, n_queries, k, d_keys_out, d_counts_out, cap,
                                     d_q_distinct, d_status, h_n_pairs, h_n_hits, &fallback));
         if (!fallback) return SGC_OK;
         if (d_status) CU(cudaMemsetAsync(d_status, 0, (size_t)nseq * 4, c->stream));

@@ -32,20 +32,40 @@ __global__ void plan_count_kernel(const int64_t* __restrict__ off, int64_t nseq,
 __global__ void plan_expand_kernel(const int64_t* __restrict__ seg_first, const int64_t* __restrict__ off,
                                    const int64_t* __restrict__ kmer_off, int64_t nseq, int k, int seg_k,
                                    SegDesc* __restrict__ segdesc) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nseq) return;
-    const int64_t a = seg_first[s], b = seg_first[s + 1];
-    if (a == b) return;
-    const int64_t o0 = off[s], nkseq = off[s + 1] - o0 - k + 1, ko = kmer_off[s];
-    for (int64_t j = a; j < b; j++) {
-        const int64_t q0 = (j - a) * seg_k;
+    // one thread per sequence; a sequence of more than 32 segments (contigs, genome-sized queries) is expanded by
+    // its whole warp
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int64_t a = 0, b = 0, o0 = 0, nkseq = 0, ko = 0;
+    if (s < nseq) {
+        a = seg_first[s];
+        b = seg_first[s + 1];
+        o0 = off[s];
+        nkseq = off[s + 1] - o0 - k + 1;
+        ko = kmer_off[s];
+    }
+    auto emit = [&](int64_t j, int64_t a_, int64_t o0_, int64_t nk_, int64_t ko_, unsigned seq_) {
+        const int64_t q0 = (j - a_) * seg_k;
         SegDesc d;
-        d.start = o0 + q0;
-        d.kout = ko + q0;
-        d.seq = (unsigned int)s;
-        d.nk = (int)(nkseq - q0 < seg_k ? nkseq - q0 : seg_k);
+        d.start = o0_ + q0;
+        d.kout = ko_ + q0;
+        d.seq = seq_;
+        d.nk = (int)(nk_ - q0 < seg_k ? nk_ - q0 : seg_k);
         d.pad[0] = d.pad[1] = 0;
         segdesc[j] = d;
+    };
+    const bool big = b - a > 32;
+    if (!big)
+        for (int64_t j = a; j < b; j++) emit(j, a, o0, nkseq, ko, (unsigned)s);
+    unsigned m = __ballot_sync(0xffffffffu, big);
+    while (m) {
+        const int src = __ffs((int)m) - 1;
+        m &= m - 1u;
+        const int64_t a_ = __shfl_sync(0xffffffffu, a, src), b_ = __shfl_sync(0xffffffffu, b, src);
+        const int64_t o0_ = __shfl_sync(0xffffffffu, o0, src), nk_ = __shfl_sync(0xffffffffu, nkseq, src);
+        const int64_t ko_ = __shfl_sync(0xffffffffu, ko, src);
+        const unsigned seq_ = (unsigned)(s - lane + src);
+        for (int64_t j = a_ + lane; j < b_; j += 32) emit(j, a_, o0_, nk_, ko_, seq_);
     }
 }
 
@@ -468,15 +488,27 @@ __global__ void iv_union_kernel(const unsigned long long* __restrict__ key, cons
 }
 // final (query << 32 | unitig, count) pairs -> per-query distinct matching k-mers and the total
 __global__ void pairs_tally_kernel(const unsigned long long* __restrict__ key, const uint32_t* __restrict__ cnt, int64_t n,
-                                   unsigned long long* q_distinct, Scalars* scal) {
+                                   unsigned long long* q_distinct, int n_queries, Scalars* scal) {
+    extern __shared__ unsigned int s_hist[];   // per-CTA counters when the queries fit (see query_count_kernel)
+    const bool use_smem = n_queries <= QHIST_MAX;
+    if (use_smem) {
+        for (int j = threadIdx.x; j < n_queries; j += blockDim.x) s_hist[j] = 0u;
+        __syncthreads();
+    }
     unsigned long long hits = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        atomicAdd(&q_distinct[key[i] >> 32], (unsigned long long)cnt[i]);
+        if (use_smem) atomicAdd(&s_hist[key[i] >> 32], cnt[i]);
+        else atomicAdd(&q_distinct[key[i] >> 32], (unsigned long long)cnt[i]);
         hits += cnt[i];
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, d);
     if ((threadIdx.x & 31) == 0 && hits) atomicAdd(&scal->n_hits, hits);
+    if (use_smem) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < n_queries; j += blockDim.x)
+            if (s_hist[j]) atomicAdd(&q_distinct[j], (unsigned long long)s_hist[j]);
+    }
 }
 // hs / qs: the missing k-mers' hashes and queries, sorted by query and then STABLY by the hashes' top 32 bits: inside
 // a run of equal top bits the elements of one query are neighbours ... of equal full hashes, ordered by query

@@ -109,6 +109,7 @@ struct LabelSeqArgs {
     uint32_t* miss_q;
     unsigned long long miss_cap;
 };
+constexpr unsigned QCHUNK = 1024;     // records a warp reserves at a time (a trip writes at most 96)
 constexpr int ERR_QUERY_CAP = 4;      // Scalars::err bit: iv_cap / miss_cap too small
 constexpr int ERR_QUERY_NOPOS = 8;    // Scalars::err bit: a hit without a store position (table filled hash by hash)
 
@@ -218,6 +219,12 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
     const int64_t nrounds = (nsegs + SPW - 1) / SPW;
     unsigned my_hits = 0;                // per lane: a launch is far below 2^32 k-mers per lane
     unsigned pair_fill = 0;              // warp-uniform: keys waiting in wt.pairs
+    // QUERY: the warp's current chunks of the interval / miss arrays (warp-uniform) and, per lane, the last record
+    // it wrote (what the unused rest of the last chunks is filled with)
+    unsigned long long iv_pos = 0, iv_end = 0, ms_pos = 0, ms_end = 0;
+    unsigned long long last_k = 0, last_v = 0, last_h = 0;
+    uint32_t last_q = 0;
+    unsigned have_last = 0;
 
     auto flush_pairs = [&]() {  // cold: out of line
         flush_pairs_out(a.scal, a.pairs, a.pairs_cap, wt.pairs, pair_fill, lane);
@@ -611,23 +618,41 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
             my_hits += nhit;
             if constexpr (QUERY) {
                 const uint32_t qid = act ? (uint32_t)__ldg(a.seq_query + d.seq) : 0u;
-                // k-mers the table does not hold: (hash, query), de-duplicated later
+                // Records go into chunks of QCHUNK slots the warp reserves from one global counter (one atomic per
+                // chunk, not per trip); what is left of a chunk is filled with copies of a valid record -- a repeated
+                // interval does not change a union, a repeated (hash, query) is a duplicate like any other.
+                // k-mers the table does not hold: (hash, query)
                 const bool miss = act && v == SGC_MISS;
                 const unsigned mm = __ballot_sync(0xffffffffu, miss);
                 if (mm) {
-                    unsigned long long base = 0;
-                    const int leader = __ffs((int)mm) - 1;
-                    if (lane == leader) base = atomicAdd(&a.scal->n_live, (unsigned long long)__popc(mm));
-                    base = __shfl_sync(0xffffffffu, base, leader);
+                    const unsigned total = (unsigned)__popc(mm);
+                    if (ms_pos + total > ms_end) {
+                        const int src = __ffs((int)mm) - 1;
+                        const unsigned long long fh = __shfl_sync(0xffffffffu, (unsigned long long)h, src);
+                        const uint32_t fq = __shfl_sync(0xffffffffu, qid, src);
+                        for (unsigned long long pp = ms_pos + lane; pp < ms_end; pp += 32)
+                            if (pp < a.miss_cap) {
+                                a.miss_hash[pp] = fh;
+                                a.miss_q[pp] = fq;
+                            }
+                        unsigned long long base = 0;
+                        if (lane == 0) base = atomicAdd(&a.scal->n_live, (unsigned long long)QCHUNK);
+                        ms_pos = __shfl_sync(0xffffffffu, base, 0);
+                        ms_end = ms_pos + QCHUNK;
+                    }
                     if (miss) {
-                        const unsigned long long pos = base + (unsigned)__popc(mm & ((1u << lane) - 1u));
+                        const unsigned long long pos = ms_pos + (unsigned)__popc(mm & ((1u << lane) - 1u));
                         if (pos < a.miss_cap) {
                             a.miss_hash[pos] = h;
                             a.miss_q[pos] = qid;
                         } else {
                             atomicOr(&a.scal->err, ERR_QUERY_CAP);
                         }
+                        last_h = h;
+                        last_q = qid;
+                        have_last |= 1u;
                     }
+                    ms_pos += total;
                 }
                 // settled k-mers: one interval of store positions per run of set bits
                 const uint32_t gp = aux & AUX_MASK;
@@ -644,26 +669,48 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                 }
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
                 if (total) {
-                    unsigned long long base = 0;
-                    if (lane == 31) base = atomicAdd(&a.scal->n_export, (unsigned long long)total);
-                    base = __shfl_sync(0xffffffffu, base, 31);
-                    unsigned long long pos = base + (unsigned)(incl - cnt);
-                    unsigned m = q_settled;
-                    while (m) {
+                    auto record = [&](unsigned m, unsigned long long& rk, unsigned long long& rv) -> unsigned {
                         const int i0 = __ffs((int)m) - 1;
-                        const unsigned above = ~(m >> i0);                 // first clear bit at or above i0
-                        const int len = __ffs((int)above) - 1;
-                        m &= ~(((1u << len) - 1u) << i0);
+                        const int len = __ffs((int)~(m >> i0)) - 1;   // set bits from i0 upwards
                         const int i1 = i0 + len - 1;
                         const int first = q_along ? (int)gp + (i0 - q_ao) : (int)gp - (i1 - q_ao);
+                        rk = ((unsigned long long)qid << 32) | (unsigned)first;
+                        rv = ((unsigned long long)len << 32) | v;
+                        return m & ~(((1u << len) - 1u) << i0);
+                    };
+                    if (iv_pos + (unsigned)total > iv_end) {
+                        unsigned long long fk = 0, fv = 0;
+                        if (cnt) record(q_settled, fk, fv);
+                        const int src = __ffs((int)__ballot_sync(0xffffffffu, cnt > 0)) - 1;
+                        fk = __shfl_sync(0xffffffffu, fk, src);
+                        fv = __shfl_sync(0xffffffffu, fv, src);
+                        for (unsigned long long pp = iv_pos + lane; pp < iv_end; pp += 32)
+                            if (pp < a.iv_cap) {
+                                a.iv_key[pp] = fk;
+                                a.iv_val[pp] = fv;
+                            }
+                        unsigned long long base = 0;
+                        if (lane == 0) base = atomicAdd(&a.scal->n_export, (unsigned long long)QCHUNK);
+                        iv_pos = __shfl_sync(0xffffffffu, base, 0);
+                        iv_end = iv_pos + QCHUNK;
+                    }
+                    unsigned long long pos = iv_pos + (unsigned)(incl - cnt);
+                    unsigned m = q_settled;
+                    while (m) {
+                        unsigned long long rk, rv;
+                        m = record(m, rk, rv);
                         if (pos < a.iv_cap) {
-                            a.iv_key[pos] = ((unsigned long long)qid << 32) | (unsigned)first;
-                            a.iv_val[pos] = ((unsigned long long)len << 32) | v;
+                            a.iv_key[pos] = rk;
+                            a.iv_val[pos] = rv;
                         } else {
                             atomicOr(&a.scal->err, ERR_QUERY_CAP);
                         }
+                        last_k = rk;
+                        last_v = rv;
+                        have_last |= 2u;
                         pos++;
                     }
+                    iv_pos += (unsigned)total;
                 }
             } else {
                 // a hit is a candidate label unless the previous item gives the same (sequence, id)
@@ -680,6 +727,27 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
     cp_async_wait_all();
 
     if (pair_fill) flush_pairs();
+    if constexpr (QUERY) {
+        if (iv_pos < iv_end) {
+            const int src = __ffs((int)__ballot_sync(0xffffffffu, (have_last & 2u) != 0)) - 1;
+            const unsigned long long fk = __shfl_sync(0xffffffffu, last_k, src), fv = __shfl_sync(0xffffffffu, last_v, src);
+            for (unsigned long long pp = iv_pos + lane; pp < iv_end; pp += 32)
+                if (pp < a.iv_cap) {
+                    a.iv_key[pp] = fk;
+                    a.iv_val[pp] = fv;
+                }
+        }
+        if (ms_pos < ms_end) {
+            const int src = __ffs((int)__ballot_sync(0xffffffffu, (have_last & 1u) != 0)) - 1;
+            const unsigned long long fh = __shfl_sync(0xffffffffu, last_h, src);
+            const uint32_t fq = __shfl_sync(0xffffffffu, last_q, src);
+            for (unsigned long long pp = ms_pos + lane; pp < ms_end; pp += 32)
+                if (pp < a.miss_cap) {
+                    a.miss_hash[pp] = fh;
+                    a.miss_q[pp] = fq;
+                }
+        }
+    }
     unsigned long long hits = my_hits;  // the host derives the misses from the plan's k-mer total
 #pragma unroll
     for (int dd = 16; dd > 0; dd >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, dd);
