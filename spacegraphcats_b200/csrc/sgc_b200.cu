@@ -218,8 +218,12 @@ int make_plan(sgc_ctx* c, const int64_t* d_off, int64_t nseq, int64_t seq_bytes,
     CU(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tb, (int64_t*)c->nseg.p, (int64_t*)c->seg_first.p, (int64_t)n1,
                                      c->stream));
     if (nseq > 0) {
-        plan_expand_kernel<<<grid_for(nseq, 256, 1 << 30), 256, 0, c->stream>>>(
-            (int64_t*)c->seg_first.p, d_off, d_kmer_off, nseq, k, seg_k, (SegDesc*)c->seg_map.p);
+        if (max_segs > 8 * nseq)  // long sequences (queries, contigs): one thread per segment
+            plan_expand_segs_kernel<<<grid_for(max_segs, 256, c->num_sms * 16), 256, 0, c->stream>>>(
+                (int64_t*)c->seg_first.p, d_off, d_kmer_off, nseq, k, seg_k, (SegDesc*)c->seg_map.p);
+        else
+            plan_expand_kernel<<<grid_for(nseq, 256, 1 << 30), 256, 0, c->stream>>>(
+                (int64_t*)c->seg_first.p, d_off, d_kmer_off, nseq, k, seg_k, (SegDesc*)c->seg_map.p);
         c->launches++;
     }
     CU(cudaGetLastError());
@@ -941,7 +945,7 @@ int launch_labelseq_query(sgc_ctx* c, const LabelSeqArgs& a);  // defined next t
 // hashes of a query on a unitig is the size of the union of its intervals there.
 //   intervals: sort by (query, first position) -> running maximum of the ends -> uncovered length of every interval
 //              -> reduce by (query, unitig) -> sort the pairs -> merge
-//   misses:    sort by query, stable sort by the hashes' top 32 bits -> first occurrences per (hash, query)
+//   misses:    sort by a 32-bit key (query, top bits of the hash) -> first occurrences per (hash, query) inside the runs
 // *fallback = true (nothing written): some hit has no store position (a table also filled hash by hash).
 int query_count_batch_store(sgc_table* t, const uint8_t* d_seq, const int64_t* d_off, int64_t nseq, const Plan& p, int64_t n,
                             const int32_t* d_seq_query, int n_queries, int k, uint64_t* d_keys_out, uint32_t* d_counts_out,
@@ -950,6 +954,7 @@ int query_count_batch_store(sgc_table* t, const uint8_t* d_seq, const int64_t* d
     sgc_ctx* c = t->ctx;
     *fallback = false;
     const int qbits = std::max(1, bits_for(std::max(n_queries, 1)));
+    if (qbits > 31) return fail(SGC_ERR_ARG, "at most 2^31 queries per batch");
     // every warp of the grid may leave one chunk partly used (it is filled with copies, sgc_labelseq.cuh)
     const unsigned long long slack = (unsigned long long)c->num_sms * SGC_LS_MIN_CTAS * WPBS * QCHUNK + 4096;
     unsigned long long iv_cap = (unsigned long long)(n / 4) + slack, ms_cap = (unsigned long long)(n / 4) + slack;
@@ -977,6 +982,7 @@ int query_count_batch_store(sgc_table* t, const uint8_t* d_seq, const int64_t* d
         a.miss_hash = (unsigned long long*)c->tmp_hash.p;
         a.miss_q = (uint32_t*)c->q_mapc.p;
         a.miss_cap = ms_cap;
+        a.miss_hbits = 32 - qbits;
         TRY(launch_labelseq_query(c, a));
         TRY(fetch_scalars(c));
         if (c->h_scal->err & ERR_QUERY_NOPOS) {
@@ -1035,23 +1041,12 @@ int query_count_batch_store(sgc_table* t, const uint8_t* d_seq, const int64_t* d
     if (n_ms > 0) {
         uint64_t *H = (uint64_t*)c->tmp_hash.p, *H2 = (uint64_t*)c->q_hash2.p;
         uint32_t *Q = (uint32_t*)c->q_mapc.p, *Q2 = (uint32_t*)c->tmp_id.p;
-        if (n_queries > 1) {  // by query (H, Q) -> (H2, Q2), then stably by hash -> (H, Q)
-            CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, Q, Q2, H, H2, n_ms, 0, qbits, c->stream));
-            TRY(ensure(c, c->cub_tmp, tb));
-            CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, Q, Q2, H, H2, n_ms, 0, qbits, c->stream));
-            CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, H2, H, Q2, Q, n_ms, 32, 64, c->stream));
-            TRY(ensure(c, c->cub_tmp, tb));
-            CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, H2, H, Q2, Q, n_ms, 32, 64, c->stream));
-        } else {
-            CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, H, H2, Q, Q2, n_ms, 32, 64, c->stream));
-            TRY(ensure(c, c->cub_tmp, tb));
-            CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, H, H2, Q, Q2, n_ms, 32, 64, c->stream));
-            std::swap(H, H2);
-            std::swap(Q, Q2);
-        }
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, Q, Q2, H, H2, n_ms, 0, 32, c->stream));
+        TRY(ensure(c, c->cub_tmp, tb));
+        CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, Q, Q2, H, H2, n_ms, 0, 32, c->stream));
         const size_t hist_bytes = n_queries <= QHIST_MAX ? (size_t)n_queries * 4 : 0;
         miss_distinct_kernel<<<grid_for(n_ms, 256, c->num_sms * 8), 256, hist_bytes, c->stream>>>(
-            H, Q, n_ms, (unsigned long long*)d_q_distinct, n_queries);
+            Q2, H2, n_ms, 32 - qbits, (unsigned long long*)d_q_distinct, n_queries);
         c->launches++;
     }
     CU(cudaGetLastError());

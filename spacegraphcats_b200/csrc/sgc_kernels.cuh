@@ -70,6 +70,29 @@ __global__ void plan_expand_kernel(const int64_t* __restrict__ seg_first, const 
 }
 
 
+// the same map, one thread per SEGMENT (batches of long sequences: queries, contigs): the segment's sequence is the
+// last one whose first segment is not after it
+__global__ void plan_expand_segs_kernel(const int64_t* __restrict__ seg_first, const int64_t* __restrict__ off,
+                                        const int64_t* __restrict__ kmer_off, int64_t nseq, int k, int seg_k,
+                                        SegDesc* __restrict__ segdesc) {
+    const int64_t nsegs = seg_first[nseq];
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < nsegs; g += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = nseq;  // first index in (lo, hi] whose seg_first is > g; seg_first[0] = 0 <= g
+        while (hi - lo > 1) {
+            const int64_t mid = lo + (hi - lo) / 2;
+            if (seg_first[mid] <= g) lo = mid; else hi = mid;
+        }
+        const int64_t s = lo, o0 = off[s], nkseq = off[s + 1] - o0 - k + 1, q0 = (g - seg_first[s]) * seg_k;
+        SegDesc d;
+        d.start = o0 + q0;
+        d.kout = kmer_off[s] + q0;
+        d.seq = (unsigned int)s;
+        d.nk = (int)(nkseq - q0 < seg_k ? nkseq - q0 : seg_k);
+        d.pad[0] = d.pad[1] = 0;
+        segdesc[g] = d;
+    }
+}
+
 // ----------------------------------------------------------------------------------
 // stand-alone table kernels
 // ----------------------------------------------------------------------------------
@@ -510,10 +533,11 @@ __global__ void pairs_tally_kernel(const unsigned long long* __restrict__ key, c
             if (s_hist[j]) atomicAdd(&q_distinct[j], (unsigned long long)s_hist[j]);
     }
 }
-// hs / qs: the missing k-mers' hashes and queries, sorted by query and then STABLY by the hashes' top 32 bits: inside
-// a run of equal top bits the elements of one query are neighbours ... of equal full hashes, ordered by query
-__global__ void __launch_bounds__(256) miss_distinct_kernel(const uint64_t* __restrict__ hs, const uint32_t* __restrict__ qs,
-                                                            int64_t n, unsigned long long* q_distinct, int n_queries) {
+// ks / hs: the missing k-mers sorted by their 32-bit key = query << hbits | top hbits bits of the hash, and their
+// full hashes.  Two elements are the same (hash, query) iff they lie in one run of equal keys and their hashes are
+// equal; every first occurrence counts.  Runs are short (a key space of 2^32 for the k-mers of one batch).
+__global__ void __launch_bounds__(256) miss_distinct_kernel(const uint32_t* __restrict__ ks, const uint64_t* __restrict__ hs,
+                                                            int64_t n, int hbits, unsigned long long* q_distinct, int n_queries) {
     extern __shared__ unsigned int s_hist[];
     const bool use_smem = n_queries <= QHIST_MAX;
     if (use_smem) {
@@ -521,18 +545,16 @@ __global__ void __launch_bounds__(256) miss_distinct_kernel(const uint64_t* __re
         __syncthreads();
     }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t key = ks[i];
         const uint64_t h = hs[i];
-        const uint32_t q = qs[i];
         bool dup = false;
-        // elements with the same full hash AND an earlier-or-equal query come before i in its run; the nearest one
-        // with the same hash has the largest such query
-        for (int64_t j = i - 1; j >= 0 && (hs[j] >> 32) == (h >> 32); j--) {
+        for (int64_t j = i - 1; j >= 0 && ks[j] == key; j--)
             if (hs[j] == h) {
-                dup = qs[j] == q;
+                dup = true;
                 break;
             }
-        }
         if (dup) continue;
+        const uint32_t q = key >> hbits;
         if (use_smem) atomicAdd(&s_hist[q], 1u);
         else atomicAdd(&q_distinct[q], 1ULL);
     }

@@ -97,7 +97,7 @@ struct LabelSeqArgs {
     int owner_bits, n_shards;
     // QUERY = true (sgc_query_count_batch): instead of per-read labels the kernel writes, per settled run, the
     // INTERVAL of store positions its k-mers lie at -- iv_key = query << 32 | first position, iv_val = length << 32 |
-    // unitig id; scal->n_export counts them -- and every k-mer that is not in the table as (hash, query) --
+    // unitig id; scal->n_export counts them -- and every k-mer that is not in the table as (hash, sort key) --
     // scal->n_live counts those.  Two store positions never hold the same hash under a clear break bit and the
     // position a probe returns is the one the table keeps for that hash, so the number of DISTINCT matching hashes
     // of a query on a unitig is the size of the union of its intervals there (search/query_by_sequence.py:170-189).
@@ -106,8 +106,9 @@ struct LabelSeqArgs {
     unsigned long long* iv_val;
     unsigned long long iv_cap;
     unsigned long long* miss_hash;
-    uint32_t* miss_q;
+    uint32_t* miss_q;          // the miss's sort key: query << miss_hbits | top miss_hbits bits of the hash
     unsigned long long miss_cap;
+    int miss_hbits;
 };
 constexpr unsigned QCHUNK = 1024;     // records a warp reserves at a time (a trip writes at most 96)
 constexpr int ERR_QUERY_CAP = 4;      // Scalars::err bit: iv_cap / miss_cap too small
@@ -618,6 +619,7 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
             my_hits += nhit;
             if constexpr (QUERY) {
                 const uint32_t qid = act ? (uint32_t)__ldg(a.seq_query + d.seq) : 0u;
+                const uint32_t mkey = (qid << a.miss_hbits) | (uint32_t)(h >> (64 - a.miss_hbits));
                 // Records go into chunks of QCHUNK slots the warp reserves from one global counter (one atomic per
                 // chunk, not per trip); what is left of a chunk is filled with copies of a valid record -- a repeated
                 // interval does not change a union, a repeated (hash, query) is a duplicate like any other.
@@ -629,7 +631,7 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                     if (ms_pos + total > ms_end) {
                         const int src = __ffs((int)mm) - 1;
                         const unsigned long long fh = __shfl_sync(0xffffffffu, (unsigned long long)h, src);
-                        const uint32_t fq = __shfl_sync(0xffffffffu, qid, src);
+                        const uint32_t fq = __shfl_sync(0xffffffffu, mkey, src);
                         for (unsigned long long pp = ms_pos + lane; pp < ms_end; pp += 32)
                             if (pp < a.miss_cap) {
                                 a.miss_hash[pp] = fh;
@@ -644,12 +646,12 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                         const unsigned long long pos = ms_pos + (unsigned)__popc(mm & ((1u << lane) - 1u));
                         if (pos < a.miss_cap) {
                             a.miss_hash[pos] = h;
-                            a.miss_q[pos] = qid;
+                            a.miss_q[pos] = mkey;
                         } else {
                             atomicOr(&a.scal->err, ERR_QUERY_CAP);
                         }
                         last_h = h;
-                        last_q = qid;
+                        last_q = mkey;
                         have_last |= 1u;
                     }
                     ms_pos += total;
