@@ -42,6 +42,10 @@ constexpr int GK = 16;        // k-mers per group: one anchor, fifteen followers
 constexpr int PAIRS_S = 64;   // candidate keys staged per warp before one global reservation
 constexpr int FOFF = 4;       // staged forward words start 4 words into their slot
 constexpr int USEQ_PAD = 8;   // words (128 bases) of zero padding on either end of the sequence store
+#ifndef SGC_LS_RUN_MIN
+#define SGC_LS_RUN_MIN 1
+#endif
+constexpr int RUN_MIN = SGC_LS_RUN_MIN;  // queued runs wait for company (or for the ranges to run out) before they take a trip
 static_assert(USEQ_PAD == SGC_STORE_PAD_WORDS && BRK_PAD == SGC_BRK_PAD_BITS, "include/sgc_b200.h states the store layout");
 #ifndef SGC_LS_NT
 #define SGC_LS_NT 256
@@ -123,11 +127,11 @@ struct alignas(16) WarpTileS {
     uint32_t P[G::SPW * G::PWS];       // the round's segments, 2 bits per base
     SegDesc D[3][G::SPW];
     unsigned long long pairs[PAIRS_S];
-    unsigned short q[G::QCAP];         // queued runs of this round: k-mer | segment << 7 | followers << 9 | back << 13 | flagged << 14
+    unsigned short qr[G::QCAP / 2];    // queued runs of this round: k-mer | segment << 7 | followers << 9 | back << 13 | flagged << 14
+    unsigned short qs[G::QCAP];        // queued ranges of k-mers to probe one by one: first k-mer | segment << 7 | (count - 1) << 9
     int gpre[G::SPW + 1];
-    unsigned qfill;
     unsigned segbad;                   // bit sg: segment sg holds a byte that is not A/C/G/T (ASCII input)
-    unsigned pad_[1];
+    unsigned pad_[2];
 };
 
 // the walk past a full home bucket, out of line
@@ -323,7 +327,6 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
             if (lane < SPW) wt.gpre[lane + 1] = incl;
             if (lane == 0) {
                 wt.gpre[0] = 0;
-                wt.qfill = 0;
                 wt.segbad = 0;
             }
         }
@@ -393,38 +396,75 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
         prefetch_raw(nxt);  // lands while this round is worked on
         cp_async_commit();
 
-        // ---- the round's work items: anchors [0, ng), then the queue ----
-        // warp-uniform state is re-read from shared memory where it is used (volatile: not hoisted)
+        // ---- the round's work items: the anchors of its groups, then what they queue ----
+        // Two queues (their cursors are warp-uniform registers): RUNS (an anchor k-mer, hashed and probed, and the
+        // followers it may settle through the store) and RANGES of k-mers that each have to be probed on their own.
+        // A trip gives its first lanes to runs -- anchors first; queued runs only when a few have gathered or nothing
+        // else is left, so that the compare code below runs in few trips -- and fills the others from the ranges.
         const volatile int* gpre = wt.gpre;
-        const volatile unsigned* qfill_p = &wt.qfill;
-        // (a trip takes the next <= 32 items that exist when it starts; what it queues is seen by the next one)
-        for (int t0 = 0, t1 = 0;; t0 = t1) {
-            const int ng = gpre[SPW];
-            const int nq = (int)*qfill_p;
-            if (t0 >= ng + nq) break;
-            t1 = t0 + 32 < ng + nq ? t0 + 32 : ng + nq;
-            const int item = t0 + lane;
-            const bool act = item < ng + nq;
+        const int ng = gpre[SPW];
+        int a_done = 0, qr_fill = 0, qr_done = 0, qs_fill = 0, qs_done = 0;
+        for (;;) {
+            const int na = ng - a_done, nr = qr_fill - qr_done, nsi = qs_fill - qs_done;
+            if (na + nr + nsi == 0) break;
+            const int n_a = na < 32 ? na : 32;
+            int n_r = 0;
+            if (n_a < 32 && nr > 0 && (na > 0 || nr >= RUN_MIN || nsi == 0)) n_r = nr < 32 - n_a ? nr : 32 - n_a;
+            const int n_run = n_a + n_r;        // lanes [0, n_run) hold runs
             // an item is a RUN: its anchor k-mer qa (hashed and probed here) and n-1 followers, the k-mers after
             // it (back = false) or before it (back = true); flagged = a miss may not turn the run around again
             int sg = 0, qa = 0, n = 1;
-            bool back = false, flagged = false;
-            if (item < ng) {
+            bool back = false, flagged = false, act = lane < n_run;
+            const bool is_anchor = lane < n_a;
+            if (is_anchor) {
+                const int item = a_done + lane;
 #pragma unroll
                 for (int s = 1; s < SPW; s++) sg += item >= gpre[s];
                 qa = (item - gpre[sg]) * GK;
                 n = GK;
             } else if (act) {
-                const unsigned u = wt.q[item - ng];
+                const unsigned u = wt.qr[qr_done + lane - n_a];
                 qa = (int)(u & 127u);
                 sg = (int)((u >> 7) & 3u);
                 n = (int)((u >> 9) & 15u) + 1;
                 back = (u >> 13) & 1u;
                 flagged = (u >> 14) & 1u;
             }
+            a_done += n_a;
+            qr_done += n_r;
+            if (n_run < 32 && nsi > 0) {  // warp-uniform: lanes [n_run, 32) take single k-mers from the next ranges
+                const bool has = lane < nsi;
+                const unsigned u = has ? wt.qs[qs_done + lane] : 0u;
+                const int cnt = has ? (int)((u >> 9) & 15u) + 1 : 0;
+                int incl = cnt;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const int x = __shfl_up_sync(0xffffffffu, incl, dd);
+                    if (lane >= dd) incl += x;
+                }
+                const int first = n_run + incl - cnt;   // the lane slot this range starts at
+                // bit j = a range starts at slot j: slot j belongs to the popc(heads up to j)-th range
+                const unsigned heads = __reduce_or_sync(0xffffffffu, has && first < 32 ? 1u << first : 0u);
+                const int it = __popc(heads & (0xFFFFFFFFu >> (31 - lane))) - 1;
+                const unsigned ui = __shfl_sync(0xffffffffu, u, it < 0 ? 0 : it);
+                const int fi = __shfl_sync(0xffffffffu, first, it < 0 ? 0 : it);
+                const int ci = __shfl_sync(0xffffffffu, cnt, it < 0 ? 0 : it);
+                if (lane >= n_run && it >= 0 && lane - fi < ci) {
+                    act = true;
+                    qa = (int)(ui & 127u) + (lane - fi);
+                    sg = (int)((ui >> 7) & 3u);
+                }
+                // ranges that fit are done; the one cut off by the end of the trip keeps what is left of it
+                const bool whole = has && first + cnt <= 32;
+                if (has && first < 32 && !whole) {
+                    const int taken = 32 - first;
+                    wt.qs[qs_done + lane] = (unsigned short)((u & 0x180u) | ((u & 127u) + (unsigned)taken) | ((unsigned)(cnt - taken - 1) << 9));
+                }
+                qs_done += __popc(__ballot_sync(0xffffffffu, whole));
+            }
             const SegDesc& d = wt.D[cur][sg];
             const int nk = d.nk;
-            if (item < ng && nk - qa < GK) n = nk - qa;
+            if (is_anchor && nk - qa < GK) n = nk - qa;
             const uint32_t* Fs = wt.F + sg * WPS + FOFF;
             const uint32_t* Rs = wt.R + sg * WPS;
 
@@ -462,8 +502,8 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
             bool q_along = true;
 
             const bool is_run = act && n > 1;
-            if (__any_sync(0xffffffffu, is_run)) {  // warp-uniform: this trip holds runs
-                unsigned singles = 0;          // followers to probe one by one, bit i = k-mer lo + i
+            if (n_run > 0) {  // warp-uniform: this trip holds runs
+                unsigned singles = 0;          // followers to probe one by one, bit i = k-mer lo + i (always a contiguous range)
                 unsigned run_item = 0u;        // a follow-up run (encoded, bit 15 set) or 0
                 int lo = qa;
                 if (is_run) {
@@ -594,27 +634,18 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                             singles = valid & ~(1u << ao);
                     }
                 }
-                // queue what the store did not settle (in item order: a read's k-mers stay neighbours)
-                const int cnt = __popc(singles) + (run_item ? 1 : 0);
-                int incl = cnt;
-#pragma unroll
-                for (int dd = 1; dd < 32; dd <<= 1) {
-                    const int x = __shfl_up_sync(0xffffffffu, incl, dd);
-                    if (lane >= dd) incl += x;
+                // queue what the store did not settle: one range and one run per lane at most
+                const unsigned ms = __ballot_sync(0xffffffffu, singles != 0u);
+                const unsigned mr = __ballot_sync(0xffffffffu, run_item != 0u);
+                const unsigned below = (1u << lane) - 1u;
+                if (singles) {
+                    const int first = lo + __ffs((int)singles) - 1;
+                    wt.qs[qs_fill + __popc(ms & below)] =
+                        (unsigned short)((unsigned)first | ((unsigned)sg << 7) | ((unsigned)(__popc(singles) - 1) << 9));
                 }
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                if (total) {
-                    int pos = nq + incl - cnt;
-                    const unsigned one = (1u << 14) | ((unsigned)sg << 7);
-                    while (singles) {
-                        const int dd = __ffs((int)singles) - 1;
-                        singles &= singles - 1u;
-                        wt.q[pos++] = (unsigned short)(one | (unsigned)(lo + dd));
-                    }
-                    if (run_item) wt.q[pos] = (unsigned short)(run_item & 0x7FFFu);
-                    __syncwarp();
-                    if (lane == 0) wt.qfill = (unsigned)(nq + total);
-                }
+                if (run_item) wt.qr[qr_fill + __popc(mr & below)] = (unsigned short)(run_item & 0x7FFFu);
+                qs_fill += __popc(ms);
+                qr_fill += __popc(mr);
             }
             my_hits += nhit;
             if constexpr (QUERY) {
