@@ -5,7 +5,7 @@ Workload (BASELINE.json configs[3]): synthetic metagenome
 500 M unitig k-mers (k=31) in a GPU-resident table replicated per GPU; 150-bp reads with 0.5 %
 substitution errors, half reverse-complemented, labelled with the distinct unitig ids their
 k-mers hit (cdbg/index_reads.py:143-152).  One STEP = one batch of 2^24 reads (2.01e9 k-mers);
-the reads are held 2 bits per base (48 bytes per read, the layout the host feeder emits) and are
+the reads are held 2 bits per base (40 bytes per 150-bp read, the layout the host feeder emits) and are
 expanded to ASCII inside the kernel.  The default 12 steps are the config's 200 M reads.
 
   value  k-mers/s, whole job, inputs resident in HBM, timed with CUDA events on the launch stream
@@ -252,7 +252,7 @@ def workload_config(args, cpu=False):
         "kmers_per_step": args.batch_reads * (READ_LEN - KSIZE + 1), "error_rate": ERR_PPM / 1e6,
         "table": "replicated", "table_kmers": args.table_kmers,
         "read_format": "ASCII (1 byte per base + int64 offsets)" if args.ascii else
-                       "2-bit packed, 48 bytes per 150-bp read (the host feeder's output; expanded to ASCII in the kernel)",
+                       "2-bit packed, 40 bytes per 150-bp read (the host feeder's output; expanded to ASCII in the kernel)",
         "label_kernel": "per-k-mer probes (SGC_NO_SIDE)" if os.environ.get("SGC_NO_SIDE") else
                         "labelseq: one hashed+probed anchor per 16 k-mers, followers settled by comparing the read's 2-bit bases with the table's unitig sequence store; unsettled k-mers hashed+probed one per lane",
         "l2": "inputs (0.8 GB packed reads/step, 27 GB table + 0.3 GB unitig sequence store) far larger than the 126 MB L2; no flush needed",
@@ -783,7 +783,7 @@ def main():
     # SURVEY 8(d)'s per-unit figure: L/(L-k+1) B of sequence + ONE 32-byte table sector + 4 B of id per k-mer
     survey_bytes = READ_LEN / nkr + SECTOR + 4.0
     # what this launch strictly needs: the read as it is stored + one sector + the labels it writes
-    in_bytes = READ_LEN / nkr if args.ascii else 48.0 / nkr
+    in_bytes = READ_LEN / nkr if args.ascii else 40.0 / nkr
     strict_bytes = in_bytes + SECTOR + 4.0 * labels_per_read / nkr
     tile_s = tile_ms.value / 1e3 / max(tile_n.value, 1)
     achieved = survey_bytes * step_kmers / tile_s / 1e9

@@ -187,8 +187,9 @@ int sgc_label_reads_finish(sgc_table* t, int64_t* h_n_kmers, int64_t* h_n_hits,
                            int64_t* h_n_labels);
 /*
  * The same step on 2-BIT PACKED reads (a quarter of the bytes over PCIe and HBM): A=0 C=1 G=2 T=3, base b
- * of record s in bits 2(b%4).. of byte 16*U(s) + b/4 where U(s) = sum over earlier records of
- * ceil(len/64) -- every record starts on a 16-byte boundary.  Lengths in bases: d_len[nseq] (int32), or
+ * of record s in bits 2(b%4).. of byte 4*U(s) + b/4 where U(s) = sum over earlier records of
+ * ceil(len/16) -- every record starts on a 4-byte boundary (40 bytes per 150-bp read); d_packed itself must be
+ * 16-byte aligned.  Lengths in bases: d_len[nseq] (int32), or
  * NULL when every record has uniform_len bases (nothing but the packed bytes crosses the bus then).
  * The kernel expands the codes back to the ASCII words the reference hash is defined on, so the labels are
  * those of sgc_label_reads on the unpacked reads.  Packed records cannot carry non-ACGT bytes: the packer

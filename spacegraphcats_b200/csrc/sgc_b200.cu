@@ -1329,7 +1329,7 @@ int make_packed_plan(sgc_ctx* c, const int32_t* d_len, int uniform_len, int64_t 
     TRY(ensure(c, c->kmer_off, n1 * 8));
     TRY(ensure(c, c->units, n1 * 8));
     TRY(ensure(c, c->unit_off, n1 * 8));
-    // every 16-byte unit holds 64 bases: at most one segment per started unit pair (seg_k = 128) plus one per record
+    // every 4-byte unit holds 16 bases: at most one segment per seg_k bases plus one per record
     const int64_t max_segs = nseq + packed_bytes * 4 / seg_k + 1;
     TRY(ensure(c, c->seg_map, (size_t)max_segs * sizeof(SegDesc)));
     CU(cudaMemsetAsync(&c->d_scal->bad_offsets, 0, sizeof(int), c->stream));
@@ -1402,13 +1402,13 @@ int sgc_label_reads_launch(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes
 
 int64_t sgc_packed_bytes(const int32_t* h_len, int uniform_len, int64_t nseq) {
     if (nseq < 0) return -1;
-    if (!h_len) return uniform_len < 0 ? -1 : nseq * (int64_t)((uniform_len + 63) / 64) * 16;
+    if (!h_len) return uniform_len < 0 ? -1 : nseq * (int64_t)((uniform_len + 15) / 16) * 4;
     int64_t units = 0;
     for (int64_t s = 0; s < nseq; s++) {
         if (h_len[s] < 0) return -1;
-        units += ((int64_t)h_len[s] + 63) / 64;
+        units += ((int64_t)h_len[s] + 15) / 16;
     }
-    return units * 16;
+    return units * 4;
 }
 
 int sgc_label_reads_packed_launch(sgc_table* t, const uint8_t* d_packed, int64_t packed_bytes, const int32_t* d_len,
@@ -1485,12 +1485,12 @@ int sgc_pack_reads_device(sgc_ctx* c, const uint8_t* d_seq, int64_t seq_bytes, c
     CU(cudaMemcpyAsync(&units, (int64_t*)c->unit_off.p + nseq, 8, cudaMemcpyDeviceToHost, c->stream));
     TRY(fetch_scalars(c));
     TRY(bad_offsets_check(c));
-    *h_packed_bytes = units * 16;
-    if (units * 16 > packed_cap) return fail(SGC_ERR_CAPACITY, "packed_cap %lld < %lld bytes", (long long)packed_cap, (long long)(units * 16));
+    *h_packed_bytes = units * 4;
+    if (units * 4 > packed_cap) return fail(SGC_ERR_CAPACITY, "packed_cap %lld < %lld bytes", (long long)packed_cap, (long long)(units * 4));
     if (d_status) CU(cudaMemsetAsync(d_status, 0, (size_t)nseq * 4, c->stream));
     if (units > 0) {
-        pack_reads_kernel<<<grid_for(units * 4, 256, c->num_sms * 16), 256, 0, c->stream>>>(
-            d_seq, d_off, (const int64_t*)c->unit_off.p, nseq, (uint32_t*)d_packed, units * 4, d_status);
+        pack_reads_kernel<<<grid_for(units, 256, c->num_sms * 16), 256, 0, c->stream>>>(
+            d_seq, d_off, (const int64_t*)c->unit_off.p, nseq, (uint32_t*)d_packed, units, d_status);
         c->launches++;
     }
     CU(cudaGetLastError());

@@ -315,7 +315,7 @@ int sgc_bgzf_inflate(const uint8_t* h_raw, int64_t raw_bytes, const int64_t* h_c
 
 // ---------------------------------------------------------------------------- 2-bit packing
 // ASCII (seq, off) -> packed records for sgc_label_reads_packed: A=0 C=1 G=2 T=3, base b of record s in bits
-// 2(b%4).. of byte 16*unit_off[s] + b/4, every record padded to a multiple of 16 bytes (64 bases).
+// 2(b%4).. of byte 4*unit_off[s] + b/4, every record padded to a multiple of 4 bytes (16 bases).
 // h_len[s] = length in bases; h_bad[s] (nullable) = 1 when the record holds a byte other than A/C/G/T (packed
 // as A: the caller applies the reference's policy -- khmer raises on such reads).  A quarter of the bytes
 // cross PCIe and HBM; the kernel expands them back to the ASCII words the reference hash is defined on.
@@ -326,9 +326,9 @@ int sgc_pack_reads(const uint8_t* h_seq, const int64_t* h_off, int64_t nseq, int
     for (int64_t s = 0; s < nseq; ++s) {
         const int64_t L = h_off[s + 1] - h_off[s];
         if (L < 0 || L > 0x7FFFFFFF) return fail(SGC_ERR_ARG, "bad offsets at record %lld", (long long)s);
-        uoff[(size_t)s + 1] = uoff[(size_t)s] + (L + 63) / 64;
+        uoff[(size_t)s + 1] = uoff[(size_t)s] + (L + 15) / 16;
     }
-    const int64_t total = uoff[(size_t)nseq] * 16;
+    const int64_t total = uoff[(size_t)nseq] * 4;
     *h_packed_bytes = total;
     if (total > packed_cap) return fail(SGC_ERR_CAPACITY, "packed_cap %lld < %lld bytes", (long long)packed_cap, (long long)total);
     if (total > 0 && (!h_packed || !h_seq)) return fail(SGC_ERR_ARG, "NULL buffer");
@@ -339,8 +339,8 @@ int sgc_pack_reads(const uint8_t* h_seq, const int64_t* h_off, int64_t nseq, int
         for (int64_t s = s0; s < s1; ++s) {
             const uint8_t* src = h_seq + h_off[s];
             const int64_t L = h_off[s + 1] - h_off[s];
-            uint8_t* dst = h_packed + uoff[(size_t)s] * 16;
-            const int64_t nbytes = (uoff[(size_t)s + 1] - uoff[(size_t)s]) * 16;
+            uint8_t* dst = h_packed + uoff[(size_t)s] * 4;
+            const int64_t nbytes = (uoff[(size_t)s + 1] - uoff[(size_t)s]) * 4;
             uint8_t bad = 0;
             int64_t b = 0, o = 0;
             for (; b + 4 <= L; b += 4, ++o) {

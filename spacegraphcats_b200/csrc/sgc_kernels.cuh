@@ -738,7 +738,7 @@ __global__ void packed_count_kernel(const int32_t* __restrict__ len, int uniform
         if (L < 0) atomicOr(&scal->bad_offsets, 1);
         else {
             nk = L - k + 1 > 0 ? L - k + 1 : 0;
-            units = (L + 63) / 64;
+            units = (L + 15) / 16;
         }
     }
     nk_out[s] = nk;
@@ -746,8 +746,8 @@ __global__ void packed_count_kernel(const int32_t* __restrict__ len, int uniform
     units_out[s] = units;
 }
 
-// segment map of packed records: start = byte offset of the segment's first base (seg_k % 64 == 0, so it
-// stays 16-byte aligned)
+// segment map of packed records (units of one 32-bit word = 16 bases): start = byte offset of the segment's first
+// base (seg_k % 16 == 0, so it stays word aligned)
 __global__ void packed_expand_kernel(const int64_t* __restrict__ seg_first, const int64_t* __restrict__ unit_off,
                                      const int64_t* __restrict__ nk_arr, const int64_t* __restrict__ kmer_off,
                                      int64_t nseq, int seg_k, int64_t packed_bytes, SegDesc* __restrict__ segdesc,
@@ -755,16 +755,16 @@ __global__ void packed_expand_kernel(const int64_t* __restrict__ seg_first, cons
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nseq) return;
     const int64_t a = seg_first[s], b = seg_first[s + 1];
-    if (unit_off[s + 1] * 16 > packed_bytes) atomicOr(&scal->bad_offsets, 1);
+    if (unit_off[s + 1] * 4 > packed_bytes) atomicOr(&scal->bad_offsets, 1);
     if (a == b) return;
-    const int64_t nkseq = nk_arr[s], ko = kmer_off[s], p0 = unit_off[s] * 16;
+    const int64_t nkseq = nk_arr[s], ko = kmer_off[s], p0 = unit_off[s] * 4;
     for (int64_t j = a; j < b; j++) {
         const int64_t q0 = (j - a) * seg_k;
         SegDesc d;
         d.start = p0 + q0 / 4;
         d.kout = ko + q0;
         d.seq = (unsigned int)s;
-        d.nk = unit_off[s + 1] * 16 > packed_bytes ? 0 : (int)(nkseq - q0 < seg_k ? nkseq - q0 : seg_k);
+        d.nk = unit_off[s + 1] * 4 > packed_bytes ? 0 : (int)(nkseq - q0 < seg_k ? nkseq - q0 : seg_k);
         d.pad[0] = d.pad[1] = 0;
         segdesc[j] = d;
     }
@@ -776,7 +776,7 @@ __global__ void len_to_i64_kernel(const int32_t* __restrict__ len, int uniform_l
     out[s] = s < nseq ? (len ? (int64_t)len[s] : (int64_t)uniform_len) : 0;
 }
 
-// base offsets -> 16-byte units per record (and the int32 lengths the packed API takes)
+// base offsets -> 4-byte units per record (and the int32 lengths the packed API takes)
 __global__ void off_to_units_kernel(const int64_t* __restrict__ off, int64_t nseq, int64_t seq_bytes,
                                     int64_t* __restrict__ units, int32_t* len_out, Scalars* scal) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -786,7 +786,7 @@ __global__ void off_to_units_kernel(const int64_t* __restrict__ off, int64_t nse
         const int64_t o0 = off[s], o1 = off[s + 1];
         if (o0 < 0 || o1 < o0 || o1 > seq_bytes || o1 - o0 > 0x7FFFFFFF) atomicOr(&scal->bad_offsets, 1);
         else {
-            u = (o1 - o0 + 63) / 64;
+            u = (o1 - o0 + 15) / 16;
             if (len_out) len_out[s] = (int32_t)(o1 - o0);
         }
     }
@@ -799,13 +799,13 @@ __global__ void pack_reads_kernel(const uint8_t* __restrict__ seq, const int64_t
                                   const int64_t* __restrict__ unit_off, int64_t nseq, uint32_t* __restrict__ packed,
                                   int64_t total_words, int32_t* status) {
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total_words; w += (int64_t)gridDim.x * blockDim.x) {
-        // record of word w: largest s with unit_off[s] * 4 <= w
+        // record of word w: largest s with unit_off[s] <= w
         int64_t lo = 0, hi = nseq - 1;
         while (lo < hi) {
             const int64_t mid = (lo + hi + 1) >> 1;
-            if (unit_off[mid] * 4 <= w) lo = mid; else hi = mid - 1;
+            if (unit_off[mid] <= w) lo = mid; else hi = mid - 1;
         }
-        const int64_t b0 = (w - unit_off[lo] * 4) * 16, L = off[lo + 1] - off[lo];
+        const int64_t b0 = (w - unit_off[lo]) * 16, L = off[lo + 1] - off[lo];
         uint32_t x = 0;
         bool bad = false;
         for (int j = 0; j < 16; j++) {
@@ -832,7 +832,7 @@ __global__ void unpack_reads_kernel(const uint32_t* __restrict__ packed, const i
             if (off[mid] <= i) lo = mid; else hi = mid - 1;
         }
         const int64_t b = i - off[lo];
-        const uint32_t x = packed[unit_off[lo] * 4 + (b >> 4)];
+        const uint32_t x = packed[unit_off[lo] + (b >> 4)];
         seq[i] = "ACGT"[(x >> (2 * (b & 15))) & 3u];
     }
 }

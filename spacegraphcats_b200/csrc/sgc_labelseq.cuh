@@ -27,7 +27,7 @@
 //     hash (2 x Murmur3 over the staged ASCII words, any byte alignment), probe the home bucket, then
 //     anchors: compare with the store and queue the unsettled followers; all: emit (sequence, id) keys.
 //   * PACKED = true: the reads arrive 2 bits per base (A=0 C=1 G=2 T=3, base b of a record in bits
-//     2(b%4).. of byte b/4, every record 16-byte aligned) and are expanded to the ASCII words the reference
+//     2(b%4).. of byte b/4, every record word aligned) and are expanded to the ASCII words the reference
 //     hash is defined on while they are staged (PRMT on "ACGT"); ASCII input is packed the other way.
 #pragma once
 #include "sgc_kmer.cuh"
@@ -71,7 +71,8 @@ struct GeoS {
     static constexpr int STRIDE = ((SEGB + 32 + 15) / 16) * 16;     // bytes per staged ASCII area
     static constexpr int WPS = STRIDE / 4;
     static constexpr int PWS = (SEGB + 15) / 16 + 4;                // 2-bit words per segment (+ slack for window reads)
-    static constexpr int RAWW = PACKED ? ((SEGB + 63) / 64) * 4 : WPS;  // words of the raw copy of a segment
+    // words of the raw copy of a segment (packed: 16-byte chunks around a word-aligned start)
+    static constexpr int RAWW = PACKED ? (((SEGB + 15) / 16 + 3 + 3) / 4) * 4 : WPS;
     static constexpr int QCAP = SPW * SEG_KS;                       // a round queues at most its own k-mers
     static_assert(32 % SPW == 0, "lanes per segment");
     static_assert(SPW <= 4 && SEG_KS <= 128 && GK <= 16, "a queued run is 15 bits: k-mer 7, segment 2, followers 4, back, flagged");
@@ -277,11 +278,13 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
         const SegDesc& d = wt.D[slot][sgi];
         if (d.nk > 0) {
             const int Ls = d.nk + k - 1;
-            if constexpr (PACKED) {  // records are 16-byte aligned and a segment starts 32 bytes after the last
-                const int nchunks = (((Ls + 3) >> 2) + 15) >> 4;
+            if constexpr (PACKED) {  // records are word aligned and a segment starts 32 bytes after the last:
+                // copy the 16-byte chunks that hold its bytes (each holds valid bytes of the buffer, so it is mapped)
+                const uintptr_t g0 = (uintptr_t)a.seq + (uintptr_t)d.start;
+                const uintptr_t a0 = g0 & ~(uintptr_t)15;
+                const int nchunks = (int)(((g0 + (uintptr_t)((Ls + 3) >> 2) + 15) & ~(uintptr_t)15) - a0) >> 4;
                 unsigned char* dst = reinterpret_cast<unsigned char*>(wt.RAW + sgi * RAWW);
-                const unsigned char* src = a.seq + d.start;
-                for (int c = sub; c < nchunks; c += LPS) cp_async16(dst + 16 * c, src + 16 * c);
+                for (int c = sub; c < nchunks; c += LPS) cp_async16(dst + 16 * c, reinterpret_cast<const void*>(a0 + 16 * (uintptr_t)c));
             } else {
                 const uintptr_t g0 = (uintptr_t)a.seq + (uintptr_t)d.start;
                 const uintptr_t a0 = g0 & ~(uintptr_t)15;
@@ -343,7 +346,7 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
             const int npw = (Ls + 15) >> 4;
             if (nk) {
                 if constexpr (PACKED) {
-                    const uint32_t* pk = wt.RAW + sg * RAWW;
+                    const uint32_t* pk = wt.RAW + sg * RAWW + ((((uintptr_t)a.seq + (uintptr_t)d.start) & 15) >> 2);
                     for (int j = sub; j < npw; j += LPS) {
                         const uint32_t x = pk[j];
                         Ps[j] = x;

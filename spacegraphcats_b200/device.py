@@ -40,7 +40,7 @@ def pack_reads_host(buf, off, n_threads=0):
     off = np.ascontiguousarray(off, np.int64)
     n = len(off) - 1
     lens = np.diff(off)
-    cap = int(((lens + 63) // 64).sum()) * 16
+    cap = int(((lens + 15) // 16).sum()) * 4
     packed = np.empty(max(cap, 16), np.uint8)
     h_len = np.zeros(max(n, 1), np.int32)
     bad = np.zeros(max(n, 1), np.uint8)
@@ -187,7 +187,7 @@ class Context:
         d_seq = self.to_device(seq, np.uint8)
         d_off = self.to_device(off, np.int64)
         nseq = d_off.numel() - 1
-        cap = (d_seq.numel() // 4 + 16 * nseq + 16 + 15) // 16 * 16  # every record rounds up to 16 bytes
+        cap = (d_seq.numel() // 4 + 4 * nseq + 16 + 15) // 16 * 16  # every record rounds up to 4 bytes
         d_packed = self.empty(cap, torch.uint8)
         d_len = self.empty(max(nseq, 1), torch.int32)
         d_stat = self.empty(max(nseq, 1), torch.int32)

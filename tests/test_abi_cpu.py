@@ -317,7 +317,7 @@ def test_bgzf_reader_on_python_written_blocks(tmp_path):
 
 
 def test_host_packer_layout_and_bad_base_flags():
-    """sgc_pack_reads: 2 bits per base, A=0 C=1 G=2 T=3, records padded to 16 bytes; non-ACGT flagged."""
+    """sgc_pack_reads: 2 bits per base, A=0 C=1 G=2 T=3, records padded to 4 bytes; non-ACGT flagged."""
     from spacegraphcats_b200.device import pack_reads_host, pack_sequences
 
     rng = np.random.default_rng(4)
@@ -331,7 +331,7 @@ def test_host_packer_layout_and_bad_base_flags():
         assert bad.tolist() == [any(c not in "ACGT" for c in s) for s in seqs]
         pos = 0
         for s in seqs:
-            nb = (len(s) + 63) // 64 * 16
+            nb = (len(s) + 15) // 16 * 4
             rec = pk[pos:pos + nb]
             pos += nb
             dec = "".join("ACGT"[(int(rec[b // 4]) >> (2 * (b % 4))) & 3] for b in range(len(s)))
@@ -341,6 +341,6 @@ def test_host_packer_layout_and_bad_base_flags():
     from spacegraphcats_b200._lib import lib
 
     L = lib()
-    assert L.sgc_packed_bytes(None, 150, 10) == 10 * 48
+    assert L.sgc_packed_bytes(None, 150, 10) == 10 * 40
     lens = np.array([0, 1, 64, 65], np.int32)
-    assert L.sgc_packed_bytes(lens.ctypes.data_as(ctypes.c_void_p), -1, 4) == (0 + 1 + 1 + 2) * 16
+    assert L.sgc_packed_bytes(lens.ctypes.data_as(ctypes.c_void_p), -1, 4) == (0 + 1 + 4 + 5) * 4
