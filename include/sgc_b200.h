@@ -323,7 +323,16 @@ int sgc_label_reads_partitioned(sgc_table* t, const uint8_t* d_seq, int64_t seq_
  *   sgc_peer_import_fd      map such an fd on this context's GPU;  sgc_peer_unmap undoes it
  *   sgc_table_set_peers     from now on sgc_label_reads* on this table probe h_bucket_ptrs[owner] and match against
  *                           the replicated store (d_useq = word of position 0 of shard 0); n_ranks = 0 undoes it
+ *   sgc_filter_insert       set the bits of n hashes in a MISS FILTER of 2^filt_bits 64-bit words (word = the hash's top
+ *                           filt_bits bits -- so an owner's hashes fill one contiguous slice of it and the full filter is
+ *                           the all-gather of the owners' slices --, four bit positions from its low 24 bits)
+ *   sgc_table_set_filter    give a peer-probed table the replicated filter: a k-mer that must be probed on its own (one
+ *                           that overlaps a sequencing error: almost always in nobody's table) and whose owner is another
+ *                           GPU is first looked up in the filter, in local HBM; a missing bit proves the miss (no false
+ *                           negatives), so the labels are unchanged and the NVLink load is saved.  d_words = NULL: off
  */
+int sgc_filter_insert(sgc_ctx* ctx, const uint64_t* d_hash, int64_t n, uint64_t* d_words, int filt_bits);
+int sgc_table_set_filter(sgc_table* t, const uint64_t* d_words, int filt_bits, int my_rank);
 #define SGC_STORE_PAD_WORDS 8 /* 32-bit words of zero padding on either side of a store shard */
 #define SGC_BRK_PAD_BITS 32   /* bit index of position 0 in a shard's break-bit array */
 int sgc_hash_positions(sgc_ctx* ctx, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off, int64_t nseq, int k,

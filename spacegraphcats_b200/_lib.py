@@ -86,6 +86,8 @@ PROTOTYPES = {
     "sgc_peer_import_fd": (_i32, [_vp, _i32, _i64, ctypes.POINTER(_vp)]),
     "sgc_peer_unmap": (_i32, [_vp, _vp, _i64]),
     "sgc_table_set_peers": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _vp, _i64]),
+    "sgc_filter_insert": (_i32, [_vp, _vp, _i64, _vp, _i32]),
+    "sgc_table_set_filter": (_i32, [_vp, _vp, _i32, _i32]),
     "sgc_peer_alloc": (_i32, [_vp, _i64, ctypes.POINTER(_vp), _vp]),
     "sgc_peer_open": (_i32, [_vp, _vp, ctypes.POINTER(_vp)]),
     "sgc_peer_close": (_i32, [_vp, _vp]),

@@ -129,6 +129,9 @@ struct sgc_table {
     // hash-range partitioned table probed over peer memory (sgc_table_set_peers): every owner's bucket array,
     // the store replicated on this GPU (one shard per rank) and the id range of every shard
     int peer_n = 0;
+    const unsigned long long* peer_filt = nullptr;  // replicated miss filter (sgc_table_set_filter), optional
+    int peer_filt_bits = 0;
+    int peer_rank = -1;
     const Bucket* peer_tbl[32] = {nullptr};
     uint32_t id_bounds[33] = {0};
     const uint32_t* peer_useq = nullptr;
@@ -1295,6 +1298,11 @@ void labelseq_args(LabelSeqArgs& a, sgc_table* t, const uint8_t* seq, const Plan
         int b = 0;
         while ((1 << b) < t->peer_n) b++;
         a.owner_bits = b;
+        if (t->peer_filt && !getenv("SGC_NO_FILTER")) {
+            a.filt = t->peer_filt;
+            a.filt_shift = 64 - t->peer_filt_bits;
+            a.my_rank = t->peer_rank;
+        }
     }
     a.pairs = (unsigned long long*)c->pairs_a.p;
     a.pairs_cap = pairs_cap;
@@ -1885,6 +1893,27 @@ int sgc_table_set_peers(sgc_table* t, int n_ranks, const void* const* h_bucket_p
     t->peer_brk = d_brk;
     t->peer_ustride = useq_stride_words;
     t->peer_bstride = brk_stride_words;
+    return SGC_OK;
+}
+
+int sgc_filter_insert(sgc_ctx* c, const uint64_t* d_hash, int64_t n, uint64_t* d_words, int filt_bits) {
+    if (!c || n < 0 || filt_bits < 1 || filt_bits > 40 || (n > 0 && (!d_hash || !d_words))) return fail(SGC_ERR_ARG, "bad argument");
+    TRY(set_device(c));
+    if (n > 0) {
+        filter_insert_kernel<<<grid_for(n, 256, c->num_sms * 16), 256, 0, c->stream>>>(d_hash, n, (unsigned long long*)d_words,
+                                                                                   64 - filt_bits);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    return SGC_OK;
+}
+
+int sgc_table_set_filter(sgc_table* t, const uint64_t* d_words, int filt_bits, int my_rank) {
+    if (!t) return fail(SGC_ERR_ARG, "table is NULL");
+    if (d_words && (filt_bits < 1 || filt_bits > 40 || my_rank < 0)) return fail(SGC_ERR_ARG, "bad argument");
+    t->peer_filt = (const unsigned long long*)d_words;
+    t->peer_filt_bits = filt_bits;
+    t->peer_rank = my_rank;
     return SGC_OK;
 }
 

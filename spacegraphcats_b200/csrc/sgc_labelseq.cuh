@@ -100,6 +100,13 @@ struct LabelSeqArgs {
     uint32_t id_bounds[33];
     long long ustride, bstride;
     int owner_bits, n_shards;
+    // PEER, optional: a replicated MISS FILTER over the hashes of all owners (one 64-bit word per hash: word = its top
+    // filt_bits bits, four bit positions from its low 24 bits; sgc_filter_insert).  A k-mer that has to be probed on
+    // its own -- in practice one that overlaps a sequencing error and is in nobody's table -- and whose owner is
+    // another GPU is first looked up here, in local HBM: a missing bit proves the miss and saves the NVLink load.
+    const unsigned long long* filt;
+    int filt_shift;   // 64 - filt_bits
+    int my_rank;
     // QUERY = true (sgc_query_count_batch): instead of per-read labels the kernel writes, per settled run, the
     // INTERVAL of store positions its k-mers lie at -- iv_key = query << 32 | first position, iv_val = length << 32 |
     // unitig id; scal->n_export counts them -- and every k-mer that is not in the table as (hash, sort key) --
@@ -141,6 +148,17 @@ __device__ __noinline__ uint32_t lookup_slow_call(const Bucket* tbl, uint32_t nl
     const uint32_t v = lookup_slow(tbl, nlines, hb, h, ax);
     *aux = ax;
     return v;
+}
+
+// the four bits of a hash in its word of the miss filter
+__host__ __device__ __forceinline__ unsigned long long filter_bits(uint64_t h) {
+    return (1ULL << (h & 63)) | (1ULL << ((h >> 6) & 63)) | (1ULL << ((h >> 12) & 63)) | (1ULL << ((h >> 18) & 63));
+}
+__global__ void filter_insert_kernel(const uint64_t* __restrict__ hash, int64_t n, unsigned long long* words, int shift) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t h = hash[i];
+        atomicOr(words + (h >> shift), filter_bits(h));
+    }
 }
 
 // 16 packed bases (one 32-bit word, 2 bits each) -> four words of ASCII
@@ -484,13 +502,26 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
             const uint64_t h = hf ^ hr;
             const uint32_t hb = act ? home_bucket(h, a.nbuckets, a.home_shift) : 0u;
             const Bucket* tb = a.tbl;
+            uint32_t hbp = hb;
+            bool known_miss = false;
             if constexpr (PEER) {
-                if (act) tb = a.peer_tbl[(unsigned)(h >> (64 - a.owner_bits))];
+                const unsigned owner = (unsigned)(h >> (64 - a.owner_bits));
+                if (act) tb = a.peer_tbl[owner];
+                if (a.filt != nullptr && n_run < 32) {  // warp-uniform: this trip holds k-mers probed on their own
+                    if (act && lane >= n_run && owner != (unsigned)a.my_rank) {
+                        const unsigned long long w = __ldg(a.filt + (h >> a.filt_shift));
+                        known_miss = (w & filter_bits(h)) != filter_bits(h);
+                        if (known_miss) {  // nothing to fetch: like an idle lane
+                            tb = a.tbl;
+                            hbp = 0u;
+                        }
+                    }
+                }
             }
             Entry e0, e1;
-            load_bucket_nc(tb + hb, e0, e1);  // idle lanes probe bucket 0 of the local table (an L2 hit)
+            load_bucket_nc(tb + hbp, e0, e1);  // idle lanes probe bucket 0 of the local table (an L2 hit)
             uint32_t v = SGC_MISS, aux = AUX_NONE;
-            if (act) {
+            if (act && !known_miss) {
                 if (!bucket_match(e0, e1, h, v, aux)) {
                     v = SGC_MISS;
                     aux = AUX_NONE;

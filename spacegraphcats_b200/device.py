@@ -306,6 +306,11 @@ class DeviceTable:
         check(self._L.sgc_table_set_peers(self._h, n, ptrs, bounds, ctypes.c_void_p(int(useq_ptr)), int(useq_stride_words),
                                           ctypes.c_void_p(int(brk_ptr)), int(brk_stride_words)))
 
+    def set_filter(self, words_ptr, filt_bits, my_rank):
+        """Give this peer-probed table the replicated miss filter (sgc_table_set_filter); words_ptr = 0 turns it off."""
+        check(self._L.sgc_table_set_filter(self._h, ctypes.c_void_p(int(words_ptr)) if words_ptr else None, int(filt_bits),
+                                           int(my_rank)))
+
     def enable_side(self):
         """Allocate the unitig-ordered side array (8 B + 1 bit per k-mer); must precede insert_sequences."""
         check(self._L.sgc_table_enable_side(self._h))

@@ -335,7 +335,7 @@ class PeerBuffers:
 class PartitionedIndex:
     """k-mer -> unitig table hash-range partitioned over the ranks of a process group."""
 
-    def __init__(self, engine, group=None, p2p=False, peer_probe=False):
+    def __init__(self, engine, group=None, p2p=False, peer_probe=False, use_filter=True):
         import torch.distributed as dist
 
         self.engine = engine
@@ -345,6 +345,10 @@ class PartitionedIndex:
         # replicated unitig sequence store: no exchange buffers, no collective in the label path
         self.peer_probe = bool(peer_probe)
         self._store = None  # (useq_all, brk_all) tensors of the replicated store
+        # peer probing: a replicated miss filter (~2 bytes per hash of the whole cDBG on every GPU) answers most
+        # probes of k-mers that are in nobody's table from local HBM instead of over NVLink
+        self.use_filter = bool(use_filter)
+        self._filter = None
         self._peer_tables = []  # peer-mapped bucket arrays (to be closed)
         self._peers = None
         self._need_seen = 0
@@ -369,7 +373,7 @@ class PartitionedIndex:
             dist.barrier(group=self.group)  # nobody is still probing this rank's table
             for ptr, nbytes in self._peer_tables:
                 c._L.sgc_peer_unmap(c._h, ctypes.c_void_p(ptr), nbytes)
-            self._peer_tables, self._store = [], None
+            self._peer_tables, self._store, self._filter = [], None, None
             dist.barrier(group=self.group)  # nobody still maps our table
         if self.table is not None and hasattr(self.table, "close"):
             self.table.close()
@@ -429,6 +433,22 @@ class PartitionedIndex:
         n_table, = self._collective_flags(self.n_local)  # the same geometry everywhere: one nbuckets for every owner
         self.table = e.new_table(max(n_table, 1), self.bits, shared=True)
         marks = self.table.insert_triples(rh, ri, ra, bounds)
+        # the miss filter: ~16 bits per hash, one 64-bit word per hash chosen by its top bits -- the owner's hashes fill
+        # one contiguous slice of it, so the replicated filter is simply the all-gather of the owners' slices
+        tot = torch.tensor([self.n_local], dtype=torch.int64, device=c.device)
+        dist.all_reduce(tot, group=self.group)
+        fbits = max(self.bits + 4, int(max(int(tot.item()), 1) // 4).bit_length())
+        self._filter = None
+        if self.use_filter:
+            with e.stream():
+                filt = torch.zeros(1 << fbits, dtype=torch.int64, device=c.device)
+            check(L.sgc_filter_insert(c._h, c.ptr(rh), rh.numel(), c.ptr(filt), fbits))
+            with e.stream():
+                per = filt.numel() // R
+                mine = filt[self.rank * per:(self.rank + 1) * per].clone()
+                dist.all_gather_into_tensor(filt, mine, group=self.group)
+                del mine
+            self._filter = (filt, fbits)
         del rh, ri, ra
         # my shard of the store, then everybody's
         ustride = (max_bytes + 15) // 16 + 2 * STORE_PAD_WORDS
@@ -470,6 +490,8 @@ class PartitionedIndex:
                 ptrs.append(p.value)
         self._store = (useq_all, brk_all)
         self.table.set_peers(ptrs, bounds, useq_all.data_ptr() + 4 * STORE_PAD_WORDS, ustride, brk_all.data_ptr(), bstride)
+        if self._filter is not None:
+            self.table.set_filter(self._filter[0].data_ptr(), self._filter[1], self.rank)
         c.sync()
         dist.barrier(group=self.group)  # every table is complete before anybody probes it
         return self

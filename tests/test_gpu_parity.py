@@ -983,6 +983,27 @@ def test_peer_probed_partitioned_table_single_gpu(ctx, O):
             res = t.label_reads(rbuf, roff, k, packed=packed)
             assert np.array_equal(res["ids_off"], o_off) and np.array_equal(res["ids"], o_ids), packed
             assert (res["n_kmers"], res["n_hits"]) == (o_nk, o_nh)
+    # the replicated miss filter (k-mers probed on their own whose owner is another rank are looked up in it first):
+    # same labels with a filter of ~16 bits per hash, and with a deliberately tiny one (nearly every bit set: it
+    # filters nothing and must not change anything either)
+    for fbits in (max(3, (len(hs) // 4).bit_length()), 3):
+        with torch.cuda.stream(ctx.stream):
+            filt = torch.zeros(1 << fbits, dtype=torch.int64, device=ctx.device)
+        for o in range(R):
+            with torch.cuda.stream(ctx.stream):
+                hh = torch.cat([x[0] for x in per_owner[o]]).contiguous()
+            check(L.sgc_filter_insert(ctx._h, ctx.ptr(hh), hh.numel(), ctx.ptr(filt), fbits))
+        ctx.sync()
+        if fbits > 3:  # an owner's hashes fill its own quarter of the words, and the filter is not saturated
+            set_bits = int(sum(bin(int(x) & 0xFFFFFFFFFFFFFFFF).count("1") for x in filt.cpu().numpy().view(np.uint64)[:256]))
+            assert 0 < set_bits < 256 * 40
+        for me in (0, 3):
+            tables[me].set_filter(filt.data_ptr(), fbits, me)
+            for packed in (False, True):
+                res = tables[me].label_reads(rbuf, roff, k, packed=packed)
+                assert np.array_equal(res["ids_off"], o_off) and np.array_equal(res["ids"], o_ids), (fbits, me, packed)
+                assert (res["n_kmers"], res["n_hits"]) == (o_nk, o_nh)
+            tables[me].set_filter(0, 0, 0)
     for t in tables:
         t.close()
 
