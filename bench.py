@@ -303,6 +303,8 @@ def partitioned_arm(args, ctx, rank, world):
         ids = torch.arange(ulo, uhi, dtype=torch.int32, device=ctx.device)
     idx = PartitionedIndex(DeviceEngine(ctx), p2p=True, peer_probe=not args.part_exchange).build(useq, uoff, KSIZE, ids)
     ctx.sync()
+    del useq, uoff, ids
+    torch.cuda.empty_cache()
     log("[rank %d] partitioned build %.1fs: %d of %d hashes (%.2f GB) on this rank"
         % (rank, time.time() - t0, idx.n_local, total_kmers, idx.table.nbytes / 1e9))
     n_reads = args.part_reads
@@ -334,6 +336,7 @@ def partitioned_arm(args, ctx, rank, world):
     ok = None
     if not args.no_part_check:
         t1 = time.time()
+        torch.cuda.empty_cache()
         rep = DeviceTable(ctx, cdbg.total_unitig_kmers, load=1.3)
         rep.insert_sequences(cdbg.useq, cdbg.uoff, KSIZE)
         ref = rep.label_reads(*batches[check_batch], KSIZE, to_host=False)
@@ -361,14 +364,16 @@ def partitioned_arm(args, ctx, rank, world):
                      if args.part_exchange else
                      "none: the label kernel loads each home bucket (32 B) straight from its owner GPU's table over NVLink "
                      "(bucket arrays shared with cuMemCreate + POSIX fds); one k-mer in sixteen + the unsettled ones are "
-                     "probed, the rest is compared with the replicated unitig sequence store; no collective in the label path"),
+                     "probed, the rest is compared with the replicated unitig sequence store; singly probed k-mers owned by another "
+                     "GPU are first looked up in a replicated miss filter in local HBM (16 bits per hash; no false negatives); no "
+                     "collective in the label path"),
         "workload": "synthetic cDBG, %d unitig k-mers k=%d hash-range partitioned across %d B200 (BASELINE.json configs[4]), "
                     "150bp reads labelled by index_reads" % (total_kmers, KSIZE, world),
         "roofline": {"bound": "nvlink", "achieved": achieved, "peak": 770.0, "unit": "GB/s", "frac": achieved / 770.0,
                      "peak_source": "measured peer copy, B200_PROFILING.md",
                      "note": "achieved = SURVEY 8d's algorithmic figure, (R-1)/R x 12 B per k-mer per GPU and direction, over "
                              "the whole step (73 G k-mers/s per GPU at R=8).  What the link really carries here is one 32-byte "
-                             "load per PROBED k-mer (~0.25 per k-mer); a B200 serves 6.8 G random 32-byte loads/s from "
+                             "load per k-mer that is probed remotely (~0.1 per k-mer with the miss filter); a B200 serves 6.8 G random 32-byte loads/s from "
                              "another process's memory over NVLink (scripts/peer_probe.cu, profiles/r02_peer_probe_microbench.txt)"},
     }
 

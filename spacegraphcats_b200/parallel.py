@@ -493,6 +493,8 @@ class PartitionedIndex:
         if self._filter is not None:
             self.table.set_filter(self._filter[0].data_ptr(), self._filter[1], self.rank)
         c.sync()
+        del d_seq, d_off, d_ids, d_koff, d_stat, my_useq, my_brk
+        torch.cuda.empty_cache()  # the build's temporaries go back to the driver: the library allocates its own scratch
         dist.barrier(group=self.group)  # every table is complete before anybody probes it
         return self
 
