@@ -59,3 +59,21 @@ def scaled_minhash(seqs, ksize, scaled, seed=SOURMASH_SEED, ctx=None):
     h, _ = sourmash_hashes(seqs, ksize, seed, ctx)
     max_hash = (1 << 64) - 1 if scaled <= 1 else int(((1 << 64) - 1) / scaled)
     return np.unique(h[h <= np.uint64(max_hash)])
+
+
+def assign_unitig_ids(seqs, ksize, ctx=None):
+    """The deterministic unitig ids of cdbg/sort_bcalm_unitigs.py:56-128: BCALM's unitigs are renumbered in the
+    order of their ``min_hashval`` -- which the reference stores as TEXT, so ``ORDER BY min_hashval`` (:108-118) is
+    the lexicographic order of the decimal strings, not the numeric one.  The reference's UNIQUE index on the column
+    (:101) makes ties an error there; here they raise ``ValueError``.
+    -> (new_id int64[n]: id of input unitig i, min_hashval uint64[n])"""
+    mins = unitig_min_hashvals(seqs, ksize, ctx=ctx)
+    if len(seqs) and int(mins.max()) == (1 << 64) - 1 and any(len(s) < int(ksize) for s in seqs):
+        raise ValueError("a unitig shorter than k has no min_hashval")
+    keys = np.array([str(int(m)) for m in mins])
+    order = np.argsort(keys, kind="stable")
+    if len(keys) > 1 and (keys[order][1:] == keys[order][:-1]).any():
+        raise ValueError("UNIQUE constraint failed: sequences.min_hashval")
+    new_id = np.empty(len(seqs), np.int64)
+    new_id[order] = np.arange(len(seqs), dtype=np.int64)
+    return new_id, mins

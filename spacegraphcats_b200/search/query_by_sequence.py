@@ -1,8 +1,10 @@
 """Query a catlas with sequences: the hot-path half of the reference's
 ``spacegraphcats/search/query_by_sequence.py`` -- ``Query.__init__`` :153-185 (hash every record's
 k-mers into ONE set) and ``Query.execute`` :187-227 (per-unitig match counts -> per-dominator
-counts -> dominators -> neighbourhood).  Signature / CSV / contig retrieval output (``QueryOutput``
-:27-150, sourmash + sqlite) stays on the CPU reference and is out of scope here.
+counts -> dominators -> neighbourhood).  Of ``QueryOutput`` (:27-150) the arithmetic is here too -- the scaled
+MinHash of the query and of the retrieved contigs (sourmash's Murmur3, seed 42: cdbg/minhash.py) and their
+containment / similarity (:41-49) --; signature files, CSV writing and the sqlite contig store stay on the CPU
+reference.
 
 All records of a query are hashed in one batch; the set() is a device sort + adjacent-unique
 fused into the lookup/count kernel (``sgc_count_matches(distinct=1)``).
@@ -28,6 +30,32 @@ class QueryResult:
         self.query_sig = getattr(query, "sig", None)
         # here is where we go from the dominators to the actual cDBG nodes (:34)
         self.shadow = catlas.shadow(doms)
+
+    # ---- the two sourmash columns of results.csv (:41-49, :52-89) --------------------------------
+    def retrieve_contigs(self, sequences):
+        """``QueryOutput.retrieve_contigs`` given the neighbourhood's contig sequences (the reference reads them from
+        the sqlite contig store by ``self.shadow``): their scaled MinHash -- every k-mer hashed on the GPU -- plus
+        the bp / contig totals of the results row."""
+        from ..cdbg.minhash import scaled_minhash
+
+        seqs = [s for s in sequences]
+        self.total_seq = len(seqs)
+        self.total_bp = sum(len(s) for s in seqs)
+        scaled = getattr(self.query, "scaled", None) or 1
+        long_enough = [s for s in seqs if len(s) >= self.query.ksize]
+        self.contigs_hashes = scaled_minhash(long_enough, self.query.ksize, scaled) if long_enough else np.zeros(0, np.uint64)
+        return self.contigs_hashes
+
+    def containment(self):
+        """``query_sig.minhash.contained_by(contigs_minhash)`` (:44-45): |Q n C| / |Q| over the scaled sketches."""
+        q = self.query.minhash_hashes
+        return float(len(np.intersect1d(q, self.contigs_hashes, assume_unique=True)) / len(q)) if len(q) else 0.0
+
+    def similarity(self):
+        """``query_sig.minhash.similarity(contigs_minhash)`` (:47-48): Jaccard index of the scaled sketches."""
+        q, c = self.query.minhash_hashes, self.contigs_hashes
+        u = len(np.union1d(q, c))
+        return float(len(np.intersect1d(q, c, assume_unique=True)) / u) if u else 0.0
 
     def response_curve_lines(self):
         """The ``*.response.txt`` curve (search_utils.output_response_curve, search/search_utils.py:268-329):
@@ -101,6 +129,7 @@ def query_batch(query_files, ksize, catlas, kmer_idx, scaled=None, catlas_name=N
     for qf in query_files:
         q = Query.__new__(Query)
         q.filename, q.ksize, q.name, q.catlas_name, q.debug, q.sig = qf, int(ksize), None, catlas_name, debug, None
+        q.scaled, q._mh = scaled, None
         seqs = []
         for record in read_records(qf):
             if q.name is None:
@@ -136,7 +165,8 @@ class Query:
         self.name = None
         self.catlas_name = catlas_name
         self.debug = debug
-        self.sig = None  # sourmash signature: out of scope (CPU reference)
+        self.scaled = scaled
+        self.sig = None  # the sourmash signature OBJECT stays on the CPU reference; its hashes: minhash_hashes
 
         seqs = []
         for record in (records if records is not None else read_records(query_file)):
@@ -152,10 +182,23 @@ class Query:
             raise ValueError("Invalid base in read (query %s)" % query_file)
         self._d_hashes = d_hashes
         self._ctx = ctx
+        self._seqs = seqs
+        self._mh = None
         self._kmers = None
         self._n_distinct = None
         self.cdbg_match_counts = None
         self.catlas_match_counts = None
+
+    @property
+    def minhash_hashes(self):
+        """The hashes of the query's scaled MinHash (``self.mh`` of the reference, :164-176: sourmash
+        ``MinHash(0, ksize, scaled=scaled)`` + ``add_sequence`` of every record that is at least k long): sorted
+        distinct sourmash hashes below 2^64 / scaled, computed on the GPU (cdbg/minhash.py)."""
+        if self._mh is None:
+            from ..cdbg.minhash import scaled_minhash
+
+            self._mh = scaled_minhash(self._seqs, self.ksize, self.scaled or 1) if self._seqs else np.zeros(0, np.uint64)
+        return self._mh
 
     # the reference exposes a Python set of ints; build it lazily
     @property

@@ -513,6 +513,13 @@ def test_query_dory_head_matches_reference_outputs(O, dory, dory_index, dory_cat
     sm = out.summary()
     assert [str(sm[c]) for c in ("bp", "contigs", "ksize", "num_query_kmers", "best_containment", "cdbg_min_overhead",
                                  "catlas_min_overhead", "catlas_name")] == row[3:]
+    # ... and its two sourmash columns: scaled MinHash of the query vs that of the retrieved contigs (GPU hashing)
+    by_id = {int(r.name): r.sequence for r in dory[0]}
+    out.retrieve_contigs(by_id[c] for c in sorted(out.shadow))
+    assert [str(out.containment()), str(out.similarity()), str(out.total_bp), str(out.total_seq)] == row[1:5]
+    want_mh = sorted({h for r in O.read_records(golden_path("data", "dory-head.fa")) for h in O.minhash_sequence_py(r.sequence, 21)
+                      if h <= int((2**64 - 1) / 1000)})
+    assert q.minhash_hashes.tolist() == want_mh and len(want_mh) > 0
 
 
 def test_query_nomatch(dory_index, dory_catlas):
@@ -1063,6 +1070,20 @@ def test_unitig_min_hashvals_match_reference_sqlite_column(ctx, dory):
     recs = dory[0]
     got = unitig_min_hashvals([r.sequence for r in recs], 21)
     assert got.tolist() == [want[int(r.name)] for r in recs]
+
+
+def test_unitig_ids_follow_the_reference_remapping(ctx, dory):
+    """cdbg/sort_bcalm_unitigs.py:101-118: ids = rank of the unitig in the TEXT order of min_hashval.  The dory fixture's
+    unitigs, shuffled (BCALM's order is arbitrary), get back exactly the ids the reference gave them."""
+    from spacegraphcats_b200.cdbg.minhash import assign_unitig_ids
+
+    recs = dory[0]
+    perm = np.random.default_rng(3).permutation(len(recs))
+    new_id, mins = assign_unitig_ids([recs[i].sequence for i in perm], 21)
+    assert new_id.tolist() == [int(recs[i].name) for i in perm]
+    assert sorted(str(int(m)) for m in mins) != [str(v) for v in sorted(int(m) for m in mins)]  # TEXT order != numeric order
+    with pytest.raises(ValueError):
+        assign_unitig_ids([recs[0].sequence, recs[0].sequence], 21)
 
 
 @pytest.mark.parametrize("k", [21, 31, 12, 33])
