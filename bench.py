@@ -254,8 +254,8 @@ def workload_config(args, cpu=False):
         "read_format": "ASCII (1 byte per base + int64 offsets)" if args.ascii else
                        "2-bit packed, 40 bytes per 150-bp read (the host feeder's output; expanded to ASCII in the kernel)",
         "label_kernel": "per-k-mer probes (SGC_NO_SIDE)" if os.environ.get("SGC_NO_SIDE") else
-                        "labelseq: one hashed+probed anchor per 16 k-mers, followers settled by comparing the read's 2-bit bases with the table's unitig sequence store; unsettled k-mers hashed+probed one per lane",
-        "l2": "inputs (0.8 GB packed reads/step, 27 GB table + 0.3 GB unitig sequence store) far larger than the 126 MB L2; no flush needed",
+                        "labelseq: one hashed+probed anchor per 16 k-mers, followers settled by comparing the read's 2-bit bases with the table's unitig sequence store; k-mers past a unitig end re-anchored as a run, k-mers overlapping a mismatch hashed+probed one per lane",
+        "l2": "inputs (0.67 GB packed reads/step, 27 GB table + 0.3 GB unitig sequence store) far larger than the 126 MB L2; no flush needed",
     }
 
 
@@ -513,9 +513,11 @@ def query_arm(args, ctx, table, cdbg, rank, world):
                 "api": "DeviceTable.count_matches_batch (what search.query_by_sequence.query_batch calls)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "bytes_per_kmer": bytes_per_kmer,
-                     "note": "whole batch call (hash kernel + one 4-pass radix sort of (hash, query) + the lookup/count "
-                             "pass) against sequence-in + one 32-byte sector + 4 B id per k-mer; the sort alone moves "
-                             "~100 B per k-mer, so this path is bound by its own streaming traffic, not by table probes"},
+                     "note": "whole batch call against sequence-in + one 32-byte sector + 4 B id per k-mer.  The label "
+                             "kernel's runs give per-query INTERVALS of unitig-store positions (16 B per settled run, not "
+                             "8 B per k-mer) and the hashes of the missing k-mers; distinct matches = union of the "
+                             "intervals (sort, running max, reduce by (query, unitig)), missing k-mers de-duplicated by one "
+                             "32-bit-key sort.  Kernel ~2.2 ms of the ~6 ms step; the rest is the two sorts and the plan"},
     }
     if not args.no_cpu and world == 1:
         # CPU arm of the query half: the oracle's batched Query restatement (C, one query per thread) on a
@@ -818,8 +820,8 @@ def main():
                 "id per k-mer = 37.25 B) x k-mers per launch / measured kernel time; frac_strict counts only what this "
                 "launch needs (packed read bytes + one sector + the labels written).  HBM on this part serves 36-46 G "
                 "random lines/s and moves 128 bytes per access (scripts/sector_probe*.cu, profiles/); the kernel hashes "
-                "and probes one k-mer in sixteen plus the k-mers it cannot settle against the unitig sequence store "
-                "(sequencing errors, unitig ends): ~0.26 table lines per k-mer",
+                "and probes one k-mer in sixteen, the first k-mer past a unitig end, and the k-mers that overlap a "
+                "sequencing error; everything else is settled against the unitig sequence store: ~0.2 table lines per k-mer",
     }
 
     # ---- CPU baseline on the host cores ---------------------------------------------------
