@@ -132,6 +132,19 @@ class Context:
     def ptr(t):
         return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
+    def hand_over(self, *tensors):
+        """Device tensors produced on the context's stream are about to be returned to the caller: order the caller's
+        current stream after the work that fills them and keep the allocator from recycling them early (ADVICE r1:
+        the context stream does not synchronise with the default stream).  -> the tensors"""
+        torch = _torch()
+        cur = torch.cuda.current_stream(self.device)
+        if cur != self.stream:
+            cur.wait_stream(self.stream)
+            for t in tensors:
+                if t is not None and hasattr(t, "record_stream"):
+                    t.record_stream(cur)
+        return tensors[0] if len(tensors) == 1 else tensors
+
     def sync(self):
         check(self._L.sgc_ctx_sync(self._h))
 
@@ -361,7 +374,7 @@ class DeviceTable:
         n = ctypes.c_int64(0)
         check(self._L.sgc_table_export(self._h, c.ptr(d_h), c.ptr(d_v), live, ctypes.byref(n)))
         if not to_host:
-            return d_h[: n.value], d_v[: n.value]
+            return c.hand_over(d_h[: n.value], d_v[: n.value])
         return c.to_host(d_h[: n.value], np.uint64), c.to_host(d_v[: n.value], np.uint32)
 
     # ---- K3 --------------------------------------------------------------
@@ -372,7 +385,7 @@ class DeviceTable:
         d_o = c.empty(d_h.numel(), torch.int32)
         check(self._L.sgc_lookup(self._h, c.ptr(d_h), d_h.numel(), c.ptr(d_o)))
         if not to_host:
-            return d_o
+            return c.hand_over(d_o)
         return c.to_host(d_o, np.uint32)
 
     # ---- K5 --------------------------------------------------------------
@@ -455,6 +468,7 @@ class DeviceTable:
             out["count_by_id"] = c.to_host(d_cnt, np.uint32) if d_cnt is not None else None
             out["status"] = c.to_host(d_stat)
         else:
+            c.hand_over(d_ids, d_koff, d_cnt, d_stat)
             out.update(kmer_ids=d_ids, kmer_off=d_koff, count_by_id=d_cnt, status=d_stat)
         return out
 
@@ -498,6 +512,7 @@ class DeviceTable:
         if to_host:
             out.update(ids_off=c.to_host(d_ioff), ids=c.to_host(d_ids, np.uint32), status=c.to_host(d_stat))
         else:
+            c.hand_over(d_ioff, d_ids, d_stat)
             out.update(ids_off=d_ioff, ids=d_ids, status=d_stat)
         return out
 
@@ -532,6 +547,7 @@ class DeviceTable:
         if to_host:
             out.update(ids_off=c.to_host(d_ioff), ids=c.to_host(d_ids, np.uint32))
         else:
+            c.hand_over(d_ioff, d_ids)
             out.update(ids_off=d_ioff, ids=d_ids)
         return out
 
