@@ -139,6 +139,7 @@ struct sgc_table {
     int64_t peer_ustride = 0, peer_bstride = 0;
     // pending label call
     bool label_pending = false;
+    bool label_counted = false;  // the label kernel already counted the candidates per sequence into label_ids_off
     int64_t label_nseq = 0;
     int64_t* label_ids_off = nullptr;
     uint32_t* label_ids_out = nullptr;
@@ -334,7 +335,7 @@ int pairs_to_csr_sorted(sgc_ctx* c, int64_t n, int64_t nseq, int64_t* d_ids_off,
 // Candidate keys in pairs_a[0..n) -> CSR of distinct ascending ids per sequence.  Synchronises.
 // Bucketed path (csr2_* kernels) when every sequence has few candidates, else the radix-sort path.
 int pairs_to_csr(sgc_ctx* c, int64_t n, int64_t nseq, int64_t* d_ids_off, uint32_t* d_ids_out, int64_t ids_cap,
-                 int64_t* h_n_labels) {
+                 int64_t* h_n_labels, bool counted = false) {  // counted: d_ids_off[s] already holds sequence s's candidates
     if (n <= 0 || nseq <= 0 || getenv("SGC_CSR_SORT"))
         return pairs_to_csr_sorted(c, n, nseq, d_ids_off, d_ids_out, ids_cap, h_n_labels);
     const int cap = c->num_sms * 16;
@@ -344,9 +345,11 @@ int pairs_to_csr(sgc_ctx* c, int64_t n, int64_t nseq, int64_t* d_ids_off, uint32
     uint32_t* run_ids = (uint32_t*)c->pairs_b.p;
     long long* start = (long long*)c->tmp_idx.p;
     unsigned long long* cnt = (unsigned long long*)d_ids_off;  // the caller's offsets double as the counters
-    CU(cudaMemsetAsync(d_ids_off, 0, (size_t)(nseq + 1) * 8, c->stream));
     CU(cudaMemsetAsync(&c->d_scal->csr_big, 0, sizeof(unsigned int), c->stream));
-    csr2_count_kernel<<<grid_for(n, 256, cap), 256, 0, c->stream>>>(A, n, cnt);
+    if (!counted) {
+        CU(cudaMemsetAsync(d_ids_off, 0, (size_t)(nseq + 1) * 8, c->stream));
+        csr2_count_kernel<<<grid_for(n, 256, cap), 256, 0, c->stream>>>(A, n, cnt);
+    }
     size_t tb = 0;
     CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, (long long*)cnt, start, nseq + 1, c->stream));
     TRY(ensure(c, c->cub_tmp, tb));
@@ -958,6 +961,12 @@ int query_count_batch_store(sgc_table* t, const uint8_t* d_seq, const int64_t* d
     *fallback = false;
     const int qbits = std::max(1, bits_for(std::max(n_queries, 1)));
     if (qbits > 31) return fail(SGC_ERR_ARG, "at most 2^31 queries per batch");
+    // the missing k-mers' sort key: query | top bits of the hash, 24 bits (3 radix passes) when that leaves the hash
+    // at least 12 bits, else 32; the runs of equal keys only have to stay short
+    const int mkbits = qbits <= 12 ? 24 : 32;
+    // the intervals' sort key: query << pbits | store position (pbits = bits of the store's size)
+    int pbits = 1;
+    while (pbits < 32 && ((int64_t)1 << pbits) <= t->store_fill + 64) pbits++;
     // every warp of the grid may leave one chunk partly used (it is filled with copies, sgc_labelseq.cuh)
     const unsigned long long slack = (unsigned long long)c->num_sms * SGC_LS_MIN_CTAS * WPBS * QCHUNK + 4096;
     unsigned long long iv_cap = (unsigned long long)(n / 4) + slack, ms_cap = (unsigned long long)(n / 4) + slack;
@@ -985,7 +994,8 @@ int query_count_batch_store(sgc_table* t, const uint8_t* d_seq, const int64_t* d
         a.miss_hash = (unsigned long long*)c->tmp_hash.p;
         a.miss_q = (uint32_t*)c->q_mapc.p;
         a.miss_cap = ms_cap;
-        a.miss_hbits = 32 - qbits;
+        a.miss_hbits = mkbits - qbits;
+        a.iv_pbits = pbits;
         TRY(launch_labelseq_query(c, a));
         TRY(fetch_scalars(c));
         if (c->h_scal->err & ERR_QUERY_NOPOS) {
@@ -1008,14 +1018,14 @@ int query_count_batch_store(sgc_table* t, const uint8_t* d_seq, const int64_t* d
         uint32_t *cnt = (uint32_t*)c->q_id.p, *cnt2 = (uint32_t*)c->q_id2.p;
         const int end_bit = std::min(64, 32 + qbits);
         // (A, B) -> sorted (C, D)
-        CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, A, C, B, D, n_iv, 0, end_bit, c->stream));
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, A, C, B, D, n_iv, 0, pbits + qbits, c->stream));
         TRY(ensure(c, c->cub_tmp, tb));
-        CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, A, C, B, D, n_iv, 0, end_bit, c->stream));
+        CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, A, C, B, D, n_iv, 0, pbits + qbits, c->stream));
         iv_end_kernel<<<grid_for(n_iv, 256, c->num_sms * 8), 256, 0, c->stream>>>(C, D, n_iv, A);
         CU(cub::DeviceScan::ExclusiveScan(nullptr, tb, A, B, MaxU64(), 0ULL, n_iv, c->stream));
         TRY(ensure(c, c->cub_tmp, tb));
         CU(cub::DeviceScan::ExclusiveScan(c->cub_tmp.p, tb, A, B, MaxU64(), 0ULL, n_iv, c->stream));
-        iv_union_kernel<<<grid_for(n_iv, 256, c->num_sms * 8), 256, 0, c->stream>>>(C, D, B, n_iv, A, cnt);
+        iv_union_kernel<<<grid_for(n_iv, 256, c->num_sms * 8), 256, 0, c->stream>>>(C, D, B, n_iv, pbits, A, cnt);
         c->launches += 2;
         // runs of equal (query, unitig): A / cnt -> C / cnt2
         long long* d_runs = &c->d_scal->n_unique;
@@ -1044,12 +1054,12 @@ int query_count_batch_store(sgc_table* t, const uint8_t* d_seq, const int64_t* d
     if (n_ms > 0) {
         uint64_t *H = (uint64_t*)c->tmp_hash.p, *H2 = (uint64_t*)c->q_hash2.p;
         uint32_t *Q = (uint32_t*)c->q_mapc.p, *Q2 = (uint32_t*)c->tmp_id.p;
-        CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, Q, Q2, H, H2, n_ms, 0, 32, c->stream));
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, Q, Q2, H, H2, n_ms, 0, mkbits, c->stream));
         TRY(ensure(c, c->cub_tmp, tb));
-        CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, Q, Q2, H, H2, n_ms, 0, 32, c->stream));
+        CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, Q, Q2, H, H2, n_ms, 0, mkbits, c->stream));
         const size_t hist_bytes = n_queries <= QHIST_MAX ? (size_t)n_queries * 4 : 0;
         miss_distinct_kernel<<<grid_for(n_ms, 256, c->num_sms * 8), 256, hist_bytes, c->stream>>>(
-            Q2, H2, n_ms, 32 - qbits, (unsigned long long*)d_q_distinct, n_queries);
+            Q2, H2, n_ms, mkbits - qbits, (unsigned long long*)d_q_distinct, n_queries);
         c->launches++;
     }
     CU(cudaGetLastError());
@@ -1319,6 +1329,7 @@ int labelseq_misses(sgc_ctx* c, const Plan& p, int64_t nseq) {
 void label_pending(sgc_table* t, int64_t nseq, int64_t* d_ids_off, uint32_t* d_ids_out, int64_t ids_cap,
                    unsigned long long pairs_cap) {
     t->label_pending = true;
+    t->label_counted = false;
     t->label_nseq = nseq;
     t->label_ids_off = d_ids_off;
     t->label_ids_out = d_ids_out;
@@ -1341,6 +1352,18 @@ int make_packed_plan(sgc_ctx* c, const int32_t* d_len, int uniform_len, int64_t 
     const int64_t max_segs = nseq + packed_bytes * 4 / seg_k + 1;
     TRY(ensure(c, c->seg_map, (size_t)max_segs * sizeof(SegDesc)));
     CU(cudaMemsetAsync(&c->d_scal->bad_offsets, 0, sizeof(int), c->stream));
+    if (!d_len && !want_base_off) {  // records of one length: closed form, one kernel
+        packed_uniform_plan_kernel<<<grid_for((int64_t)n1, 256, c->num_sms * 32), 256, 0, c->stream>>>(
+            uniform_len, nseq, k, seg_k, packed_bytes, (int64_t*)c->kmer_off.p, (int64_t*)c->seg_first.p,
+            (int64_t*)c->unit_off.p, (SegDesc*)c->seg_map.p, c->d_scal);
+        c->launches++;
+        CU(cudaGetLastError());
+        plan->kmer_off = (int64_t*)c->kmer_off.p;
+        plan->seg_first = (int64_t*)c->seg_first.p;
+        plan->segdesc = (const SegDesc*)c->seg_map.p;
+        plan->nsegs_p = (int64_t*)c->seg_first.p + nseq;
+        return SGC_OK;
+    }
     packed_count_kernel<<<grid_for((int64_t)n1, 256, 1 << 30), 256, 0, c->stream>>>(
         d_len, uniform_len, nseq, k, seg_k, (int64_t*)c->nk.p, (int64_t*)c->nseg.p, (int64_t*)c->units.p, c->d_scal);
     c->launches++;
@@ -1389,10 +1412,14 @@ int sgc_label_reads_launch(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes
     TRY(make_plan(c, d_off, nseq, seq_bytes, k, nullptr, &p, side ? SEG_KS : SEG_K));
     unsigned long long pairs_cap = 0;
     TRY(label_common_prologue(t, nseq, ids_cap, &pairs_cap));
+    bool counted = false;
     if (nseq > 0) {
         if (side) {
             LabelSeqArgs a;
             labelseq_args(a, t, d_seq, p, k, d_status, pairs_cap);
+            a.cnt = (unsigned long long*)d_ids_off;  // the caller's offsets double as the counters (pairs_to_csr)
+            CU(cudaMemsetAsync(d_ids_off, 0, (size_t)(nseq + 1) * 8, c->stream));
+            counted = true;
             TRY(launch_labelseq<false>(c, a));
             TRY(labelseq_misses(c, p, nseq));
         } else {
@@ -1405,6 +1432,7 @@ int sgc_label_reads_launch(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes
     }
     CU(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(Scalars), cudaMemcpyDeviceToHost, c->stream));
     label_pending(t, nseq, d_ids_off, d_ids_out, ids_cap, pairs_cap);
+    t->label_counted = counted;
     return SGC_OK;
 }
 
@@ -1437,10 +1465,14 @@ int sgc_label_reads_packed_launch(sgc_table* t, const uint8_t* d_packed, int64_t
     TRY(make_packed_plan(c, d_len, uniform_len, nseq, packed_bytes, k, SEG_KS, !side, &p));
     unsigned long long pairs_cap = 0;
     TRY(label_common_prologue(t, nseq, ids_cap, &pairs_cap));
+    bool counted = false;
     if (nseq > 0) {
         if (side) {
             LabelSeqArgs a;
             labelseq_args(a, t, d_packed, p, k, nullptr, pairs_cap);
+            a.cnt = (unsigned long long*)d_ids_off;
+            CU(cudaMemsetAsync(d_ids_off, 0, (size_t)(nseq + 1) * 8, c->stream));
+            counted = true;
             TRY(launch_labelseq<true>(c, a));
             TRY(labelseq_misses(c, p, nseq));
         } else {
@@ -1461,6 +1493,7 @@ int sgc_label_reads_packed_launch(sgc_table* t, const uint8_t* d_packed, int64_t
     }
     CU(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(Scalars), cudaMemcpyDeviceToHost, c->stream));
     label_pending(t, nseq, d_ids_off, d_ids_out, ids_cap, pairs_cap);
+    t->label_counted = counted;
     return SGC_OK;
 }
 
@@ -1523,7 +1556,7 @@ int sgc_label_reads_finish(sgc_table* t, int64_t* h_n_kmers, int64_t* h_n_hits, 
                     n_pairs, n_pairs);
     }
     return pairs_to_csr(c, (int64_t)n_pairs, t->label_nseq, t->label_ids_off, t->label_ids_out, t->label_ids_cap,
-                        h_n_labels);
+                        h_n_labels, t->label_counted);
 }
 
 int sgc_label_reads(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off, int64_t nseq, int k,

@@ -488,24 +488,25 @@ __global__ void __launch_bounds__(256) query_count_kernel(const Bucket* tbl, uin
 }
 
 // ---- the store-position form of the batched query (labelseq_kernel<.., QUERY>) ----
-// intervals sorted by key = query << 32 | first position; val = length << 32 | unitig id.
-// e[i] = query << 32 | end (exclusive) -- a running maximum of e over the sorted intervals is, in its high word, the
-// query of the latest interval and, in its low word, how far that query's earlier intervals reach.
+// intervals sorted by key = query << pbits | first position (pbits = bits of the store's size); val = length << 32 |
+// unitig id.  e[i] = query << pbits | end (exclusive) -- a running maximum of e over the sorted intervals is, above
+// pbits, the query of the latest interval and, below, how far that query's earlier intervals reach.
 __global__ void iv_end_kernel(const unsigned long long* __restrict__ key, const unsigned long long* __restrict__ val, int64_t n,
                               unsigned long long* __restrict__ e) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        e[i] = key[i] + (val[i] >> 32);  // positions are 30 bits: the sum stays inside the low word
+        e[i] = key[i] + (val[i] >> 32);  // (the store is padded: an end never carries into the query bits)
 }
 // the part of interval i that no earlier interval of its query covers -> (query << 32 | unitig, length)
 __global__ void iv_union_kernel(const unsigned long long* __restrict__ key, const unsigned long long* __restrict__ val,
-                                const unsigned long long* __restrict__ pmax, int64_t n, unsigned long long* __restrict__ key2,
-                                uint32_t* __restrict__ cnt) {
+                                const unsigned long long* __restrict__ pmax, int64_t n, int pbits,
+                                unsigned long long* __restrict__ key2, uint32_t* __restrict__ cnt) {
+    const unsigned long long pmask = (1ULL << pbits) - 1ULL;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const unsigned long long k = key[i], v = val[i], pm = pmax[i];
-        const uint32_t start = (uint32_t)k, end = start + (uint32_t)(v >> 32);
+        const uint32_t start = (uint32_t)(k & pmask), end = start + (uint32_t)(v >> 32);
         uint32_t from = start;
-        if ((pm >> 32) == (k >> 32) && (uint32_t)pm > from) from = (uint32_t)pm;
-        key2[i] = (k & 0xFFFFFFFF00000000ULL) | (v & 0xFFFFFFFFULL);
+        if ((pm >> pbits) == (k >> pbits) && (uint32_t)(pm & pmask) > from) from = (uint32_t)(pm & pmask);
+        key2[i] = ((k >> pbits) << 32) | (v & 0xFFFFFFFFULL);
         cnt[i] = end > from ? end - from : 0u;
     }
 }
@@ -767,6 +768,34 @@ __global__ void packed_expand_kernel(const int64_t* __restrict__ seg_first, cons
         d.nk = unit_off[s + 1] * 4 > packed_bytes ? 0 : (int)(nkseq - q0 < seg_k ? nkseq - q0 : seg_k);
         d.pad[0] = d.pad[1] = 0;
         segdesc[j] = d;
+    }
+}
+
+// records of ONE length: the whole plan in closed form, one pass (no scans)
+__global__ void packed_uniform_plan_kernel(int uniform_len, int64_t nseq, int k, int seg_k, int64_t packed_bytes,
+                                           int64_t* __restrict__ kmer_off, int64_t* __restrict__ seg_first,
+                                           int64_t* __restrict__ unit_off, SegDesc* __restrict__ segdesc, Scalars* scal) {
+    const int64_t nk = uniform_len - k + 1 > 0 ? uniform_len - k + 1 : 0, nseg = (nk + seg_k - 1) / seg_k;
+    const int64_t units = ((int64_t)uniform_len + 15) / 16;
+    const bool bad = nseq * units * 4 > packed_bytes;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s <= nseq; s += (int64_t)gridDim.x * blockDim.x) {
+        kmer_off[s] = s * nk;
+        seg_first[s] = s * nseg;
+        unit_off[s] = s * units;
+        if (s == nseq) {
+            if (bad) atomicOr(&scal->bad_offsets, 1);
+            break;
+        }
+        for (int64_t j = 0; j < nseg; j++) {
+            const int64_t q0 = j * seg_k;
+            SegDesc d;
+            d.start = s * units * 4 + q0 / 4;
+            d.kout = s * nk + q0;
+            d.seq = (unsigned int)s;
+            d.nk = bad ? 0 : (int)(nk - q0 < seg_k ? nk - q0 : seg_k);
+            d.pad[0] = d.pad[1] = 0;
+            segdesc[s * nseg + j] = d;
+        }
     }
 }
 

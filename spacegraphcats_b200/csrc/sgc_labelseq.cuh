@@ -93,6 +93,7 @@ struct LabelSeqArgs {
     const uint32_t* brk;      // bit BRK_PAD + p = break before position p
     unsigned long long* pairs;
     unsigned long long pairs_cap;
+    unsigned long long* cnt;  // nullable: per-sequence candidate counters (zeroed by the caller), bumped as keys are flushed
     // PEER = true: the table is hash-range partitioned over n_shards GPUs (owner = top owner_bits bits of the hash)
     // and probed where it lies, over NVLink peer memory; the store is replicated, one shard per rank (ustride /
     // bstride words apart), and the shard of a hit follows from its unitig id (ids are dealt out in ranges)
@@ -108,7 +109,7 @@ struct LabelSeqArgs {
     int filt_shift;   // 64 - filt_bits
     int my_rank;
     // QUERY = true (sgc_query_count_batch): instead of per-read labels the kernel writes, per settled run, the
-    // INTERVAL of store positions its k-mers lie at -- iv_key = query << 32 | first position, iv_val = length << 32 |
+    // INTERVAL of store positions its k-mers lie at -- iv_key = query << iv_pbits | first position, iv_val = length << 32 |
     // unitig id; scal->n_export counts them -- and every k-mer that is not in the table as (hash, sort key) --
     // scal->n_live counts those.  Two store positions never hold the same hash under a clear break bit and the
     // position a probe returns is the one the table keeps for that hash, so the number of DISTINCT matching hashes
@@ -121,6 +122,7 @@ struct LabelSeqArgs {
     uint32_t* miss_q;          // the miss's sort key: query << miss_hbits | top miss_hbits bits of the hash
     unsigned long long miss_cap;
     int miss_hbits;
+    int iv_pbits;              // iv_key = query << iv_pbits | first position
 };
 constexpr unsigned QCHUNK = 1024;     // records a warp reserves at a time (a trip writes at most 96)
 constexpr int ERR_QUERY_CAP = 4;      // Scalars::err bit: iv_cap / miss_cap too small
@@ -251,7 +253,8 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
     unsigned have_last = 0;
 
     auto flush_pairs = [&]() {  // cold: out of line
-        flush_pairs_out(a.scal, a.pairs, a.pairs_cap, wt.pairs, pair_fill, lane);
+        if (a.cnt) flush_pairs_count_out(a.scal, a.pairs, a.pairs_cap, wt.pairs, pair_fill, lane, a.cnt);
+        else flush_pairs_out(a.scal, a.pairs, a.pairs_cap, wt.pairs, pair_fill, lane);
         pair_fill = 0;
     };
     // one candidate (sequence, id) key per lane at most; the order of the keys is irrelevant (they are
@@ -741,7 +744,7 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                         const int len = __ffs((int)~(m >> i0)) - 1;   // set bits from i0 upwards
                         const int i1 = i0 + len - 1;
                         const int first = q_along ? (int)gp + (i0 - q_ao) : (int)gp - (i1 - q_ao);
-                        rk = ((unsigned long long)qid << 32) | (unsigned)first;
+                        rk = ((unsigned long long)qid << a.iv_pbits) | (unsigned)first;
                         rv = ((unsigned long long)len << 32) | v;
                         return m & ~(((1u << len) - 1u) << i0);
                     };

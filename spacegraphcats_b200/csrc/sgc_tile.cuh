@@ -129,6 +129,22 @@ __device__ __noinline__ void flush_pairs_out(Scalars* scal, unsigned long long* 
     __syncwarp();
 }
 
+// the same, and every key counted under its sequence (the first step of the label tail, done while the keys are at hand)
+__device__ __noinline__ void flush_pairs_count_out(Scalars* scal, unsigned long long* pairs, unsigned long long cap,
+                                                   const unsigned long long* staged, unsigned n, int lane,
+                                                   unsigned long long* cnt) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&scal->pair_count, (unsigned long long)n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (unsigned j = lane; j < n; j += 32)
+        if (base + j < cap) {
+            const unsigned long long key = staged[j];
+            pairs[base + j] = key;
+            atomicAdd(&cnt[key >> 32], 1ULL);
+        }
+    __syncwarp();
+}
+
 template <int K, int MODE>
 __global__ void __launch_bounds__(NT, (MODE == MODE_LABEL || MODE == MODE_LOOKUP) ? SGC_PROBE_MIN_CTAS : 1) tile_kernel(const TileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
