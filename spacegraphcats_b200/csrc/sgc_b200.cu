@@ -970,6 +970,7 @@ int query_count_batch_store(sgc_table* t, const uint8_t* d_seq, const int64_t* d
     // every warp of the grid may leave one chunk partly used (it is filled with copies, sgc_labelseq.cuh)
     const unsigned long long slack = (unsigned long long)c->num_sms * SGC_LS_MIN_CTAS * WPBS * QCHUNK + 4096;
     unsigned long long iv_cap = (unsigned long long)(n / 4) + slack, ms_cap = (unsigned long long)(n / 4) + slack;
+    if (getenv("SGC_QUERY_SMALL_CAPS")) iv_cap = ms_cap = 2048;  // test knob: force the overflow + retry path
     int64_t n_iv = 0, n_ms = 0;
     for (int attempt = 0;; attempt++) {
         TRY(ensure(c, c->iv_a, (size_t)iv_cap * 8));

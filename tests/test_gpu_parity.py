@@ -1188,6 +1188,61 @@ def test_count_matches_batch_sets_per_query(ctx, O):
     assert table.count_matches_batch([], 21) == []
 
 
+def test_count_matches_batch_many_queries_retry_and_fallback(ctx, O, monkeypatch):
+    """The store-position form of sgc_query_count_batch off its beaten path: thousands of queries (32-bit miss keys,
+    per-query counters in global memory), record buffers that overflow and are re-sized, and a table that also holds
+    hashes without a store position (filled hash by hash), which must fall back to the hash-sort form."""
+    from spacegraphcats_b200.cdbg.hashing import GpuKmerTable
+    from spacegraphcats_b200.device import pack_sequences
+
+    rng = np.random.default_rng(91)
+    k = 31
+    lut = np.frombuffer(b"ACGT", np.uint8)
+    g = lut[rng.integers(0, 4, 400_000)].tobytes().decode()
+    useqs = [g[a : a + 150 + k - 1] for a in range(0, len(g) - 200, 150)]
+    ubuf, uoff = pack_sequences(useqs)
+    table = GpuKmerTable.from_sequences(ubuf, uoff, k, ctx=ctx)
+    otab, _, _ = O.build_mphf(k, lambda: iter(O.Record(str(i), s) for i, s in enumerate(useqs)))
+
+    def check(queries, tab=table, ot=otab):
+        got = tab.count_matches_batch(queries, k)
+        assert len(got) == len(queries)
+        for qi, (q, (counts, n_distinct)) in enumerate(zip(queries, got)):
+            okm = O.query_kmers([O.Record("r", s) for s in q], k)
+            assert n_distinct == len(okm), qi
+            assert counts == O.count_cdbg_matches(ot, okm), qi
+
+    def mutate(s):
+        b = bytearray(s.encode())
+        for p in rng.integers(0, len(b), max(1, len(b) // 150)):
+            b[p] = ord("ACGT"[(("ACGT".index(chr(b[p]))) + 1) % 4])
+        return b.decode()
+
+    for nq in (5000, 9000):  # > 4096: 32-bit keys for the missing k-mers; > 8192: no shared-memory counters
+        starts = rng.integers(0, len(g) - 400, nq)
+        check([[mutate(g[a : a + int(n)])] for a, n in zip(starts, rng.integers(k, 400, nq))])
+    few = [[mutate(g[a : a + 30_000]), g[a + 100 : a + 900]] for a in rng.integers(0, len(g) - 31_000, 6)]
+    monkeypatch.setenv("SGC_QUERY_SMALL_CAPS", "1")
+    check(few)  # the first attempt overflows its interval and miss buffers
+    monkeypatch.delenv("SGC_QUERY_SMALL_CAPS")
+    # a hash set by hand has no place in the sequence store: the batch falls back to sorting hashes
+    extra = "".join(rng.choice(list("ACGT"), 60))
+    eh = O.hash_sequence(extra[:k], k)[0]
+    table[eh] = 7
+    o2 = dict(zip(otab.mphf_to_hash.tolist(), otab.mphf_to_value.tolist()))
+    o2[eh] = 7
+    got = table.count_matches_batch(few + [[extra]], k)
+    okm = O.query_kmers([O.Record("r", extra)], k)
+    want = {}
+    for h in okm:
+        if h in o2:
+            want[o2[h]] = want.get(o2[h], 0) + 1
+    assert got[-1] == (want, len(okm)) and want.get(7) == 1
+    for q, (counts, n_distinct) in zip(few, got):
+        okm = O.query_kmers([O.Record("r", s) for s in q], k)
+        assert n_distinct == len(okm) and counts == O.count_cdbg_matches(otab, okm)
+
+
 # ---------------------------------------------------------------- the reference-side binding (INTEGRATION.md)
 def test_reference_side_binding_drives_the_reference_loops(tmp_path, O, dory):
     """tests/refshim/sgc_b200_binding.py -- the raw ctypes stand-in for ``khmer`` / ``bbhash_table`` a reference
