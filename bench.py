@@ -743,7 +743,8 @@ def main():
         e2e = {
             "value": world * step_kmers * args.steps / dt, "unit": "k-mers/s",
             "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int((n_reads + 1) * 8 + tot_labels // args.steps * 4),
+            # the CSR offsets return as one byte per read (rebuilt on the host by sgc_counts8_to_offsets) + the ids
+            "d2h_bytes_per_step": int((n_reads + 1) + tot_labels // args.steps * 4),
             "ms_per_step": dt / args.steps * 1e3,
             "api": "GpuKmerTable.label_reads_stream (pinned double buffers, H2D / kernels / D2H of consecutive batches "
                    "overlapped; the loop index_reads.main runs)",

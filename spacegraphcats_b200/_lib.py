@@ -63,6 +63,8 @@ PROTOTYPES = {
     "sgc_label_reads_launch": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _i64, _vp]),
     "sgc_label_reads_finish": (_i32, [_vp, _pi64, _pi64, _pi64]),
     "sgc_packed_bytes": (_i64, [_vp, _i32, _i64]),
+    "sgc_offsets_to_counts8": (_i32, [_vp, _vp, _i64, _vp]),
+    "sgc_counts8_to_offsets": (_i32, [_vp, _i64, _i32, _vp]),
     "sgc_label_reads_packed_launch": (_i32, [_vp, _vp, _i64, _vp, _i32, _i64, _i32, _vp, _vp, _i64]),
     "sgc_label_reads_packed": (_i32, [_vp, _vp, _i64, _vp, _i32, _i64, _i32, _vp, _vp, _i64, _pi64, _pi64, _pi64]),
     "sgc_pack_reads_device": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _pi64]),

@@ -1567,6 +1567,18 @@ int sgc_label_reads(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes, const
     return sgc_label_reads_finish(t, h_n_kmers, h_n_hits, h_n_labels);
 }
 
+int sgc_offsets_to_counts8(sgc_ctx* c, const int64_t* d_off, int64_t n, uint8_t* d_counts) {
+    if (!c || n < 0 || !d_counts || (n > 0 && !d_off)) return fail(SGC_ERR_ARG, "bad argument");
+    TRY(set_device(c));
+    CU(cudaMemsetAsync(d_counts + n, 0, 1, c->stream));
+    if (n > 0) {
+        offsets_to_counts8_kernel<<<grid_for(n, 256, c->num_sms * 16), 256, 0, c->stream>>>(d_off, n, d_counts);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    return SGC_OK;
+}
+
 int sgc_labels_from_ids(sgc_ctx* c, const uint32_t* d_kmer_ids, const int64_t* d_kmer_off, int64_t nseq,
                         int64_t n_kmers, int64_t* d_ids_off, uint32_t* d_ids_out, int64_t ids_cap, int64_t* h_n_hits,
                         int64_t* h_n_labels) {

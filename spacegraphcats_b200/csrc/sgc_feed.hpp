@@ -365,6 +365,33 @@ int sgc_pack_reads(const uint8_t* h_seq, const int64_t* h_off, int64_t nseq, int
     return SGC_OK;
 }
 
+// ---------------------------------------------------------------------------- label offsets on the wire
+// The CSR offsets of a labelled batch travel device -> host as one byte per read (its number of labels; see
+// sgc_offsets_to_counts8) and are rebuilt here: h_off[0] = 0, h_off[s+1] = h_off[s] + h_counts[s].  Two passes over
+// thread-sized ranges (sums, then the offsets).
+int sgc_counts8_to_offsets(const uint8_t* h_counts, int64_t n, int n_threads, int64_t* h_off) {
+    if (n < 0 || !h_off || (n > 0 && !h_counts)) return fail(SGC_ERR_ARG, "bad argument");
+    const int nt = feed::pick_threads(n_threads, std::max<int64_t>(n >> 18, 1));
+    std::vector<int64_t> base((size_t)nt + 1, 0);
+    feed::parallel_for(nt, [&](int t) {
+        const int64_t a = n * t / nt, b = n * (t + 1) / nt;
+        int64_t s = 0;
+        for (int64_t i = a; i < b; ++i) s += h_counts[i];
+        base[(size_t)t + 1] = s;
+    });
+    for (int t = 0; t < nt; ++t) base[(size_t)t + 1] += base[(size_t)t];
+    feed::parallel_for(nt, [&](int t) {
+        const int64_t a = n * t / nt, b = n * (t + 1) / nt;
+        int64_t s = base[(size_t)t];
+        for (int64_t i = a; i < b; ++i) {
+            h_off[i] = s;
+            s += h_counts[i];
+        }
+    });
+    h_off[n] = base[(size_t)nt];
+    return SGC_OK;
+}
+
 // ---------------------------------------------------------------------------- records
 // h_info[0..2] = number of records, total sequence bytes, format (0 FASTA, 1 FASTQ)
 int sgc_reads_count(const uint8_t* h_data, int64_t n, int n_threads, int64_t* h_info) {

@@ -799,6 +799,15 @@ __global__ void packed_uniform_plan_kernel(int uniform_len, int64_t nseq, int k,
     }
 }
 
+// CSR offsets -> one byte per sequence (its count); counts[n] = 1 if some count does not fit (> 255)
+__global__ void offsets_to_counts8_kernel(const int64_t* __restrict__ off, int64_t n, uint8_t* __restrict__ counts) {
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = off[s + 1] - off[s];
+        counts[s] = (uint8_t)c;
+        if (c > 255 || c < 0) counts[n] = 1;
+    }
+}
+
 __global__ void len_to_i64_kernel(const int32_t* __restrict__ len, int uniform_len, int64_t nseq, int64_t* __restrict__ out) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s > nseq) return;
