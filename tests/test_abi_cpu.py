@@ -344,3 +344,19 @@ def test_host_packer_layout_and_bad_base_flags():
     assert L.sgc_packed_bytes(None, 150, 10) == 10 * 40
     lens = np.array([0, 1, 64, 65], np.int32)
     assert L.sgc_packed_bytes(lens.ctypes.data_as(ctypes.c_void_p), -1, 4) == (0 + 1 + 4 + 5) * 4
+
+
+def test_counts8_to_offsets_host():
+    """sgc_counts8_to_offsets (host, threaded): the CSR offsets of a labelled batch rebuilt from one byte per read."""
+    from spacegraphcats_b200._lib import lib
+
+    L = lib()
+    rng = np.random.default_rng(8)
+    for n in (0, 1, 7, 1000, 3_000_001):
+        cnt = rng.integers(0, 256, n + 1).astype(np.uint8)  # (the byte after the last count is the overflow flag)
+        for threads in (1, 5, 0):
+            off = np.full(n + 1, -1, np.int64)
+            rc = L.sgc_counts8_to_offsets(cnt.ctypes.data_as(ctypes.c_void_p), n, threads, off.ctypes.data_as(ctypes.c_void_p))
+            assert rc == 0
+            assert np.array_equal(off, np.concatenate([[0], np.cumsum(cnt[:n].astype(np.int64))]))
+    assert L.sgc_counts8_to_offsets(None, 5, 1, None) != 0
