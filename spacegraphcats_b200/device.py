@@ -574,6 +574,11 @@ class DeviceTable:
             self._stream_state = ([_StreamSlot(), _StreamSlot()], torch.cuda.Stream(device=c.device),
                                   torch.cuda.Stream(device=c.device))
         slots, copy_stream, back_stream = self._stream_state
+        import os as _os
+
+        if _os.environ.get("SGC_STREAM_SERIAL"):  # experiment knob: uploads and downloads on ONE copy stream
+            back_stream = copy_stream
+        no_d2h = bool(_os.environ.get("SGC_STREAM_NO_D2H"))  # experiment knob: results stay on the device (timing only)
         for s in slots:
             s.copied, s.returned = torch.cuda.Event(), torch.cuda.Event()
             s.returned.record(back_stream)
@@ -646,7 +651,7 @@ class DeviceTable:
             with torch.cuda.stream(back_stream):
                 back_stream.wait_event(done)
                 h_cnt8[: n + 1].copy_(d_cnt8[: n + 1], non_blocking=True)
-                if nl:
+                if nl and not no_d2h:
                     h_ids[:nl].copy_(slot.d_in["ids"][:nl], non_blocking=True)
                 if h_stat is not None and n:
                     h_stat[:n].copy_(slot.d_in["status"][:n], non_blocking=True)
