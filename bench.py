@@ -641,6 +641,7 @@ def main():
     table._dev = dev_table  # the product object whose streaming API the e2e arm calls
     live, multi, max_id = dev_table.stats()
     TABLE_BYTES.append(dev_table.nbytes + dev_table.side_nbytes)
+    HAS_STORE[0] = dev_table.side_nbytes > 0 and not os.environ.get("SGC_NO_SIDE")
     log("[rank %d] cDBG: %d unitigs, table %d live hashes (%d multicount) in %.2f GB (+%.2f GB unitig sequence store), built in %.1fs"
         % (rank, cdbg.n_unitigs, live, multi, dev_table.nbytes / 1e9, dev_table.side_nbytes / 1e9, time.time() - t0))
     nb = max(1, min(args.distinct_batches, args.steps + args.warmup))
@@ -868,9 +869,16 @@ def main():
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(gpu_launches),
         "roofline": roofline, "cpu_baseline": cpu, "query": query, "partitioned": partitioned,
     }
+    if not HAS_STORE[0]:  # e.g. more than 2^30 - 2 store positions per table: the per-k-mer kernel ran, say so
+        line["config"]["label_kernel"] = ("per-k-mer probes: this table carries no unitig sequence store (more than 2^30 "
+                                          "positions, SGC_NO_SIDE, or a table filled hash by hash)")
+        line["roofline"]["kernel"] = "tile_kernel<31, MODE_LABEL>"
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+HAS_STORE = [True]
 
 
 def dev_table_bytes(live):
