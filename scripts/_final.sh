@@ -1,3 +1,4 @@
+# GPU-box helper: everything behind profiles/r02_*: GPU tests, default bench, reference arm, ncu launch list, ncu --set full of the label kernel
 set -x
 (time timeout 900 python -m pytest tests -m gpu -x -q) > gpurun_out/f_pytest.log 2>&1; tail -3 gpurun_out/f_pytest.log
 (time timeout 600 python bench.py) > gpurun_out/f_bench.log 2> gpurun_out/f_bench.err; tail -c 600 gpurun_out/f_bench.log

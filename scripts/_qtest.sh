@@ -1,3 +1,4 @@
+# GPU-box helper: GPU parity tests + a short device-resident bench (label and query arms); prints value / step / kernel ms
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
 timeout 300 python bench.py --no-cpu --steps 5 --no-e2e 2>gpurun_out/err.log | python -c "
 import json,sys
