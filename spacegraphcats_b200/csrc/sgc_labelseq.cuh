@@ -38,7 +38,12 @@ namespace sgc {
 namespace dev {
 
 constexpr int SEG_KS = 128;   // k-mers per segment of the labelseq plan
-constexpr int GK = 16;        // k-mers per group: one anchor, fifteen followers
+#ifndef SGC_LS_GK
+#define SGC_LS_GK 16
+#endif
+constexpr int GK = SGC_LS_GK; // k-mers per group: one anchor, GK - 1 followers
+static_assert(GK == 16 || GK == 24 || GK == 32, "group size");
+constexpr unsigned GKMASK = GK >= 32 ? 0xFFFFFFFFu : ((1u << (GK & 31)) - 1u);
 constexpr int PAIRS_S = 64;   // candidate keys staged per warp before one global reservation
 constexpr int FOFF = 4;       // staged forward words start 4 words into their slot
 constexpr int USEQ_PAD = 8;   // words (128 bases) of zero padding on either end of the sequence store
@@ -75,7 +80,7 @@ struct GeoS {
     static constexpr int RAWW = PACKED ? (((SEGB + 15) / 16 + 3 + 3) / 4) * 4 : WPS;
     static constexpr int QCAP = SPW * SEG_KS;                       // a round queues at most its own k-mers
     static_assert(32 % SPW == 0, "lanes per segment");
-    static_assert(SPW <= 4 && SEG_KS <= 128 && GK <= 16, "a queued run is 15 bits: k-mer 7, segment 2, followers 4, back, flagged");
+    static_assert(SPW <= 4 && SEG_KS <= 128 && GK <= 32, "a queued run is 16 bits: k-mer 7, segment 2, followers 5, back, flagged");
 };
 
 struct LabelSeqArgs {
@@ -137,7 +142,7 @@ struct alignas(16) WarpTileS {
     uint32_t P[G::SPW * G::PWS];       // the round's segments, 2 bits per base
     SegDesc D[3][G::SPW];
     unsigned long long pairs[PAIRS_S];
-    unsigned short qr[G::QCAP / 2];    // queued runs of this round: k-mer | segment << 7 | followers << 9 | back << 13 | flagged << 14
+    unsigned short qr[G::QCAP / 2];    // queued runs of this round: k-mer | segment << 7 | followers << 9 | back << 14 | flagged << 15
     unsigned short qs[G::QCAP];        // queued ranges of k-mers to probe one by one: first k-mer | segment << 7 | (count - 1) << 9
     int gpre[G::SPW + 1];
     unsigned segbad;                   // bit sg: segment sg holds a byte that is not A/C/G/T (ASCII input)
@@ -450,16 +455,16 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                 const unsigned u = wt.qr[qr_done + lane - n_a];
                 qa = (int)(u & 127u);
                 sg = (int)((u >> 7) & 3u);
-                n = (int)((u >> 9) & 15u) + 1;
-                back = (u >> 13) & 1u;
-                flagged = (u >> 14) & 1u;
+                n = (int)((u >> 9) & 31u) + 1;
+                back = (u >> 14) & 1u;
+                flagged = (u >> 15) & 1u;
             }
             a_done += n_a;
             qr_done += n_r;
             if (n_run < 32 && nsi > 0) {  // warp-uniform: lanes [n_run, 32) take single k-mers from the next ranges
                 const bool has = lane < nsi;
                 const unsigned u = has ? wt.qs[qs_done + lane] : 0u;
-                const int cnt = has ? (int)((u >> 9) & 15u) + 1 : 0;
+                const int cnt = has ? (int)((u >> 9) & 31u) + 1 : 0;
                 int incl = cnt;
 #pragma unroll
                 for (int dd = 1; dd < 32; dd <<= 1) {
@@ -546,7 +551,7 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                 if (is_run) {
                     lo = back ? qa - (n - 1) : qa;
                     const int ao = back ? n - 1 : 0;            // the anchor's place in the window of k-mers lo .. lo+n-1
-                    const unsigned valid = (1u << n) - 1u;
+                    const unsigned valid = n >= 32 ? 0xFFFFFFFFu : (1u << n) - 1u;
                     const uint32_t gp = aux & AUX_MASK;
                     const bool has_g = v != SGC_MISS && gp != AUX_NONE && !((wt.segbad >> sg) & 1u);
                     if (has_g) {
@@ -559,14 +564,15 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                             useq += shard * a.ustride;
                             brkp += shard * a.bstride;
                         }
-                        // break bits of positions gp-15 .. gp+16
-                        const uint32_t bi = gp + (uint32_t)(BRK_PAD - (GK - 1));
+                        // break bits of positions gp-31 .. gp (low word, bit 31 = gp) and gp+1 .. gp+32 (high word)
+                        const uint32_t bi = gp + (uint32_t)(BRK_PAD - 31);
                         const uint32_t w0 = __ldg(brkp + (bi >> 5)), w1 = __ldg(brkp + (bi >> 5) + 1);
+                        const uint32_t w2 = __ldg(brkp + (bi >> 5) + 2);
                         unsigned clean;  // bit i: the k bases of k-mer lo+i equal the store's
                         if constexpr (K != 0) {
                             constexpr int WL = GK - 1 + (K ? K : 1);   // bases of a full window
                             constexpr int NWD = (WL + 15) / 16;
-                            static_assert(NWD <= 3 || K == 0, "window words");
+                            static_assert(NWD <= 4 || K == 0, "window words");
                             // read k-mer lo+i lies at store position gp + (i - ao) (along) or gp - (i - ao): the window's
                             // base j is store base wsi + j, resp. the complement of store base wsi + WL - 1 - j
                             const int wsi = along ? (int)gp - ao : (int)gp + ao - (GK - 1);
@@ -611,8 +617,8 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                                 }
                             }
                             // k-mer i is clean when its k bases avoid every mismatch: i + K - 1 < f, or i > l
-                            const unsigned clean_a = f >= K ? (f - K + 1 >= GK ? 0xFFFFu : (1u << (f - K + 1)) - 1u) : 0u;
-                            const unsigned clean_b = l < 0 ? 0xFFFFu : (l >= GK - 1 ? 0u : (0xFFFFu << (l + 1)) & 0xFFFFu);
+                            const unsigned clean_a = f >= K ? (f - K + 1 >= GK ? GKMASK : (1u << (f - K + 1)) - 1u) : 0u;
+                            const unsigned clean_b = l < 0 ? GKMASK : (l >= GK - 1 ? 0u : (GKMASK << (l + 1)) & GKMASK);
                             clean = clean_a | clean_b;
                         } else {
                             // any k: walk the bases away from the anchor until the first mismatch
@@ -633,13 +639,14 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                             }
                             // the anchor and its first c-1 followers are clean; as bits of the window lo .. lo+n-1
                             const int c = f >= k ? (f - k + 1 >= n ? n : f - k + 1) : 0;
-                            const unsigned pre = (1u << c) - 1u;
+                            const unsigned pre = c >= 32 ? 0xFFFFFFFFu : (1u << c) - 1u;
                             clean = back ? pre << (n - c) : pre;
                         }
-                        const uint32_t bits = __funnelshift_r(w0, w1, bi & 31u);  // bit b = position gp-15+b
+                        const uint32_t below = __funnelshift_r(w0, w1, bi & 31u);   // bit b = position gp-31+b
+                        const uint32_t above = __funnelshift_r(w1, w2, bi & 31u);   // bit b = position gp+1+b
                         // the lim followers next to the anchor may inherit its id: no break in (gp, gp+d] resp. (gp-d, gp]
-                        const unsigned lim = along != back ? (unsigned)__ffs((int)((bits >> 16) | 0x8000u)) - 1u
-                                                           : (unsigned)__clz((int)((bits << 16) | 0x10000u));
+                        const unsigned lim = along != back ? (unsigned)__ffs((int)(above | 0x80000000u)) - 1u
+                                                           : (unsigned)__clz((int)(below | 1u));
                         const unsigned inh = back ? ((int)lim >= n - 1 ? valid : valid & ~((1u << (n - 1 - (int)lim)) - 1u))
                                                   : ((2u << lim) - 1u) & valid;
                         const unsigned settled = ((clean & inh) | (1u << ao)) & valid;
@@ -652,7 +659,7 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                         if (valid & ~inh) {  // the k-mers past the break: a run of their own, anchored next to the break
                             const int n2 = n - 1 - (int)lim;
                             const int qa2 = back ? qa - ((int)lim + 1) : qa + (int)lim + 1;
-                            run_item = 0x8000u | (flagged ? 1u << 14 : 0u) | (back ? 1u << 13 : 0u) | ((unsigned)(n2 - 1) << 9) |
+                            run_item = 0x10000u | (flagged ? 1u << 15 : 0u) | (back ? 1u << 14 : 0u) | ((unsigned)(n2 - 1) << 9) |
                                        ((unsigned)sg << 7) | (unsigned)qa2;
                         }
 #else
@@ -664,7 +671,7 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
 #if SGC_LS_REANCHOR
                         if (!flagged && n > 2 && !((wt.segbad >> sg) & 1u) && (v == SGC_MISS)) {
                             const int qa2 = back ? qa - (n - 1) : qa + (n - 1);
-                            run_item = 0x8000u | (1u << 14) | (back ? 0u : 1u << 13) | ((unsigned)(n - 2) << 9) | ((unsigned)sg << 7) |
+                            run_item = 0x10000u | (1u << 15) | (back ? 0u : 1u << 14) | ((unsigned)(n - 2) << 9) | ((unsigned)sg << 7) |
                                        (unsigned)qa2;
                         } else
 #endif
@@ -674,13 +681,13 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                 // queue what the store did not settle: one range and one run per lane at most
                 const unsigned ms = __ballot_sync(0xffffffffu, singles != 0u);
                 const unsigned mr = __ballot_sync(0xffffffffu, run_item != 0u);
-                const unsigned below = (1u << lane) - 1u;
+                const unsigned lower = (1u << lane) - 1u;
                 if (singles) {
                     const int first = lo + __ffs((int)singles) - 1;
-                    wt.qs[qs_fill + __popc(ms & below)] =
+                    wt.qs[qs_fill + __popc(ms & lower)] =
                         (unsigned short)((unsigned)first | ((unsigned)sg << 7) | ((unsigned)(__popc(singles) - 1) << 9));
                 }
-                if (run_item) wt.qr[qr_fill + __popc(mr & below)] = (unsigned short)(run_item & 0x7FFFu);
+                if (run_item) wt.qr[qr_fill + __popc(mr & lower)] = (unsigned short)(run_item & 0xFFFFu);
                 qs_fill += __popc(ms);
                 qr_fill += __popc(mr);
             }
@@ -741,12 +748,13 @@ __global__ void __launch_bounds__(NTS, SGC_LS_MIN_CTAS) labelseq_kernel(const La
                 if (total) {
                     auto record = [&](unsigned m, unsigned long long& rk, unsigned long long& rv) -> unsigned {
                         const int i0 = __ffs((int)m) - 1;
-                        const int len = __ffs((int)~(m >> i0)) - 1;   // set bits from i0 upwards
+                        const unsigned rest = ~(m >> i0);
+                        const int len = rest ? __ffs((int)rest) - 1 : 32 - i0;   // set bits from i0 upwards
                         const int i1 = i0 + len - 1;
                         const int first = q_along ? (int)gp + (i0 - q_ao) : (int)gp - (i1 - q_ao);
                         rk = ((unsigned long long)qid << a.iv_pbits) | (unsigned)first;
                         rv = ((unsigned long long)len << 32) | v;
-                        return m & ~(((1u << len) - 1u) << i0);
+                        return len >= 32 ? 0u : m & ~(((1u << len) - 1u) << i0);
                     };
                     if (iv_pos + (unsigned)total > iv_end) {
                         unsigned long long fk = 0, fv = 0;
