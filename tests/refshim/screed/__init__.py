@@ -5,12 +5,25 @@ import gzip
 from .screedRecord import Record
 
 
+class _Records(list):
+    """what screed.open returns: iterable, and a context manager (search/query_by_sequence.py:170)"""
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def close(self):
+        pass
+
+
 def open(filename):  # noqa: A001
     with builtins.open(filename, "rb") as fp:
         raw = fp.read()
     if raw[:2] == b"\x1f\x8b":
         raw = gzip.decompress(raw)
-    return list(_parse(raw.decode("ascii")))
+    return _Records(_parse(raw.decode("ascii")))
 
 
 def _parse(text):

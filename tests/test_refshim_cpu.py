@@ -1,6 +1,7 @@
-"""The reference's OWN Python (spacegraphcats/cdbg/{hashing,index_cdbg_by_kmer,index_reads}.py, imported UNMODIFIED
-from /root/reference) running on the test shims of its two third-party natives -- ``khmer`` and ``bbhash_table``
-(tests/refshim/) -- backed here by the CPU oracle.  This pins, in a container without a GPU, that
+"""The reference's OWN Python (spacegraphcats/cdbg/{hashing,index_cdbg_by_kmer,index_reads}.py and
+search/{query_by_sequence,catlas,search_utils}.py, imported UNMODIFIED from /root/reference) running on the test
+shims of its third-party natives -- ``khmer``, ``bbhash_table``, ``screed``, ``sourmash`` (tests/refshim/) -- backed
+here by the CPU oracle.  This pins, in a container without a GPU, that
 
   * the shim surface is exactly what the reference calls (the same shim modules, switched to the raw ctypes
     binding of libsgc_b200.so, are exercised on the GPU by tests/test_gpu_parity.py::test_reference_side_binding_*),
@@ -114,3 +115,62 @@ def test_reference_index_reads_main_on_dory(ref, dory_records, tmp_path):
     offs = src.virtual_offsets(pos).tolist()
     want, _, total = O.label_reads(zip(reads, offs), O.OracleTable.from_arrays(z["mphf_to_hash"], z["mphf_to_value"]), 21)
     assert rows == sorted(want) and len(total) == 736
+
+
+def test_reference_query_on_dory_head(ref, dory_records, tmp_path):
+    """The reference's own ``Query`` / ``QueryOutput`` (search/query_by_sequence.py:27-267) and ``CAtlas``
+    (search/catlas.py) on the shims: dory-head against the dory cDBG reproduces tests/test_dory_workflow.py:217-228
+    and the reference's result files -- match counts {118: 834, 187: 797}, frontier {97, 150}, the results.csv row
+    (containment, similarity, bp, contigs, k, query k-mers, upper bounds), cdbg ids, response curve -- and equals
+    the oracle's restatement of Query.execute."""
+    import csv
+    import gzip
+    import io
+
+    from oracle import oracle as O
+
+    import spacegraphcats.search.query_by_sequence as qbs
+    from spacegraphcats.search.catlas import CAtlas
+
+    assert qbs.__file__.startswith(REF)
+    table, sizes = ref.index_cdbg_by_kmer.build_mphf(21, lambda: iter(dory_records))
+    kmer_idx = ref.hashing.MPHF_KmerIndex(21, table, sizes)
+    catlas = CAtlas(str(tmp_path), os.path.dirname(golden_path("dory_k21_r1", "catlas.csv")), load_sizefile=None)
+    catlas.decorate_with_index_sizes(kmer_idx)
+    qfile = golden_path("data", "dory-head.fa")
+    q = qbs.Query(qfile, 21, 1000, "dory_k21_r1")
+    out = q.execute(catlas, kmer_idx)
+    assert len(q.kmers) == 1631
+    assert q.cdbg_match_counts == {118: 834, 187: 797}
+    assert out.doms == {97, 150} and out.shadow == {118, 187}
+    # the oracle's restatement of the same steps
+    ocat = O.OracleCAtlas(golden_path("dory_k21_r1", "catlas.csv"), golden_path("dory_k21_r1", "first_doms.txt"))
+    z = np.load(golden_path("dory_k21_contigs.indices.npz"))
+    ocdbg, ocat_counts, odoms, oshadow = O.query_execute(O.query_kmers(O.read_records(qfile), 21),
+                                                         O.OracleTable.from_arrays(z["mphf_to_hash"], z["mphf_to_value"]),
+                                                         sizes, ocat)
+    assert (q.cdbg_match_counts, q.catlas_match_counts, out.doms, out.shadow) == (ocdbg, ocat_counts, odoms, oshadow)
+    # QueryOutput: contigs from a sqlite store like sort_bcalm_unitigs writes, then the result files
+    db = sqlite3.connect(str(tmp_path / "bcalm.unitigs.db"))
+    db.execute("CREATE TABLE sequences (id INTEGER, sequence TEXT, offset INTEGER PRIMARY KEY, min_hashval TEXT, abund FLOAT)")
+    db.executemany("INSERT INTO sequences (id, sequence, offset) VALUES (?, ?, ?)",
+                   [(int(r.name), r.sequence, i) for i, r in enumerate(dory_records)])
+    db.commit()
+    out.retrieve_contigs(db)
+    buf = io.StringIO()
+    outdir = tmp_path / "search"
+    outdir.mkdir()
+    out.write(csv.writer(buf), buf, str(outdir), "dory_k21_r1")
+    got_row = buf.getvalue().strip().split(",")
+    with open(golden_path("dory_k21_r1_search", "results.csv")) as fp:
+        want_row = [ln.strip().split(",") for ln in fp][1]
+    assert got_row[1:] == want_row[1:]  # (column 0 is the query's path on the reference authors' machine)
+    with gzip.open(golden_path("dory_k21_r1_search", "dory-head.fa.cdbg_ids.txt.gz"), "rt") as a, \
+            gzip.open(str(outdir / "dory-head.fa.cdbg_ids.txt.gz"), "rt") as b:
+        assert a.read() == b.read()
+    with gzip.open(golden_path("dory_k21_r1_search", "dory-head.fa.frontier.txt.gz"), "rt") as a, \
+            gzip.open(str(outdir / "dory-head.fa.frontier.txt.gz"), "rt") as b:
+        assert sorted(a.read().split()) == sorted(b.read().split())
+    with open(golden_path("dory_k21_r1_search", "dory-head.fa.response.txt")) as a, \
+            open(str(outdir / "dory-head.fa.response.txt")) as b:
+        assert a.read() == b.read()
