@@ -84,7 +84,7 @@ def main():
     # sequence data
     for f in ("dory-head.fa", "random-query-nomatch.fa", "dory-k21-hashval-queries.txt", "dory-k31-hashval-queries.txt"):
         shutil.copyfile(ref("data", f), out("data", f))
-    for f in ("dory-subset.fq", "dory-subset.fa", "shew-os223-200k.fa"):
+    for f in ("dory-subset.fq", "dory-subset.fa", "shew-os223-200k.fa", "bcalm.dory.k21.unitigs.fa"):
         gz_copy(ref("data", f), out("data", f + ".gz"))
     for f in ("twofoo-genes.fa.gz",) + tuple("acido-chunk%d.fa.gz" % i for i in range(1, 9)):
         shutil.copyfile(ref("data", f), out("data", f))

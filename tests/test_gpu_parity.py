@@ -1086,6 +1086,21 @@ def test_unitig_ids_follow_the_reference_remapping(ctx, dory):
         assign_unitig_ids([recs[0].sequence, recs[0].sequence], 21)
 
 
+def test_unitig_ids_from_raw_bcalm_output(ctx, O, dory):
+    """f4 from BCALM's own file (data/bcalm.dory.k21.unitigs.fa: arbitrary order, BCALM's numbering, either strand):
+    assign_unitig_ids gives every unitig the id it has in the reference's dory cDBG (the reference's own
+    sort_bcalm_unitigs.main does the same on the CPU shims: tests/test_refshim_cpu.py)."""
+    from spacegraphcats_b200.cdbg.minhash import assign_unitig_ids
+
+    recs = O.read_records(golden_path("data", "bcalm.dory.k21.unitigs.fa.gz"))
+    assert len(recs) == 736
+    canon = lambda s: min(s, O.revcomp(s.encode()).decode())  # noqa: E731
+    want = {canon(r.sequence): int(r.name) for r in dory[0]}
+    new_id, _ = assign_unitig_ids([r.sequence for r in recs], 21)
+    assert new_id.tolist() == [want[canon(r.sequence)] for r in recs]
+    assert new_id.tolist() != [int(r.name.split()[0]) for r in recs]  # BCALM's own numbering is another one
+
+
 @pytest.mark.parametrize("k", [21, 31, 12, 33])
 def test_sourmash_hashes_vs_oracle(ctx, O, k):
     from spacegraphcats_b200.cdbg.minhash import scaled_minhash, sourmash_hashes, unitig_min_hashvals

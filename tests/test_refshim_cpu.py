@@ -174,3 +174,33 @@ def test_reference_query_on_dory_head(ref, dory_records, tmp_path):
     with open(golden_path("dory_k21_r1_search", "dory-head.fa.response.txt")) as a, \
             open(str(outdir / "dory-head.fa.response.txt")) as b:
         assert a.read() == b.read()
+
+
+def test_reference_sort_bcalm_unitigs_on_dory(ref, dory_records, tmp_path):
+    """The reference's own ``sort_bcalm_unitigs.main`` (cdbg/sort_bcalm_unitigs.py:19-196) on raw BCALM output
+    (data/bcalm.dory.k21.unitigs.fa) with the sourmash shim: the ids it assigns (rank in the TEXT order of
+    min_hashval, :101-118) and the min_hashvals are those of the reference's dory fixture -- which pins the shim's
+    hash (Murmur3 seed 42 of the canonical k-mer) and the id rule spacegraphcats_b200.cdbg.minhash.assign_unitig_ids
+    follows, starting from BCALM's own file."""
+    import json
+    import shutil
+
+    from oracle import oracle as O
+
+    import spacegraphcats.cdbg.sort_bcalm_unitigs as sbu
+
+    assert sbu.__file__.startswith(REF)
+    fa = str(tmp_path / "bcalm.dory.k21.unitigs.fa")  # (main writes a .sig next to its input)
+    shutil.copy(os.path.join(REF, "data", "bcalm.dory.k21.unitigs.fa"), fa)
+    db_out, pkl = str(tmp_path / "bcalm.unitigs.db"), str(tmp_path / "bcalm.unitigs.pickle")
+    assert sbu.main([fa, db_out, pkl, "-k", "21"]) == 0
+    rows = sqlite3.connect(db_out).execute("SELECT id, sequence, min_hashval FROM sequences ORDER BY id").fetchall()
+    assert len(rows) == len(dory_records) == 736
+    with open(golden_path("dory_k21_min_hashval.json")) as fp:
+        want_min = {int(a): b for a, b in json.load(fp).items()}
+    canon = lambda s: min(s, O.revcomp(s.encode()).decode())  # noqa: E731  (BCALM may write a unitig on either strand)
+    by_id = {int(r.name): r.sequence for r in dory_records}
+    for cdbg_id, seq, mh in rows:
+        assert int(mh) == want_min[cdbg_id]
+        assert canon(seq) == canon(by_id[cdbg_id])
+    assert [r[0] for r in sorted(rows, key=lambda r: r[2])] == list(range(736))  # TEXT order of min_hashval = id order
