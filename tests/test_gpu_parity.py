@@ -557,6 +557,20 @@ def test_dominator_abundance_totals(O, dory, dory_index, dory_catlas):
     assert {d: got_dom[d] for d in want_dom} == want_dom
     assert got_dom[dory_catlas.root] == 240920
     assert sum(want_dom.values()) == 240920 and sum(ref_sizes.values()) == 212475
+    # ... and, row for row, the two CSV files the reference's OWN count_dominator_abundance.main wrote for this sample
+    # (run on the CPU shims by tests/golden/make_ref_outputs.py, committed as dory_subset_abund.json)
+    with open(golden_path("dory_subset_abund.json")) as fp:
+        ref_out = json.load(fp)
+    assert [[i, int(c), ref_sizes[i]] for i, c in enumerate(res["count_by_id"].tolist())] == ref_out["cdbg"]
+    dory_catlas.decorate_with_index_sizes(dory_index)
+    sizes = dory_catlas.index_sizes
+    got_rows = [[n, dory_catlas.levels[n], got_dom[n], sizes[n]] for n in sorted(dory_catlas)]
+    # count_dominator_abundance.py:138-157: whole components hang directly under the root; their rows are repeated for
+    # the levels they skip
+    max_level = max(dory_catlas.levels.values())
+    for n in set(dory_catlas.children[dory_catlas.root]):
+        got_rows += [[n, level, got_dom[n], sizes[n]] for level in range(dory_catlas.levels[n] + 1, max_level)]
+    assert sorted(got_rows) == sorted(ref_out["dom"])
 
 
 # ---------------------------------------------------------------- index_reads main

@@ -204,3 +204,24 @@ def test_reference_sort_bcalm_unitigs_on_dory(ref, dory_records, tmp_path):
         assert int(mh) == want_min[cdbg_id]
         assert canon(seq) == canon(by_id[cdbg_id])
     assert [r[0] for r in sorted(rows, key=lambda r: r[2])] == list(range(736))  # TEXT order of min_hashval = id order
+
+
+def test_reference_count_dominator_abundance_on_dory(ref, tmp_path):
+    """The reference's own ``count_dominator_abundance.main`` (search/count_dominator_abundance.py:24-170) on the shims,
+    over dory-subset.fa: the pins of tests/test_dory_workflow.py:849-870 (737 + 2836 CSV lines, totals 240920 / 212475,
+    the top dominator row) and, row for row, the committed golden vectors the GPU test compares with
+    (tests/golden/dory_subset_abund.json, written by tests/golden/make_ref_outputs.py from this very run)."""
+    import json
+
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    try:
+        import make_ref_outputs
+    finally:
+        sys.path.pop(0)
+    res = make_ref_outputs.run_abundance(str(tmp_path))
+    assert len(res["cdbg"]) + 1 == 737 and len(res["dom"]) + 1 == 2836
+    assert sum(r[1] for r in res["cdbg"]) == 240920 and sum(r[2] for r in res["cdbg"]) == 212475
+    top = [r for r in res["dom"] if r[1] == 7]
+    assert top and all(r[2] == 240920 and r[3] == 212475 for r in top)
+    with open(golden_path("dory_subset_abund.json")) as fp:
+        assert json.load(fp) == res
