@@ -225,3 +225,52 @@ def test_reference_count_dominator_abundance_on_dory(ref, tmp_path):
     assert top and all(r[2] == 240920 and r[3] == 212475 for r in top)
     with open(golden_path("dory_subset_abund.json")) as fp:
         assert json.load(fp) == res
+
+
+@pytest.mark.parametrize("flags", [[], ["-N"], ["-P"]])
+def test_reference_index_reads_pairing_vs_oracle_loop(ref, tmp_path, flags):
+    """The reference's own index_reads.main on mate pairs (its pairing fixture tests/test-data/twofoo-short-paired-test
+    plus corner cases: /1,/2 names, equal names, a short read between mates, a short mate, names of length 2, a read
+    that hits nothing) in its three modes: the rows equal the oracle's restatement of the loop (oracle.label_reads,
+    which the GPU tests compare the CUDA path with), so that restatement is pinned on the reference's code itself."""
+    from oracle import oracle as O
+    from spacegraphcats_b200.utils import bgzf
+
+    k = 31
+    fixture = O.read_records(golden_path("data", "twofoo-short-paired-test.fa.gz"))
+    rng = np.random.default_rng(4)
+    genome = "".join(rng.choice(list("ACGT"), 6000))
+    extra = [
+        O.Record("p1/1", genome[0:150]), O.Record("p1/2", genome[300:450]),
+        O.Record("p2/1", genome[600:750]), O.Record("p3/2", genome[900:1050]),
+        O.Record("same", genome[1200:1350]), O.Record("same", genome[1500:1650]),
+        O.Record("q/1", genome[2000:2150]), O.Record("short", "ACGT"), O.Record("q/2", genome[2300:2450]),
+        O.Record("r/1", genome[2600:2750]), O.Record("r/2", "ACGTACGT"),
+        O.Record("/1", genome[3000:3150]), O.Record("/2", genome[3300:3450]),
+        O.Record("nohit", "".join(rng.choice(list("ACGT"), 150))),
+    ]
+    reads = list(fixture) + extra
+    pieces = []
+    for r in list(fixture) + [O.Record("g", genome)]:
+        for a in range(0, max(len(r.sequence) - k + 1, 0), 100):
+            pieces.append(r.sequence[a : a + 100 + k - 1])
+    urecs = [O.Record(str(i), s) for i, s in enumerate(pieces)]
+    table, sizes = ref.index_cdbg_by_kmer.build_mphf(k, lambda: iter(urecs))
+    d = tmp_path / "cdbg"
+    d.mkdir()
+    ref.hashing.MPHF_KmerIndex(k, table, sizes).save(str(d))
+    rp = str(tmp_path / "reads.bgz")
+    write_bgzf(rp, "".join(">%s\n%s\n" % (r.name, r.sequence) for r in reads).encode(), block_size=700)
+    db = str(tmp_path / "out.index")
+    rc = ref.index_reads.main([str(d), rp, db, "-k", str(k)] + flags)
+    rows = sorted(sqlite3.connect(db).execute("SELECT offset, cdbg_id FROM sequences").fetchall())
+    src = bgzf.open_reads(rp)
+    names, _, _, pos = bgzf.parse_records(src.data)
+    assert names == [r.name for r in reads]
+    offs = src.virtual_offsets(pos).tolist()
+    otab, _, _ = O.build_mphf(k, lambda: iter(urecs))
+    want, n_paired, total = O.label_reads(zip(reads, offs), otab, k, ignore_paired="-N" in flags)
+    assert rows == sorted(want)
+    assert (n_paired > 0) == ("-N" not in flags)
+    ids_complete = max(total) + 1 == len(total)
+    assert rc == (0 if ids_complete and not ("-P" in flags and not n_paired) else -1)
