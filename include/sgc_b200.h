@@ -150,7 +150,11 @@ int sgc_count_matches(sgc_table* t, const uint64_t* d_hash, int64_t n, int disti
  * all sequences of a query are consecutive).  Results: d_q_distinct[n_queries] = len(query.kmers);
  * (d_keys_out, d_counts_out)[0 .. *h_n_pairs) = ((query << 32) | unitig id, number of the query's DISTINCT
  * k-mers on that unitig), ascending by key -- query q's dict is its run of keys.  cap = capacity of the two
- * output arrays (SGC_ERR_CAPACITY with *h_n_pairs = needed).  Synchronises.
+ * output arrays (SGC_ERR_CAPACITY with *h_n_pairs = needed).  *h_n_hits = distinct matching k-mers over all queries.
+ * Synchronises.  Two forms, same results: a table that carries the unitig sequence store runs the label kernel in
+ * query mode -- per settled run the interval of store positions, per missing k-mer its hash; distinct matches = size of
+ * the union of a query's intervals per unitig (no k-mer hash is written to memory) --, any other table (or
+ * SGC_QUERY_SORT=1) hashes every k-mer, sorts (hash, query) and looks the first occurrences up.
  */
 int sgc_query_count_batch(sgc_table* t, const uint8_t* d_seq, int64_t seq_bytes, const int64_t* d_off,
                           int64_t nseq, const int32_t* d_seq_query, int n_queries, int k,
