@@ -5,7 +5,7 @@ all-to-all, each rank labels its own reads through request/reply all-to-alls.  R
 labels against a replicated table built on the same GPU (when --check) and prints k-mers/s."""
 import argparse, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch, torch.distributed as dist
+import torch, torch.distributed as dist
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--table-kmers", type=float, default=4e8)

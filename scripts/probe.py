@@ -1,7 +1,7 @@
 """First-contact GPU probe: stage-by-stage throughput on a reduced synthetic workload."""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 import __graft_entry__ as g
 g.build()
 from spacegraphcats_b200.device import get_context

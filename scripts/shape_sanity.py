@@ -1,7 +1,7 @@
 """Timing sanity on awkward input shapes (one huge sequence, millions of tiny ones, unitig-like ragged)."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 import __graft_entry__ as g
 g.build()
 from spacegraphcats_b200.device import get_context

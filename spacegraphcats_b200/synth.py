@@ -77,8 +77,6 @@ class SyntheticCdbg:
         self.total_unitig_kmers = self.n_kmers + self.dup_kmers
 
     def build_table(self, side=None):
-        import os
-
         from .device import DeviceTable
 
         if side is None:

@@ -4,7 +4,6 @@ CPU-only.  Everything the GPU parity tests trust is first proven here.
 """
 import gzip
 import json
-import os
 
 import numpy as np
 import pytest
