@@ -90,7 +90,9 @@ class Model:
         return ids, hits
 
     # ---- the kernel's algorithm
-    def label(self, read, stats):
+    def label(self, read, stats, intervals=None, misses=None):
+        """intervals / misses (lists, optional): what the kernel's QUERY mode writes -- per settled run of window indices
+        the (first store position, length, id) interval, per k-mer the table does not hold its hash"""
         k, S = self.k, self.store
         comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
         nk = len(read) - k + 1
@@ -105,8 +107,13 @@ class Model:
             v, gp, ori, read_ori = self.probe(read[qa : qa + k])
             if v is not None:
                 ids.add(v)
+            elif misses is not None:
+                hf, hr = self.hashes(read[qa : qa + k])
+                misses.append(hf ^ hr)
             if n == 1:
                 hits += v is not None
+                if v is not None and intervals is not None:
+                    intervals.append((gp, 1, v))
                 continue
             if v is None:
                 if not flagged and n > 2:
@@ -138,6 +145,15 @@ class Model:
             inh = {i for i in range(n) if (i >= n - 1 - lim if back else i <= lim)}
             settled = (clean & inh) | {ao}
             hits += len(settled)
+            if intervals is not None:  # one interval per run of consecutive settled window indices
+                idx = sorted(settled)
+                start = prev = idx[0]
+                for i in idx[1:] + [None]:
+                    if i is None or i != prev + 1:
+                        first = gp + (start - ao) if along else gp - (prev - ao)
+                        intervals.append((first, prev - start + 1, v))
+                        start = i
+                    prev = i
             stats["settled"] += len(settled) - 1
             singles = sorted(inh - settled)
             assert not singles or singles == list(range(singles[0], singles[-1] + 1)), "one contiguous range"
@@ -195,3 +211,60 @@ def test_label_model_equals_per_kmer_probing(k, glen, alphabet):
     assert stats["probes"] <= total
     if alphabet == "ACGT" and k >= 21:
         assert stats["probes"] < 0.5 * total and stats["settled"] > 0.4 * total
+
+
+@pytest.mark.parametrize("k,glen,alphabet", [(21, 6000, "ACGT"), (11, 5000, "ACGT"), (9, 4000, "AC")])
+def test_query_model_union_of_intervals_equals_the_set_of_hashes(k, glen, alphabet):
+    """sgc_query_count_batch through the sequence store: a query's records are run through the same algorithm, every
+    settled run contributes the interval of store positions it lies at, and the number of DISTINCT matching hashes on
+    a unitig is the size of the union of the query's intervals with that id; the distinct missing hashes are counted
+    separately.  Equals Query's set semantics (search/query_by_sequence.py:170-189) -- also when k-mers repeat inside
+    the query, across its records, on both strands, and inside the cDBG (later occurrences of a hash are fenced off by
+    break bits, so only the position the table keeps for a hash is ever reported)."""
+    O = _murmur()
+    rng = np.random.default_rng(k * 11 + glen)
+    g, useqs = _cdbg(rng, k, glen, alphabet)
+    rc = lambda s: O.revcomp(s.encode()).decode()  # noqa: E731
+    useqs = [rc(u) if rng.random() < 0.5 else u for u in useqs]
+    ids = list(range(len(useqs)))
+    useqs += [useqs[3], rc(useqs[10]), useqs[20]]
+    ids += [len(ids), len(ids) + 1, 20]
+    order = rng.permutation(len(useqs))
+    useqs, ids = [useqs[i] for i in order], [ids[i] for i in order]
+    m = Model(O, useqs, ids, k)
+    for q in range(12):
+        records = []
+        for _ in range(int(rng.integers(1, 5))):
+            n = int(rng.integers(k, 900))
+            a = int(rng.integers(0, glen - n))
+            s = list(g[a : a + n])
+            for p in np.flatnonzero(rng.random(n) < 0.01):
+                s[p] = alphabet[(alphabet.index(s[p]) + 1) % len(alphabet)]
+            s = "".join(s)
+            records.append(rc(s) if rng.random() < 0.5 else s)
+        records.append(records[0])            # the same record twice
+        records.append(rc(records[-2]))       # ... and a reverse complement: the same hashes again
+        # the reference: one set of hashes per query, counted per unitig
+        hashes = set()
+        for s in records:
+            for i in range(len(s) - k + 1):
+                hf, hr = m.hashes(s[i : i + k])
+                hashes.add(hf ^ hr)
+        want = {}
+        for h in hashes:
+            e = m.slot.get(h)
+            if e is not None and e[0] != MULTI:
+                want[e[0]] = want.get(e[0], 0) + 1
+        # the kernel's way
+        intervals, misses = [], []
+        for s in records:
+            m.label(s, {"probes": 0, "settled": 0}, intervals, misses)
+        covered = {}
+        for first, length, v in intervals:
+            covered.setdefault(v, set()).update(range(first, first + length))
+        got = {v: len(p) for v, p in covered.items()}
+        assert got == want, q
+        assert sum(got.values()) + len(set(misses)) == len(hashes)
+        # positions of different ids never coincide (an interval never spans two unitigs)
+        allpos = [p for ps in covered.values() for p in ps]
+        assert len(allpos) == len(set(allpos))
